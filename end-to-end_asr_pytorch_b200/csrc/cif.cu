@@ -1,0 +1,505 @@
+// cif.cu - continuous integrate-and-fire, forward + analytic backward (sm_100a).
+//
+// Replaces CIF_Model.cif (/root/reference/src/transformer/cif_model.py:57-106).
+//
+// Forward: ONE WARP per (utterance, hidden slice).  The scalar recurrence
+// (integrate / fire / cur / rem) is evaluated redundantly by every lane in the
+// reference's exact fp32 operation order (no FMA contraction, no reassociation),
+// so fire positions are bit-identical; the [T, slice] stream of encoder frames is
+// the only real traffic.  Two variants, same arithmetic:
+//   * tma   : 2-D TMA tiles [32 rows x W floats] into a multi-stage shared-memory
+//             ring with mbarrier completion (needs H % 4 == 0);
+//   * plain : vectorised global loads with an 8-row register prefetch (any H).
+// Backward: the carried frame gradient is constant inside a fire segment, so
+// every frame row is independent given the saved schedule: one warp per row
+// streams hidden/g_out and writes g_hidden plus two dot products; a tiny second
+// kernel turns the dot products into g_alpha with a reverse (suffix) scan.
+#include "common.cuh"
+
+namespace asr {
+
+// ---- vector helpers -----------------------------------------------------------
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<1> {
+    using type = float;
+};
+template <>
+struct VecT<2> {
+    using type = float2;
+};
+template <>
+struct VecT<4> {
+    using type = float4;
+};
+
+template <int VEC>
+__device__ __forceinline__ void vload(float (&d)[VEC], const float* p) {
+    if constexpr (VEC == 4) {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        float2 v = *reinterpret_cast<const float2*>(p);
+        d[0] = v.x; d[1] = v.y;
+    } else {
+        d[0] = *p;
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void vload_nc(float (&d)[VEC], const float* p) {
+    if constexpr (VEC == 4) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    } else if constexpr (VEC == 2) {
+        float2 v = __ldg(reinterpret_cast<const float2*>(p));
+        d[0] = v.x; d[1] = v.y;
+    } else {
+        d[0] = __ldg(p);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void vstore(float* p, const float (&s)[VEC]) {
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4*>(p) = make_float4(s[0], s[1], s[2], s[3]);
+    } else if constexpr (VEC == 2) {
+        *reinterpret_cast<float2*>(p) = make_float2(s[0], s[1]);
+    } else {
+        *p = s[0];
+    }
+}
+
+// One step of the scalar recurrence, cif_model.py:69-81, in the reference's
+// operation order.  __f*_rn intrinsics are never contracted into FMAs.
+__device__ __forceinline__ void cif_chain_step(float a, float thr, float& integ, bool& fire, float& cur, float& rem) {
+    const float dc = __fsub_rn(1.0f, integ);   // distribution_completion   (:69)
+    const float s = __fadd_rn(integ, a);        // integrate += alpha        (:71)
+    fire = s > thr;                             // fire_place                (:74)
+    integ = fire ? __fsub_rn(s, 1.0f) : s;      //                           (:75-77)
+    cur = fire ? dc : a;                        //                           (:78-80)
+    rem = __fsub_rn(a, cur);                    // remainds                  (:81)
+}
+
+struct CifFwdArgs {
+    const float* hidden;
+    const float* alphas;
+    float thr;
+    int B, T, H, L;
+    float* out;
+    int* fire_t;
+    int* n_fired;
+    float* cur;
+    float* rem;
+    int* sched;
+    float* alpha_sum;
+    const float* target_num;
+    float* qua_term;
+};
+
+// Shared epilogue: zero rows k..L-1 of this warp's slice and publish counters.
+template <int VEC>
+__device__ __forceinline__ void cif_fwd_finish(const CifFwdArgs& a, int b, int slice, int lane, int col, bool col_ok,
+                                               int k, float asum) {
+    float z[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) z[i] = 0.0f;
+    if (col_ok) {
+        for (int kk = k; kk < a.L; ++kk) vstore<VEC>(a.out + ((size_t)b * a.L + kk) * a.H + col, z);
+    }
+    if (slice == 0) {
+        for (int kk = k + lane; kk < a.L; kk += 32) a.fire_t[(size_t)b * a.L + kk] = -1;
+        if (lane == 0) {
+            a.n_fired[b] = k;
+            a.alpha_sum[b] = asum;
+            if (a.target_num != nullptr && a.qua_term != nullptr) {
+                const float d = __fsub_rn(asum, a.target_num[b]);
+                a.qua_term[b] = __fmul_rn(d, d);
+            }
+        }
+    }
+}
+
+// ---- forward, plain loads -----------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, int nslices) {
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (warp >= a.B * nslices) return;
+    const int b = warp / nslices;
+    const int slice = warp - b * nslices;
+    const int col = slice * (32 * VEC) + lane * VEC;
+    const bool col_ok = col < a.H;
+    const bool rec = (slice == 0);
+    const float* hrow = a.hidden + (size_t)b * a.T * a.H + (col_ok ? col : 0);
+    const float* arow = a.alphas + (size_t)b * a.T;
+
+    float frame[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
+    float integ = 0.0f, asum = 0.0f;
+    int k = 0;
+    constexpr int U = 8;
+
+    for (int t0 = 0; t0 < a.T; t0 += 32) {
+        const int tt = t0 + lane;
+        const float my_alpha = (tt < a.T) ? __ldg(arow + tt) : 0.0f;
+        float rc = 0.0f, rr = 0.0f;
+        int rs = 0;
+        const int nrow = min(32, a.T - t0);
+        for (int r0 = 0; r0 < nrow; r0 += U) {
+            float h[U][VEC];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (r0 + u < nrow && col_ok) {
+                    vload_nc<VEC>(h[u], hrow + (size_t)(t0 + r0 + u) * a.H);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) h[u][i] = 0.0f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int r = r0 + u;
+                if (r < nrow) {   // warp-uniform
+                    const float al = __shfl_sync(0xffffffffu, my_alpha, r);
+                    bool fire;
+                    float cur, rem;
+                    cif_chain_step(al, a.thr, integ, fire, cur, rem);
+                    asum = __fadd_rn(asum, al);
+                    if (rec && lane == r) {
+                        rc = cur;
+                        rr = rem;
+                        rs = (k << 1) | (fire ? 1 : 0);
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) frame[i] = __fadd_rn(frame[i], __fmul_rn(cur, h[u][i]));   // :83
+                    if (fire) {
+                        if (k < a.L) {
+                            if (col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, frame);
+                            if (rec && lane == 0) a.fire_t[(size_t)b * a.L + k] = t0 + r;
+                        }
+#pragma unroll
+                        for (int i = 0; i < VEC; ++i) frame[i] = __fmul_rn(rem, h[u][i]);   // :85-87
+                        ++k;
+                    }
+                }
+            }
+        }
+        if (rec && tt < a.T) {
+            a.cur[(size_t)b * a.T + tt] = rc;
+            a.rem[(size_t)b * a.T + tt] = rr;
+            a.sched[(size_t)b * a.T + tt] = rs;
+        }
+    }
+    cif_fwd_finish<VEC>(a, b, slice, lane, col, col_ok, k, asum);
+}
+
+// ---- forward, TMA pipeline ----------------------------------------------------
+// One warp per CTA.  Tile = ROWS x (32*VEC) floats; NSTAGE tiles in flight.
+constexpr int kCifRows = 32;
+constexpr int kCifMaxStages = 12;
+
+template <int VEC>
+__global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__ CUtensorMap tmap, const CifFwdArgs a,
+                                                         int nstage) {
+    constexpr int W = 32 * VEC;
+    constexpr uint32_t kTileBytes = kCifRows * W * sizeof(float);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bars[kCifMaxStages];
+
+    const int lane = threadIdx.x;
+    const int slice = blockIdx.x;
+    const int b = blockIdx.y;
+    const int col = slice * W + lane * VEC;
+    const bool col_ok = col < a.H;
+    const bool rec = (slice == 0);
+    const float* arow = a.alphas + (size_t)b * a.T;
+    const int nchunk = (a.T + kCifRows - 1) / kCifRows;
+    const int row0 = b * a.T;
+
+    if (lane == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < nstage; ++s) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (int s = 0; s < nstage && s < nchunk; ++s) {
+            mbar_arrive_expect_tx(&bars[s], kTileBytes);
+            tma_load_2d(smem_raw + (size_t)s * kTileBytes, &tmap, slice * W, row0 + s * kCifRows, &bars[s]);
+        }
+    }
+
+    float frame[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
+    float integ = 0.0f, asum = 0.0f;
+    int k = 0;
+    int stage = 0;
+    uint32_t phase = 0;
+    float next_alpha = (lane < a.T) ? __ldg(arow + lane) : 0.0f;
+
+    for (int c = 0; c < nchunk; ++c) {
+        const int t0 = c * kCifRows;
+        const int tt = t0 + lane;
+        const float my_alpha = next_alpha;
+        {
+            const int tn = tt + kCifRows;
+            next_alpha = (tn < a.T) ? __ldg(arow + tn) : 0.0f;
+        }
+        const int nrow = min(kCifRows, a.T - t0);
+        float rc = 0.0f, rr = 0.0f;
+        int rs = 0;
+
+        mbar_wait(&bars[stage], phase);
+        const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * kTileBytes) + lane * VEC;
+
+#pragma unroll 8
+        for (int r = 0; r < kCifRows; ++r) {
+            if (r < nrow) {   // warp-uniform
+                float h[VEC];
+                vload<VEC>(h, tile + r * W);
+                const float al = __shfl_sync(0xffffffffu, my_alpha, r);
+                bool fire;
+                float cur, rem;
+                cif_chain_step(al, a.thr, integ, fire, cur, rem);
+                asum = __fadd_rn(asum, al);
+                if (rec && lane == r) {
+                    rc = cur;
+                    rr = rem;
+                    rs = (k << 1) | (fire ? 1 : 0);
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) frame[i] = __fadd_rn(frame[i], __fmul_rn(cur, h[i]));   // :83
+                if (fire) {
+                    if (k < a.L) {
+                        if (col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, frame);
+                        if (rec && lane == 0) a.fire_t[(size_t)b * a.L + k] = t0 + r;
+                    }
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) frame[i] = __fmul_rn(rem, h[i]);   // :85-87
+                    ++k;
+                }
+            }
+        }
+        if (rec && tt < a.T) {
+            a.cur[(size_t)b * a.T + tt] = rc;
+            a.rem[(size_t)b * a.T + tt] = rr;
+            a.sched[(size_t)b * a.T + tt] = rs;
+        }
+        // every lane is done reading this stage -> refill it
+        __syncwarp();
+        const int cn = c + nstage;
+        if (lane == 0 && cn < nchunk) {
+            mbar_arrive_expect_tx(&bars[stage], kTileBytes);
+            tma_load_2d(smem_raw + (size_t)stage * kTileBytes, &tmap, slice * W, row0 + cn * kCifRows, &bars[stage]);
+        }
+        if (++stage == nstage) {
+            stage = 0;
+            phase ^= 1u;
+        }
+    }
+    cif_fwd_finish<VEC>(a, b, slice, lane, col, col_ok, k, asum);
+}
+
+// ---- backward -----------------------------------------------------------------
+struct CifBwdArgs {
+    const float* hidden;
+    const float* g_out;
+    const int* n_fired;
+    const float* cur;
+    const float* rem;
+    const int* sched;
+    int B, T, H, L;
+    float* g_hidden;
+    float* part;   // == g_alphas, finalised by the scan kernel
+    float* gcf;    // workspace [B*T]: fire ? gcur : 0
+};
+
+constexpr int kBwdRowsPerCta = 32;
+
+template <int VEC>
+__global__ void __launch_bounds__(256) cif_bwd_rows_kernel(const CifBwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarp = blockDim.x >> 5;
+    const long long total = (long long)a.B * a.T;
+    const long long base = (long long)blockIdx.x * kBwdRowsPerCta;
+    for (int i = warp; i < kBwdRowsPerCta; i += nwarp) {
+        const long long row = base + i;
+        if (row >= total) break;
+        const int b = (int)(row / a.T);
+        const int sc = __ldg(a.sched + row);
+        const bool fire = (sc & 1) != 0;
+        const int seg = sc >> 1;
+        const int nf = min(__ldg(a.n_fired + b), a.L);
+        const float c = __ldg(a.cur + row);
+        const float r = __ldg(a.rem + row);
+        const float* gp = (seg < nf) ? a.g_out + ((size_t)b * a.L + seg) * a.H : nullptr;
+        const float* gG = (fire && seg + 1 < nf) ? a.g_out + ((size_t)b * a.L + seg + 1) * a.H : nullptr;
+        const float* h = a.hidden + (size_t)row * a.H;
+        float* gh = a.g_hidden + (size_t)row * a.H;
+        float d1 = 0.0f, d2 = 0.0f;
+        for (int col = lane * VEC; col < a.H; col += 32 * VEC) {
+            float hv[VEC], pv[VEC], Gv[VEC], o[VEC];
+            vload_nc<VEC>(hv, h + col);
+            if (gp != nullptr) {
+                vload<VEC>(pv, gp + col);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) pv[j] = 0.0f;
+            }
+            if (gG != nullptr) {
+                vload<VEC>(Gv, gG + col);
+            } else {
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) Gv[j] = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                o[j] = __fmul_rn(c, pv[j]);
+                d1 = fmaf(pv[j], hv[j], d1);
+                if (fire) {
+                    o[j] = __fadd_rn(o[j], __fmul_rn(r, Gv[j]));
+                    d2 = fmaf(Gv[j], hv[j], d2);
+                }
+            }
+            vstore<VEC>(gh + col, o);
+        }
+        d1 = warp_sum(d1);
+        d2 = warp_sum(d2);
+        if (lane == 0) {
+            a.part[row] = fire ? d2 : d1;
+            a.gcf[row] = fire ? (d1 - d2) : 0.0f;
+        }
+    }
+}
+
+// g_alpha[t] = part[t] - sum_{s>t} gcf[s]    (one warp per utterance, reverse scan)
+__global__ void __launch_bounds__(128) cif_bwd_scan_kernel(float* g_alpha, const float* gcf, int B, int T) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    float* ga = g_alpha + (size_t)b * T;
+    const float* gc = gcf + (size_t)b * T;
+    float carry = 0.0f;
+    for (int t0 = ((T - 1) / 32) * 32; t0 >= 0; t0 -= 32) {
+        const int t = t0 + lane;
+        const float v = (t < T) ? gc[t] : 0.0f;
+        float incl = v;   // inclusive suffix sum over lanes >= lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float y = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += y;
+        }
+        float excl = __shfl_down_sync(0xffffffffu, incl, 1);
+        if (lane == 31) excl = 0.0f;
+        if (t < T) ga[t] = ga[t] - (carry + excl);
+        carry += __shfl_sync(0xffffffffu, incl, 0);
+    }
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float threshold, int B, int T, int H, int L,
+                               float* out, int* fire_t, int* n_fired, float* cur, float* rem, int* sched,
+                               float* alpha_sum, const float* target_num, float* qua_term, void* stream) {
+    ASR_REQUIRE(B > 0 && T > 0 && H > 0 && L >= 0, "asr_cif_fwd_f32: bad shape B=%d T=%d H=%d L=%d", B, T, H, L);
+    ASR_REQUIRE(hidden && alphas && n_fired && cur && rem && sched && alpha_sum, "asr_cif_fwd_f32: null pointer");
+    ASR_REQUIRE(L == 0 || (out && fire_t), "asr_cif_fwd_f32: null output with L=%d", L);
+    ASR_REQUIRE((long long)B * T < (1ll << 30), "asr_cif_fwd_f32: B*T too large");
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CifFwdArgs a{hidden, alphas, threshold, B, T, H, L, out, fire_t, n_fired, cur, rem, sched, alpha_sum, target_num, qua_term};
+
+    const bool vec4_ok = (H % 4 == 0) && aligned16(hidden) && (L == 0 || aligned16(out));
+    int variant = get_opt("cif_fwd_variant");
+    if (variant == 0) variant = (vec4_ok && T >= 64) ? 2 : 1;
+    if (variant == 2 && !vec4_ok) variant = 1;
+
+    // slice width: widest that still yields >= 2 warps per SM
+    int width = get_opt("cif_fwd_width");
+    if (width != 32 && width != 64 && width != 128) {
+        const int want = 2 * num_sms();
+        width = 128;
+        while (width > 32 && (long long)B * ((H + width - 1) / width) < want) width >>= 1;
+    }
+    if (!vec4_ok) {
+        // generic path: scalar or float2 lanes
+        width = (H % 2 == 0 && (reinterpret_cast<uintptr_t>(hidden) & 7u) == 0 && (L == 0 || (reinterpret_cast<uintptr_t>(out) & 7u) == 0)) ? 64 : 32;
+        if (width == 64 && (long long)B * ((H + 63) / 64) < 2 * num_sms()) width = 32;
+    }
+    const int nslices = (H + width - 1) / width;
+
+    if (variant == 2) {
+        CUtensorMap tmap;
+        if (make_tmap_2d(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hidden, (uint64_t)B * T, (uint64_t)H,
+                         (uint64_t)H * 4, kCifRows, (uint32_t)width, CU_TENSOR_MAP_SWIZZLE_NONE) != 0)
+            return 4;
+        int nstage = get_opt("cif_fwd_stages");
+        if (nstage <= 0) nstage = 6;
+        if (nstage > kCifMaxStages) nstage = kCifMaxStages;
+        const size_t smem = (size_t)nstage * kCifRows * width * 4;
+        dim3 grid(nslices, B);
+        ASR_REQUIRE(B <= 65535, "asr_cif_fwd_f32: B=%d exceeds grid.y", B);
+        if (width == 128) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_tma_kernel<4><<<grid, 32, smem, st>>>(tmap, a, nstage);
+        } else if (width == 64) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_tma_kernel<2><<<grid, 32, smem, st>>>(tmap, a, nstage);
+        } else {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_tma_kernel<1><<<grid, 32, smem, st>>>(tmap, a, nstage);
+        }
+        ASR_LAUNCH_CHECK();
+        return 0;
+    }
+
+    const long long nwarps = (long long)B * nslices;
+    const int blocks = (int)((nwarps + 3) / 4);
+    if (width == 128) {
+        cif_fwd_plain_kernel<4><<<blocks, 128, 0, st>>>(a, nslices);
+    } else if (width == 64) {
+        cif_fwd_plain_kernel<2><<<blocks, 128, 0, st>>>(a, nslices);
+    } else {
+        cif_fwd_plain_kernel<1><<<blocks, 128, 0, st>>>(a, nslices);
+    }
+    ASR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t asr_cif_bwd_workspace_bytes(int B, int T) {
+    return (size_t)(B > 0 ? B : 0) * (size_t)(T > 0 ? T : 0) * sizeof(float);
+}
+
+extern "C" int asr_cif_bwd_f32(const float* hidden, const float* g_out, const int* n_fired, const float* cur,
+                               const float* rem, const int* sched, int B, int T, int H, int L, float* g_hidden,
+                               float* g_alphas, void* ws, size_t ws_bytes, void* stream) {
+    ASR_REQUIRE(B > 0 && T > 0 && H > 0 && L >= 0, "asr_cif_bwd_f32: bad shape B=%d T=%d H=%d L=%d", B, T, H, L);
+    ASR_REQUIRE(hidden && n_fired && cur && rem && sched && g_hidden && g_alphas && ws, "asr_cif_bwd_f32: null pointer");
+    ASR_REQUIRE(L == 0 || g_out, "asr_cif_bwd_f32: null g_out with L=%d", L);
+    ASR_REQUIRE(ws_bytes >= asr_cif_bwd_workspace_bytes(B, T), "asr_cif_bwd_f32: workspace too small (%zu < %zu)",
+                ws_bytes, asr_cif_bwd_workspace_bytes(B, T));
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CifBwdArgs a{hidden, g_out, n_fired, cur, rem, sched, B, T, H, L, g_hidden, g_alphas, static_cast<float*>(ws)};
+    const long long rows = (long long)B * T;
+    const int blocks = (int)((rows + kBwdRowsPerCta - 1) / kBwdRowsPerCta);
+    const bool v4 = (H % 4 == 0) && aligned16(hidden) && aligned16(g_hidden) && (L == 0 || aligned16(g_out));
+    const bool v2 = (H % 2 == 0) && ((reinterpret_cast<uintptr_t>(hidden) | reinterpret_cast<uintptr_t>(g_hidden) |
+                                      reinterpret_cast<uintptr_t>(g_out)) & 7u) == 0;
+    if (v4) {
+        cif_bwd_rows_kernel<4><<<blocks, 256, 0, st>>>(a);
+    } else if (v2) {
+        cif_bwd_rows_kernel<2><<<blocks, 256, 0, st>>>(a);
+    } else {
+        cif_bwd_rows_kernel<1><<<blocks, 256, 0, st>>>(a);
+    }
+    ASR_LAUNCH_CHECK();
+    cif_bwd_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(g_alphas, static_cast<const float*>(ws), B, T);
+    ASR_LAUNCH_CHECK();
+    return 0;
+}

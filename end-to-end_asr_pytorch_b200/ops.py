@@ -1,0 +1,166 @@
+"""torch.autograd.Function wrappers over the C ABI (include/asr_sm100.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every hot-path
+computation below is one call into libasr_sm100.so.  No CPU fallback: tensors
+must live on a CUDA (sm_100) device.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import ptr, stream_ptr, check
+
+
+def _require_cuda(name, t, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: libasr_sm100 has no CPU path" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+# ---------------------------------------------------------------------------------
+# CIF  (reference: src/transformer/cif_model.py:57-106)
+# ---------------------------------------------------------------------------------
+class _CifFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, hidden, alphas, threshold, L, target_num):
+        B, T, H = hidden.shape
+        dev = hidden.device
+        out = torch.empty((B, L, H), dtype=torch.float32, device=dev)
+        fire_t = torch.empty((B, L), dtype=torch.int32, device=dev)
+        n_fired = torch.empty((B,), dtype=torch.int32, device=dev)
+        cur = torch.empty((B, T), dtype=torch.float32, device=dev)
+        rem = torch.empty((B, T), dtype=torch.float32, device=dev)
+        sched = torch.empty((B, T), dtype=torch.int32, device=dev)
+        alpha_sum = torch.empty((B,), dtype=torch.float32, device=dev)
+        qua_term = torch.empty((B,), dtype=torch.float32, device=dev) if target_num is not None else None
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_cif_fwd_f32(
+                ptr(hidden), ptr(alphas), ctypes.c_float(threshold), B, T, H, L,
+                ptr(out) if L > 0 else None, ptr(fire_t) if L > 0 else None, ptr(n_fired),
+                ptr(cur), ptr(rem), ptr(sched), ptr(alpha_sum), ptr(target_num), ptr(qua_term),
+                stream_ptr()), "asr_cif_fwd_f32")
+        ctx.save_for_backward(hidden, n_fired, cur, rem, sched)
+        ctx.dims = (B, T, H, L)
+        if qua_term is None:
+            qua_term = alpha_sum.new_empty((0,))
+        ctx.mark_non_differentiable(fire_t, n_fired, alpha_sum, qua_term)
+        return out, fire_t, n_fired, alpha_sum, qua_term
+
+    @staticmethod
+    def backward(ctx, g_out, *unused):
+        hidden, n_fired, cur, rem, sched = ctx.saved_tensors
+        B, T, H, L = ctx.dims
+        dev = hidden.device
+        g_out = g_out.contiguous()
+        if g_out.dtype != torch.float32:
+            g_out = g_out.float()
+        g_hidden = torch.empty_like(hidden)
+        g_alphas = torch.empty((B, T), dtype=torch.float32, device=dev)
+        ws_bytes = _lib.lib().asr_cif_bwd_workspace_bytes(B, T)
+        ws = torch.empty((max(ws_bytes, 4) // 4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_cif_bwd_f32(
+                ptr(hidden), ptr(g_out) if L > 0 else None, ptr(n_fired), ptr(cur), ptr(rem), ptr(sched),
+                B, T, H, L, ptr(g_hidden), ptr(g_alphas), ptr(ws), ws_bytes, stream_ptr()), "asr_cif_bwd_f32")
+        return g_hidden, g_alphas, None, None, None
+
+
+def cif_label_len(alphas):
+    """L of cif_model.py:95-96: max_b int(round(sum_t alphas)) - one host sync, like the reference."""
+    return int(torch.round(alphas.sum(-1)).int().max().item())
+
+
+def cif(hidden, alphas, threshold, L=None, target_num=None, check_overflow=True, return_aux=False):
+    """Integrate-and-fire.  hidden [B,T,H] f32, alphas [B,T] f32 -> [B,L,H] f32.
+
+    L defaults to the reference's max_b round(sum_t alphas).  With return_aux the
+    result is (out, aux) where aux holds fire_t [B,L] (frame index of each fire),
+    n_fired [B], alpha_sum [B] and, when target_num [B] is given, qua_term [B] =
+    (alpha_sum - target_num)^2.
+    """
+    _require_cuda("hidden", hidden, torch.float32)
+    _require_cuda("alphas", alphas, torch.float32)
+    if hidden.dim() != 3 or alphas.dim() != 2 or hidden.shape[:2] != alphas.shape:
+        raise ValueError("cif: hidden [B,T,H] and alphas [B,T] expected, got %s and %s"
+                         % (tuple(hidden.shape), tuple(alphas.shape)))
+    hidden_c = hidden.contiguous()
+    alphas_c = alphas.contiguous()
+    if L is None:
+        L = cif_label_len(alphas_c)
+    if target_num is not None:
+        _require_cuda("target_num", target_num, torch.float32)
+        target_num = target_num.contiguous()
+    out, fire_t, n_fired, alpha_sum, qua_term = _CifFunction.apply(hidden_c, alphas_c, float(threshold), int(L), target_num)
+    if check_overflow:
+        worst = int(n_fired.max().item()) if n_fired.numel() else 0
+        if worst > L:
+            # the reference dies in torch.zeros([max_label_len - l.size(0), H]) (cif_model.py:100)
+            raise RuntimeError("cif: an utterance fired %d times but the output holds L=%d rows "
+                               "(L = max round(sum alphas), cif_model.py:95-100)" % (worst, L))
+    if return_aux:
+        aux = {"fire_t": fire_t, "n_fired": n_fired, "alpha_sum": alpha_sum,
+               "qua_term": qua_term if target_num is not None else None}
+        return out, aux
+    return out
+
+
+# ---------------------------------------------------------------------------------
+# CTC loss  (reference: src/transformer/loss.py:39-43, src/ctcModel/loss.py:7-11)
+# ---------------------------------------------------------------------------------
+class _CtcLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, in_len, tgt_len, blank):
+        B, T, V = logits.shape
+        S = targets.shape[1]
+        dev = logits.device
+        need_grad = ctx.needs_input_grad[0]
+        nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        g = torch.empty_like(logits) if need_grad else None
+        ws_bytes = _lib.lib().asr_ctc_workspace_bytes(B, T, V, S)
+        ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_ctc_fwd_bwd_f32(
+                ptr(logits), ptr(targets) if S > 0 else None, ptr(in_len), ptr(tgt_len),
+                B, T, V, S, int(blank), ptr(nll), ptr(g), ptr(ws), ws_bytes, stream_ptr()),
+                "asr_ctc_fwd_bwd_f32")
+        # reduction='mean' of F.ctc_loss: mean_b(nll_b / clamp(target_len_b, 1))
+        loss = (nll / tgt_len.clamp(min=1).to(nll.dtype)).mean()
+        ctx.g = g
+        ctx.mark_non_differentiable(nll)
+        return loss, nll
+
+    @staticmethod
+    def backward(ctx, g_loss, g_nll_unused):
+        g = ctx.g
+        if g is None:
+            raise RuntimeError("ctc_loss: backward called twice (the fused gradient buffer is handed out once)")
+        ctx.g = None
+        g_loss = g_loss.reshape(1).to(dtype=torch.float32, device=g.device).contiguous()
+        with torch.cuda.device(g.device):
+            # scales in place on the device only when the incoming gradient is not exactly 1
+            check(_lib.lib().asr_scale_inplace_f32(ptr(g), g.numel(), ptr(g_loss), stream_ptr()),
+                  "asr_scale_inplace_f32")
+        return g, None, None, None, None
+
+
+def ctc_loss(logits, len_logits, targets, blank=None, return_nll=False):
+    """Mean CTC loss of raw logits [B,T,V] (log-softmax fused), targets [B,S]
+    0-padded int64, blank = V-1 by default - the reference's call convention."""
+    _require_cuda("logits", logits)
+    if logits.dim() != 3:
+        raise ValueError("ctc_loss: logits [B,T,V] expected")
+    if logits.dtype != torch.float32:
+        logits = logits.float()
+    B, T, V = logits.shape
+    if blank is None:
+        blank = V - 1
+    logits_c = logits.contiguous()
+    targets_c = targets.to(device=logits.device, dtype=torch.int64).contiguous()
+    tgt_len = targets_c.ne(0).sum(1).to(torch.int32)
+    in_len = len_logits.to(device=logits.device, dtype=torch.int32).contiguous()
+    loss, nll = _CtcLossFunction.apply(logits_c, targets_c, in_len, tgt_len, blank)
+    if return_nll:
+        return loss, nll
+    return loss

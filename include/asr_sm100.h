@@ -1,0 +1,157 @@
+/*
+ * asr_sm100.h - C ABI of libasr_sm100.so: the B200 (sm_100a) acoustic-model
+ * training hot path of eastonYi/end-to-end_asr_pytorch.
+ *
+ * The reference has no FFI / operator registry: the drop-in
+ * boundary is the Python API of three modules.  Every entry point below is what
+ * the Python-side `torch.autograd.Function` wrappers bind through ctypes, and
+ * each one names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C symbols, plain pointers and sizes, no torch / C++ types;
+ *   - return 0 on success, non-zero on failure (never throws, never exits);
+ *     `asr_last_error()` returns a thread-local description of the last failure;
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no allocation inside the library: outputs, saved-for-backward buffers and
+ *     workspaces are owned by the caller (PyTorch caching allocator);
+ *   - tensors are contiguous, row-major; base pointers 16-byte aligned;
+ *   - `stream` is a `cudaStream_t` passed as void*; all calls are asynchronous
+ *     on that stream and stateless, hence re-entrant per stream;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every
+ *     compute entry point returns an error.
+ */
+#ifndef ASR_SM100_H
+#define ASR_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASR_SM100_ABI_VERSION 1
+
+/* ---- housekeeping ------------------------------------------------------- */
+int         asr_abi_version(void);
+const char* asr_last_error(void);
+/* 0 when the current CUDA device is compute capability 10.x, else non-zero. */
+int         asr_device_ok(void);
+/* Tuning knobs (kernel variants; all variants are sm_100a CUDA).  Unknown keys
+ * return non-zero.  Keys: "cif_fwd_variant" (0 = auto, 1 = plain loads,
+ * 2 = TMA pipeline), "cif_fwd_width" (0 = auto, 32/64/128 floats per warp),
+ * "cif_fwd_stages" (0 = auto), "ctc_rec_variant" (0 = auto). */
+int         asr_set_option(const char* key, int value);
+int         asr_get_option(const char* key, int* value);
+/* Number of kernels launched by this library since load (all streams). */
+uint64_t    asr_launch_count(void);
+
+/* ---- CIF: continuous integrate-and-fire --------------------------------- */
+/*
+ * Replaces CIF_Model.cif, /root/reference/src/transformer/cif_model.py:57-106
+ * (forward) and the autograd graph it builds (backward).
+ *
+ *   hidden  [B,T,H] f32   encoder frames
+ *   alphas  [B,T]   f32   per-frame weights (already scaled, cif_model.py:48)
+ *   L               rows of the output; the caller sizes it the reference's
+ *                   way: max_b int(round(sum_t alphas[b,t]))  (cif_model.py:95-96)
+ * outputs
+ *   out       [B,L,H] f32  fired frames, zero rows beyond n_fired[b] (written
+ *                          entirely by the kernel, no pre-zeroing needed)
+ *   fire_t    [B,L]   i32  frame index of the k-th fire, -1 beyond n_fired[b]
+ *   n_fired   [B]     i32  number of fires (may exceed L: rows >= L are dropped
+ *                          and the Python wrapper raises, like the reference's
+ *                          torch.zeros(negative) at cif_model.py:100)
+ *   cur, rem  [B,T]   f32  saved for backward (cif_model.py:78-81)
+ *   sched     [B,T]   i32  saved for backward: (#fires before t) << 1 | fire_t
+ *   alpha_sum [B]     f32  sum_t alphas[b,t] (sequential fp32 order); with
+ *   target_num[B]     f32  (may be NULL) the kernel also emits
+ *   qua_term  [B]     f32  (alpha_sum - target_num)^2, the per-utterance term of
+ *                          the quantity loss (transformer/loss.py:55)
+ */
+int asr_cif_fwd_f32(const float* hidden, const float* alphas, float threshold,
+                    int B, int T, int H, int L,
+                    float* out, int* fire_t, int* n_fired,
+                    float* cur, float* rem, int* sched,
+                    float* alpha_sum, const float* target_num, float* qua_term,
+                    void* stream);
+
+/*
+ * Analytic backward of the above (SURVEY.md 8a row a2').
+ *   g_out [B,L,H] -> g_hidden [B,T,H], g_alphas [B,T]
+ * ws: asr_cif_bwd_workspace_bytes(B,T) bytes of device scratch.
+ */
+size_t asr_cif_bwd_workspace_bytes(int B, int T);
+int asr_cif_bwd_f32(const float* hidden, const float* g_out,
+                    const int* n_fired, const float* cur, const float* rem, const int* sched,
+                    int B, int T, int H, int L,
+                    float* g_hidden, float* g_alphas,
+                    void* ws, size_t ws_bytes, void* stream);
+
+/* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
+/*
+ * Replaces log_softmax + torch.nn.functional.ctc_loss as called at
+ * /root/reference/src/transformer/loss.py:39-43, src/ctcModel/loss.py:7-11 and
+ * src/mask_lm/loss.py:38-41 (blank = V-1, targets 0-padded [B,S] int64).
+ *
+ *   logits   [B,T,V] f32
+ *   targets  [B,S]   i64   0 = padding; tgt_len[b] = number of leading labels
+ *   in_len   [B]     i32   valid frames per utterance (<= T)
+ *   tgt_len  [B]     i32   labels per utterance (<= S)
+ * outputs
+ *   nll      [B]     f32   -log p(targets|logits); +inf when no alignment exists
+ *   g_logits [B,T,V] f32   (may be NULL: forward only) d(mean loss)/d logits,
+ *                          mean loss = mean_b(nll_b / max(tgt_len_b,1));
+ *                          exactly 0 for t >= in_len[b]; NaN rows for an
+ *                          infeasible utterance (zero_infinity=False semantics)
+ * ws: asr_ctc_workspace_bytes(B,T,V,S) bytes of device scratch.  It holds the
+ *     gathered log-probabilities [B,T,S+1]; the alpha/beta lattice never leaves
+ *     shared memory.
+ */
+size_t asr_ctc_workspace_bytes(int B, int T, int V, int S);
+int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
+                        const int* in_len, const int* tgt_len,
+                        int B, int T, int V, int S, int blank,
+                        float* nll, float* g_logits,
+                        void* ws, size_t ws_bytes, void* stream);
+/* In-place g *= *scale_dev, skipped on the device when *scale_dev == 1.0f
+ * (autograd's incoming gradient for the loss; it is 1 in the reference's
+ * solvers, transformer/solver.py:153). */
+int asr_scale_inplace_f32(float* g, size_t n, const float* scale_dev, void* stream);
+
+/* ---- multi-head attention core ------------------------------------------ */
+/*
+ * Replaces ScaledDotProductAttention.forward,
+ * /root/reference/src/transformer/attention.py:74-86 (and the head split /
+ * merge copies at :47-49,:56-57), bf16 in, fp32 accumulate.
+ *
+ *   q [B,Lq,Hh,D], k,v [B,Lk,Hh,D] bf16 (the natural layout of the w_qs/w_ks/w_vs
+ *   outputs, attention.py:43-45; D = 64), out [B,Lq,Hh,D] bf16 (what `fc` eats).
+ *   kv_len [B] i32 or NULL: keys >= kv_len[b] are masked (get_attn_pad_mask /
+ *   get_attn_key_pad_mask, utils/utils.py:147-165); causal != 0 adds the
+ *   subsequent mask (utils.py:136-144); dense_mask [B,Lq,Lk] u8 or NULL is the
+ *   general form (non-zero = masked).  lse [B,Hh,Lq] f32 is saved for backward.
+ *   A fully masked row yields NaN like the reference's softmax over all -inf.
+ */
+int asr_mha_fwd_bf16(const void* q, const void* k, const void* v,
+                     const int* kv_len, const uint8_t* dense_mask, int causal,
+                     int B, int Hh, int Lq, int Lk, int D, float scale,
+                     void* out, float* lse, void* stream);
+size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int D);
+int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, const void* out,
+                     const void* g_out, const float* lse,
+                     const int* kv_len, const uint8_t* dense_mask, int causal,
+                     int B, int Hh, int Lq, int Lk, int D, float scale,
+                     void* g_q, void* g_k, void* g_v,
+                     void* ws, size_t ws_bytes, void* stream);
+/* attention probabilities [Hh*B, Lq, Lk] f32 in the reference's head-major row
+ * order (attention.py:47,62) - only computed when a caller asks for `attn`. */
+int asr_mha_probs_f32(const void* q, const void* k,
+                      const int* kv_len, const uint8_t* dense_mask, int causal,
+                      int B, int Hh, int Lq, int Lk, int D, float scale,
+                      float* attn, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASR_SM100_H */

@@ -1,0 +1,154 @@
+"""CTC kernels vs the oracle, the reference-generated golden vectors and torch's
+own F.ctc_loss on the same device (the library call the reference makes)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+from conftest import load_golden
+from helpers import pkg, make_ctc_inputs, to_np
+
+pytestmark = pytest.mark.gpu
+
+CTC = load_golden("ctc")
+CASES = sorted({k.split("_")[0] for k in CTC.files})
+
+
+def _ours(logits, targets, in_len, need_grad=True):
+    ops = pkg("ops")
+    lg = logits.clone().requires_grad_(need_grad)
+    loss, nll = ops.ctc_loss(lg, in_len, targets, return_nll=True)
+    grad = None
+    if need_grad:
+        loss.backward()
+        grad = lg.grad
+    return loss.detach(), nll, grad
+
+
+def _torch_ref(logits, targets, in_len, dtype=torch.float32):
+    """Exactly the reference's call sequence (transformer/loss.py:39-43) on this device."""
+    lg = logits.to(dtype).clone().requires_grad_(True)
+    V = lg.size(-1)
+    tl = targets.ne(0).int().sum(1)
+    lp = F.log_softmax(lg, dim=-1).transpose(0, 1)
+    loss = F.ctc_loss(lp, targets, in_len, tl, blank=V - 1)
+    loss.backward()
+    nll = F.ctc_loss(lp.detach(), targets, in_len, tl, blank=V - 1, reduction="none")
+    return loss.detach(), nll, lg.grad
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_golden(case):
+    logits = torch.as_tensor(CTC[case + "_logits"]).cuda()
+    targets = torch.as_tensor(CTC[case + "_targets"]).cuda()
+    in_len = torch.as_tensor(CTC[case + "_in_len"]).cuda()
+    loss, nll, grad = _ours(logits, targets, in_len)
+    ref_nll, ref_loss, ref_grad = CTC[case + "_nll"], CTC[case + "_loss"], CTC[case + "_grad"]
+    fin = np.isfinite(ref_nll)
+    np.testing.assert_array_equal(np.isfinite(to_np(nll)), fin)
+    np.testing.assert_allclose(to_np(nll)[fin], ref_nll[fin], rtol=1e-5)
+    if np.isfinite(ref_loss):
+        np.testing.assert_allclose(float(loss), ref_loss, rtol=1e-5)
+    else:
+        assert np.isinf(float(loss)) and float(loss) > 0
+    g = to_np(grad)
+    gscale = np.nanmax(np.abs(ref_grad)) + 1e-30
+    for b in range(g.shape[0]):
+        if fin[b]:
+            # fp32 rtol 1e-5 relative to the gradient scale of the tensor
+            assert np.abs(g[b] - ref_grad[b]).max() <= 1e-5 * gscale + 1e-5 * np.abs(ref_grad[b]).max()
+        else:
+            np.testing.assert_array_equal(np.isnan(g[b]), np.isnan(ref_grad[b]))
+        assert not g[b, int(CTC[case + "_in_len"][b]):].any()
+
+
+def test_forward_only_matches_and_writes_no_grad():
+    logits = torch.as_tensor(CTC["b_logits"]).cuda()
+    targets = torch.as_tensor(CTC["b_targets"]).cuda()
+    in_len = torch.as_tensor(CTC["b_in_len"]).cuda()
+    with torch.no_grad():
+        loss, nll, _ = _ours(logits, targets, in_len, need_grad=False)
+    np.testing.assert_allclose(to_np(nll), CTC["b_nll"], rtol=1e-5)
+    np.testing.assert_allclose(float(loss), CTC["b_loss"], rtol=1e-5)
+
+
+def test_reference_entry_points():
+    tl = pkg("transformer.loss")
+    cl = pkg("ctcModel.loss")
+    g = load_golden("qua")
+    dev = "cuda"
+    qua, ctc, ce = tl.cal_ctc_qua_ce_loss(torch.as_tensor(g["logits"]).to(dev), torch.as_tensor(g["in_len"]).to(dev),
+                                          torch.as_tensor(g["_number"]).to(dev), torch.as_tensor(g["number"]).to(dev),
+                                          torch.as_tensor(g["ce_logits"]).to(dev), torch.as_tensor(g["targets"]).to(dev),
+                                          smoothing=0.1)
+    np.testing.assert_allclose(float(qua), g["qua"], rtol=1e-6)
+    np.testing.assert_allclose(float(ctc), g["ctc"], rtol=1e-5)
+    np.testing.assert_allclose(float(ce), g["ce"], rtol=1e-5)
+    loss = cl.cal_loss(torch.as_tensor(g["logits"]).to(dev), torch.as_tensor(g["in_len"]).to(dev),
+                       torch.as_tensor(g["targets"]).to(dev))
+    np.testing.assert_allclose(float(loss), g["ctc"], rtol=1e-5)
+
+
+def test_incoming_gradient_scale():
+    """loss * 3 must scale the fused gradient (device-side, no host sync)."""
+    ops = pkg("ops")
+    logits, targets, in_len = make_ctc_inputs(4, 30, 50, 6, seed=3)
+    a = logits.clone().requires_grad_(True)
+    ops.ctc_loss(a, in_len, targets).backward()
+    b = logits.clone().requires_grad_(True)
+    (3.0 * ops.ctc_loss(b, in_len, targets)).backward()
+    torch.testing.assert_close(b.grad, 3.0 * a.grad, rtol=1e-6, atol=0)
+
+
+@pytest.mark.parametrize("B,T,V,S", [(4, 50, 100, 10), (3, 33, 4233, 7), (6, 70, 31, 20), (2, 200, 64, 40),
+                                     (2, 90, 17, 80), (3, 64, 4233, 1), (2, 40, 10, 100)])
+def test_random_vs_oracle_fp64(B, T, V, S):
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=100 + T + S)
+    loss, nll, grad = _ours(logits, targets, in_len)
+    o_loss, o_nll, o_grad = oracle.ctc_loss_and_grad(to_np(logits), to_np(targets), to_np(in_len))
+    r_loss, r_nll, r_grad = _torch_ref(logits, targets, in_len)
+    fin = np.isfinite(o_nll)
+    np.testing.assert_array_equal(np.isfinite(to_np(nll)), fin)
+    # ours vs fp64 truth must be no worse than 1e-5, or than torch's own fp32 error (x2)
+    err_ours = np.abs(to_np(nll)[fin] - o_nll[fin]) / np.abs(o_nll[fin])
+    err_ref = np.abs(to_np(r_nll)[fin] - o_nll[fin]) / np.abs(o_nll[fin])
+    assert (err_ours <= np.maximum(1e-5, 2 * err_ref)).all(), (err_ours, err_ref)
+    if not fin.any():
+        assert np.isnan(to_np(grad)[:, 0]).all()
+        return
+    gs = np.nanmax(np.abs(o_grad[fin]))
+    ge_ours = np.abs(to_np(grad)[fin] - o_grad[fin]).max() / gs
+    ge_ref = np.abs(to_np(r_grad)[fin] - o_grad[fin]).max() / gs
+    assert ge_ours <= max(1e-5, 2 * ge_ref), (ge_ours, ge_ref)
+
+
+@pytest.mark.parametrize("B,T,S", [(32, 200, 10), (64, 400, 20)])
+def test_config2_sizes_vs_torch_on_device(B, T, S):
+    """BASELINE config 2 shapes (V=4233): ours vs the library call the reference
+    makes, on the same device, plus size-independent properties."""
+    V = 4233
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=1236)
+    loss, nll, grad = _ours(logits, targets, in_len)
+    r_loss, r_nll, r_grad = _torch_ref(logits, targets, in_len)
+    d_loss, d_nll, d_grad = _torch_ref(logits, targets, in_len, dtype=torch.float64)
+    err_ours = ((nll.double() - d_nll).abs() / d_nll.abs()).max().item()
+    err_ref = ((r_nll.double() - d_nll).abs() / d_nll.abs()).max().item()
+    assert err_ours <= max(1e-5, 2 * err_ref), (err_ours, err_ref)
+    gs = d_grad.abs().max().item()
+    ge_ours = (grad.double() - d_grad).abs().max().item() / gs
+    ge_ref = (r_grad.double() - d_grad).abs().max().item() / gs
+    assert ge_ours <= max(1e-5, 2 * ge_ref), (ge_ours, ge_ref)
+    # properties: rows of d nll/d logits sum to zero (softmax and occupancy both sum to 1);
+    # frames beyond the input length are exactly zero
+    row_sum = grad.double().sum(-1).abs().max().item()
+    assert row_sum <= 1e-6 * max(1.0, gs * V)
+    for b in (0, B // 2, B - 1):
+        assert not grad[b, int(in_len[b]):].any()
+
+
+def test_determinism():
+    logits, targets, in_len = make_ctc_inputs(8, 120, 500, 15, seed=7)
+    _, n1, g1 = _ours(logits, targets, in_len)
+    _, n2, g2 = _ours(logits, targets, in_len)
+    assert torch.equal(n1, n2) and torch.equal(g1, g2)
