@@ -1,0 +1,448 @@
+#!/usr/bin/env python3
+"""bench.py - throughput of the CIF + CTC training hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" is one pass of the hot path over one batch of synthetic
+utterances, the work the reference does per training step around its encoder:
+
+    CTC loss + gradient on the logits [B,T,V]          (a4: K1 row pass, K2 lattice, K3 sparse update)
+    CIF forward on the encoder frames [B,T,H] + quantity term  (a1-a3)
+    CIF backward                                         (a2')
+
+Workload `cif_ctc_joint` = the largest shape of BASELINE config 2 (CTC sweep:
+B=256, T=1600, S=80, V=4233) with the CIF layer of config 4 run on the same batch
+(H=512).  Every rank processes its own batch (data parallel by utterance, weak
+scaling); the hot-path kernels need no collective, only the scalar losses are
+all-reduced for logging.
+
+The JSON line carries:
+  value        utterances/s with inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e          same metric through the public Python API (ops.cif / ops.ctc_loss +
+               autograd) with the inputs copied from pinned host memory and the losses
+               read back every step
+  roofline     the dominant kernel (ctc_rows) against the measured HBM copy peak,
+               timed live with CUDA events inside the timed region
+  cpu_baseline the reference's torch-CPU path (oracle/torch_port.py) on a bounded
+               sample of the same workload, on this box's host cores
+`--impl reference` times only that CPU path (rank 0), in the same JSON shape.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CIF/CTC train utts/sec"
+UNIT = "utts/s"
+
+WORKLOADS = {
+    # name: per-GPU batch
+    "cif_ctc_joint": dict(B=256, T=1600, S=80, V=4233, H=512),
+    "cif_ctc_small": dict(B=32, T=200, S=10, V=4233, H=512),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cif_ctc_joint", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances per CPU-baseline step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+# synthetic inputs, generated on the device that uses them
+# ---------------------------------------------------------------------------------------
+def make_inputs(w, device, seed):
+    B, T, S, V, H = w["B"], w["T"], w["S"], w["V"], w["H"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    logits = torch.randn(B, T, V, device=device, generator=g)
+    hidden = torch.randn(B, T, H, device=device, generator=g)
+    targets = torch.randint(1, V - 1, (B, S), device=device, generator=g)
+    rep = torch.rand(B, S, device=device, generator=g) < 0.1
+    for s in range(1, S):
+        targets[:, s] = torch.where(rep[:, s], targets[:, s - 1], targets[:, s])
+    in_len = torch.randint(int(0.6 * T), T + 1, (B,), device=device, generator=g).to(torch.int32)
+    tgt_len = torch.randint(max(1, S // 2), S + 1, (B,), device=device, generator=g)
+    targets = targets * (torch.arange(S, device=device)[None, :] < tgt_len[:, None]).long()
+    # assigner output: sigmoid weights, zero on padded frames (attentionAssigner.py:34-40)
+    alphas = torch.sigmoid(torch.randn(B, T, device=device, generator=g))
+    alphas = alphas * (torch.arange(T, device=device)[None, :] < in_len[:, None]).float()
+    noise = torch.rand(B, device=device, generator=g)
+    return dict(logits=logits, hidden=hidden, targets=targets, in_len=in_len, tgt_len=tgt_len.to(torch.int32),
+                alphas=alphas, noise=noise)
+
+
+def scale_alphas(alphas, targets, noise):
+    """cif_model.py:43-48 (torch glue, outside the kernels)."""
+    _num = alphas.sum(-1)
+    num = (targets > 0).float().sum(-1)
+    return _num, num, alphas * ((num + noise - 0.5) / _num)[:, None]
+
+
+# ---------------------------------------------------------------------------------------
+# clocks: sampled with NVML while the timed region runs
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.ok = [], set(), False
+        self._stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+            self.max_mhz = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append(mhz)
+                for bit, name in self.REASONS.items():
+                    if bits & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.ok:
+            self.th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self.ok:
+            self.th.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+class HotPath:
+    """Preallocated buffers + direct C-ABI calls (what the autograd wrappers do, minus the allocator)."""
+
+    def __init__(self, w, inp, pkg):
+        self.w, self.inp = w, inp
+        self.lib = pkg._lib
+        self.L = self.lib.lib()
+        B, T, S, V, H = w["B"], w["T"], w["S"], w["V"], w["H"]
+        dev = inp["logits"].device
+        self.nll = torch.empty(B, device=dev)
+        self.g_logits = torch.empty_like(inp["logits"])
+        self.ws_bytes = self.L.asr_ctc_workspace_bytes(B, T, V, S)
+        self.ws = torch.empty(self.ws_bytes // 4 + 1, device=dev)
+        _num, num, self.alphas = scale_alphas(inp["alphas"], inp["targets"], inp["noise"])
+        self.num = num.contiguous()
+        self.alphas = self.alphas.contiguous()
+        self.Lout = int(torch.round(self.alphas.sum(-1)).int().max().item())
+        self.out = torch.empty(B, self.Lout, H, device=dev)
+        self.fire_t = torch.empty(B, self.Lout, dtype=torch.int32, device=dev)
+        self.n_fired = torch.empty(B, dtype=torch.int32, device=dev)
+        self.cur = torch.empty(B, T, device=dev)
+        self.rem = torch.empty(B, T, device=dev)
+        self.sched = torch.empty(B, T, dtype=torch.int32, device=dev)
+        self.asum = torch.empty(B, device=dev)
+        self.qua = torch.empty(B, device=dev)
+        self.g_out = torch.randn(B, self.Lout, H, device=dev)
+        self.g_hidden = torch.empty_like(inp["hidden"])
+        self.g_alpha = torch.empty(B, T, device=dev)
+        self.cif_ws = torch.empty(B * T, device=dev)
+        self.valid_frames = int(inp["in_len"].sum().item())
+        self.n_kernels_per_step = 3 + 1 + 2
+
+    def ctc(self, stages):
+        w, i, p = self.w, self.inp, self.lib.ptr
+        self.lib.check(self.L.asr_ctc_stages_f32(
+            p(i["logits"]), p(i["targets"]), p(i["in_len"]), p(i["tgt_len"]), w["B"], w["T"], w["V"], w["S"],
+            w["V"] - 1, p(self.nll), p(self.g_logits), p(self.ws), self.ws_bytes, stages, self.lib.stream_ptr()),
+            "asr_ctc_stages_f32")
+
+    def cif_fwd(self):
+        w, i, p = self.w, self.inp, self.lib.ptr
+        self.lib.check(self.L.asr_cif_fwd_f32(
+            p(i["hidden"]), p(self.alphas), 0.95, w["B"], w["T"], w["H"], self.Lout, p(self.out), p(self.fire_t),
+            p(self.n_fired), p(self.cur), p(self.rem), p(self.sched), p(self.asum), p(self.num), p(self.qua),
+            self.lib.stream_ptr()), "asr_cif_fwd_f32")
+
+    def cif_bwd(self):
+        w, i, p = self.w, self.inp, self.lib.ptr
+        self.lib.check(self.L.asr_cif_bwd_f32(
+            p(i["hidden"]), p(self.g_out), p(self.n_fired), p(self.cur), p(self.rem), p(self.sched), w["B"], w["T"],
+            w["H"], self.Lout, p(self.g_hidden), p(self.g_alpha), p(self.cif_ws), self.cif_ws.numel() * 4,
+            self.lib.stream_ptr()), "asr_cif_bwd_f32")
+
+    def step(self, ev=None):
+        """One hot-path pass; ev = list of 6 CUDA events recorded between the stages."""
+        def mark(k):
+            if ev is not None:
+                ev[k].record()
+        mark(0)
+        self.ctc(1)
+        mark(1)
+        self.ctc(2)
+        mark(2)
+        self.ctc(4)
+        mark(3)
+        self.cif_fwd()
+        mark(4)
+        self.cif_bwd()
+        mark(5)
+
+    def bytes_model(self):
+        """ALGORITHMIC bytes per launch, stated in DESIGN.md."""
+        w = self.w
+        B, T, V, H, L = w["B"], w["T"], w["V"], w["H"], self.Lout
+        return {
+            "ctc_rows": 8 * V * self.valid_frames,                       # read logits once + write grad once, valid frames
+            "ctc_total": 8 * V * self.valid_frames,
+            "cif_fwd": 4 * (B * T * H + B * T) + 4 * B * L * H,
+            "cif_bwd": 4 * (2 * B * T * H + B * L * H + 4 * B * T),
+        }
+
+
+def e2e_step(pkg, w, host, dev_buf, g_out):
+    """Public-API step with host inputs: pinned H2D copies, ops.cif / ops.ctc_loss, autograd, D2H of the losses."""
+    ops = pkg.ops
+    for k in ("logits", "hidden", "alphas", "targets", "in_len", "noise"):
+        dev_buf[k].copy_(host[k], non_blocking=True)
+    logits = dev_buf["logits"].requires_grad_(True)
+    hidden = dev_buf["hidden"].requires_grad_(True)
+    alphas_raw = dev_buf["alphas"].requires_grad_(True)
+    _num, num, alphas = scale_alphas(alphas_raw, dev_buf["targets"], dev_buf["noise"])
+    fired = ops.cif(hidden, alphas, 0.95)
+    qua = torch.pow(_num - num, 2).mean()
+    ctc = ops.ctc_loss(logits, dev_buf["in_len"], dev_buf["targets"])
+    total = ctc + 0.001 * qua + (fired * g_out[:, :fired.size(1)]).sum()
+    total.backward()
+    losses = torch.stack([ctc.detach(), qua.detach()]).cpu()          # D2H, synchronises
+    for k in ("logits", "hidden", "alphas"):
+        dev_buf[k].grad = None
+        dev_buf[k].requires_grad_(False)
+    return losses
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return {}
+
+
+def cpu_reference_step(w, sample, seed, threads=None):
+    """The reference's torch-CPU path on `sample` utterances of the workload."""
+    from oracle import torch_port
+    if threads:
+        torch.set_num_threads(threads)
+    wc = dict(w, B=sample)
+    inp = make_inputs(wc, "cpu", seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    g_fired = torch.randn(sample, w["S"] + 2, w["H"], generator=g)
+
+    def run():
+        t0 = time.perf_counter()
+        r = torch_port.joint_hot_path_step(inp["hidden"], inp["alphas"], inp["logits"], inp["in_len"], inp["targets"],
+                                           inp["noise"], g_fired)
+        return time.perf_counter() - t0, r
+    return run
+
+
+def run_reference(args, w, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run = cpu_reference_step(w, args.cpu_sample, 1236)
+    for _ in range(max(args.warmup, 1)):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    dt = time.perf_counter() - t0
+    value = args.cpu_sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload=args.workload, **w, per_step_sample=args.cpu_sample,
+                       note="torch-CPU port of the reference path (oracle/torch_port.py); each step = %d utterances "
+                            "of the workload shape" % args.cpu_sample),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d utterances x T=%d, S=%d, V=%d, H=%d per step" % (
+                             args.cpu_sample, w["T"], w["S"], w["V"], w["H"])},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    w = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, w, rank, world)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    import asr_b200 as pkg
+    launches0 = pkg._lib.launch_count()
+    inp = make_inputs(w, device, 1236 + rank)
+    hp = HotPath(w, inp, pkg)
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ---------------------------------------------------
+    for _ in range(W):
+        hp.step()
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(6)] for _ in range(K)]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = pkg._lib.launch_count()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for k in range(K):
+        hp.step(evs[k])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    timed_launches = pkg._lib.launch_count() - l0
+    total_ms = t_start.elapsed_time(t_end)
+    stage_ms = [sum(evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(K)) / K for i in range(5)]
+    t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * w["B"] / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host inputs ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {k: inp[k].cpu().pin_memory() for k in ("logits", "hidden", "alphas", "targets", "in_len", "noise")}
+        dev_buf = {k: torch.empty_like(inp[k]) for k in host}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        Ke = max(3, min(K, 5))
+        for _ in range(2):
+            e2e_step(pkg, w, host, dev_buf, hp.g_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            losses = e2e_step(pkg, w, host, dev_buf, hp.g_out)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * w["B"] * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(losses.numel() * losses.element_size()) + 8, "steps": Ke,
+               "api": "ops.cif + ops.ctc_loss + autograd.backward, pinned-host inputs, losses read back"}
+        del host, dev_buf
+
+    # ---- roofline of the dominant kernel, rank 0 --------------------------------------
+    peaks, peak_src = load_peaks()
+    bm = hp.bytes_model()
+    names = ["ctc_rows", "ctc_lattice", "ctc_apply", "cif_fwd", "cif_bwd"]
+    kernels = []
+    for i, n in enumerate(names):
+        ent = {"kernel": n, "ms": stage_ms[i], "share_of_step": stage_ms[i] / sum(stage_ms)}
+        if n in bm:
+            ent["algorithmic_bytes"] = bm[n]
+            ent["GBps"] = bm[n] / (stage_ms[i] * 1e-3) / 1e9
+            ent["frac_of_hbm_peak"] = ent["GBps"] / peaks["hbm_gbs"]
+        kernels.append(ent)
+    traffic = load_traffic()
+    dom = kernels[0]
+    roofline = {"bound": "hbm", "kernel": "asr::ctc_rows_kernel", "achieved": dom["GBps"], "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": dom["GBps"] / peaks["hbm_gbs"], "peak_source": peak_src,
+                "traffic": traffic.get("ctc_rows_kernel_bytes_per_launch"),
+                "algorithmic_bytes_per_launch": bm["ctc_rows"],
+                "avg_launch_ms": stage_ms[0],
+                "ctc_whole_GBps": bm["ctc_total"] / (sum(stage_ms[:3]) * 1e-3) / 1e9,
+                "ctc_whole_frac": bm["ctc_total"] / (sum(stage_ms[:3]) * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+    if rank == 0:
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            run = cpu_reference_step(w, args.cpu_sample, 1236)
+            run()
+            dt_cpu, _ = run()
+            cpu_baseline = {"value": args.cpu_sample / dt_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": "%d utterances x T=%d, S=%d, V=%d, H=%d, one step after one warm-up (%.1f s)" % (
+                                args.cpu_sample, w["T"], w["S"], w["V"], w["H"], dt_cpu)}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload=args.workload, per_gpu=w, L=hp.Lout, valid_frames=hp.valid_frames,
+                           parallelism="dp%d by utterance, no data-path collective" % world,
+                           l2="inputs (%.1f GB logits + %.1f GB hidden per GPU) exceed the 126 MB L2; no flush needed" % (
+                               inp["logits"].numel() * 4 / 1e9, inp["hidden"].numel() * 4 / 1e9)),
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(timed_launches),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

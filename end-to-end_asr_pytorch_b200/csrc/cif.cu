@@ -96,6 +96,46 @@ struct CifFwdArgs {
     float* qua_term;
 };
 
+// Phase 1 of a 32-frame chunk: the scalar recurrence only (no memory traffic).
+// The sequential loop carries nothing but `integrate` (4 dependent instructions per
+// frame); lane r snapshots the value of integrate BEFORE frame r, and cur / rem /
+// fire are then derived lane-parallel with the reference's own operations, so they
+// are bit-identical to a frame-by-frame evaluation.
+template <bool FULL>
+__device__ __forceinline__ void cif_chain_chunk(float my_alpha, int nrow, float thr, int lane, float& integ,
+                                                float& asum, float& my_cur, float& my_rem, unsigned& fire_mask) {
+    float my_prev = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        if (FULL || r < nrow) {   // warp-uniform
+            const float al = __shfl_sync(0xffffffffu, my_alpha, r);
+            if (lane == r) my_prev = integ;
+            const float s = __fadd_rn(integ, al);              // integrate += alpha        (:71)
+            integ = (s > thr) ? __fsub_rn(s, 1.0f) : s;        // fire -> integrate - 1     (:74-77)
+        }
+    }
+    const float dc = __fsub_rn(1.0f, my_prev);                 // distribution_completion   (:69)
+    const float s = __fadd_rn(my_prev, my_alpha);
+    const bool fire = (lane < nrow) && (s > thr);
+    my_cur = fire ? dc : my_alpha;                             //                           (:78-80)
+    my_rem = __fsub_rn(my_alpha, my_cur);                      // remainds                  (:81)
+    fire_mask = __ballot_sync(0xffffffffu, fire);
+    asum += warp_sum(my_alpha);                                // lanes >= nrow hold 0
+}
+
+// Saved-for-backward schedule and fire positions of a chunk (slice-0 warps only).
+__device__ __forceinline__ void cif_record_chunk(const CifFwdArgs& a, int b, int tt, int lane, int k, float my_cur,
+                                                 float my_rem, unsigned fire_mask) {
+    if (tt < a.T) {
+        const int before = k + __popc(fire_mask & ((1u << lane) - 1u));
+        const bool fired = (fire_mask >> lane) & 1u;
+        a.cur[(size_t)b * a.T + tt] = my_cur;
+        a.rem[(size_t)b * a.T + tt] = my_rem;
+        a.sched[(size_t)b * a.T + tt] = (before << 1) | (fired ? 1 : 0);
+        if (fired && before < a.L) a.fire_t[(size_t)b * a.L + before] = tt;
+    }
+}
+
 // Shared epilogue: zero rows k..L-1 of this warp's slice and publish counters.
 template <int VEC>
 __device__ __forceinline__ void cif_fwd_finish(const CifFwdArgs& a, int b, int slice, int lane, int col, bool col_ok,
@@ -116,6 +156,53 @@ __device__ __forceinline__ void cif_fwd_finish(const CifFwdArgs& a, int b, int s
                 a.qua_term[b] = __fmul_rn(d, d);
             }
         }
+    }
+}
+
+// One frame of phase 2: frame += cur*h (:83); on a fire emit the frame and restart
+// it from rem*h (:85-87).  `fired` is warp-uniform; written as selects so that the
+// compiler keeps the unrolled loop free of branches (only the store is predicated).
+template <int VEC>
+__device__ __forceinline__ void cif_frame_step(const CifFwdArgs& a, int b, int col, bool col_ok, const float (&h)[VEC],
+                                               float c, float rm, bool fired, float (&frame)[VEC], int& k) {
+    float pre[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) pre[i] = __fadd_rn(frame[i], __fmul_rn(c, h[i]));
+    if (fired && k < a.L && col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, pre);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) frame[i] = fired ? __fmul_rn(rm, h[i]) : pre[i];
+    k += fired ? 1 : 0;
+}
+
+// Phase 2 over a full 32-row tile in shared memory: loads are issued 8 rows at a
+// time ahead of the arithmetic (tile rows + the broadcast (cur, rem) pairs).
+template <int VEC>
+__device__ __forceinline__ void cif_tile_full(const CifFwdArgs& a, int b, int col, bool col_ok, const float* tile,
+                                              int row_stride, const float2* cr, unsigned mask, float (&frame)[VEC],
+                                              int& k) {
+#pragma unroll 1
+    for (int r0 = 0; r0 < 32; r0 += 8) {
+        float h[8][VEC];
+        float2 w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            vload<VEC>(h[u], tile + (r0 + u) * row_stride);
+            w[u] = cr[r0 + u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            cif_frame_step<VEC>(a, b, col, col_ok, h[u], w[u].x, w[u].y, (mask >> (r0 + u)) & 1u, frame, k);
+    }
+}
+template <int VEC>
+__device__ __forceinline__ void cif_tile_partial(const CifFwdArgs& a, int b, int col, bool col_ok, const float* tile,
+                                                 int row_stride, const float2* cr, unsigned mask, int nrow,
+                                                 float (&frame)[VEC], int& k) {
+    for (int r = 0; r < nrow; ++r) {
+        float h[VEC];
+        vload<VEC>(h, tile + r * row_stride);
+        const float2 w = cr[r];
+        cif_frame_step<VEC>(a, b, col, col_ok, h, w.x, w.y, (mask >> r) & 1u, frame, k);
     }
 }
 
@@ -143,9 +230,15 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
     for (int t0 = 0; t0 < a.T; t0 += 32) {
         const int tt = t0 + lane;
         const float my_alpha = (tt < a.T) ? __ldg(arow + tt) : 0.0f;
-        float rc = 0.0f, rr = 0.0f;
-        int rs = 0;
         const int nrow = min(32, a.T - t0);
+        float my_cur, my_rem;
+        unsigned fire_mask;
+        if (nrow == 32)
+            cif_chain_chunk<true>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        else
+            cif_chain_chunk<false>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        if (rec) cif_record_chunk(a, b, tt, lane, k, my_cur, my_rem, fire_mask);
+
         for (int r0 = 0; r0 < nrow; r0 += U) {
             float h[U][VEC];
 #pragma unroll
@@ -157,45 +250,25 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
                     for (int i = 0; i < VEC; ++i) h[u][i] = 0.0f;
                 }
             }
+            float cc[U], rr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cc[u] = __shfl_sync(0xffffffffu, my_cur, (r0 + u) & 31);
+                rr[u] = __shfl_sync(0xffffffffu, my_rem, (r0 + u) & 31);
+            }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int r = r0 + u;
-                if (r < nrow) {   // warp-uniform
-                    const float al = __shfl_sync(0xffffffffu, my_alpha, r);
-                    bool fire;
-                    float cur, rem;
-                    cif_chain_step(al, a.thr, integ, fire, cur, rem);
-                    asum = __fadd_rn(asum, al);
-                    if (rec && lane == r) {
-                        rc = cur;
-                        rr = rem;
-                        rs = (k << 1) | (fire ? 1 : 0);
-                    }
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) frame[i] = __fadd_rn(frame[i], __fmul_rn(cur, h[u][i]));   // :83
-                    if (fire) {
-                        if (k < a.L) {
-                            if (col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, frame);
-                            if (rec && lane == 0) a.fire_t[(size_t)b * a.L + k] = t0 + r;
-                        }
-#pragma unroll
-                        for (int i = 0; i < VEC; ++i) frame[i] = __fmul_rn(rem, h[u][i]);   // :85-87
-                        ++k;
-                    }
-                }
+                if (r < nrow)   // warp-uniform
+                    cif_frame_step<VEC>(a, b, col, col_ok, h[u], cc[u], rr[u], (fire_mask >> r) & 1u, frame, k);
             }
-        }
-        if (rec && tt < a.T) {
-            a.cur[(size_t)b * a.T + tt] = rc;
-            a.rem[(size_t)b * a.T + tt] = rr;
-            a.sched[(size_t)b * a.T + tt] = rs;
         }
     }
     cif_fwd_finish<VEC>(a, b, slice, lane, col, col_ok, k, asum);
 }
 
 // ---- forward, TMA pipeline ----------------------------------------------------
-// One warp per CTA.  Tile = ROWS x (32*VEC) floats; NSTAGE tiles in flight.
+// One warp per CTA.  Tile = 32 rows x (32*VEC) floats; NSTAGE tiles in flight.
 constexpr int kCifRows = 32;
 constexpr int kCifMaxStages = 12;
 
@@ -206,6 +279,7 @@ __global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__
     constexpr uint32_t kTileBytes = kCifRows * W * sizeof(float);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bars[kCifMaxStages];
+    __shared__ __align__(16) float2 s_cr[kCifRows];
 
     const int lane = threadIdx.x;
     const int slice = blockIdx.x;
@@ -248,45 +322,26 @@ __global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__
             next_alpha = (tn < a.T) ? __ldg(arow + tn) : 0.0f;
         }
         const int nrow = min(kCifRows, a.T - t0);
-        float rc = 0.0f, rr = 0.0f;
-        int rs = 0;
 
+        // phase 1: recurrence (overlaps the TMA transfer of this stage)
+        float my_cur, my_rem;
+        unsigned fire_mask;
+        if (nrow == kCifRows)
+            cif_chain_chunk<true>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        else
+            cif_chain_chunk<false>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        if (rec) cif_record_chunk(a, b, tt, lane, k, my_cur, my_rem, fire_mask);
+
+        // phase 2: weighted accumulation of the staged tile
+        __syncwarp();
+        s_cr[lane] = make_float2(my_cur, my_rem);
+        __syncwarp();
         mbar_wait(&bars[stage], phase);
         const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * kTileBytes) + lane * VEC;
-
-#pragma unroll 8
-        for (int r = 0; r < kCifRows; ++r) {
-            if (r < nrow) {   // warp-uniform
-                float h[VEC];
-                vload<VEC>(h, tile + r * W);
-                const float al = __shfl_sync(0xffffffffu, my_alpha, r);
-                bool fire;
-                float cur, rem;
-                cif_chain_step(al, a.thr, integ, fire, cur, rem);
-                asum = __fadd_rn(asum, al);
-                if (rec && lane == r) {
-                    rc = cur;
-                    rr = rem;
-                    rs = (k << 1) | (fire ? 1 : 0);
-                }
-#pragma unroll
-                for (int i = 0; i < VEC; ++i) frame[i] = __fadd_rn(frame[i], __fmul_rn(cur, h[i]));   // :83
-                if (fire) {
-                    if (k < a.L) {
-                        if (col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, frame);
-                        if (rec && lane == 0) a.fire_t[(size_t)b * a.L + k] = t0 + r;
-                    }
-#pragma unroll
-                    for (int i = 0; i < VEC; ++i) frame[i] = __fmul_rn(rem, h[i]);   // :85-87
-                    ++k;
-                }
-            }
-        }
-        if (rec && tt < a.T) {
-            a.cur[(size_t)b * a.T + tt] = rc;
-            a.rem[(size_t)b * a.T + tt] = rr;
-            a.sched[(size_t)b * a.T + tt] = rs;
-        }
+        if (nrow == kCifRows)
+            cif_tile_full<VEC>(a, b, col, col_ok, tile, W, s_cr, fire_mask, frame, k);
+        else
+            cif_tile_partial<VEC>(a, b, col, col_ok, tile, W, s_cr, fire_mask, nrow, frame, k);
         // every lane is done reading this stage -> refill it
         __syncwarp();
         const int cn = c + nstage;
@@ -300,6 +355,144 @@ __global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__
         }
     }
     cif_fwd_finish<VEC>(a, b, slice, lane, col, col_ok, k, asum);
+}
+
+// ---- forward, warp-specialised TMA pipeline ---------------------------------------
+// CTA = NW data warps + 1 schedule warp, working on (utterance b, a group of
+// NW*32*VEC hidden columns).  The schedule warp runs the scalar recurrence once per
+// CTA (not once per slice), publishes each chunk's cur/rem/fire-mask in shared
+// memory and issues the TMA tile loads; data warps only do the weighted
+// accumulation, branch-free, from shared memory.  full[] = tile landed AND schedule
+// published; empty[] = all data warps are done with the stage.
+struct CifSched {
+    float2 cr[kCifRows];   // (cur, rem) per frame of the chunk
+    unsigned mask;         // fire bits
+    int pad[3];
+};
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(160) cif_fwd_ws_kernel(const __grid_constant__ CUtensorMap tmap, const CifFwdArgs a,
+                                                         int nstage, int nw) {
+    constexpr int W = 32 * VEC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full[kCifMaxStages];
+    __shared__ __align__(8) uint64_t empty[kCifMaxStages];
+    __shared__ __align__(16) CifSched sched[kCifMaxStages];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int CW = nw * W;   // columns per CTA
+    const uint32_t tile_bytes = (uint32_t)(kCifRows * CW * sizeof(float));
+    const int cgroup = blockIdx.x;
+    const int b = blockIdx.y;
+    const int nchunk = (a.T + kCifRows - 1) / kCifRows;
+    const int row0 = b * a.T;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmap);
+        for (int s = 0; s < nstage; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nw);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == nw) {
+        // ===== schedule + producer warp =====
+        const float* arow = a.alphas + (size_t)b * a.T;
+        const bool rec = (cgroup == 0);
+        float integ = 0.0f, asum = 0.0f;
+        int k = 0, stage = 0;
+        uint32_t phase = 0;
+        float next_alpha = (lane < a.T) ? __ldg(arow + lane) : 0.0f;
+        for (int c = 0; c < nchunk; ++c) {
+            const int t0 = c * kCifRows;
+            const int tt = t0 + lane;
+            const float my_alpha = next_alpha;
+            {
+                const int tn = tt + kCifRows;
+                next_alpha = (tn < a.T) ? __ldg(arow + tn) : 0.0f;
+            }
+            const int nrow = min(kCifRows, a.T - t0);
+            if (c >= nstage) mbar_wait(&empty[stage], phase ^ 1u);
+            if (lane == 0) {
+                mbar_expect_tx(&full[stage], tile_bytes);
+                tma_load_2d(smem_raw + (size_t)stage * tile_bytes, &tmap, cgroup * CW, row0 + t0, &full[stage]);
+            }
+            float my_cur, my_rem;
+            unsigned mask;
+            if (nrow == kCifRows)
+                cif_chain_chunk<true>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, mask);
+            else
+                cif_chain_chunk<false>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, mask);
+            sched[stage].cr[lane] = make_float2(my_cur, my_rem);
+            if (lane == 0) sched[stage].mask = mask;
+            __syncwarp();
+            if (rec && tt < a.T) {
+                const float2 cr = make_float2(my_cur, my_rem);
+                const int before = k + __popc(mask & ((1u << lane) - 1u));
+                const bool fired = (mask >> lane) & 1u;
+                a.cur[(size_t)b * a.T + tt] = cr.x;
+                a.rem[(size_t)b * a.T + tt] = cr.y;
+                a.sched[(size_t)b * a.T + tt] = (before << 1) | (fired ? 1 : 0);
+                if (fired && before < a.L) a.fire_t[(size_t)b * a.L + before] = tt;
+            }
+            k += __popc(mask);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);   // release: schedule visible, tile bytes pending
+            if (++stage == nstage) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        if (rec) {
+            for (int kk = k + lane; kk < a.L; kk += 32) a.fire_t[(size_t)b * a.L + kk] = -1;
+            if (lane == 0) {
+                a.n_fired[b] = k;
+                a.alpha_sum[b] = asum;
+                if (a.target_num != nullptr && a.qua_term != nullptr) {
+                    const float d = __fsub_rn(asum, a.target_num[b]);
+                    a.qua_term[b] = __fmul_rn(d, d);
+                }
+            }
+        }
+    } else {
+        // ===== data warps =====
+        const int col = cgroup * CW + warp * W + lane * VEC;
+        const bool col_ok = col < a.H;
+        float frame[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
+        int k = 0, stage = 0;
+        uint32_t phase = 0;
+        for (int c = 0; c < nchunk; ++c) {
+            const int nrow = min(kCifRows, a.T - c * kCifRows);
+            mbar_wait(&full[stage], phase);
+            const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * tile_bytes) + warp * W + lane * VEC;
+            const float2* cr = sched[stage].cr;
+            const unsigned mask = sched[stage].mask;
+            if (nrow == kCifRows)
+                cif_tile_full<VEC>(a, b, col, col_ok, tile, CW, cr, mask, frame, k);
+            else
+                cif_tile_partial<VEC>(a, b, col, col_ok, tile, CW, cr, mask, nrow, frame, k);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            if (++stage == nstage) {
+                stage = 0;
+                phase ^= 1u;
+            }
+        }
+        float z[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) z[i] = 0.0f;
+        if (col_ok)
+            for (int kk = k; kk < a.L; ++kk) vstore<VEC>(a.out + ((size_t)b * a.L + kk) * a.H + col, z);
+    }
 }
 
 // ---- backward -----------------------------------------------------------------
@@ -375,27 +568,60 @@ __global__ void __launch_bounds__(256) cif_bwd_rows_kernel(const CifBwdArgs a) {
     }
 }
 
-// g_alpha[t] = part[t] - sum_{s>t} gcf[s]    (one warp per utterance, reverse scan)
-__global__ void __launch_bounds__(128) cif_bwd_scan_kernel(float* g_alpha, const float* gcf, int B, int T) {
-    const int lane = threadIdx.x & 31;
-    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (b >= B) return;
+// g_alpha[t] = part[t] - sum_{s>t} gcf[s]    (one CTA per utterance; tiles of
+// 256 x 4 frames processed from the end, block-wide exclusive suffix scan per tile)
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 4;
+__global__ void __launch_bounds__(kScanThreads) cif_bwd_scan_kernel(float* g_alpha, const float* gcf, int B, int T) {
+    __shared__ float wsum[kScanThreads / 32];
+    __shared__ float tile_total;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     float* ga = g_alpha + (size_t)b * T;
     const float* gc = gcf + (size_t)b * T;
+    constexpr int TILE = kScanThreads * kScanItems;
     float carry = 0.0f;
-    for (int t0 = ((T - 1) / 32) * 32; t0 >= 0; t0 -= 32) {
-        const int t = t0 + lane;
-        const float v = (t < T) ? gc[t] : 0.0f;
-        float incl = v;   // inclusive suffix sum over lanes >= lane
+    for (int base = ((T - 1) / TILE) * TILE; base >= 0; base -= TILE) {
+        float v[kScanItems], p[kScanItems];
+        const int t0 = base + tid * kScanItems;
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const int t = t0 + i;
+            v[i] = (t < T) ? gc[t] : 0.0f;
+            p[i] = (t < T) ? ga[t] : 0.0f;
+        }
+        // thread-local suffix sums: s[i] = sum_{j>i} v[j]
+        float s[kScanItems];
+        float run = 0.0f;
+#pragma unroll
+        for (int i = kScanItems - 1; i >= 0; --i) {
+            s[i] = run;
+            run += v[i];
+        }
+        // warp-level exclusive suffix over thread totals
+        float incl = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const float y = __shfl_down_sync(0xffffffffu, incl, o);
             if (lane + o < 32) incl += y;
         }
-        float excl = __shfl_down_sync(0xffffffffu, incl, 1);
-        if (lane == 31) excl = 0.0f;
-        if (t < T) ga[t] = ga[t] - (carry + excl);
-        carry += __shfl_sync(0xffffffffu, incl, 0);
+        if (lane == 0) wsum[warp] = incl;
+        __syncthreads();
+        float after = incl - run;   // later threads of this warp
+        for (int w = warp + 1; w < kScanThreads / 32; ++w) after += wsum[w];
+        if (tid == 0) {
+            float tot = 0.0f;
+            for (int w = 0; w < kScanThreads / 32; ++w) tot += wsum[w];
+            tile_total = tot;
+        }
+#pragma unroll
+        for (int i = 0; i < kScanItems; ++i) {
+            const int t = t0 + i;
+            if (t < T) ga[t] = p[i] - (carry + after + s[i]);
+        }
+        __syncthreads();
+        carry += tile_total;
+        __syncthreads();
     }
 }
 
@@ -416,8 +642,8 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
 
     const bool vec4_ok = (H % 4 == 0) && aligned16(hidden) && (L == 0 || aligned16(out));
     int variant = get_opt("cif_fwd_variant");
-    if (variant == 0) variant = (vec4_ok && T >= 64) ? 2 : 1;
-    if (variant == 2 && !vec4_ok) variant = 1;
+    if (variant == 0) variant = (vec4_ok && T >= 64) ? 3 : 1;   // measured on B200: 3 > 2 > 1 for long T
+    if (variant >= 2 && !vec4_ok) variant = 1;
 
     // slice width: widest that still yields >= 2 warps per SM
     int width = get_opt("cif_fwd_width");
@@ -432,6 +658,42 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
         if (width == 64 && (long long)B * ((H + 63) / 64) < 2 * num_sms()) width = 32;
     }
     const int nslices = (H + width - 1) / width;
+
+    if (variant == 3) {
+        // warp-specialised: CTA columns = nw * width, at most 256 (TMA box limit)
+        int nw = get_opt("cif_fwd_rows");   // reused knob: data warps per CTA (0 = auto)
+        int wv = get_opt("cif_fwd_width");
+        if (wv != 32 && wv != 64 && wv != 128) wv = 64;   // float2 per lane: best measured (cfg 4)
+        if (nw <= 0) nw = 4;
+        while (nw * wv > 256) nw >>= 1;
+        while (nw > 1 && (nw - 1) * wv >= H) --nw;   // no idle data warps for narrow H
+        if (nw > 4) nw = 4;
+        const int cw = nw * wv;
+        const int ngroups = (H + cw - 1) / cw;
+        CUtensorMap tmap;
+        if (make_tmap_2d(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hidden, (uint64_t)B * T, (uint64_t)H,
+                         (uint64_t)H * 4, kCifRows, (uint32_t)cw, CU_TENSOR_MAP_SWIZZLE_NONE) != 0)
+            return 4;
+        int nstage = get_opt("cif_fwd_stages");
+        if (nstage <= 0) nstage = 4;
+        if (nstage > kCifMaxStages) nstage = kCifMaxStages;
+        const size_t smem = (size_t)nstage * kCifRows * cw * 4;
+        ASR_REQUIRE(B <= 65535, "asr_cif_fwd_f32: B=%d exceeds grid.y", B);
+        dim3 grid(ngroups, B);
+        const int threads = (nw + 1) * 32;
+        if (wv == 128) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_ws_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_ws_kernel<4><<<grid, threads, smem, st>>>(tmap, a, nstage, nw);
+        } else if (wv == 64) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_ws_kernel<2><<<grid, threads, smem, st>>>(tmap, a, nstage, nw);
+        } else {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(cif_fwd_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cif_fwd_ws_kernel<1><<<grid, threads, smem, st>>>(tmap, a, nstage, nw);
+        }
+        ASR_LAUNCH_CHECK();
+        return 0;
+    }
 
     if (variant == 2) {
         CUtensorMap tmap;
@@ -499,7 +761,7 @@ extern "C" int asr_cif_bwd_f32(const float* hidden, const float* g_out, const in
         cif_bwd_rows_kernel<1><<<blocks, 256, 0, st>>>(a);
     }
     ASR_LAUNCH_CHECK();
-    cif_bwd_scan_kernel<<<(B + 3) / 4, 128, 0, st>>>(g_alphas, static_cast<const float*>(ws), B, T);
+    cif_bwd_scan_kernel<<<B, kScanThreads, 0, st>>>(g_alphas, static_cast<const float*>(ws), B, T);
     ASR_LAUNCH_CHECK();
     return 0;
 }

@@ -4,26 +4,38 @@
 // (/root/reference/src/transformer/loss.py:39-43, src/ctcModel/loss.py:7-11):
 // blank = V-1, 0-padded [B,S] int64 targets, reduction='mean', zero_infinity=False.
 //
-// Two kernels per call, logits are read ONCE and the gradient written ONCE:
+// Three kernels per call; logits are read ONCE and the gradient written ONCE:
 //
-//  K1 ctc_rows    one CTA per frame row (b,t): the row lives in registers; one
-//                 pass gives the row log-sum-exp, the <= S+1 log-probs the lattice
-//                 needs (gathered into a compact [B,T,S+1] table) and - when a
-//                 gradient is wanted - the dense part of it, softmax * 1/(B*len).
-//                 Pure streaming: 4V bytes read + 4V bytes written per frame.
-//  K2 ctc_lattice one warp per utterance: log-space alpha sweep with warp-level
-//                 logsumexp (each lane owns NS consecutive lattice states, one
-//                 shuffle per step), checkpoints every K frames in shared memory,
-//                 then a backward beta sweep that recomputes alpha block by block
-//                 from the checkpoints.  The T x (2S+1) lattice never exists in
-//                 HBM.  The sparse part of the gradient, -occupancy(t,c)/(B*len),
-//                 is applied in place with fire-and-forget RED.ADD (one add per
-//                 address: deterministic).
+//  K1 ctc_rows     one CTA per frame row (b,t): the row lives in registers; one pass
+//                  gives the row log-sum-exp, the <= S+1 log-probs the lattice needs
+//                  (gathered into a compact [B,T,S+2] table, log2 domain) and - when a
+//                  gradient is wanted - the dense part of it, softmax * 1/(B*len).
+//                  Pure streaming: 4V bytes read + 4V bytes written per frame.
+//  K2 ctc_lattice  one warp per utterance: log-space (base 2) alpha sweep with
+//                  warp-level logsumexp - each lane owns NS consecutive lattice
+//                  states, one shuffle per step, 2-3 MUFU ops per state, no branches
+//                  - with checkpoints every K frames in shared memory, then a
+//                  backward beta sweep that recomputes alpha block by block from the
+//                  checkpoints.  The T x (2S+1) lattice never exists in HBM.  The
+//                  per-frame label occupancies overwrite the gathered table in place.
+//  K3 ctc_apply    one warp per frame row: g[t,c] -= occupancy(t,c)/(B*len) for the
+//                  <= S+1 classes of the utterance (repeated labels merged in a fixed
+//                  order): every address is touched once, deterministic, no atomics.
+//
+// Design notes from measurement on B200: a linear-domain lattice in
+// fp64 ran 2.7x slower than this MUFU version (dependent DADD/DMUL chains), and an
+// fp32 linear-domain lattice with per-frame power-of-two rescaling was faster but
+// loses probability mass: the dynamic range ACROSS states at one frame reaches
+// 2^-400 for T=1600, S=80, far beyond fp32 exponents.  Log space is the robust choice.
 #include "common.cuh"
 
 namespace asr {
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
+
+// Large finite stand-in for log(0): every lattice step stays branch-free (max / min /
+// MUFU), unreachable states simply sit near kNeg and exp2 of anything that far down is 0.
+constexpr float kNeg = -1.0e30f;
 
 struct CtcArgs {
     const float* logits;
@@ -33,7 +45,8 @@ struct CtcArgs {
     int B, T, V, S, blank, SP;
     float* nll;
     float* g;     // may be null
-    float* glp;   // [B,T,SP]: [0] = blank, [1+j] = label j
+    float* glp;   // [B,T,SP] log2-probabilities: [0] = blank, [1+j] = label j, [S+1] = kNeg
+    int* dlink;   // [B,S] repeated-label links: (next occurrence + 1) | (has earlier occurrence << 30)
 };
 
 // ---------------------------------------------------------------------------------
@@ -128,8 +141,9 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
     for (int j = tid; j <= Sb; j += NT) {
         int c = (j == 0) ? a.blank : (int)__ldg(a.targets + (size_t)b * a.S + (j - 1));
         c = min(max(c, 0), V - 1);
-        glp[j] = __ldg(x + c) - lse;
+        glp[j] = (__ldg(x + c) - lse) * 1.4426950408889634f;   // log2 domain for the lattice
     }
+    if (tid == NT - 1) glp[a.S + 1] = kNeg;   // "impossible" slot read by out-of-range lattice states
 
     if (GRAD) {
         const float coef = 1.0f / (Ssum * (float)a.B * (float)max(Sb, 1));
@@ -146,15 +160,29 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
 // ---------------------------------------------------------------------------------
 // K2: one warp per utterance.
 // ---------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// log2(2^a + 2^b): one EX2 + one LG2
 __device__ __forceinline__ float lse2(float a, float b) {
     const float m = fmaxf(a, b);
-    const float ms = (m == neg_inf()) ? 0.0f : m;
-    return ms + __logf(__expf(a - ms) + __expf(b - ms));
+    const float d = fminf(a, b) - m;
+    return m + lg2f(1.0f + ex2f(d));
 }
+// log2(2^a + 2^b + 2^c): two EX2 + one LG2 (the largest term contributes exactly 1)
 __device__ __forceinline__ float lse3(float a, float b, float c) {
-    const float m = fmaxf(fmaxf(a, b), c);
-    const float ms = (m == neg_inf()) ? 0.0f : m;
-    return ms + __logf(__expf(a - ms) + __expf(b - ms) + __expf(c - ms));
+    const float hi = fmaxf(a, b), lo2 = fminf(a, b);
+    const float m = fmaxf(hi, c);
+    const float lo = fminf(lo2, c);
+    const float mid = fmaxf(lo2, fminf(hi, c));
+    return m + lg2f((1.0f + ex2f(mid - m)) + ex2f(lo - m));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -166,57 +194,53 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Lane l owns states s = l*NS .. l*NS+NS-1 (even s = blank, odd s = label (s-1)/2).
 template <int NS>
 struct Lattice {
     static constexpr int NH = NS / 2;
-    int lab[NH];
-    int li[NH];     // index of this label's log-prob in a gathered row (0 when invalid)
-    bool vl[NH];    // label state valid
-    bool vb[NH];    // blank state valid
+    int li[NH];     // index of this label's log-prob in a gathered row (the kNeg slot when invalid)
+    int bi[NH];     // index of the blank log-prob (the kNeg slot when the blank state is invalid)
     bool skp[NH];   // label state may be entered from s-2
     bool skf[NH];   // label state may jump to s+2
 
-    // alpha_t from alpha_{t-1}; row = gathered log-probs of frame t
+    // alpha_t from alpha_{t-1}; row = gathered log2-probs of frame t
     __device__ __forceinline__ void alpha_step(float (&al)[NS], const float* row, int lane) const {
         float x = __shfl_up_sync(0xffffffffu, al[NS - 1], 1);
-        if (lane == 0) x = neg_inf();
-        const float lpb = row[0];
+        if (lane == 0) x = kNeg;
         float nw[NS];
-        nw[0] = vb[0] ? lse2(al[0], x) + lpb : neg_inf();
-        nw[1] = vl[0] ? lse3(al[1], al[0], skp[0] ? x : neg_inf()) + row[li[0]] : neg_inf();
+        nw[0] = lse2(al[0], x) + row[bi[0]];
+        nw[1] = lse3(al[1], al[0], skp[0] ? x : kNeg) + row[li[0]];
 #pragma unroll
         for (int q = 1; q < NH; ++q) {
-            nw[2 * q] = vb[q] ? lse2(al[2 * q], al[2 * q - 1]) + lpb : neg_inf();
-            nw[2 * q + 1] = vl[q] ? lse3(al[2 * q + 1], al[2 * q], skp[q] ? al[2 * q - 1] : neg_inf()) + row[li[q]]
-                                  : neg_inf();
+            nw[2 * q] = lse2(al[2 * q], al[2 * q - 1]) + row[bi[q]];
+            nw[2 * q + 1] = lse3(al[2 * q + 1], al[2 * q], skp[q] ? al[2 * q - 1] : kNeg) + row[li[q]];
         }
 #pragma unroll
         for (int r = 0; r < NS; ++r) al[r] = nw[r];
     }
     __device__ __forceinline__ void alpha_init(float (&al)[NS], const float* row, int lane) const {
 #pragma unroll
-        for (int r = 0; r < NS; ++r) al[r] = neg_inf();
+        for (int r = 0; r < NS; ++r) al[r] = kNeg;
         if (lane == 0) {
-            al[0] = row[0];
-            if (vl[0]) al[1] = row[1];
+            al[0] = row[bi[0]];
+            al[1] = row[li[0]];
         }
     }
-    // beta_t from beta_{t+1}; row = gathered log-probs of frame t
+    // beta_t from beta_{t+1}; row = gathered log2-probs of frame t
     __device__ __forceinline__ void beta_step(float (&be)[NS], const float* row, int lane) const {
         float y0 = __shfl_down_sync(0xffffffffu, be[0], 1);
         float y1 = __shfl_down_sync(0xffffffffu, be[1], 1);
         if (lane == 31) {
-            y0 = neg_inf();
-            y1 = neg_inf();
+            y0 = kNeg;
+            y1 = kNeg;
         }
-        const float lpb = row[0];
         float nw[NS];
 #pragma unroll
         for (int q = 0; q < NH; ++q) {
-            nw[2 * q] = vb[q] ? lse2(be[2 * q], be[2 * q + 1]) + lpb : neg_inf();
+            nw[2 * q] = lse2(be[2 * q], be[2 * q + 1]) + row[bi[q]];
             const float n1 = (q < NH - 1) ? be[(2 * q + 2) % NS] : y0;
             const float n2 = (q < NH - 1) ? be[(2 * q + 3) % NS] : y1;
-            nw[2 * q + 1] = vl[q] ? lse3(be[2 * q + 1], n1, skf[q] ? n2 : neg_inf()) + row[li[q]] : neg_inf();
+            nw[2 * q + 1] = lse3(be[2 * q + 1], n1, skf[q] ? n2 : kNeg) + row[li[q]];
         }
 #pragma unroll
         for (int r = 0; r < NS; ++r) be[r] = nw[r];
@@ -231,55 +255,51 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
     const int lane = threadIdx.x;
     const int b = blockIdx.x;
     const int T = a.T, SP = a.SP;
+    const int ZI = a.S + 1;   // slot of every row that holds kNeg
     const int Tb = min(max(__ldg(a.in_len + b), 0), T);
     const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
     const int nc_max = (T + K - 1) / K;
 
     // shared memory carve-up
-    float* lpbuf0 = reinterpret_cast<float*>(smem_raw);
+    float* lpbuf0 = reinterpret_cast<float*>(smem_raw);   // [K][SP] chunk of the gathered table
     float* lpbuf1 = lpbuf0 + (size_t)K * SP;
-    float* ckpt = lpbuf1 + (size_t)K * SP;            // [nc_max][NSL]
-    float* blk = ckpt + (size_t)nc_max * NSL;         // [K][NSL]
-    float* blpart = blk + (size_t)K * NSL;            // [K][33]
-    float* occ = blpart + (size_t)K * 33;             // [32*NH]
-    int* dupn = reinterpret_cast<int*>(occ + 32 * NH);   // [32*NH]
-    int* tgt = dupn + 32 * NH;                        // [32*NH]
+    float* ckpt = lpbuf1 + (size_t)K * SP;                // [nc_max][NSL] alpha checkpoints
+    float* blk = ckpt + (size_t)nc_max * NSL;             // [K][NSL] alpha of the block
+    float* blpart = blk + (size_t)K * NSL;                // [K][33] per-lane blank occupancy partials
+    int* tgt = reinterpret_cast<int*>(blpart + (size_t)K * 33);   // [32*NH]
 
     // ---- per-lane lattice description ------------------------------------------
     for (int j = lane; j < 32 * NH; j += 32) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
     __syncwarp();
     Lattice<NS> lat;
-    bool leader[NH];
-    int any_dup = 0;
+    bool vl[NH], vb[NH];
 #pragma unroll
     for (int q = 0; q < NH; ++q) {
         const int j = lane * NH + q;
-        lat.vl[q] = j < Sb;
-        lat.vb[q] = j <= Sb;
-        lat.lab[q] = lat.vl[q] ? min(max(tgt[j], 0), a.V - 1) : 0;
-        lat.li[q] = lat.vl[q] ? 1 + j : 0;
-        lat.skp[q] = lat.vl[q] && j > 0 && tgt[j] != tgt[j - 1];
-        lat.skf[q] = lat.vl[q] && (j + 1 < Sb) && tgt[j + 1] != tgt[j];
-        leader[q] = lat.vl[q];
-        int nxt = -1;
-        if (lat.vl[q]) {
-            for (int jj = 0; jj < j; ++jj)
-                if (tgt[jj] == tgt[j]) leader[q] = false;
+        vl[q] = j < Sb;
+        vb[q] = j <= Sb;
+        lat.li[q] = vl[q] ? 1 + j : ZI;
+        lat.bi[q] = vb[q] ? 0 : ZI;
+        lat.skp[q] = vl[q] && j > 0 && tgt[j] != tgt[j - 1];
+        lat.skf[q] = vl[q] && (j + 1 < Sb) && tgt[j + 1] != tgt[j];
+    }
+    // repeated-label links for K3 (it merges the occupancies of a class that occurs more than once)
+    if (a.g != nullptr) {
+        for (int j = lane; j < Sb; j += 32) {
+            int nxt = -1, earlier = 0;
+            for (int jj = 0; jj < j; ++jj) earlier |= (tgt[jj] == tgt[j]);
             for (int jj = Sb - 1; jj > j; --jj)
                 if (tgt[jj] == tgt[j]) nxt = jj;
+            a.dlink[(size_t)b * a.S + j] = (nxt + 1) | (earlier << 30);
         }
-        dupn[j] = nxt;
-        if (nxt >= 0) any_dup = 1;
     }
-    any_dup = __any_sync(0xffffffffu, any_dup);
-    __syncwarp();
 
     if (Tb == 0) {   // no frames: nll = 0 for an empty target, +inf otherwise (ATen)
         if (lane == 0) a.nll[b] = (Sb == 0) ? 0.0f : -neg_inf();
         return;
     }
 
-    const float* glp_b = a.glp + (size_t)b * T * SP;
+    float* glp_b = a.glp + (size_t)b * T * SP;
     const int nc = (Tb + K - 1) / K;
 
     auto load_chunk = [&](int c, float* dst) {
@@ -315,32 +335,35 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
         for (int r = 0; r < NS; ++r) ckpt[(size_t)c * NSL + lane * NS + r] = al[r];
         __syncwarp();
     }
-    // nll = -LSE(alpha_{T-1}(2S), alpha_{T-1}(2S-1))
-    float nll;
+    // nll = -LSE(alpha_{T-1}(2S), alpha_{T-1}(2S-1));  nll2 is the same in log2 units
+    float nll2;
+    bool feasible;
     {
         const float* fin = ckpt + (size_t)(nc - 1) * NSL;
         const float a_end = fin[2 * Sb];
-        const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : neg_inf();
-        nll = -lse2(a_end, a_lab);
-        if (lane == 0) a.nll[b] = nll;
+        const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : kNeg;
+        const float ll2 = lse2(a_end, a_lab);
+        feasible = ll2 > -1.0e29f;
+        nll2 = -ll2;
+        if (lane == 0) a.nll[b] = feasible ? nll2 * 0.6931471805599453f : -neg_inf();
     }
     if (a.g == nullptr) return;
 
-    float* g_b = a.g + (size_t)b * T * a.V;
-    if (!(nll < -neg_inf())) {
+    if (!feasible) {
         // infeasible alignment (or NaN input): the reference's gradient is NaN on every
         // valid frame row (log_softmax backward spreads the NaN), zero_infinity=False
+        float* g_b = a.g + (size_t)b * T * a.V;
         const float qnan = __int_as_float(0x7fc00000);
         const size_t n = (size_t)Tb * a.V;
         for (size_t i = lane; i < n; i += 32) g_b[i] = qnan;
+        for (size_t i = lane; i < (size_t)Tb * SP; i += 32) glp_b[i] = 0.0f;   // nothing for K3 to apply
         return;
     }
-    const float scale = 1.0f / ((float)a.B * (float)max(Sb, 1));
 
-    // ---- sweep 2: beta backwards, alpha recomputed per chunk ----------------------
+    // ---- sweep 2: beta backwards, alpha recomputed per chunk, occupancy out -------
     float be[NS];
 #pragma unroll
-    for (int r = 0; r < NS; ++r) be[r] = neg_inf();
+    for (int r = 0; r < NS; ++r) be[r] = kNeg;
     load_chunk(nc - 1, ((nc - 1) & 1) ? lpbuf1 : lpbuf0);
     for (int c = nc - 1; c >= 0; --c) {
         float* cur = (c & 1) ? lpbuf1 : lpbuf0;
@@ -375,42 +398,25 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
 #pragma unroll
                 for (int q = 0; q < NH; ++q) {
                     const int j = lane * NH + q;
-                    be[2 * q] = (j == Sb) ? row[0] : neg_inf();
-                    be[2 * q + 1] = (j == Sb - 1) ? row[lat.li[q]] : neg_inf();
+                    be[2 * q] = (j == Sb) ? row[0] : kNeg;
+                    be[2 * q + 1] = (j == Sb - 1) ? row[lat.li[q]] : kNeg;
                 }
             } else {
                 lat.beta_step(be, row, lane);
             }
+            // occupancy(t,s) = exp2(alpha + beta - lp + nll); both alpha and beta include lp_t
             const float lpb = row[0];
             float bsum = 0.0f;
-            float ov[NH];
+            float* orow = glp_b + (size_t)t * SP;
 #pragma unroll
             for (int q = 0; q < NH; ++q) {
                 const float ab = blk[(size_t)i * NSL + lane * NS + 2 * q] + be[2 * q];
-                if (lat.vb[q]) bsum += __expf(ab - lpb + nll);
+                bsum += vb[q] ? ex2f((ab - lpb) + nll2) : 0.0f;
                 const float al_l = blk[(size_t)i * NSL + lane * NS + 2 * q + 1] + be[2 * q + 1];
-                ov[q] = lat.vl[q] ? __expf(al_l - row[lat.li[q]] + nll) : 0.0f;
+                const float ov = ex2f((al_l - row[lat.li[q]]) + nll2);
+                if (vl[q]) orow[1 + lane * NH + q] = ov;   // per label position; K3 merges repeats
             }
             blpart[i * 33 + lane] = bsum;
-            float* grow = g_b + (size_t)t * a.V;
-            if (any_dup) {
-#pragma unroll
-                for (int q = 0; q < NH; ++q) occ[lane * NH + q] = ov[q];
-                __syncwarp();
-#pragma unroll
-                for (int q = 0; q < NH; ++q) {
-                    if (leader[q]) {
-                        float vsum = ov[q];
-                        for (int jj = dupn[lane * NH + q]; jj >= 0; jj = dupn[jj]) vsum += occ[jj];
-                        atomicAdd(grow + lat.lab[q], -vsum * scale);
-                    }
-                }
-                __syncwarp();
-            } else {
-#pragma unroll
-                for (int q = 0; q < NH; ++q)
-                    if (lat.vl[q]) atomicAdd(grow + lat.lab[q], -ov[q] * scale);
-            }
         }
         __syncwarp();
         // blank column: one lane per frame of the chunk sums the 32 partials
@@ -418,7 +424,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
             float sacc = 0.0f;
 #pragma unroll 8
             for (int l = 0; l < 32; ++l) sacc += blpart[i * 33 + l];
-            atomicAdd(g_b + (size_t)(t0 + i) * a.V + a.blank, -sacc * scale);
+            glp_b[(size_t)(t0 + i) * SP] = sacc;
         }
         __syncwarp();
     }
@@ -428,7 +434,42 @@ static size_t lattice_smem_bytes(int NS, int K, int T, int SP) {
     const int NH = NS / 2, NSL = 32 * NS;
     const size_t nc = (size_t)(T + K - 1) / K;
     size_t f = 2 * (size_t)K * SP + nc * NSL + (size_t)K * NSL + (size_t)K * 33 + 32 * NH;
-    return f * 4 + 2 * (size_t)32 * NH * 4;
+    return f * 4;
+}
+
+// ---------------------------------------------------------------------------------
+// K3: g[b,t,c] -= occupancy(b,t,c) / (B * len_b)  for the <= S+1 classes of the utterance.
+// One warp per valid frame row.  A class that occurs several times in the target is
+// handled by its first occurrence, which walks the link chain and sums the others in a
+// fixed order, so every address is touched exactly once (deterministic, no atomics).
+// Occupancies below 1e-12 are skipped: they cannot change an fp32 gradient whose dense
+// part is softmax/(B*len) by more than 1e-12 of the gradient scale.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ctc_apply_kernel(const CtcArgs a) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)a.B * a.T) return;
+    const int b = (int)(row / a.T);
+    const int t = (int)(row - (long long)b * a.T);
+    const int Tb = min(max(__ldg(a.in_len + b), 0), a.T);
+    if (t >= Tb) return;
+    const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
+    const float scale = 1.0f / ((float)a.B * (float)max(Sb, 1));
+    const float* orow = a.glp + (size_t)row * a.SP;
+    const int* dl = a.dlink + (size_t)b * a.S;
+    float* grow = a.g + (size_t)row * a.V;
+    for (int j = lane; j <= Sb; j += 32) {
+        float v = orow[j];
+        int c = a.blank;
+        if (j > 0) {
+            const int link = __ldg(dl + j - 1);
+            if (link >> 30) continue;   // a repeat: its first occurrence carries the sum
+            for (int nx = (link & 0x3fffffff) - 1; nx >= 0; nx = (__ldg(dl + nx) & 0x3fffffff) - 1) v += orow[1 + nx];
+            c = (int)__ldg(a.targets + (size_t)b * a.S + (j - 1));
+            c = min(max(c, 0), a.V - 1);
+        }
+        if (!(fabsf(v) < 1.0e-12f)) grow[c] -= v * scale;   // NaN goes through
+    }
 }
 
 // ---------------------------------------------------------------------------------
@@ -446,11 +487,13 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* g, size_t n, 
 using namespace asr;
 
 static inline int round_up4(int x) { return (x + 3) & ~3; }
+// row stride of the gathered table: blank + S labels + one always-zero slot, 16-byte rows
+static inline int table_stride(int S) { return round_up4(S + 2); }
 
 extern "C" size_t asr_ctc_workspace_bytes(int B, int T, int V, int S) {
     (void)V;
     if (B <= 0 || T <= 0 || S < 0) return 0;
-    return (size_t)B * T * round_up4(S + 1) * sizeof(float) + 256;
+    return (size_t)B * T * table_stride(S) * sizeof(float) + (size_t)B * (S + 1) * sizeof(int) + 512;
 }
 
 template <int NT, bool GRAD>
@@ -483,7 +526,7 @@ static int launch_rows_nt(const CtcArgs& a, long long rows, cudaStream_t st) {
 }
 
 template <int NS>
-static int launch_lattice(const CtcArgs& a, cudaStream_t st) {
+static int launch_lattice(const CtcArgs& a, int stages, cudaStream_t st) {
     int K = 32;
     size_t smem = lattice_smem_bytes(NS, K, a.T, a.SP);
     while (smem > 200 * 1024 && K < 256) {
@@ -493,22 +536,29 @@ static int launch_lattice(const CtcArgs& a, cudaStream_t st) {
     ASR_REQUIRE(smem <= 227 * 1024, "asr_ctc: T=%d S=%d needs %zu bytes of shared memory for the lattice (max 232448)",
                 a.T, a.S, smem);
     ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ctc_lattice_kernel<NS><<<a.B, 32, smem, st>>>(a, K);
-    ASR_LAUNCH_CHECK();
+    if (stages & 2) {
+        ctc_lattice_kernel<NS><<<a.B, 32, smem, st>>>(a, K);
+        ASR_LAUNCH_CHECK();
+    }
+    if ((stages & 4) && a.g != nullptr) {
+        const long long rows = (long long)a.B * a.T;
+        ctc_apply_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a);
+        ASR_LAUNCH_CHECK();
+    }
     return 0;
 }
 
-extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
-                                   int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
-                                   size_t ws_bytes, void* stream) {
-    ASR_REQUIRE(B > 0 && T > 0 && V > 1 && S >= 0, "asr_ctc_fwd_bwd_f32: bad shape B=%d T=%d V=%d S=%d", B, T, V, S);
-    ASR_REQUIRE(logits && in_len && tgt_len && nll && ws && (S == 0 || targets), "asr_ctc_fwd_bwd_f32: null pointer");
-    ASR_REQUIRE(blank >= 0 && blank < V, "asr_ctc_fwd_bwd_f32: blank %d out of range", blank);
-    ASR_REQUIRE(ws_bytes >= asr_ctc_workspace_bytes(B, T, V, S), "asr_ctc_fwd_bwd_f32: workspace too small (%zu < %zu)",
+extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                  size_t ws_bytes, int stages, void* stream) {
+    ASR_REQUIRE(B > 0 && T > 0 && V > 1 && S >= 0, "asr_ctc: bad shape B=%d T=%d V=%d S=%d", B, T, V, S);
+    ASR_REQUIRE(logits && in_len && tgt_len && nll && ws && (S == 0 || targets), "asr_ctc: null pointer");
+    ASR_REQUIRE(blank >= 0 && blank < V, "asr_ctc: blank %d out of range", blank);
+    ASR_REQUIRE(ws_bytes >= asr_ctc_workspace_bytes(B, T, V, S), "asr_ctc: workspace too small (%zu < %zu)",
                 ws_bytes, asr_ctc_workspace_bytes(B, T, V, S));
-    ASR_REQUIRE(V <= 65000, "asr_ctc_fwd_bwd_f32: V=%d > 65000 not supported", V);
-    ASR_REQUIRE(2 * S + 1 <= 32 * 16, "asr_ctc_fwd_bwd_f32: S=%d > 255 labels not supported", S);
-    ASR_REQUIRE((long long)B * T < (1ll << 31) - 1, "asr_ctc_fwd_bwd_f32: B*T too large");
+    ASR_REQUIRE(V <= 65000, "asr_ctc: V=%d > 65000 not supported", V);
+    ASR_REQUIRE(2 * S + 1 <= 32 * 16, "asr_ctc: S=%d > 255 labels not supported", S);
+    ASR_REQUIRE((long long)B * T < (1ll << 31) - 1, "asr_ctc: B*T too large");
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
@@ -518,23 +568,33 @@ extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, 
     a.in_len = in_len;
     a.tgt_len = tgt_len;
     a.B = B; a.T = T; a.V = V; a.S = S; a.blank = blank;
-    a.SP = round_up4(S + 1);
+    a.SP = table_stride(S);
     a.nll = nll;
     a.g = g_logits;
     uintptr_t w = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
     a.glp = reinterpret_cast<float*>(w);
+    a.dlink = reinterpret_cast<int*>(a.glp + (size_t)B * T * a.SP);
 
-    const long long rows = (long long)B * T;
-    int rc = g_logits ? launch_rows_nt<true>(a, rows, st) : launch_rows_nt<false>(a, rows, st);
-    if (rc != 0) return rc;
+    if (stages & 1) {
+        const long long rows = (long long)B * T;
+        int rc = g_logits ? launch_rows_nt<true>(a, rows, st) : launch_rows_nt<false>(a, rows, st);
+        if (rc != 0) return rc;
+    }
+    if ((stages & 6) == 0) return 0;
 
     const int states = 2 * S + 1;
-    if (states <= 64) return launch_lattice<2>(a, st);
-    if (states <= 128) return launch_lattice<4>(a, st);
-    if (states <= 192) return launch_lattice<6>(a, st);
-    if (states <= 256) return launch_lattice<8>(a, st);
-    if (states <= 384) return launch_lattice<12>(a, st);
-    return launch_lattice<16>(a, st);
+    if (states <= 64) return launch_lattice<2>(a, stages, st);
+    if (states <= 128) return launch_lattice<4>(a, stages, st);
+    if (states <= 192) return launch_lattice<6>(a, stages, st);
+    if (states <= 256) return launch_lattice<8>(a, stages, st);
+    if (states <= 384) return launch_lattice<12>(a, stages, st);
+    return launch_lattice<16>(a, stages, st);
+}
+
+extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                   int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                   size_t ws_bytes, void* stream) {
+    return asr_ctc_stages_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, 7, stream);
 }
 
 extern "C" int asr_scale_inplace_f32(float* g, size_t n, const float* scale_dev, void* stream) {

@@ -39,8 +39,9 @@ const char* asr_last_error(void);
 int         asr_device_ok(void);
 /* Tuning knobs (kernel variants; all variants are sm_100a CUDA).  Unknown keys
  * return non-zero.  Keys: "cif_fwd_variant" (0 = auto, 1 = plain loads,
- * 2 = TMA pipeline), "cif_fwd_width" (0 = auto, 32/64/128 floats per warp),
- * "cif_fwd_stages" (0 = auto), "ctc_rec_variant" (0 = auto). */
+ * 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline), "cif_fwd_width"
+ * (0 = auto, 32/64/128 floats per warp), "cif_fwd_stages" (0 = auto),
+ * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
 /* Number of kernels launched by this library since load (all streams). */
@@ -105,8 +106,9 @@ int asr_cif_bwd_f32(const float* hidden, const float* g_out,
  *                          exactly 0 for t >= in_len[b]; NaN rows for an
  *                          infeasible utterance (zero_infinity=False semantics)
  * ws: asr_ctc_workspace_bytes(B,T,V,S) bytes of device scratch.  It holds the
- *     gathered log-probabilities [B,T,S+1]; the alpha/beta lattice never leaves
- *     shared memory.
+ *     gathered log-probabilities [B,T,S+2] (overwritten in place by the per-frame
+ *     label occupancies) and the repeated-label links [B,S]; the alpha/beta
+ *     lattice itself never leaves shared memory.
  */
 size_t asr_ctc_workspace_bytes(int B, int T, int V, int S);
 int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
@@ -114,6 +116,15 @@ int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
                         int B, int T, int V, int S, int blank,
                         float* nll, float* g_logits,
                         void* ws, size_t ws_bytes, void* stream);
+/* Same call split into its three kernels, for per-kernel timing with CUDA events
+ * (bench.py): stages is a bit mask, 1 = K1 row pass (log-sum-exp, gather, dense
+ * gradient), 2 = K2 lattice (alpha/beta, nll, occupancies), 4 = K3 sparse gradient
+ * update.  Stages must be issued in order on one stream; 7 = the call above. */
+int asr_ctc_stages_f32(const float* logits, const int64_t* targets,
+                       const int* in_len, const int* tgt_len,
+                       int B, int T, int V, int S, int blank,
+                       float* nll, float* g_logits,
+                       void* ws, size_t ws_bytes, int stages, void* stream);
 /* In-place g *= *scale_dev, skipped on the device when *scale_dev == 1.0f
  * (autograd's incoming gradient for the loss; it is 1 in the reference's
  * solvers, transformer/solver.py:153). */

@@ -11,23 +11,24 @@ pytestmark = pytest.mark.gpu
 
 CIF = load_golden("cif")
 CASES = sorted({k.split("_")[0] for k in CIF.files})
-# (variant, width): 1 = plain loads, 2 = TMA pipeline
-VARIANTS = [(1, 32), (1, 64), (1, 128), (2, 32), (2, 64), (2, 128), (0, 0)]
+# (variant, width): 1 = plain loads, 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline
+VARIANTS = [(1, 32), (1, 64), (1, 128), (2, 32), (2, 64), (2, 128), (3, 32), (3, 64), (3, 128), (0, 0)]
 
 
 @pytest.fixture(autouse=True)
 def _reset_options():
     lib = pkg("_lib")
     yield
-    for k in ("cif_fwd_variant", "cif_fwd_width", "cif_fwd_stages"):
+    for k in ("cif_fwd_variant", "cif_fwd_width", "cif_fwd_stages", "cif_fwd_rows"):
         lib.set_option(k, 0)
 
 
-def _set(variant, width, stages=0):
+def _set(variant, width, stages=0, nw=0):
     lib = pkg("_lib")
     lib.set_option("cif_fwd_variant", variant)
     lib.set_option("cif_fwd_width", width)
     lib.set_option("cif_fwd_stages", stages)
+    lib.set_option("cif_fwd_rows", nw)
 
 
 def _run(hidden, alphas, thr, L, g_out=None):
@@ -93,9 +94,9 @@ def test_cpu_tensor_is_rejected():
 
 @pytest.mark.parametrize("B,T,H,n", [(8, 21, 512, 14), (5, 167, 512, 20), (3, 301, 320, 40), (2, 97, 100, 9),
                                      (2, 64, 37, 9), (1, 700, 256, 60)])
-@pytest.mark.parametrize("variant,width", [(1, 0), (2, 0), (2, 128)])
+@pytest.mark.parametrize("variant,width", [(1, 0), (2, 0), (2, 128), (3, 0), (3, 64), (3, 128)])
 def test_random_vs_oracle(B, T, H, n, variant, width):
-    if variant == 2 and H % 4:
+    if variant >= 2 and H % 4:
         pytest.skip("TMA path needs 16-byte rows")
     _set(variant, width)
     hidden, alphas = make_cif_inputs(B, T, H, n, seed=1234 + T)
@@ -117,6 +118,9 @@ def test_stage_counts_agree():
     outs = []
     for stages in (1, 2, 3, 6, 12):
         _set(2, 64, stages)
+        outs.append(_run(to_np(hidden), to_np(alphas), 0.95, 60)["out"])
+    for stages, nw in ((1, 1), (2, 4), (3, 2), (8, 4), (12, 1)):
+        _set(3, 32, stages, nw)
         outs.append(_run(to_np(hidden), to_np(alphas), 0.95, 60)["out"])
     for o in outs[1:]:
         np.testing.assert_array_equal(bits(o), bits(outs[0]))
@@ -140,6 +144,10 @@ def test_cfg4_long_utterance_stress():
     _set(1, 0)
     out_plain = ops.cif(hidden, alphas, 0.95, L=L)
     assert torch.equal(out.detach(), out_plain)
+    _set(3, 0)
+    out_ws, aux_ws = ops.cif(hidden, alphas, 0.95, L=L, return_aux=True)
+    assert torch.equal(out.detach(), out_ws)
+    assert torch.equal(aux["fire_t"], aux_ws["fire_t"]) and torch.equal(aux["n_fired"], aux_ws["n_fired"])
     # slice vs oracle
     sel = [0, 31, 63]
     ref_out, ref_fire, ref_n = oracle.cif_forward(to_np(hidden[sel]), to_np(alphas[sel]), 0.95, L=L)

@@ -54,10 +54,15 @@ def test_golden(case):
         assert np.isinf(float(loss)) and float(loss) > 0
     g = to_np(grad)
     gscale = np.nanmax(np.abs(ref_grad)) + 1e-30
+    # the golden vector is the reference's own fp32 result; its distance from the fp64 oracle is
+    # the reference's rounding noise, which no other fp32 implementation can be asked to reproduce
+    _, _, o_grad = oracle.ctc_loss_and_grad(CTC[case + "_logits"], CTC[case + "_targets"], CTC[case + "_in_len"])
     for b in range(g.shape[0]):
         if fin[b]:
-            # fp32 rtol 1e-5 relative to the gradient scale of the tensor
-            assert np.abs(g[b] - ref_grad[b]).max() <= 1e-5 * gscale + 1e-5 * np.abs(ref_grad[b]).max()
+            ref_noise = np.abs(ref_grad[b] - o_grad[b]).max()
+            # fp32 rtol 1e-5 of the gradient scale
+            assert np.abs(g[b] - ref_grad[b]).max() <= 1e-5 * gscale + 2 * ref_noise
+            assert np.abs(g[b] - o_grad[b]).max() <= 1e-5 * gscale + ref_noise
         else:
             np.testing.assert_array_equal(np.isnan(g[b]), np.isnan(ref_grad[b]))
         assert not g[b, int(CTC[case + "_in_len"][b]):].any()

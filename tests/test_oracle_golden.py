@@ -153,3 +153,29 @@ def test_masks():
     np.testing.assert_array_equal(oracle.get_attn_pad_mask(g["lens"], 3), g["attn_pad_mask"])
     np.testing.assert_array_equal(oracle.get_subsequent_mask(g["seq"]), g["subsequent_mask"])
     np.testing.assert_array_equal(oracle.get_attn_key_pad_mask(g["seq"], g["seq"], 0), g["key_pad_mask"])
+
+
+# ---- the torch-CPU port used as the timed CPU baseline must agree with the same goldens ----
+def test_torch_port_matches_goldens():
+    import torch
+    from oracle import torch_port
+    for case in ("a", "c", "d"):
+        hidden, alphas = torch.as_tensor(CIF[case + "_hidden"]), torch.as_tensor(CIF[case + "_alphas"])
+        out = torch_port.cif_loop(hidden, alphas, float(CIF[case + "_thr"]))
+        assert torch.equal(out, torch.as_tensor(CIF[case + "_out"]))
+    for case in ("a", "b", "f"):
+        loss = torch_port.ctc_mean_loss(torch.as_tensor(CTC[case + "_logits"]), torch.as_tensor(CTC[case + "_in_len"]),
+                                        torch.as_tensor(CTC[case + "_targets"]))
+        np.testing.assert_allclose(loss.numpy(), CTC[case + "_loss"], rtol=1e-6)
+    w = {k: torch.as_tensor(v) for k, v in _weights().items()}
+    for case in MHA_CASES:
+        mask = MHA[case + "_mask"]
+        mask = None if mask.size == 0 else torch.as_tensor(mask.astype(bool))
+        q, kv = torch.as_tensor(MHA[case + "_q"]), torch.as_tensor(MHA[case + "_kv"])
+        y, attn = torch_port.attention_block(q, kv, kv, w, 2, mask)
+        np.testing.assert_allclose(y.numpy(), MHA[case + "_y"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(attn.numpy(), MHA[case + "_attn"], rtol=1e-5, atol=1e-7)
+    g = load_golden("cif_glue")
+    _num, num, scaled = torch_port.scale_alphas(torch.as_tensor(g["alpha"]), torch.as_tensor(g["targets"]),
+                                                torch.as_tensor(g["rand"]))
+    assert torch.equal(scaled, torch.as_tensor(g["scaled"])) and torch.equal(_num, torch.as_tensor(g["_num"]))

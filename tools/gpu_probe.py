@@ -1,7 +1,12 @@
 #!/usr/bin/env python3
-"""Quick on-GPU timing probe of the hot-path kernels (CUDA events, L2 flushed
-between iterations).  Writes gpurun_out/probe_<tag>.json.  Not a benchmark of
-record - bench.py is; this is the builder's iteration tool."""
+"""Quick on-GPU timing probe of the hot-path kernels through the C ABI with
+preallocated buffers (CUDA events on the launching stream, L2 flushed between
+iterations).  Writes gpurun_out/probe_<tag>.json.  Not a benchmark of record -
+bench.py is; this is the builder's iteration tool.
+
+    python tools/gpu_probe.py <tag> [cif] [ctc] [once]
+`once` runs every kernel exactly once (for an ncu launch list)."""
+import ctypes
 import json
 import os
 import sys
@@ -17,7 +22,10 @@ from helpers import make_cif_inputs, make_ctc_inputs  # noqa: E402
 
 ops = asr_b200.ops
 lib = asr_b200._lib
+L = lib.lib()
+ptr, sp, check = lib.ptr, lib.stream_ptr, lib.check
 
+ONCE = "once" in sys.argv
 _flush = None
 
 
@@ -29,6 +37,10 @@ def flush_l2():
 
 
 def timeit(fn, iters=5, warmup=2):
+    if ONCE:
+        fn()
+        torch.cuda.synchronize()
+        return 0.0, 0.0
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
@@ -45,67 +57,83 @@ def timeit(fn, iters=5, warmup=2):
     return ts[len(ts) // 2], ts[0]
 
 
+class CifBuffers:
+    def __init__(self, B, T, H, n, seed=1238):
+        self.B, self.T, self.H = B, T, H
+        self.hidden, self.alphas = make_cif_inputs(B, T, H, n, seed=seed)
+        self.L = ops.cif_label_len(self.alphas)
+        d = "cuda"
+        self.out = torch.empty(B, self.L, H, device=d)
+        self.fire_t = torch.empty(B, self.L, dtype=torch.int32, device=d)
+        self.n_fired = torch.empty(B, dtype=torch.int32, device=d)
+        self.cur = torch.empty(B, T, device=d)
+        self.rem = torch.empty(B, T, device=d)
+        self.sched = torch.empty(B, T, dtype=torch.int32, device=d)
+        self.asum = torch.empty(B, device=d)
+        self.g_out = torch.randn(B, self.L, H, device=d)
+        self.g_hidden = torch.empty(B, T, H, device=d)
+        self.g_alpha = torch.empty(B, T, device=d)
+        self.ws = torch.empty(B * T, device=d)
+        self.fwd_bytes = 4 * (B * T * H + B * T) + 4 * B * self.L * H
+        self.bwd_bytes = 4 * (2 * B * T * H + B * self.L * H + 4 * B * T)
+
+    def fwd(self):
+        check(L.asr_cif_fwd_f32(ptr(self.hidden), ptr(self.alphas), 0.95, self.B, self.T, self.H, self.L,
+                                ptr(self.out), ptr(self.fire_t), ptr(self.n_fired), ptr(self.cur), ptr(self.rem),
+                                ptr(self.sched), ptr(self.asum), None, None, sp()), "cif_fwd")
+
+    def bwd(self):
+        check(L.asr_cif_bwd_f32(ptr(self.hidden), ptr(self.g_out), ptr(self.n_fired), ptr(self.cur), ptr(self.rem),
+                                ptr(self.sched), self.B, self.T, self.H, self.L, ptr(self.g_hidden),
+                                ptr(self.g_alpha), ptr(self.ws), self.ws.numel() * 4, sp()), "cif_bwd")
+
+
 def probe_cif(res, B=64, T=3000, H=512, n=300):
-    hidden, alphas = make_cif_inputs(B, T, H, n, seed=1238)
-    L = ops.cif_label_len(alphas)
-    fwd_bytes = 4 * (B * T * H + B * T) + 4 * B * L * H
-    bwd_bytes = 4 * (2 * B * T * H + B * L * H + 4 * B * T)
-    for variant, width, stages in [(1, 128, 0), (1, 64, 0), (1, 32, 0), (2, 128, 6), (2, 64, 6), (2, 32, 6),
-                                   (2, 64, 3), (2, 64, 12), (2, 128, 3), (2, 128, 10), (2, 32, 12)]:
+    c = CifBuffers(B, T, H, n)
+    combos = [(2, 0, 0, 0), (3, 32, 4, 4)] if ONCE else [(2, 64, 3, 0), (3, 32, 4, 4), (3, 32, 2, 4), (3, 32, 8, 4), (3, 64, 4, 2), (3, 64, 4, 4), (3, 128, 4, 1), (3, 128, 4, 2), (3, 64, 8, 2), (3, 32, 4, 2), (3, 32, 6, 3),
+                                       (0, 0, 0, 0)]
+    for variant, width, stages, nw in combos:
+        lib.set_option("cif_fwd_rows", nw)
         lib.set_option("cif_fwd_variant", variant)
         lib.set_option("cif_fwd_width", width)
         lib.set_option("cif_fwd_stages", stages)
-        med, best = timeit(lambda: ops.cif(hidden, alphas, 0.95, L=L, check_overflow=False))
-        res.append({"kernel": "cif_fwd", "variant": variant, "width": width, "stages": stages, "B": B, "T": T, "H": H,
-                    "L": L, "ms": med * 1e3, "best_ms": best * 1e3, "GBps": fwd_bytes / med / 1e9})
+        med, best = timeit(c.fwd)
+        res.append({"kernel": "cif_fwd", "variant": variant, "width": width, "stages": stages, "nw": nw, "B": B, "T": T, "H": H,
+                    "L": c.L, "us": med * 1e6, "best_us": best * 1e6, "GBps": c.fwd_bytes / max(med, 1e-9) / 1e9})
         print(res[-1], flush=True)
-    for k in ("cif_fwd_variant", "cif_fwd_width", "cif_fwd_stages"):
+    for k in ("cif_fwd_variant", "cif_fwd_width", "cif_fwd_stages", "cif_fwd_rows"):
         lib.set_option(k, 0)
-    h = hidden.clone().requires_grad_(True)
-    a = alphas.clone().requires_grad_(True)
-    out = ops.cif(h, a, 0.95, L=L, check_overflow=False)
-    g_out = torch.randn_like(out)
-    med, best = timeit(lambda: torch.autograd.grad(out, [h, a], g_out, retain_graph=True))
-    res.append({"kernel": "cif_bwd", "B": B, "T": T, "H": H, "L": L, "ms": med * 1e3, "best_ms": best * 1e3,
-                "GBps": bwd_bytes / med / 1e9})
+    c.fwd()
+    med, best = timeit(c.bwd)
+    res.append({"kernel": "cif_bwd", "B": B, "T": T, "H": H, "L": c.L, "us": med * 1e6, "best_us": best * 1e6,
+                "GBps": c.bwd_bytes / max(med, 1e-9) / 1e9})
     print(res[-1], flush=True)
 
 
 def probe_ctc(res, shapes):
+    V = 4233
     for (B, T, S) in shapes:
-        V = 4233
         logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=1236)
+        tgt_len = targets.ne(0).sum(1).to(torch.int32)
         valid = int(in_len.sum().item())
         alg = 8 * V * valid
-        lg = logits.requires_grad_(True)
+        nll = torch.empty(B, device="cuda")
+        g = torch.empty_like(logits)
+        wsb = L.asr_ctc_workspace_bytes(B, T, V, S)
+        ws = torch.empty(wsb // 4 + 1, device="cuda")
 
-        def step():
-            loss = ops.ctc_loss(lg, in_len, targets)
-            loss.backward()
-            lg.grad = None
-        med, best = timeit(step, iters=4, warmup=2)
-        res.append({"kernel": "ctc_fwd_bwd", "B": B, "T": T, "S": S, "V": V, "valid_frames": valid, "ms": med * 1e3,
-                    "best_ms": best * 1e3, "GBps_alg": alg / med / 1e9})
+        def run(grad):
+            check(L.asr_ctc_fwd_bwd_f32(ptr(logits), ptr(targets), ptr(in_len), ptr(tgt_len), B, T, V, S, V - 1,
+                                        ptr(nll), ptr(g) if grad else None, ptr(ws), wsb, sp()), "ctc")
+        med, best = timeit(lambda: run(True), iters=4)
+        res.append({"kernel": "ctc_fwd_bwd", "B": B, "T": T, "S": S, "V": V, "valid_frames": valid, "us": med * 1e6,
+                    "best_us": best * 1e6, "GBps_alg": alg / max(med, 1e-9) / 1e9})
         print(res[-1], flush=True)
-        with torch.no_grad():
-            med, best = timeit(lambda: ops.ctc_loss(logits.detach(), in_len, targets), iters=4, warmup=2)
-        res.append({"kernel": "ctc_fwd_only", "B": B, "T": T, "S": S, "V": V, "ms": med * 1e3,
-                    "GBps_alg": 4 * V * valid / med / 1e9})
+        med, best = timeit(lambda: run(False), iters=4)
+        res.append({"kernel": "ctc_fwd_only", "B": B, "T": T, "S": S, "V": V, "us": med * 1e6,
+                    "GBps_alg": 4 * V * valid / max(med, 1e-9) / 1e9})
         print(res[-1], flush=True)
-        # torch's own path (what the reference calls) for comparison
-        import torch.nn.functional as F
-        lg2 = logits.detach().clone().requires_grad_(True)
-        tl = targets.ne(0).int().sum(1)
-
-        def ref_step():
-            lp = F.log_softmax(lg2, dim=-1).transpose(0, 1)
-            loss = F.ctc_loss(lp, targets, in_len, tl, blank=V - 1)
-            loss.backward()
-            lg2.grad = None
-        med, best = timeit(ref_step, iters=3, warmup=1)
-        res.append({"kernel": "torch_ctc_fwd_bwd", "B": B, "T": T, "S": S, "ms": med * 1e3, "GBps_alg": alg / med / 1e9})
-        print(res[-1], flush=True)
-        del logits, lg, lg2
+        del logits, g
         torch.cuda.empty_cache()
 
 
@@ -114,15 +142,19 @@ def main():
     res = []
     t0 = time.time()
     print(torch.cuda.get_device_name(0), os.cpu_count(), flush=True)
-    # memcpy ceiling on this box
-    a = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
-    b = torch.empty_like(a)
-    med, best = timeit(lambda: b.copy_(a))
-    res.append({"kernel": "torch_copy_1GiB", "ms": med * 1e3, "GBps": 2 * (1 << 30) / med / 1e9})
-    print(res[-1], flush=True)
-    del a, b
-    probe_cif(res)
-    probe_ctc(res, [(32, 200, 10), (64, 400, 20), (128, 800, 40), (32, 1600, 80), (256, 1600, 80)])
+    if not ONCE:
+        a = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        b = torch.empty_like(a)
+        med, best = timeit(lambda: b.copy_(a))
+        res.append({"kernel": "torch_copy_1GiB", "us": med * 1e6, "GBps": 2 * (1 << 30) / med / 1e9})
+        print(res[-1], flush=True)
+        del a, b
+    if "cif" in sys.argv or not ({"cif", "ctc"} & set(sys.argv)):
+        probe_cif(res)
+    if "ctc" in sys.argv or not ({"cif", "ctc"} & set(sys.argv)):
+        shapes = [(32, 1600, 80), (256, 1600, 80)] if ONCE else \
+            [(32, 200, 10), (64, 400, 20), (128, 800, 40), (32, 1600, 80), (256, 1600, 80)]
+        probe_ctc(res, shapes)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "probe_%s.json" % tag), "w") as f:
         json.dump(res, f, indent=1)
