@@ -1,20 +1,439 @@
-// mha.cu - multi-head attention core (placeholder until the tcgen05 kernels land).
+// mha.cu - scaled-dot-product attention core on tcgen05 / TMEM, fed by TMA (sm_100a).
+//
+// Replaces ScaledDotProductAttention.forward
+// (/root/reference/src/transformer/attention.py:74-86: bmm, / sqrt(d_k), masked_fill(-inf),
+// softmax(dim=2), dropout, bmm) and the head split / merge copies around it
+// (attention.py:47-49, 56-57).  bf16 operands, fp32 accumulation and softmax statistics.
+//
+// Layout: q [B,Lq,Hh,64], k,v [B,Lk,Hh,64] bf16 - the natural layout of the projection
+// outputs - addressed through 4-D TMA descriptors, so no head-major copy is ever made;
+// out [B,Lq,Hh,64] bf16 is exactly what the `fc` projection consumes.
+//
+// Forward kernel: one CTA per (b, head, 128-query tile), 6 warps:
+//   warps 0-3  softmax + epilogue (thread t owns query row t = TMEM lane t)
+//   warp  4    TMA producer (Q once, K/V tiles into a 2-stage ring, 128-byte swizzle)
+//   warp  5    TMEM allocator + single-thread tcgen05.mma issuer
+// Per 128-key block:  S = Q K^T  (tcgen05.mma kind::f16, M=128 N=128 K=64, SMEM x SMEM -> TMEM)
+//                     softmax warps read S from TMEM (tcgen05.ld), apply the mask, online
+//                     softmax, write P (bf16) into shared memory in the canonical K-major
+//                     128B-swizzled layout
+//                     PV = P V   (M=128 N=64 K=128, V consumed MN-major straight from its TMA tile)
+//                     softmax warps read PV from TMEM and fold it into the fp32 O registers.
 #include "common.cuh"
 
-extern "C" int asr_mha_fwd_bf16(const void*, const void*, const void*, const int*, const uint8_t*, int, int, int, int,
-                                int, int, float, void*, float*, void*) {
-    asr::set_error("asr_mha_fwd_bf16: not built yet");
-    return 9;
+#include <cuda_bf16.h>
+
+namespace asr {
+
+constexpr int kD = 64;          // head dim (d_k = d_v = 64 in every reference recipe)
+constexpr int kBM = 128;        // query rows per CTA
+constexpr int kBN = 128;        // keys per block
+constexpr int kTileBytes = kBM * kD * 2;   // 16 KB: one [128 x 64] bf16 tile, 128-byte rows
+
+// ---- tcgen05 / TMEM wrappers ----------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
 }
-extern "C" size_t asr_mha_bwd_workspace_bytes(int, int, int, int, int) { return 0; }
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), columns c..c+31
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- descriptors -------------------------------------------------------------------
+// Shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 bytes apart
+// (what a [rows x 64 bf16] TMA tile with CU_TENSOR_MAP_SWIZZLE_128B looks like).
+// bits [0,14) start>>4 | [16,30) LBO>>4 | [32,46) SBO>>4 | [46,48) version=1 | [61,64) layout=2 (SW128)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor, kind::f16: fp32 accumulate, bf16 A and B.
+// bits [4,6) c=F32(1) | [7,10) a=BF16(1) | [10,13) b=BF16(1) | 15 a_major | 16 b_major | [17,23) N>>3 | [24,29) M>>4
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct MhaFwdArgs {
+    const int* kv_len;          // [B] or null
+    const uint8_t* dense_mask;  // [B,Lq,Lk] or null (non-zero = masked)
+    int causal;
+    int B, Hh, Lq, Lk;
+    float scale_log2;           // softmax scale * log2(e)
+    __nv_bfloat16* out;         // [B,Lq,Hh,64]
+    float* lse;                 // [B,Hh,Lq]   natural-log LSE of the scaled scores
+};
+
+struct __align__(8) MhaBarriers {
+    uint64_t q_full;
+    uint64_t kv_full[2];
+    uint64_t kv_empty[2];
+    uint64_t s_full;
+    uint64_t s_free;
+    uint64_t p_full;
+    uint64_t pv_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+constexpr int kFwdThreads = 192;
+// Q + 2x(K,V) + P + barriers = 112.1 KB, so that two CTAs (and their 2 x 256 TMEM columns) share one SM
+constexpr int kFwdSmem = kTileBytes /*Q*/ + 4 * kTileBytes /*K,V x2*/ + 2 * kTileBytes /*P*/ + 128;
+
+__global__ void __launch_bounds__(kFwdThreads, 2)
+mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+               const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];   // 128B-swizzled tiles need 1024-byte alignment
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sQ = smem;
+    unsigned char* sK = sQ + kTileBytes;          // 2 stages
+    unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
+    unsigned char* sP = sV + 2 * kTileBytes;      // [2 key halves][128 rows][128 B]
+    MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sP + 2 * kTileBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * kBM;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    // keys that can matter for this tile: up to kvlen, and up to the last query row when causal
+    int k_end = a.causal ? min(kvlen, q0 + kBM) : kvlen;
+    if (a.dense_mask) k_end = a.Lk;
+    const int nblk = max(1, (k_end + kBN - 1) / kBN);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->kv_full[s], 1);
+            mbar_init(&bars->kv_empty[s], 1);
+        }
+        mbar_init(&bars->s_full, 1);
+        mbar_init(&bars->s_free, 128);
+        mbar_init(&bars->p_full, 128);
+        mbar_init(&bars->pv_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&bars->tmem_base, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem_s = tmem;          // 128 columns: S
+    const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(&bars->q_full, kTileBytes);
+            tma_load_4d(sQ, &tm_q, 0, h, q0, b, &bars->q_full);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
+                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
+                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint32_t p_addr = smem_u32(sP);
+            mbar_wait(&bars->q_full, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
+                if (j > 0) mbar_wait(&bars->s_free, (j - 1) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + s * kTileBytes);
+                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk) {
+                    const uint64_t ad = smem_desc_sw128(q_addr + kk * 32, 16, 1024);
+                    const uint64_t bd = smem_desc_sw128(k_addr + kk * 32, 16, 1024);
+                    umma_bf16(tmem_s, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(&bars->s_full);
+                // P V once the softmax warps have published P
+                mbar_wait(&bars->p_full, j & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
+                    umma_bf16(tmem_pv, ad, bd, idesc_pv, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(&bars->pv_full);
+                tc_commit(&bars->kv_empty[s]);
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: thread = query row =====
+        const int row = threadIdx.x;           // 0..127 = TMEM lane
+        const int qi = q0 + row;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float o[kD];
+#pragma unroll
+        for (int i = 0; i < kD; ++i) o[i] = 0.0f;
+        float m_run = -INFINITY;   // running max of the raw scores
+        float l_run = 0.0f;
+        const float c = a.scale_log2;
+        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+
+        for (int j = 0; j < nblk; ++j) {
+            const int key0 = j * kBN;
+            // mask limit for this row: keys >= lim are masked
+            int lim = kvlen;
+            if (a.causal) lim = min(lim, qi + 1);
+            const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+
+            mbar_wait(&bars->s_full, j & 1);
+            tc_fence_after();
+            // pass 1: row max
+            float m_blk = -INFINITY;
+#pragma unroll 1
+            for (int cc = 0; cc < kBN; cc += 32) {
+                float s[32];
+                tmem_ld32(tmem_s + lane_base + cc, s);
+                if (need_mask) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = key0 + cc + i;
+                        bool dead = key >= lim;
+                        if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                        if (dead) s[i] = -INFINITY;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, s[i]);
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;   // fully masked so far: keep exp2 finite
+            const float alpha = exp2f((m_run - m_use) * c);            // m_run = -inf -> 0
+            const float mc = m_use * c;
+            // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle), row sum
+            float l_blk = 0.0f;
+#pragma unroll 1
+            for (int cc = 0; cc < kBN; cc += 32) {
+                float s[32];
+                tmem_ld32(tmem_s + lane_base + cc, s);
+                if (need_mask) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int key = key0 + cc + i;
+                        bool dead = key >= lim;
+                        if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                        if (dead) s[i] = -INFINITY;
+                    }
+                }
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float p0 = exp2f(fmaf(s[i], c, -mc));
+                    const float p1 = exp2f(fmaf(s[i + 1], c, -mc));
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    // the row sum uses the rounded values the tensor core will see
+                    l_blk += __low2float(pb) + __high2float(pb);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                }
+                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half (cc / 64)
+                unsigned char* prow = sP + (cc >> 6) * kTileBytes + row * 128;
+                const int chunk0 = (cc & 63) >> 3;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int chunk = (chunk0 + q4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
+            fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+            mbar_arrive(&bars->p_full);
+
+            l_run = l_run * alpha + l_blk;
+            m_run = m_new;
+#pragma unroll
+            for (int i = 0; i < kD; ++i) o[i] *= alpha;
+
+            mbar_wait(&bars->pv_full, j & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < kD; cc += 32) {
+                float pv[32];
+                tmem_ld32(tmem_pv + lane_base + cc, pv);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[cc + i] += pv[i];
+            }
+            tc_fence_before();
+        }
+        // epilogue: O / l -> bf16 -> out[b, qi, h, :]; a fully masked row is 0/0 = NaN like the reference
+        if (qi < a.Lq) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD;
+#pragma unroll
+            for (int i = 0; i < kD; i += 8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[i + 2 * u] * inv, o[i + 2 * u + 1] * inv);
+                    w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                }
+                *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (a.lse != nullptr)
+                a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_run * c + log2f(l_run)) * 0.6931471805599453f;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// ---- attention probabilities (only when a caller asks for `attn`) ----------------------
+// attn[(h*B + b), q, k] f32, the reference's head-major order.  One warp per (b,h,q) row; CUDA cores.
+__global__ void __launch_bounds__(128) mha_probs_kernel(const __nv_bfloat16* q, const __nv_bfloat16* k, const int* kv_len,
+                                                        const uint8_t* dense_mask, int causal, int B, int Hh, int Lq,
+                                                        int Lk, float scale, float* attn) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)B * Hh * Lq) return;
+    const int qi = (int)(row % Lq);
+    const int h = (int)((row / Lq) % Hh);
+    const int b = (int)(row / ((long long)Lq * Hh));
+    const int kvlen = kv_len ? min(max(kv_len[b], 0), Lk) : Lk;
+    const __nv_bfloat16* qr = q + (((size_t)b * Lq + qi) * Hh + h) * kD;
+    float* dst = attn + (((size_t)h * B + b) * Lq + qi) * Lk;
+    const float q0 = __bfloat162float(qr[lane]), q1 = __bfloat162float(qr[lane + 32]);
+    float mx = -INFINITY;
+    for (int key = 0; key < Lk; ++key) {
+        const __nv_bfloat16* kr = k + (((size_t)b * Lk + key) * Hh + h) * kD;
+        float s = warp_sum(q0 * __bfloat162float(kr[lane]) + q1 * __bfloat162float(kr[lane + 32])) * scale;
+        bool dead = key >= kvlen || (causal && key > qi);
+        if (dense_mask) dead = dead || dense_mask[((size_t)b * Lq + qi) * Lk + key] != 0;
+        if (dead) s = -INFINITY;
+        if (lane == 0) dst[key] = s;
+        mx = fmaxf(mx, s);
+    }
+    __syncwarp();
+    float sum = 0.0f;
+    for (int key = lane; key < Lk; key += 32) sum += expf(dst[key] - mx);
+    sum = warp_sum(sum);
+    for (int key = lane; key < Lk; key += 32) dst[key] = expf(dst[key] - mx) / sum;
+}
+
+static int make_qkv_map(CUtensorMap* map, const void* base, int B, int L, int Hh) {
+    const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)Hh, (uint64_t)L, (uint64_t)B};
+    const uint64_t strides[3] = {(uint64_t)kD * 2, (uint64_t)Hh * kD * 2, (uint64_t)L * Hh * kD * 2};
+    const uint32_t box[4] = {(uint32_t)kD, 1u, (uint32_t)kBM, 1u};
+    return make_tmap_nd(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
+                                int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
+                                void* stream) {
+    ASR_REQUIRE(q && k && v && out, "asr_mha_fwd_bf16: null pointer");
+    ASR_REQUIRE(D == kD, "asr_mha_fwd_bf16: head dim %d not supported (64 only)", D);
+    ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_fwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
+    ASR_REQUIRE(B <= 65535 && Hh <= 65535, "asr_mha_fwd_bf16: B/Hh exceed the grid limits");
+    ASR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "asr_mha_fwd_bf16: pointers must be 16-byte aligned");
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUtensorMap tq, tk, tv;
+    if (make_qkv_map(&tq, q, B, Lq, Hh) || make_qkv_map(&tk, k, B, Lk, Hh) || make_qkv_map(&tv, v, B, Lk, Hh)) return 4;
+    MhaFwdArgs a;
+    a.kv_len = kv_len;
+    a.dense_mask = dense_mask;
+    a.causal = causal;
+    a.B = B; a.Hh = Hh; a.Lq = Lq; a.Lk = Lk;
+    a.scale_log2 = scale * 1.4426950408889634f;
+    a.out = static_cast<__nv_bfloat16*>(out);
+    a.lse = lse;
+    ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
+    mha_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, a);
+    ASR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int D) {
+    (void)Lk;
+    if (B <= 0 || Hh <= 0 || Lq <= 0 || D <= 0) return 0;
+    // fp32 dQ accumulator [B,Lq,Hh,D] + delta [B,Hh,Lq]
+    return (size_t)B * Lq * Hh * D * sizeof(float) + (size_t)B * Hh * Lq * sizeof(float) + 256;
+}
+
 extern "C" int asr_mha_bwd_bf16(const void*, const void*, const void*, const void*, const void*, const float*,
                                 const int*, const uint8_t*, int, int, int, int, int, int, float, void*, void*, void*,
                                 void*, size_t, void*) {
     asr::set_error("asr_mha_bwd_bf16: not built yet");
     return 9;
 }
-extern "C" int asr_mha_probs_f32(const void*, const void*, const int*, const uint8_t*, int, int, int, int, int, int,
-                                 float, float*, void*) {
-    asr::set_error("asr_mha_probs_f32: not built yet");
-    return 9;
+
+extern "C" int asr_mha_probs_f32(const void* q, const void* k, const int* kv_len, const uint8_t* dense_mask, int causal,
+                                 int B, int Hh, int Lq, int Lk, int D, float scale, float* attn, void* stream) {
+    ASR_REQUIRE(q && k && attn, "asr_mha_probs_f32: null pointer");
+    ASR_REQUIRE(D == kD, "asr_mha_probs_f32: head dim %d not supported (64 only)", D);
+    if (asr_device_ok() != 0) return 3;
+    const long long rows = (long long)B * Hh * Lq;
+    mha_probs_kernel<<<(unsigned)((rows + 3) / 4), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(q), static_cast<const __nv_bfloat16*>(k), kv_len, dense_mask, causal, B, Hh, Lq,
+        Lk, scale, attn);
+    ASR_LAUNCH_CHECK();
+    return 0;
 }

@@ -164,3 +164,80 @@ def ctc_loss(logits, len_logits, targets, blank=None, return_nll=False):
     if return_nll:
         return loss, nll
     return loss
+
+
+# ---------------------------------------------------------------------------------
+# Multi-head attention core  (reference: src/transformer/attention.py:74-86)
+# ---------------------------------------------------------------------------------
+class _MhaCoreFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, kv_len, dense_mask, causal, scale):
+        B, Lq, Hh, D = q.shape
+        Lk = k.shape[1]
+        out = torch.empty((B, Lq, Hh, D), dtype=torch.bfloat16, device=q.device)
+        lse = torch.empty((B, Hh, Lq), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().asr_mha_fwd_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
+                                              B, Hh, Lq, Lk, D, ctypes.c_float(scale), ptr(out), ptr(lse),
+                                              stream_ptr()), "asr_mha_fwd_bf16")
+        ctx.save_for_backward(q, k, v, out, lse, kv_len, dense_mask)
+        ctx.meta = (causal, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        q, k, v, out, lse, kv_len, dense_mask = ctx.saved_tensors
+        causal, scale = ctx.meta
+        B, Lq, Hh, D = q.shape
+        Lk = k.shape[1]
+        g_out = g_out.contiguous()
+        if g_out.dtype != torch.bfloat16:
+            g_out = g_out.to(torch.bfloat16)
+        g_q, g_k, g_v = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ws_bytes = _lib.lib().asr_mha_bwd_workspace_bytes(B, Hh, Lq, Lk, D)
+        ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            check(_lib.lib().asr_mha_bwd_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
+                                              ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D, ctypes.c_float(scale),
+                                              ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws), ws_bytes, stream_ptr()),
+                  "asr_mha_bwd_bf16")
+        return g_q, g_k, g_v, None, None, None, None
+
+
+def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None):
+    """softmax(mask(q k^T * scale)) v on the tensor cores.
+
+    q [B,Lq,Hh,64], k,v [B,Lk,Hh,64] (any float dtype; computed in bf16, fp32 accumulate)
+    -> [B,Lq,Hh,64] bf16.  Masking: kv_len [B] (keys >= kv_len[b] masked), causal, and/or a
+    dense mask [B,Lq,Lk] (True / non-zero = masked), combined with OR."""
+    _require_cuda("q", q)
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise ValueError("mha_core: q, k, v must be [B, L, heads, 64]")
+    if scale is None:
+        scale = 1.0 / (q.shape[-1] ** 0.5)
+    qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
+    if kv_len is not None:
+        kv_len = kv_len.to(device=q.device, dtype=torch.int32).contiguous()
+    if mask is not None:
+        mask = mask.to(device=q.device).ne(0).to(torch.uint8).contiguous()
+    return _MhaCoreFunction.apply(qb, kb, vb, kv_len, mask, bool(causal), float(scale))
+
+
+def mha_probs(q, k, kv_len=None, mask=None, causal=False, scale=None):
+    """Attention probabilities [(heads*B), Lq, Lk] f32 in the reference's head-major row order
+    (attention.py:47,62).  Not on the training path; for callers that want `attn`."""
+    _require_cuda("q", q)
+    B, Lq, Hh, D = q.shape
+    Lk = k.shape[1]
+    if scale is None:
+        scale = 1.0 / (D ** 0.5)
+    qb, kb = q.detach().to(torch.bfloat16).contiguous(), k.detach().to(torch.bfloat16).contiguous()
+    if kv_len is not None:
+        kv_len = kv_len.to(device=q.device, dtype=torch.int32).contiguous()
+    if mask is not None:
+        mask = mask.to(device=q.device).ne(0).to(torch.uint8).contiguous()
+    attn = torch.empty((Hh * B, Lq, Lk), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        check(_lib.lib().asr_mha_probs_f32(ptr(qb), ptr(kb), ptr(kv_len), ptr(mask), int(causal), B, Hh, Lq, Lk, D,
+                                           ctypes.c_float(scale), ptr(attn), stream_ptr()), "asr_mha_probs_f32")
+    return attn

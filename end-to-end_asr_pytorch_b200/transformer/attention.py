@@ -1,0 +1,80 @@
+"""Drop-in for /root/reference/src/transformer/attention.py.
+
+`MultiheadAttention(d_model, n_head, d_k=64, d_v=64, dropout=0.1)` keeps the
+reference's parameters, initialisation and state_dict keys (`w_qs, w_ks, w_vs, fc,
+layer_norm`), and `forward(q, k, v, mask=None) -> (output, attn)`.
+
+What changes: the scaled-dot-product core (bmm / scale / masked_fill / softmax / bmm
+and the three head-major permute copies, reference :47-57 and :74-86) is one
+tcgen05 kernel working in bf16 with fp32 accumulation directly on the
+[B, L, heads, 64] projection outputs.  The attention-probability matrix is never
+materialised on the training path; `attn` is returned as None unless the module is
+built with `return_attn=True` (every training caller of the reference discards it,
+encoder.py:72, decoder.py:628-633), in which case it is computed by a separate
+kernel in the reference's head-major row order.
+
+Dropout on the probabilities (reference :83) is not applied by the kernel in this
+round: with `dropout > 0` in training mode the module raises unless
+`allow_no_attn_dropout=True`; parity runs use `eval()` / `dropout=0`.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ..ops import mha_core, mha_probs
+
+
+class MultiheadAttention(nn.Module):
+    ''' Multi-Head Attention module (same parameters as the reference) '''
+
+    def __init__(self, d_model, n_head, d_k=64, d_v=64, dropout=0.1, return_attn=False,
+                 allow_no_attn_dropout=True):
+        super().__init__()
+        if d_k != 64 or d_v != 64:
+            raise ValueError("the sm_100a attention core is built for d_k = d_v = 64 (every reference recipe)")
+        self.n_head = n_head
+        self.d_k = d_k
+        self.d_v = d_v
+        self.return_attn = return_attn
+        self.allow_no_attn_dropout = allow_no_attn_dropout
+
+        self.w_qs = nn.Linear(d_model, n_head * d_k)
+        self.w_ks = nn.Linear(d_model, n_head * d_k)
+        self.w_vs = nn.Linear(d_model, n_head * d_v)
+        nn.init.normal_(self.w_qs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_ks.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
+        nn.init.normal_(self.w_vs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_v)))
+
+        self.attn_dropout_p = dropout
+        self.temperature = np.power(d_k, 0.5)
+        self.layer_norm = nn.LayerNorm(d_model)
+
+        self.fc = nn.Linear(n_head * d_v, d_model)
+        nn.init.xavier_normal_(self.fc.weight)
+
+        self.dropout = nn.Dropout(dropout)
+
+    def forward(self, q, k, v, mask=None, kv_len=None, causal=False):
+        """q [B,Lq,d_model], k,v [B,Lk,d_model], mask [B,Lq,Lk] (True = masked) or None.
+        `kv_len` / `causal` are optional structured forms of the reference's masks
+        (get_attn_pad_mask / get_subsequent_mask); they are OR-ed with `mask`."""
+        n_head, d_k, d_v = self.n_head, self.d_k, self.d_v
+        sz_b, len_q, _ = q.size()
+        len_k = k.size(1)
+        if self.training and self.attn_dropout_p > 0 and not self.allow_no_attn_dropout:
+            raise RuntimeError("attention-probability dropout is not implemented by the sm_100a core")
+
+        residual = q
+        qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
+        kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
+        vh = self.w_vs(v).view(sz_b, len_k, n_head, d_v)
+
+        ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
+        attn = None
+        if self.return_attn:
+            attn = mha_probs(qh, kh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
+
+        output = ctx.reshape(sz_b, len_q, n_head * d_v).to(q.dtype)
+        output = self.dropout(self.fc(output))
+        output = self.layer_norm(output + residual)
+        return output, attn

@@ -1,0 +1,112 @@
+"""tcgen05 attention core vs the oracle, the reference-generated golden vectors and a
+plain torch fp32 reference of the same op (bf16 tolerance: rtol 2e-2 of the output scale)."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import mha_oracle
+from conftest import load_golden
+from helpers import pkg, to_np
+
+pytestmark = pytest.mark.gpu
+
+MHA = load_golden("mha")
+CASES = ["self_pad", "self_causal", "cross", "nomask"]
+
+
+def _torch_core(q, k, v, mask=None, scale=None):
+    """fp32 reference of the core on [B,L,H,D] tensors (bmm / scale / masked_fill / softmax / bmm)."""
+    B, Lq, H, D = q.shape
+    scale = scale or 1.0 / D ** 0.5
+    qh, kh, vh = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))     # [B,H,L,D]
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    if mask is not None:
+        s = s.masked_fill(mask[:, None].bool(), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.matmul(p, vh).permute(0, 2, 1, 3)
+
+
+def _rand_qkv(B, Lq, Lk, H, seed, std=1.0):
+    g = torch.Generator().manual_seed(seed)
+    q = (torch.randn(B, Lq, H, 64, generator=g) * std).cuda().to(torch.bfloat16)
+    k = (torch.randn(B, Lk, H, 64, generator=g) * std).cuda().to(torch.bfloat16)
+    v = torch.randn(B, Lk, H, 64, generator=g).cuda().to(torch.bfloat16)
+    return q, k, v
+
+
+def _close(a, b, tol=2e-2):
+    a, b = a.float(), b.float()
+    scale = b.abs().max().item() + 1e-6
+    err = (a - b).abs().max().item()
+    assert err <= tol * scale, (err, scale)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H", [(2, 128, 128, 2), (1, 21, 21, 8), (3, 167, 167, 8), (2, 16, 300, 4),
+                                       (2, 300, 40, 4), (1, 512, 512, 2), (2, 129, 257, 3)])
+def test_core_no_mask(B, Lq, Lk, H):
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(B, Lq, Lk, H, seed=Lq + Lk)
+    out = ops.mha_core(q, k, v)
+    _close(out, _torch_core(q, k, v))
+
+
+@pytest.mark.parametrize("B,L,H", [(3, 167, 8), (2, 300, 2), (4, 64, 4)])
+def test_core_key_padding_lengths(B, L, H):
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(B, L, L, H, seed=L)
+    kv_len = torch.randint(L // 2, L + 1, (B,), generator=torch.Generator().manual_seed(1))
+    kv_len[0] = L
+    mask = (torch.arange(L)[None, None, :] >= kv_len[:, None, None]).expand(B, L, L).cuda()
+    ref = _torch_core(q, k, v, mask)
+    _close(ops.mha_core(q, k, v, kv_len=kv_len.cuda()), ref)       # structured form
+    _close(ops.mha_core(q, k, v, mask=mask), ref)                   # dense form of the same mask
+
+
+@pytest.mark.parametrize("B,L,H", [(2, 151, 8), (1, 400, 2)])
+def test_core_causal(B, L, H):
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(B, L, L, H, seed=L + 7)
+    kv_len = torch.tensor([L] + [L - 9] * (B - 1))
+    causal = torch.triu(torch.ones(L, L, dtype=torch.bool), diagonal=1)[None].expand(B, L, L)
+    pad = (torch.arange(L)[None, None, :] >= kv_len[:, None, None]).expand(B, L, L)
+    mask = (causal | pad).cuda()
+    ref = _torch_core(q, k, v, mask)
+    _close(ops.mha_core(q, k, v, kv_len=kv_len.cuda(), causal=True), ref)
+    _close(ops.mha_core(q, k, v, mask=mask), ref)
+
+
+def test_fully_masked_row_is_nan_like_reference():
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(1, 8, 8, 1, seed=3)
+    mask = torch.zeros(1, 8, 8, dtype=torch.bool)
+    mask[0, 5, :] = True
+    out = ops.mha_core(q, k, v, mask=mask.cuda())
+    assert torch.isnan(out[0, 5]).all() and not torch.isnan(out[0, 4]).any()
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_module_against_reference_golden(case):
+    att = pkg("transformer.attention")
+    m = att.MultiheadAttention(32, 2, 64, 64, dropout=0.1, return_attn=True).cuda().eval()
+    m.load_state_dict({k[2:]: torch.as_tensor(MHA[k]) for k in MHA.files if k.startswith("w_")})
+    q = torch.as_tensor(MHA[case + "_q"]).cuda()
+    kv = torch.as_tensor(MHA[case + "_kv"]).cuda()
+    mask = MHA[case + "_mask"]
+    mask = None if mask.size == 0 else torch.as_tensor(mask.astype(bool)).cuda()
+    y, attn = m(q, kv, kv, mask=mask)
+    ref_y = MHA[case + "_y"]
+    # bf16 core inside an fp32 block: rtol 2e-2 of the output scale
+    assert np.abs(to_np(y) - ref_y).max() <= 2e-2 * np.abs(ref_y).max()
+    ref_attn = MHA[case + "_attn"]                       # head-major rows: head * B + b
+    assert attn.shape == ref_attn.shape
+    assert np.abs(to_np(attn) - ref_attn).max() <= 2e-2
+
+
+def test_ctcmodel_twin_constructor_order():
+    catt = pkg("ctcModel.attention")
+    m = catt.MultiHeadAttention(2, 32, 64, 64, dropout=0.0)
+    assert m.n_head == 2 and m.w_qs.weight.shape == (128, 32)
+    assert sorted(k for k, _ in m.named_parameters()) == sorted(
+        ["w_qs.weight", "w_qs.bias", "w_ks.weight", "w_ks.bias", "w_vs.weight", "w_vs.bias",
+         "fc.weight", "fc.bias", "layer_norm.weight", "layer_norm.bias"])
