@@ -341,6 +341,306 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
+// =====================================================================================
+// Backward.  One CTA per (b, head, 128-key tile j); loop over the 128-query tiles i.
+//   S  = Q_i K_j^T            dP = dO_i V_j^T                (both into TMEM)
+//   P  = exp2(S*c - lse_i)    dS = P o (dP - delta_i) * scale (softmax warps, masks as in forward)
+//   dV_j += P^T dO_i          dK_j += dS^T Q_i               (accumulate in TMEM over i)
+//   dQ_i  = dS K_j            -> fp32 red.add into the dQ workspace (summed over the key tiles)
+// P and dS are written once to shared memory as [2 key halves][128 q][64 keys] bf16 with the
+// 128-byte swizzle; the same bytes serve as the K-major A operand of dS K and, read
+// MN-major, as the transposed A operand of P^T dO and dS^T Q.  Q_i, dO_i, K_j, V_j are
+// consumed straight from their TMA tiles, K-major or MN-major as each product needs.
+// TMEM columns: S 0-127 | dP 128-255 | dV 256-319 | dK 320-383 | dQ 384-447  (512 allocated).
+// =====================================================================================
+struct MhaBwdArgs {
+    const int* kv_len;
+    const uint8_t* dense_mask;
+    int causal;
+    int B, Hh, Lq, Lk;
+    float scale;
+    float scale_log2;
+    const float* lse;     // [B,Hh,Lq]
+    const float* delta;   // [B,Hh,Lq]  rowsum(dO o O)
+    float* dq_acc;        // [B,Lq,Hh,64] fp32, zeroed
+    __nv_bfloat16* g_k;   // [B,Lk,Hh,64]
+    __nv_bfloat16* g_v;
+};
+
+struct __align__(8) MhaBwdBarriers {
+    uint64_t kv_full;
+    uint64_t qdo_full[2];
+    uint64_t qdo_empty[2];
+    uint64_t sdp_full;
+    uint64_t sdp_free;
+    uint64_t pds_full;
+    uint64_t dq_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+constexpr int kBwdSmem = 2 * kTileBytes /*K,V*/ + 4 * kTileBytes /*Q,dO x2*/ + 2 * kTileBytes /*P*/ + 2 * kTileBytes /*dS*/ + 128;
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(kFwdThreads, 1)
+mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const MhaBwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sK = smem;
+    unsigned char* sV = sK + kTileBytes;
+    unsigned char* sQ = sV + kTileBytes;            // 2 stages
+    unsigned char* sDO = sQ + 2 * kTileBytes;       // 2 stages
+    unsigned char* sP = sDO + 2 * kTileBytes;       // [2][128][128B]
+    unsigned char* sDS = sP + 2 * kTileBytes;       // [2][128][128B]
+    MhaBwdBarriers* bars = reinterpret_cast<MhaBwdBarriers*>(sDS + 2 * kTileBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int key0 = blockIdx.x * kBN;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    const int nq = (a.Lq + kBM - 1) / kBM;
+    int i_start = a.causal ? (key0 / kBM) : 0;
+    // a key tile that is entirely padding (and no dense mask decides otherwise) gets zero gradients
+    const bool dead_tile = (a.dense_mask == nullptr) && (key0 >= kvlen);
+    if (dead_tile) i_start = nq;
+    const int nsteps = max(0, nq - i_start);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->kv_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->qdo_full[s], 1);
+            mbar_init(&bars->qdo_empty[s], 1);
+        }
+        mbar_init(&bars->sdp_full, 1);
+        mbar_init(&bars->sdp_free, 128);
+        mbar_init(&bars->pds_full, 128);
+        mbar_init(&bars->dq_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0 && nsteps > 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_do);
+            mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileBytes);
+            tma_load_4d(sK, &tm_k, 0, h, key0, b, &bars->kv_full);
+            tma_load_4d(sV, &tm_v, 0, h, key0, b, &bars->kv_full);
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it & 1;
+                if (it >= 2) mbar_wait(&bars->qdo_empty[s], ((it >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bars->qdo_full[s], 2 * kTileBytes);
+                tma_load_4d(sQ + s * kTileBytes, &tm_q, 0, h, (i_start + it) * kBM, b, &bars->qdo_full[s]);
+                tma_load_4d(sDO + s * kTileBytes, &tm_do, 0, h, (i_start + it) * kBM, b, &bars->qdo_full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer =====
+        if (lane == 0 && nsteps > 0) {
+            constexpr uint32_t id_s = make_idesc(kBM, kBN, 0, 0);     // S  = Q K^T   / dP = dO V^T
+            constexpr uint32_t id_t = make_idesc(kBN, kD, 1, 1);      // dV = P^T dO  / dK = dS^T Q  (A and B MN-major)
+            constexpr uint32_t id_q = make_idesc(kBM, kD, 0, 1);      // dQ = dS K    (A K-major, B MN-major)
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+            mbar_wait(&bars->kv_full, 0);
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it & 1;
+                const uint32_t q_addr = smem_u32(sQ + s * kTileBytes);
+                const uint32_t do_addr = smem_u32(sDO + s * kTileBytes);
+                mbar_wait(&bars->qdo_full[s], (it >> 1) & 1);
+                if (it > 0) mbar_wait(&bars->sdp_free, (it - 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tm_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              id_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tm_dp, smem_desc_sw128(do_addr + kk * 32, 16, 1024), smem_desc_sw128(v_addr + kk * 32, 16, 1024),
+                              id_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->sdp_full);
+
+                mbar_wait(&bars->pds_full, it & 1);
+                tc_fence_after();
+                // contraction over the 128 queries of the tile: 8 steps of 16 rows (2048 bytes)
+#pragma unroll
+                for (int kk = 0; kk < kBM / 16; ++kk) {
+                    umma_bf16(tm_dv, smem_desc_sw128(p_addr + kk * 2048, kTileBytes, 1024),
+                              smem_desc_sw128(do_addr + kk * 2048, kTileBytes, 1024), id_t, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+#pragma unroll
+                for (int kk = 0; kk < kBM / 16; ++kk) {
+                    umma_bf16(tm_dk, smem_desc_sw128(ds_addr + kk * 2048, kTileBytes, 1024),
+                              smem_desc_sw128(q_addr + kk * 2048, kTileBytes, 1024), id_t, (it > 0 || kk > 0) ? 1u : 0u);
+                }
+                // contraction over the 128 keys: dS K-major (two 64-key halves), K tile MN-major
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    umma_bf16(tm_dq, smem_desc_sw128(ds_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024),
+                              smem_desc_sw128(k_addr + kk * 2048, kTileBytes, 1024), id_q, kk > 0 ? 1u : 0u);
+                }
+                tc_commit(&bars->dq_full);
+                tc_commit(&bars->qdo_empty[s]);
+            }
+        }
+    } else {
+        // ===== softmax-backward warps: thread = query row of the tile (and key row in the epilogue) =====
+        const int row = threadIdx.x;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const float c = a.scale_log2;
+        for (int it = 0; it < nsteps; ++it) {
+            const int qi = (i_start + it) * kBM + row;
+            const bool q_ok = qi < a.Lq;
+            const size_t stat = ((size_t)b * a.Hh + h) * a.Lq + (q_ok ? qi : 0);
+            const float lse2 = q_ok ? __ldg(a.lse + stat) * 1.4426950408889634f : INFINITY;
+            const float dlt = q_ok ? __ldg(a.delta + stat) : 0.0f;
+            int lim = kvlen;
+            if (a.causal) lim = min(lim, qi + 1);
+            const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+            const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+
+            mbar_wait(&bars->sdp_full, it & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int cc = 0; cc < kBN; cc += 32) {
+                float sv[32], dp[32];
+                tmem_ld32(tm_s + lane_base + cc, sv);
+                tmem_ld32(tm_dp + lane_base + cc, dp);
+                uint32_t pk[16], dk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float p0 = exp2f(fmaf(sv[i], c, -lse2));
+                    float p1 = exp2f(fmaf(sv[i + 1], c, -lse2));
+                    if (need_mask) {
+                        const int key = key0 + cc + i;
+                        bool d0 = key >= lim, d1 = key + 1 >= lim;
+                        if (mrow != nullptr) {
+                            if (key < a.Lk) d0 = d0 || (mrow[key] != 0);
+                            if (key + 1 < a.Lk) d1 = d1 || (mrow[key + 1] != 0);
+                        }
+                        if (d0) p0 = 0.0f;
+                        if (d1) p1 = 0.0f;
+                    }
+                    const float s0 = p0 * (dp[i] - dlt) * a.scale;
+                    const float s1 = p1 * (dp[i + 1] - dlt) * a.scale;
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    const __nv_bfloat162 sb = __floats2bfloat162_rn(s0, s1);
+                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                    dk[i >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
+                }
+                const int off = (cc >> 6) * kTileBytes + row * 128;
+                const int chunk0 = (cc & 63) >> 3;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int chunk = (chunk0 + q4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(sP + off + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                    *reinterpret_cast<uint4*>(sDS + off + chunk * 16) = make_uint4(dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->sdp_free);
+            fence_proxy_async();
+            mbar_arrive(&bars->pds_full);
+
+            // dQ_i partial -> fp32 workspace
+            mbar_wait(&bars->dq_full, it & 1);
+            tc_fence_after();
+            float* dq_row = a.dq_acc + (((size_t)b * a.Lq + (q_ok ? qi : 0)) * a.Hh + h) * kD;
+#pragma unroll
+            for (int cc = 0; cc < kD; cc += 32) {
+                float dq[32];
+                tmem_ld32(tm_dq + lane_base + cc, dq);
+                if (q_ok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) red_add_v4(dq_row + cc + i, dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+                }
+            }
+            tc_fence_before();
+        }
+        // epilogue: dK_j, dV_j (thread = key row).  The TMEM loads are warp-collective, so every
+        // thread issues them; only rows inside the sequence store.
+        const int key = key0 + row;
+        const bool key_ok = key < a.Lk;
+        const size_t kv_off = (((size_t)b * a.Lk + (key_ok ? key : 0)) * a.Hh + h) * kD;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+            for (int cc = 0; cc < kD; cc += 32) {
+                float acc[32];
+                if (nsteps > 0) {   // CTA-uniform
+                    tmem_ld32((part == 0 ? tm_dk : tm_dv) + lane_base + cc, acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                }
+                if (key_ok) {
+                    __nv_bfloat16* dst = (part == 0 ? a.g_k : a.g_v) + kv_off + cc;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const __nv_bfloat162 v2 = __floats2bfloat162_rn(acc[i + 2 * u], acc[i + 2 * u + 1]);
+                            w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per row of 64)
+__global__ void __launch_bounds__(256) mha_delta_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta,
+                                                        int B, int Hh, int Lq) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b, q, h)
+    if (row >= (long long)B * Lq * Hh) return;
+    const __nv_bfloat162 ov = reinterpret_cast<const __nv_bfloat162*>(o + row * kD)[lane];
+    const __nv_bfloat162 gv = reinterpret_cast<const __nv_bfloat162*>(d_o + row * kD)[lane];
+    float s = __low2float(ov) * __low2float(gv) + __high2float(ov) * __high2float(gv);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const int hh = (int)(row % Hh);
+        const long long bq = row / Hh;
+        const int qi = (int)(bq % Lq);
+        const int bb = (int)(bq / Lq);
+        delta[((size_t)bb * Hh + hh) * Lq + qi] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) f32_to_bf16_kernel(const float* src, __nv_bfloat16* dst, size_t n4) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        const __nv_bfloat162 a2 = __floats2bfloat162_rn(v.x, v.y), b2 = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a2), *reinterpret_cast<const uint32_t*>(&b2));
+    }
+}
+
 // ---- attention probabilities (only when a caller asks for `attn`) ----------------------
 // attn[(h*B + b), q, k] f32, the reference's head-major order.  One warp per (b,h,q) row; CUDA cores.
 __global__ void __launch_bounds__(128) mha_probs_kernel(const __nv_bfloat16* q, const __nv_bfloat16* k, const int* kv_len,
@@ -418,11 +718,53 @@ extern "C" size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int
     return (size_t)B * Lq * Hh * D * sizeof(float) + (size_t)B * Hh * Lq * sizeof(float) + 256;
 }
 
-extern "C" int asr_mha_bwd_bf16(const void*, const void*, const void*, const void*, const void*, const float*,
-                                const int*, const uint8_t*, int, int, int, int, int, int, float, void*, void*, void*,
-                                void*, size_t, void*) {
-    asr::set_error("asr_mha_bwd_bf16: not built yet");
-    return 9;
+extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
+                                const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
+                                int Lq, int Lk, int D, float scale, void* g_q, void* g_k, void* g_v, void* ws,
+                                size_t ws_bytes, void* stream) {
+    ASR_REQUIRE(q && k && v && out && g_out && lse && g_q && g_k && g_v && ws, "asr_mha_bwd_bf16: null pointer");
+    ASR_REQUIRE(D == kD, "asr_mha_bwd_bf16: head dim %d not supported (64 only)", D);
+    ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_bwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
+    ASR_REQUIRE(B <= 65535 && Hh <= 65535, "asr_mha_bwd_bf16: B/Hh exceed the grid limits");
+    ASR_REQUIRE(ws_bytes >= asr_mha_bwd_workspace_bytes(B, Hh, Lq, Lk, D), "asr_mha_bwd_bf16: workspace too small");
+    ASR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(g_out) && aligned16(g_q) && aligned16(g_k) &&
+                    aligned16(g_v), "asr_mha_bwd_bf16: pointers must be 16-byte aligned");
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uintptr_t w = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
+    float* dq_acc = reinterpret_cast<float*>(w);
+    const size_t nq_elems = (size_t)B * Lq * Hh * kD;
+    float* delta = dq_acc + nq_elems;
+    ASR_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, nq_elems * sizeof(float), st));
+    const long long rows = (long long)B * Lq * Hh;
+    mha_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                 static_cast<const __nv_bfloat16*>(g_out), delta, B, Hh, Lq);
+    ASR_LAUNCH_CHECK();
+    CUtensorMap tq, tk, tv, tdo;
+    if (make_qkv_map(&tq, q, B, Lq, Hh) || make_qkv_map(&tk, k, B, Lk, Hh) || make_qkv_map(&tv, v, B, Lk, Hh) ||
+        make_qkv_map(&tdo, g_out, B, Lq, Hh))
+        return 4;
+    MhaBwdArgs a;
+    a.kv_len = kv_len;
+    a.dense_mask = dense_mask;
+    a.causal = causal;
+    a.B = B; a.Hh = Hh; a.Lq = Lq; a.Lk = Lk;
+    a.scale = scale;
+    a.scale_log2 = scale * 1.4426950408889634f;
+    a.lse = lse;
+    a.delta = delta;
+    a.dq_acc = dq_acc;
+    a.g_k = static_cast<__nv_bfloat16*>(g_k);
+    a.g_v = static_cast<__nv_bfloat16*>(g_v);
+    ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
+    mha_bwd_kernel<<<grid, kFwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+    ASR_LAUNCH_CHECK();
+    size_t blocks = (nq_elems / 4 + 255) / 256;
+    if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
+    f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(g_q), nq_elems / 4);
+    ASR_LAUNCH_CHECK();
+    return 0;
 }
 
 extern "C" int asr_mha_probs_f32(const void* q, const void* k, const int* kv_len, const uint8_t* dense_mask, int causal,
