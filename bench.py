@@ -250,6 +250,44 @@ def e2e_step(pkg, w, host, dev_buf, g_out):
     return losses
 
 
+def attention_microbench(pkg, device, iters=5):
+    """tcgen05 attention core, forward and backward, on the SURVEY 8(d) microbench shape
+    (B*heads = 128, L = 2048, d = 64, no mask); CUDA events, inputs >> L2 per call not needed
+    (compute bound).  Reported next to the hot-path kernels as the tensor-core row."""
+    lib = pkg._lib
+    L = lib.lib()
+    p, sp = lib.ptr, lib.stream_ptr
+    B, Ls, H = 16, 2048, 8
+    g = torch.Generator(device=device).manual_seed(5)
+    q, k, v, do = (torch.randn(B, Ls, H, 64, device=device, generator=g).to(torch.bfloat16) for _ in range(4))
+    out = torch.empty_like(q)
+    lse = torch.empty(B, H, Ls, device=device)
+    gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+    wsb = L.asr_mha_bwd_workspace_bytes(B, H, Ls, Ls, 64)
+    ws = torch.empty(wsb // 4 + 1, device=device)
+
+    def fwd():
+        lib.check(L.asr_mha_fwd_bf16(p(q), p(k), p(v), None, None, 0, B, H, Ls, Ls, 64, 0.125, p(out), p(lse), sp()), "mha_fwd")
+
+    def bwd():
+        lib.check(L.asr_mha_bwd_bf16(p(q), p(k), p(v), p(out), p(do), p(lse), None, None, 0, B, H, Ls, Ls, 64, 0.125,
+                                     p(gq), p(gk), p(gv), p(ws), wsb, sp()), "mha_bwd")
+    res = {}
+    for name, fn, flops in (("mha_fwd", fwd, 4.0 * B * H * Ls * Ls * 64), ("mha_bwd", bwd, 10.0 * B * H * Ls * Ls * 64)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms": ms, "TFLOPs": flops / (ms * 1e-3) / 1e12, "shape": "B=%d L=%d heads=%d d=64 bf16" % (B, Ls, H)}
+    return res
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -400,12 +438,18 @@ def main():
     names = ["ctc_rows", "ctc_lattice", "ctc_apply", "cif_fwd", "cif_bwd"]
     kernels = []
     for i, n in enumerate(names):
-        ent = {"kernel": n, "ms": stage_ms[i], "share_of_step": stage_ms[i] / sum(stage_ms)}
+        ent = {"kernel": n, "bound": "hbm", "ms": stage_ms[i], "share_of_step": stage_ms[i] / sum(stage_ms)}
         if n in bm:
             ent["algorithmic_bytes"] = bm[n]
             ent["GBps"] = bm[n] / (stage_ms[i] * 1e-3) / 1e9
             ent["frac_of_hbm_peak"] = ent["GBps"] / peaks["hbm_gbs"]
         kernels.append(ent)
+    if rank == 0:
+        att = attention_microbench(pkg, device)
+        for n in ("mha_fwd", "mha_bwd"):
+            kernels.append({"kernel": n, "bound": "tensor", "ms": att[n]["ms"], "TFLOPs": att[n]["TFLOPs"],
+                            "frac_of_bf16_peak": att[n]["TFLOPs"] / peaks["bf16_tflops"], "shape": att[n]["shape"],
+                            "in_timed_step": False})
     traffic = load_traffic()
     dom = kernels[0]
     roofline = {"bound": "hbm", "kernel": "asr::ctc_rows_kernel", "achieved": dom["GBps"], "peak": peaks["hbm_gbs"],

@@ -1,0 +1,112 @@
+"""Data-parallel training plumbing: one process per GPU, gradients only over NCCL.
+
+The hot-path kernels have no cross-utterance coupling: every rank runs
+them on its own utterances and the only exchange per step is the parameter-gradient
+all-reduce.  `GradAllReduce` does that with bucket views (gradients accumulate
+directly inside flat per-bucket buffers, no copies) and launches each bucket's
+all-reduce from a post-accumulate hook as soon as its last gradient is written, in
+reverse parameter order, so the collectives overlap the rest of the backward pass.
+The reference itself is single-GPU (CIF.sh:5,71); this is new plumbing around it.
+
+Loss normalisation note: `ctc_loss`, the quantity loss and the CE are local-batch
+means; averaging gradients over ranks equals the global-batch gradient when every
+rank holds the same number of utterances / tokens (true for the synthetic configs).
+"""
+import torch
+import torch.distributed as dist
+
+
+def broadcast_parameters(module, src=0):
+    """Make every rank start from rank `src`'s parameters and buffers."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src)
+
+
+class GradAllReduce:
+    """Bucketed, overlapped gradient averaging for `module` (call `finish()` before the optimiser step).
+
+        sync = GradAllReduce(model, bucket_mb=25)
+        loss.backward()        # buckets are all-reduced as they fill
+        sync.finish()          # wait + average; then optimizer.step()
+    """
+
+    def __init__(self, module, bucket_mb=25.0, process_group=None):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
+        params = [p for p in module.parameters() if p.requires_grad]
+        self.params = params
+        self.buckets = []          # (flat buffer, [params])
+        self._owner = {}
+        cap = int(bucket_mb * 1024 * 1024)
+        cur, cur_bytes = [], 0
+        # reverse order: the last layers' gradients are ready first
+        for p in reversed(params):
+            nbytes = p.numel() * p.element_size()
+            if cur and (cur_bytes + nbytes > cap or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self._seal(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            self._seal(cur)
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self.reset()
+
+    def _seal(self, plist):
+        flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
+        off = 0
+        for p in plist:
+            p.grad = flat[off:off + p.numel()].view_as(p)      # gradient lives inside the bucket
+            self._owner[p] = len(self.buckets)
+            off += p.numel()
+        self.buckets.append((flat, plist))
+
+    def reset(self):
+        """Zero the buckets (instead of optimizer.zero_grad(), which would detach the views)."""
+        for i, (flat, plist) in enumerate(self.buckets):
+            flat.zero_()
+            self._pending[i] = len(plist)
+        self._handles = []
+
+    def _on_grad(self, p):
+        i = self._owner[p]
+        self._pending[i] -= 1
+        if self._pending[i] == 0 and self.world > 1:
+            flat = self.buckets[i][0]
+            self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+
+    def finish(self):
+        """Wait for the outstanding all-reduces and turn the sums into means."""
+        if self.world > 1:
+            for i, (flat, _) in enumerate(self.buckets):
+                if self._pending[i] != 0:      # some parameter of this bucket got no gradient this step
+                    self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+            for h, flat in self._handles:
+                h.wait()
+                flat.div_(self.world)
+        for i, (_, plist) in enumerate(self.buckets):
+            self._pending[i] = len(plist)
+        self._handles = []
+
+    def grad_bytes(self):
+        return sum(flat.numel() * flat.element_size() for flat, _ in self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+
+
+def shard_utterances(n_utts, rank=None, world=None):
+    """Contiguous utterance range of this rank (data parallel by utterance)."""
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if world is None:
+        world = dist.get_world_size() if dist.is_initialized() else 1
+    per = (n_utts + world - 1) // world
+    lo = min(n_utts, rank * per)
+    return lo, min(n_utts, lo + per)

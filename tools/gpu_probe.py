@@ -137,6 +137,51 @@ def probe_ctc(res, shapes):
         torch.cuda.empty_cache()
 
 
+def probe_mha(res):
+    shapes = [(64, 167, 8), (64, 512, 8), (32, 1024, 8), (16, 2048, 8), (8, 4096, 8)]
+    if ONCE:
+        shapes = [(16, 2048, 8)]
+    for (B, Ls, H) in shapes:
+        for causal in (False, True):
+            g = torch.Generator(device="cuda").manual_seed(5)
+            q = torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+            k = torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+            v = torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+            do = torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+            out = torch.empty_like(q)
+            lse = torch.empty(B, H, Ls, device="cuda")
+            gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            wsb = L.asr_mha_bwd_workspace_bytes(B, H, Ls, Ls, 64)
+            ws = torch.empty(wsb // 4 + 1, device="cuda")
+            scale = 0.125
+
+            def fwd():
+                check(L.asr_mha_fwd_bf16(ptr(q), ptr(k), ptr(v), None, None, int(causal), B, H, Ls, Ls, 64, scale,
+                                         ptr(out), ptr(lse), sp()), "mha_fwd")
+
+            def bwd():
+                check(L.asr_mha_bwd_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(do), ptr(lse), None, None, int(causal),
+                                         B, H, Ls, Ls, 64, scale, ptr(gq), ptr(gk), ptr(gv), ptr(ws), wsb, sp()), "mha_bwd")
+            div = 2.0 if causal else 1.0
+            med, best = timeit(fwd)
+            fl = 4.0 * B * H * Ls * Ls * 64 / div
+            res.append({"kernel": "mha_fwd", "B": B, "L": Ls, "H": H, "causal": causal, "us": med * 1e6,
+                        "TFLOPs": fl / max(med, 1e-9) / 1e12})
+            print(res[-1], flush=True)
+            med, best = timeit(bwd)
+            fl = 10.0 * B * H * Ls * Ls * 64 / div
+            res.append({"kernel": "mha_bwd", "B": B, "L": Ls, "H": H, "causal": causal, "us": med * 1e6,
+                        "TFLOPs": fl / max(med, 1e-9) / 1e12})
+            print(res[-1], flush=True)
+            if not ONCE and not causal:
+                import torch.nn.functional as F
+                qh, kh, vh = (t.permute(0, 2, 1, 3).contiguous() for t in (q, k, v))
+                med, best = timeit(lambda: F.scaled_dot_product_attention(qh, kh, vh))
+                res.append({"kernel": "torch_sdpa_fwd", "B": B, "L": Ls, "us": med * 1e6,
+                            "TFLOPs": 4.0 * B * H * Ls * Ls * 64 / med / 1e12})
+                print(res[-1], flush=True)
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     res = []
@@ -149,9 +194,12 @@ def main():
         res.append({"kernel": "torch_copy_1GiB", "us": med * 1e6, "GBps": 2 * (1 << 30) / med / 1e9})
         print(res[-1], flush=True)
         del a, b
-    if "cif" in sys.argv or not ({"cif", "ctc"} & set(sys.argv)):
+    sel = {"cif", "ctc", "mha"} & set(sys.argv)
+    if "mha" in sel or not sel:
+        probe_mha(res)
+    if "cif" in sel or not sel:
         probe_cif(res)
-    if "ctc" in sys.argv or not ({"cif", "ctc"} & set(sys.argv)):
+    if "ctc" in sel or not sel:
         shapes = [(32, 1600, 80), (256, 1600, 80)] if ONCE else \
             [(32, 200, 10), (64, 400, 20), (128, 800, 40), (32, 1600, 80), (256, 1600, 80)]
         probe_ctc(res, shapes)
