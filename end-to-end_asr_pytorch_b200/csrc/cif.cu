@@ -159,27 +159,45 @@ __device__ __forceinline__ void cif_fwd_finish(const CifFwdArgs& a, int b, int s
     }
 }
 
-// One frame of phase 2: frame += cur*h (:83); on a fire emit the frame and restart
-// it from rem*h (:85-87).  `fired` is warp-uniform; written as selects so that the
-// compiler keeps the unrolled loop free of branches (only the store is predicated).
+// Predicated vector store (no branch): if (pred) *p = v.
 template <int VEC>
-__device__ __forceinline__ void cif_frame_step(const CifFwdArgs& a, int b, int col, bool col_ok, const float (&h)[VEC],
-                                               float c, float rm, bool fired, float (&frame)[VEC], int& k) {
+__device__ __forceinline__ void vstore_if(float* p, const float (&v)[VEC], bool pred) {
+    const unsigned pr = pred ? 1u : 0u;
+    if constexpr (VEC == 4) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v4.f32 [%1], {%2, %3, %4, %5};\n\t}"
+                     ::"r"(pr), "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    } else if constexpr (VEC == 2) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.v2.f32 [%1], {%2, %3};\n\t}"
+                     ::"r"(pr), "l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %0, 0;\n\t@q st.global.f32 [%1], %2;\n\t}"
+                     ::"r"(pr), "l"(p), "f"(v[0]) : "memory");
+    }
+}
+
+// One frame of phase 2: frame += cur*h (:83); on a fire emit the frame and restart
+// it from rem*h (:85-87).  `fired` is warp-uniform.  Written with selects, a predicated
+// store and a running output pointer, so the unrolled loop contains no branch at all.
+// `optr` points at this lane's slot of output row k; `room` = rows still free (L - k).
+template <int VEC>
+__device__ __forceinline__ void cif_frame_step(const float (&h)[VEC], float c, float rm, bool fired, bool col_ok,
+                                               size_t row_stride, float (&frame)[VEC], float*& optr, int& room) {
     float pre[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) pre[i] = __fadd_rn(frame[i], __fmul_rn(c, h[i]));
-    if (fired && k < a.L && col_ok) vstore<VEC>(a.out + ((size_t)b * a.L + k) * a.H + col, pre);
+    vstore_if<VEC>(optr, pre, fired && col_ok && room > 0);
 #pragma unroll
     for (int i = 0; i < VEC; ++i) frame[i] = fired ? __fmul_rn(rm, h[i]) : pre[i];
-    k += fired ? 1 : 0;
+    optr += fired ? row_stride : 0;
+    room -= fired ? 1 : 0;
 }
 
 // Phase 2 over a full 32-row tile in shared memory: loads are issued 8 rows at a
 // time ahead of the arithmetic (tile rows + the broadcast (cur, rem) pairs).
 template <int VEC>
-__device__ __forceinline__ void cif_tile_full(const CifFwdArgs& a, int b, int col, bool col_ok, const float* tile,
-                                              int row_stride, const float2* cr, unsigned mask, float (&frame)[VEC],
-                                              int& k) {
+__device__ __forceinline__ void cif_tile_full(bool col_ok, size_t out_stride, const float* tile, int row_stride,
+                                              const float2* cr, unsigned mask, float (&frame)[VEC], float*& optr,
+                                              int& room) {
 #pragma unroll 1
     for (int r0 = 0; r0 < 32; r0 += 8) {
         float h[8][VEC];
@@ -191,18 +209,18 @@ __device__ __forceinline__ void cif_tile_full(const CifFwdArgs& a, int b, int co
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            cif_frame_step<VEC>(a, b, col, col_ok, h[u], w[u].x, w[u].y, (mask >> (r0 + u)) & 1u, frame, k);
+            cif_frame_step<VEC>(h[u], w[u].x, w[u].y, (mask >> (r0 + u)) & 1u, col_ok, out_stride, frame, optr, room);
     }
 }
 template <int VEC>
-__device__ __forceinline__ void cif_tile_partial(const CifFwdArgs& a, int b, int col, bool col_ok, const float* tile,
-                                                 int row_stride, const float2* cr, unsigned mask, int nrow,
-                                                 float (&frame)[VEC], int& k) {
+__device__ __forceinline__ void cif_tile_partial(bool col_ok, size_t out_stride, const float* tile, int row_stride,
+                                                 const float2* cr, unsigned mask, int nrow, float (&frame)[VEC],
+                                                 float*& optr, int& room) {
     for (int r = 0; r < nrow; ++r) {
         float h[VEC];
         vload<VEC>(h, tile + r * row_stride);
         const float2 w = cr[r];
-        cif_frame_step<VEC>(a, b, col, col_ok, h, w.x, w.y, (mask >> r) & 1u, frame, k);
+        cif_frame_step<VEC>(h, w.x, w.y, (mask >> r) & 1u, col_ok, out_stride, frame, optr, room);
     }
 }
 
@@ -224,7 +242,9 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
 #pragma unroll
     for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
     float integ = 0.0f, asum = 0.0f;
-    int k = 0;
+    int k = 0;                 // fires so far (schedule side)
+    int room = a.L;            // output rows still free (data side)
+    float* optr = a.out + (size_t)b * a.L * a.H + (col_ok ? col : 0);
     constexpr int U = 8;
 
     for (int t0 = 0; t0 < a.T; t0 += 32) {
@@ -238,6 +258,7 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
         else
             cif_chain_chunk<false>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
         if (rec) cif_record_chunk(a, b, tt, lane, k, my_cur, my_rem, fire_mask);
+        k += __popc(fire_mask);
 
         for (int r0 = 0; r0 < nrow; r0 += U) {
             float h[U][VEC];
@@ -260,7 +281,7 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
             for (int u = 0; u < U; ++u) {
                 const int r = r0 + u;
                 if (r < nrow)   // warp-uniform
-                    cif_frame_step<VEC>(a, b, col, col_ok, h[u], cc[u], rr[u], (fire_mask >> r) & 1u, frame, k);
+                    cif_frame_step<VEC>(h[u], cc[u], rr[u], (fire_mask >> r) & 1u, col_ok, (size_t)a.H, frame, optr, room);
             }
         }
     }
@@ -308,7 +329,9 @@ __global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__
 #pragma unroll
     for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
     float integ = 0.0f, asum = 0.0f;
-    int k = 0;
+    int k = 0;                 // fires so far (schedule side)
+    int room = a.L;            // output rows still free (data side)
+    float* optr = a.out + (size_t)b * a.L * a.H + (col_ok ? col : 0);
     int stage = 0;
     uint32_t phase = 0;
     float next_alpha = (lane < a.T) ? __ldg(arow + lane) : 0.0f;
@@ -338,10 +361,11 @@ __global__ void __launch_bounds__(32) cif_fwd_tma_kernel(const __grid_constant__
         __syncwarp();
         mbar_wait(&bars[stage], phase);
         const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * kTileBytes) + lane * VEC;
+        k += __popc(fire_mask);
         if (nrow == kCifRows)
-            cif_tile_full<VEC>(a, b, col, col_ok, tile, W, s_cr, fire_mask, frame, k);
+            cif_tile_full<VEC>(col_ok, (size_t)a.H, tile, W, s_cr, fire_mask, frame, optr, room);
         else
-            cif_tile_partial<VEC>(a, b, col, col_ok, tile, W, s_cr, fire_mask, nrow, frame, k);
+            cif_tile_partial<VEC>(col_ok, (size_t)a.H, tile, W, s_cr, fire_mask, nrow, frame, optr, room);
         // every lane is done reading this stage -> refill it
         __syncwarp();
         const int cn = c + nstage;
@@ -469,6 +493,8 @@ __global__ void __launch_bounds__(160) cif_fwd_ws_kernel(const __grid_constant__
 #pragma unroll
         for (int i = 0; i < VEC; ++i) frame[i] = 0.0f;
         int k = 0, stage = 0;
+        int room = a.L;
+        float* optr = a.out + (size_t)b * a.L * a.H + (col_ok ? col : 0);
         uint32_t phase = 0;
         for (int c = 0; c < nchunk; ++c) {
             const int nrow = min(kCifRows, a.T - c * kCifRows);
@@ -476,10 +502,11 @@ __global__ void __launch_bounds__(160) cif_fwd_ws_kernel(const __grid_constant__
             const float* tile = reinterpret_cast<const float*>(smem_raw + (size_t)stage * tile_bytes) + warp * W + lane * VEC;
             const float2* cr = sched[stage].cr;
             const unsigned mask = sched[stage].mask;
+            k += __popc(mask);
             if (nrow == kCifRows)
-                cif_tile_full<VEC>(a, b, col, col_ok, tile, CW, cr, mask, frame, k);
+                cif_tile_full<VEC>(col_ok, (size_t)a.H, tile, CW, cr, mask, frame, optr, room);
             else
-                cif_tile_partial<VEC>(a, b, col, col_ok, tile, CW, cr, mask, nrow, frame, k);
+                cif_tile_partial<VEC>(col_ok, (size_t)a.H, tile, CW, cr, mask, nrow, frame, optr, room);
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[stage]);
             if (++stage == nstage) {
@@ -675,7 +702,7 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
                          (uint64_t)H * 4, kCifRows, (uint32_t)cw, CU_TENSOR_MAP_SWIZZLE_NONE) != 0)
             return 4;
         int nstage = get_opt("cif_fwd_stages");
-        if (nstage <= 0) nstage = 4;
+        if (nstage <= 0) nstage = (cw >= 256) ? 2 : 3;   // <= 64-96 KB per CTA: 2-3 CTAs (10-15 warps) per SM
         if (nstage > kCifMaxStages) nstage = kCifMaxStages;
         const size_t smem = (size_t)nstage * kCifRows * cw * 4;
         ASR_REQUIRE(B <= 65535, "asr_cif_fwd_f32: B=%d exceeds grid.y", B);

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
 #pragma unroll
             for (int r = 0; r < NS; ++r) blk[(size_t)i * NSL + lane * NS + r] = al[r];
         }
-        // beta + occupancy
+        // beta (sequential): alpha + beta replaces alpha in the block buffer; the occupancies are
+        // computed afterwards in a loop whose iterations are independent (off the critical path)
         for (int i = n - 1; i >= 0; --i) {
             const int t = t0 + i;
             const float* row = cur + i * SP;
@@ -404,16 +405,22 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
             } else {
                 lat.beta_step(be, row, lane);
             }
-            // occupancy(t,s) = exp2(alpha + beta - lp + nll); both alpha and beta include lp_t
+            float* ab = blk + (size_t)i * NSL + lane * NS;
+#pragma unroll
+            for (int r = 0; r < NS; ++r) ab[r] += be[r];
+        }
+        // occupancy(t,s) = exp2(alpha + beta - lp + nll); both alpha and beta include lp_t
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const float* row = cur + i * SP;
+            const float* ab = blk + (size_t)i * NSL + lane * NS;
             const float lpb = row[0];
             float bsum = 0.0f;
-            float* orow = glp_b + (size_t)t * SP;
+            float* orow = glp_b + (size_t)(t0 + i) * SP;
 #pragma unroll
             for (int q = 0; q < NH; ++q) {
-                const float ab = blk[(size_t)i * NSL + lane * NS + 2 * q] + be[2 * q];
-                bsum += vb[q] ? ex2f((ab - lpb) + nll2) : 0.0f;
-                const float al_l = blk[(size_t)i * NSL + lane * NS + 2 * q + 1] + be[2 * q + 1];
-                const float ov = ex2f((al_l - row[lat.li[q]]) + nll2);
+                bsum += vb[q] ? ex2f((ab[2 * q] - lpb) + nll2) : 0.0f;
+                const float ov = ex2f((ab[2 * q + 1] - row[lat.li[q]]) + nll2);
                 if (vl[q]) orow[1 + lane * NH + q] = ov;   // per label position; K3 merges repeats
             }
             blpart[i * 33 + lane] = bsum;
