@@ -49,6 +49,11 @@ WORKLOADS = {
     # name: per-GPU batch
     "cif_ctc_joint": dict(B=256, T=1600, S=80, V=4233, H=512),
     "cif_ctc_small": dict(B=32, T=200, S=10, V=4233, H=512),
+    # BASELINE config 5: the whole CIF_Model (reference recipe defaults: LFR 4/3, 3 conv layers, 6+6
+    # layers, d_model 512, 8 heads, d_inner 2048, V=4233) trained data-parallel with an NCCL gradient
+    # all-reduce; 500 raw frames -> 167 LFR frames x 320 -> 21 encoder frames, 14 labels
+    "train": dict(B=64, T=167, S=14, V=4233, H=512, D=320),
+    "train_long": dict(B=32, T=534, S=45, V=4233, H=512, D=320),
 }
 
 
@@ -288,6 +293,108 @@ def attention_microbench(pkg, device, iters=5):
     return res
 
 
+# ---------------------------------------------------------------------------------------
+# workload "train": full CIF_Model step, data parallel with gradient all-reduce (config 5)
+# ---------------------------------------------------------------------------------------
+def _model_args(w):
+    return argparse.Namespace(d_input=80, LFR_m=4, n_conv_layers=3, d_model=w["H"], n_layers_enc=6, n_head=8,
+                              d_inner=2048, dropout=0.1, d_assigner_hidden=512, w_context=3, n_assigner_layers=3,
+                              sos_id=2, vocab_size=w["V"], n_layers_dec=6, spec_aug_cfg=None)
+
+
+def _train_inputs(w, device, seed):
+    B, T, S, V, D = w["B"], w["T"], w["S"], w["V"], w["D"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    feats = torch.randn(B, T, D, device=device, generator=g)
+    lens = torch.randint(int(0.7 * T), T + 1, (B,), device=device, generator=g)
+    lens[0] = T
+    feats = feats * (torch.arange(T, device=device)[None, :, None] < lens[:, None, None]).float()
+    targets = torch.randint(4, V - 1, (B, S), device=device, generator=g)
+    tl = torch.randint(max(1, (2 * S) // 3), S + 1, (B,), device=device, generator=g)
+    targets = targets * (torch.arange(S, device=device)[None, :] < tl[:, None]).long()
+    return feats, lens, targets
+
+
+def run_train(args, w, rank, world, device):
+    import importlib
+    import torch.distributed as dist
+    import asr_b200 as pkg
+    cm = importlib.import_module("end-to-end_asr_pytorch_b200.transformer.cif_model")
+    lossm = importlib.import_module("end-to-end_asr_pytorch_b200.transformer.loss")
+    dp = importlib.import_module("end-to-end_asr_pytorch_b200.dp")
+    torch.manual_seed(1234)
+    model = cm.CIF_Model.create_model(_model_args(w)).to(device).train()
+    dp.broadcast_parameters(model, 0)
+    sync = dp.GradAllReduce(model, bucket_mb=25)
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.9, 0.98), eps=1e-9)
+    feats, lens, targets = _train_inputs(w, device, 1240 + rank)
+    torch.manual_seed(100 + rank)          # per-rank noise / dropout streams
+    n_params = sum(p.numel() for p in model.parameters())
+
+    def step(f, l, t):
+        sync.reset()
+        ctc_logits, len_ctc, _num, num, logits = model(f, l, t)
+        qua, ctc, ce = lossm.cal_ctc_qua_ce_loss(ctc_logits, len_ctc, _num, num, logits, t, smoothing=0.1)
+        loss = 0.001 * qua + ctc + ce
+        loss.backward()
+        sync.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    K, W = args.steps, max(args.warmup, 3)
+    for _ in range(W):
+        step(feats, lens, targets)
+    barrier()
+    sampler = ClockSampler(device.index or 0)
+    sampler.start()
+    l0 = pkg._lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        loss = step(feats, lens, targets)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = pkg._lib.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / K
+    # end to end: features / targets from pinned host memory every step, loss read back
+    host = [x.cpu().pin_memory() for x in (feats, lens, targets)]
+    bufs = [torch.empty_like(x) for x in (feats, lens, targets)]
+    Ke = max(3, min(K, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        for b_, h_ in zip(bufs, host):
+            b_.copy_(h_, non_blocking=True)
+        lv = step(*bufs).item()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        line = {"metric": METRIC, "value": world * w["B"] / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 (attention core bf16)", "data": "synthetic",
+                "config": dict(workload=args.workload, per_gpu=w, model="CIF_Model reference recipe defaults",
+                               params=n_params, grad_allreduce_bytes=sync.grad_bytes(),
+                               parallelism="dp%d by utterance, NCCL gradient all-reduce (bucketed, overlapped)" % world,
+                               note="attention-probability dropout is not applied by the tcgen05 core"),
+                "clocks": clocks,
+                "e2e": {"value": world * w["B"] * Ke / float(dt.item()), "unit": UNIT,
+                        "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in host), "d2h_bytes_per_step": 4,
+                        "steps": Ke, "api": "CIF_Model.forward + cal_ctc_qua_ce_loss + backward + all-reduce + Adam"},
+                "gpu_launches": int(launches), "last_loss": lv, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -371,6 +478,13 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
+
+    if args.workload.startswith("train"):
+        run_train(args, w, rank, world, device)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     import asr_b200 as pkg
     launches0 = pkg._lib.launch_count()

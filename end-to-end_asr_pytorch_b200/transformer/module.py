@@ -1,0 +1,40 @@
+"""Caller-side building blocks (plain PyTorch; not on the kernel hot path).
+
+Same parameter / buffer names as /root/reference/src/transformer/module.py so that
+checkpoints interchange: `PositionalEncoding.pe`, `PositionwiseFeedForward.{w_1,w_2,layer_norm}`.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class PositionalEncoding(nn.Module):
+    """Sinusoidal table, returned for the first T positions of the input."""
+
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        pos = torch.arange(0, max_len, dtype=torch.float32).unsqueeze(1)
+        inv_freq = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+        table = torch.zeros(max_len, d_model)
+        table[:, 0::2] = torch.sin(pos * inv_freq)
+        table[:, 1::2] = torch.cos(pos * inv_freq)
+        self.register_buffer('pe', table.unsqueeze(0))
+
+    def forward(self, input):
+        return self.pe[:, :input.size(1)]
+
+
+class PositionwiseFeedForward(nn.Module):
+    """LayerNorm(x + W2 relu(W1 x))."""
+
+    def __init__(self, d_model, d_ff, dropout=0.1):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, d_ff)
+        self.w_2 = nn.Linear(d_ff, d_model)
+        self.dropout = nn.Dropout(dropout)
+        self.layer_norm = nn.LayerNorm(d_model)
+
+    def forward(self, x):
+        return self.layer_norm(self.dropout(self.w_2(F.relu(self.w_1(x)))) + x)

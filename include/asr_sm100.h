@@ -41,7 +41,9 @@ int         asr_device_ok(void);
  * return non-zero.  Keys: "cif_fwd_variant" (0 = auto, 1 = plain loads,
  * 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline), "cif_fwd_width"
  * (0 = auto, 32/64/128 floats per warp), "cif_fwd_stages" (0 = auto),
- * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto). */
+ * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto), "ctc_fuse_apply"
+ * (0 = separate K3 pass applies the sparse gradient update (default, faster),
+ * 1 = the lattice kernel applies it itself with RED.ADD). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
 /* Number of kernels launched by this library since load (all streams). */

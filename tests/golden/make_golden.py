@@ -21,7 +21,10 @@ Every array is produced by reference code:
   * CIF glue : the scaling lines cif_model.py:43-48 executed verbatim through
                CIF_Model.forward is not possible without the whole model, so
                the glue golden stores the inputs/outputs of those four lines
-               re-executed here with torch.rand stubbed to 0.5-noise = 0.
+               re-executed here with the torch.rand(B) draw stored alongside.
+  * CIF_Model: a small model built from the reference's own classes (conv front
+               end, encoder, assigner, Decoder_CIF) run through CIF_Model.forward,
+               cal_ctc_qua_ce_loss and autograd on config-1-shaped inputs.
   * CTC      : transformer.loss.cal_ctc_ce_loss (loss.py:34-48) and
                ctcModel.loss.cal_loss (ctcModel/loss.py:4-13); per-utterance
                nll from F.ctc_loss(reduction='none') on the same log-probs.
@@ -293,6 +296,49 @@ def make_masks(uutils):
     print("masks: done")
 
 
+def make_cif_model(cif_model, tloss):
+    """A small CIF_Model (reference classes, reference forward, reference losses, autograd)
+    on config-1-shaped inputs: 8 utterances x 167 LFR frames x 320 (500 raw frames, m=4 n=3)."""
+    from transformer.conv_encoder import Conv2dSubsample
+    from transformer.encoder import Encoder
+    from transformer.attentionAssigner import Attention_Assigner
+    from transformer.decoder import Decoder_CIF
+    torch.manual_seed(2026)
+    d_model, vocab = 64, 100
+    model = cif_model.CIF_Model(Conv2dSubsample(d_input=320, d_model=d_model, n_layers=3),
+                                Encoder(d_input=d_model, n_layers=1, n_head=2, d_model=d_model, d_inner=128, dropout=0.1),
+                                Attention_Assigner(d_input=d_model, d_hidden=d_model, w_context=3, n_layers=3),
+                                Decoder_CIF(sos_id=2, n_tgt_vocab=vocab, n_layers=1, n_head=2, d_model=d_model,
+                                            d_inner=128, dropout=0.1)).eval()
+    g = torch.Generator().manual_seed(1235)
+    B, T, S = 8, 167, 14
+    feats = torch.randn(B, T, 320, generator=g)
+    lens = torch.tensor([167, 167, 160, 151, 140, 133, 120, 101])
+    feats = feats * (torch.arange(T)[None, :, None] < lens[:, None, None]).float()
+    targets = torch.randint(4, vocab - 1, (B, S), generator=g)
+    tl = torch.tensor([14, 13, 14, 12, 11, 12, 10, 9])
+    targets = targets * (torch.arange(S)[None, :] < tl[:, None]).long()
+    torch.manual_seed(77)                      # fixes torch.rand(B) inside forward (cif_model.py:47)
+    ctc_logits, len_ctc, _num, num, logits = model(feats, lens, targets)
+    qua, ctc, ce = tloss.cal_ctc_qua_ce_loss(ctc_logits, len_ctc, _num, num, logits, targets, smoothing=0.1)
+    loss = 0.001 * qua + ctc + ce
+    loss.backward()
+    out = {"feats": feats.numpy(), "lens": lens.numpy(), "targets": targets.numpy(), "rand_seed": np.int64(77),
+           "ctc_logits": ctc_logits.detach().numpy(), "len_ctc": len_ctc.numpy(), "_num": _num.detach().numpy(),
+           "num": num.numpy(), "logits": logits.detach().numpy(), "qua": qua.detach().numpy(),
+           "ctc": ctc.detach().numpy(), "ce": ce.detach().numpy()}
+    for k, v in model.state_dict().items():
+        if not k.endswith(".pe"):              # the sinusoid tables are deterministic, not stored
+            out["sd:" + k] = v.numpy()
+    for k, p in model.named_parameters():
+        if k in ("ctc_fc.weight", "assigner.linear.weight", "decoder.tgt_word_prj.weight", "encoder.linear_in.weight",
+                 "conv_encoder.affine.bias", "encoder.layer_stack.0.slf_attn.w_qs.weight"):
+            out["grad:" + k] = p.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "cif_model.npz"), **out)
+    print("cif_model: logits", tuple(logits.shape), "ctc_logits", tuple(ctc_logits.shape),
+          "losses", float(qua), float(ctc), float(ce), "params", sum(p.numel() for p in model.parameters()))
+
+
 def main():
     cif_model, tloss, closs, attention, uutils = _import_reference()
     torch.set_num_threads(1)
@@ -302,6 +348,7 @@ def main():
     make_qua(tloss)
     make_mha(attention, uutils)
     make_masks(uutils)
+    make_cif_model(cif_model, tloss)
 
 
 if __name__ == "__main__":

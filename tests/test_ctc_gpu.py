@@ -15,6 +15,15 @@ CTC = load_golden("ctc")
 CASES = sorted({k.split("_")[0] for k in CTC.files})
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["separate_apply", "fused_apply"])
+def apply_mode(request):
+    """Sparse gradient update as the separate K3 pass (default) or inside the lattice kernel."""
+    lib = pkg("_lib")
+    lib.set_option("ctc_fuse_apply", request.param)
+    yield request.param
+    lib.set_option("ctc_fuse_apply", 0)
+
+
 def _ours(logits, targets, in_len, need_grad=True):
     ops = pkg("ops")
     lg = logits.clone().requires_grad_(need_grad)
