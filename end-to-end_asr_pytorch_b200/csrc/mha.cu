@@ -55,7 +55,39 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), columns c..c+31
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), columns c..c+31.
+// tmem_ld32_issue starts the (asynchronous) load, tmem_ld_wait makes its registers valid.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// two exponentials per MUFU op, straight into the packed bf16 pair the tensor core will read
+__device__ __forceinline__ uint32_t ex2_bf16x2(float lo, float hi) {
+    uint32_t packed, y;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(packed) : "f"(hi), "f"(lo));
+    asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(y) : "r"(packed));
+    return y;
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -84,6 +116,15 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
+    return d;
+}
+// All-ones B operand: no swizzle, zero leading / stride offsets, so every 8x16-byte core matrix of the
+// [N x K] operand aliases the same 128 bytes of bf16 1.0.  P x ones gives the row sums of the bf16
+// probabilities exactly as the tensor core sees them (fp32 accumulate) without any CUDA-core adds.
+__device__ __forceinline__ uint64_t smem_desc_ones(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 46;
     return d;
 }
 // Instruction descriptor, kind::f16: fp32 accumulate, bf16 A and B.
@@ -117,7 +158,7 @@ struct __align__(8) MhaBarriers {
 
 constexpr int kFwdThreads = 192;
 // Q + 2x(K,V) + P + barriers = 112.1 KB, so that two CTAs (and their 2 x 256 TMEM columns) share one SM
-constexpr int kFwdSmem = kTileBytes /*Q*/ + 4 * kTileBytes /*K,V x2*/ + 2 * kTileBytes /*P*/ + 128;
+constexpr int kFwdSmem = kTileBytes /*Q*/ + 4 * kTileBytes /*K,V x2*/ + 2 * kTileBytes /*P*/ + 128 /*barriers*/ + 128 /*ones*/;
 
 __global__ void __launch_bounds__(kFwdThreads, 2)
 mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
@@ -129,9 +170,12 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
     unsigned char* sP = sV + 2 * kTileBytes;      // [2 key halves][128 rows][128 B]
     MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sP + 2 * kTileBytes);
+    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sP + 2 * kTileBytes + 128);   // 128 bytes of bf16 1.0
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
+    fence_proxy_async();   // generic-proxy write -> visible to the tensor core after the block barrier below
     const int q0 = blockIdx.x * kBM;
     const int h = blockIdx.y;
     const int b = blockIdx.z;
@@ -163,6 +207,7 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const uint32_t tmem = bars->tmem_base;
     const uint32_t tmem_s = tmem;          // 128 columns: S
     const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
+    const uint32_t tmem_l = tmem + 192;    // 16 columns: P x ones (row sums)
 
     if (warp == 4) {
         // ===== TMA producer =====
@@ -185,8 +230,11 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (lane == 0) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
             const uint32_t q_addr = smem_u32(sQ);
             const uint32_t p_addr = smem_u32(sP);
+            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
+            fence_proxy_async();   // the ones tile was written through the generic proxy
             mbar_wait(&bars->q_full, 0);
             for (int j = 0; j < nblk; ++j) {
                 const int s = j & 1;
@@ -210,6 +258,7 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
                     const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
                     umma_bf16(tmem_pv, ad, bd, idesc_pv, kk > 0 ? 1u : 0u);
+                    umma_bf16(tmem_l, ad, ones_desc, idesc_l, kk > 0 ? 1u : 0u);
                 }
                 tc_commit(&bars->pv_full);
                 tc_commit(&bars->kv_empty[s]);
@@ -237,53 +286,46 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
             mbar_wait(&bars->s_full, j & 1);
             tc_fence_after();
-            // pass 1: row max
-            float m_blk = -INFINITY;
-#pragma unroll 1
-            for (int cc = 0; cc < kBN; cc += 32) {
-                float s[32];
-                tmem_ld32(tmem_s + lane_base + cc, s);
-                if (need_mask) {
+            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int key = key0 + cc + i;
-                        bool dead = key >= lim;
-                        if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                        if (dead) s[i] = -INFINITY;
-                    }
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + cc + i;
+                    bool dead = key >= lim;
+                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                    if (dead) r[i] = 0xff800000u;   // -inf
                 }
+            };
+            // pass 1: row max.  TMEM loads are double-buffered: chunk c+1 is in flight while chunk c is reduced.
+            float m_blk = -INFINITY;
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(tmem_s + lane_base, ra);
+                tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, s[i]);
+                for (int cc = 0; cc < kBN; cc += 64) {
+                    tmem_ld32_issue(tmem_s + lane_base + cc + 32, rb);
+                    if (need_mask) apply_mask(ra, cc);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(ra[i]));
+                    tmem_ld_wait();
+                    if (cc + 64 < kBN) tmem_ld32_issue(tmem_s + lane_base + cc + 64, ra);
+                    if (need_mask) apply_mask(rb, cc + 32);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(rb[i]));
+                    if (cc + 64 < kBN) tmem_ld_wait();
+                }
             }
             const float m_new = fmaxf(m_run, m_blk);
             const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;   // fully masked so far: keep exp2 finite
-            const float alpha = exp2f((m_run - m_use) * c);            // m_run = -inf -> 0
+            const float alpha = ex2_approx((m_run - m_use) * c);       // m_run = -inf -> 0
             const float mc = m_use * c;
             // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle), row sum
-            float l_blk = 0.0f;
-#pragma unroll 1
-            for (int cc = 0; cc < kBN; cc += 32) {
-                float s[32];
-                tmem_ld32(tmem_s + lane_base + cc, s);
-                if (need_mask) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int key = key0 + cc + i;
-                        bool dead = key >= lim;
-                        if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                        if (dead) s[i] = -INFINITY;
-                    }
-                }
+            auto emit = [&](uint32_t (&r)[32], int cc) {
+                if (need_mask) apply_mask(r, cc);
                 uint32_t pk[16];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const float p0 = exp2f(fmaf(s[i], c, -mc));
-                    const float p1 = exp2f(fmaf(s[i + 1], c, -mc));
-                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                    // the row sum uses the rounded values the tensor core will see
-                    l_blk += __low2float(pb) + __high2float(pb);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                }
+                for (int i = 0; i < 32; i += 2)
+                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
                 // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half (cc / 64)
                 unsigned char* prow = sP + (cc >> 6) * kTileBytes + row * 128;
                 const int chunk0 = (cc & 63) >> 3;
@@ -292,25 +334,40 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     const int chunk = (chunk0 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
                 }
+            };
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(tmem_s + lane_base, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < kBN; cc += 64) {
+                    tmem_ld32_issue(tmem_s + lane_base + cc + 32, rb);
+                    emit(ra, cc);
+                    tmem_ld_wait();
+                    if (cc + 64 < kBN) tmem_ld32_issue(tmem_s + lane_base + cc + 64, ra);
+                    emit(rb, cc + 32);
+                    if (cc + 64 < kBN) tmem_ld_wait();
+                }
             }
             tc_fence_before();
             mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
             fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
             mbar_arrive(&bars->p_full);
 
-            l_run = l_run * alpha + l_blk;
             m_run = m_new;
-#pragma unroll
-            for (int i = 0; i < kD; ++i) o[i] *= alpha;
 
             mbar_wait(&bars->pv_full, j & 1);
             tc_fence_after();
+            l_run = fmaf(l_run, alpha, tmem_ld1(tmem_l + lane_base));   // row sum of the bf16 P, from the tensor core
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(tmem_pv + lane_base, ra);
+                tmem_ld32_issue(tmem_pv + lane_base + 32, rb);
+                tmem_ld_wait();
 #pragma unroll
-            for (int cc = 0; cc < kD; cc += 32) {
-                float pv[32];
-                tmem_ld32(tmem_pv + lane_base + cc, pv);
+                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(ra[i]));
 #pragma unroll
-                for (int i = 0; i < 32; ++i) o[cc + i] += pv[i];
+                for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(rb[i]));
             }
             tc_fence_before();
         }
@@ -524,8 +581,8 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 uint32_t pk[16], dk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float p0 = exp2f(fmaf(sv[i], c, -lse2));
-                    float p1 = exp2f(fmaf(sv[i + 1], c, -lse2));
+                    float p0 = ex2_approx(fmaf(sv[i], c, -lse2));
+                    float p1 = ex2_approx(fmaf(sv[i + 1], c, -lse2));
                     if (need_mask) {
                         const int key = key0 + cc + i;
                         bool d0 = key >= lim, d1 = key + 1 >= lim;
