@@ -67,6 +67,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances per CPU-baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the full-model data-parallel step (config 5)")
     return ap.parse_args()
 
 
@@ -315,7 +316,7 @@ def _train_inputs(w, device, seed):
     return feats, lens, targets
 
 
-def run_train(args, w, rank, world, device):
+def run_train(args, w, rank, world, device, steps=None, emit=True):
     import importlib
     import torch.distributed as dist
     import asr_b200 as pkg
@@ -345,7 +346,7 @@ def run_train(args, w, rank, world, device):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    K, W = args.steps, max(args.warmup, 3)
+    K, W = (steps or args.steps), max(args.warmup, 3)
     for _ in range(W):
         step(feats, lens, targets)
     barrier()
@@ -379,6 +380,8 @@ def run_train(args, w, rank, world, device):
     dt = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sync.remove()
+    line = None
     if rank == 0:
         line = {"metric": METRIC, "value": world * w["B"] / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
                 "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -392,7 +395,11 @@ def run_train(args, w, rank, world, device):
                         "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in host), "d2h_bytes_per_step": 4,
                         "steps": Ke, "api": "CIF_Model.forward + cal_ctc_qua_ce_loss + backward + all-reduce + Adam"},
                 "gpu_launches": int(launches), "last_loss": lv, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
+    del model, opt, sync
+    torch.cuda.empty_cache()
+    return line
 
 
 def load_peaks():
@@ -549,6 +556,7 @@ def main():
     # ---- roofline of the dominant kernel, rank 0 --------------------------------------
     peaks, peak_src = load_peaks()
     bm = hp.bytes_model()
+    L_out, valid_frames = hp.Lout, hp.valid_frames
     names = ["ctc_rows", "ctc_lattice", "ctc_apply", "cif_fwd", "cif_bwd"]
     kernels = []
     for i, n in enumerate(names):
@@ -571,8 +579,23 @@ def main():
                 "traffic": traffic.get("ctc_rows_kernel_bytes_per_launch"),
                 "algorithmic_bytes_per_launch": bm["ctc_rows"],
                 "avg_launch_ms": stage_ms[0],
+                "joint_step_GBps": (bm["ctc_total"] + bm["cif_fwd"] + bm["cif_bwd"]) / (sum(stage_ms) * 1e-3) / 1e9,
+                "joint_step_frac": (bm["ctc_total"] + bm["cif_fwd"] + bm["cif_bwd"]) / (sum(stage_ms) * 1e-3) / 1e9 / peaks["hbm_gbs"],
                 "ctc_whole_GBps": bm["ctc_total"] / (sum(stage_ms[:3]) * 1e-3) / 1e9,
                 "ctc_whole_frac": bm["ctc_total"] / (sum(stage_ms[:3]) * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+
+    # ---- BASELINE config 5 next to the hot-path number: the whole CIF_Model trained data parallel
+    #      (NCCL gradient all-reduce), a few steps, same launch ------------------------------
+    train_step = None
+    if not args.no_train_step:
+        del hp
+        torch.cuda.empty_cache()
+        tl = run_train(args, dict(WORKLOADS["train"]), rank, world, device, steps=5, emit=False)
+        if tl is not None:
+            train_step = {k: tl[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
+            train_step.update(workload="train", per_gpu=tl["config"]["per_gpu"], params=tl["config"]["params"],
+                              grad_allreduce_bytes=tl["config"]["grad_allreduce_bytes"],
+                              parallelism=tl["config"]["parallelism"])
 
     if rank == 0:
         cpu_baseline = None
@@ -589,12 +612,12 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload=args.workload, per_gpu=w, L=hp.Lout, valid_frames=hp.valid_frames,
+            "config": dict(workload=args.workload, per_gpu=w, L=L_out, valid_frames=valid_frames,
                            parallelism="dp%d by utterance, no data-path collective" % world,
                            l2="inputs (%.1f GB logits + %.1f GB hidden per GPU) exceed the 126 MB L2; no flush needed" % (
                                inp["logits"].numel() * 4 / 1e9, inp["hidden"].numel() * 4 / 1e9)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(timed_launches),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "train_step": train_step,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
