@@ -156,6 +156,142 @@ struct __align__(8) MhaBarriers {
     uint32_t pad;
 };
 
+// Per-tile resources of the softmax warps (one 128-query tile).
+struct FwdTile {
+    uint64_t* s_full;
+    uint64_t* s_free;
+    uint64_t* p_full;
+    uint64_t* pv_full;
+    uint32_t tmem_s, tmem_pv, tmem_l;
+    unsigned char* sP;
+};
+
+// Online softmax + epilogue of one 128-query tile: thread `row` owns query row q0 + row (= TMEM lane row).
+__device__ __forceinline__ void fwd_softmax_tile(const MhaFwdArgs& a, const FwdTile& t, int row, int q0, int b, int h,
+                                                 int kvlen, int nblk) {
+        const int qi = q0 + row;
+        const uint32_t lane_base = (uint32_t)((row >> 5) * 32) << 16;
+        float o[kD];
+#pragma unroll
+        for (int i = 0; i < kD; ++i) o[i] = 0.0f;
+        float m_run = -INFINITY;   // running max of the raw scores
+        float l_run = 0.0f;
+        const float c = a.scale_log2;
+        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+
+        for (int j = 0; j < nblk; ++j) {
+            const int key0 = j * kBN;
+            // mask limit for this row: keys >= lim are masked
+            int lim = kvlen;
+            if (a.causal) lim = min(lim, qi + 1);
+            const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+
+            mbar_wait(t.s_full, j & 1);
+            tc_fence_after();
+            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + cc + i;
+                    bool dead = key >= lim;
+                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                    if (dead) r[i] = 0xff800000u;   // -inf
+                }
+            };
+            // pass 1: row max.  TMEM loads are double-buffered: chunk c+1 is in flight while chunk c is reduced.
+            float m_blk = -INFINITY;
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(t.tmem_s + lane_base, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < kBN; cc += 64) {
+                    tmem_ld32_issue(t.tmem_s + lane_base + cc + 32, rb);
+                    if (need_mask) apply_mask(ra, cc);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(ra[i]));
+                    tmem_ld_wait();
+                    if (cc + 64 < kBN) tmem_ld32_issue(t.tmem_s + lane_base + cc + 64, ra);
+                    if (need_mask) apply_mask(rb, cc + 32);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(rb[i]));
+                    if (cc + 64 < kBN) tmem_ld_wait();
+                }
+            }
+            const float m_new = fmaxf(m_run, m_blk);
+            const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;   // fully masked so far: keep exp2 finite
+            const float alpha = ex2_approx((m_run - m_use) * c);       // m_run = -inf -> 0
+            const float mc = m_use * c;
+            // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle), row sum
+            auto emit = [&](uint32_t (&r)[32], int cc) {
+                if (need_mask) apply_mask(r, cc);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
+                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half (cc / 64)
+                unsigned char* prow = t.sP + (cc >> 6) * kTileBytes + row * 128;
+                const int chunk0 = (cc & 63) >> 3;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int chunk = (chunk0 + q4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                }
+            };
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(t.tmem_s + lane_base, ra);
+                tmem_ld_wait();
+#pragma unroll
+                for (int cc = 0; cc < kBN; cc += 64) {
+                    tmem_ld32_issue(t.tmem_s + lane_base + cc + 32, rb);
+                    emit(ra, cc);
+                    tmem_ld_wait();
+                    if (cc + 64 < kBN) tmem_ld32_issue(t.tmem_s + lane_base + cc + 64, ra);
+                    emit(rb, cc + 32);
+                    if (cc + 64 < kBN) tmem_ld_wait();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(t.s_free);       // S may be overwritten by the next Q K^T
+            fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+            mbar_arrive(t.p_full);
+
+            m_run = m_new;
+
+            mbar_wait(t.pv_full, j & 1);
+            tc_fence_after();
+            l_run = fmaf(l_run, alpha, tmem_ld1(t.tmem_l + lane_base));   // row sum of the bf16 P, from the tensor core
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(t.tmem_pv + lane_base, ra);
+                tmem_ld32_issue(t.tmem_pv + lane_base + 32, rb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(ra[i]));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(rb[i]));
+            }
+            tc_fence_before();
+        }
+        // epilogue: O / l -> bf16 -> out[b, qi, h, :]; a fully masked row is 0/0 = NaN like the reference
+        if (qi < a.Lq) {
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD;
+#pragma unroll
+            for (int i = 0; i < kD; i += 8) {
+                uint32_t w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[i + 2 * u] * inv, o[i + 2 * u + 1] * inv);
+                    w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                }
+                *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            if (a.lse != nullptr)
+                a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_run * c + log2f(l_run)) * 0.6931471805599453f;
+        }
+}
+
 constexpr int kFwdThreads = 192;
 // Q + 2x(K,V) + P + barriers = 112.1 KB, so that two CTAs (and their 2 x 256 TMEM columns) share one SM
 constexpr int kFwdSmem = kTileBytes /*Q*/ + 4 * kTileBytes /*K,V x2*/ + 2 * kTileBytes /*P*/ + 128 /*barriers*/ + 128 /*ones*/;
@@ -266,128 +402,16 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
     } else {
         // ===== softmax + epilogue: thread = query row =====
-        const int row = threadIdx.x;           // 0..127 = TMEM lane
-        const int qi = q0 + row;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        float o[kD];
-#pragma unroll
-        for (int i = 0; i < kD; ++i) o[i] = 0.0f;
-        float m_run = -INFINITY;   // running max of the raw scores
-        float l_run = 0.0f;
-        const float c = a.scale_log2;
-        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
-
-        for (int j = 0; j < nblk; ++j) {
-            const int key0 = j * kBN;
-            // mask limit for this row: keys >= lim are masked
-            int lim = kvlen;
-            if (a.causal) lim = min(lim, qi + 1);
-            const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
-
-            mbar_wait(&bars->s_full, j & 1);
-            tc_fence_after();
-            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + cc + i;
-                    bool dead = key >= lim;
-                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                    if (dead) r[i] = 0xff800000u;   // -inf
-                }
-            };
-            // pass 1: row max.  TMEM loads are double-buffered: chunk c+1 is in flight while chunk c is reduced.
-            float m_blk = -INFINITY;
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(tmem_s + lane_base, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int cc = 0; cc < kBN; cc += 64) {
-                    tmem_ld32_issue(tmem_s + lane_base + cc + 32, rb);
-                    if (need_mask) apply_mask(ra, cc);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(ra[i]));
-                    tmem_ld_wait();
-                    if (cc + 64 < kBN) tmem_ld32_issue(tmem_s + lane_base + cc + 64, ra);
-                    if (need_mask) apply_mask(rb, cc + 32);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(rb[i]));
-                    if (cc + 64 < kBN) tmem_ld_wait();
-                }
-            }
-            const float m_new = fmaxf(m_run, m_blk);
-            const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;   // fully masked so far: keep exp2 finite
-            const float alpha = ex2_approx((m_run - m_use) * c);       // m_run = -inf -> 0
-            const float mc = m_use * c;
-            // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle), row sum
-            auto emit = [&](uint32_t (&r)[32], int cc) {
-                if (need_mask) apply_mask(r, cc);
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
-                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half (cc / 64)
-                unsigned char* prow = sP + (cc >> 6) * kTileBytes + row * 128;
-                const int chunk0 = (cc & 63) >> 3;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = (chunk0 + q4) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                }
-            };
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(tmem_s + lane_base, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int cc = 0; cc < kBN; cc += 64) {
-                    tmem_ld32_issue(tmem_s + lane_base + cc + 32, rb);
-                    emit(ra, cc);
-                    tmem_ld_wait();
-                    if (cc + 64 < kBN) tmem_ld32_issue(tmem_s + lane_base + cc + 64, ra);
-                    emit(rb, cc + 32);
-                    if (cc + 64 < kBN) tmem_ld_wait();
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
-            fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
-            mbar_arrive(&bars->p_full);
-
-            m_run = m_new;
-
-            mbar_wait(&bars->pv_full, j & 1);
-            tc_fence_after();
-            l_run = fmaf(l_run, alpha, tmem_ld1(tmem_l + lane_base));   // row sum of the bf16 P, from the tensor core
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(tmem_pv + lane_base, ra);
-                tmem_ld32_issue(tmem_pv + lane_base + 32, rb);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(ra[i]));
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(rb[i]));
-            }
-            tc_fence_before();
-        }
-        // epilogue: O / l -> bf16 -> out[b, qi, h, :]; a fully masked row is 0/0 = NaN like the reference
-        if (qi < a.Lq) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD;
-#pragma unroll
-            for (int i = 0; i < kD; i += 8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[i + 2 * u] * inv, o[i + 2 * u + 1] * inv);
-                    w[u] = *reinterpret_cast<const uint32_t*>(&v2);
-                }
-                *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            if (a.lse != nullptr)
-                a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_run * c + log2f(l_run)) * 0.6931471805599453f;
-        }
+        FwdTile t;
+        t.s_full = &bars->s_full;
+        t.s_free = &bars->s_free;
+        t.p_full = &bars->p_full;
+        t.pv_full = &bars->pv_full;
+        t.tmem_s = tmem_s;
+        t.tmem_pv = tmem_pv;
+        t.tmem_l = tmem_l;
+        t.sP = sP;
+        fwd_softmax_tile(a, t, threadIdx.x, q0, b, h, kvlen, nblk);
     }
 
     tc_fence_before();
@@ -395,6 +419,158 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (warp == 5) {
         tc_fence_after();
         tmem_dealloc(tmem, 256);
+    }
+}
+
+// ---- forward, two query tiles per CTA in ping-pong -------------------------------------------
+// 10 warps: softmax warpgroup 0 (warps 0-3, tile 0), softmax warpgroup 1 (warps 4-7, tile 1), TMA
+// producer (warp 8), MMA issuer (warp 9).  Both tiles share the K/V stages; while one warpgroup
+// runs its softmax the tensor core works for the other (S, PV and row-sum MMAs), so the serial
+// MMA -> softmax -> MMA chain of a single tile no longer leaves the tensor pipe idle.
+// TMEM: S0 0-127 | S1 128-255 | PV0 256-319 | PV1 320-383 | L0 384-399 | L1 400-415 (512 allocated).
+struct __align__(8) MhaBarriers2 {
+    uint64_t q_full;
+    uint64_t kv_full[2];
+    uint64_t kv_empty[2];
+    uint64_t s_full[2];
+    uint64_t s_free[2];
+    uint64_t p_full[2];
+    uint64_t pv_full[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+constexpr int kFwd2Threads = 320;
+constexpr int kFwd2Smem = 2 * kTileBytes /*Q x2*/ + 4 * kTileBytes /*K,V x2*/ + 4 * kTileBytes /*P x2*/ + 128 + 128;
+
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+mha_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sQ = smem;                       // 2 tiles
+    unsigned char* sK = sQ + 2 * kTileBytes;        // 2 stages
+    unsigned char* sV = sK + 2 * kTileBytes;        // 2 stages
+    unsigned char* sP = sV + 2 * kTileBytes;        // 2 tiles x [2 key halves][128][128B]
+    MhaBarriers2* bars = reinterpret_cast<MhaBarriers2*>(sP + 4 * kTileBytes);
+    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sP + 4 * kTileBytes + 128);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
+    fence_proxy_async();
+    const int q0 = blockIdx.x * (2 * kBM);
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int ntile = (q0 + kBM < a.Lq) ? 2 : 1;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    int k_end = a.causal ? min(kvlen, q0 + kBM * ntile) : kvlen;
+    if (a.dense_mask) k_end = a.Lk;
+    const int nblk = max(1, (k_end + kBN - 1) / kBN);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->kv_full[s], 1);
+            mbar_init(&bars->kv_empty[s], 1);
+            mbar_init(&bars->s_full[s], 1);
+            mbar_init(&bars->s_free[s], 128);
+            mbar_init(&bars->p_full[s], 128);
+            mbar_init(&bars->pv_full[s], 1);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(&bars->q_full, ntile * kTileBytes);
+            for (int t = 0; t < ntile; ++t) tma_load_4d(sQ + t * kTileBytes, &tm_q, 0, h, q0 + t * kBM, b, &bars->q_full);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
+                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
+                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);
+            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);
+            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
+            auto issue_s = [&](int t, int stage) {
+                const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
+                const uint32_t k_addr = smem_u32(sK + stage * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem + t * 128, smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+                              smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full[t]);
+            };
+            mbar_wait(&bars->q_full, 0);
+            mbar_wait(&bars->kv_full[0], 0);
+            tc_fence_after();
+            for (int t = 0; t < ntile; ++t) issue_s(t, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
+                for (int t = 0; t < ntile; ++t) {
+                    const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
+                    mbar_wait(&bars->p_full[t], j & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk) {
+                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                        umma_bf16(tmem + 256 + t * 64, ad, smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024), idesc_pv,
+                                  kk > 0 ? 1u : 0u);
+                        umma_bf16(tmem + 384 + t * 16, ad, ones_desc, idesc_l, kk > 0 ? 1u : 0u);
+                    }
+                    tc_commit(&bars->pv_full[t]);
+                    if (t == ntile - 1) tc_commit(&bars->kv_empty[s]);
+                    if (j + 1 < nblk) {
+                        if (t == 0) mbar_wait(&bars->kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                        mbar_wait(&bars->s_free[t], j & 1);   // this tile's S buffer has been consumed
+                        tc_fence_after();
+                        issue_s(t, (j + 1) & 1);
+                    }
+                }
+            }
+        }
+    } else {
+        // ===== softmax warpgroups =====
+        const int t = warp >> 2;
+        if (t < ntile) {
+            FwdTile ft;
+            ft.s_full = &bars->s_full[t];
+            ft.s_free = &bars->s_free[t];
+            ft.p_full = &bars->p_full[t];
+            ft.pv_full = &bars->pv_full[t];
+            ft.tmem_s = tmem + t * 128;
+            ft.tmem_pv = tmem + 256 + t * 64;
+            ft.tmem_l = tmem + 384 + t * 16;
+            ft.sP = sP + t * 2 * kTileBytes;
+            fwd_softmax_tile(a, ft, threadIdx.x & 127, q0 + t * kBM, b, h, kvlen, nblk);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -761,9 +937,18 @@ extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, con
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = static_cast<__nv_bfloat16*>(out);
     a.lse = lse;
-    ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-    dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-    mha_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, a);
+    // Two query tiles per CTA in ping-pong when there is more than one tile of queries
+    // ("mha_variant": 0 = auto, 1 = always one tile per CTA, 2 = always two).
+    const int variant = get_opt("mha_variant");
+    if (variant == 2 || (variant == 0 && Lq >= 1024)) {   // measured: ping-pong wins from L ~ 1k on
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
+        dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
+        mha_fwd2_kernel<<<grid, kFwd2Threads, kFwd2Smem, st>>>(tq, tk, tv, a);
+    } else {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
+        mha_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, a);
+    }
     ASR_LAUNCH_CHECK();
     return 0;
 }

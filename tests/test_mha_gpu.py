@@ -15,6 +15,15 @@ MHA = load_golden("mha")
 CASES = ["self_pad", "self_causal", "cross", "nomask"]
 
 
+@pytest.fixture(autouse=True, params=[0, 1, 2], ids=["auto", "one_tile", "two_tile_pingpong"])
+def fwd_variant(request):
+    """Forward kernel variant: one 128-query tile per CTA, or two tiles in ping-pong."""
+    lib = pkg("_lib")
+    lib.set_option("mha_variant", request.param)
+    yield request.param
+    lib.set_option("mha_variant", 0)
+
+
 def _torch_core(q, k, v, mask=None, scale=None):
     """fp32 reference of the core on [B,L,H,D] tensors (bmm / scale / masked_fill / softmax / bmm)."""
     B, Lq, H, D = q.shape

@@ -169,11 +169,14 @@ def probe_mha(res):
                 check(L.asr_mha_bwd_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(do), ptr(lse), None, None, int(causal),
                                          B, H, Ls, Ls, 64, scale, ptr(gq), ptr(gk), ptr(gv), ptr(ws), wsb, sp()), "mha_bwd")
             div = 2.0 if causal else 1.0
-            med, best = timeit(fwd)
             fl = 4.0 * B * H * Ls * Ls * 64 / div
-            res.append({"kernel": "mha_fwd", "B": B, "L": Ls, "H": H, "causal": causal, "us": med * 1e6,
-                        "TFLOPs": fl / max(med, 1e-9) / 1e12})
-            print(res[-1], flush=True)
+            for variant in (1, 2):
+                lib.set_option("mha_variant", variant)
+                med, best = timeit(fwd)
+                res.append({"kernel": "mha_fwd", "variant": variant, "B": B, "L": Ls, "H": H, "causal": causal,
+                            "us": med * 1e6, "TFLOPs": fl / max(med, 1e-9) / 1e12})
+                print(res[-1], flush=True)
+            lib.set_option("mha_variant", 0)
             med, best = timeit(bwd)
             fl = 10.0 * B * H * Ls * Ls * 64 / div
             res.append({"kernel": "mha_bwd", "B": B, "L": Ls, "H": H, "causal": causal, "us": med * 1e6,
