@@ -29,6 +29,10 @@
 // 2^-400 for T=1600, S=80, far beyond fp32 exponents.  Log space is the robust choice.
 #include "common.cuh"
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+
 namespace asr {
 
 __device__ __forceinline__ float neg_inf() { return __int_as_float(0xff800000); }
@@ -43,6 +47,7 @@ struct CtcArgs {
     const int* in_len;
     const int* tgt_len;
     int B, T, V, S, blank, SP;
+    int Bn;       // batch size the mean loss is normalised by (>= B when this launch covers a slice of the batch)
     float* nll;
     float* g;     // may be null
     float* glp;   // [B,T,SP] log2-probabilities: [0] = blank, [1+j] = label j, [S+1] = kNeg
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
     if (tid == NT - 1) glp[a.S + 1] = kNeg;   // "impossible" slot read by out-of-range lattice states
 
     if (GRAD) {
-        const float coef = 1.0f / (Ssum * (float)a.B * (float)max(Sb, 1));
+        const float coef = 1.0f / (Ssum * (float)a.Bn * (float)max(Sb, 1));
         float4* gv = reinterpret_cast<float4*>(g + lead);
 #pragma unroll
         for (int j = 0; j < VPT; ++j) {
@@ -432,7 +437,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
             // apply g[t,c] -= occupancy/(B*len) right here: one fire-and-forget RED.ADD per touched
             // class and frame (repeats merged by their first occurrence -> one addend per address,
             // deterministic); occupancies below 1e-12 cannot change the fp32 gradient and are skipped
-            const float scale = 1.0f / ((float)a.B * (float)max(Sb, 1));
+            const float scale = 1.0f / ((float)a.Bn * (float)max(Sb, 1));
             float* g_b = a.g + (size_t)b * T * a.V;
             if (!any_dup) {
 #pragma unroll 4
@@ -514,6 +519,257 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
     }
 }
 
+// ---------------------------------------------------------------------------------
+// K2, two-warp version (default).  Sweep 1 (alpha + checkpoints every 32 frames) is the same
+// sequential recursion on warp 0.  In sweep 2 the two recursions run on different warps as a
+// pipeline over 16-frame half-chunks: warp 0 recomputes alpha from the checkpoints into a
+// double-buffered block buffer, warp 1 runs beta over the finished block, forms the
+// occupancies and writes them out.  The alpha recompute therefore leaves the critical path
+// (at the price of recomputing every odd half-chunk's predecessor: 1.5x alpha work).
+// ---------------------------------------------------------------------------------
+constexpr int kHalf = 16;   // frames per pipeline step
+constexpr int kCk = 32;     // frames per checkpoint
+
+struct __align__(8) LatticeSync {
+    uint64_t ready[2];
+    uint64_t freeb[2];
+    float nll2;
+    int feasible;
+};
+
+template <int NS>
+__global__ void __launch_bounds__(128) ctc_lattice2_kernel(const CtcArgs a) {
+    constexpr int NH = NS / 2;
+    constexpr int NSL = 32 * NS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int cwarp = (blockDim.x >> 5) - 1;   // consumer warp: the last one (idle warps in between only hit the barriers)
+    const int b = blockIdx.x;
+    const int T = a.T, SP = a.SP;
+    const int ZI = a.S + 1;
+    const int Tb = min(max(__ldg(a.in_len + b), 0), T);
+    const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
+    const int nck_max = (T + kCk - 1) / kCk;
+
+    float* lpring = reinterpret_cast<float*>(smem_raw);         // [4][kHalf][SP]
+    float* abuf = lpring + (size_t)4 * kHalf * SP;              // [2][kHalf][NSL]
+    float* ckpt = abuf + (size_t)2 * kHalf * NSL;               // [nck_max][NSL]
+    float* blpart = ckpt + (size_t)nck_max * NSL;               // [kHalf][33]
+    int* tgt = reinterpret_cast<int*>(blpart + (size_t)kHalf * 33);   // [32*NH]
+    LatticeSync* sync = reinterpret_cast<LatticeSync*>(tgt + 32 * NH);
+
+    for (int j = threadIdx.x; j < 32 * NH; j += blockDim.x) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
+    if (threadIdx.x == 0) {
+        mbar_init(&sync->ready[0], 1);
+        mbar_init(&sync->ready[1], 1);
+        mbar_init(&sync->freeb[0], 1);
+        mbar_init(&sync->freeb[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    Lattice<NS> lat;
+    bool vl[NH], vb[NH];
+#pragma unroll
+    for (int q = 0; q < NH; ++q) {
+        const int j = lane * NH + q;
+        vl[q] = j < Sb;
+        vb[q] = j <= Sb;
+        lat.li[q] = vl[q] ? 1 + j : ZI;
+        lat.bi[q] = vb[q] ? 0 : ZI;
+        lat.skp[q] = vl[q] && j > 0 && tgt[j] != tgt[j - 1];
+        lat.skf[q] = vl[q] && (j + 1 < Sb) && tgt[j + 1] != tgt[j];
+    }
+    if (warp == cwarp && a.g != nullptr) {   // repeated-label links for K3
+        for (int j = lane; j < Sb; j += 32) {
+            int nxt = -1, earlier = 0;
+            for (int jj = 0; jj < j; ++jj) earlier |= (tgt[jj] == tgt[j]);
+            for (int jj = Sb - 1; jj > j; --jj)
+                if (tgt[jj] == tgt[j]) nxt = jj;
+            a.dlink[(size_t)b * a.S + j] = (nxt + 1) | (earlier << 30);
+        }
+    }
+    if (Tb == 0) {
+        if (threadIdx.x == 0) a.nll[b] = (Sb == 0) ? 0.0f : -neg_inf();
+        return;
+    }
+    float* glp_b = a.glp + (size_t)b * T * SP;
+    auto load_rows = [&](int t0, int n, float* dst) {   // one warp, cp.async, n rows from frame t0
+        const float* src = glp_b + (size_t)t0 * SP;
+        const int pieces = (n * SP) >> 2;
+        for (int i = lane; i < pieces; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+        cp_async_commit();
+    };
+
+    // ---- sweep 1 (warp 0): alpha with a checkpoint every kCk frames ----------------------
+    float al[NS];
+    if (warp == 0) {
+        const int nck = (Tb + kCk - 1) / kCk;
+        float* buf0 = lpring;                           // ring slots 0-1 = one 32-frame buffer
+        float* buf1 = lpring + (size_t)2 * kHalf * SP;   // ring slots 2-3
+        load_rows(0, min(kCk, Tb), buf0);
+        for (int c = 0; c < nck; ++c) {
+            float* cur = (c & 1) ? buf1 : buf0;
+            if (c + 1 < nck) {
+                load_rows((c + 1) * kCk, min(kCk, Tb - (c + 1) * kCk), (c & 1) ? buf0 : buf1);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const int n = min(kCk, Tb - c * kCk);
+            for (int i = 0; i < n; ++i) {
+                const float* row = cur + i * SP;
+                if (c == 0 && i == 0)
+                    lat.alpha_init(al, row, lane);
+                else
+                    lat.alpha_step(al, row, lane);
+            }
+#pragma unroll
+            for (int r = 0; r < NS; ++r) ckpt[(size_t)c * NSL + lane * NS + r] = al[r];
+            __syncwarp();
+        }
+        const float* fin = ckpt + (size_t)(nck - 1) * NSL;
+        const float a_end = fin[2 * Sb];
+        const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : kNeg;
+        const float ll2 = lse2(a_end, a_lab);
+        if (lane == 0) {
+            sync->feasible = ll2 > -1.0e29f;
+            sync->nll2 = -ll2;
+            a.nll[b] = (ll2 > -1.0e29f) ? -ll2 * 0.6931471805599453f : -neg_inf();
+        }
+    }
+    __syncthreads();
+    if (a.g == nullptr) return;
+    const float nll2 = sync->nll2;
+    if (!sync->feasible) {
+        float* g_b = a.g + (size_t)b * T * a.V;
+        const float qnan = __int_as_float(0x7fc00000);
+        const size_t n = (size_t)Tb * a.V;
+        for (size_t i = threadIdx.x; i < n; i += blockDim.x) g_b[i] = qnan;
+        for (size_t i = threadIdx.x; i < (size_t)Tb * SP; i += blockDim.x) glp_b[i] = 0.0f;
+        return;
+    }
+
+    // ---- sweep 2: two-warp pipeline over 16-frame half-chunks, last to first ------------------
+    const int nh = (Tb + kHalf - 1) / kHalf;
+    if (warp == 0) {
+        // ===== alpha recompute producer =====
+        // lp rows of half-chunk h live in ring slot h & 3
+        {
+            const int h = nh - 1;
+            load_rows(h * kHalf, min(kHalf, Tb - h * kHalf), lpring + (size_t)(h & 3) * kHalf * SP);
+        }
+        for (int h = nh - 1; h >= 0; --h) {
+            const int use = (nh - 1 - h) >> 1;            // how many times buffer h&1 was used before
+            if (use > 0) mbar_wait_fast(&sync->freeb[h & 1], (use - 1) & 1);
+            if (h > 0) {
+                load_rows((h - 1) * kHalf, kHalf, lpring + (size_t)((h - 1) & 3) * kHalf * SP);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const int n = min(kHalf, Tb - h * kHalf);
+            const float* rows = lpring + (size_t)(h & 3) * kHalf * SP;
+            float* dst = abuf + (size_t)(h & 1) * kHalf * NSL;
+            if ((h & 1) == 0) {
+                // starts on a checkpoint boundary
+                if (h > 0) {
+#pragma unroll
+                    for (int r = 0; r < NS; ++r) al[r] = ckpt[(size_t)(h / 2 - 1) * NSL + lane * NS + r];
+                }
+            } else {
+                // alpha at the end of half-chunk h-1: from the checkpoint before it, 16 steps over h-1
+                cp_async_wait<0>();
+                __syncwarp();
+                const float* prev = lpring + (size_t)((h - 1) & 3) * kHalf * SP;
+                if (h > 1) {
+#pragma unroll
+                    for (int r = 0; r < NS; ++r) al[r] = ckpt[(size_t)((h - 1) / 2 - 1) * NSL + lane * NS + r];
+                }
+                for (int i = 0; i < kHalf; ++i) {
+                    if (h == 1 && i == 0)
+                        lat.alpha_init(al, prev, lane);
+                    else
+                        lat.alpha_step(al, prev + i * SP, lane);
+                }
+            }
+            for (int i = 0; i < n; ++i) {
+                if (h == 0 && i == 0)
+                    lat.alpha_init(al, rows, lane);
+                else
+                    lat.alpha_step(al, rows + i * SP, lane);
+#pragma unroll
+                for (int r = 0; r < NS; ++r) dst[(size_t)i * NSL + lane * NS + r] = al[r];
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sync->ready[h & 1]);
+        }
+    } else if (warp == cwarp) {
+        // ===== beta + occupancy consumer =====
+        float be[NS];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) be[r] = kNeg;
+        for (int h = nh - 1; h >= 0; --h) {
+            const int use = (nh - 1 - h) >> 1;
+            mbar_wait_fast(&sync->ready[h & 1], use & 1);
+            const int t0 = h * kHalf;
+            const int n = min(kHalf, Tb - t0);
+            const float* rows = lpring + (size_t)(h & 3) * kHalf * SP;
+            float* blk = abuf + (size_t)(h & 1) * kHalf * NSL;
+            for (int i = n - 1; i >= 0; --i) {
+                const int t = t0 + i;
+                const float* row = rows + i * SP;
+                if (t == Tb - 1) {
+#pragma unroll
+                    for (int q = 0; q < NH; ++q) {
+                        const int j = lane * NH + q;
+                        be[2 * q] = (j == Sb) ? row[0] : kNeg;
+                        be[2 * q + 1] = (j == Sb - 1) ? row[lat.li[q]] : kNeg;
+                    }
+                } else {
+                    lat.beta_step(be, row, lane);
+                }
+                float* ab = blk + (size_t)i * NSL + lane * NS;
+#pragma unroll
+                for (int r = 0; r < NS; ++r) ab[r] += be[r];
+            }
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+                const float* row = rows + i * SP;
+                const float* ab = blk + (size_t)i * NSL + lane * NS;
+                const float lpb = row[0];
+                float bsum = 0.0f;
+                float* orow = glp_b + (size_t)(t0 + i) * SP;
+#pragma unroll
+                for (int q = 0; q < NH; ++q) {
+                    bsum += vb[q] ? ex2f((ab[2 * q] - lpb) + nll2) : 0.0f;
+                    const float ov = ex2f((ab[2 * q + 1] - row[lat.li[q]]) + nll2);
+                    if (vl[q]) orow[1 + lane * NH + q] = ov;
+                }
+                blpart[i * 33 + lane] = bsum;
+            }
+            __syncwarp();
+            for (int i = lane; i < n; i += 32) {
+                float sacc = 0.0f;
+#pragma unroll 8
+                for (int l = 0; l < 32; ++l) sacc += blpart[i * 33 + l];
+                glp_b[(size_t)(t0 + i) * SP] = sacc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sync->freeb[h & 1]);
+        }
+    }
+}
+
+static size_t lattice2_smem_bytes(int NS, int T, int SP) {
+    const int NH = NS / 2, NSL = 32 * NS;
+    const size_t nck = (size_t)(T + kCk - 1) / kCk;
+    size_t f = 4 * (size_t)kHalf * SP + 2 * (size_t)kHalf * NSL + nck * NSL + (size_t)kHalf * 33 + 32 * NH;
+    return f * 4 + sizeof(LatticeSync) + 16;
+}
+
 static size_t lattice_smem_bytes(int NS, int K, int T, int SP) {
     const int NH = NS / 2, NSL = 32 * NS;
     const size_t nc = (size_t)(T + K - 1) / K;
@@ -538,7 +794,7 @@ __global__ void __launch_bounds__(256) ctc_apply_kernel(const CtcArgs a) {
     const int Tb = min(max(__ldg(a.in_len + b), 0), a.T);
     if (t >= Tb) return;
     const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
-    const float scale = 1.0f / ((float)a.B * (float)max(Sb, 1));
+    const float scale = 1.0f / ((float)a.Bn * (float)max(Sb, 1));
     const float* orow = a.glp + (size_t)row * a.SP;
     const int* dl = a.dlink + (size_t)b * a.S;
     float* grow = a.g + (size_t)row * a.V;
@@ -621,7 +877,17 @@ static int launch_lattice(const CtcArgs& a, int stages, cudaStream_t st) {
                 a.T, a.S, smem);
     ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (stages & 2) {
-        ctc_lattice_kernel<NS><<<a.B, 32, smem, st>>>(a, K);
+        const size_t smem2 = lattice2_smem_bytes(NS, a.T, a.SP);
+        if (get_opt("ctc_lattice_variant") == 2 && !a.fuse_apply && smem2 <= 110 * 1024) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            {
+                int cw = get_opt("ctc_lattice_cwarp");
+                if (cw < 1 || cw > 3) cw = 1;
+                ctc_lattice2_kernel<NS><<<a.B, 32 * (cw + 1), smem2, st>>>(a);
+            }
+        } else {
+            ctc_lattice_kernel<NS><<<a.B, 32, smem, st>>>(a, K);
+        }
         ASR_LAUNCH_CHECK();
     }
     if ((stages & 4) && a.g != nullptr && !a.fuse_apply) {
@@ -630,6 +896,54 @@ static int launch_lattice(const CtcArgs& a, int stages, cudaStream_t st) {
         ASR_LAUNCH_CHECK();
     }
     return 0;
+}
+
+// One K1 / K2 / K3 sequence over the utterances described by `a`, on one stream.
+static int ctc_run(const CtcArgs& a, int stages, cudaStream_t st) {
+    if (stages & 1) {
+        const long long rows = (long long)a.B * a.T;
+        int rc = a.g ? launch_rows_nt<true>(a, rows, st) : launch_rows_nt<false>(a, rows, st);
+        if (rc != 0) return rc;
+    }
+    if ((stages & 6) == 0) return 0;
+    const int states = 2 * a.S + 1;
+    if (states <= 64) return launch_lattice<2>(a, stages, st);
+    if (states <= 128) return launch_lattice<4>(a, stages, st);
+    if (states <= 192) return launch_lattice<6>(a, stages, st);
+    if (states <= 256) return launch_lattice<8>(a, stages, st);
+    if (states <= 384) return launch_lattice<12>(a, stages, st);
+    return launch_lattice<16>(a, stages, st);
+}
+
+// Streams and events of the sliced pipeline, one set per device, created on first use.
+constexpr int kMaxChunks = 8;
+struct CtcPipe {
+    cudaStream_t rows = nullptr;
+    cudaStream_t lat[kMaxChunks] = {};
+    cudaEvent_t fork = nullptr, k1[kMaxChunks] = {}, done[kMaxChunks] = {};
+};
+static CtcPipe* ctc_pipe() {
+    static std::mutex mu;
+    static std::map<int, CtcPipe*> pipes;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { set_error("asr_ctc: cudaGetDevice failed"); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = pipes.find(dev);
+    if (it != pipes.end()) return it->second;
+    CtcPipe* p = new CtcPipe();
+    int lo = 0, hi = 0;
+    bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess;
+    // lattice slices get the highest priority: a few warps that must start the moment their rows are ready
+    ok = ok && cudaStreamCreateWithPriority(&p->rows, cudaStreamNonBlocking, lo) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; c < kMaxChunks && ok; ++c) {
+        ok = ok && cudaStreamCreateWithPriority(&p->lat[c], cudaStreamNonBlocking, hi) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&p->k1[c], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&p->done[c], cudaEventDisableTiming) == cudaSuccess;
+    }
+    if (!ok) { set_error("asr_ctc: could not create the pipeline streams: %s", cudaGetErrorString(cudaGetLastError())); delete p; return nullptr; }
+    pipes[dev] = p;
+    return p;
 }
 
 extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
@@ -652,6 +966,7 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
     a.in_len = in_len;
     a.tgt_len = tgt_len;
     a.B = B; a.T = T; a.V = V; a.S = S; a.blank = blank;
+    a.Bn = B;
     a.SP = table_stride(S);
     a.nll = nll;
     a.g = g_logits;
@@ -660,20 +975,45 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
     a.dlink = reinterpret_cast<int*>(a.glp + (size_t)B * T * a.SP);
     a.fuse_apply = get_opt("ctc_fuse_apply") == 1 ? 1 : 0;   // measured on B200: the separate K3 pass is 22% faster end to end
 
-    if (stages & 1) {
-        const long long rows = (long long)B * T;
-        int rc = g_logits ? launch_rows_nt<true>(a, rows, st) : launch_rows_nt<false>(a, rows, st);
-        if (rc != 0) return rc;
-    }
-    if ((stages & 6) == 0) return 0;
+    // The lattice kernel is a latency-bound chain over T (its duration does not depend on B),
+    // the row and apply kernels are HBM-bound.  Slicing the batch and running each slice's
+    // lattice on its own stream hides all but the last slice's lattice behind the row kernels.
+    int nchunk = get_opt("ctc_chunks");
+    if (nchunk <= 0) nchunk = (int)std::min<long long>(4, std::max<long long>(1, (long long)B * T / 65536));   // measured: 4 slices beat 2 and 8 at B*T = 410k
+    nchunk = std::min(std::min(nchunk, kMaxChunks), B);
+    if (stages != 7 || nchunk <= 1) return ctc_run(a, stages, st);
 
-    const int states = 2 * S + 1;
-    if (states <= 64) return launch_lattice<2>(a, stages, st);
-    if (states <= 128) return launch_lattice<4>(a, stages, st);
-    if (states <= 192) return launch_lattice<6>(a, stages, st);
-    if (states <= 256) return launch_lattice<8>(a, stages, st);
-    if (states <= 384) return launch_lattice<12>(a, stages, st);
-    return launch_lattice<16>(a, stages, st);
+    CtcPipe* p = ctc_pipe();
+    if (p == nullptr) return 3;
+    ASR_CHECK_CUDA(cudaEventRecord(p->fork, st));
+    ASR_CHECK_CUDA(cudaStreamWaitEvent(p->rows, p->fork, 0));
+    const int per = (B + nchunk - 1) / nchunk;
+    int used = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = c * per;
+        const int n = std::min(per, B - b0);
+        if (n <= 0) break;
+        CtcArgs ac = a;
+        ac.B = n;
+        ac.logits = a.logits + (size_t)b0 * T * V;
+        ac.targets = a.targets ? a.targets + (size_t)b0 * S : nullptr;
+        ac.in_len = a.in_len + b0;
+        ac.tgt_len = a.tgt_len + b0;
+        ac.nll = a.nll + b0;
+        ac.g = a.g ? a.g + (size_t)b0 * T * V : nullptr;
+        ac.glp = a.glp + (size_t)b0 * T * a.SP;
+        ac.dlink = a.dlink + (size_t)b0 * S;
+        int rc = ctc_run(ac, 1, p->rows);
+        if (rc != 0) return rc;
+        ASR_CHECK_CUDA(cudaEventRecord(p->k1[c], p->rows));
+        ASR_CHECK_CUDA(cudaStreamWaitEvent(p->lat[c], p->k1[c], 0));
+        rc = ctc_run(ac, 6, p->lat[c]);
+        if (rc != 0) return rc;
+        ASR_CHECK_CUDA(cudaEventRecord(p->done[c], p->lat[c]));
+        used = c + 1;
+    }
+    for (int c = 0; c < used; ++c) ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[c], 0));
+    return 0;
 }
 
 extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,

@@ -16,7 +16,10 @@
  *     workspaces are owned by the caller (PyTorch caching allocator);
  *   - tensors are contiguous, row-major; base pointers 16-byte aligned;
  *   - `stream` is a `cudaStream_t` passed as void*; all calls are asynchronous
- *     on that stream and stateless, hence re-entrant per stream;
+ *     and ordered on that stream: they start after the work already queued on it
+ *     and the work queued after them sees their results.  asr_ctc_fwd_bwd_f32 may
+ *     fork onto library-owned streams in between (event fork/join, also legal
+ *     under CUDA-graph capture); calls are stateless, hence re-entrant per stream;
  *   - there is NO CPU fallback: on a machine without an sm_100 device every
  *     compute entry point returns an error.
  */
@@ -43,7 +46,14 @@ int         asr_device_ok(void);
  * (0 = auto, 32/64/128 floats per warp), "cif_fwd_stages" (0 = auto),
  * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto), "ctc_fuse_apply"
  * (0 = separate K3 pass applies the sparse gradient update (default, faster),
- * 1 = the lattice kernel applies it itself with RED.ADD). */
+ * 1 = the lattice kernel applies it itself with RED.ADD), "ctc_lattice_variant"
+ * (0 = one warp per utterance (default), 2 = two-warp alpha-producer /
+ * beta-consumer pipeline), "ctc_lattice_cwarp" (variant 2: warp index of the
+ * consumer, 1..3), "ctc_chunks" (asr_ctc_fwd_bwd_f32 slices the batch into this
+ * many pieces and runs each slice's lattice on a library-owned stream so that it
+ * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
+ * max 8; results are bit-identical for every value), "mha_variant" (0 = auto,
+ * 1 = one tile per CTA, 2 = two-tile ping-pong). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
 /* Number of kernels launched by this library since load (all streams). */

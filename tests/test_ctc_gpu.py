@@ -15,13 +15,16 @@ CTC = load_golden("ctc")
 CASES = sorted({k.split("_")[0] for k in CTC.files})
 
 
-@pytest.fixture(autouse=True, params=[0, 1], ids=["separate_apply", "fused_apply"])
+@pytest.fixture(autouse=True, params=[(0, 0), (0, 2), (1, 0)], ids=["one_warp_lattice", "two_warp_lattice", "fused_apply"])
 def apply_mode(request):
-    """Sparse gradient update as the separate K3 pass (default) or inside the lattice kernel."""
+    """Lattice kernel variants: one-warp lattice + separate K3 pass (default), the two-warp
+    producer/consumer lattice, and the one-warp lattice that applies the sparse update itself."""
     lib = pkg("_lib")
-    lib.set_option("ctc_fuse_apply", request.param)
+    lib.set_option("ctc_fuse_apply", request.param[0])
+    lib.set_option("ctc_lattice_variant", request.param[1])
     yield request.param
     lib.set_option("ctc_fuse_apply", 0)
+    lib.set_option("ctc_lattice_variant", 0)
 
 
 def _ours(logits, targets, in_len, need_grad=True):
@@ -166,3 +169,24 @@ def test_determinism():
     _, n1, g1 = _ours(logits, targets, in_len)
     _, n2, g2 = _ours(logits, targets, in_len)
     assert torch.equal(n1, n2) and torch.equal(g1, g2)
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 8])
+def test_sliced_pipeline_is_bit_identical(chunks):
+    """The batch-sliced multi-stream pipeline (option ctc_chunks) must not change a single bit:
+    every utterance's lattice is independent and the mean-loss normaliser stays the full B."""
+    lib = pkg("_lib")
+    B, T, V, S = 11, 70, 257, 9        # 11 utterances: ragged slices for every chunk count
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=321)
+    try:
+        lib.set_option("ctc_chunks", 1)
+        loss1, nll1, g1 = _ours(logits, targets, in_len)
+        lib.set_option("ctc_chunks", chunks)
+        loss2, nll2, g2 = _ours(logits, targets, in_len)
+        # and again, back to back on the same streams (event reuse)
+        loss3, nll3, g3 = _ours(logits, targets, in_len)
+    finally:
+        lib.set_option("ctc_chunks", 0)
+    torch.cuda.synchronize()
+    assert torch.equal(nll1, nll2) and torch.equal(g1, g2) and torch.equal(loss1, loss2)
+    assert torch.equal(nll1, nll3) and torch.equal(g1, g3)

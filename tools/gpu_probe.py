@@ -125,12 +125,12 @@ def probe_ctc(res, shapes):
         def run(grad):
             check(L.asr_ctc_fwd_bwd_f32(ptr(logits), ptr(targets), ptr(in_len), ptr(tgt_len), B, T, V, S, V - 1,
                                         ptr(nll), ptr(g) if grad else None, ptr(ws), wsb, sp()), "ctc")
-        lib.set_option("ctc_fuse_apply", 1)
+        lib.set_option("ctc_lattice_variant", 1)
         med, best = timeit(lambda: run(True), iters=4)
-        res.append({"kernel": "ctc_fwd_bwd_fused_red", "B": B, "T": T, "S": S, "us": med * 1e6,
+        res.append({"kernel": "ctc_fwd_bwd_one_warp_lattice", "B": B, "T": T, "S": S, "us": med * 1e6,
                     "GBps_alg": alg / max(med, 1e-9) / 1e9})
         print(res[-1], flush=True)
-        lib.set_option("ctc_fuse_apply", 0)
+        lib.set_option("ctc_lattice_variant", 0)
         med, best = timeit(lambda: run(True), iters=4)
         res.append({"kernel": "ctc_fwd_bwd", "B": B, "T": T, "S": S, "V": V, "valid_frames": valid, "us": med * 1e6,
                     "best_us": best * 1e6, "GBps_alg": alg / max(med, 1e-9) / 1e9})
