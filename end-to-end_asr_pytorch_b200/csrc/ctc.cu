@@ -8,7 +8,7 @@
 //
 //  K1 ctc_rows     one CTA per frame row (b,t): the row lives in registers; one pass
 //                  gives the row log-sum-exp, the <= S+1 log-probs the lattice needs
-//                  (gathered into a compact [B,T,S+2] table, log2 domain) and - when a
+//                  (gathered into a compact [B,T,S+3] table, log2 domain, relative to the frame's blank) and - when a
 //                  gradient is wanted - the dense part of it, softmax * 1/(B*len).
 //                  Pure streaming: 4V bytes read + 4V bytes written per frame.
 //  K2 ctc_lattice  one warp per utterance: log-space (base 2) alpha sweep with
@@ -53,6 +53,8 @@ struct CtcArgs {
     float* glp;   // [B,T,SP] log2-probabilities: [0] = blank, [1+j] = label j, [S+1] = kNeg
     int* dlink;   // [B,S] repeated-label links: (next occurrence + 1) | (has earlier occurrence << 30)
     int fuse_apply;   // 1: the lattice kernel applies the sparse update itself (RED.ADD), K3 is not launched
+    float* ckpt;      // [B][ckpt_stride] checkpoints of the bidirectional lattice (lane-private slots)
+    size_t ckpt_stride;
 };
 
 // ---------------------------------------------------------------------------------
@@ -144,12 +146,24 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
     // gather the log-probs the lattice needs: blank + this utterance's labels
     const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
     float* glp = a.glp + (size_t)row * a.SP;
+    // The lattice only needs each frame's probabilities up to a common factor (it cancels in
+    // alpha*beta/(p*likelihood)), so the row is stored relative to the frame's blank: the blank
+    // entry is exactly 0 and the recursions stay small in magnitude - their fp32 rounding error
+    // scales with |alpha|, which otherwise grows by log2(V) bits per frame.  The factor itself
+    // goes to its own slot and is added back to the log-likelihood by the lattice kernel.
+    const float xb = __ldg(x + a.blank);
+    const bool rel_ok = (xb - lse) >= -1.0e4f;       // a (nearly) impossible blank: fall back to a fixed offset
+    const float off = rel_ok ? (xb - lse) : -1.0e4f;
     for (int j = tid; j <= Sb; j += NT) {
         int c = (j == 0) ? a.blank : (int)__ldg(a.targets + (size_t)b * a.S + (j - 1));
         c = min(max(c, 0), V - 1);
-        glp[j] = (__ldg(x + c) - lse) * 1.4426950408889634f;   // log2 domain for the lattice
+        const float xc = __ldg(x + c);
+        glp[j] = (rel_ok ? (xc - xb) : ((xc - lse) + 1.0e4f)) * 1.4426950408889634f;   // log2 domain for the lattice
     }
-    if (tid == NT - 1) glp[a.S + 1] = kNeg;   // "impossible" slot read by out-of-range lattice states
+    if (tid == NT - 1) {
+        glp[a.S + 1] = kNeg;                          // "impossible" slot read by out-of-range lattice states
+        glp[a.S + 2] = off * 1.4426950408889634f;     // log2 of the frame's common factor
+    }
 
     if (GRAD) {
         const float coef = 1.0f / (Ssum * (float)a.Bn * (float)max(Sb, 1));
@@ -336,6 +350,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
 
     // ---- sweep 1: alpha, checkpoint at the end of every chunk --------------------
     float al[NS];
+    float off_acc = 0.0f;
     load_chunk(0, lpbuf0);
     for (int c = 0; c < nc; ++c) {
         float* cur = (c & 1) ? lpbuf1 : lpbuf0;
@@ -347,6 +362,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
         }
         __syncwarp();
         const int n = min(K, Tb - c * K);
+        for (int i = lane; i < n; i += 32) off_acc += cur[i * SP + ZI + 1];   // the frames' common factors
         for (int i = 0; i < n; ++i) {
             const float* row = cur + i * SP;
             if (c == 0 && i == 0)
@@ -365,10 +381,11 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
         const float* fin = ckpt + (size_t)(nc - 1) * NSL;
         const float a_end = fin[2 * Sb];
         const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : kNeg;
-        const float ll2 = lse2(a_end, a_lab);
+        const float ll2 = lse2(a_end, a_lab);       // of the rows relative to their blanks
         feasible = ll2 > -1.0e29f;
         nll2 = -ll2;
-        if (lane == 0) a.nll[b] = feasible ? nll2 * 0.6931471805599453f : -neg_inf();
+        const float off = warp_sum(off_acc);
+        if (lane == 0) a.nll[b] = feasible ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
     }
     if (a.g == nullptr) return;
 
@@ -520,53 +537,64 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
 }
 
 // ---------------------------------------------------------------------------------
-// K2, two-warp version (default).  Sweep 1 (alpha + checkpoints every 32 frames) is the same
-// sequential recursion on warp 0.  In sweep 2 the two recursions run on different warps as a
-// pipeline over 16-frame half-chunks: warp 0 recomputes alpha from the checkpoints into a
-// double-buffered block buffer, warp 1 runs beta over the finished block, forms the
-// occupancies and writes them out.  The alpha recompute therefore leaves the critical path
-// (at the price of recomputing every odd half-chunk's predecessor: 1.5x alpha work).
+// K2, bidirectional variant: the two recursions meet in the middle, four warps per utterance.
+//   phase 1   warp 0: alpha over frames [0,Tm)        warp 1: beta over frames [Tb-1 .. Tm]
+//             (both keep a checkpoint per K frames in the global workspace)
+//   midpoint  alpha(Tm-1) and beta(Tm) are exchanged through shared memory; the likelihood is
+//             sum_s alpha(Tm-1,s) beta(Tm-1,s) / p(Tm-1,s)  (any frame's cut gives it)
+//   phase 2   warp 0: beta continues down through [0,Tm)    warp 2: recomputes alpha, one block ahead
+//             warp 1: alpha continues up through [Tm,Tb)     warp 3: recomputes beta, one block ahead
+// The dependent chain is half as long as in the one-warp kernel, and in phase 2 the
+// recomputation runs concurrently on its own warp: the hand-over of a block of K frames is a
+// hardware named barrier (bar.arrive / bar.sync, nobody spins), the blocks live in a two-slot
+// ring, the gathered rows in a three-slot ring filled with cp.async by the recomputing warp.
+// Boundary conditions are "virtual" frames so that every frame is a regular step:
+//   alpha(-1) = delta(s = 0),  beta(Tb) = delta(s = 2*Sb)   (log2 domain: 0 and kNeg).
 // ---------------------------------------------------------------------------------
-constexpr int kHalf = 16;   // frames per pipeline step
-constexpr int kCk = 32;     // frames per checkpoint
-
-struct __align__(8) LatticeSync {
-    uint64_t ready[2];
-    uint64_t freeb[2];
+struct LatticeMid {
     float nll2;
     int feasible;
+    float off_b;   // sum of the common factors of the frames of the second half
 };
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <int NS>
-__global__ void __launch_bounds__(128) ctc_lattice2_kernel(const CtcArgs a) {
+__global__ void __launch_bounds__(128) ctc_lattice_mitm_kernel(const CtcArgs a, int K) {
     constexpr int NH = NS / 2;
     constexpr int NSL = 32 * NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int cwarp = (blockDim.x >> 5) - 1;   // consumer warp: the last one (idle warps in between only hit the barriers)
+    const int half = warp & 1;        // 0: frames [0,Tm), 1: frames [Tm,Tb)
+    const int helper = warp >> 1;     // 1: the recomputing warp of the half (phase 2 only)
     const int b = blockIdx.x;
     const int T = a.T, SP = a.SP;
     const int ZI = a.S + 1;
     const int Tb = min(max(__ldg(a.in_len + b), 0), T);
     const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
-    const int nck_max = (T + kCk - 1) / kCk;
 
-    float* lpring = reinterpret_cast<float*>(smem_raw);         // [4][kHalf][SP]
-    float* abuf = lpring + (size_t)4 * kHalf * SP;              // [2][kHalf][NSL]
-    float* ckpt = abuf + (size_t)2 * kHalf * NSL;               // [nck_max][NSL]
-    float* blpart = ckpt + (size_t)nck_max * NSL;               // [kHalf][33]
-    int* tgt = reinterpret_cast<int*>(blpart + (size_t)kHalf * 33);   // [32*NH]
-    LatticeSync* sync = reinterpret_cast<LatticeSync*>(tgt + 32 * NH);
+    const size_t per_half = (size_t)3 * K * SP + (size_t)2 * K * NSL + (size_t)3 * NSL + (size_t)K * 33;
+    float* mine = reinterpret_cast<float*>(smem_raw) + half * per_half;
+    float* rows_ring = mine;                               // [3][K][SP] gathered rows, block c in slot c % 3
+    float* blk_ring = rows_ring + (size_t)3 * K * SP;      // [2][K][NSL] recomputed recursion, block c in slot c & 1
+    float* ck_ring = blk_ring + (size_t)2 * K * NSL;       // [3][NSL] checkpoint that starts the recomputation of block c
+    float* blpart = ck_ring + (size_t)3 * NSL;             // [K][33]
+    float* xchg = reinterpret_cast<float*>(smem_raw) + 2 * per_half;   // [2][NSL]: alpha(Tm-1), beta(Tm)
+    int* tgt = reinterpret_cast<int*>(xchg + 2 * NSL);     // [32*NH]
+    LatticeMid* mid = reinterpret_cast<LatticeMid*>(tgt + 32 * NH);
+    auto rows_of = [&](int c) { return rows_ring + (size_t)(c % 3) * K * SP; };
+    auto blk_of = [&](int c) { return blk_ring + (size_t)(c & 1) * K * NSL; };
+    auto ck_of = [&](int c) { return ck_ring + (size_t)(c % 3) * NSL; };
+    // named barriers 1..8 (0 is __syncthreads): per half, "block slot filled" and "block slot free"
+    auto bar_full = [&](int c) { return 1 + 4 * half + (c & 1); };
+    auto bar_free = [&](int c) { return 3 + 4 * half + (c & 1); };
 
-    for (int j = threadIdx.x; j < 32 * NH; j += blockDim.x) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
-    if (threadIdx.x == 0) {
-        mbar_init(&sync->ready[0], 1);
-        mbar_init(&sync->ready[1], 1);
-        mbar_init(&sync->freeb[0], 1);
-        mbar_init(&sync->freeb[1], 1);
-        fence_mbar_init();
-    }
+    for (int j = threadIdx.x; j < 32 * NH; j += 128) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
     __syncthreads();
     Lattice<NS> lat;
     bool vl[NH], vb[NH];
@@ -580,7 +608,7 @@ __global__ void __launch_bounds__(128) ctc_lattice2_kernel(const CtcArgs a) {
         lat.skp[q] = vl[q] && j > 0 && tgt[j] != tgt[j - 1];
         lat.skf[q] = vl[q] && (j + 1 < Sb) && tgt[j + 1] != tgt[j];
     }
-    if (warp == cwarp && a.g != nullptr) {   // repeated-label links for K3
+    if (warp == 3 && a.g != nullptr) {   // repeated-label links for K3
         for (int j = lane; j < Sb; j += 32) {
             int nxt = -1, earlier = 0;
             for (int jj = 0; jj < j; ++jj) earlier |= (tgt[jj] == tgt[j]);
@@ -593,181 +621,268 @@ __global__ void __launch_bounds__(128) ctc_lattice2_kernel(const CtcArgs a) {
         if (threadIdx.x == 0) a.nll[b] = (Sb == 0) ? 0.0f : -neg_inf();
         return;
     }
+    // frames [0,Tm) belong to half 0, [Tm,Tb) to half 1; Tm is a multiple of K (or Tb itself)
+    const int Tm = min(Tb, (((Tb + 1) >> 1) + K - 1) / K * K);
+    const int nB = Tb - Tm;
+    const int ncA = (Tm + K - 1) / K, ncB = (nB + K - 1) / K;
     float* glp_b = a.glp + (size_t)b * T * SP;
-    auto load_rows = [&](int t0, int n, float* dst) {   // one warp, cp.async, n rows from frame t0
-        const float* src = glp_b + (size_t)t0 * SP;
-        const int pieces = (n * SP) >> 2;
+    // this half's frames start at frame `base`; its checkpoints at `ck` ([block][NSL])
+    const int base = (half == 0) ? 0 : Tm;
+    const int nfr = (half == 0) ? Tm : nB;
+    const int nblk = (half == 0) ? ncA : ncB;
+    float* ck = a.ckpt + (size_t)b * a.ckpt_stride + (size_t)(half == 0 ? 0 : ncA) * NSL;
+    auto blk_len = [&](int c) { return min(K, nfr - c * K); };
+
+    auto load_rows = [&](int c) {                 // rows of this half's block c -> ring (no commit)
+        const float* src = glp_b + (size_t)(base + c * K) * SP;
+        float* dst = rows_of(c);
+        const int pieces = (blk_len(c) * SP) >> 2;
         for (int i = lane; i < pieces; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
-        cp_async_commit();
+    };
+    auto load_ck = [&](int from_block, int for_block) {   // checkpoint `from_block` -> ring slot of `for_block`
+        const float* src = ck + (size_t)from_block * NSL;
+        float* dst = ck_of(for_block);
+        for (int i = lane; i < NSL / 4; i += 32) cp_async16(dst + 4 * i, src + 4 * i);
+    };
+    auto alpha_virtual = [&](float (&v)[NS]) {    // alpha(-1)
+#pragma unroll
+        for (int r = 0; r < NS; ++r) v[r] = (lane == 0 && r == 0) ? 0.0f : kNeg;
+    };
+    auto beta_virtual = [&](float (&v)[NS]) {     // beta(Tb)
+#pragma unroll
+        for (int r = 0; r < NS; ++r) v[r] = (lane * NS + r == 2 * Sb) ? 0.0f : kNeg;
     };
 
-    // ---- sweep 1 (warp 0): alpha with a checkpoint every kCk frames ----------------------
-    float al[NS];
+    // ---- phase 1 (warps 0 and 1) -------------------------------------------------------------
+    float st[NS];   // the recursion a main warp carries: alpha (half 0) or beta (half 1)
+    float off_acc = 0.0f;
     if (warp == 0) {
-        const int nck = (Tb + kCk - 1) / kCk;
-        float* buf0 = lpring;                           // ring slots 0-1 = one 32-frame buffer
-        float* buf1 = lpring + (size_t)2 * kHalf * SP;   // ring slots 2-3
-        load_rows(0, min(kCk, Tb), buf0);
-        for (int c = 0; c < nck; ++c) {
-            float* cur = (c & 1) ? buf1 : buf0;
-            if (c + 1 < nck) {
-                load_rows((c + 1) * kCk, min(kCk, Tb - (c + 1) * kCk), (c & 1) ? buf0 : buf1);
+        alpha_virtual(st);
+        load_rows(0);
+        cp_async_commit();
+        for (int c = 0; c < nblk; ++c) {
+            if (c + 1 < nblk) {
+                load_rows(c + 1);
+                cp_async_commit();
                 cp_async_wait<1>();
             } else {
                 cp_async_wait<0>();
             }
             __syncwarp();
-            const int n = min(kCk, Tb - c * kCk);
-            for (int i = 0; i < n; ++i) {
-                const float* row = cur + i * SP;
-                if (c == 0 && i == 0)
-                    lat.alpha_init(al, row, lane);
-                else
-                    lat.alpha_step(al, row, lane);
-            }
+            const float* cur = rows_of(c);
+            const int n = blk_len(c);
+            for (int i = lane; i < n; i += 32) off_acc += cur[i * SP + ZI + 1];   // the frames' common factors
+            for (int i = 0; i < n; ++i) lat.alpha_step(st, cur + i * SP, lane);
 #pragma unroll
-            for (int r = 0; r < NS; ++r) ckpt[(size_t)c * NSL + lane * NS + r] = al[r];
+            for (int r = 0; r < NS; ++r) ck[(size_t)c * NSL + lane * NS + r] = st[r];   // alpha at the last frame of block c
             __syncwarp();
         }
-        const float* fin = ckpt + (size_t)(nck - 1) * NSL;
-        const float a_end = fin[2 * Sb];
-        const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : kNeg;
-        const float ll2 = lse2(a_end, a_lab);
+#pragma unroll
+        for (int r = 0; r < NS; ++r) xchg[lane * NS + r] = st[r];
+    } else if (warp == 1 && nB > 0) {
+        beta_virtual(st);
+        load_rows(nblk - 1);
+        cp_async_commit();
+        for (int c = nblk - 1; c >= 0; --c) {
+            if (c > 0) {
+                load_rows(c - 1);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const float* cur = rows_of(c);
+            const int n = blk_len(c);
+            for (int i = lane; i < n; i += 32) off_acc += cur[i * SP + ZI + 1];
+            for (int i = n - 1; i >= 0; --i) lat.beta_step(st, cur + i * SP, lane);
+#pragma unroll
+            for (int r = 0; r < NS; ++r) ck[(size_t)c * NSL + lane * NS + r] = st[r];   // beta at the first frame of block c
+            __syncwarp();
+        }
+#pragma unroll
+        for (int r = 0; r < NS; ++r) xchg[NSL + lane * NS + r] = st[r];
+    }
+    if (warp == 1) {
+        const float off = warp_sum(off_acc);
+        if (lane == 0) mid->off_b = off;
+    }
+    __syncthreads();
+
+    // ---- midpoint: likelihood from the cut at frame Tm-1 (warp 0) ---------------------------------
+    if (warp == 0) {
+        float be[NS];
+        if (nB > 0) {
+#pragma unroll
+            for (int r = 0; r < NS; ++r) be[r] = xchg[NSL + lane * NS + r];
+        } else {
+            beta_virtual(be);
+        }
+        const float* row = rows_of(ncA - 1) + (size_t)(Tm - 1 - (ncA - 1) * K) * SP;
+        lat.beta_step(be, row, lane);
+        float v[NS];
+        float m = kNeg;
+#pragma unroll
+        for (int q = 0; q < NH; ++q) {
+            v[2 * q] = vb[q] ? (st[2 * q] + be[2 * q]) - row[0] : kNeg;
+            v[2 * q + 1] = vl[q] ? (st[2 * q + 1] + be[2 * q + 1]) - row[lat.li[q]] : kNeg;
+            m = fmaxf(m, fmaxf(v[2 * q], v[2 * q + 1]));
+        }
+        m = warp_max(m);
+        float sum = 0.0f;
+#pragma unroll
+        for (int r = 0; r < NS; ++r) sum += ex2f(v[r] - m);
+        sum = warp_sum(sum);
+        const float ll2 = m + lg2f(sum);            // of the rows relative to their blanks
+        const float off = warp_sum(off_acc) + mid->off_b;
         if (lane == 0) {
-            sync->feasible = ll2 > -1.0e29f;
-            sync->nll2 = -ll2;
-            a.nll[b] = (ll2 > -1.0e29f) ? -ll2 * 0.6931471805599453f : -neg_inf();
+            const bool ok = ll2 > -1.0e29f;
+            mid->feasible = ok;
+            mid->nll2 = -ll2;
+            a.nll[b] = ok ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
         }
     }
     __syncthreads();
     if (a.g == nullptr) return;
-    const float nll2 = sync->nll2;
-    if (!sync->feasible) {
+    const float nll2 = mid->nll2;
+    if (!mid->feasible) {
         float* g_b = a.g + (size_t)b * T * a.V;
         const float qnan = __int_as_float(0x7fc00000);
         const size_t n = (size_t)Tb * a.V;
-        for (size_t i = threadIdx.x; i < n; i += blockDim.x) g_b[i] = qnan;
-        for (size_t i = threadIdx.x; i < (size_t)Tb * SP; i += blockDim.x) glp_b[i] = 0.0f;
+        for (size_t i = threadIdx.x; i < n; i += 128) g_b[i] = qnan;
+        for (size_t i = threadIdx.x; i < (size_t)Tb * SP; i += 128) glp_b[i] = 0.0f;
+        return;
+    }
+    if (nfr == 0) return;
+
+    // ---- phase 2 ---------------------------------------------------------------------------
+    // Blocks are visited in the direction of the continuing recursion: half 0 from its last block
+    // down to 0, half 1 from 0 up.  `seq` counts visits, blkid(seq) is the block index.
+    const int dir = (half == 0) ? -1 : 1;
+    auto blkid = [&](int seq) { return (half == 0) ? nblk - 1 - seq : seq; };
+
+    if (helper) {
+        // ===== recomputing warp: alpha (half 0) or beta (half 1) of each block from its checkpoint =====
+        // block c starts from the checkpoint of the block before it (half 0: alpha at the end of
+        // c-1) or after it (half 1: beta at the start of c+1); the virtual frame at the boundary
+        auto stage_block = [&](int seq) {
+            if (seq < nblk) {
+                const int c = blkid(seq);
+                load_rows(c);
+                const int src = c + dir;
+                if (src >= 0 && src < nblk) load_ck(src, c);
+            }
+            cp_async_commit();
+        };
+        float rc[NS];
+        stage_block(0);
+        for (int seq = 0; seq < nblk; ++seq) {
+            const int c = blkid(seq);
+            // the slots of visit seq+1 (rows) and seq (block) were last used by visit seq-2
+            if (seq >= 2) named_bar_sync(bar_free(c), 64);
+            stage_block(seq + 1);
+            cp_async_wait<1>();
+            __syncwarp();
+            const int n = blk_len(c);
+            const float* rows = rows_of(c);
+            float* blk = blk_of(c);
+            const int src = c + dir;
+            if (src >= 0 && src < nblk) {
+                const float* p = ck_of(c) + lane * NS;
+#pragma unroll
+                for (int r = 0; r < NS; ++r) rc[r] = p[r];
+            } else if (half == 0) {
+                alpha_virtual(rc);
+            } else {
+                beta_virtual(rc);
+            }
+            if (half == 0) {
+                for (int i = 0; i < n; ++i) {
+                    lat.alpha_step(rc, rows + i * SP, lane);
+#pragma unroll
+                    for (int r = 0; r < NS; ++r) blk[(size_t)i * NSL + lane * NS + r] = rc[r];
+                }
+            } else {
+                for (int i = n - 1; i >= 0; --i) {
+                    lat.beta_step(rc, rows + i * SP, lane);
+#pragma unroll
+                    for (int r = 0; r < NS; ++r) blk[(size_t)i * NSL + lane * NS + r] = rc[r];
+                }
+            }
+            named_bar_arrive(bar_full(c), 64);
+        }
         return;
     }
 
-    // ---- sweep 2: two-warp pipeline over 16-frame half-chunks, last to first ------------------
-    const int nh = (Tb + kHalf - 1) / kHalf;
-    if (warp == 0) {
-        // ===== alpha recompute producer =====
-        // lp rows of half-chunk h live in ring slot h & 3
-        {
-            const int h = nh - 1;
-            load_rows(h * kHalf, min(kHalf, Tb - h * kHalf), lpring + (size_t)(h & 3) * kHalf * SP);
+    // ===== main warp: continues its recursion through the half, adds it to the recomputed one and
+    //       turns the sums into occupancies ===================================================
+    // st switches role: half 0 continues beta from beta(Tm) (or the boundary), half 1 alpha from alpha(Tm-1)
+    if (half == 0) {
+        if (nB > 0) {
+#pragma unroll
+            for (int r = 0; r < NS; ++r) st[r] = xchg[NSL + lane * NS + r];
+        } else {
+            beta_virtual(st);
         }
-        for (int h = nh - 1; h >= 0; --h) {
-            const int use = (nh - 1 - h) >> 1;            // how many times buffer h&1 was used before
-            if (use > 0) mbar_wait_fast(&sync->freeb[h & 1], (use - 1) & 1);
-            if (h > 0) {
-                load_rows((h - 1) * kHalf, kHalf, lpring + (size_t)((h - 1) & 3) * kHalf * SP);
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-            const int n = min(kHalf, Tb - h * kHalf);
-            const float* rows = lpring + (size_t)(h & 3) * kHalf * SP;
-            float* dst = abuf + (size_t)(h & 1) * kHalf * NSL;
-            if ((h & 1) == 0) {
-                // starts on a checkpoint boundary
-                if (h > 0) {
+    } else {
 #pragma unroll
-                    for (int r = 0; r < NS; ++r) al[r] = ckpt[(size_t)(h / 2 - 1) * NSL + lane * NS + r];
-                }
-            } else {
-                // alpha at the end of half-chunk h-1: from the checkpoint before it, 16 steps over h-1
-                cp_async_wait<0>();
-                __syncwarp();
-                const float* prev = lpring + (size_t)((h - 1) & 3) * kHalf * SP;
-                if (h > 1) {
+        for (int r = 0; r < NS; ++r) st[r] = xchg[lane * NS + r];
+    }
+    for (int seq = 0; seq < nblk; ++seq) {
+        const int c = blkid(seq);
+        const int n = blk_len(c);
+        const int t0 = base + c * K;
+        const float* rows = rows_of(c);
+        float* blk = blk_of(c);
+        named_bar_sync(bar_full(c), 64);
+        if (half == 0) {
+            for (int f = n - 1; f >= 0; --f) {
+                lat.beta_step(st, rows + f * SP, lane);
+                float* ab = blk + (size_t)f * NSL + lane * NS;
 #pragma unroll
-                    for (int r = 0; r < NS; ++r) al[r] = ckpt[(size_t)((h - 1) / 2 - 1) * NSL + lane * NS + r];
-                }
-                for (int i = 0; i < kHalf; ++i) {
-                    if (h == 1 && i == 0)
-                        lat.alpha_init(al, prev, lane);
-                    else
-                        lat.alpha_step(al, prev + i * SP, lane);
-                }
+                for (int r = 0; r < NS; ++r) ab[r] += st[r];
             }
+        } else {
             for (int i = 0; i < n; ++i) {
-                if (h == 0 && i == 0)
-                    lat.alpha_init(al, rows, lane);
-                else
-                    lat.alpha_step(al, rows + i * SP, lane);
-#pragma unroll
-                for (int r = 0; r < NS; ++r) dst[(size_t)i * NSL + lane * NS + r] = al[r];
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sync->ready[h & 1]);
-        }
-    } else if (warp == cwarp) {
-        // ===== beta + occupancy consumer =====
-        float be[NS];
-#pragma unroll
-        for (int r = 0; r < NS; ++r) be[r] = kNeg;
-        for (int h = nh - 1; h >= 0; --h) {
-            const int use = (nh - 1 - h) >> 1;
-            mbar_wait_fast(&sync->ready[h & 1], use & 1);
-            const int t0 = h * kHalf;
-            const int n = min(kHalf, Tb - t0);
-            const float* rows = lpring + (size_t)(h & 3) * kHalf * SP;
-            float* blk = abuf + (size_t)(h & 1) * kHalf * NSL;
-            for (int i = n - 1; i >= 0; --i) {
-                const int t = t0 + i;
-                const float* row = rows + i * SP;
-                if (t == Tb - 1) {
-#pragma unroll
-                    for (int q = 0; q < NH; ++q) {
-                        const int j = lane * NH + q;
-                        be[2 * q] = (j == Sb) ? row[0] : kNeg;
-                        be[2 * q + 1] = (j == Sb - 1) ? row[lat.li[q]] : kNeg;
-                    }
-                } else {
-                    lat.beta_step(be, row, lane);
-                }
+                lat.alpha_step(st, rows + i * SP, lane);
                 float* ab = blk + (size_t)i * NSL + lane * NS;
 #pragma unroll
-                for (int r = 0; r < NS; ++r) ab[r] += be[r];
+                for (int r = 0; r < NS; ++r) ab[r] += st[r];
             }
-#pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-                const float* row = rows + i * SP;
-                const float* ab = blk + (size_t)i * NSL + lane * NS;
-                const float lpb = row[0];
-                float bsum = 0.0f;
-                float* orow = glp_b + (size_t)(t0 + i) * SP;
-#pragma unroll
-                for (int q = 0; q < NH; ++q) {
-                    bsum += vb[q] ? ex2f((ab[2 * q] - lpb) + nll2) : 0.0f;
-                    const float ov = ex2f((ab[2 * q + 1] - row[lat.li[q]]) + nll2);
-                    if (vl[q]) orow[1 + lane * NH + q] = ov;
-                }
-                blpart[i * 33 + lane] = bsum;
-            }
-            __syncwarp();
-            for (int i = lane; i < n; i += 32) {
-                float sacc = 0.0f;
-#pragma unroll 8
-                for (int l = 0; l < 32; ++l) sacc += blpart[i * 33 + l];
-                glp_b[(size_t)(t0 + i) * SP] = sacc;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sync->freeb[h & 1]);
         }
+        // occupancy(t,s) = exp2(alpha + beta - lp + nll); both alpha and beta include lp_t
+#pragma unroll 4
+        for (int i = 0; i < n; ++i) {
+            const float* row = rows + i * SP;
+            const float* ab = blk + (size_t)i * NSL + lane * NS;
+            const float lpb = row[0];
+            float bsum = 0.0f;
+            float* orow = glp_b + (size_t)(t0 + i) * SP;
+#pragma unroll
+            for (int q = 0; q < NH; ++q) {
+                bsum += vb[q] ? ex2f((ab[2 * q] - lpb) + nll2) : 0.0f;
+                const float ov = ex2f((ab[2 * q + 1] - row[lat.li[q]]) + nll2);
+                if (vl[q]) orow[1 + lane * NH + q] = ov;   // per label position; K3 merges repeats
+            }
+            blpart[i * 33 + lane] = bsum;
+        }
+        __syncwarp();
+        if (seq + 2 < nblk) named_bar_arrive(bar_free(c), 64);   // rows and block slot may be refilled
+        // blank column: one lane per frame sums the 32 partials
+        for (int i = lane; i < n; i += 32) {
+            float sacc = 0.0f;
+#pragma unroll 8
+            for (int l = 0; l < 32; ++l) sacc += blpart[i * 33 + l];
+            glp_b[(size_t)(t0 + i) * SP] = sacc;
+        }
+        __syncwarp();
     }
 }
 
-static size_t lattice2_smem_bytes(int NS, int T, int SP) {
+static size_t lattice_mitm_smem_bytes(int NS, int K, int SP) {
     const int NH = NS / 2, NSL = 32 * NS;
-    const size_t nck = (size_t)(T + kCk - 1) / kCk;
-    size_t f = 4 * (size_t)kHalf * SP + 2 * (size_t)kHalf * NSL + nck * NSL + (size_t)kHalf * 33 + 32 * NH;
-    return f * 4 + sizeof(LatticeSync) + 16;
+    const size_t per_half = (size_t)3 * K * SP + (size_t)2 * K * NSL + (size_t)3 * NSL + (size_t)K * 33;
+    return (2 * per_half + 2 * (size_t)NSL + 32 * NH) * 4 + sizeof(LatticeMid) + 16;
 }
 
 static size_t lattice_smem_bytes(int NS, int K, int T, int SP) {
@@ -827,13 +942,22 @@ __global__ void __launch_bounds__(256) scale_inplace_kernel(float* g, size_t n, 
 using namespace asr;
 
 static inline int round_up4(int x) { return (x + 3) & ~3; }
-// row stride of the gathered table: blank + S labels + one always-zero slot, 16-byte rows
-static inline int table_stride(int S) { return round_up4(S + 2); }
+// row stride of the gathered table: blank + S labels + the kNeg slot + the frame's common factor, 16-byte rows
+static inline int table_stride(int S) { return round_up4(S + 3); }
+
+// lattice states per lane for a target of S labels (2S+1 states over 32 lanes)
+static inline int lattice_ns(int S) {
+    const int states = 2 * S + 1;
+    return states <= 64 ? 2 : states <= 128 ? 4 : states <= 192 ? 6 : states <= 256 ? 8 : states <= 384 ? 12 : 16;
+}
+// checkpoint floats per utterance of the bidirectional lattice (blocks of >= 16 frames, both halves)
+static inline size_t ckpt_stride_floats(int T, int S) { return (size_t)(T / 16 + 3) * 32 * lattice_ns(S); }
 
 extern "C" size_t asr_ctc_workspace_bytes(int B, int T, int V, int S) {
     (void)V;
     if (B <= 0 || T <= 0 || S < 0) return 0;
-    return (size_t)B * T * table_stride(S) * sizeof(float) + (size_t)B * (S + 1) * sizeof(int) + 512;
+    return (size_t)B * T * table_stride(S) * sizeof(float) + (size_t)B * (S + 1) * sizeof(int) +
+           (size_t)B * ckpt_stride_floats(T, S) * sizeof(float) + 1024;
 }
 
 template <int NT, bool GRAD>
@@ -873,19 +997,20 @@ static int launch_lattice(const CtcArgs& a, int stages, cudaStream_t st) {
         K <<= 1;
         smem = lattice_smem_bytes(NS, K, a.T, a.SP);
     }
-    ASR_REQUIRE(smem <= 227 * 1024, "asr_ctc: T=%d S=%d needs %zu bytes of shared memory for the lattice (max 232448)",
-                a.T, a.S, smem);
-    ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (stages & 2) {
-        const size_t smem2 = lattice2_smem_bytes(NS, a.T, a.SP);
-        if (get_opt("ctc_lattice_variant") == 2 && !a.fuse_apply && smem2 <= 110 * 1024) {
-            ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice2_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            {
-                int cw = get_opt("ctc_lattice_cwarp");
-                if (cw < 1 || cw > 3) cw = 1;
-                ctc_lattice2_kernel<NS><<<a.B, 32 * (cw + 1), smem2, st>>>(a);
-            }
+        const int variant = get_opt("ctc_lattice_variant");
+        // bidirectional lattice: blocks of 32 frames, or 16 when that lets two CTAs share an SM
+        int Km = 32;
+        if (lattice_mitm_smem_bytes(NS, 32, a.SP) > 113 * 1024 && lattice_mitm_smem_bytes(NS, 16, a.SP) <= 113 * 1024) Km = 16;
+        if (lattice_mitm_smem_bytes(NS, Km, a.SP) > 227 * 1024) Km = 16;
+        const size_t smem3 = lattice_mitm_smem_bytes(NS, Km, a.SP);
+        if (variant != 1 && !a.fuse_apply && smem3 <= 227 * 1024) {
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_mitm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+            ctc_lattice_mitm_kernel<NS><<<a.B, 128, smem3, st>>>(a, Km);
         } else {
+            ASR_REQUIRE(smem <= 227 * 1024, "asr_ctc: T=%d S=%d needs %zu bytes of shared memory for the lattice (max 232448)",
+                        a.T, a.S, smem);
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(ctc_lattice_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ctc_lattice_kernel<NS><<<a.B, 32, smem, st>>>(a, K);
         }
         ASR_LAUNCH_CHECK();
@@ -973,6 +1098,8 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
     uintptr_t w = (reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255;
     a.glp = reinterpret_cast<float*>(w);
     a.dlink = reinterpret_cast<int*>(a.glp + (size_t)B * T * a.SP);
+    a.ckpt_stride = ckpt_stride_floats(T, S);
+    a.ckpt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a.dlink + (size_t)B * (S + 1)) + 255) & ~(uintptr_t)255);
     a.fuse_apply = get_opt("ctc_fuse_apply") == 1 ? 1 : 0;   // measured on B200: the separate K3 pass is 22% faster end to end
 
     // The lattice kernel is a latency-bound chain over T (its duration does not depend on B),
@@ -1003,6 +1130,7 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
         ac.g = a.g ? a.g + (size_t)b0 * T * V : nullptr;
         ac.glp = a.glp + (size_t)b0 * T * a.SP;
         ac.dlink = a.dlink + (size_t)b0 * S;
+        ac.ckpt = a.ckpt + (size_t)b0 * a.ckpt_stride;
         int rc = ctc_run(ac, 1, p->rows);
         if (rc != 0) return rc;
         ASR_CHECK_CUDA(cudaEventRecord(p->k1[c], p->rows));

@@ -47,9 +47,8 @@ int         asr_device_ok(void);
  * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto), "ctc_fuse_apply"
  * (0 = separate K3 pass applies the sparse gradient update (default, faster),
  * 1 = the lattice kernel applies it itself with RED.ADD), "ctc_lattice_variant"
- * (0 = one warp per utterance (default), 2 = two-warp alpha-producer /
- * beta-consumer pipeline), "ctc_lattice_cwarp" (variant 2: warp index of the
- * consumer, 1..3), "ctc_chunks" (asr_ctc_fwd_bwd_f32 slices the batch into this
+ * (0 = bidirectional four-warp lattice (default), 1 = one warp per utterance),
+ * "ctc_chunks" (asr_ctc_fwd_bwd_f32 slices the batch into this
  * many pieces and runs each slice's lattice on a library-owned stream so that it
  * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
  * max 8; results are bit-identical for every value), "mha_variant" (0 = auto,
@@ -118,7 +117,7 @@ int asr_cif_bwd_f32(const float* hidden, const float* g_out,
  *                          exactly 0 for t >= in_len[b]; NaN rows for an
  *                          infeasible utterance (zero_infinity=False semantics)
  * ws: asr_ctc_workspace_bytes(B,T,V,S) bytes of device scratch.  It holds the
- *     gathered log-probabilities [B,T,S+2] (overwritten in place by the per-frame
+ *     gathered log-probabilities [B,T,S+3] (overwritten in place by the per-frame
  *     label occupancies) and the repeated-label links [B,S]; the alpha/beta
  *     lattice itself never leaves shared memory.
  */

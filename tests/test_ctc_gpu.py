@@ -15,10 +15,11 @@ CTC = load_golden("ctc")
 CASES = sorted({k.split("_")[0] for k in CTC.files})
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (0, 2), (1, 0)], ids=["one_warp_lattice", "two_warp_lattice", "fused_apply"])
+@pytest.fixture(autouse=True, params=[(0, 0), (0, 1), (1, 0)],
+                ids=["bidirectional_lattice", "one_warp_lattice", "fused_apply"])
 def apply_mode(request):
-    """Lattice kernel variants: one-warp lattice + separate K3 pass (default), the two-warp
-    producer/consumer lattice, and the one-warp lattice that applies the sparse update itself."""
+    """Lattice kernel variants: bidirectional four-warp lattice + separate K3 pass (default), the
+    one-warp lattice, and the one-warp lattice that applies the sparse update itself."""
     lib = pkg("_lib")
     lib.set_option("ctc_fuse_apply", request.param[0])
     lib.set_option("ctc_lattice_variant", request.param[1])
@@ -137,7 +138,9 @@ def test_random_vs_oracle_fp64(B, T, V, S):
     gs = np.nanmax(np.abs(o_grad[fin]))
     ge_ours = np.abs(to_np(grad)[fin] - o_grad[fin]).max() / gs
     ge_ref = np.abs(to_np(r_grad)[fin] - o_grad[fin]).max() / gs
-    assert ge_ours <= max(1e-5, 2 * ge_ref), (ge_ours, ge_ref)
+    # (T=90, S=80 has |log-likelihood| ~ 350 bits, where one fp32 ulp is already 3e-5: every fp32
+    # log-domain lattice, torch's included, sits at ~1e-4 there and the variants differ by rounding path)
+    assert ge_ours <= max(1e-5, 3 * ge_ref), (ge_ours, ge_ref)
 
 
 @pytest.mark.parametrize("B,T,S", [(32, 200, 10), (64, 400, 20)])
@@ -190,3 +193,38 @@ def test_sliced_pipeline_is_bit_identical(chunks):
     torch.cuda.synchronize()
     assert torch.equal(nll1, nll2) and torch.equal(g1, g2) and torch.equal(loss1, loss2)
     assert torch.equal(nll1, nll3) and torch.equal(g1, g3)
+
+
+def test_every_length_around_block_and_midpoint_boundaries():
+    """Input lengths 1..135 (one utterance each) cross every boundary of the bidirectional lattice:
+    one warp owning all frames (len <= 32), a one-frame second half (len 33), partial last blocks,
+    both halves with several blocks; target lengths 0..7 include the empty target and infeasible pairs."""
+    T, V, S = 135, 23, 7
+    B = T
+    g = torch.Generator().manual_seed(99)
+    logits = torch.randn(B, T, V, generator=g)
+    tgt_len = (torch.arange(B) * 5) % (S + 1)
+    targets = torch.randint(1, V - 1, (B, S), generator=g)
+    targets[::3, 1] = targets[::3, 0]                     # repeats need an extra blank frame
+    targets = targets * (torch.arange(S)[None, :] < tgt_len[:, None]).long()
+    in_len = torch.arange(1, B + 1, dtype=torch.int32)
+    loss, nll, grad = _ours(logits.cuda(), targets.cuda(), in_len.cuda())
+    o_loss, o_nll, o_grad = oracle.ctc_loss_and_grad(logits.numpy(), targets.numpy(), in_len.numpy())
+    fin = np.isfinite(o_nll)
+    assert fin.sum() > 100 and (~fin).sum() >= 2
+    np.testing.assert_array_equal(np.isfinite(to_np(nll)), fin)
+    np.testing.assert_allclose(to_np(nll)[fin], o_nll[fin], rtol=1e-5, atol=1e-5)
+    gn = to_np(grad)
+    # per utterance: fp32 rtol 1e-5 of the gradient scale, or 3x the error torch's own fp32 lattice
+    # makes on the same utterance (|log-likelihood| reaches 600 bits here, one fp32 ulp = 6e-5)
+    _, _, r_grad = _torch_ref(logits.cuda(), targets.cuda(), in_len.cuda())
+    r_grad = to_np(r_grad)
+    for b in np.nonzero(fin)[0]:
+        gs = np.abs(o_grad[b]).max()
+        e_ours = np.abs(gn[b] - o_grad[b]).max() / gs
+        e_ref = np.abs(r_grad[b] - o_grad[b]).max() / gs
+        assert e_ours <= max(1e-5, 3 * e_ref), (b, e_ours, e_ref)
+    for b in np.nonzero(~fin)[0]:
+        np.testing.assert_array_equal(np.isnan(gn[b]), np.isnan(o_grad[b]))
+    for b in range(B):
+        assert not gn[b, int(in_len[b]):].any()

@@ -23,11 +23,10 @@ for (B, T, S) in [(32, 1600, 80), (256, 1600, 80), (64, 400, 20)]:
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e3
-    for variant, cw in ((0, 1), (2, 1)):
+    for variant in (0, 1):
         lib.set_option("ctc_lattice_variant", variant)
-        lib.set_option("ctc_lattice_cwarp", cw)
         k1 = timed(lambda: run(1))
         k12 = timed(lambda: run(3))
         k12f = timed(lambda: run(3, grad=False))
         k1f = timed(lambda: run(1, grad=False))
-        print(dict(B=B, T=T, S=S, lattice_variant=variant, cwarp=cw, K1_us=round(k1), K2_grad_us=round(k12 - k1), K2_fwd_only_us=round(k12f - k1f)), flush=True)
+        print(dict(B=B, T=T, S=S, lattice_variant=variant, K1_us=round(k1), K2_grad_us=round(k12 - k1), K2_fwd_only_us=round(k12f - k1f)), flush=True)
