@@ -68,6 +68,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--serial", action="store_true", help="time the hot path one kernel at a time on one stream")
+    ap.add_argument("--ctc-chunks", type=int, default=0, help="batch slices of the CTC pipeline (0 = library default)")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full-model data-parallel step (config 5)")
     return ap.parse_args()
 
@@ -185,7 +186,6 @@ class HotPath:
         self.cif_ws = torch.empty(B * T, device=dev)
         self.valid_frames = int(inp["in_len"].sum().item())
         self.n_kernels_per_step = 3 + 1 + 2
-        self.side = torch.cuda.Stream(device=dev)
 
     def ctc(self, stages):
         w, i, p = self.w, self.inp, self.lib.ptr
@@ -209,20 +209,18 @@ class HotPath:
             self.lib.stream_ptr()), "asr_cif_bwd_f32")
 
     def step_overlapped(self):
-        """One hot-path pass the way the library is meant to be driven: the CTC call (which slices
-        the batch over its own streams) on the current stream, the CIF forward/backward pair on a
-        side stream, joined at the end.  The two halves share no data."""
+        """One hot-path pass the way the library is meant to be driven: one stream, the CTC call in
+        its two phases with the CIF forward/backward pair queued in between, where it runs next to
+        the last slice's latency-bound lattice.  The two halves share no data."""
+        import ctypes
         w, i, p = self.w, self.inp, self.lib.ptr
-        cur = torch.cuda.current_stream()
-        self.side.wait_stream(cur)
-        self.lib.check(self.L.asr_ctc_fwd_bwd_f32(
-            p(i["logits"]), p(i["targets"]), p(i["in_len"]), p(i["tgt_len"]), w["B"], w["T"], w["V"], w["S"],
-            w["V"] - 1, p(self.nll), p(self.g_logits), p(self.ws), self.ws_bytes, self.lib.stream_ptr()),
-            "asr_ctc_fwd_bwd_f32")
-        with torch.cuda.stream(self.side):
-            self.cif_fwd()
-            self.cif_bwd()
-        cur.wait_stream(self.side)
+        args = (p(i["logits"]), p(i["targets"]), p(i["in_len"]), p(i["tgt_len"]), w["B"], w["T"], w["V"], w["S"],
+                w["V"] - 1, p(self.nll), p(self.g_logits), p(self.ws), self.ws_bytes, self.lib.stream_ptr())
+        ticket = ctypes.c_int(0)
+        self.lib.check(self.L.asr_ctc_begin_f32(*args, ctypes.byref(ticket)), "asr_ctc_begin_f32")
+        self.cif_fwd()
+        self.cif_bwd()
+        self.lib.check(self.L.asr_ctc_finish_f32(*args, ticket.value), "asr_ctc_finish_f32")
 
     def step(self, ev=None):
         """One serial hot-path pass; ev = list of 6 CUDA events recorded between the stages."""
@@ -512,6 +510,8 @@ def main():
         return
 
     import asr_b200 as pkg
+    if args.ctc_chunks:
+        pkg._lib.set_option("ctc_chunks", args.ctc_chunks)
     launches0 = pkg._lib.launch_count()
     inp = make_inputs(w, device, 1236 + rank)
     hp = HotPath(w, inp, pkg)
@@ -643,7 +643,7 @@ def main():
             "config": dict(workload=args.workload, per_gpu=w, L=L_out, valid_frames=valid_frames,
                            parallelism="dp%d by utterance, no data-path collective" % world,
                            schedule="serial, one stream" if args.serial else
-                           "CTC batch slices pipelined over library streams, CIF pair on a side stream",
+                           "one stream; CTC begin (rows + lattices on library streams) / CIF pair / CTC finish (apply)",
                            l2="inputs (%.1f GB logits + %.1f GB hidden per GPU) exceed the 126 MB L2; no flush needed" % (
                                inp["logits"].numel() * 4 / 1e9, inp["hidden"].numel() * 4 / 1e9)),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(timed_launches),

@@ -32,6 +32,10 @@ SIGNATURES = {
     "asr_ctc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "asr_ctc_fwd_bwd_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _vp, _vp, _vp, _c_size_t, _vp]),
+    "asr_ctc_begin_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                   _vp, _vp, _vp, _c_size_t, _vp, ctypes.POINTER(_c_int)]),
+    "asr_ctc_finish_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                    _vp, _vp, _vp, _c_size_t, _vp, _c_int]),
     "asr_ctc_stages_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                     _vp, _vp, _vp, _c_size_t, _c_int, _vp]),
     "asr_scale_inplace_f32": (_c_int, [_vp, _c_size_t, _vp, _vp]),

@@ -30,6 +30,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <map>
 #include <mutex>
 
@@ -1041,11 +1042,13 @@ static int ctc_run(const CtcArgs& a, int stages, cudaStream_t st) {
 }
 
 // Streams and events of the sliced pipeline, one set per device, created on first use.
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 8;     // slices per call
+constexpr int kTickets = 4;       // calls in flight between begin and finish
+constexpr int kLatStreams = 8;
 struct CtcPipe {
-    cudaStream_t rows = nullptr;
-    cudaStream_t lat[kMaxChunks] = {};
-    cudaEvent_t fork = nullptr, k1[kMaxChunks] = {}, done[kMaxChunks] = {};
+    cudaStream_t lat[kLatStreams] = {};
+    cudaEvent_t k1[kTickets][kMaxChunks] = {}, done[kTickets][kMaxChunks] = {};
+    std::atomic<int> next_ticket{0};
 };
 static CtcPipe* ctc_pipe() {
     static std::mutex mu;
@@ -1058,22 +1061,21 @@ static CtcPipe* ctc_pipe() {
     CtcPipe* p = new CtcPipe();
     int lo = 0, hi = 0;
     bool ok = cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess;
-    // lattice slices get the highest priority: a few warps that must start the moment their rows are ready
-    ok = ok && cudaStreamCreateWithPriority(&p->rows, cudaStreamNonBlocking, lo) == cudaSuccess;
-    ok = ok && cudaEventCreateWithFlags(&p->fork, cudaEventDisableTiming) == cudaSuccess;
-    for (int c = 0; c < kMaxChunks && ok; ++c) {
+    // the lattices get the highest priority: a few warps that must start the moment their rows are ready
+    for (int c = 0; c < kLatStreams && ok; ++c)
         ok = ok && cudaStreamCreateWithPriority(&p->lat[c], cudaStreamNonBlocking, hi) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&p->k1[c], cudaEventDisableTiming) == cudaSuccess;
-        ok = ok && cudaEventCreateWithFlags(&p->done[c], cudaEventDisableTiming) == cudaSuccess;
-    }
+    for (int t = 0; t < kTickets && ok; ++t)
+        for (int c = 0; c < kMaxChunks && ok; ++c) {
+            ok = ok && cudaEventCreateWithFlags(&p->k1[t][c], cudaEventDisableTiming) == cudaSuccess;
+            ok = ok && cudaEventCreateWithFlags(&p->done[t][c], cudaEventDisableTiming) == cudaSuccess;
+        }
     if (!ok) { set_error("asr_ctc: could not create the pipeline streams: %s", cudaGetErrorString(cudaGetLastError())); delete p; return nullptr; }
     pipes[dev] = p;
     return p;
 }
 
-extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
-                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
-                                  size_t ws_bytes, int stages, void* stream) {
+static int ctc_make_args(CtcArgs& a, const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                         int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws, size_t ws_bytes) {
     ASR_REQUIRE(B > 0 && T > 0 && V > 1 && S >= 0, "asr_ctc: bad shape B=%d T=%d V=%d S=%d", B, T, V, S);
     ASR_REQUIRE(logits && in_len && tgt_len && nll && ws && (S == 0 || targets), "asr_ctc: null pointer");
     ASR_REQUIRE(blank >= 0 && blank < V, "asr_ctc: blank %d out of range", blank);
@@ -1083,9 +1085,6 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
     ASR_REQUIRE(2 * S + 1 <= 32 * 16, "asr_ctc: S=%d > 255 labels not supported", S);
     ASR_REQUIRE((long long)B * T < (1ll << 31) - 1, "asr_ctc: B*T too large");
     if (asr_device_ok() != 0) return 3;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-
-    CtcArgs a;
     a.logits = logits;
     a.targets = targets;
     a.in_len = in_len;
@@ -1101,53 +1100,110 @@ extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, c
     a.ckpt_stride = ckpt_stride_floats(T, S);
     a.ckpt = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(a.dlink + (size_t)B * (S + 1)) + 255) & ~(uintptr_t)255);
     a.fuse_apply = get_opt("ctc_fuse_apply") == 1 ? 1 : 0;   // measured on B200: the separate K3 pass is 22% faster end to end
+    return 0;
+}
 
-    // The lattice kernel is a latency-bound chain over T (its duration does not depend on B),
-    // the row and apply kernels are HBM-bound.  Slicing the batch and running each slice's
-    // lattice on its own stream hides all but the last slice's lattice behind the row kernels.
+// utterances [b0, b0+n) of `a`
+static CtcArgs ctc_slice(const CtcArgs& a, int b0, int n) {
+    CtcArgs ac = a;
+    ac.B = n;
+    ac.logits = a.logits + (size_t)b0 * a.T * a.V;
+    ac.targets = a.targets ? a.targets + (size_t)b0 * a.S : nullptr;
+    ac.in_len = a.in_len + b0;
+    ac.tgt_len = a.tgt_len + b0;
+    ac.nll = a.nll + b0;
+    ac.g = a.g ? a.g + (size_t)b0 * a.T * a.V : nullptr;
+    ac.glp = a.glp + (size_t)b0 * a.T * a.SP;
+    ac.dlink = a.dlink + (size_t)b0 * a.S;
+    ac.ckpt = a.ckpt + (size_t)b0 * a.ckpt_stride;
+    return ac;
+}
+
+// The lattice kernel is a latency-bound chain over T (its duration does not depend on B), the
+// row and apply kernels are HBM-bound - and two HBM-bound kernels side by side only slow each
+// other down (measured).  So the HBM-bound kernels stay in order on the caller's stream and only
+// the lattices leave it: the batch is cut into slices, each slice's lattice runs on a
+// library-owned high-priority stream right after the slice's row kernel and overlaps whatever
+// the caller's stream does next (the next slice's rows, or the caller's own kernels between
+// begin and finish).  finish waits for the lattices and applies the sparse update.
+static int ctc_slices(int B, int T) {
     int nchunk = get_opt("ctc_chunks");
-    if (nchunk <= 0) nchunk = (int)std::min<long long>(4, std::max<long long>(1, (long long)B * T / 65536));   // measured: 4 slices beat 2 and 8 at B*T = 410k
-    nchunk = std::min(std::min(nchunk, kMaxChunks), B);
-    if (stages != 7 || nchunk <= 1) return ctc_run(a, stages, st);
+    if (nchunk <= 0) nchunk = (int)std::min<long long>(4, std::max<long long>(1, (long long)B * T / 65536));   // measured at B*T = 410k: 4 beats 1, 2 and 8
+    return std::min(std::min(nchunk, kMaxChunks), B);
+}
 
+extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                 int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                 size_t ws_bytes, void* stream, int* ticket) {
+    ASR_REQUIRE(ticket != nullptr, "asr_ctc_begin_f32: ticket is null");
+    CtcArgs a;
+    int rc = ctc_make_args(a, logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes);
+    if (rc != 0) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
     CtcPipe* p = ctc_pipe();
     if (p == nullptr) return 3;
-    ASR_CHECK_CUDA(cudaEventRecord(p->fork, st));
-    ASR_CHECK_CUDA(cudaStreamWaitEvent(p->rows, p->fork, 0));
+    const int tk = p->next_ticket.fetch_add(1) % kTickets;
+    const int nchunk = ctc_slices(B, T);
     const int per = (B + nchunk - 1) / nchunk;
-    int used = 0;
     for (int c = 0; c < nchunk; ++c) {
         const int b0 = c * per;
         const int n = std::min(per, B - b0);
         if (n <= 0) break;
-        CtcArgs ac = a;
-        ac.B = n;
-        ac.logits = a.logits + (size_t)b0 * T * V;
-        ac.targets = a.targets ? a.targets + (size_t)b0 * S : nullptr;
-        ac.in_len = a.in_len + b0;
-        ac.tgt_len = a.tgt_len + b0;
-        ac.nll = a.nll + b0;
-        ac.g = a.g ? a.g + (size_t)b0 * T * V : nullptr;
-        ac.glp = a.glp + (size_t)b0 * T * a.SP;
-        ac.dlink = a.dlink + (size_t)b0 * S;
-        ac.ckpt = a.ckpt + (size_t)b0 * a.ckpt_stride;
-        int rc = ctc_run(ac, 1, p->rows);
+        const CtcArgs ac = ctc_slice(a, b0, n);
+        rc = ctc_run(ac, 1, st);
         if (rc != 0) return rc;
-        ASR_CHECK_CUDA(cudaEventRecord(p->k1[c], p->rows));
-        ASR_CHECK_CUDA(cudaStreamWaitEvent(p->lat[c], p->k1[c], 0));
-        rc = ctc_run(ac, 6, p->lat[c]);
+        cudaStream_t ls = p->lat[(tk * kMaxChunks + c) % kLatStreams];
+        ASR_CHECK_CUDA(cudaEventRecord(p->k1[tk][c], st));
+        ASR_CHECK_CUDA(cudaStreamWaitEvent(ls, p->k1[tk][c], 0));
+        rc = ctc_run(ac, 2, ls);
         if (rc != 0) return rc;
-        ASR_CHECK_CUDA(cudaEventRecord(p->done[c], p->lat[c]));
-        used = c + 1;
+        ASR_CHECK_CUDA(cudaEventRecord(p->done[tk][c], ls));
     }
-    for (int c = 0; c < used; ++c) ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[c], 0));
+    *ticket = tk;
     return 0;
+}
+
+extern "C" int asr_ctc_finish_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                  size_t ws_bytes, void* stream, int ticket) {
+    ASR_REQUIRE(ticket >= 0 && ticket < kTickets, "asr_ctc_finish_f32: bad ticket %d", ticket);
+    CtcArgs a;
+    int rc = ctc_make_args(a, logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes);
+    if (rc != 0) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CtcPipe* p = ctc_pipe();
+    if (p == nullptr) return 3;
+    const int nchunk = ctc_slices(B, T);
+    const int per = (B + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk; ++c) {
+        const int b0 = c * per;
+        const int n = std::min(per, B - b0);
+        if (n <= 0) break;
+        ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[ticket][c], 0));
+        rc = ctc_run(ctc_slice(a, b0, n), 4, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
+}
+
+extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                  size_t ws_bytes, int stages, void* stream) {
+    CtcArgs a;
+    int rc = ctc_make_args(a, logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes);
+    if (rc != 0) return rc;
+    return ctc_run(a, stages, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
                                    int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
                                    size_t ws_bytes, void* stream) {
-    return asr_ctc_stages_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, 7, stream);
+    if (ctc_slices(B, T) <= 1)
+        return asr_ctc_stages_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, 7, stream);
+    int ticket = 0;
+    int rc = asr_ctc_begin_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, &ticket);
+    if (rc != 0) return rc;
+    return asr_ctc_finish_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, ticket);
 }
 
 extern "C" int asr_scale_inplace_f32(float* g, size_t n, const float* scale_dev, void* stream) {

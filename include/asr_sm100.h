@@ -48,8 +48,8 @@ int         asr_device_ok(void);
  * (0 = separate K3 pass applies the sparse gradient update (default, faster),
  * 1 = the lattice kernel applies it itself with RED.ADD), "ctc_lattice_variant"
  * (0 = bidirectional four-warp lattice (default), 1 = one warp per utterance),
- * "ctc_chunks" (asr_ctc_fwd_bwd_f32 slices the batch into this
- * many pieces and runs each slice's lattice on a library-owned stream so that it
+ * "ctc_chunks" (asr_ctc_fwd_bwd_f32 / begin / finish slice the batch into this
+ * many pieces and run each slice's lattice on a library-owned stream so that it
  * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
  * max 8; results are bit-identical for every value), "mha_variant" (0 = auto,
  * 1 = one tile per CTA, 2 = two-tile ping-pong). */
@@ -127,10 +127,29 @@ int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
                         int B, int T, int V, int S, int blank,
                         float* nll, float* g_logits,
                         void* ws, size_t ws_bytes, void* stream);
+/* The same call in two phases.  begin queues the row kernels on `stream` and the
+ * lattices on library-owned streams and returns a ticket; finish (same arguments,
+ * same stream, the ticket) waits for the lattices and applies the sparse gradient
+ * update.  Whatever the caller queues on `stream` between the two runs next to
+ * the last slice's lattice, which is a latency-bound chain that leaves the GPU
+ * almost idle - bench.py puts the CIF forward/backward pair there.  nll and
+ * g_logits are complete (in stream order) after finish.  At most 4 begins may be
+ * outstanding per device.  asr_ctc_fwd_bwd_f32 == begin immediately followed by
+ * finish. */
+int asr_ctc_begin_f32(const float* logits, const int64_t* targets,
+                      const int* in_len, const int* tgt_len,
+                      int B, int T, int V, int S, int blank,
+                      float* nll, float* g_logits,
+                      void* ws, size_t ws_bytes, void* stream, int* ticket);
+int asr_ctc_finish_f32(const float* logits, const int64_t* targets,
+                       const int* in_len, const int* tgt_len,
+                       int B, int T, int V, int S, int blank,
+                       float* nll, float* g_logits,
+                       void* ws, size_t ws_bytes, void* stream, int ticket);
 /* Same call split into its three kernels, for per-kernel timing with CUDA events
  * (bench.py): stages is a bit mask, 1 = K1 row pass (log-sum-exp, gather, dense
  * gradient), 2 = K2 lattice (alpha/beta, nll, occupancies), 4 = K3 sparse gradient
- * update.  Stages must be issued in order on one stream; 7 = the call above. */
+ * update.  Stages must be issued in order on one stream; no slicing, one stream. */
 int asr_ctc_stages_f32(const float* logits, const int64_t* targets,
                        const int* in_len, const int* tgt_len,
                        int B, int T, int V, int S, int blank,

@@ -228,3 +228,46 @@ def test_every_length_around_block_and_midpoint_boundaries():
         np.testing.assert_array_equal(np.isnan(gn[b]), np.isnan(o_grad[b]))
     for b in range(B):
         assert not gn[b, int(in_len[b]):].any()
+
+
+def test_begin_finish_with_work_in_between_is_bit_identical():
+    """asr_ctc_begin_f32 / asr_ctc_finish_f32 with unrelated kernels queued in between must give
+    exactly what the single call gives (two outstanding tickets, interleaved)."""
+    import ctypes
+    lib = pkg("_lib")
+    L, p = lib.lib(), lib.ptr
+    B, T, V, S = 9, 80, 131, 6
+    outs = []
+    try:
+        lib.set_option("ctc_chunks", 3)
+        data = []
+        for seed in (5, 6):
+            logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=seed)
+            tgt_len = targets.ne(0).sum(1).to(torch.int32)
+            wsb = L.asr_ctc_workspace_bytes(B, T, V, S)
+            d = dict(logits=logits, targets=targets, in_len=in_len, tgt_len=tgt_len, wsb=wsb)
+            for tag in ("one", "two"):
+                d["nll_" + tag] = torch.empty(B, device="cuda")
+                d["g_" + tag] = torch.empty_like(logits)
+                d["ws_" + tag] = torch.empty(wsb // 4 + 1, device="cuda")
+            data.append(d)
+
+        def args(d, tag):
+            return (p(d["logits"]), p(d["targets"]), p(d["in_len"]), p(d["tgt_len"]), B, T, V, S, V - 1,
+                    p(d["nll_" + tag]), p(d["g_" + tag]), p(d["ws_" + tag]), d["wsb"], lib.stream_ptr())
+        for d in data:
+            lib.check(L.asr_ctc_fwd_bwd_f32(*args(d, "one")), "fwd_bwd")
+        tickets = [ctypes.c_int(-1), ctypes.c_int(-1)]
+        filler = torch.randn(1 << 20, device="cuda")
+        for d, tk in zip(data, tickets):
+            lib.check(L.asr_ctc_begin_f32(*args(d, "two"), ctypes.byref(tk)), "begin")
+            filler = filler * 1.0001 + 1.0
+        assert tickets[0].value != tickets[1].value
+        for d, tk in zip(data, tickets):
+            lib.check(L.asr_ctc_finish_f32(*args(d, "two"), tk.value), "finish")
+        torch.cuda.synchronize()
+        for d in data:
+            assert torch.equal(d["nll_one"], d["nll_two"])
+            assert torch.equal(d["g_one"], d["g_two"])
+    finally:
+        lib.set_option("ctc_chunks", 0)
