@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Runs the CTC kernels once at one shape (for ncu captures).
-    python tools/ctc_once.py B T S [grad] [variant]"""
+    [ASR_CTC_CHUNKS=n] python tools/ctc_once.py B T S [grad] [lattice variant]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,8 @@ from helpers import make_ctc_inputs
 lib = asr_b200._lib; L = lib.lib(); ptr, sp, check = lib.ptr, lib.stream_ptr, lib.check
 B, T, S = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 grad = len(sys.argv) > 4 and sys.argv[4] == "1"
-if len(sys.argv) > 5: lib.set_option("ctc_rec_variant", int(sys.argv[5]))
+if len(sys.argv) > 5: lib.set_option("ctc_lattice_variant", int(sys.argv[5]))
+if os.environ.get("ASR_CTC_CHUNKS"): lib.set_option("ctc_chunks", int(os.environ["ASR_CTC_CHUNKS"]))
 V = 4233
 logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=1236)
 tgt_len = targets.ne(0).sum(1).to(torch.int32)
