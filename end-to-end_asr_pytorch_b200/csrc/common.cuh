@@ -99,6 +99,33 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Wait flavours for latency experiments: 0 = suspend-hinted try_wait (mbar_wait), 1 = plain try_wait
+// (short hardware time limit), 2 = non-blocking test_wait polling.
+__device__ __forceinline__ void mbar_wait_mode(uint64_t* bar, uint32_t parity, int mode) {
+    if (mode == 0) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        if (mode == 1) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        } else {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        }
+        if (ok) return;
+        if (++spins > (1u << 26)) __trap();
+    }
+}
+
 // 2-D TMA tile load: global (tensor map) -> shared, completion on an mbarrier.
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(

@@ -105,6 +105,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // ---- descriptors -------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 bytes apart
 // (what a [rows x 64 bf16] TMA tile with CU_TENSOR_MAP_SWIZZLE_128B looks like).
@@ -598,6 +612,7 @@ struct MhaBwdArgs {
     float* dq_acc;        // [B,Lq,Hh,64] fp32, zeroed
     __nv_bfloat16* g_k;   // [B,Lk,Hh,64]
     __nv_bfloat16* g_v;
+    int debug;            // timing experiments only: 1 = skip the dQ reduction, 2 = skip the exponentials
 };
 
 struct __align__(8) MhaBwdBarriers {
@@ -605,7 +620,6 @@ struct __align__(8) MhaBwdBarriers {
     uint64_t qdo_full[2];
     uint64_t qdo_empty[2];
     uint64_t sdp_full;
-    uint64_t sdp_free;
     uint64_t pds_full;
     uint64_t dq_full;
     uint32_t tmem_base;
@@ -618,7 +632,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(kFwdThreads, 1)
+// CG = column groups: the softmax-backward work of a 128 x 128 tile is spread over 4*CG warps
+// (warp w: TMEM lane quarter w % 4 = query rows, column group w / 4).  One warp per SM
+// sub-partition (CG = 1) leaves every dependent instruction's latency exposed; 4 per
+// sub-partition hide it.
+template <int CG>
+__global__ void __launch_bounds__(128 * CG + 64, 1)
 mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const MhaBwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -651,12 +670,12 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_init(&bars->qdo_empty[s], 1);
         }
         mbar_init(&bars->sdp_full, 1);
-        mbar_init(&bars->sdp_free, 128);
-        mbar_init(&bars->pds_full, 128);
+        mbar_init(&bars->pds_full, 128 * CG);
         mbar_init(&bars->dq_full, 1);
         fence_mbar_init();
     }
-    if (warp == 5) {
+    constexpr int kTmaWarp = 4 * CG, kMmaWarp = 4 * CG + 1;
+    if (warp == kMmaWarp) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -666,7 +685,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const uint32_t tmem = bars->tmem_base;
     const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
 
-    if (warp == 4) {
+    if (warp == kTmaWarp) {
         // ===== TMA producer =====
         if (lane == 0 && nsteps > 0) {
             tma_prefetch_desc(&tm_q);
@@ -682,21 +701,21 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tma_load_4d(sDO + s * kTileBytes, &tm_do, 0, h, (i_start + it) * kBM, b, &bars->qdo_full[s]);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA issuer =====
+        // Order on the tensor pipe: S/dP of tile it+1 go BEFORE dV/dK/dQ of tile it, so the softmax
+        // warps can start on tile it+1 while the three accumulating products of tile it run.
         if (lane == 0 && nsteps > 0) {
             constexpr uint32_t id_s = make_idesc(kBM, kBN, 0, 0);     // S  = Q K^T   / dP = dO V^T
             constexpr uint32_t id_t = make_idesc(kBN, kD, 1, 1);      // dV = P^T dO  / dK = dS^T Q  (A and B MN-major)
             constexpr uint32_t id_q = make_idesc(kBM, kD, 0, 1);      // dQ = dS K    (A K-major, B MN-major)
             const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
             const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
-            mbar_wait(&bars->kv_full, 0);
-            for (int it = 0; it < nsteps; ++it) {
+            auto issue_sdp = [&](int it) {
                 const int s = it & 1;
                 const uint32_t q_addr = smem_u32(sQ + s * kTileBytes);
                 const uint32_t do_addr = smem_u32(sDO + s * kTileBytes);
                 mbar_wait(&bars->qdo_full[s], (it >> 1) & 1);
-                if (it > 0) mbar_wait(&bars->sdp_free, (it - 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int kk = 0; kk < kD / 16; ++kk)
@@ -707,9 +726,17 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     umma_bf16(tm_dp, smem_desc_sw128(do_addr + kk * 32, 16, 1024), smem_desc_sw128(v_addr + kk * 32, 16, 1024),
                               id_s, kk > 0 ? 1u : 0u);
                 tc_commit(&bars->sdp_full);
-
+            };
+            mbar_wait(&bars->kv_full, 0);
+            issue_sdp(0);
+            for (int it = 0; it < nsteps; ++it) {
+                const int s = it & 1;
+                const uint32_t q_addr = smem_u32(sQ + s * kTileBytes);
+                const uint32_t do_addr = smem_u32(sDO + s * kTileBytes);
+                // P/dS of tile it are in shared memory; S/dP (TMEM) and dQ of tile it-1 (TMEM) have been read
                 mbar_wait(&bars->pds_full, it & 1);
                 tc_fence_after();
+                if (it + 1 < nsteps) issue_sdp(it + 1);
                 // contraction over the 128 queries of the tile: 8 steps of 16 rows (2048 bytes)
 #pragma unroll
                 for (int kk = 0; kk < kBM / 16; ++kk) {
@@ -732,10 +759,27 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             }
         }
     } else {
-        // ===== softmax-backward warps: thread = query row of the tile (and key row in the epilogue) =====
-        const int row = threadIdx.x;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        // ===== softmax-backward warps: thread = (query row of the tile, column group); key row in the epilogue =====
+        const int row = (warp & 3) * 32 + lane;
+        const int cg = warp >> 2;
+        constexpr int kColsS = kBN / CG;    // S / dP columns of this thread
+        constexpr int kColsD = kD / CG;     // dQ / dK / dV columns of this thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float c = a.scale_log2;
+        float* prev_dq_row = nullptr;       // where dQ of the previous tile goes (null: row outside the sequence)
+        auto flush_dq = [&](const float (&dq)[kColsD], float* dst) {
+            if (dst != nullptr && !(a.debug & 1)) {
+#pragma unroll
+                for (int i = 0; i < kColsD; i += 4) red_add_v4(dst + i, dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+            }
+        };
+        auto load_dq = [&](float (&dq)[kColsD]) {
+            if constexpr (kColsD == 32) {
+                tmem_ld32(tm_dq + lane_base + cg * kColsD, dq);
+            } else {
+                tmem_ld16(tm_dq + lane_base + cg * kColsD, dq);
+            }
+        };
         for (int it = 0; it < nsteps; ++it) {
             const int qi = (i_start + it) * kBM + row;
             const bool q_ok = qi < a.Lq;
@@ -747,14 +791,17 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
             const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
 
+            // P and dS of this thread's columns, packed bf16, kept in registers until the products of
+            // the previous tile have released the shared-memory tiles
+            uint32_t pk[kColsS / 2], dk[kColsS / 2];
             mbar_wait(&bars->sdp_full, it & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int cc = 0; cc < kBN; cc += 32) {
+#pragma unroll
+            for (int c0 = 0; c0 < kColsS; c0 += 32) {
+                const int cc = cg * kColsS + c0;
                 float sv[32], dp[32];
                 tmem_ld32(tm_s + lane_base + cc, sv);
                 tmem_ld32(tm_dp + lane_base + cc, dp);
-                uint32_t pk[16], dk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = ex2_approx(fmaf(sv[i], c, -lse2));
@@ -773,65 +820,71 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     const float s1 = p1 * (dp[i + 1] - dlt) * a.scale;
                     const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
                     const __nv_bfloat162 sb = __floats2bfloat162_rn(s0, s1);
-                    pk[i >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                    dk[i >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
+                    pk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                    dk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
                 }
+            }
+            float dq[kColsD];
+            if (it > 0) {
+                // dV/dK/dQ of the previous tile are done: its P/dS tiles are free and its dQ is in TMEM
+                mbar_wait(&bars->dq_full, (it - 1) & 1);
+                tc_fence_after();
+                load_dq(dq);
+            }
+#pragma unroll
+            for (int c0 = 0; c0 < kColsS; c0 += 32) {
+                const int cc = cg * kColsS + c0;
                 const int off = (cc >> 6) * kTileBytes + row * 128;
                 const int chunk0 = (cc & 63) >> 3;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int chunk = (chunk0 + q4) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(sP + off + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                    *reinterpret_cast<uint4*>(sDS + off + chunk * 16) = make_uint4(dk[4 * q4], dk[4 * q4 + 1], dk[4 * q4 + 2], dk[4 * q4 + 3]);
+                    const int w0 = (c0 >> 1) + 4 * q4;
+                    *reinterpret_cast<uint4*>(sP + off + chunk * 16) = make_uint4(pk[w0], pk[w0 + 1], pk[w0 + 2], pk[w0 + 3]);
+                    *reinterpret_cast<uint4*>(sDS + off + chunk * 16) = make_uint4(dk[w0], dk[w0 + 1], dk[w0 + 2], dk[w0 + 3]);
                 }
             }
             tc_fence_before();
-            mbar_arrive(&bars->sdp_free);
             fence_proxy_async();
             mbar_arrive(&bars->pds_full);
-
-            // dQ_i partial -> fp32 workspace
-            mbar_wait(&bars->dq_full, it & 1);
-            tc_fence_after();
-            float* dq_row = a.dq_acc + (((size_t)b * a.Lq + (q_ok ? qi : 0)) * a.Hh + h) * kD;
-#pragma unroll
-            for (int cc = 0; cc < kD; cc += 32) {
-                float dq[32];
-                tmem_ld32(tm_dq + lane_base + cc, dq);
-                if (q_ok) {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) red_add_v4(dq_row + cc + i, dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
-                }
-            }
-            tc_fence_before();
+            if (it > 0) flush_dq(dq, prev_dq_row);
+            prev_dq_row = q_ok ? a.dq_acc + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + cg * kColsD : nullptr;
         }
-        // epilogue: dK_j, dV_j (thread = key row).  The TMEM loads are warp-collective, so every
-        // thread issues them; only rows inside the sequence store.
+        if (nsteps > 0) {
+            float dq[kColsD];
+            mbar_wait(&bars->dq_full, (nsteps - 1) & 1);
+            tc_fence_after();
+            load_dq(dq);
+            flush_dq(dq, prev_dq_row);
+        }
+        // epilogue: dK_j, dV_j (thread = key row, kColsD columns).  The TMEM loads are warp-collective,
+        // so every thread issues them; only rows inside the sequence store.
         const int key = key0 + row;
         const bool key_ok = key < a.Lk;
-        const size_t kv_off = (((size_t)b * a.Lk + (key_ok ? key : 0)) * a.Hh + h) * kD;
+        const size_t kv_off = (((size_t)b * a.Lk + (key_ok ? key : 0)) * a.Hh + h) * kD + cg * kColsD;
 #pragma unroll
         for (int part = 0; part < 2; ++part) {
+            const uint32_t src = (part == 0 ? tm_dk : tm_dv) + lane_base + cg * kColsD;
+            __nv_bfloat16* dst = (part == 0 ? a.g_k : a.g_v) + kv_off;
 #pragma unroll
-            for (int cc = 0; cc < kD; cc += 32) {
-                float acc[32];
+            for (int cc = 0; cc < kColsD; cc += 16) {
+                float acc[16];
                 if (nsteps > 0) {   // CTA-uniform
-                    tmem_ld32((part == 0 ? tm_dk : tm_dv) + lane_base + cc, acc);
+                    tmem_ld16(src + cc, acc);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) acc[i] = 0.0f;
+                    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
                 }
                 if (key_ok) {
-                    __nv_bfloat16* dst = (part == 0 ? a.g_k : a.g_v) + kv_off + cc;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) {
+                    for (int i = 0; i < 16; i += 8) {
                         uint32_t w[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             const __nv_bfloat162 v2 = __floats2bfloat162_rn(acc[i + 2 * u], acc[i + 2 * u + 1]);
                             w[u] = *reinterpret_cast<const uint32_t*>(&v2);
                         }
-                        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                        *reinterpret_cast<uint4*>(dst + cc + i) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
             }
@@ -840,7 +893,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }
@@ -998,9 +1051,16 @@ extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, con
     a.dq_acc = dq_acc;
     a.g_k = static_cast<__nv_bfloat16*>(g_k);
     a.g_v = static_cast<__nv_bfloat16*>(g_v);
-    ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    a.debug = get_opt("mha_bwd_debug");
     dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
-    mha_bwd_kernel<<<grid, kFwdThreads, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+    const int cgo = get_opt("mha_bwd_groups");   // softmax-backward warps = 4 * groups; 0 = default (4)
+    if (cgo == 2) {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        mha_bwd_kernel<2><<<grid, 256 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+    } else {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+        mha_bwd_kernel<4><<<grid, 512 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+    }
     ASR_LAUNCH_CHECK();
     size_t blocks = (nq_elems / 4 + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;

@@ -15,13 +15,16 @@ MHA = load_golden("mha")
 CASES = ["self_pad", "self_causal", "cross", "nomask"]
 
 
-@pytest.fixture(autouse=True, params=[0, 1, 2], ids=["auto", "one_tile", "two_tile_pingpong"])
+@pytest.fixture(autouse=True, params=[(0, 0), (1, 2), (2, 4)], ids=["auto", "one_tile_bwd8w", "two_tile_pingpong_bwd16w"])
 def fwd_variant(request):
-    """Forward kernel variant: one 128-query tile per CTA, or two tiles in ping-pong."""
+    """Forward kernel variant (one 128-query tile per CTA, or two tiles in ping-pong) and the number
+    of softmax-backward warp groups (16 warps by default, 8 is the other template instance)."""
     lib = pkg("_lib")
-    lib.set_option("mha_variant", request.param)
+    lib.set_option("mha_variant", request.param[0])
+    lib.set_option("mha_bwd_groups", request.param[1])
     yield request.param
     lib.set_option("mha_variant", 0)
+    lib.set_option("mha_bwd_groups", 0)
 
 
 def _torch_core(q, k, v, mask=None, scale=None):
