@@ -626,7 +626,19 @@ struct __align__(8) MhaBwdBarriers {
     uint32_t pad;
 };
 
-constexpr int kBwdSmem = 2 * kTileBytes /*K,V*/ + 4 * kTileBytes /*Q,dO x2*/ + 2 * kTileBytes /*P*/ + 2 * kTileBytes /*dS*/ + 128;
+constexpr int kBwdSmem = 2 * kTileBytes /*K,V*/ + 4 * kTileBytes /*Q,dO x2*/ + 2 * kTileBytes /*P*/ + 2 * kTileBytes /*dS*/ +
+                         2 * kTileBytes /*dQ staging: two [128 x 32] fp32 boxes*/ + 128;
+
+// Bulk reduce-add of a shared-memory box into a global fp32 tensor (out-of-range rows are clipped).
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(smem_src))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -639,7 +651,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int CG>
 __global__ void __launch_bounds__(128 * CG + 64, 1)
 mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do, const MhaBwdArgs a) {
+               const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+               const __grid_constant__ CUtensorMap tm_dqacc, const MhaBwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     unsigned char* sK = smem;
@@ -648,7 +661,8 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     unsigned char* sDO = sQ + 2 * kTileBytes;       // 2 stages
     unsigned char* sP = sDO + 2 * kTileBytes;       // [2][128][128B]
     unsigned char* sDS = sP + 2 * kTileBytes;       // [2][128][128B]
-    MhaBwdBarriers* bars = reinterpret_cast<MhaBwdBarriers*>(sDS + 2 * kTileBytes);
+    unsigned char* sDQ = sDS + 2 * kTileBytes;      // [2][128][128B] fp32 staging of one dQ tile (columns 0-31 | 32-63)
+    MhaBwdBarriers* bars = reinterpret_cast<MhaBwdBarriers*>(sDQ + 2 * kTileBytes);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -766,11 +780,26 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         constexpr int kColsD = kD / CG;     // dQ / dK / dV columns of this thread
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         const float c = a.scale_log2;
-        float* prev_dq_row = nullptr;       // where dQ of the previous tile goes (null: row outside the sequence)
-        auto flush_dq = [&](const float (&dq)[kColsD], float* dst) {
-            if (dst != nullptr && !(a.debug & 1)) {
+        // dQ of a tile leaves through shared memory and ONE bulk reduce-add per 32-column box (TMA,
+        // asynchronous, rows beyond Lq clipped by the tensor map) instead of per-thread RED.ADDs
+        const bool dq_issuer = (warp == 0 && lane == 0);
+        auto flush_dq = [&](const float (&dq)[kColsD], int q_tile) {
+            if (a.debug & 1) return;
+            if (dq_issuer) bulk_wait_read0();                 // the previous tile's reduce has read the staging
+            bar_sync_named(1, 128 * CG);
+            const int col0 = cg * kColsD;                     // first of this thread's dQ columns
+            unsigned char* dst = sDQ + (col0 >> 5) * kTileBytes + row * 128;
 #pragma unroll
-                for (int i = 0; i < kColsD; i += 4) red_add_v4(dst + i, dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+            for (int i = 0; i < kColsD; i += 4) {
+                const int chunk = (((col0 & 31) + i) >> 2) ^ (row & 7);
+                *reinterpret_cast<float4*>(dst + chunk * 16) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+            }
+            fence_proxy_async();
+            bar_sync_named(2, 128 * CG);
+            if (dq_issuer) {
+                tma_reduce_add_4d(&tm_dqacc, sDQ, 0, h, q_tile * kBM, b);
+                tma_reduce_add_4d(&tm_dqacc, sDQ + kTileBytes, 32, h, q_tile * kBM, b);
+                bulk_commit();
             }
         };
         auto load_dq = [&](float (&dq)[kColsD]) {
@@ -780,12 +809,20 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tmem_ld16(tm_dq + lane_base + cg * kColsD, dq);
             }
         };
+        // row statistics of the next tile are fetched one tile ahead
+        auto load_stats = [&](int it, float& lse2_o, float& dlt_o) {
+            const int qi = (i_start + it) * kBM + row;
+            const bool ok = it < nsteps && qi < a.Lq;
+            const size_t stat = ((size_t)b * a.Hh + h) * a.Lq + (ok ? qi : 0);
+            lse2_o = ok ? __ldg(a.lse + stat) * 1.4426950408889634f : INFINITY;
+            dlt_o = ok ? __ldg(a.delta + stat) : 0.0f;
+        };
+        float lse2_n, dlt_n;
+        load_stats(0, lse2_n, dlt_n);
         for (int it = 0; it < nsteps; ++it) {
             const int qi = (i_start + it) * kBM + row;
-            const bool q_ok = qi < a.Lq;
-            const size_t stat = ((size_t)b * a.Hh + h) * a.Lq + (q_ok ? qi : 0);
-            const float lse2 = q_ok ? __ldg(a.lse + stat) * 1.4426950408889634f : INFINITY;
-            const float dlt = q_ok ? __ldg(a.delta + stat) : 0.0f;
+            const float lse2 = lse2_n, dlt = dlt_n;
+            load_stats(it + 1, lse2_n, dlt_n);
             int lim = kvlen;
             if (a.causal) lim = min(lim, qi + 1);
             const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
@@ -847,15 +884,15 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&bars->pds_full);
-            if (it > 0) flush_dq(dq, prev_dq_row);
-            prev_dq_row = q_ok ? a.dq_acc + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + cg * kColsD : nullptr;
+            if (it > 0) flush_dq(dq, i_start + it - 1);
         }
         if (nsteps > 0) {
             float dq[kColsD];
             mbar_wait(&bars->dq_full, (nsteps - 1) & 1);
             tc_fence_after();
             load_dq(dq);
-            flush_dq(dq, prev_dq_row);
+            flush_dq(dq, i_start + nsteps - 1);
+            if (dq_issuer) bulk_wait0();    // the reduce must have landed before the kernel ends
         }
         // epilogue: dK_j, dV_j (thread = key row, kColsD columns).  The TMEM loads are warp-collective,
         // so every thread issues them; only rows inside the sequence store.
@@ -1035,10 +1072,17 @@ extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, con
     mha_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
                                                                  static_cast<const __nv_bfloat16*>(g_out), delta, B, Hh, Lq);
     ASR_LAUNCH_CHECK();
-    CUtensorMap tq, tk, tv, tdo;
+    CUtensorMap tq, tk, tv, tdo, tdq;
     if (make_qkv_map(&tq, q, B, Lq, Hh) || make_qkv_map(&tk, k, B, Lk, Hh) || make_qkv_map(&tv, v, B, Lk, Hh) ||
         make_qkv_map(&tdo, g_out, B, Lq, Hh))
         return 4;
+    {   // fp32 dQ accumulator [B,Lq,Hh,64]: boxes of [128 rows x 32 columns] (128-byte rows, swizzled)
+        const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)Hh, (uint64_t)Lq, (uint64_t)B};
+        const uint64_t strides[3] = {(uint64_t)kD * 4, (uint64_t)Hh * kD * 4, (uint64_t)Lq * Hh * kD * 4};
+        const uint32_t box[4] = {32u, 1u, (uint32_t)kBM, 1u};
+        if (make_tmap_nd(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dq_acc, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B))
+            return 4;
+    }
     MhaBwdArgs a;
     a.kv_len = kv_len;
     a.dense_mask = dense_mask;
@@ -1056,10 +1100,10 @@ extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, con
     const int cgo = get_opt("mha_bwd_groups");   // softmax-backward warps = 4 * groups; 0 = default (4)
     if (cgo == 2) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-        mha_bwd_kernel<2><<<grid, 256 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+        mha_bwd_kernel<2><<<grid, 256 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);
     } else {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-        mha_bwd_kernel<4><<<grid, 512 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, a);
+        mha_bwd_kernel<4><<<grid, 512 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);
     }
     ASR_LAUNCH_CHECK();
     size_t blocks = (nq_elems / 4 + 255) / 256;
