@@ -69,6 +69,7 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -118,6 +119,23 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// TMEM stores (registers -> accumulator columns), used to rescale O in place
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(__float_as_uint(v)) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors -------------------------------------------------------------------
 // Shared-memory matrix descriptor, 128-byte swizzle, 8-row groups 1024 bytes apart
@@ -436,6 +454,258 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
+// ---- forward, eight softmax warps per tile --------------------------------------------------
+// 10 warps: softmax warps 0-7 (warp w: TMEM lane quarter w % 4 = query rows, key half w / 4 of
+// every 128-key block), TMA producer (warp 8), MMA issuer (warp 9); two CTAs per SM.
+// A query row is shared by two threads: each takes the maximum over its 64 scores, the two
+// halves meet through shared memory and a 256-thread named barrier, each exponentiates its
+// half and owns 32 of the 64 output columns.  Four softmax warps per SM sub-partition (two
+// CTAs) hide the dependent-instruction latency that one warp per sub-partition leaves exposed.
+// The tensor pipe is fed out of order with respect to the tiles: S of block j+1 is issued as
+// soon as S of block j has been read (before P V of block j), and O is updated with P V of
+// block j-1 while block j is in flight, so neither product is waited for right after its issue.
+constexpr int kFwd3Threads = 320;
+constexpr int kFwd3Smem = kFwdSmem + 2 * 128 * 2 /*row maxima of the two halves, bf16*/;
+static_assert(2 * (kFwd3Smem + 1024) <= 233472, "two CTAs of the forward kernel must fit one SM");
+
+__global__ void __launch_bounds__(kFwd3Threads, 2)
+mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sQ = smem;
+    unsigned char* sK = sQ + kTileBytes;          // 2 stages
+    unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
+    unsigned char* sP = sV + 2 * kTileBytes;      // [2 key halves][128 rows][128 B]
+    MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sP + 2 * kTileBytes);
+    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sP + 2 * kTileBytes + 128);   // 128 bytes of bf16 1.0
+    __nv_bfloat16* sMax = reinterpret_cast<__nv_bfloat16*>(sP + 2 * kTileBytes + 256);   // [2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
+    fence_proxy_async();
+    const int q0 = blockIdx.x * kBM;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    int k_end = a.causal ? min(kvlen, q0 + kBM) : kvlen;
+    if (a.dense_mask) k_end = a.Lk;
+    const int nblk = max(1, (k_end + kBN - 1) / kBN);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->kv_full[s], 1);
+            mbar_init(&bars->kv_empty[s], 1);
+        }
+        mbar_init(&bars->s_full, 1);
+        mbar_init(&bars->s_free, 256);
+        mbar_init(&bars->p_full, 256);
+        mbar_init(&bars->pv_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(&bars->tmem_base, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem_s = tmem;          // 128 columns: S
+    const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
+    const uint32_t tmem_l = tmem + 192;    // 16 columns: P x ones (row sums)
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(&bars->q_full, kTileBytes);
+            tma_load_4d(sQ, &tm_q, 0, h, q0, b, &bars->q_full);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
+                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
+                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint32_t p_addr = smem_u32(sP);
+            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
+            fence_proxy_async();
+            auto issue_s = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + s * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full);
+            };
+            mbar_wait(&bars->q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
+                if (j + 1 < nblk) {
+                    mbar_wait(&bars->s_free, j & 1);      // S of block j has been read
+                    issue_s(j + 1);
+                }
+                mbar_wait(&bars->p_full, j & 1);          // P of block j is in shared memory, P V of block j-1 has been read
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
+                    umma_bf16(tmem_pv, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
+                    umma_bf16(tmem_l, ad, ones_desc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                tc_commit(&bars->pv_full);
+                tc_commit(&bars->kv_empty[s]);
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: thread = (query row, key half) =====
+        // O and the row sums accumulate in TMEM across the key blocks (P V and P x ones issued with
+        // accumulate).  They are scaled with m_used, the row maximum at the last rescale; a new
+        // maximum only forces a rescale (TMEM load, multiply, TMEM store) when it exceeds m_used by
+        // more than 8 in the exponent - otherwise the probabilities simply run up to 2^8, which
+        // bf16 P and the fp32 accumulators hold without loss.
+        const int row = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        const int qi = q0 + row;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        float m_used = -INFINITY;
+        const float c = a.scale_log2;
+        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+        for (int j = 0; j < nblk; ++j) {
+            const int key0 = j * kBN + half * 64;
+            int lim = kvlen;
+            if (a.causal) lim = min(lim, qi + 1);
+            const bool need_mask = (j * kBN + kBN > lim) || (mrow != nullptr);
+            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + cc + i;
+                    bool dead = key >= lim;
+                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                    if (dead) r[i] = 0xff800000u;   // -inf
+                }
+            };
+            mbar_wait(&bars->s_full, j & 1);
+            tc_fence_after();
+            // pass 1: maximum over this thread's 64 scores, then over both halves of the row
+            float m_half = -INFINITY;
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(tmem_s + lane_base + half * 64, ra);
+                tmem_ld32_issue(tmem_s + lane_base + half * 64 + 32, rb);
+                tmem_ld_wait();
+                if (need_mask) {
+                    apply_mask(ra, 0);
+                    apply_mask(rb, 32);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m_half = fmaxf(m_half, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+            }
+            // (any common reference works for the exponent, so the halves trade bf16-rounded maxima:
+            // 512 bytes instead of 1 KB keeps two CTAs on one SM; the next write is ordered behind
+            // this read by the s_free -> s_full chain)
+            const __nv_bfloat16 m_half_r = __float2bfloat16_rn(m_half);
+            sMax[half * 128 + row] = m_half_r;
+            bar_sync_named(1, 256);
+            const float m_new = fmaxf(m_used, fmaxf(__bfloat162float(m_half_r), __bfloat162float(sMax[(half ^ 1) * 128 + row])));
+            // P V of the previous block must be complete before its P tile is overwritten (and before O is rescaled)
+            if (j > 0) {
+                mbar_wait(&bars->pv_full, (j - 1) & 1);
+                tc_fence_after();
+            }
+            const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);   // same answer in both threads of the row
+            if (j == 0) {
+                m_used = m_new;
+            } else if (__any_sync(0xffffffffu, grow)) {          // TMEM accesses are warp-collective: all lanes go
+                const float f = grow ? ex2_approx((m_used - m_new) * c) : 1.0f;   // m_used = -inf -> 0
+                uint32_t r[32];
+                tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                tmem_st32(tmem_pv + lane_base + half * 32, r);
+                if (half == 0) tmem_st1(tmem_l + lane_base, tmem_ld1(tmem_l + lane_base) * f);
+                tmem_st_wait();
+                if (grow) m_used = m_new;
+            }
+            const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
+            // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle)
+            unsigned char* prow = sP + half * kTileBytes + row * 128;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                uint32_t r[32];
+                tmem_ld32_issue(tmem_s + lane_base + half * 64 + part * 32, r);
+                tmem_ld_wait();
+                if (need_mask) apply_mask(r, part * 32);
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const int chunk = (part * 4 + q4) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
+            fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+            mbar_arrive(&bars->p_full);
+        }
+        mbar_wait(&bars->pv_full, (nblk - 1) & 1);
+        tc_fence_after();
+        // epilogue: O / l -> bf16 -> out[b, qi, h, half*32 ..]; a fully masked row is 0/0 = NaN like the reference
+        {
+            uint32_t r[32];
+            tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
+            const float l_run = tmem_ld1(tmem_l + lane_base);
+            tc_fence_before();
+            if (qi < a.Lq) {
+                const float inv = 1.0f / l_run;
+                __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(r[i + 2 * u]) * inv, __uint_as_float(r[i + 2 * u + 1]) * inv);
+                        w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                    }
+                    *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if (a.lse != nullptr && half == 0)
+                    a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_used * c + log2f(l_run)) * 0.6931471805599453f;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
 // ---- forward, two query tiles per CTA in ping-pong -------------------------------------------
 // 10 warps: softmax warpgroup 0 (warps 0-3, tile 0), softmax warpgroup 1 (warps 4-7, tile 1), TMA
 // producer (warp 8), MMA issuer (warp 9).  Both tiles share the K/V stages; while one warpgroup
@@ -638,7 +908,6 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const 
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -1027,10 +1296,14 @@ extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, con
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = static_cast<__nv_bfloat16*>(out);
     a.lse = lse;
-    // Two query tiles per CTA in ping-pong when there is more than one tile of queries
-    // ("mha_variant": 0 = auto, 1 = always one tile per CTA, 2 = always two).
+    // "mha_variant": 0 = auto (3), 1 = one tile per CTA with four softmax warps, 2 = two tiles per CTA
+    // in ping-pong, 3 = one tile per CTA with eight softmax warps and O accumulated in TMEM.
     const int variant = get_opt("mha_variant");
-    if (variant == 2 || (variant == 0 && Lq >= 1024)) {   // measured: ping-pong wins from L ~ 1k on
+    if (variant == 0 || variant == 3) {   // measured: the eight-softmax-warp kernel wins at every length (534 vs 467 TFLOP/s at L=2048)
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
+        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
+        mha_fwd3_kernel<<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+    } else if (variant == 2) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
         mha_fwd2_kernel<<<grid, kFwd2Threads, kFwd2Smem, st>>>(tq, tk, tv, a);

@@ -8,6 +8,7 @@ import asr_b200
 lib = asr_b200._lib; L = lib.lib(); ptr, sp, check = lib.ptr, lib.stream_ptr, lib.check
 B, Ls, H = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 causal = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+if os.environ.get("ASR_MHA_VARIANT"): lib.set_option("mha_variant", int(os.environ["ASR_MHA_VARIANT"]))
 g = torch.Generator(device="cuda").manual_seed(5)
 q, k, v, do = (torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16) for _ in range(4))
 out = torch.empty_like(q); lse = torch.empty(B, H, Ls, device="cuda")
