@@ -174,7 +174,36 @@ struct MhaFwdArgs {
     float scale_log2;           // softmax scale * log2(e)
     __nv_bfloat16* out;         // [B,Lq,Hh,64]
     float* lse;                 // [B,Hh,Lq]   natural-log LSE of the scaled scores
+    // dropout on the probabilities (attention.py:83): element (b,h,q,k) is dropped when its random
+    // byte is < drop_thresh; kept elements are scaled by inv_keep = 256 / (256 - drop_thresh)
+    uint32_t drop_thresh;       // 0 = no dropout
+    float inv_keep;
+    uint32_t seed_lo, seed_hi;
 };
+
+// Philox4x32-7 (counter-based: forward and backward regenerate the same bits from the element's
+// coordinates).  One call yields the 16 random bytes of keys [k16*16, k16*16+16) of row q of head bh.
+__device__ __forceinline__ uint4 philox16(uint32_t k16, uint32_t q, uint32_t bh, uint32_t seed_lo, uint32_t seed_hi) {
+    uint32_t c0 = k16, c1 = q, c2 = bh, c3 = 0x2545F491u;
+    uint32_t k0 = seed_lo, k1 = seed_hi;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0;
+        c1 = lo1;
+        c2 = hi0 ^ c3 ^ k1;
+        c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+// random byte of key (k & 15) out of a philox16 result
+__device__ __forceinline__ uint32_t philox_byte(const uint4& r, int k) {
+    const uint32_t w = (k & 8) ? ((k & 4) ? r.w : r.z) : ((k & 4) ? r.y : r.x);
+    return (w >> ((k & 3) * 8)) & 0xffu;
+}
 
 struct __align__(8) MhaBarriers {
     uint64_t q_full;
@@ -468,6 +497,7 @@ constexpr int kFwd3Threads = 320;
 constexpr int kFwd3Smem = kFwdSmem + 2 * 128 * 2 /*row maxima of the two halves, bf16*/;
 static_assert(2 * (kFwd3Smem + 1024) <= 233472, "two CTAs of the forward kernel must fit one SM");
 
+template <bool DROP>
 __global__ void __launch_bounds__(kFwd3Threads, 2)
 mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
@@ -570,7 +600,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
                     const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
                     umma_bf16(tmem_pv, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
-                    umma_bf16(tmem_l, ad, ones_desc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);
+                    if (!DROP) umma_bf16(tmem_l, ad, ones_desc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);   // with dropout the P tile is not the softmax any more
                 }
                 tc_commit(&bars->pv_full);
                 tc_commit(&bars->kv_empty[s]);
@@ -588,6 +618,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int qi = q0 + row;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         float m_used = -INFINITY;
+        float l_part = 0.0f;         // DROP: sum of this thread's (undropped) probabilities, scaled like O
         const float c = a.scale_log2;
         const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
         for (int j = 0; j < nblk; ++j) {
@@ -643,7 +674,11 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
                 tmem_st32(tmem_pv + lane_base + half * 32, r);
-                if (half == 0) tmem_st1(tmem_l + lane_base, tmem_ld1(tmem_l + lane_base) * f);
+                if (DROP) {
+                    l_part *= f;
+                } else if (half == 0) {
+                    tmem_st1(tmem_l + lane_base, tmem_ld1(tmem_l + lane_base) * f);
+                }
                 tmem_st_wait();
                 if (grow) m_used = m_new;
             }
@@ -657,9 +692,28 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tmem_ld_wait();
                 if (need_mask) apply_mask(r, part * 32);
                 uint32_t pk[16];
+                if (DROP) {
+                    // fp32 exponentials: their sum is the softmax normaliser, the dropped and rescaled copy goes to the P tile
 #pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
+                    for (int g = 0; g < 2; ++g) {
+                        const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                   a.seed_lo, a.seed_hi);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i]), c, -mc));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i + 1]), c, -mc));
+                            l_part += p0 + p1;
+                            p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                            p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                            pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2)
+                        pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
+                }
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int chunk = (part * 4 + q4) ^ (row & 7);
@@ -674,10 +728,19 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_wait(&bars->pv_full, (nblk - 1) & 1);
         tc_fence_after();
         // epilogue: O / l -> bf16 -> out[b, qi, h, half*32 ..]; a fully masked row is 0/0 = NaN like the reference
+        if (DROP) {
+            // the two halves of a row add their normaliser parts through two spare accumulator columns
+            tmem_st1(tmem_l + lane_base + half, l_part);
+            tmem_st_wait();
+            tc_fence_before();
+            bar_sync_named(1, 256);
+            tc_fence_after();
+        }
         {
             uint32_t r[32];
             tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
-            const float l_run = tmem_ld1(tmem_l + lane_base);
+            float l_run = tmem_ld1(tmem_l + lane_base);
+            if (DROP) l_run += tmem_ld1(tmem_l + lane_base + 1);
             tc_fence_before();
             if (qi < a.Lq) {
                 const float inv = 1.0f / l_run;
@@ -882,7 +945,10 @@ struct MhaBwdArgs {
     float* dq_acc;        // [B,Lq,Hh,64] fp32, zeroed
     __nv_bfloat16* g_k;   // [B,Lk,Hh,64]
     __nv_bfloat16* g_v;
-    int debug;            // timing experiments only: 1 = skip the dQ reduction, 2 = skip the exponentials
+    int debug;            // timing experiments only: 1 = skip the dQ reduction
+    uint32_t drop_thresh; // dropout on the probabilities, same meaning as in MhaFwdArgs
+    float inv_keep;
+    uint32_t seed_lo, seed_hi;
 };
 
 struct __align__(8) MhaBwdBarriers {
@@ -917,7 +983,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // (warp w: TMEM lane quarter w % 4 = query rows, column group w / 4).  One warp per SM
 // sub-partition (CG = 1) leaves every dependent instruction's latency exposed; 4 per
 // sub-partition hide it.
-template <int CG>
+template <int CG, bool DROP>
 __global__ void __launch_bounds__(128 * CG + 64, 1)
 mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -1108,6 +1174,11 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 float sv[32], dp[32];
                 tmem_ld32(tm_s + lane_base + cc, sv);
                 tmem_ld32(tm_dp + lane_base + cc, dp);
+                uint4 rnd[2];
+                if (DROP) {
+                    rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
+                    rnd[1] = philox16(((uint32_t)(key0 + cc) >> 4) + 1, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
+                }
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = ex2_approx(fmaf(sv[i], c, -lse2));
@@ -1122,9 +1193,19 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         if (d0) p0 = 0.0f;
                         if (d1) p1 = 0.0f;
                     }
-                    const float s0 = p0 * (dp[i] - dlt) * a.scale;
-                    const float s1 = p1 * (dp[i + 1] - dlt) * a.scale;
-                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                    float g0 = dp[i], g1 = dp[i + 1];      // d(loss)/d(dropped, rescaled probability)
+                    float pd0 = p0, pd1 = p1;              // the probabilities P V was computed with
+                    if (DROP) {
+                        const bool k0 = philox_byte(rnd[i >> 4], i & 15) >= a.drop_thresh;
+                        const bool k1 = philox_byte(rnd[i >> 4], (i + 1) & 15) >= a.drop_thresh;
+                        g0 = k0 ? g0 * a.inv_keep : 0.0f;
+                        g1 = k1 ? g1 * a.inv_keep : 0.0f;
+                        pd0 = k0 ? p0 * a.inv_keep : 0.0f;
+                        pd1 = k1 ? p1 * a.inv_keep : 0.0f;
+                    }
+                    const float s0 = p0 * (g0 - dlt) * a.scale;
+                    const float s1 = p1 * (g1 - dlt) * a.scale;
+                    const __nv_bfloat162 pb = __floats2bfloat162_rn(pd0, pd1);
                     const __nv_bfloat162 sb = __floats2bfloat162_rn(s0, s1);
                     pk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
                     dk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
@@ -1265,6 +1346,29 @@ __global__ void __launch_bounds__(128) mha_probs_kernel(const __nv_bfloat16* q, 
     for (int key = lane; key < Lk; key += 32) dst[key] = expf(dst[key] - mx) / sum;
 }
 
+// keep[b,h,q,k] = 1 when the dropout of (seed, threshold) keeps that probability - the same bits the
+// attention kernels regenerate; for tests and for callers that want to inspect a mask
+__global__ void __launch_bounds__(256) mha_dropout_keep_kernel(uint8_t* keep, int B, int Hh, int Lq, int Lk, uint32_t thresh,
+                                                              uint32_t seed_lo, uint32_t seed_hi) {
+    const int k16n = (Lk + 15) >> 4;
+    const long long total = (long long)B * Hh * Lq * k16n;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int k16 = (int)(idx % k16n);
+    const long long rq = idx / k16n;
+    const int q = (int)(rq % Lq);
+    const int bh = (int)(rq / Lq);
+    const uint4 rnd = philox16((uint32_t)k16, (uint32_t)q, (uint32_t)bh, seed_lo, seed_hi);
+    uint8_t* dst = keep + ((size_t)bh * Lq + q) * Lk + (size_t)k16 * 16;
+    for (int i = 0; i < 16 && k16 * 16 + i < Lk; ++i) dst[i] = philox_byte(rnd, i) >= thresh ? 1 : 0;
+}
+
+static inline uint32_t drop_threshold(float p_drop) {
+    if (!(p_drop > 0.0f)) return 0;
+    int t = (int)(p_drop * 256.0f + 0.5f);
+    return (uint32_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
+}
+
 static int make_qkv_map(CUtensorMap* map, const void* base, int B, int L, int Hh) {
     const uint64_t dims[4] = {(uint64_t)kD, (uint64_t)Hh, (uint64_t)L, (uint64_t)B};
     const uint64_t strides[3] = {(uint64_t)kD * 2, (uint64_t)Hh * kD * 2, (uint64_t)L * Hh * kD * 2};
@@ -1276,14 +1380,15 @@ static int make_qkv_map(CUtensorMap* map, const void* base, int B, int L, int Hh
 
 using namespace asr;
 
-extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
-                                int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
-                                void* stream) {
+static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
+                        int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
+                        float p_drop, uint64_t seed, void* stream) {
     ASR_REQUIRE(q && k && v && out, "asr_mha_fwd_bf16: null pointer");
     ASR_REQUIRE(D == kD, "asr_mha_fwd_bf16: head dim %d not supported (64 only)", D);
     ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_fwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
     ASR_REQUIRE(B <= 65535 && Hh <= 65535, "asr_mha_fwd_bf16: B/Hh exceed the grid limits");
     ASR_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(out), "asr_mha_fwd_bf16: pointers must be 16-byte aligned");
+    ASR_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "asr_mha_fwd_dropout_bf16: p_drop %f outside [0, 1)", (double)p_drop);
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUtensorMap tq, tk, tv;
@@ -1296,13 +1401,22 @@ extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, con
     a.scale_log2 = scale * 1.4426950408889634f;
     a.out = static_cast<__nv_bfloat16*>(out);
     a.lse = lse;
+    a.drop_thresh = drop_threshold(p_drop);
+    a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);
+    a.seed_lo = (uint32_t)seed;
+    a.seed_hi = (uint32_t)(seed >> 32);
     // "mha_variant": 0 = auto (3), 1 = one tile per CTA with four softmax warps, 2 = two tiles per CTA
     // in ping-pong, 3 = one tile per CTA with eight softmax warps and O accumulated in TMEM.
+    // Dropout exists in variant 3 only.
     const int variant = get_opt("mha_variant");
-    if (variant == 0 || variant == 3) {   // measured: the eight-softmax-warp kernel wins at every length (534 vs 467 TFLOP/s at L=2048)
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
+    if (a.drop_thresh > 0) {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-        mha_fwd3_kernel<<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+        mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+    } else if (variant == 0 || variant == 3) {   // measured: the eight-softmax-warp kernel wins at every length (534 vs 467 TFLOP/s at L=2048)
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
+        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
+        mha_fwd3_kernel<false><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
     } else if (variant == 2) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
@@ -1316,6 +1430,30 @@ extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, con
     return 0;
 }
 
+extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
+                                int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
+                                void* stream) {
+    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, 0.0f, 0, stream);
+}
+
+extern "C" int asr_mha_fwd_dropout_bf16(const void* q, const void* k, const void* v, const int* kv_len,
+                                        const uint8_t* dense_mask, int causal, int B, int Hh, int Lq, int Lk, int D,
+                                        float scale, float p_drop, uint64_t seed, void* out, float* lse, void* stream) {
+    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, p_drop, seed, stream);
+}
+
+extern "C" float asr_mha_dropout_keep_prob(float p_drop) { return (256.0f - (float)drop_threshold(p_drop)) / 256.0f; }
+
+extern "C" int asr_mha_dropout_keep_u8(int B, int Hh, int Lq, int Lk, float p_drop, uint64_t seed, uint8_t* keep, void* stream) {
+    ASR_REQUIRE(keep != nullptr && B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_dropout_keep_u8: bad arguments");
+    if (asr_device_ok() != 0) return 3;
+    const long long total = (long long)B * Hh * Lq * ((Lk + 15) >> 4);
+    mha_dropout_keep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        keep, B, Hh, Lq, Lk, drop_threshold(p_drop), (uint32_t)seed, (uint32_t)(seed >> 32));
+    ASR_LAUNCH_CHECK();
+    return 0;
+}
+
 extern "C" size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int D) {
     (void)Lk;
     if (B <= 0 || Hh <= 0 || Lq <= 0 || D <= 0) return 0;
@@ -1323,10 +1461,10 @@ extern "C" size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int
     return (size_t)B * Lq * Hh * D * sizeof(float) + (size_t)B * Hh * Lq * sizeof(float) + 256;
 }
 
-extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
-                                const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
-                                int Lq, int Lk, int D, float scale, void* g_q, void* g_k, void* g_v, void* ws,
-                                size_t ws_bytes, void* stream) {
+static int mha_bwd_impl(const void* q, const void* k, const void* v, const void* out, const void* g_out,
+                        const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
+                        int Lq, int Lk, int D, float scale, float p_drop, uint64_t seed, void* g_q, void* g_k, void* g_v,
+                        void* ws, size_t ws_bytes, void* stream) {
     ASR_REQUIRE(q && k && v && out && g_out && lse && g_q && g_k && g_v && ws, "asr_mha_bwd_bf16: null pointer");
     ASR_REQUIRE(D == kD, "asr_mha_bwd_bf16: head dim %d not supported (64 only)", D);
     ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_bwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
@@ -1369,21 +1507,47 @@ extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, con
     a.g_k = static_cast<__nv_bfloat16*>(g_k);
     a.g_v = static_cast<__nv_bfloat16*>(g_v);
     a.debug = get_opt("mha_bwd_debug");
+    ASR_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "asr_mha_bwd_dropout_bf16: p_drop %f outside [0, 1)", (double)p_drop);
+    a.drop_thresh = drop_threshold(p_drop);
+    a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);
+    a.seed_lo = (uint32_t)seed;
+    a.seed_hi = (uint32_t)(seed >> 32);
+    const bool drop = a.drop_thresh > 0;
     dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
     const int cgo = get_opt("mha_bwd_groups");   // softmax-backward warps = 4 * groups; 0 = default (4)
+#define ASR_LAUNCH_BWD(CGV, DR)                                                                                              \
+    do {                                                                                                                   \
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<CGV, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); \
+        mha_bwd_kernel<CGV, DR><<<grid, 128 * CGV + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);                          \
+    } while (0)
     if (cgo == 2) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-        mha_bwd_kernel<2><<<grid, 256 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);
+        if (drop) ASR_LAUNCH_BWD(2, true); else ASR_LAUNCH_BWD(2, false);
     } else {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
-        mha_bwd_kernel<4><<<grid, 512 + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);
+        if (drop) ASR_LAUNCH_BWD(4, true); else ASR_LAUNCH_BWD(4, false);
     }
+#undef ASR_LAUNCH_BWD
     ASR_LAUNCH_CHECK();
     size_t blocks = (nq_elems / 4 + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
     f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(g_q), nq_elems / 4);
     ASR_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
+                                const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
+                                int Lq, int Lk, int D, float scale, void* g_q, void* g_k, void* g_v, void* ws,
+                                size_t ws_bytes, void* stream) {
+    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, 0.0f, 0, g_q, g_k, g_v,
+                        ws, ws_bytes, stream);
+}
+
+extern "C" int asr_mha_bwd_dropout_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
+                                        const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B,
+                                        int Hh, int Lq, int Lk, int D, float scale, float p_drop, uint64_t seed, void* g_q,
+                                        void* g_k, void* g_v, void* ws, size_t ws_bytes, void* stream) {
+    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, p_drop, seed, g_q, g_k,
+                        g_v, ws, ws_bytes, stream);
 }
 
 extern "C" int asr_mha_probs_f32(const void* q, const void* k, const int* kv_len, const uint8_t* dense_mask, int causal,

@@ -171,23 +171,24 @@ def ctc_loss(logits, len_logits, targets, blank=None, return_nll=False):
 # ---------------------------------------------------------------------------------
 class _MhaCoreFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, kv_len, dense_mask, causal, scale):
+    def forward(ctx, q, k, v, kv_len, dense_mask, causal, scale, p_drop, seed):
         B, Lq, Hh, D = q.shape
         Lk = k.shape[1]
         out = torch.empty((B, Lq, Hh, D), dtype=torch.bfloat16, device=q.device)
         lse = torch.empty((B, Hh, Lq), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            check(_lib.lib().asr_mha_fwd_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
-                                              B, Hh, Lq, Lk, D, ctypes.c_float(scale), ptr(out), ptr(lse),
-                                              stream_ptr()), "asr_mha_fwd_bf16")
+            check(_lib.lib().asr_mha_fwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
+                                                      B, Hh, Lq, Lk, D, ctypes.c_float(scale), ctypes.c_float(p_drop),
+                                                      ctypes.c_uint64(seed), ptr(out), ptr(lse), stream_ptr()),
+                  "asr_mha_fwd_dropout_bf16")
         ctx.save_for_backward(q, k, v, out, lse, kv_len, dense_mask)
-        ctx.meta = (causal, scale)
+        ctx.meta = (causal, scale, p_drop, seed)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         q, k, v, out, lse, kv_len, dense_mask = ctx.saved_tensors
-        causal, scale = ctx.meta
+        causal, scale, p_drop, seed = ctx.meta
         B, Lq, Hh, D = q.shape
         Lk = k.shape[1]
         g_out = g_out.contiguous()
@@ -197,22 +198,28 @@ class _MhaCoreFunction(torch.autograd.Function):
         ws_bytes = _lib.lib().asr_mha_bwd_workspace_bytes(B, Hh, Lq, Lk, D)
         ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            check(_lib.lib().asr_mha_bwd_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
-                                              ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D, ctypes.c_float(scale),
-                                              ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws), ws_bytes, stream_ptr()),
-                  "asr_mha_bwd_bf16")
-        return g_q, g_k, g_v, None, None, None, None
+            check(_lib.lib().asr_mha_bwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
+                                                      ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D, ctypes.c_float(scale),
+                                                      ctypes.c_float(p_drop), ctypes.c_uint64(seed),
+                                                      ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws), ws_bytes, stream_ptr()),
+                  "asr_mha_bwd_dropout_bf16")
+        return g_q, g_k, g_v, None, None, None, None, None, None
 
 
-def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None):
+def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_p=0.0, seed=None):
     """softmax(mask(q k^T * scale)) v on the tensor cores.
 
     q [B,Lq,Hh,64], k,v [B,Lk,Hh,64] (any float dtype; computed in bf16, fp32 accumulate)
     -> [B,Lq,Hh,64] bf16.  Masking: kv_len [B] (keys >= kv_len[b] masked), causal, and/or a
-    dense mask [B,Lq,Lk] (True / non-zero = masked), combined with OR."""
+    dense mask [B,Lq,Lk] (True / non-zero = masked), combined with OR.
+    dropout_p > 0 applies the reference's dropout to the probabilities (attention.py:83) inside
+    the kernel; `seed` (default: drawn from torch's CPU generator, so torch.manual_seed makes it
+    reproducible) selects the mask, which backward regenerates."""
     _require_cuda("q", q)
     if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
         raise ValueError("mha_core: q, k, v must be [B, L, heads, 64]")
+    if not 0.0 <= dropout_p < 1.0:
+        raise ValueError("mha_core: dropout_p must be in [0, 1)")
     if scale is None:
         scale = 1.0 / (q.shape[-1] ** 0.5)
     qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
@@ -220,7 +227,19 @@ def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None):
         kv_len = kv_len.to(device=q.device, dtype=torch.int32).contiguous()
     if mask is not None:
         mask = mask.to(device=q.device).ne(0).to(torch.uint8).contiguous()
-    return _MhaCoreFunction.apply(qb, kb, vb, kv_len, mask, bool(causal), float(scale))
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _MhaCoreFunction.apply(qb, kb, vb, kv_len, mask, bool(causal), float(scale), float(dropout_p),
+                                  int(seed or 0))
+
+
+def mha_dropout_keep(B, Hh, Lq, Lk, dropout_p, seed, device="cuda"):
+    """(keep mask [B,Hh,Lq,Lk] bool, keep probability) of mha_core's dropout for (dropout_p, seed)."""
+    keep = torch.empty((B, Hh, Lq, Lk), dtype=torch.uint8, device=device)
+    with torch.cuda.device(keep.device):
+        check(_lib.lib().asr_mha_dropout_keep_u8(B, Hh, Lq, Lk, ctypes.c_float(dropout_p), ctypes.c_uint64(seed),
+                                                 ptr(keep), stream_ptr()), "asr_mha_dropout_keep_u8")
+    return keep.bool(), float(_lib.lib().asr_mha_dropout_keep_prob(ctypes.c_float(dropout_p)))
 
 
 def mha_probs(q, k, kv_len=None, mask=None, causal=False, scale=None):

@@ -13,9 +13,11 @@ built with `return_attn=True` (every training caller of the reference discards i
 encoder.py:72, decoder.py:628-633), in which case it is computed by a separate
 kernel in the reference's head-major row order.
 
-Dropout on the probabilities (reference :83) is not applied by the kernel in this
-round: with `dropout > 0` in training mode the module raises unless
-`allow_no_attn_dropout=True`; parity runs use `eval()` / `dropout=0`.
+Dropout on the probabilities (reference :83) happens inside the kernel in training
+mode: a counter-based generator keyed by a per-call seed (drawn from torch's CPU
+generator, so `torch.manual_seed` reproduces a run) decides per (b, head, q, k), and
+backward regenerates the same mask.  The rate is quantised to 1/256 (0.1 -> 26/256)
+with the exactly matching rescale, so the expectation is unbiased.
 """
 import numpy as np
 import torch
@@ -27,8 +29,7 @@ from ..ops import mha_core, mha_probs
 class MultiheadAttention(nn.Module):
     ''' Multi-Head Attention module (same parameters as the reference) '''
 
-    def __init__(self, d_model, n_head, d_k=64, d_v=64, dropout=0.1, return_attn=False,
-                 allow_no_attn_dropout=True):
+    def __init__(self, d_model, n_head, d_k=64, d_v=64, dropout=0.1, return_attn=False):
         super().__init__()
         if d_k != 64 or d_v != 64:
             raise ValueError("the sm_100a attention core is built for d_k = d_v = 64 (every reference recipe)")
@@ -36,7 +37,6 @@ class MultiheadAttention(nn.Module):
         self.d_k = d_k
         self.d_v = d_v
         self.return_attn = return_attn
-        self.allow_no_attn_dropout = allow_no_attn_dropout
 
         self.w_qs = nn.Linear(d_model, n_head * d_k)
         self.w_ks = nn.Linear(d_model, n_head * d_k)
@@ -61,15 +61,15 @@ class MultiheadAttention(nn.Module):
         n_head, d_k, d_v = self.n_head, self.d_k, self.d_v
         sz_b, len_q, _ = q.size()
         len_k = k.size(1)
-        if self.training and self.attn_dropout_p > 0 and not self.allow_no_attn_dropout:
-            raise RuntimeError("attention-probability dropout is not implemented by the sm_100a core")
 
         residual = q
         qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
         kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
         vh = self.w_vs(v).view(sz_b, len_k, n_head, d_v)
 
-        ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
+        p_attn = self.attn_dropout_p if self.training else 0.0
+        ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature),
+                       dropout_p=p_attn)
         attn = None
         if self.return_attn:
             attn = mha_probs(qh, kh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))

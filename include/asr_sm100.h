@@ -187,6 +187,31 @@ int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, const void* ou
                      int B, int Hh, int Lq, int Lk, int D, float scale,
                      void* g_q, void* g_k, void* g_v,
                      void* ws, size_t ws_bytes, void* stream);
+/* The same pair with the reference's dropout on the probabilities
+ * (`attn = self.dropout(attn)`, attention.py:83, training mode): element
+ * (b,h,q,k) of softmax(S) is zeroed with probability p and the kept ones are
+ * scaled by 1/(1-p) before the product with V; backward regenerates the same
+ * mask from (seed, coordinates) with a counter-based generator (Philox4x32-7),
+ * nothing is stored.  p is quantised to 1/256: the drop probability actually used
+ * is round(256 p)/256 and the scale its exact inverse keep probability
+ * (asr_mha_dropout_keep_prob), so the expectation is unbiased.  p_drop = 0 is the
+ * plain call.  asr_mha_dropout_keep_u8 writes the keep mask [B,Hh,Lq,Lk] u8 for
+ * the same (p_drop, seed): tests and debugging. */
+int asr_mha_fwd_dropout_bf16(const void* q, const void* k, const void* v,
+                             const int* kv_len, const uint8_t* dense_mask, int causal,
+                             int B, int Hh, int Lq, int Lk, int D, float scale,
+                             float p_drop, uint64_t seed,
+                             void* out, float* lse, void* stream);
+int asr_mha_bwd_dropout_bf16(const void* q, const void* k, const void* v, const void* out,
+                             const void* g_out, const float* lse,
+                             const int* kv_len, const uint8_t* dense_mask, int causal,
+                             int B, int Hh, int Lq, int Lk, int D, float scale,
+                             float p_drop, uint64_t seed,
+                             void* g_q, void* g_k, void* g_v,
+                             void* ws, size_t ws_bytes, void* stream);
+float asr_mha_dropout_keep_prob(float p_drop);
+int asr_mha_dropout_keep_u8(int B, int Hh, int Lq, int Lk, float p_drop, uint64_t seed,
+                            uint8_t* keep, void* stream);
 /* attention probabilities [Hh*B, Lq, Lk] f32 in the reference's head-major row
  * order (attention.py:47,62) - only computed when a caller asks for `attn`. */
 int asr_mha_probs_f32(const void* q, const void* k,

@@ -7,7 +7,7 @@ twin at src/ctcModel/attention.py is identical apart from the ctor order):
     q,k,v   = w_qs(q), w_ks(k), w_vs(v)                       :43-45
     split into heads, HEAD-MAJOR batch order (row = head * B + b)  :47-49
     attn    = softmax(masked_fill(q k^T / sqrt(d_k), mask, -inf), dim=2)   :76-82
-    (dropout on the probabilities - identity here: parity runs use eval())
+    attn    = dropout(attn)   (training mode; here with an explicit keep mask)   :83
     out     = attn v                                          :84
     merge heads -> fc -> (dropout) -> LayerNorm(out + residual)    :56-60
 A fully masked row is NaN in the reference (softmax over all -inf); so it is here.
@@ -22,9 +22,11 @@ def _softmax_lastdim(x):
         return e / e.sum(-1, keepdims=True)
 
 
-def mha_core_forward(q, k, v, mask=None, scale=None, dtype=np.float64):
+def mha_core_forward(q, k, v, mask=None, scale=None, dtype=np.float64, keep=None, keep_prob=1.0):
     """q [N,Lq,d], k [N,Lk,d], v [N,Lk,dv]; mask [N,Lq,Lk] bool (True = masked).
-    Returns (out [N,Lq,dv], attn [N,Lq,Lk])."""
+    keep [N,Lq,Lk] bool + keep_prob: the dropout of attention.py:83 with an explicit mask
+    (nn.Dropout zeroes with probability p and scales the rest by 1/(1-p) = 1/keep_prob).
+    Returns (out [N,Lq,dv], attn [N,Lq,Lk]); attn is the softmax BEFORE dropout."""
     q, k, v = (np.asarray(a).astype(dtype) for a in (q, k, v))
     if scale is None:
         scale = 1.0 / np.sqrt(q.shape[-1])
@@ -32,17 +34,19 @@ def mha_core_forward(q, k, v, mask=None, scale=None, dtype=np.float64):
     if mask is not None:
         s = np.where(np.asarray(mask).astype(bool), dtype(-np.inf), s)
     attn = _softmax_lastdim(s)
-    return np.einsum("nqk,nkd->nqd", attn, v), attn
+    used = attn if keep is None else attn * np.asarray(keep).astype(dtype) / dtype(keep_prob)
+    return np.einsum("nqk,nkd->nqd", used, v), attn
 
 
-def mha_core_backward(q, k, v, g_out, mask=None, scale=None, dtype=np.float64):
+def mha_core_backward(q, k, v, g_out, mask=None, scale=None, dtype=np.float64, keep=None, keep_prob=1.0):
     """Gradients of mha_core_forward's `out` w.r.t. q, k, v."""
     q, k, v, g_out = (np.asarray(a).astype(dtype) for a in (q, k, v, g_out))
     if scale is None:
         scale = 1.0 / np.sqrt(q.shape[-1])
     _, p = mha_core_forward(q, k, v, mask, scale, dtype)
-    g_v = np.einsum("nqk,nqd->nkd", p, g_out)
-    g_p = np.einsum("nqd,nkd->nqk", g_out, v)
+    m = 1.0 if keep is None else np.asarray(keep).astype(dtype) / dtype(keep_prob)
+    g_v = np.einsum("nqk,nqd->nkd", p * m, g_out)
+    g_p = np.einsum("nqd,nkd->nqk", g_out, v) * m        # through the dropout to the softmax output
     g_s = p * (g_p - (g_p * p).sum(-1, keepdims=True))
     g_q = np.einsum("nqk,nkd->nqd", g_s, k) * dtype(scale)
     g_k = np.einsum("nqk,nqd->nkd", g_s, q) * dtype(scale)

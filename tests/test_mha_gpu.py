@@ -196,3 +196,100 @@ def test_module_gradients_against_reference_golden(case):
         ref = MHA[case + "_gw_" + pn]
         scale = max(np.abs(ref).max(), bias_scale if pn == "w_ks.bias" else 0.0)
         assert np.abs(to_np(p.grad) - ref).max() <= 3e-2 * scale + 1e-6, pn
+
+
+# ---- dropout on the probabilities (reference attention.py:83) -----------------------------------
+def _torch_core_dropout(q, k, v, keep, keep_prob, mask=None, scale=None):
+    """fp32 reference with an explicit keep mask [B,H,Lq,Lk]: softmax, drop, rescale, product."""
+    B, Lq, H, D = q.shape
+    scale = scale or 1.0 / D ** 0.5
+    qh, kh, vh = (t.float().permute(0, 2, 1, 3) for t in (q, k, v))
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    if mask is not None:
+        s = s.masked_fill(mask[:, None].bool(), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    p = p * keep.float() / keep_prob
+    return torch.matmul(p, vh).permute(0, 2, 1, 3)
+
+
+def test_dropout_mask_statistics_and_determinism():
+    ops = pkg("ops")
+    B, H, Lq, Lk = 2, 4, 200, 333
+    keep, kp = ops.mha_dropout_keep(B, H, Lq, Lk, 0.1, seed=1234)
+    assert abs(kp - 230.0 / 256.0) < 1e-7          # 0.1 is quantised to 26/256
+    n = keep.numel()
+    frac = keep.float().mean().item()
+    assert abs(frac - kp) < 5 * (kp * (1 - kp) / n) ** 0.5
+    # per row and per column too (no stripes)
+    assert (keep.float().mean(-1) - kp).abs().max().item() < 0.12
+    assert (keep.float().mean(-2) - kp).abs().max().item() < 0.12
+    keep2, _ = ops.mha_dropout_keep(B, H, Lq, Lk, 0.1, seed=1234)
+    keep3, _ = ops.mha_dropout_keep(B, H, Lq, Lk, 0.1, seed=1235)
+    assert torch.equal(keep, keep2)
+    assert 0.7 < (keep ^ keep3).float().mean().item() / (2 * kp * (1 - kp)) < 1.3   # independent masks
+    keep0, kp0 = ops.mha_dropout_keep(1, 1, 8, 40, 0.0, seed=7)
+    assert kp0 == 1.0 and keep0.all()
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H,p,causal", [(2, 128, 128, 2, 0.1, False), (1, 167, 167, 8, 0.1, True),
+                                               (2, 70, 300, 4, 0.3, False), (1, 257, 129, 3, 0.5, False)])
+def test_dropout_forward_backward_match_explicit_mask(B, Lq, Lk, H, p, causal):
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(B, Lq, Lk, H, seed=11 + Lq)
+    kv_len = torch.tensor([Lk - 7 * i for i in range(B)], dtype=torch.int32, device="cuda")
+    seed = 99 + Lk
+    keep, kp = ops.mha_dropout_keep(B, H, Lq, Lk, p, seed)
+    dense = torch.arange(Lk, device="cuda")[None, None, :] >= kv_len[:, None, None]
+    dense = dense.expand(B, Lq, Lk)
+    if causal:
+        dense = dense | torch.triu(torch.ones(Lq, Lk, dtype=torch.bool, device="cuda"), 1)[None]
+    qs, ks, vs = (t.clone().requires_grad_(True) for t in (q, k, v))
+    out = ops.mha_core(qs, ks, vs, kv_len=kv_len, causal=causal, dropout_p=p, seed=seed)
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    ref = _torch_core_dropout(qr, kr, vr, keep, kp, mask=dense)
+    _close(out, ref)
+    g = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    out.backward(g.to(out.dtype))
+    ref.backward(g)
+    _close(qs.grad, qr.grad, 3e-2)
+    _close(ks.grad, kr.grad, 3e-2)
+    _close(vs.grad, vr.grad, 3e-2)
+    # same seed -> same result, other seed -> a different mask
+    out2 = ops.mha_core(q, k, v, kv_len=kv_len, causal=causal, dropout_p=p, seed=seed)
+    out3 = ops.mha_core(q, k, v, kv_len=kv_len, causal=causal, dropout_p=p, seed=seed + 1)
+    assert torch.equal(out.detach(), out2)
+    assert not torch.equal(out.detach(), out3)
+
+
+def test_dropout_zero_is_the_plain_kernel_and_expectation_is_unbiased():
+    ops = pkg("ops")
+    q, k, v = _rand_qkv(1, 128, 256, 2, seed=5)
+    plain = ops.mha_core(q, k, v)
+    assert torch.equal(plain, ops.mha_core(q, k, v, dropout_p=0.0, seed=123))
+    acc = torch.zeros_like(plain, dtype=torch.float32)
+    n = 64
+    for s in range(n):
+        acc += ops.mha_core(q, k, v, dropout_p=0.25, seed=1000 + s).float()
+    # mean over 64 masks approaches the undropped output: error ~ sqrt(p/(1-p)/n) of a row's spread
+    _close(acc / n, plain, 0.25)
+
+
+def test_module_applies_attention_dropout_only_in_training():
+    MHA = pkg("transformer.attention").MultiheadAttention
+    torch.manual_seed(0)
+    m = MHA(128, 2, dropout=0.2).cuda()
+    x = torch.randn(2, 50, 128, device="cuda")
+    m.eval()
+    y0, _ = m(x, x, x)
+    y1, _ = m(x, x, x)
+    assert torch.equal(y0, y1)
+    m.train()
+    torch.manual_seed(1)
+    t0, _ = m(x, x, x)
+    torch.manual_seed(1)
+    t1, _ = m(x, x, x)
+    torch.manual_seed(2)
+    t2, _ = m(x, x, x)
+    assert torch.equal(t0, t1) and not torch.equal(t0, t2) and not torch.equal(t0, y0)
+    t0.sum().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())

@@ -146,6 +146,35 @@ def test_mha_core_backward_against_finite_difference():
         np.testing.assert_allclose(grad, num, rtol=1e-5, atol=1e-7)
 
 
+def test_mha_dropout_oracle_against_finite_difference():
+    """The explicit-mask dropout of the oracle (attention.py:83 semantics) and its analytic backward."""
+    rng = np.random.default_rng(1)
+    N, Lq, Lk, d = 2, 3, 5, 4
+    q, k, v = rng.normal(size=(N, Lq, d)), rng.normal(size=(N, Lk, d)), rng.normal(size=(N, Lk, d))
+    g = rng.normal(size=(N, Lq, d))
+    keep = rng.random((N, Lq, Lk)) > 0.3
+    out, attn = oracle.mha_core_forward(q, k, v, keep=keep, keep_prob=0.7)
+    np.testing.assert_allclose(out, np.einsum("nqk,nkd->nqd", attn * keep / 0.7, v))
+    gq, gk, gv = oracle.mha_core_backward(q, k, v, g, keep=keep, keep_prob=0.7)
+
+    def f(qq, kk, vv):
+        return (mha_oracle.mha_core_forward(qq, kk, vv, keep=keep, keep_prob=0.7)[0] * g).sum()
+    eps = 1e-6
+    for arr, grad in ((q, gq), (k, gk), (v, gv)):
+        num = np.zeros_like(arr)
+        it = np.nditer(arr, flags=["multi_index"])
+        for _ in it:
+            i = it.multi_index
+            old = arr[i]
+            arr[i] = old + eps
+            fp = f(q, k, v)
+            arr[i] = old - eps
+            fm = f(q, k, v)
+            arr[i] = old
+            num[i] = (fp - fm) / (2 * eps)
+        np.testing.assert_allclose(grad, num, rtol=1e-5, atol=1e-7)
+
+
 def test_masks():
     g = load_golden("masks")
     np.testing.assert_array_equal(oracle.sequence_mask(g["lens"]), g["sequence_mask"])
