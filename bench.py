@@ -405,7 +405,7 @@ def run_train(args, w, rank, world, device, steps=None, emit=True):
                 "config": dict(workload=args.workload, per_gpu=w, model="CIF_Model reference recipe defaults",
                                params=n_params, grad_allreduce_bytes=sync.grad_bytes(),
                                parallelism="dp%d by utterance, NCCL gradient all-reduce (bucketed, overlapped)" % world,
-                               note="attention-probability dropout is not applied by the tcgen05 core"),
+                               note="training mode: attention-probability dropout 0.1 applied inside the tcgen05 kernels"),
                 "clocks": clocks,
                 "e2e": {"value": world * w["B"] * Ke / float(dt.item()), "unit": UNIT,
                         "h2d_bytes_per_step": sum(h.numel() * h.element_size() for h in host), "d2h_bytes_per_step": 4,

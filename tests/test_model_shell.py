@@ -48,9 +48,10 @@ def test_create_model_builds_the_recipe_default():
     assert m.ctc_fc.weight.shape == (50, 64) and m.conv_encoder.affine.in_features == 32 * 160
 
 
-def _torch_fp32_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None):
+def _torch_fp32_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_p=0.0, seed=None):
     """fp32 stand-in for ops.mha_core with the same signature (test only: isolates the CIF / CTC
     drop-ins from bf16 rounding in the attention, which can move a fire by one frame)."""
+    assert dropout_p == 0.0, "the stand-in is for eval-mode parity runs"
     B, Lq, H, D = q.shape
     Lk = k.shape[1]
     s = torch.einsum("bqhd,bkhd->bhqk", q.float(), k.float()) * (scale or 1.0 / D ** 0.5)
