@@ -55,6 +55,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same product with the A operand read from tensor memory (lane = row, 8 columns = 16 bf16 of K).
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), columns c..c+31.
 // tmem_ld32_issue starts the (asynchronous) load, tmem_ld_wait makes its registers valid.
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
@@ -130,6 +139,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
           "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
           "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
           "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, float v) {
@@ -723,6 +740,280 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_before();
             mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
             fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+            mbar_arrive(&bars->p_full);
+        }
+        mbar_wait(&bars->pv_full, (nblk - 1) & 1);
+        tc_fence_after();
+        // epilogue: O / l -> bf16 -> out[b, qi, h, half*32 ..]; a fully masked row is 0/0 = NaN like the reference
+        if (DROP) {
+            // the two halves of a row add their normaliser parts through two spare accumulator columns
+            tmem_st1(tmem_l + lane_base + half, l_part);
+            tmem_st_wait();
+            tc_fence_before();
+            bar_sync_named(1, 256);
+            tc_fence_after();
+        }
+        {
+            uint32_t r[32];
+            tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
+            float l_run = tmem_ld1(tmem_l + lane_base);
+            if (DROP) l_run += tmem_ld1(tmem_l + lane_base + 1);
+            tc_fence_before();
+            if (qi < a.Lq) {
+                const float inv = 1.0f / l_run;
+                __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + half * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(r[i + 2 * u]) * inv, __uint_as_float(r[i + 2 * u + 1]) * inv);
+                        w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                    }
+                    *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                if (a.lse != nullptr && half == 0)
+                    a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_used * c + log2f(l_run)) * 0.6931471805599453f;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+// ---- forward, eight softmax warps per tile, P in tensor memory -----------------------------------
+// Same thread layout as mha_fwd3_kernel, but the probabilities never touch shared memory: each
+// thread writes its packed bf16 P over the S columns it has just read (tcgen05.st) and the
+// P V / P x ones products take their A operand from TMEM.  Per 128-key block that removes the
+// 32 KB P store and two 32 KB P reads from the shared-memory pipe, which was the bound
+// (176 KB per block at 128 B/clk ~ 1400 cycles against ~800 cycles of tensor work).  S and P
+// share columns, so Q K^T of block j+1 runs after P V of block j (tensor-pipe issue order); the
+// second CTA on the SM fills the gap.
+// TMEM: S/P 0-127 (P of keys [64h+32p, +32) packed in columns 64h+32p .. +15) | O 128-191 | L 192-207.
+// 10 warps: softmax warps 0-7 (warp w: TMEM lane quarter w % 4 = query rows, key half w / 4 of
+// every 128-key block), TMA producer (warp 8), MMA issuer (warp 9); two CTAs per SM.
+// A query row is shared by two threads: each takes the maximum over its 64 scores, the two
+// halves meet through shared memory and a 256-thread named barrier, each exponentiates its
+// half and owns 32 of the 64 output columns.  Four softmax warps per SM sub-partition (two
+// CTAs) hide the dependent-instruction latency that one warp per sub-partition leaves exposed.
+// The tensor pipe is fed out of order with respect to the tiles: S of block j+1 is issued as
+// soon as S of block j has been read (before P V of block j), and O is updated with P V of
+// block j-1 while block j is in flight, so neither product is waited for right after its issue.
+constexpr int kFwd4Threads = 320;
+constexpr int kFwd4Smem = 5 * kTileBytes /*Q + K,V x2*/ + 128 /*barriers*/ + 128 /*ones*/ + 2 * 128 * 2 /*row maxima*/;
+
+template <bool DROP>
+__global__ void __launch_bounds__(kFwd4Threads, 2)
+mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sQ = smem;
+    unsigned char* sK = sQ + kTileBytes;          // 2 stages
+    unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
+    MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sV + 2 * kTileBytes);
+    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sV + 2 * kTileBytes + 128);   // 128 bytes of bf16 1.0
+    __nv_bfloat16* sMax = reinterpret_cast<__nv_bfloat16*>(sV + 2 * kTileBytes + 256);   // [2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
+    fence_proxy_async();
+    const int q0 = blockIdx.x * kBM;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    int k_end = a.causal ? min(kvlen, q0 + kBM) : kvlen;
+    if (a.dense_mask) k_end = a.Lk;
+    const int nblk = max(1, (k_end + kBN - 1) / kBN);
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->kv_full[s], 1);
+            mbar_init(&bars->kv_empty[s], 1);
+        }
+        mbar_init(&bars->s_full, 1);
+        mbar_init(&bars->p_full, 256);
+        mbar_init(&bars->pv_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) {
+        tmem_alloc(&bars->tmem_base, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tmem_s = tmem;          // 128 columns: S
+    const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
+    const uint32_t tmem_l = tmem + 192;    // 16 columns: P x ones (row sums)
+
+    if (warp == 8) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(&bars->q_full, kTileBytes);
+            tma_load_4d(sQ, &tm_q, 0, h, q0, b, &bars->q_full);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
+                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
+                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
+            fence_proxy_async();
+            mbar_wait(&bars->q_full, 0);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j & 1;
+                mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
+                tc_fence_after();
+                const uint32_t k_addr = smem_u32(sK + s * kTileBytes);
+                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
+                // S overwrites the P of the previous block: ordered behind its P V by the pipe's issue order
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full);             // also: every earlier product (P V of block j-1) is complete
+                mbar_wait(&bars->p_full, j & 1);      // P of block j is in TMEM
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    // keys [16 kk, 16 kk + 16): half kk >> 2, 32-key part (kk >> 1) & 1, 8 packed columns
+                    const uint32_t a_tmem = tmem_s + 64 * (kk >> 2) + 32 * ((kk >> 1) & 1) + 8 * (kk & 1);
+                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
+                    umma_bf16_ts(tmem_pv, a_tmem, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
+                    if (!DROP) umma_bf16_ts(tmem_l, a_tmem, ones_desc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);
+                }
+                tc_commit(&bars->pv_full);
+                tc_commit(&bars->kv_empty[s]);
+            }
+        }
+    } else {
+        // ===== softmax + epilogue: thread = (query row, key half) =====
+        // O and the row sums accumulate in TMEM across the key blocks (P V and P x ones issued with
+        // accumulate).  They are scaled with m_used, the row maximum at the last rescale; a new
+        // maximum only forces a rescale (TMEM load, multiply, TMEM store) when it exceeds m_used by
+        // more than 8 in the exponent - otherwise the probabilities simply run up to 2^8, which
+        // bf16 P and the fp32 accumulators hold without loss.
+        const int row = (warp & 3) * 32 + lane;
+        const int half = warp >> 2;
+        const int qi = q0 + row;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        float m_used = -INFINITY;
+        float l_part = 0.0f;         // DROP: sum of this thread's (undropped) probabilities, scaled like O
+        const float c = a.scale_log2;
+        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+        for (int j = 0; j < nblk; ++j) {
+            const int key0 = j * kBN + half * 64;
+            int lim = kvlen;
+            if (a.causal) lim = min(lim, qi + 1);
+            const bool need_mask = (j * kBN + kBN > lim) || (mrow != nullptr);
+            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int key = key0 + cc + i;
+                    bool dead = key >= lim;
+                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                    if (dead) r[i] = 0xff800000u;   // -inf
+                }
+            };
+            mbar_wait(&bars->s_full, j & 1);
+            tc_fence_after();
+            // pass 1: maximum over this thread's 64 scores, then over both halves of the row
+            float m_half = -INFINITY;
+            {
+                uint32_t ra[32], rb[32];
+                tmem_ld32_issue(tmem_s + lane_base + half * 64, ra);
+                tmem_ld32_issue(tmem_s + lane_base + half * 64 + 32, rb);
+                tmem_ld_wait();
+                if (need_mask) {
+                    apply_mask(ra, 0);
+                    apply_mask(rb, 32);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) m_half = fmaxf(m_half, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+            }
+            // (any common reference works for the exponent, so the halves trade bf16-rounded maxima:
+            // 512 bytes instead of 1 KB keeps two CTAs on one SM; the next write is ordered behind
+            // this read by the s_free -> s_full chain)
+            const __nv_bfloat16 m_half_r = __float2bfloat16_rn(m_half);
+            sMax[half * 128 + row] = m_half_r;
+            bar_sync_named(1, 256);
+            const float m_new = fmaxf(m_used, fmaxf(__bfloat162float(m_half_r), __bfloat162float(sMax[(half ^ 1) * 128 + row])));
+            // (s_full of this block was committed after P V of the previous one: O is stable here)
+            const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);   // same answer in both threads of the row
+            if (j == 0) {
+                m_used = m_new;
+            } else if (__any_sync(0xffffffffu, grow)) {          // TMEM accesses are warp-collective: all lanes go
+                const float f = grow ? ex2_approx((m_used - m_new) * c) : 1.0f;   // m_used = -inf -> 0
+                uint32_t r[32];
+                tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
+                tmem_st32(tmem_pv + lane_base + half * 32, r);
+                if (DROP) {
+                    l_part *= f;
+                } else if (half == 0) {
+                    tmem_st1(tmem_l + lane_base, tmem_ld1(tmem_l + lane_base) * f);
+                }
+                tmem_st_wait();
+                if (grow) m_used = m_new;
+            }
+            const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
+            // pass 2: probabilities -> packed bf16 -> over the S columns just read (A operand of P V)
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                uint32_t r[32];
+                tmem_ld32_issue(tmem_s + lane_base + half * 64 + part * 32, r);
+                tmem_ld_wait();
+                if (need_mask) apply_mask(r, part * 32);
+                uint32_t pk[16];
+                if (DROP) {
+                    // fp32 exponentials: their sum is the softmax normaliser, the dropped and rescaled copy goes to the P tile
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                   a.seed_lo, a.seed_hi);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float p0 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i]), c, -mc));
+                            float p1 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i + 1]), c, -mc));
+                            l_part += p0 + p1;
+                            p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                            p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                            pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2)
+                        pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
+                }
+                tmem_st16(tmem_s + lane_base + half * 64 + part * 32, pk);
+            }
+            tmem_st_wait();
+            tc_fence_before();
             mbar_arrive(&bars->p_full);
         }
         mbar_wait(&bars->pv_full, (nblk - 1) & 1);
@@ -1413,6 +1704,10 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+    } else if (variant == 4) {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd4Smem));
+        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
+        mha_fwd4_kernel<false><<<grid, kFwd4Threads, kFwd4Smem, st>>>(tq, tk, tv, a);
     } else if (variant == 0 || variant == 3) {   // measured: the eight-softmax-warp kernel wins at every length (534 vs 467 TFLOP/s at L=2048)
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);

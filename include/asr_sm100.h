@@ -53,7 +53,8 @@ int         asr_device_ok(void);
  * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
  * max 8; results are bit-identical for every value), "mha_variant" (0 = auto = 3,
  * 1 = one tile per CTA with four softmax warps, 2 = two-tile ping-pong, 3 = eight
- * softmax warps per tile, O accumulated in TMEM with lazy rescale), "mha_bwd_groups" (softmax-backward
+ * softmax warps per tile, O accumulated in TMEM with lazy rescale, 4 = as 3 with P
+ * kept in TMEM as the A operand of P V), "mha_bwd_groups" (softmax-backward
  * warps per CTA = 4 * groups; 0 = default (4 groups), 2). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
