@@ -288,6 +288,97 @@ __global__ void __launch_bounds__(128) cif_fwd_plain_kernel(const CifFwdArgs a, 
     cif_fwd_finish<VEC>(a, b, slice, lane, col, col_ok, k, asum);
 }
 
+// ---- forward, schedule + segment-parallel rows ---------------------------------
+// The fire schedule only depends on alphas: one warp per utterance runs the exact recurrence
+// once (cur / rem / sched / fire_t / n_fired: what backward needs anyway).  With the fire
+// positions known, output row l is an ordered weighted sum over the frames of one segment,
+//     out[l] = rem[t0] h[t0] + sum_{t0 < t <= t1} cur[t] h[t],   t0 = fire_t[l-1], t1 = fire_t[l]
+// (row 0: 0 + sum_{t <= t1}), so rows are independent: one warp per (row, column slice), every
+// warp streams ~T/L frames with 8 loads in flight.  Same operations in the same order as the
+// frame-by-frame loop, hence the same bits; the boundary frame of each segment is read twice
+// (+L/T of the traffic), and the grid no longer depends on B*H/width filling the machine.
+__global__ void __launch_bounds__(128) cif_schedule_kernel(const CifFwdArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= a.B) return;
+    const float* arow = a.alphas + (size_t)b * a.T;
+    float integ = 0.0f, asum = 0.0f;
+    int k = 0;
+    for (int t0 = 0; t0 < a.T; t0 += 32) {
+        const int tt = t0 + lane;
+        const float my_alpha = (tt < a.T) ? __ldg(arow + tt) : 0.0f;
+        const int nrow = min(32, a.T - t0);
+        float my_cur, my_rem;
+        unsigned fire_mask;
+        if (nrow == 32)
+            cif_chain_chunk<true>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        else
+            cif_chain_chunk<false>(my_alpha, nrow, a.thr, lane, integ, asum, my_cur, my_rem, fire_mask);
+        cif_record_chunk(a, b, tt, lane, k, my_cur, my_rem, fire_mask);
+        k += __popc(fire_mask);
+    }
+    for (int kk = k + lane; kk < a.L; kk += 32) a.fire_t[(size_t)b * a.L + kk] = -1;
+    if (lane == 0) {
+        a.n_fired[b] = k;
+        a.alpha_sum[b] = asum;
+        if (a.target_num != nullptr && a.qua_term != nullptr) {
+            const float d = __fsub_rn(asum, a.target_num[b]);
+            a.qua_term[b] = __fmul_rn(d, d);
+        }
+    }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(128) cif_rows_kernel(const CifFwdArgs a, int nslices) {
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= (long long)a.B * a.L * nslices) return;
+    const int slice = (int)(w % nslices);
+    const long long bl = w / nslices;
+    const int l = (int)(bl % a.L);
+    const int b = (int)(bl / a.L);
+    const int col = slice * (32 * VEC) + lane * VEC;
+    if (col >= a.H) return;
+    float* orow = a.out + ((size_t)b * a.L + l) * a.H + col;
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.0f;
+    if (l >= __ldg(a.n_fired + b)) {     // beyond the last fire: zero row
+        vstore<VEC>(orow, acc);
+        return;
+    }
+    const int t1 = __ldg(a.fire_t + (size_t)b * a.L + l);
+    const int t0 = (l > 0) ? __ldg(a.fire_t + (size_t)b * a.L + l - 1) : -1;
+    const float* hrow = a.hidden + (size_t)b * a.T * a.H + col;
+    const float* crow = a.cur + (size_t)b * a.T;
+    if (l > 0) {                         // the fire frame of the previous row opens this one: frame = rem * h   (:87)
+        float h[VEC];
+        vload_nc<VEC>(h, hrow + (size_t)t0 * a.H);
+        const float rm = a.rem[(size_t)b * a.T + t0];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = __fmul_rn(rm, h[i]);
+    }
+    constexpr int U = 8;
+    for (int t = t0 + 1; t <= t1; t += U) {
+        float h[U][VEC];
+        float c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int tu = min(t + u, t1);   // clamped loads (valid addresses), unused beyond t1
+            vload_nc<VEC>(h[u], hrow + (size_t)tu * a.H);
+            c[u] = crow[tu];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (t + u <= t1) {               // warp-uniform
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(c[u], h[u][i]));   // frame += cur * h   (:83)
+            }
+        }
+    }
+    vstore<VEC>(orow, acc);
+}
+
 // ---- forward, TMA pipeline ----------------------------------------------------
 // One warp per CTA.  Tile = 32 rows x (32*VEC) floats; NSTAGE tiles in flight.
 constexpr int kCifRows = 32;
@@ -669,11 +760,23 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
 
     const bool vec4_ok = (H % 4 == 0) && aligned16(hidden) && (L == 0 || aligned16(out));
     int variant = get_opt("cif_fwd_variant");
-    if (variant == 0) variant = (vec4_ok && T >= 64) ? 3 : 1;   // measured on B200: 3 > 2 > 1 for long T
-    if (variant >= 2 && !vec4_ok) variant = 1;
+    bool auto_v2 = false;
+    if (variant == 0) {
+        // measured on B200 (tools/gpu_probe.py cif): with enough (utterance, 128-column) slices to keep
+        // 4 one-warp CTAs per SM busy for several waves, the one-warp TMA pipeline (variant 2, width 128,
+        // 3 stages = 48 KB) streams at 5.4 TB/s (B=256, T=1600, H=512: 164 us vs 198 us); below that the
+        // warp-specialised kernel (variant 3) wins (B=64, T=3000: 105-111 us vs 124-137 us; B=128: 88 us).
+        variant = (vec4_ok && T >= 64) ? 3 : 1;
+        if (variant == 3 && (long long)B * ((H + 127) / 128) >= 6ll * num_sms()) {
+            variant = 2;
+            auto_v2 = true;
+        }
+    }
+    if ((variant == 2 || variant == 3) && !vec4_ok) variant = 1;
 
     // slice width: widest that still yields >= 2 warps per SM
     int width = get_opt("cif_fwd_width");
+    if (auto_v2) width = 128;
     if (width != 32 && width != 64 && width != 128) {
         const int want = 2 * num_sms();
         width = 128;
@@ -685,6 +788,26 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
         if (width == 64 && (long long)B * ((H + 63) / 64) < 2 * num_sms()) width = 32;
     }
     const int nslices = (H + width - 1) / width;
+
+    if (variant == 4) {
+        cif_schedule_kernel<<<(B + 3) / 4, 128, 0, st>>>(a);
+        ASR_LAUNCH_CHECK();
+        if (L > 0) {
+            const int rw = vec4_ok ? 128 : width;          // float4 lanes whenever the rows allow it
+            const int rs = (H + rw - 1) / rw;
+            const long long nw = (long long)B * L * rs;
+            const unsigned blocks = (unsigned)((nw + 3) / 4);
+            if (rw == 128) {
+                cif_rows_kernel<4><<<blocks, 128, 0, st>>>(a, rs);
+            } else if (rw == 64) {
+                cif_rows_kernel<2><<<blocks, 128, 0, st>>>(a, rs);
+            } else {
+                cif_rows_kernel<1><<<blocks, 128, 0, st>>>(a, rs);
+            }
+            ASR_LAUNCH_CHECK();
+        }
+        return 0;
+    }
 
     if (variant == 3) {
         // warp-specialised: CTA columns = nw * width, at most 256 (TMA box limit)
@@ -728,7 +851,7 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
                          (uint64_t)H * 4, kCifRows, (uint32_t)width, CU_TENSOR_MAP_SWIZZLE_NONE) != 0)
             return 4;
         int nstage = get_opt("cif_fwd_stages");
-        if (nstage <= 0) nstage = 6;
+        if (nstage <= 0) nstage = auto_v2 ? 3 : 6;
         if (nstage > kCifMaxStages) nstage = kCifMaxStages;
         const size_t smem = (size_t)nstage * kCifRows * width * 4;
         dim3 grid(nslices, B);

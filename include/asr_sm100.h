@@ -42,7 +42,8 @@ const char* asr_last_error(void);
 int         asr_device_ok(void);
 /* Tuning knobs (kernel variants; all variants are sm_100a CUDA).  Unknown keys
  * return non-zero.  Keys: "cif_fwd_variant" (0 = auto, 1 = plain loads,
- * 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline), "cif_fwd_width"
+ * 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline, 4 = schedule kernel +
+ * segment-parallel rows), "cif_fwd_width"
  * (0 = auto, 32/64/128 floats per warp), "cif_fwd_stages" (0 = auto),
  * "cif_fwd_rows" (variant 3: data warps per CTA, 0 = auto), "ctc_fuse_apply"
  * (0 = separate K3 pass applies the sparse gradient update (default, faster),

@@ -11,8 +11,9 @@ pytestmark = pytest.mark.gpu
 
 CIF = load_golden("cif")
 CASES = sorted({k.split("_")[0] for k in CIF.files})
-# (variant, width): 1 = plain loads, 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline
-VARIANTS = [(1, 32), (1, 64), (1, 128), (2, 32), (2, 64), (2, 128), (3, 32), (3, 64), (3, 128), (0, 0)]
+# (variant, width): 1 = plain loads, 2 = one-warp TMA pipeline, 3 = warp-specialised TMA pipeline,
+# 4 = schedule kernel + segment-parallel rows
+VARIANTS = [(1, 32), (1, 64), (1, 128), (2, 32), (2, 64), (2, 128), (3, 32), (3, 64), (3, 128), (4, 0), (4, 32), (0, 0)]
 
 
 @pytest.fixture(autouse=True)

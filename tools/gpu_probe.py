@@ -90,8 +90,7 @@ class CifBuffers:
 
 def probe_cif(res, B=64, T=3000, H=512, n=300):
     c = CifBuffers(B, T, H, n)
-    combos = [(2, 0, 0, 0), (3, 32, 4, 4)] if ONCE else [(2, 64, 3, 0), (3, 32, 4, 4), (3, 32, 2, 4), (3, 32, 8, 4), (3, 64, 4, 2), (3, 64, 4, 4), (3, 128, 4, 1), (3, 128, 4, 2), (3, 64, 8, 2), (3, 32, 4, 2), (3, 32, 6, 3),
-                                       (0, 0, 0, 0)]
+    combos = [(2, 0, 0, 0), (3, 32, 4, 4)] if ONCE else [(2, 64, 3, 0), (2, 64, 2, 0), (2, 64, 4, 0), (2, 64, 6, 0), (2, 128, 2, 0), (2, 128, 3, 0), (2, 32, 4, 0), (2, 32, 6, 0), (3, 128, 4, 1), (3, 0, 0, 0), (0, 0, 0, 0)]
     for variant, width, stages, nw in combos:
         lib.set_option("cif_fwd_rows", nw)
         lib.set_option("cif_fwd_variant", variant)
@@ -191,6 +190,13 @@ def probe_mha(res):
                 print(res[-1], flush=True)
 
 
+def probe_cif_shapes(res):
+    probe_cif(res)
+    probe_cif(res, B=256, T=1600, H=512, n=80)
+    probe_cif(res, B=128, T=1600, H=512, n=80)
+    probe_cif(res, B=16, T=1000, H=256, n=60)
+
+
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     res = []
@@ -207,7 +213,7 @@ def main():
     if "mha" in sel or not sel:
         probe_mha(res)
     if "cif" in sel or not sel:
-        probe_cif(res)
+        probe_cif_shapes(res)
     if "ctc" in sel or not sel:
         shapes = [(32, 1600, 80), (256, 1600, 80)] if ONCE else \
             [(32, 200, 10), (64, 400, 20), (128, 800, 40), (32, 1600, 80), (256, 1600, 80)]
