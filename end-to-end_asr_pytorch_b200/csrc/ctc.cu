@@ -1132,6 +1132,28 @@ static int ctc_slices(int B, int T) {
     return std::min(std::min(nchunk, kMaxChunks), B);
 }
 
+// Slice c of nchunk: the last slice is a quarter of the others.  Its lattice is the one nothing
+// hides (it starts when the last row kernel ends), so at least the apply pass that has to wait
+// for it is short.
+static void ctc_slice_bounds(int B, int nchunk, int c, int& b0, int& n) {
+    if (nchunk <= 1) {
+        b0 = 0;
+        n = B;
+        return;
+    }
+    int last = B / (4 * (nchunk - 1) + 1);
+    if (get_opt("ctc_even_slices") == 1 || last < 1) last = (B + nchunk - 1) / nchunk;
+    const int rest = B - last;
+    const int per = (rest + nchunk - 2) / (nchunk - 1);
+    if (c < nchunk - 1) {
+        b0 = c * per;
+        n = std::max(0, std::min(per, rest - b0));
+    } else {
+        b0 = rest;
+        n = last;
+    }
+}
+
 extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
                                  size_t ws_bytes, void* stream, int* ticket) {
@@ -1144,11 +1166,10 @@ extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, co
     if (p == nullptr) return 3;
     const int tk = p->next_ticket.fetch_add(1) % kTickets;
     const int nchunk = ctc_slices(B, T);
-    const int per = (B + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
-        const int b0 = c * per;
-        const int n = std::min(per, B - b0);
-        if (n <= 0) break;
+        int b0, n;
+        ctc_slice_bounds(B, nchunk, c, b0, n);
+        if (n <= 0) continue;
         const CtcArgs ac = ctc_slice(a, b0, n);
         rc = ctc_run(ac, 1, st);
         if (rc != 0) return rc;
@@ -1174,11 +1195,10 @@ extern "C" int asr_ctc_finish_f32(const float* logits, const int64_t* targets, c
     CtcPipe* p = ctc_pipe();
     if (p == nullptr) return 3;
     const int nchunk = ctc_slices(B, T);
-    const int per = (B + nchunk - 1) / nchunk;
     for (int c = 0; c < nchunk; ++c) {
-        const int b0 = c * per;
-        const int n = std::min(per, B - b0);
-        if (n <= 0) break;
+        int b0, n;
+        ctc_slice_bounds(B, nchunk, c, b0, n);
+        if (n <= 0) continue;
         ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[ticket][c], 0));
         rc = ctc_run(ctc_slice(a, b0, n), 4, st);
         if (rc != 0) return rc;
