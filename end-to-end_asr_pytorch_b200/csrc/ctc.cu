@@ -1184,9 +1184,14 @@ extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, co
     return 0;
 }
 
-extern "C" int asr_ctc_finish_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
-                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
-                                  size_t ws_bytes, void* stream, int ticket) {
+// per_slice: apply each slice as soon as its lattice is done (right for begin immediately followed by
+// finish: the early slices' apply passes run next to the last lattices).  Otherwise wait for every
+// lattice and apply the whole batch in one launch: when the caller has queued its own HBM-bound work
+// in between, the lattices have had that time, and the apply kernel and a lattice slow each other
+// down 2.5-2.8x when they do run side by side (tools/ctc_k2_contention.py).
+static int ctc_finish_impl(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                           int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                           size_t ws_bytes, void* stream, int ticket, bool per_slice) {
     ASR_REQUIRE(ticket >= 0 && ticket < kTickets, "asr_ctc_finish_f32: bad ticket %d", ticket);
     CtcArgs a;
     int rc = ctc_make_args(a, logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes);
@@ -1200,10 +1205,19 @@ extern "C" int asr_ctc_finish_f32(const float* logits, const int64_t* targets, c
         ctc_slice_bounds(B, nchunk, c, b0, n);
         if (n <= 0) continue;
         ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[ticket][c], 0));
-        rc = ctc_run(ctc_slice(a, b0, n), 4, st);
-        if (rc != 0) return rc;
+        if (per_slice) {
+            rc = ctc_run(ctc_slice(a, b0, n), 4, st);
+            if (rc != 0) return rc;
+        }
     }
-    return 0;
+    return per_slice ? 0 : ctc_run(a, 4, st);
+}
+
+extern "C" int asr_ctc_finish_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                  int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws,
+                                  size_t ws_bytes, void* stream, int ticket) {
+    return ctc_finish_impl(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, ticket,
+                           get_opt("ctc_finish_per_slice") == 1);
 }
 
 extern "C" int asr_ctc_stages_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
@@ -1223,7 +1237,7 @@ extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, 
     int ticket = 0;
     int rc = asr_ctc_begin_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, &ticket);
     if (rc != 0) return rc;
-    return asr_ctc_finish_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, ticket);
+    return ctc_finish_impl(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, ticket, true);
 }
 
 extern "C" int asr_scale_inplace_f32(float* g, size_t n, const float* scale_dev, void* stream) {

@@ -136,7 +136,9 @@ int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
  * same stream, the ticket) waits for the lattices and applies the sparse gradient
  * update.  Whatever the caller queues on `stream` between the two runs next to
  * the last slice's lattice, which is a latency-bound chain that leaves the GPU
- * almost idle - bench.py puts the CIF forward/backward pair there.  nll and
+ * almost idle - bench.py puts the CIF forward/backward pair there.  finish then
+ * applies the whole batch in one launch (option "ctc_finish_per_slice" = 1: slice
+ * by slice as each lattice completes, which is what asr_ctc_fwd_bwd_f32 does).  nll and
  * g_logits are complete (in stream order) after finish.  At most 4 begins may be
  * outstanding per device.  asr_ctc_fwd_bwd_f32 == begin immediately followed by
  * finish. */
