@@ -1142,7 +1142,7 @@ static void ctc_slice_bounds(int B, int nchunk, int c, int& b0, int& n) {
         return;
     }
     int last = B / (4 * (nchunk - 1) + 1);
-    if (get_opt("ctc_even_slices") == 1 || last < 1) last = (B + nchunk - 1) / nchunk;
+    if (last < 1) last = (B + nchunk - 1) / nchunk;
     const int rest = B - last;
     const int per = (rest + nchunk - 2) / (nchunk - 1);
     if (c < nchunk - 1) {

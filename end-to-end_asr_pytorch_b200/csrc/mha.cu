@@ -1236,7 +1236,6 @@ struct MhaBwdArgs {
     float* dq_acc;        // [B,Lq,Hh,64] fp32, zeroed
     __nv_bfloat16* g_k;   // [B,Lk,Hh,64]
     __nv_bfloat16* g_v;
-    int debug;            // timing experiments only: 1 = skip the dQ reduction
     uint32_t drop_thresh; // dropout on the probabilities, same meaning as in MhaFwdArgs
     float inv_keep;
     uint32_t seed_lo, seed_hi;
@@ -1410,7 +1409,6 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // asynchronous, rows beyond Lq clipped by the tensor map) instead of per-thread RED.ADDs
         const bool dq_issuer = (warp == 0 && lane == 0);
         auto flush_dq = [&](const float (&dq)[kColsD], int q_tile) {
-            if (a.debug & 1) return;
             if (dq_issuer) bulk_wait_read0();                 // the previous tile's reduce has read the staging
             bar_sync_named(1, 128 * CG);
             const int col0 = cg * kColsD;                     // first of this thread's dQ columns
@@ -1801,7 +1799,6 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
     a.dq_acc = dq_acc;
     a.g_k = static_cast<__nv_bfloat16*>(g_k);
     a.g_v = static_cast<__nv_bfloat16*>(g_v);
-    a.debug = get_opt("mha_bwd_debug");
     ASR_REQUIRE(p_drop >= 0.0f && p_drop < 1.0f, "asr_mha_bwd_dropout_bf16: p_drop %f outside [0, 1)", (double)p_drop);
     a.drop_thresh = drop_threshold(p_drop);
     a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);

@@ -52,7 +52,9 @@ int         asr_device_ok(void);
  * "ctc_chunks" (asr_ctc_fwd_bwd_f32 / begin / finish slice the batch into this
  * many pieces and run each slice's lattice on a library-owned stream so that it
  * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
- * max 8; results are bit-identical for every value), "mha_variant" (0 = auto = 3,
+ * max 8; results are bit-identical for every value), "ctc_finish_per_slice"
+ * (asr_ctc_finish_f32: 0 = one apply launch after all lattices, 1 = slice by
+ * slice), "mha_variant" (0 = auto = 3,
  * 1 = one tile per CTA with four softmax warps, 2 = two-tile ping-pong, 3 = eight
  * softmax warps per tile, O accumulated in TMEM with lazy rescale, 4 = as 3 with P
  * kept in TMEM as the A operand of P V), "mha_bwd_groups" (softmax-backward

@@ -34,11 +34,6 @@ for B, Ls, H in shapes:
         ms = timed(bwd)
         print("B=%d L=%d H=%d bwd %2d softmax warps: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, 4 * grp, ms, 2.5 * flop / ms / 1e9), flush=True)
     lib.set_option("mha_bwd_groups", 0)
-    for dbg in (1,):
-        lib.set_option("mha_bwd_debug", dbg)
-        ms = timed(bwd)
-        print("B=%d L=%d H=%d bwd debug=%d (1: no dQ reduction, 4: plain try_wait, 8: test_wait polling): %.3f ms" % (B, Ls, H, dbg, ms), flush=True)
-    lib.set_option("mha_bwd_debug", 0)
     def fwd_d(): check(L.asr_mha_fwd_dropout_bf16(ptr(q), ptr(k), ptr(v), None, None, 0, B, H, Ls, Ls, 64, 0.125, 0.1, 77, ptr(out), ptr(lse), sp()), "fwd")
     def bwd_d(): check(L.asr_mha_bwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(do), ptr(lse), None, None, 0, B, H, Ls, Ls, 64, 0.125, 0.1, 77, ptr(gq), ptr(gk), ptr(gv), ptr(ws), wsb, sp()), "bwd")
     ms = timed(fwd_d); print("B=%d L=%d H=%d fwd with dropout 0.1: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, ms, flop / ms / 1e9), flush=True)
