@@ -284,6 +284,51 @@ def e2e_step(pkg, w, host, dev_buf, g_out):
     return losses
 
 
+def assigner_microbench(pkg, w, inp, device, iters=5):
+    """CIF weight producer (assigner tail + scaling) on the bench shape: x = the encoder
+    output of the step [B,T,H], ragged lengths.  HBM-bound: forward reads the valid rows of x once,
+    backward reads them once more and writes g_x once."""
+    lib = pkg._lib
+    L = lib.lib()
+    p, sp = lib.ptr, lib.stream_ptr
+    B, T, D = w["B"], w["T"], w["H"]
+    x = inp["hidden"]
+    g = torch.Generator(device=device).manual_seed(6)
+    wt = torch.randn(D, device=device, generator=g) * 0.05
+    bias = torch.zeros(1, device=device)
+    lens = inp["in_len"]
+    noise = inp["tgt_len"].float() + 0.25
+    alpha, a_raw = torch.empty(B, T, device=device), torch.empty(B, T, device=device)
+    num = torch.empty(B, device=device)
+    g_alpha, g_num = torch.randn(B, T, device=device, generator=g), torch.randn(B, device=device, generator=g)
+    g_x, g_w, g_b = torch.empty_like(x), torch.empty(D, device=device), torch.empty(1, device=device)
+    wsb = L.asr_cif_alpha_bwd_workspace_bytes(B, T, D)
+    ws = torch.empty(wsb // 4 + 1, device=device)
+
+    def fwd():
+        lib.check(L.asr_cif_alpha_fwd_f32(p(x), p(wt), p(bias), p(lens), p(noise), B, T, D, p(alpha), p(a_raw), p(num), sp()), "alpha_fwd")
+
+    def bwd():
+        lib.check(L.asr_cif_alpha_bwd_f32(p(x), p(wt), p(lens), p(noise), p(a_raw), p(num), p(g_alpha), p(g_num), B, T, D,
+                                          p(g_x), p(g_w), p(g_b), p(ws), wsb, sp()), "alpha_bwd")
+    valid = int(lens.sum().item())
+    res = {}
+    for name, fn, nbytes in (("cif_alpha_fwd", fwd, 4 * valid * D + 12 * B * T),
+                             ("cif_alpha_bwd", bwd, 4 * valid * D + 4 * B * T * D + 16 * B * T)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        res[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9}
+    return res
+
+
 def attention_microbench(pkg, device, iters=5):
     """tcgen05 attention core, forward and backward, on the SURVEY 8(d) microbench shape
     (B*heads = 128, L = 2048, d = 64, no mask); CUDA events, inputs >> L2 per call not needed
@@ -614,6 +659,11 @@ def main():
             ent["frac_of_hbm_peak"] = ent["GBps"] / peaks["hbm_gbs"]
         kernels.append(ent)
     if rank == 0:
+        asg = assigner_microbench(pkg, w, inp, device)
+        for n in ("cif_alpha_fwd", "cif_alpha_bwd"):
+            kernels.append({"kernel": n, "bound": "hbm", "ms": asg[n]["ms"], "algorithmic_bytes": asg[n]["algorithmic_bytes"],
+                            "GBps": asg[n]["GBps"], "frac_of_hbm_peak": asg[n]["GBps"] / peaks["hbm_gbs"],
+                            "in_timed_step": False, "note": "SURVEY 8(f2): assigner tail + alpha scaling, next-row kernel"})
         att = attention_microbench(pkg, device)
         for n in ("mha_fwd", "mha_bwd"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": att[n]["ms"], "TFLOPs": att[n]["TFLOPs"],

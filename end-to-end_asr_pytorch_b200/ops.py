@@ -67,6 +67,62 @@ class _CifFunction(torch.autograd.Function):
         return g_hidden, g_alphas, None, None, None
 
 
+class _CifAlphaFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, lens, num_noise):
+        B, T, D = x.shape
+        dev = x.device
+        alpha = torch.empty((B, T), dtype=torch.float32, device=dev)
+        a_raw = torch.empty((B, T), dtype=torch.float32, device=dev)
+        num_raw = torch.empty((B,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_cif_alpha_fwd_f32(ptr(x), ptr(weight), ptr(bias), ptr(lens), ptr(num_noise), B, T, D,
+                                                   ptr(alpha), ptr(a_raw), ptr(num_raw), stream_ptr()),
+                  "asr_cif_alpha_fwd_f32")
+        ctx.save_for_backward(x, weight, lens, num_noise, a_raw, num_raw)
+        ctx.wshape = weight.shape
+        return alpha, num_raw
+
+    @staticmethod
+    def backward(ctx, g_alpha, g_num):
+        x, weight, lens, num_noise, a_raw, num_raw = ctx.saved_tensors
+        B, T, D = x.shape
+        dev = x.device
+        g_alpha = g_alpha.contiguous().float()
+        g_num = g_num.contiguous().float() if g_num is not None else None
+        g_x = torch.empty_like(x)
+        g_w = torch.empty((D,), dtype=torch.float32, device=dev)
+        g_b = torch.empty((1,), dtype=torch.float32, device=dev)
+        ws_bytes = _lib.lib().asr_cif_alpha_bwd_workspace_bytes(B, T, D)
+        ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_cif_alpha_bwd_f32(ptr(x), ptr(weight), ptr(lens), ptr(num_noise), ptr(a_raw), ptr(num_raw),
+                                                   ptr(g_alpha), ptr(g_num), B, T, D, ptr(g_x), ptr(g_w), ptr(g_b),
+                                                   ptr(ws), ws_bytes, stream_ptr()), "asr_cif_alpha_bwd_f32")
+        return g_x, g_w.view(ctx.wshape), g_b, None, None
+
+
+def cif_alpha(x, weight, bias, lens, num_noise=None):
+    """The CIF weight producer: tail of the attention assigner + the scaling of CIF_Model.forward.
+
+    x [B,T,D] f32 (assigner activations), weight [1,D] or [D], bias [1] (the assigner's `linear`),
+    lens [B] valid frames, num_noise [B] (= #labels + U[0,1) - 0.5; None: no scaling)
+    -> (alpha [B,T] scaled weights, _num [B] = sum_t of the unscaled weights).
+    attentionAssigner.py:36-40 and cif_model.py:43-48 in one pass over x."""
+    _require_cuda("x", x, torch.float32)
+    if x.dim() != 3:
+        raise ValueError("cif_alpha: x must be [B, T, D]")
+    x = x.contiguous()
+    weight = weight.contiguous().float()
+    bias = bias.contiguous().float().view(1)
+    lens = lens.to(device=x.device, dtype=torch.int32).contiguous()
+    if num_noise is not None:
+        num_noise = num_noise.to(device=x.device, dtype=torch.float32).contiguous()
+    if weight.numel() != x.shape[-1]:
+        raise ValueError("cif_alpha: weight must have D elements")
+    return _CifAlphaFunction.apply(x, weight, bias, lens, num_noise)
+
+
 def cif_label_len(alphas):
     """L of cif_model.py:95-96: max_b int(round(sum_t alphas)) - one host sync, like the reference."""
     return int(torch.round(alphas.sum(-1)).int().max().item())

@@ -36,11 +36,15 @@ def _sibling(name):
 class CIF_Model(nn.Module):
     """Conv front-end -> Transformer encoder -> (ctc_fc | assigner -> CIF -> decoder)."""
 
-    def __init__(self, conv_encoder, encoder, assigner, decoder, spec_aug_cfg=None):
+    def __init__(self, conv_encoder, encoder, assigner, decoder, spec_aug_cfg=None, fused_alpha=False):
         super().__init__()
         self.conv_encoder = conv_encoder
         self.encoder = encoder
         self.assigner = assigner
+        # True: the assigner tail and the scaling below run as one kernel pass (ops.cif_alpha).  Same
+        # math, different fp32 summation order than torch's Linear/sum, so a weight that lands within
+        # one ulp of the threshold may fire a frame earlier or later than in the reference.
+        self.fused_alpha = fused_alpha
         self.decoder = decoder
         self.spec_aug_cfg = spec_aug_cfg
         self.ctc_fc = nn.Linear(encoder.d_output, decoder.d_output, bias=False)
@@ -62,14 +66,16 @@ class CIF_Model(nn.Module):
         ctc_logits = self.ctc_fc(encoder_outputs)
         len_ctc_logits = len_sequence
 
-        alpha = self.assigner(encoder_outputs, len_sequence)
-
         # quantity (before scaling) and target-length scaling, reference :43-48
-        _num = alpha.sum(-1)
         num = (targets > 0).float().sum(-1)
-        noise = torch.rand(alpha.size(0)).to(alpha.device)
+        noise = torch.rand(targets.size(0)).to(num.device)
         num_noise = num + noise - 0.5
-        alpha = alpha * (num_noise / _num)[:, None]
+        if self.fused_alpha and hasattr(self.assigner, "forward_scaled"):
+            alpha, _num = self.assigner.forward_scaled(encoder_outputs, len_sequence, num_noise)
+        else:
+            alpha = self.assigner(encoder_outputs, len_sequence)
+            _num = alpha.sum(-1)
+            alpha = alpha * (num_noise / _num)[:, None]
 
         fired = self.cif(encoder_outputs, alpha, threshold=threshold)
 

@@ -106,6 +106,37 @@ int asr_cif_bwd_f32(const float* hidden, const float* g_out,
                     float* g_hidden, float* g_alphas,
                     void* ws, size_t ws_bytes, void* stream);
 
+/* ---- CIF weight producer --------------------------------- */
+/*
+ * Replaces the tail of Attention_Assigner.forward,
+ * /root/reference/src/transformer/attentionAssigner.py:36-40
+ *     alphas = sigmoid(linear(x).squeeze(-1)) * sequence_mask(input_lengths)
+ * and the scaling glue of CIF_Model.forward, src/transformer/cif_model.py:43-48
+ *     _num = alpha.sum(-1);  alpha *= (num_noise / _num)[:, None]
+ * in one pass over x (padded frames are not read).
+ *
+ *   x [B,T,D] f32  assigner activations after its dropout; w [D], bias [1]: `linear`
+ *   len [B] i32    valid frames; num_noise [B] f32 = #labels + U[0,1) - 0.5, drawn
+ *                  by the caller (cif_model.py:46-47), or NULL: no scaling (decoding)
+ * outputs
+ *   alpha   [B,T]  the weights cif() consumes (0 at padded frames)
+ *   a_raw   [B,T]  unscaled weights, saved for backward
+ *   num_raw [B]    _num = sum_t a_raw, the quantity-loss input (loss.py:55)
+ * backward: g_alpha [B,T], g_num [B] or NULL (gradient of the quantity loss w.r.t.
+ * _num) -> g_x [B,T,D], g_w [D], g_bias [1].  All reductions have a fixed order.
+ */
+int asr_cif_alpha_fwd_f32(const float* x, const float* w, const float* bias,
+                          const int* len, const float* num_noise,
+                          int B, int T, int D,
+                          float* alpha, float* a_raw, float* num_raw, void* stream);
+size_t asr_cif_alpha_bwd_workspace_bytes(int B, int T, int D);
+int asr_cif_alpha_bwd_f32(const float* x, const float* w, const int* len,
+                          const float* num_noise, const float* a_raw, const float* num_raw,
+                          const float* g_alpha, const float* g_num,
+                          int B, int T, int D,
+                          float* g_x, float* g_w, float* g_bias,
+                          void* ws, size_t ws_bytes, void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at

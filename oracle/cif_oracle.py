@@ -44,6 +44,42 @@ def cif_scale_with_num(alpha, _num, num, rand):
     return (np.asarray(alpha, dtype=_F32) * (num_noise / _num)[:, None]).astype(_F32)
 
 
+def assigner_tail_forward(x, w, b, lens, num_noise=None, dtype=np.float64):
+    """attentionAssigner.py:36-40 + cif_model.py:43-48.
+    x [B,T,D], w [D] (or [1,D]), b scalar, lens [B]; num_noise [B] or None (no scaling).
+    Returns (alpha_raw [B,T], _num [B], alpha [B,T])."""
+    x = np.asarray(x).astype(dtype)
+    w = np.asarray(w).astype(dtype).reshape(-1)
+    z = x @ w + dtype(np.asarray(b).reshape(-1)[0])                      # linear(x).squeeze(-1)      :37
+    s = 1.0 / (1.0 + np.exp(-z))                                         # sigmoid                    :38
+    mask = (np.arange(x.shape[1])[None, :] < np.asarray(lens)[:, None])  # sequence_mask              :39
+    a_raw = s * mask                                                     #                            :41
+    num = a_raw.sum(-1)                                                  # _num                       cif_model.py:44
+    if num_noise is None:
+        return a_raw, num, a_raw
+    r = np.asarray(num_noise).astype(dtype) / num
+    return a_raw, num, a_raw * r[:, None]                                #                            :48
+
+
+def assigner_tail_backward(x, w, b, lens, num_noise, g_alpha, g_num=None, dtype=np.float64):
+    """Gradients of (sum(alpha * g_alpha) + sum(_num * g_num)) w.r.t. x, w, b (analytic)."""
+    x = np.asarray(x).astype(dtype)
+    w1 = np.asarray(w).astype(dtype).reshape(-1)
+    a_raw, num, _ = assigner_tail_forward(x, w1, b, lens, num_noise, dtype)
+    g_alpha = np.asarray(g_alpha).astype(dtype)
+    mask = (np.arange(x.shape[1])[None, :] < np.asarray(lens)[:, None])
+    c = np.zeros(x.shape[0], dtype) if g_num is None else np.asarray(g_num).astype(dtype).copy()
+    r = np.ones(x.shape[0], dtype)
+    if num_noise is not None:
+        r = np.asarray(num_noise).astype(dtype) / num
+        c = c - (r / num) * (g_alpha * a_raw).sum(-1)
+    d_a = g_alpha * r[:, None] + c[:, None]
+    dz = d_a * mask * a_raw * (1.0 - a_raw)
+    g_x = dz[:, :, None] * w1[None, None, :]
+    g_w = np.einsum("bt,btd->d", dz, x)
+    return g_x, g_w, dz.sum()
+
+
 def cif_schedule(alphas, threshold):
     """Scalar recurrence only.  Returns dict of [B,T] arrays: fire (bool),
     cur, rem (float32), seg (int32, number of fires strictly before t) and

@@ -157,6 +157,40 @@ def make_cif_glue():
     print("cif glue: done")
 
 
+def make_assigner_tail(uutils):
+    """attentionAssigner.py:36-40 (linear -> sigmoid -> sequence_mask, the reference's own mask builder)
+    followed by cif_model.py:43-48, with autograd gradients for a fixed upstream gradient."""
+    g = torch.Generator().manual_seed(78)
+    B, T, D = 4, 23, 36
+    x = torch.randn(B, T, D, generator=g, requires_grad=True)
+    lin = torch.nn.Linear(D, 1)
+    with torch.no_grad():
+        lin.weight.copy_(torch.randn(1, D, generator=g) * 0.3)
+        lin.bias.copy_(torch.randn(1, generator=g) * 0.1)
+    lens = torch.tensor([23, 17, 9, 1])
+    targets = torch.randint(1, 40, (B, 7), generator=g)
+    targets[1, 5:] = 0
+    targets[3, 1:] = 0
+    rnd = torch.rand(B, generator=g)
+    alphas = lin(x).squeeze(-1)                                   # attentionAssigner.py:37
+    alphas = torch.sigmoid(alphas)                                # :38
+    pad_mask = uutils.sequence_mask(lens)                         # :39
+    alpha = alphas * pad_mask                                     # :41
+    _num = alpha.sum(-1)                                          # cif_model.py:44
+    num = (targets > 0).float().sum(-1)                           # :46
+    num_noise = num + rnd - 0.5                                   # :47
+    scaled = alpha * (num_noise / _num)[:, None].repeat(1, alpha.size(1))   # :48 (out of place for autograd)
+    g_alpha = torch.randn(B, T, generator=g)
+    g_num = torch.randn(B, generator=g)
+    ((scaled * g_alpha).sum() + (_num * g_num).sum()).backward()
+    np.savez_compressed(os.path.join(HERE, "assigner_tail.npz"),
+                        x=x.detach().numpy(), w=lin.weight.detach().numpy(), b=lin.bias.detach().numpy(),
+                        lens=lens.numpy(), num_noise=num_noise.detach().numpy(), alpha_raw=alpha.detach().numpy(),
+                        _num=_num.detach().numpy(), scaled=scaled.detach().numpy(), g_alpha=g_alpha.numpy(),
+                        g_num=g_num.numpy(), g_x=x.grad.numpy(), g_w=lin.weight.grad.numpy(), g_b=lin.bias.grad.numpy())
+    print("assigner tail: done")
+
+
 def make_ctc(tloss, closs):
     out = {}
     g = torch.Generator().manual_seed(4233)
@@ -344,6 +378,7 @@ def main():
     torch.set_num_threads(1)
     make_cif(cif_model)
     make_cif_glue()
+    make_assigner_tail(uutils)
     make_ctc(tloss, closs)
     make_qua(tloss)
     make_mha(attention, uutils)

@@ -62,6 +62,25 @@ def test_cif_glue():
     np.testing.assert_array_equal(scaled2.view(np.uint32), g["scaled"].view(np.uint32))
 
 
+def test_assigner_tail_matches_reference():
+    """attentionAssigner.py:36-40 + cif_model.py:43-48, values and autograd gradients
+    produced by the reference's own ops (tests/golden/make_golden.py: make_assigner_tail)."""
+    g = load_golden("assigner_tail")
+    a_raw, num, alpha = oracle.assigner_tail_forward(g["x"], g["w"], g["b"], g["lens"], g["num_noise"])
+    np.testing.assert_allclose(a_raw, g["alpha_raw"], rtol=2e-6, atol=1e-7)
+    np.testing.assert_allclose(num, g["_num"], rtol=2e-6)
+    np.testing.assert_allclose(alpha, g["scaled"], rtol=3e-6, atol=1e-7)
+    assert not a_raw[1, 17:].any() and not a_raw[3, 1:].any()          # zero at padded frames
+    g_x, g_w, g_b = oracle.assigner_tail_backward(g["x"], g["w"], g["b"], g["lens"], g["num_noise"], g["g_alpha"], g["g_num"])
+    sx, sw = np.abs(g["g_x"]).max(), np.abs(g["g_w"]).max()
+    assert np.abs(g_x - g["g_x"]).max() <= 1e-5 * sx
+    assert np.abs(g_w - g["g_w"].reshape(-1)).max() <= 1e-5 * sw
+    np.testing.assert_allclose(g_b, g["g_b"][0], rtol=1e-4)
+    # without scaling (decoding path): alpha is the masked sigmoid itself
+    a2, n2, al2 = oracle.assigner_tail_forward(g["x"], g["w"], g["b"], g["lens"], None)
+    np.testing.assert_array_equal(a2, al2)
+
+
 @pytest.mark.parametrize("case", CTC_CASES)
 def test_ctc_matches_reference(case):
     logits, targets, in_len = CTC[case + "_logits"], CTC[case + "_targets"], CTC[case + "_in_len"]
