@@ -311,3 +311,66 @@ extern "C" int asr_cif_alpha_bwd_f32(const float* x, const float* w, const int* 
     ASR_LAUNCH_CHECK();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------
+// Input side of the path: low-frame-rate stacking of a padded batch.
+// Reference: build_LFR_features, /root/reference/src/utils/data.py:191-218 (numpy, one
+// utterance at a time in the data loader): output frame i is the concatenation of input
+// frames i*n .. i*n+m-1, the last ones repeated beyond the end of the utterance.
+//   out[b, i, j*D + d] = in[b, min(i*n + j, len_b - 1), d]   for i < ceil(len_b / n), else 0
+// Pure copy: bit-exact.  One warp per output frame, 16-byte lanes when the rows allow it.
+// ---------------------------------------------------------------------------------
+namespace asr {
+
+__global__ void __launch_bounds__(256) lfr_kernel(const float* in, const int* len, int B, int T, int D, int m, int n,
+                                                  int To, float* out, int* out_len, int vec4) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)B * To) return;
+    const int b = (int)(row / To);
+    const int i = (int)(row - (long long)b * To);
+    const int lb = min(max(__ldg(len + b), 0), T);
+    const int lo = (lb + n - 1) / n;
+    if (i == 0 && lane == 0) out_len[b] = lo;
+    float* orow = out + (size_t)row * m * D;
+    const float* ib = in + (size_t)b * T * D;
+    if (vec4) {
+        const int dv = D / 4;
+        float4* ov = reinterpret_cast<float4*>(orow);
+        for (int c = lane; c < m * dv; c += 32) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < lo) {
+                const int j = c / dv;
+                const int t = min(i * n + j, lb - 1);
+                v = __ldg(reinterpret_cast<const float4*>(ib + (size_t)t * D) + (c - j * dv));
+            }
+            ov[c] = v;
+        }
+    } else {
+        for (int c = lane; c < m * D; c += 32) {
+            float v = 0.0f;
+            if (i < lo) {
+                const int j = c / D;
+                const int t = min(i * n + j, lb - 1);
+                v = __ldg(ib + (size_t)t * D + (c - j * D));
+            }
+            orow[c] = v;
+        }
+    }
+}
+
+}  // namespace asr
+
+extern "C" int asr_lfr_f32(const float* in, const int* len, int B, int T, int D, int m, int n, float* out, int* out_len,
+                           void* stream) {
+    ASR_REQUIRE(in && len && out && out_len, "asr_lfr_f32: null pointer");
+    ASR_REQUIRE(B > 0 && T > 0 && D > 0 && m > 0 && n > 0, "asr_lfr_f32: bad arguments B=%d T=%d D=%d m=%d n=%d", B, T, D, m, n);
+    if (asr_device_ok() != 0) return 3;
+    const int To = (T + n - 1) / n;
+    const int vec4 = (D % 4 == 0) && aligned16(in) && aligned16(out);
+    const long long rows = (long long)B * To;
+    lfr_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(in, len, B, T, D, m, n, To, out,
+                                                                                         out_len, vec4);
+    ASR_LAUNCH_CHECK();
+    return 0;
+}

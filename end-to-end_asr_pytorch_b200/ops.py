@@ -123,6 +123,26 @@ def cif_alpha(x, weight, bias, lens, num_noise=None):
     return _CifAlphaFunction.apply(x, weight, bias, lens, num_noise)
 
 
+def build_lfr_features(features, lens, m, n):
+    """Low-frame-rate stacking of a padded batch on the device (utils/data.py:191-218 applied to every
+    utterance): features [B,T,D] f32, lens [B] -> (out [B, ceil(T/n), m*D], out_lens [B] = ceil(lens/n)).
+    Frame i of utterance b is frames i*n .. i*n+m-1 side by side, the last frame repeated past the end;
+    rows beyond out_lens[b] are zero.  A pure copy, no gradient."""
+    _require_cuda("features", features, torch.float32)
+    if features.dim() != 3:
+        raise ValueError("build_lfr_features: features must be [B, T, D]")
+    features = features.detach().contiguous()
+    B, T, D = features.shape
+    lens = lens.to(device=features.device, dtype=torch.int32).contiguous()
+    To = (T + n - 1) // n
+    out = torch.empty((B, To, m * D), dtype=torch.float32, device=features.device)
+    out_lens = torch.empty((B,), dtype=torch.int32, device=features.device)
+    with torch.cuda.device(features.device):
+        check(_lib.lib().asr_lfr_f32(ptr(features), ptr(lens), B, T, D, int(m), int(n), ptr(out), ptr(out_lens),
+                                     stream_ptr()), "asr_lfr_f32")
+    return out, out_lens
+
+
 def cif_label_len(alphas):
     """L of cif_model.py:95-96: max_b int(round(sum_t alphas)) - one host sync, like the reference."""
     return int(torch.round(alphas.sum(-1)).int().max().item())

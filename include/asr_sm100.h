@@ -137,6 +137,17 @@ int asr_cif_alpha_bwd_f32(const float* x, const float* w, const int* len,
                           float* g_x, float* g_w, float* g_bias,
                           void* ws, size_t ws_bytes, void* stream);
 
+/* ---- input side: low-frame-rate stacking ----------------- */
+/*
+ * Replaces build_LFR_features, /root/reference/src/utils/data.py:191-218 (numpy, per
+ * utterance in the data loader) for a padded batch already on the device:
+ *   out[b, i, j*D + d] = in[b, min(i*n + j, len[b]-1), d]   i < ceil(len[b]/n), else 0
+ *   in [B,T,D] f32, len [B] i32 -> out [B, ceil(T/n), m*D] f32, out_len [B] = ceil(len/n).
+ * A pure copy: bit-exact with the reference.
+ */
+int asr_lfr_f32(const float* in, const int* len, int B, int T, int D, int m, int n,
+                float* out, int* out_len, void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at

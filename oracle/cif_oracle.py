@@ -44,6 +44,15 @@ def cif_scale_with_num(alpha, _num, num, rand):
     return (np.asarray(alpha, dtype=_F32) * (num_noise / _num)[:, None]).astype(_F32)
 
 
+def build_lfr_features(inputs, m, n):
+    """utils/data.py:191-218 for one utterance [T,D]: frame i = frames i*n .. i*n+m-1 side by side,
+    the last frame repeated past the end.  Returns [ceil(T/n), m*D]."""
+    inputs = np.asarray(inputs)
+    T = inputs.shape[0]
+    idx = np.minimum(np.arange((T + n - 1) // n)[:, None] * n + np.arange(m)[None, :], T - 1)
+    return inputs[idx].reshape(idx.shape[0], -1)
+
+
 def assigner_tail_forward(x, w, b, lens, num_noise=None, dtype=np.float64):
     """attentionAssigner.py:36-40 + cif_model.py:43-48.
     x [B,T,D], w [D] (or [1,D]), b scalar, lens [B]; num_noise [B] or None (no scaling).

@@ -191,6 +191,26 @@ def make_assigner_tail(uutils):
     print("assigner tail: done")
 
 
+def make_lfr():
+    """utils/data.py:191-218 executed on a few utterances (the function is pure numpy)."""
+    import importlib
+    import types
+    # utils/data.py imports kaldi_io (not installed here) for its ark readers; the function under
+    # test is pure numpy, so an empty stand-in module is enough to execute the reference file
+    sys.modules.setdefault("kaldi_io", types.ModuleType("kaldi_io"))
+    udata = importlib.import_module("utils.data")
+    rng = np.random.default_rng(79)
+    out = {}
+    for name, (T, D, m, n) in {"a": (17, 8, 4, 3), "b": (16, 5, 4, 3), "c": (3, 8, 4, 3), "d": (9, 4, 1, 1),
+                               "e": (10, 6, 1, 2), "f": (7, 3, 3, 1), "g": (1, 4, 4, 3)}.items():
+        x = rng.normal(size=(T, D)).astype(np.float32)
+        out[name + "_x"] = x
+        out[name + "_mn"] = np.array([m, n])
+        out[name + "_y"] = udata.build_LFR_features(x, m, n).astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "lfr.npz"), **out)
+    print("lfr: done")
+
+
 def make_ctc(tloss, closs):
     out = {}
     g = torch.Generator().manual_seed(4233)
@@ -379,6 +399,7 @@ def main():
     make_cif(cif_model)
     make_cif_glue()
     make_assigner_tail(uutils)
+    make_lfr()
     make_ctc(tloss, closs)
     make_qua(tloss)
     make_mha(attention, uutils)

@@ -126,3 +126,32 @@ def test_cif_model_with_fused_alpha_trains():
     np.testing.assert_allclose(res[1][2], res[0][2], rtol=1e-5)
     assert res[1][4] == res[0][4]
     assert np.isfinite(res[1][5]).all() and np.abs(res[1][5]).sum() > 0
+
+
+# ---- low-frame-rate stacking ------------------------------------------------------
+def test_lfr_golden_bit_exact():
+    ops = pkg("ops")
+    g = load_golden("lfr")
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        m, n = (int(v) for v in g[name + "_mn"])
+        x = torch.as_tensor(g[name + "_x"]).cuda()[None]
+        y, yl = ops.build_lfr_features(x, torch.tensor([x.size(1)]), m, n)
+        ref = g[name + "_y"]
+        assert int(yl[0]) == ref.shape[0] and tuple(y.shape[1:]) == ref.shape
+        np.testing.assert_array_equal(to_np(y[0]).view(np.uint32), ref.view(np.uint32))
+
+
+@pytest.mark.parametrize("B,T,D,m,n", [(5, 167, 80, 4, 3), (3, 50, 83, 4, 3), (2, 31, 40, 1, 1), (4, 64, 8, 3, 2)])
+def test_lfr_ragged_batch_vs_oracle(B, T, D, m, n):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(T + D)
+    x = torch.randn(B, T, D, generator=gen)
+    lens = torch.randint(1, T + 1, (B,), generator=gen)
+    lens[0] = T
+    y, yl = ops.build_lfr_features(x.cuda(), lens, m, n)
+    assert y.shape == (B, (T + n - 1) // n, m * D)
+    for b in range(B):
+        ref = oracle.build_lfr_features(x[b, :int(lens[b])].numpy(), m, n)
+        assert int(yl[b]) == ref.shape[0]
+        np.testing.assert_array_equal(to_np(y[b, :ref.shape[0]]).view(np.uint32), ref.view(np.uint32))
+        assert not to_np(y[b, ref.shape[0]:]).any()          # zero beyond the utterance

@@ -62,6 +62,16 @@ def test_cif_glue():
     np.testing.assert_array_equal(scaled2.view(np.uint32), g["scaled"].view(np.uint32))
 
 
+def test_lfr_matches_reference():
+    """utils/data.py:191-218 executed on small utterances (make_golden.py: make_lfr)."""
+    g = load_golden("lfr")
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        m, n = (int(v) for v in g[name + "_mn"])
+        y = oracle.build_lfr_features(g[name + "_x"], m, n)
+        assert y.shape == g[name + "_y"].shape
+        np.testing.assert_array_equal(y.view(np.uint32), g[name + "_y"].view(np.uint32))
+
+
 def test_assigner_tail_matches_reference():
     """attentionAssigner.py:36-40 + cif_model.py:43-48, values and autograd gradients
     produced by the reference's own ops (tests/golden/make_golden.py: make_assigner_tail)."""
