@@ -271,3 +271,30 @@ def test_begin_finish_with_work_in_between_is_bit_identical():
             assert torch.equal(d["g_one"], d["g_two"])
     finally:
         lib.set_option("ctc_chunks", 0)
+
+
+@pytest.mark.parametrize("B,T,V,S", [(2, 600, 300, 255), (3, 3000, 64, 30), (2, 700, 40, 150), (1, 1, 5, 1), (4, 37, 9, 0)])
+def test_extreme_shapes_vs_torch_on_device(B, T, V, S):
+    """Maximum label count (511 lattice states: one-warp fallback), very long inputs (global checkpoints),
+    12 states per lane, a single frame, and empty targets, against torch's own fp32 path and the fp64 oracle."""
+    if S == 0:
+        logits = torch.randn(B, T, V, generator=torch.Generator().manual_seed(1)).cuda()
+        targets = torch.zeros(B, 1, dtype=torch.int64).cuda()
+        in_len = torch.tensor([T, T - 3, 1, 20][:B], dtype=torch.int32).cuda()
+    else:
+        logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=7 + T)
+    loss, nll, grad = _ours(logits, targets, in_len)
+    o_loss, o_nll, o_grad = oracle.ctc_loss_and_grad(to_np(logits), to_np(targets), to_np(in_len))
+    r_loss, r_nll, r_grad = _torch_ref(logits, targets, in_len)
+    fin = np.isfinite(o_nll)
+    np.testing.assert_array_equal(np.isfinite(to_np(nll)), fin)
+    err_ours = np.abs(to_np(nll)[fin] - o_nll[fin]) / np.maximum(np.abs(o_nll[fin]), 1.0)
+    err_ref = np.abs(to_np(r_nll)[fin] - o_nll[fin]) / np.maximum(np.abs(o_nll[fin]), 1.0)
+    assert (err_ours <= np.maximum(1e-5, 2 * err_ref)).all(), (err_ours, err_ref)
+    if fin.any():
+        gs = np.nanmax(np.abs(o_grad[fin]))
+        ge_ours = np.abs(to_np(grad)[fin] - o_grad[fin]).max() / gs
+        ge_ref = np.abs(to_np(r_grad)[fin] - o_grad[fin]).max() / gs
+        assert ge_ours <= max(1e-5, 3 * ge_ref), (ge_ours, ge_ref)
+    for b in range(B):
+        assert not to_np(grad)[b, int(in_len[b]):].any()
