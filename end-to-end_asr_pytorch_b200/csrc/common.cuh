@@ -99,6 +99,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One arrival per warp: every lane's earlier writes are ordered before lane 0's arrive by the warp
+// barrier.  512 per-thread arrivals on one mbarrier are 512 serialised shared-memory atomics.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
+
 // Wait flavours for latency experiments: 0 = suspend-hinted try_wait (mbar_wait), 1 = plain try_wait
 // (short hardware time limit), 2 = non-blocking test_wait polling.
 __device__ __forceinline__ void mbar_wait_mode(uint64_t* bar, uint32_t parity, int mode) {

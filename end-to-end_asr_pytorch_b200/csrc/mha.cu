@@ -25,6 +25,7 @@
 
 namespace asr {
 
+
 constexpr int kD = 64;          // head dim (d_k = d_v = 64 in every reference recipe)
 constexpr int kBM = 128;        // query rows per CTA
 constexpr int kBN = 128;        // keys per block
@@ -330,9 +331,9 @@ __device__ __forceinline__ void fwd_softmax_tile(const MhaFwdArgs& a, const FwdT
                 }
             }
             tc_fence_before();
-            mbar_arrive(t.s_free);       // S may be overwritten by the next Q K^T
+            mbar_arrive_warp(t.s_free);       // S may be overwritten by the next Q K^T
             fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
-            mbar_arrive(t.p_full);
+            mbar_arrive_warp(t.p_full);
 
             m_run = m_new;
 
@@ -406,8 +407,8 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_init(&bars->kv_empty[s], 1);
         }
         mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->s_free, 128);
-        mbar_init(&bars->p_full, 128);
+        mbar_init(&bars->s_free, 4);      // one arrival per softmax warp
+        mbar_init(&bars->p_full, 4);
         mbar_init(&bars->pv_full, 1);
         fence_mbar_init();
     }
@@ -547,8 +548,8 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(&bars->kv_empty[s], 1);
         }
         mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->s_free, 256);
-        mbar_init(&bars->p_full, 256);
+        mbar_init(&bars->s_free, 8);      // one arrival per softmax warp
+        mbar_init(&bars->p_full, 8);
         mbar_init(&bars->pv_full, 1);
         fence_mbar_init();
     }
@@ -738,9 +739,9 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
             }
             tc_fence_before();
-            mbar_arrive(&bars->s_free);       // S may be overwritten by the next Q K^T
+            mbar_arrive_warp(&bars->s_free);       // S may be overwritten by the next Q K^T
             fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
-            mbar_arrive(&bars->p_full);
+            mbar_arrive_warp(&bars->p_full);
         }
         mbar_wait(&bars->pv_full, (nblk - 1) & 1);
         tc_fence_after();
@@ -839,7 +840,7 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(&bars->kv_empty[s], 1);
         }
         mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->p_full, 256);
+        mbar_init(&bars->p_full, 8);      // one arrival per softmax warp
         mbar_init(&bars->pv_full, 1);
         fence_mbar_init();
     }
@@ -1014,7 +1015,7 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(&bars->p_full);
+            mbar_arrive_warp(&bars->p_full);
         }
         mbar_wait(&bars->pv_full, (nblk - 1) & 1);
         tc_fence_after();
@@ -1057,6 +1058,323 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == 9) {
         tc_fence_after();
         tmem_dealloc(tmem, 256);
+    }
+}
+
+constexpr int kFwd6Stages = 4;   // K and V rings: a TMA load takes longer than a block of work, so it is issued three blocks ahead
+
+// ---- forward, two query tiles per CTA, one thread per query row, scores read from TMEM once ---------------
+// Tensor memory has ONE read port of 64 B/clk per SM (measured with clock64 traces): the softmax warps'
+// tcgen05.ld and the A-operand reads of TMEM-sourced MMAs share it, so a 128 x 128 fp32 score tile costs
+// 1024 cycles per read.  Here the only TMEM reader is ONE load of the scores: a softmax thread owns a whole
+// query row, its 128 scores go to registers once (setmaxnreg moves registers from the TMA / MMA warpgroup
+// to the softmax warpgroups: 224 per thread), the row maximum needs no exchange with other threads, P goes
+// to shared memory (K-major, 128-byte swizzle) and the row sums are accumulated by the row's own thread
+// from the packed bf16 probabilities it has just produced (no P x ones product).  The scores sit in
+// registers ~50 cycles after S is ready, so S is handed back at once and Q K^T of the next block runs under
+// the current block's exponentials.  Two tiles per CTA (warps 0-3 and 4-7) share every K/V tile (4-deep TMA
+// rings for K and for V: a load takes longer than a block of work) and run in opposite phases.  O
+// accumulates in TMEM with the lazy rescale of mha_fwd3_kernel.
+// TMEM (512 columns): S_A 0-127 | S_B 128-255 | O_A 256-319 | O_B 320-383.
+struct __align__(8) MhaBarriers8 {
+    uint64_t q_full;
+    uint64_t k_full[kFwd6Stages];
+    uint64_t k_empty[kFwd6Stages];
+    uint64_t v_full[kFwd6Stages];
+    uint64_t v_empty[kFwd6Stages];
+    uint64_t s_full[2];     // per tile
+    uint64_t s_free[2];
+    uint64_t p_full[2];
+    uint64_t pv_full[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+constexpr int kFwd8Threads = 384;   // 8 softmax warps + one utility warpgroup (TMA, MMA, two idle warps)
+constexpr int kFwd8Smem = (2 + 2 * kFwd6Stages + 4) * kTileBytes /*Q x2 + K ring + V ring + P x2*/ + 256 /*barriers*/;
+static_assert(kFwd8Smem <= 232448, "shared memory of the forward kernel");
+
+template <bool DROP>
+__global__ void __launch_bounds__(kFwd8Threads, 1)
+mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sQ = smem;                              // 2 tiles
+    unsigned char* sK = sQ + 2 * kTileBytes;               // kFwd6Stages tiles
+    unsigned char* sV = sK + kFwd6Stages * kTileBytes;     // kFwd6Stages tiles
+    unsigned char* sP = sV + kFwd6Stages * kTileBytes;     // [2 tiles][2 key halves][128 rows][128 B]
+    MhaBarriers8* bars = reinterpret_cast<MhaBarriers8*>(sP + 4 * kTileBytes);
+    static_assert(sizeof(MhaBarriers8) <= 256, "barrier block");
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * 2 * kBM;
+    const int h = blockIdx.y;
+    const int b = blockIdx.z;
+    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+    const int ntile = (q0 + kBM < a.Lq) ? 2 : 1;           // the second tile may lie entirely beyond Lq
+    // key blocks each tile needs: up to kvlen, and up to its last query row when causal
+    int nb[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        int k_end = a.causal ? min(kvlen, q0 + t * kBM + kBM) : kvlen;
+        if (a.dense_mask) k_end = a.Lk;
+        nb[t] = (t < ntile) ? max(1, (k_end + kBN - 1) / kBN) : 0;
+    }
+    const int nblk = max(nb[0], nb[1]);                    // nb[1] >= nb[0] whenever tile 1 exists
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->q_full, 1);
+        for (int s = 0; s < kFwd6Stages; ++s) {
+            mbar_init(&bars->k_full[s], 1);
+            mbar_init(&bars->k_empty[s], 1);
+            mbar_init(&bars->v_full[s], 1);
+            mbar_init(&bars->v_empty[s], 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->s_full[t], 1);
+            mbar_init(&bars->s_free[t], 4);       // one arrival per softmax warp of the tile
+            mbar_init(&bars->p_full[t], 4);
+            mbar_init(&bars->pv_full[t], 1);
+        }
+        fence_mbar_init();
+    }
+    constexpr int kTmaWarp = 8, kMmaWarp = 9;
+    // (register reallocation between warpgroups at the head of every role: the softmax threads hold a
+    // whole row of scores, the utility warpgroup needs next to nothing)
+    if (warp == kMmaWarp) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == kTmaWarp) {
+        // ===== TMA producer =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(&bars->q_full, ntile * kTileBytes);
+            for (int t = 0; t < ntile; ++t) tma_load_4d(sQ + t * kTileBytes, &tm_q, 0, h, q0 + t * kBM, b, &bars->q_full);
+            for (int j = 0; j < nblk; ++j) {
+                const int s = j % kFwd6Stages;
+                const int use = j / kFwd6Stages;
+                if (use > 0) mbar_wait(&bars->k_empty[s], (use - 1) & 1);    // freed by the last Q K^T of block j - stages
+                mbar_arrive_expect_tx(&bars->k_full[s], kTileBytes);
+                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->k_full[s]);
+                if (use > 0) mbar_wait(&bars->v_empty[s], (use - 1) & 1);    // freed by the last P V of block j - stages
+                mbar_arrive_expect_tx(&bars->v_full[s], kTileBytes);
+                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->v_full[s]);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer (one thread) =====
+        // S of a tile's next block is issued as soon as its scores have been read (s_free), P V when P is there
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            // S of (tile t, block j); `last` releases the K stage (no later product reads it)
+            auto issue_s = [&](int t, int j, bool last) {
+                const int ks = j % kFwd6Stages;
+                mbar_wait(&bars->k_full[ks], (j / kFwd6Stages) & 1);
+                if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);      // scores of block j-1 are in registers
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
+                const uint32_t k_addr = smem_u32(sK + ks * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem + 128 * t, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full[t]);
+                if (last) tc_commit(&bars->k_empty[ks]);
+            };
+            mbar_wait(&bars->q_full, 0);
+            for (int t = 0; t < ntile; ++t) issue_s(t, 0, t == ntile - 1);
+            for (int j = 0; j < nblk; ++j) {
+                const int vs = j % kFwd6Stages;
+                const uint32_t v_addr = smem_u32(sV + vs * kTileBytes);
+                // next block's scores first: they only need s_free, which arrives long before p_full
+                for (int t = 0; t < ntile; ++t) {
+                    if (j + 1 < nb[t]) {
+                        bool last_k = true;
+                        for (int t2 = t + 1; t2 < ntile; ++t2) last_k = last_k && (j + 1 >= nb[t2]);
+                        issue_s(t, j + 1, last_k);
+                    }
+                }
+                for (int t = 0; t < ntile; ++t) {
+                    if (j >= nb[t]) continue;                 // causal: the first tile needs fewer key blocks
+                    mbar_wait(&bars->v_full[vs], (j / kFwd6Stages) & 1);
+                    mbar_wait(&bars->p_full[t], j & 1);       // P of (t, j) is in shared memory
+                    tc_fence_after();
+                    const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
+                    const uint32_t tmem_o = tmem + 256 + 64 * t;
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk) {
+                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                        const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
+                        umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
+                    }
+                    tc_commit(&bars->pv_full[t]);
+                    bool last_v = true;
+                    for (int t2 = t + 1; t2 < ntile; ++t2) last_v = last_v && (j >= nb[t2]);
+                    if (last_v) tc_commit(&bars->v_empty[vs]);
+                }
+            }
+        }
+    } else if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // the two idle warps of the utility warpgroup
+    } else {
+        // ===== softmax + epilogue: warps 0-3 own tile 0, warps 4-7 tile 1; thread = query row =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+        const int t = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        if (t < ntile) {
+            const int qi = q0 + t * kBM + row;
+            const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+            const uint32_t tmem_s = tmem + 128 * t + lane_base;
+            const uint32_t tmem_o = tmem + 256 + 64 * t + lane_base;
+            unsigned char* prow = sP + t * 2 * kTileBytes + row * 128;
+            float m_used = -INFINITY;
+            float l_run = 0.0f;          // sum of the row's (undropped) probabilities, scaled like O
+            const float c = a.scale_log2;
+            const int nbt = nb[t];
+            for (int j = 0; j < nbt; ++j) {
+                const int key0 = j * kBN;
+                int lim = kvlen;
+                if (a.causal) lim = min(lim, qi + 1);
+                const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+                mbar_wait(&bars->s_full[t], j & 1);
+                tc_fence_after();
+                uint32_t r[4][32];           // the row's 128 scores: read from TMEM exactly once
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld32_issue(tmem_s + 32 * q, r[q]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive_warp(&bars->s_free[t]);      // the scores are in registers: S may be overwritten
+                float m_blk = -INFINITY;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int key = key0 + 32 * q + i;
+                            bool dead = key >= lim;
+                            if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                            if (dead) r[q][i] = 0xff800000u;   // -inf
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[q][i]));
+                }
+                const float m_new = fmaxf(m_used, m_blk);
+                const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);
+                bool pv_waited = false;
+                if (j == 0) {
+                    m_used = m_new;
+                } else if (__any_sync(0xffffffffu, grow)) {      // TMEM accesses are warp-collective: all lanes go
+                    // O is being accumulated by P V of this tile's previous block: wait for it before touching O
+                    mbar_wait(&bars->pv_full[t], (j - 1) & 1);
+                    tc_fence_after();
+                    pv_waited = true;
+                    const float f = grow ? ex2_approx((m_used - m_new) * c) : 1.0f;   // m_used = -inf -> 0
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t o32[32];
+                        tmem_ld32_issue(tmem_o + 32 * hh, o32);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * f);
+                        tmem_st32(tmem_o + 32 * hh, o32);
+                    }
+                    l_run *= f;
+                    tmem_st_wait();
+                    if (grow) m_used = m_new;
+                }
+                const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
+                // the P tile is free once P V of the previous block has read it
+                if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
+                float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t pk[16];
+                    if (DROP) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                       a.seed_lo, a.seed_hi);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
+                                float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i + 1]), c, -mc));
+                                lsum[q] += p0 + p1;
+                                p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                                p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                                const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                                pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const uint32_t w = ex2_bf16x2(fmaf(__uint_as_float(r[q][i]), c, -mc), fmaf(__uint_as_float(r[q][i + 1]), c, -mc));
+                            pk[i >> 1] = w;
+                            // the normaliser is the sum of the probabilities P V really uses: the bf16 values
+                            lsum[q] += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+                        }
+                    }
+                    // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half q / 2
+                    unsigned char* pr = prow + (q >> 1) * kTileBytes;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int chunk = ((q & 1) * 4 + q4) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(pr + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                    }
+                }
+                l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+                fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+                mbar_arrive_warp(&bars->p_full[t]);
+            }
+            // epilogue
+            mbar_wait(&bars->pv_full[t], (nbt - 1) & 1);
+            tc_fence_after();
+            const float inv = 1.0f / l_run;
+            __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Hh + h) * kD;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                uint32_t o32[32];
+                tmem_ld32_issue(tmem_o + 32 * hh, o32);
+                tmem_ld_wait();
+                if (qi < a.Lq) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(o32[i + 2 * u]) * inv,
+                                                                             __uint_as_float(o32[i + 2 * u + 1]) * inv);
+                            w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + 32 * hh + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            if (qi < a.Lq && a.lse != nullptr)
+                a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_used * c + log2f(l_run)) * 0.6931471805599453f;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
     }
 }
 
@@ -1111,8 +1429,8 @@ mha_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_init(&bars->kv_full[s], 1);
             mbar_init(&bars->kv_empty[s], 1);
             mbar_init(&bars->s_full[s], 1);
-            mbar_init(&bars->s_free[s], 128);
-            mbar_init(&bars->p_full[s], 128);
+            mbar_init(&bars->s_free[s], 4);   // one arrival per softmax warp
+            mbar_init(&bars->p_full[s], 4);
             mbar_init(&bars->pv_full[s], 1);
         }
         fence_mbar_init();
@@ -1309,7 +1627,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_init(&bars->qdo_empty[s], 1);
         }
         mbar_init(&bars->sdp_full, 1);
-        mbar_init(&bars->pds_full, 128 * CG);
+        mbar_init(&bars->pds_full, 4 * CG);   // one arrival per softmax warp
         mbar_init(&bars->dq_full, 1);
         fence_mbar_init();
     }
@@ -1522,7 +1840,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             }
             tc_fence_before();
             fence_proxy_async();
-            mbar_arrive(&bars->pds_full);
+            mbar_arrive_warp(&bars->pds_full);
             if (it > 0) flush_dq(dq, i_start + it - 1);
         }
         if (nsteps > 0) {
@@ -1702,6 +2020,10 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+    } else if (variant == 8) {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem));
+        dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
+        mha_fwd8_kernel<false><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);
     } else if (variant == 4) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd4Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);

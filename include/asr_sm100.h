@@ -57,7 +57,8 @@ int         asr_device_ok(void);
  * slice), "mha_variant" (0 = auto = 3,
  * 1 = one tile per CTA with four softmax warps, 2 = two-tile ping-pong, 3 = eight
  * softmax warps per tile, O accumulated in TMEM with lazy rescale, 4 = as 3 with P
- * kept in TMEM as the A operand of P V), "mha_bwd_groups" (softmax-backward
+ * kept in TMEM as the A operand of P V, 8 = two tiles per CTA sharing K/V, one thread
+ * per query row, scores read from TMEM once), "mha_bwd_groups" (softmax-backward
  * warps per CTA = 4 * groups; 0 = default (4 groups), 2). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
