@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr",
     "-Xptxas", "-v",
-]
+] + os.environ.get("ASR_NVCC_EXTRA", "").split()   # e.g. -DASR_MHA_TRACE for the clock64 traces of tools/mha_trace.py
 
 
 def find_nvcc():

@@ -80,6 +80,29 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         : "memory");
 }
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two lanes of a row
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo, float hi) {
+    uint32_t w;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+    return w;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -1070,6 +1093,23 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 }
 
+#ifdef ASR_MHA_TRACE
+// clock64 stamps of CTA (0,0,0): [tile][block < 16][point < 12], read back with asr_debug_mha_trace (tools/mha_trace.py)
+__device__ long long g_mha_trace[2 * 16 * 12];
+#define MHA_TRACE(t, j, k)                                                                    \
+    do {                                                                                      \
+        if (lane == 0 && (warp & 3) == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) \
+            g_mha_trace[((t) * 16 + (j)) * 12 + (k)] = clock64();                             \
+    } while (0)
+#define MHA_TRACE_MMA(t, j, k)                                                                \
+    do {                                                                                      \
+        if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) g_mha_trace[((t) * 16 + (j)) * 12 + (k)] = clock64(); \
+    } while (0)
+#else
+#define MHA_TRACE(t, j, k) do { } while (0)
+#define MHA_TRACE_MMA(t, j, k) do { } while (0)
+#endif
+
 constexpr int kFwd6Stages = 4;   // K and V rings: a TMA load takes longer than a block of work, so it is issued three blocks ahead
 
 // ---- forward, two query tiles per CTA, one thread per query row, scores read from TMEM once ---------------
@@ -1102,7 +1142,10 @@ constexpr int kFwd8Threads = 384;   // 8 softmax warps + one utility warpgroup (
 constexpr int kFwd8Smem = (2 + 2 * kFwd6Stages + 4) * kTileBytes /*Q x2 + K ring + V ring + P x2*/ + 256 /*barriers*/;
 static_assert(kFwd8Smem <= 232448, "shared memory of the forward kernel");
 
-template <bool DROP>
+// MODE bit 0: the two tiles take turns on the TMEM read port (named-barrier token), which keeps them in
+// opposite phases: one loads its scores while the other runs its exponentials.  MODE bit 1: fp32
+// exponentials with packed f32x2 arithmetic (FFMA2 / FADD2), row sums from the unrounded fp32 values.
+template <bool DROP, int MODE, int POLY>
 __global__ void __launch_bounds__(kFwd8Threads, 1)
 mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
@@ -1193,6 +1236,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 mbar_wait(&bars->k_full[ks], (j / kFwd6Stages) & 1);
                 if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);      // scores of block j-1 are in registers
                 tc_fence_after();
+                MHA_TRACE_MMA(t, j, 10);
                 const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
                 const uint32_t k_addr = smem_u32(sK + ks * kTileBytes);
 #pragma unroll
@@ -1201,6 +1245,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                               idesc_s, kk > 0 ? 1u : 0u);
                 tc_commit(&bars->s_full[t]);
                 if (last) tc_commit(&bars->k_empty[ks]);
+                MHA_TRACE_MMA(t, j, 11);
             };
             mbar_wait(&bars->q_full, 0);
             for (int t = 0; t < ntile; ++t) issue_s(t, 0, t == ntile - 1);
@@ -1220,6 +1265,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     mbar_wait(&bars->v_full[vs], (j / kFwd6Stages) & 1);
                     mbar_wait(&bars->p_full[t], j & 1);       // P of (t, j) is in shared memory
                     tc_fence_after();
+                    MHA_TRACE_MMA(t, j, 8);
                     const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
                     const uint32_t tmem_o = tmem + 256 + 64 * t;
 #pragma unroll
@@ -1229,6 +1275,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
                     }
                     tc_commit(&bars->pv_full[t]);
+                    MHA_TRACE_MMA(t, j, 9);
                     bool last_v = true;
                     for (int t2 = t + 1; t2 < ntile; ++t2) last_v = last_v && (j >= nb[t2]);
                     if (last_v) tc_commit(&bars->v_empty[vs]);
@@ -1253,20 +1300,38 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float l_run = 0.0f;          // sum of the row's (undropped) probabilities, scaled like O
             const float c = a.scale_log2;
             const int nbt = nb[t];
-            for (int j = 0; j < nbt; ++j) {
+            // token ring of the two tiles (MODE bit 0): tile 0 waits on barrier 1, tile 1 on barrier 2; whoever has
+            // read its scores hands the TMEM port to the other tile.  Both tiles walk nblk turns (a tile that
+            // has run out of key blocks just passes the token on); tile 1 grants the first turn.
+            const bool pp = (MODE & 1) && ntile == 2;
+            const int nturn = pp ? nblk : nbt;
+            if (pp && t == 1) bar_arrive_named(1, 256);
+            for (int j = 0; j < nturn; ++j) {
+                if (pp) bar_sync_named(1 + t, 256);
+                if (j >= nbt) {
+                    if (t == 0 || j + 1 < nturn) bar_arrive_named(2 - t, 256);
+                    continue;
+                }
                 const int key0 = j * kBN;
                 int lim = kvlen;
                 if (a.causal) lim = min(lim, qi + 1);
                 const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+                MHA_TRACE(t, j, 0);
                 mbar_wait(&bars->s_full[t], j & 1);
                 tc_fence_after();
+                MHA_TRACE(t, j, 1);
                 uint32_t r[4][32];           // the row's 128 scores: read from TMEM exactly once
 #pragma unroll
                 for (int q = 0; q < 4; ++q) tmem_ld32_issue(tmem_s + 32 * q, r[q]);
                 tmem_ld_wait();
+#ifdef ASR_MHA_TRACE
+                if ((r[0][0] ^ r[1][0] ^ r[2][0] ^ r[3][31]) == 0x7fc54321u) __trap();   // the stamp waits for the data
+#endif
+                MHA_TRACE(t, j, 2);
+                if (pp && (t == 0 || j + 1 < nturn)) bar_arrive_named(2 - t, 256);
                 tc_fence_before();
                 mbar_arrive_warp(&bars->s_free[t]);      // the scores are in registers: S may be overwritten
-                float m_blk = -INFINITY;
+                float m_q[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (need_mask) {
@@ -1278,12 +1343,15 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             if (dead) r[q][i] = 0xff800000u;   // -inf
                         }
                     }
+                    m_q[q] = -INFINITY;          // four independent chains
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(r[q][i]));
+                    for (int i = 0; i < 32; ++i) m_q[q] = fmaxf(m_q[q], __uint_as_float(r[q][i]));
                 }
+                const float m_blk = fmaxf(fmaxf(m_q[0], m_q[1]), fmaxf(m_q[2], m_q[3]));
                 const float m_new = fmaxf(m_used, m_blk);
                 const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);
                 bool pv_waited = false;
+                MHA_TRACE(t, j, 3);
                 if (j == 0) {
                     m_used = m_new;
                 } else if (__any_sync(0xffffffffu, grow)) {      // TMEM accesses are warp-collective: all lanes go
@@ -1306,12 +1374,33 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     if (grow) m_used = m_new;
                 }
                 const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
-                // the P tile is free once P V of the previous block has read it
-                if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
+                MHA_TRACE(t, j, 4);
+                // The P tile is free once P V of the previous block has read it.  MODE bit 2: the first two
+                // 32-key chunks are exponentiated into registers before that wait (the product finishes ~500
+                // cycles after the row maximum is known), and stored behind it.
+                constexpr bool kLateWait = (MODE & 4) != 0;
+                if (!kLateWait && j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
+                MHA_TRACE(t, j, 5);
                 float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                uint32_t pk_all[4][16];
+                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half q / 2
+                auto store_chunk = [&](int q) {
+                    unsigned char* pr = prow + (q >> 1) * kTileBytes;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int chunk = ((q & 1) * 4 + q4) ^ (row & 7);
+                        *reinterpret_cast<uint4*>(pr + chunk * 16) =
+                            make_uint4(pk_all[q][4 * q4], pk_all[q][4 * q4 + 1], pk_all[q][4 * q4 + 2], pk_all[q][4 * q4 + 3]);
+                    }
+                };
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    uint32_t pk[16];
+                    uint32_t (&pk)[16] = pk_all[q];
+                    if (kLateWait && q == 2) {
+                        if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
+                        store_chunk(0);
+                        store_chunk(1);
+                    }
                     if (DROP) {
 #pragma unroll
                         for (int g = 0; g < 2; ++g) {
@@ -1328,6 +1417,42 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                                 pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
                             }
                         }
+                    } else if (MODE & 2) {
+                        const uint64_t c2 = pack_f32x2(c, c);
+                        const uint64_t mc2 = pack_f32x2(-mc, -mc);
+                        uint64_t ls2 = pack_f32x2(0.0f, 0.0f);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float x0, x1;
+                            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1])), c2, mc2);
+                            unpack_f32x2(x2, x0, x1);
+                            if (((i >> 1) & 3) < POLY) {
+                                // 2^x on the FMA pipe for POLY of every 4 pairs (the XU pipe does 16 exponentials per
+                                // clock and SM, the bound of this loop): x = n + f, n = round(x), |f| <= 1/2,
+                                // 2^f by a cubic (7.5e-5 relative, below the bf16 rounding of P), n added to the
+                                // exponent field.  The magic constant leaves n in the low mantissa bits of tt.
+                                const uint64_t xc = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+                                const uint64_t tt = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
+                                const uint64_t nn = add_f32x2(tt, pack_f32x2(-12582912.0f, -12582912.0f));
+                                const uint64_t ff = fma_f32x2(nn, pack_f32x2(-1.0f, -1.0f), xc);
+                                uint64_t pp2 = fma_f32x2(pack_f32x2(0.0551716685f, 0.0551716685f), ff, pack_f32x2(0.2426111251f, 0.2426111251f));
+                                pp2 = fma_f32x2(pp2, ff, pack_f32x2(0.6932609677f, 0.6932609677f));
+                                pp2 = fma_f32x2(pp2, ff, pack_f32x2(0.9999280572f, 0.9999280572f));
+                                float p0, p1, t0, t1;
+                                unpack_f32x2(pp2, p0, p1);
+                                unpack_f32x2(tt, t0, t1);
+                                x0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+                                x1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+                            } else {
+                                x0 = ex2_approx(x0);
+                                x1 = ex2_approx(x1);
+                            }
+                            ls2 = add_f32x2(ls2, pack_f32x2(x0, x1));
+                            pk[i >> 1] = cvt_bf16x2(x0, x1);
+                        }
+                        float l0, l1;
+                        unpack_f32x2(ls2, l0, l1);
+                        lsum[q] = l0 + l1;
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
@@ -1337,17 +1462,13 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             lsum[q] += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
                         }
                     }
-                    // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half q / 2
-                    unsigned char* pr = prow + (q >> 1) * kTileBytes;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int chunk = ((q & 1) * 4 + q4) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(pr + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                    }
+                    if (!kLateWait || q >= 2) store_chunk(q);
                 }
                 l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+                MHA_TRACE(t, j, 6);
                 fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
                 mbar_arrive_warp(&bars->p_full[t]);
+                MHA_TRACE(t, j, 7);
             }
             // epilogue
             mbar_wait(&bars->pv_full[t], (nbt - 1) & 1);
@@ -2029,10 +2150,22 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
-    } else if (variant == 8) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem));
+    } else if (variant >= 8 && variant <= 15) {
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
-        mha_fwd8_kernel<false><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);
+#define ASR_LAUNCH_FWD8(MODE, POLY)                                                                                           \
+    do {                                                                                                                      \
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false, MODE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); \
+        mha_fwd8_kernel<false, MODE, POLY><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);                             \
+    } while (0)
+        if (variant == 8) ASR_LAUNCH_FWD8(0, 0);
+        else if (variant == 9) ASR_LAUNCH_FWD8(1, 0);
+        else if (variant == 10) ASR_LAUNCH_FWD8(2, 0);
+        else if (variant == 11) ASR_LAUNCH_FWD8(3, 0);
+        else if (variant == 12) ASR_LAUNCH_FWD8(6, 0);
+        else if (variant == 13) ASR_LAUNCH_FWD8(6, 1);
+        else if (variant == 14) ASR_LAUNCH_FWD8(6, 2);
+        else ASR_LAUNCH_FWD8(2, 1);
+#undef ASR_LAUNCH_FWD8
     } else if (variant == 4) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd4Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
@@ -2065,6 +2198,12 @@ extern "C" int asr_mha_fwd_dropout_bf16(const void* q, const void* k, const void
                                         float scale, float p_drop, uint64_t seed, void* out, float* lse, void* stream) {
     return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, p_drop, seed, stream);
 }
+
+#ifdef ASR_MHA_TRACE
+extern "C" int asr_debug_mha_trace(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, asr::g_mha_trace, sizeof(long long) * 2 * 16 * 12);
+}
+#endif
 
 extern "C" float asr_mha_dropout_keep_prob(float p_drop) { return (256.0f - (float)drop_threshold(p_drop)) / 256.0f; }
 
