@@ -80,6 +80,18 @@ __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32
         : "memory");
 }
 __device__ __forceinline__ void bar_sync_named(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// One lane of a converged warp, chosen by the hardware.  tcgen05.mma / commit issued under this predicate
+// compile to a plain predicated UTCHMMA; under `if (lane == 0)` ptxas cannot tell that a single thread is
+// active and wraps every MMA in a serialising loop over the active lanes (~70 cycles per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bar_arrive_named(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // packed fp32 pairs (FFMA2 / FADD2 on sm_100): one issue slot for two lanes of a row
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
@@ -449,7 +461,7 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     if (warp == 4) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
@@ -465,7 +477,7 @@ mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
     } else if (warp == 5) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
             constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
@@ -593,7 +605,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (warp == 8) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
@@ -609,7 +621,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == 9) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
             constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
@@ -890,7 +902,7 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (warp == 8) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
@@ -906,7 +918,7 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == 9) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
             constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
@@ -1094,20 +1106,26 @@ mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 }
 
 #ifdef ASR_MHA_TRACE
-// clock64 stamps of CTA (0,0,0): [tile][block < 16][point < 12], read back with asr_debug_mha_trace (tools/mha_trace.py)
-__device__ long long g_mha_trace[2 * 16 * 12];
+// clock64 stamps of CTA (0,0,0): [tile][block < 16][point < 20], read back with asr_debug_mha_trace (tools/mha_trace.py)
+__device__ long long g_mha_trace[2 * 16 * 20];
 #define MHA_TRACE(t, j, k)                                                                    \
     do {                                                                                      \
         if (lane == 0 && (warp & 3) == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) \
-            g_mha_trace[((t) * 16 + (j)) * 12 + (k)] = clock64();                             \
+            g_mha_trace[((t) * 16 + (j)) * 20 + (k)] = clock64();                             \
+    } while (0)
+#define MHA_TRACE_WARP(t, j, k)                                                               \
+    do {                                                                                      \
+        if (lane == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16)             \
+            g_mha_trace[((t) * 16 + (j)) * 20 + (k) + (warp & 3)] = clock64();                \
     } while (0)
 #define MHA_TRACE_MMA(t, j, k)                                                                \
     do {                                                                                      \
-        if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) g_mha_trace[((t) * 16 + (j)) * 12 + (k)] = clock64(); \
+        if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) g_mha_trace[((t) * 16 + (j)) * 20 + (k)] = clock64(); \
     } while (0)
 #else
 #define MHA_TRACE(t, j, k) do { } while (0)
 #define MHA_TRACE_MMA(t, j, k) do { } while (0)
+#define MHA_TRACE_WARP(t, j, k) do { } while (0)
 #endif
 
 constexpr int kFwd6Stages = 4;   // K and V rings: a TMA load takes longer than a block of work, so it is issued three blocks ahead
@@ -1124,7 +1142,7 @@ constexpr int kFwd6Stages = 4;   // K and V rings: a TMA load takes longer than 
 // the current block's exponentials.  Two tiles per CTA (warps 0-3 and 4-7) share every K/V tile (4-deep TMA
 // rings for K and for V: a load takes longer than a block of work) and run in opposite phases.  O
 // accumulates in TMEM with the lazy rescale of mha_fwd3_kernel.
-// TMEM (512 columns): S_A 0-127 | S_B 128-255 | O_A 256-319 | O_B 320-383.
+// TMEM (512 columns): S_A 0-127 | S_B 128-255 | O_A 256-319 | O_B 320-383 | P_A 384-447 | P_B 448-511 (MODE bit 4).
 struct __align__(8) MhaBarriers8 {
     uint64_t q_full;
     uint64_t k_full[kFwd6Stages];
@@ -1142,10 +1160,11 @@ constexpr int kFwd8Threads = 384;   // 8 softmax warps + one utility warpgroup (
 constexpr int kFwd8Smem = (2 + 2 * kFwd6Stages + 4) * kTileBytes /*Q x2 + K ring + V ring + P x2*/ + 256 /*barriers*/;
 static_assert(kFwd8Smem <= 232448, "shared memory of the forward kernel");
 
-// MODE bit 0: the two tiles take turns on the TMEM read port (named-barrier token), which keeps them in
-// opposite phases: one loads its scores while the other runs its exponentials.  MODE bit 1: fp32
-// exponentials with packed f32x2 arithmetic (FFMA2 / FADD2), row sums from the unrounded fp32 values.
-template <bool DROP, int MODE, int POLY>
+// MODE bit 0: the two tiles take turns on the XU pipe (named-barrier token), which keeps them in
+// opposite phases: one loads its scores and finds the row maxima while the other runs its exponentials.  MODE bit 1: fp32
+// exponentials with packed f32x2 arithmetic (FFMA2 / FADD2), row sums from the unrounded fp32 values.  MODE bit 4:
+// P stays in tensor memory (own columns) as the A operand of P V.  MODE bit 5: one MMA issuer per tile.
+template <bool DROP, int MODE>
 __global__ void __launch_bounds__(kFwd8Threads, 1)
 mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
@@ -1179,9 +1198,10 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(&bars->q_full, 1);
         for (int s = 0; s < kFwd6Stages; ++s) {
             mbar_init(&bars->k_full[s], 1);
-            mbar_init(&bars->k_empty[s], 1);
+            // MODE bit 5: one MMA issuer per tile, each of them releases every stage once
+            mbar_init(&bars->k_empty[s], (MODE & 32) ? ntile : 1);
             mbar_init(&bars->v_full[s], 1);
-            mbar_init(&bars->v_empty[s], 1);
+            mbar_init(&bars->v_empty[s], (MODE & 32) ? ntile : 1);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->s_full[t], 1);
@@ -1206,7 +1226,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     if (warp == kTmaWarp) {
         // ===== TMA producer =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
@@ -1223,11 +1243,79 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->v_full[s]);
             }
         }
+    } else if ((MODE & 32) && (warp == kMmaWarp || warp == kMmaWarp + 1)) {
+        // ===== MMA issuers, one elected thread per tile (MODE bit 5) =====
+        // A single issuer walking S(0) S(1) PV(0) PV(1) in order spends ~100 cycles per Q K^T MMA, ~70 per P V
+        // MMA and 100-200 per (already complete) mbarrier wait - its sub-partition is shared with two busy
+        // softmax warps - which adds up to the whole period of a key block.  Two issuers on two sub-partitions
+        // halve that chain, and a tile's P V no longer queues behind the other tile's waits.
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        const int t = warp - kMmaWarp;
+        if (t < ntile && elect_one_sync()) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
+            const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
+            const uint32_t tmem_s = tmem + 128 * t;
+            const uint32_t tmem_o = tmem + 256 + 64 * t;
+            const uint32_t tmem_p = tmem + 384 + 64 * t;
+            const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
+            const int nbt = nb[t];
+            // S of block j, or just the release of its K stage when this tile does not need the block
+            auto issue_s = [&](int j) {
+                const int ks = j % kFwd6Stages;
+                mbar_wait(&bars->k_full[ks], (j / kFwd6Stages) & 1);
+                if (j >= nbt) {
+                    mbar_arrive(&bars->k_empty[ks]);
+                    return;
+                }
+                if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);      // scores of block j-1 are in registers
+                tc_fence_after();
+                MHA_TRACE_MMA(t, j, 10);
+                const uint32_t k_addr = smem_u32(sK + ks * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full[t]);
+                tc_commit(&bars->k_empty[ks]);
+                MHA_TRACE_MMA(t, j, 11);
+            };
+            mbar_wait(&bars->q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nblk; ++j) {
+                const int vs = j % kFwd6Stages;
+                if (j + 1 < nblk) issue_s(j + 1);
+                MHA_TRACE_MMA(t, j, 16);
+                mbar_wait(&bars->v_full[vs], (j / kFwd6Stages) & 1);
+                MHA_TRACE_MMA(t, j, 17);
+                if (j >= nbt) {
+                    mbar_arrive(&bars->v_empty[vs]);
+                    continue;
+                }
+                mbar_wait(&bars->p_full[t], j & 1);
+                tc_fence_after();
+                MHA_TRACE_MMA(t, j, 8);
+                const uint32_t v_addr = smem_u32(sV + vs * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kBN / 16; ++kk) {
+                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
+                    if (MODE & 16) {
+                        umma_bf16_ts(tmem_o, tmem_p + 8 * kk, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                    } else {
+                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                        umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&bars->pv_full[t]);
+                tc_commit(&bars->v_empty[vs]);
+                MHA_TRACE_MMA(t, j, 9);
+            }
+        }
     } else if (warp == kMmaWarp) {
         // ===== MMA issuer (one thread) =====
-        // S of a tile's next block is issued as soon as its scores have been read (s_free), P V when P is there
+        // S of a tile's next block is issued as soon as its scores have been read (s_free), P V when P is there.
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
             // S of (tile t, block j); `last` releases the K stage (no later product reads it)
@@ -1262,17 +1350,24 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
                 for (int t = 0; t < ntile; ++t) {
                     if (j >= nb[t]) continue;                 // causal: the first tile needs fewer key blocks
+                    MHA_TRACE_MMA(t, j, 16);
                     mbar_wait(&bars->v_full[vs], (j / kFwd6Stages) & 1);
-                    mbar_wait(&bars->p_full[t], j & 1);       // P of (t, j) is in shared memory
+                    MHA_TRACE_MMA(t, j, 17);
+                    mbar_wait(&bars->p_full[t], j & 1);       // P of (t, j) is in shared memory / tensor memory
                     tc_fence_after();
                     MHA_TRACE_MMA(t, j, 8);
                     const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
                     const uint32_t tmem_o = tmem + 256 + 64 * t;
 #pragma unroll
                     for (int kk = 0; kk < kBN / 16; ++kk) {
-                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
                         const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
-                        umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
+                        if (MODE & 16) {
+                            // A operand = the row's packed bf16 probabilities in tensor memory: 16 keys = 8 columns
+                            umma_bf16_ts(tmem_o, tmem + 384 + 64 * t + 8 * kk, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                        } else {
+                            const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
+                            umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
+                        }
                     }
                     tc_commit(&bars->pv_full[t]);
                     MHA_TRACE_MMA(t, j, 9);
@@ -1300,15 +1395,16 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             float l_run = 0.0f;          // sum of the row's (undropped) probabilities, scaled like O
             const float c = a.scale_log2;
             const int nbt = nb[t];
-            // token ring of the two tiles (MODE bit 0): tile 0 waits on barrier 1, tile 1 on barrier 2; whoever has
-            // read its scores hands the TMEM port to the other tile.  Both tiles walk nblk turns (a tile that
-            // has run out of key blocks just passes the token on); tile 1 grants the first turn.
+            // token ring of the two tiles (MODE bit 0): tile 0 waits on barrier 1, tile 1 on barrier 2; a tile holds
+            // the token while it runs its exponentials and then hands it to the other tile, so the two tiles
+            // cannot fall into lockstep on the XU pipe.  Both tiles walk nblk turns (a tile that has run out of
+            // key blocks just passes the token on); tile 1 grants the first turn.
             const bool pp = (MODE & 1) && ntile == 2;
             const int nturn = pp ? nblk : nbt;
             if (pp && t == 1) bar_arrive_named(1, 256);
             for (int j = 0; j < nturn; ++j) {
-                if (pp) bar_sync_named(1 + t, 256);
                 if (j >= nbt) {
+                    bar_sync_named(1 + t, 256);
                     if (t == 0 || j + 1 < nturn) bar_arrive_named(2 - t, 256);
                     continue;
                 }
@@ -1328,7 +1424,6 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if ((r[0][0] ^ r[1][0] ^ r[2][0] ^ r[3][31]) == 0x7fc54321u) __trap();   // the stamp waits for the data
 #endif
                 MHA_TRACE(t, j, 2);
-                if (pp && (t == 0 || j + 1 < nturn)) bar_arrive_named(2 - t, 256);
                 tc_fence_before();
                 mbar_arrive_warp(&bars->s_free[t]);      // the scores are in registers: S may be overwritten
                 float m_q[4];
@@ -1375,16 +1470,17 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 }
                 const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
                 MHA_TRACE(t, j, 4);
-                // The P tile is free once P V of the previous block has read it.  MODE bit 2: the first two
-                // 32-key chunks are exponentiated into registers before that wait (the product finishes ~500
-                // cycles after the row maximum is known), and stored behind it.
-                constexpr bool kLateWait = (MODE & 4) != 0;
-                if (!kLateWait && j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
-                MHA_TRACE(t, j, 5);
+                // The P tile is free once P V of the previous block has read it.
+                if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
                 float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 uint32_t pk_all[4][16];
-                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half q / 2
+                // 32 keys = 16 packed columns of the row's TMEM lane (MODE bit 4), or 64 bytes = four 16-byte chunks of
+                // the row's 128-byte line in key half q / 2 of the shared P tile
                 auto store_chunk = [&](int q) {
+                    if (MODE & 16) {
+                        tmem_st16(tmem + 384 + 64 * t + lane_base + 16 * q, pk_all[q]);
+                        return;
+                    }
                     unsigned char* pr = prow + (q >> 1) * kTileBytes;
 #pragma unroll
                     for (int q4 = 0; q4 < 4; ++q4) {
@@ -1393,82 +1489,83 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             make_uint4(pk_all[q][4 * q4], pk_all[q][4 * q4 + 1], pk_all[q][4 * q4 + 2], pk_all[q][4 * q4 + 3]);
                     }
                 };
+                if (!DROP && (MODE & 2)) {
+                    // x = s * scale - max in place, packed; no XU work yet
+                    const uint64_t c2 = pack_f32x2(c, c);
+                    const uint64_t mc2 = pack_f32x2(-mc, -mc);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint32_t (&pk)[16] = pk_all[q];
-                    if (kLateWait && q == 2) {
-                        if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
-                        store_chunk(0);
-                        store_chunk(1);
-                    }
-                    if (DROP) {
-#pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
-                                                       a.seed_lo, a.seed_hi);
-#pragma unroll
-                            for (int i = 0; i < 16; i += 2) {
-                                float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
-                                float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i + 1]), c, -mc));
-                                lsum[q] += p0 + p1;
-                                p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
-                                p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
-                                const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                                pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                            }
-                        }
-                    } else if (MODE & 2) {
-                        const uint64_t c2 = pack_f32x2(c, c);
-                        const uint64_t mc2 = pack_f32x2(-mc, -mc);
-                        uint64_t ls2 = pack_f32x2(0.0f, 0.0f);
+                    for (int q = 0; q < 4; ++q) {
 #pragma unroll
                         for (int i = 0; i < 32; i += 2) {
                             float x0, x1;
-                            const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1])), c2, mc2);
-                            unpack_f32x2(x2, x0, x1);
-                            if (((i >> 1) & 3) < POLY) {
-                                // 2^x on the FMA pipe for POLY of every 4 pairs (the XU pipe does 16 exponentials per
-                                // clock and SM, the bound of this loop): x = n + f, n = round(x), |f| <= 1/2,
-                                // 2^f by a cubic (7.5e-5 relative, below the bf16 rounding of P), n added to the
-                                // exponent field.  The magic constant leaves n in the low mantissa bits of tt.
-                                const uint64_t xc = pack_f32x2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
-                                const uint64_t tt = add_f32x2(xc, pack_f32x2(12582912.0f, 12582912.0f));
-                                const uint64_t nn = add_f32x2(tt, pack_f32x2(-12582912.0f, -12582912.0f));
-                                const uint64_t ff = fma_f32x2(nn, pack_f32x2(-1.0f, -1.0f), xc);
-                                uint64_t pp2 = fma_f32x2(pack_f32x2(0.0551716685f, 0.0551716685f), ff, pack_f32x2(0.2426111251f, 0.2426111251f));
-                                pp2 = fma_f32x2(pp2, ff, pack_f32x2(0.6932609677f, 0.6932609677f));
-                                pp2 = fma_f32x2(pp2, ff, pack_f32x2(0.9999280572f, 0.9999280572f));
-                                float p0, p1, t0, t1;
-                                unpack_f32x2(pp2, p0, p1);
-                                unpack_f32x2(tt, t0, t1);
-                                x0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
-                                x1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
-                            } else {
-                                x0 = ex2_approx(x0);
-                                x1 = ex2_approx(x1);
-                            }
-                            ls2 = add_f32x2(ls2, pack_f32x2(x0, x1));
-                            pk[i >> 1] = cvt_bf16x2(x0, x1);
+                            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1])), c2, mc2), x0, x1);
+                            r[q][i] = __float_as_uint(x0);
+                            r[q][i + 1] = __float_as_uint(x1);
+                        }
+                    }
+                    if (pp) bar_sync_named(1 + t, 256);          // this tile's turn on the XU pipe
+                    MHA_TRACE(t, j, 5);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint64_t ls2 = pack_f32x2(0.0f, 0.0f);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2_approx(__uint_as_float(r[q][i]));
+                            const float p1 = ex2_approx(__uint_as_float(r[q][i + 1]));
+                            ls2 = add_f32x2(ls2, pack_f32x2(p0, p1));
+                            pk_all[q][i >> 1] = cvt_bf16x2(p0, p1);
                         }
                         float l0, l1;
                         unpack_f32x2(ls2, l0, l1);
                         lsum[q] = l0 + l1;
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            const uint32_t w = ex2_bf16x2(fmaf(__uint_as_float(r[q][i]), c, -mc), fmaf(__uint_as_float(r[q][i + 1]), c, -mc));
-                            pk[i >> 1] = w;
-                            // the normaliser is the sum of the probabilities P V really uses: the bf16 values
-                            lsum[q] += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
-                        }
+                        store_chunk(q);
                     }
-                    if (!kLateWait || q >= 2) store_chunk(q);
+                } else {
+                    if (pp) bar_sync_named(1 + t, 256);
+                    MHA_TRACE(t, j, 5);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t (&pk)[16] = pk_all[q];
+                        if (DROP) {
+#pragma unroll
+                            for (int g = 0; g < 2; ++g) {
+                                const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                           a.seed_lo, a.seed_hi);
+#pragma unroll
+                                for (int i = 0; i < 16; i += 2) {
+                                    float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
+                                    float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i + 1]), c, -mc));
+                                    lsum[q] += p0 + p1;
+                                    p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                                    p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                                    pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                const uint32_t w = ex2_bf16x2(fmaf(__uint_as_float(r[q][i]), c, -mc), fmaf(__uint_as_float(r[q][i + 1]), c, -mc));
+                                pk[i >> 1] = w;
+                                // the normaliser is the sum of the probabilities P V really uses: the bf16 values
+                                lsum[q] += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+                            }
+                        }
+                        store_chunk(q);
+                    }
                 }
+                if (pp && (t == 0 || j + 1 < nturn)) bar_arrive_named(2 - t, 256);
                 l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
                 MHA_TRACE(t, j, 6);
-                fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
+                if (MODE & 16) {
+                    tmem_st_wait();
+                    tc_fence_before();
+                } else {
+                    fence_proxy_async();          // P (generic proxy) -> visible to the tensor core (async proxy)
+                }
                 mbar_arrive_warp(&bars->p_full[t]);
                 MHA_TRACE(t, j, 7);
+                MHA_TRACE_WARP(t, j, 12);
             }
             // epilogue
             mbar_wait(&bars->pv_full[t], (nbt - 1) & 1);
@@ -1576,7 +1673,7 @@ mha_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     if (warp == 8) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
@@ -1592,7 +1689,7 @@ mha_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
     } else if (warp == 9) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (elect_one_sync()) {
             constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);
             constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);
@@ -1774,7 +1871,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     if (warp == kTmaWarp) {
         // ===== TMA producer =====
-        if (lane == 0 && nsteps > 0) {
+        if (nsteps > 0 && elect_one_sync()) {
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_do);
             mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileBytes);
@@ -1792,7 +1889,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // ===== MMA issuer =====
         // Order on the tensor pipe: S/dP of tile it+1 go BEFORE dV/dK/dQ of tile it, so the softmax
         // warps can start on tile it+1 while the three accumulating products of tile it run.
-        if (lane == 0 && nsteps > 0) {
+        if (nsteps > 0 && elect_one_sync()) {
             constexpr uint32_t id_s = make_idesc(kBM, kBN, 0, 0);     // S  = Q K^T   / dP = dO V^T
             constexpr uint32_t id_t = make_idesc(kBN, kD, 1, 1);      // dV = P^T dO  / dK = dS^T Q  (A and B MN-major)
             constexpr uint32_t id_q = make_idesc(kBM, kD, 0, 1);      // dQ = dS K    (A K-major, B MN-major)
@@ -2142,35 +2239,33 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);
     a.seed_lo = (uint32_t)seed;
     a.seed_hi = (uint32_t)(seed >> 32);
-    // "mha_variant": 0 = auto (3), 1 = one tile per CTA with four softmax warps, 2 = two tiles per CTA
-    // in ping-pong, 3 = one tile per CTA with eight softmax warps and O accumulated in TMEM.
-    // Dropout exists in variant 3 only.
+    // "mha_variant": 0 = auto (21), 1 = one tile per CTA with four softmax warps, 2 = two tiles per CTA
+    // in ping-pong, 3 = one tile per CTA with eight softmax warps and O accumulated in TMEM, 4 = 3 with P in
+    // tensor memory, 8 = two tiles per CTA, one thread per row, scores read once, 10 = 8 with packed f32x2
+    // arithmetic, 21 = 10 with the XU token, P in tensor memory and one MMA issuer per tile (measured at
+    // L = 2048: 550 / 550 / 603 / 687 TFLOP/s for 3 / 8 / 10 / 21).  Dropout exists in variants 3 and 21.
     const int variant = get_opt("mha_variant");
-    if (a.drop_thresh > 0) {
+    if (a.drop_thresh > 0 && variant != 21) {   // with dropout the two-threads-per-row kernel wins (397 vs 312 TFLOP/s: Philox per element)
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
-    } else if (variant >= 8 && variant <= 15) {
+    } else if (variant == 0 || variant == 8 || variant == 10 || variant == 21) {
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
-#define ASR_LAUNCH_FWD8(MODE, POLY)                                                                                           \
+#define ASR_LAUNCH_FWD8(DR, MODE)                                                                                             \
     do {                                                                                                                      \
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false, MODE, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); \
-        mha_fwd8_kernel<false, MODE, POLY><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);                             \
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<DR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); \
+        mha_fwd8_kernel<DR, MODE><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);                                      \
     } while (0)
-        if (variant == 8) ASR_LAUNCH_FWD8(0, 0);
-        else if (variant == 9) ASR_LAUNCH_FWD8(1, 0);
-        else if (variant == 10) ASR_LAUNCH_FWD8(2, 0);
-        else if (variant == 11) ASR_LAUNCH_FWD8(3, 0);
-        else if (variant == 12) ASR_LAUNCH_FWD8(6, 0);
-        else if (variant == 13) ASR_LAUNCH_FWD8(6, 1);
-        else if (variant == 14) ASR_LAUNCH_FWD8(6, 2);
-        else ASR_LAUNCH_FWD8(2, 1);
+        if (a.drop_thresh > 0) ASR_LAUNCH_FWD8(true, 51);
+        else if (variant == 8) ASR_LAUNCH_FWD8(false, 0);
+        else if (variant == 10) ASR_LAUNCH_FWD8(false, 2);
+        else ASR_LAUNCH_FWD8(false, 51);
 #undef ASR_LAUNCH_FWD8
     } else if (variant == 4) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd4Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd4_kernel<false><<<grid, kFwd4Threads, kFwd4Smem, st>>>(tq, tk, tv, a);
-    } else if (variant == 0 || variant == 3) {   // measured: the eight-softmax-warp kernel wins at every length (534 vs 467 TFLOP/s at L=2048)
+    } else if (variant == 3) {
         ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
         mha_fwd3_kernel<false><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
@@ -2201,7 +2296,7 @@ extern "C" int asr_mha_fwd_dropout_bf16(const void* q, const void* k, const void
 
 #ifdef ASR_MHA_TRACE
 extern "C" int asr_debug_mha_trace(long long* host_out) {
-    return (int)cudaMemcpyFromSymbol(host_out, asr::g_mha_trace, sizeof(long long) * 2 * 16 * 12);
+    return (int)cudaMemcpyFromSymbol(host_out, asr::g_mha_trace, sizeof(long long) * 2 * 16 * 20);
 }
 #endif
 

@@ -15,7 +15,9 @@ MHA = load_golden("mha")
 CASES = ["self_pad", "self_causal", "cross", "nomask"]
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (1, 2), (2, 4), (3, 0), (4, 0), (8, 0), (9, 0), (11, 0), (12, 0), (14, 0)], ids=["auto", "one_tile_bwd8w", "two_tile_pingpong_bwd16w", "eight_softmax_warps", "p_in_tmem", "row_per_thread_single_read", "single_read_token", "single_read_token_packed", "single_read_late_wait", "single_read_poly_exp2"])
+@pytest.fixture(autouse=True, params=[(0, 0), (1, 2), (2, 4), (3, 0), (4, 0), (8, 0), (10, 0), (21, 0)],
+                ids=["auto", "one_tile_bwd8w", "two_tile_pingpong_bwd16w", "eight_softmax_warps", "p_in_tmem", "row_per_thread_single_read",
+                     "single_read_packed", "single_read_token_tmem_p_two_issuers"])
 def fwd_variant(request):
     """Forward kernel variant (one 128-query tile per CTA, or two tiles in ping-pong) and the number
     of softmax-backward warp groups (16 warps by default, 8 is the other template instance)."""
