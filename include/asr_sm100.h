@@ -54,11 +54,13 @@ int         asr_device_ok(void);
  * overlaps the HBM-bound row kernels of the next slice; 0 = auto, 1 = no slicing,
  * max 8; results are bit-identical for every value), "ctc_finish_per_slice"
  * (asr_ctc_finish_f32: 0 = one apply launch after all lattices, 1 = slice by
- * slice), "mha_variant" (0 = auto = 3,
+ * slice), "mha_variant" (0 = auto = 21 without dropout, 3 with,
  * 1 = one tile per CTA with four softmax warps, 2 = two-tile ping-pong, 3 = eight
  * softmax warps per tile, O accumulated in TMEM with lazy rescale, 4 = as 3 with P
  * kept in TMEM as the A operand of P V, 8 = two tiles per CTA sharing K/V, one thread
- * per query row, scores read from TMEM once), "mha_bwd_groups" (softmax-backward
+ * per query row, scores read from TMEM once, 10 = 8 with packed f32x2 arithmetic,
+ * 21 = 10 with the tiles taking turns on the XU pipe, P in TMEM and one MMA issuer
+ * per tile), "mha_bwd_groups" (softmax-backward
  * warps per CTA = 4 * groups; 0 = default (4 groups), 2). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);
