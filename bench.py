@@ -329,6 +329,39 @@ def assigner_microbench(pkg, w, inp, device, iters=5):
     return res
 
 
+def spec_aug_microbench(pkg, device, iters=5):
+    """SpecAugment on the device on a batch of LFR-stacked fbank of the bench size
+    (B=256 x T=1600 x 320 bins, ragged, two bands + two spans per utterance).  HBM-bound: the batch is read
+    once for the two means; only the masked cells are written."""
+    import importlib
+    ops = importlib.import_module("end-to-end_asr_pytorch_b200.ops")
+    B, T, V, R = 256, 1600, 320, 2
+    g = torch.Generator(device=device).manual_seed(8)
+    x = torch.randn(B, T, V, device=device, generator=g)
+    lens = torch.randint(T // 2, T + 1, (B,), device=device, generator=g)
+    fw = torch.randint(0, 27, (R, B), device=device, generator=g)
+    f0 = (torch.rand(R, B, device=device, generator=g) * (V - fw)).long()
+    tw = torch.randint(0, 40, (R, B), device=device, generator=g)
+    t0 = (torch.rand(R, B, device=device, generator=g) * (lens[None] - tw)).long()
+    masked = int((T * fw.sum() + V * tw.sum()).item())
+    nbytes = 4 * B * T * V + 4 * masked
+
+    def run():
+        ops.spec_aug_apply(x, lens, f0, fw, t0, tw)
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9,
+            "shape": "B=%d T=%d V=%d, %d bands + %d spans per utterance" % (B, T, V, R, R)}
+
+
 def attention_microbench(pkg, device, iters=5):
     """tcgen05 attention core, forward and backward, on the SURVEY 8(d) microbench shape
     (B*heads = 128, L = 2048, d = 64, no mask); CUDA events, inputs >> L2 per call not needed
@@ -664,6 +697,10 @@ def main():
             kernels.append({"kernel": n, "bound": "hbm", "ms": asg[n]["ms"], "algorithmic_bytes": asg[n]["algorithmic_bytes"],
                             "GBps": asg[n]["GBps"], "frac_of_hbm_peak": asg[n]["GBps"] / peaks["hbm_gbs"],
                             "in_timed_step": False, "note": "SURVEY 8(f2): assigner tail + alpha scaling, next-row kernel"})
+        sa = spec_aug_microbench(pkg, device)
+        kernels.append({"kernel": "spec_aug", "bound": "hbm", "ms": sa["ms"], "algorithmic_bytes": sa["algorithmic_bytes"],
+                        "GBps": sa["GBps"], "frac_of_hbm_peak": sa["GBps"] / peaks["hbm_gbs"], "shape": sa["shape"],
+                        "in_timed_step": False, "note": "SURVEY 8(f4): SpecAugment, three launches incl. the means"})
         att = attention_microbench(pkg, device)
         for n in ("mha_fwd", "mha_bwd"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": att[n]["ms"], "TFLOPs": att[n]["TFLOPs"],

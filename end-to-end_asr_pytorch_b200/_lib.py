@@ -34,6 +34,8 @@ SIGNATURES = {
     "asr_cif_alpha_bwd_f32": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int,
                                        _vp, _vp, _vp, _vp, _c_size_t, _vp]),
     "asr_lfr_f32": (_c_int, [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp]),
+    "asr_spec_aug_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "asr_spec_aug_f32": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "asr_ctc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
     "asr_ctc_fwd_bwd_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _vp, _vp, _vp, _c_size_t, _vp]),

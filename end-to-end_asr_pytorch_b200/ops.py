@@ -143,6 +143,33 @@ def build_lfr_features(features, lens, m, n):
     return out, out_lens
 
 
+def spec_aug_apply(features, lens, f0, fw, t0, tw):
+    """The masking part of spec_aug (utils/utils.py:168-194) on the device, IN PLACE: features [B,T,V] f32,
+    lens [B], and the drawn frequency bands (f0, fw) / time spans (t0, tw) as [R,B] integer tensors.  Cells in
+    a time span get the per-bin mean over time (sum / lens), other cells in a frequency band the per-frame
+    mean over bins, both of the batch as it was on entry.  Returns features.  No gradient (the reference
+    masks the input features, which carry none)."""
+    _require_cuda("features", features, torch.float32)
+    if features.dim() != 3 or not features.is_contiguous():
+        raise ValueError("spec_aug_apply: features must be a contiguous [B, T, V] tensor (masked in place)")
+    B, T, V = features.shape
+    dev = features.device
+    lens = lens.to(device=dev, dtype=torch.int32).contiguous()
+    R = f0.shape[0] if f0.dim() == 2 else 0
+    for m in (f0, fw, t0, tw):
+        if m.dim() != 2 or tuple(m.shape) != (R, B):
+            raise ValueError("spec_aug_apply: the mask arrays must all be [R, B]")
+    # one [4,R,B] i32 block (one stack + one cast instead of four casts)
+    masks = torch.stack([m.to(dev) for m in (f0, fw, t0, tw)]).to(torch.int32).contiguous()
+    wsb = _lib.lib().asr_spec_aug_workspace_bytes(B, T, V)
+    ws = torch.empty((wsb + 3) // 4, dtype=torch.float32, device=dev)
+    base, step = masks.data_ptr(), R * B * 4
+    with torch.cuda.device(dev):
+        check(_lib.lib().asr_spec_aug_f32(ptr(features), ptr(lens), base, base + step, base + 2 * step, base + 3 * step,
+                                          int(R), B, T, V, ptr(ws), wsb, stream_ptr()), "asr_spec_aug_f32")
+    return features
+
+
 def cif_label_len(alphas):
     """L of cif_model.py:95-96: max_b int(round(sum_t alphas)) - one host sync, like the reference."""
     return int(torch.round(alphas.sum(-1)).int().max().item())

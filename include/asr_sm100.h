@@ -151,6 +151,24 @@ int asr_cif_alpha_bwd_f32(const float* x, const float* w, const int* len,
 int asr_lfr_f32(const float* in, const int* len, int B, int T, int D, int m, int n,
                 float* out, int* out_len, void* stream);
 
+/* ---- input side: SpecAugment ------------------------------ */
+/*
+ * Replaces the masking loops of spec_aug, /root/reference/src/utils/utils.py:168-194, for a
+ * padded batch on the device, in place.  The caller draws the bands / spans (the reference
+ * draws them with torch.rand, utils.py:178-181 and 186-189; the host mirror makes the same
+ * calls in the same order) and passes them as [R,B] i32 arrays:
+ *   freq_mean[b,t] = mean_v feats[b,t,:]            time_mean[b,v] = sum_t feats[b,:,v] / lens[b]
+ *   feats[b,t,v]   = time_mean[b,v]  if t0[r,b] <= t < t0[r,b]+tw[r,b] for some r
+ *                    freq_mean[b,t]  else if f0[r,b] <= v < f0[r,b]+fw[r,b] for some r
+ * (both means of the batch as it was on entry; identical to the reference's mask-by-mask
+ * order because every mask of a family writes the same value and the time spans are
+ * applied last).  Bands / spans are clipped to [0,V) / [0,T).  V <= 1024.  The workspace
+ * holds the two means and the per-64-frame column sums.
+ */
+size_t asr_spec_aug_workspace_bytes(int B, int T, int V);
+int asr_spec_aug_f32(float* feats, const int* lens, const int* f0, const int* fw, const int* t0, const int* tw,
+                     int R, int B, int T, int V, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at

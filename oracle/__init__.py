@@ -25,7 +25,7 @@ on the reference's call sites (`src/transformer/loss.py:34-48`,
 reduction, zero_infinity=False) through the golden vectors above.
 """
 from .cif_oracle import cif_forward, cif_backward, cif_schedule, cif_scale_alphas  # noqa: F401
-from .cif_oracle import assigner_tail_forward, assigner_tail_backward, build_lfr_features  # noqa: F401
+from .cif_oracle import assigner_tail_forward, assigner_tail_backward, build_lfr_features, spec_aug_apply  # noqa: F401
 from .ctc_oracle import ctc_loss_and_grad  # noqa: F401
 from .mha_oracle import mha_core_forward, mha_core_backward, mha_module_forward  # noqa: F401
 from .mask_oracle import (sequence_mask, get_attn_pad_mask, get_subsequent_mask,  # noqa: F401

@@ -197,3 +197,22 @@ def cif_backward(hidden, alphas, threshold, g_out, dtype=np.float32):
             if fired:
                 S = S + gcur
     return g_hidden, g_alpha
+
+
+def spec_aug_apply(features, lens, f0, fw, t0, tw):
+    """Masking loops of spec_aug, /root/reference/src/utils/utils.py:168-194, with the drawn bands / spans given
+    ([R,B] integer arrays): both means from the batch as it was on entry (:171-173), all frequency bands first
+    (:176-183), then all time spans (:185-192), each as the reference's slice assignment.  Returns a copy."""
+    x = np.array(features, dtype=np.float32, copy=True)
+    B, T, V = x.shape
+    freq_means = x.mean(axis=-1, dtype=np.float32)
+    time_means = x.sum(axis=1, dtype=np.float32) / np.asarray(lens, dtype=np.float32)[:, None]
+    for r in range(np.asarray(f0).shape[0]):
+        for b in range(B):
+            a, w = int(f0[r][b]), int(fw[r][b])
+            x[b, :, a:a + w] = freq_means[b][:, None]
+    for r in range(np.asarray(t0).shape[0]):
+        for b in range(B):
+            a, w = int(t0[r][b]), int(tw[r][b])
+            x[b, a:a + w, :] = time_means[b][None, :]
+    return x

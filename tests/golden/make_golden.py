@@ -191,6 +191,42 @@ def make_assigner_tail(uutils):
     print("assigner tail: done")
 
 
+def make_spec_aug(uutils):
+    """utils/utils.py:168-194 executed on CPU; the torch.rand draws are recorded so that the device kernels and
+    the oracle can be fed the very same bands / spans, and the generator seed so that the host mirror's draws
+    (utils.spec_aug_draw) can be checked against them."""
+    out = {}
+    real_rand = torch.rand
+    for name, (B, T, V, cfg, seed) in {"a": (4, 60, 80, "2-27-2-40", 5), "b": (2, 90, 320, "2-27-2-40", 6),
+                                       "c": (2, 33, 40, "1-10-3-8", 7), "d": (5, 100, 33, "2-5-1-30", 8)}.items():
+        g = torch.Generator().manual_seed(100 + seed)
+        x = torch.randn(B, T, V, generator=g)
+        lens = torch.randint(T // 2 + 1, T + 1, (B,), generator=g)
+        lens[0] = T
+        for b in range(B):
+            x[b, int(lens[b]):] = 0.0          # "features are padded with zeros" (utils.py:173)
+        draws = []
+
+        def recording_rand(*a, **k):
+            r = real_rand(*a, **k)
+            draws.append(r.clone())
+            return r
+        torch.manual_seed(seed)
+        torch.rand = recording_rand
+        try:
+            y, _ = uutils.spec_aug(x.clone(), lens, cfg)
+        finally:
+            torch.rand = real_rand
+        out[name + "_x"] = x.numpy()
+        out[name + "_lens"] = lens.numpy()
+        out[name + "_cfg"] = np.array([int(i) for i in cfg.split("-")])
+        out[name + "_seed"] = np.array([seed])
+        out[name + "_draws"] = torch.stack(draws).numpy()      # [4 * time_mask_num, B] in call order
+        out[name + "_y"] = y.numpy()
+    np.savez_compressed(os.path.join(HERE, "spec_aug.npz"), **out)
+    print("spec_aug: done")
+
+
 def make_lfr():
     """utils/data.py:191-218 executed on a few utterances (the function is pure numpy)."""
     import importlib
@@ -400,6 +436,7 @@ def main():
     make_cif_glue()
     make_assigner_tail(uutils)
     make_lfr()
+    make_spec_aug(uutils)
     make_ctc(tloss, closs)
     make_qua(tloss)
     make_mha(attention, uutils)

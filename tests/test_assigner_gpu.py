@@ -155,3 +155,74 @@ def test_lfr_ragged_batch_vs_oracle(B, T, D, m, n):
         assert int(yl[b]) == ref.shape[0]
         np.testing.assert_array_equal(to_np(y[b, :ref.shape[0]]).view(np.uint32), ref.view(np.uint32))
         assert not to_np(y[b, ref.shape[0]:]).any()          # zero beyond the utterance
+
+
+# ---- SpecAugment -------------------------------------------------------------------
+def test_spec_aug_golden():
+    """The reference's spec_aug run on CPU with recorded draws (tests/golden/make_golden.py: make_spec_aug)."""
+    from test_oracle_golden import _spec_aug_masks
+    ops = pkg("ops")
+    g = load_golden("spec_aug")
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        masks = [torch.as_tensor(m) for m in _spec_aug_masks(g, name)]
+        x = torch.as_tensor(g[name + "_x"]).cuda()
+        y = ops.spec_aug_apply(x, torch.as_tensor(g[name + "_lens"]), *masks)
+        assert y.data_ptr() == x.data_ptr()                     # in place, like the reference
+        ref = g[name + "_y"]
+        same = ref == g[name + "_x"]
+        got = to_np(y)
+        np.testing.assert_array_equal(got[same].view(np.uint32), ref[same].view(np.uint32))
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("B,T,V,R", [(6, 500, 320, 2), (3, 167, 80, 2), (2, 70, 33, 3), (4, 1600, 320, 1), (2, 64, 1024, 2)])
+def test_spec_aug_ragged_vs_oracle(B, T, V, R):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(B * T + V)
+    x = torch.randn(B, T, V, generator=gen)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=gen)
+    lens[0] = T
+    for b in range(B):
+        x[b, int(lens[b]):] = 0.0
+    fw = torch.randint(0, min(27, V), (R, B), generator=gen)
+    f0 = (torch.rand(R, B, generator=gen) * (V - fw)).long()
+    tw = torch.randint(0, 40, (R, B), generator=gen)
+    t0 = (torch.rand(R, B, generator=gen) * (lens[None] - tw)).long()
+    fw[0, 0] = 0                                               # an empty band and an empty span
+    tw[-1, -1] = 0
+    ref = oracle.spec_aug_apply(x.numpy(), lens.numpy(), f0.numpy(), fw.numpy(), t0.numpy(), tw.numpy())
+    y = to_np(ops.spec_aug_apply(x.clone().cuda(), lens, f0, fw, t0, tw))
+    same = ref == x.numpy()
+    np.testing.assert_array_equal(y[same].view(np.uint32), ref[same].view(np.uint32))
+    np.testing.assert_allclose(y, ref, rtol=1e-5, atol=3e-6)
+    # run-to-run bit reproducibility (fixed summation order, no atomics)
+    y2 = to_np(ops.spec_aug_apply(x.clone().cuda(), lens, f0, fw, t0, tw))
+    np.testing.assert_array_equal(y.view(np.uint32), y2.view(np.uint32))
+
+
+def test_spec_aug_drop_in_signature():
+    """utils.spec_aug(padded_features, feature_lengths, config) as cif_model.py:33 calls it: in place, returns
+    (features, lengths); its masks are the ones spec_aug_draw yields for the same generator state."""
+    uu = pkg("utils.utils")
+    B, T, V = 4, 120, 80
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, T, V, generator=gen).cuda()
+    lens = torch.tensor([120, 100, 90, 64]).cuda()
+    x0 = x.clone()
+    torch.manual_seed(11)
+    y, yl = uu.spec_aug(x, lens, "2-27-2-40")
+    assert y is x and yl is lens
+    torch.manual_seed(11)
+    f0, fw, t0, tw = uu.spec_aug_draw(B, V, lens, "2-27-2-40", x.device)
+    ref = oracle.spec_aug_apply(to_np(x0), to_np(lens), to_np(f0), to_np(fw), to_np(t0), to_np(tw))
+    np.testing.assert_allclose(to_np(y), ref, rtol=1e-5, atol=3e-6)
+    assert (to_np(y) != to_np(x0)).any()
+
+
+def test_spec_aug_rejects_cpu_and_wide_features():
+    ops = pkg("ops")
+    z = torch.zeros(1, 1, dtype=torch.long)
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        ops.spec_aug_apply(torch.zeros(1, 4, 8), torch.tensor([4]), z, z, z, z)
+    with pytest.raises(RuntimeError):
+        ops.spec_aug_apply(torch.zeros(1, 4, 1025).cuda(), torch.tensor([4]), z, z, z, z)

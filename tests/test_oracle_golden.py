@@ -72,6 +72,55 @@ def test_lfr_matches_reference():
         np.testing.assert_array_equal(y.view(np.uint32), g[name + "_y"].view(np.uint32))
 
 
+def _spec_aug_masks(g, name):
+    """Bands / spans from the recorded torch.rand draws, with the reference's arithmetic (utils.py:178-181,186-189)."""
+    import torch
+    draws = torch.as_tensor(g[name + "_draws"])
+    lens = torch.as_tensor(g[name + "_lens"])
+    _, fwid, tnum, twid = (int(v) for v in g[name + "_cfg"])
+    V = g[name + "_x"].shape[2]
+    f0, fw, t0, tw = [], [], [], []
+    for r in range(tnum):
+        fs = (fwid * draws[2 * r]).long()
+        fw.append(fs)
+        f0.append(((V - fs).float() * draws[2 * r + 1]).long())
+    for r in range(tnum):
+        ts = (twid * draws[2 * tnum + 2 * r]).long()
+        tw.append(ts)
+        t0.append(((lens - ts).float() * draws[2 * tnum + 2 * r + 1]).long())
+    return tuple(torch.stack(m).numpy() for m in (f0, fw, t0, tw))
+
+
+def test_spec_aug_matches_reference():
+    """utils/utils.py:168-194 executed on CPU with its torch.rand draws recorded
+    (make_golden.py: make_spec_aug).  Unmasked cells bit-exact, the means to fp32 summation-order accuracy."""
+    g = load_golden("spec_aug")
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        f0, fw, t0, tw = _spec_aug_masks(g, name)
+        y = oracle.spec_aug_apply(g[name + "_x"], g[name + "_lens"], f0, fw, t0, tw)
+        ref = g[name + "_y"]
+        same = ref == g[name + "_x"]
+        assert 0.02 < 1.0 - same.mean() < 0.9                   # the fixture masks something, not everything
+        np.testing.assert_array_equal(y[same].view(np.uint32), ref[same].view(np.uint32))
+        np.testing.assert_allclose(y, ref, rtol=1e-5, atol=2e-6)
+
+
+def test_spec_aug_draws_follow_the_reference():
+    """The host mirror makes the reference's torch.rand calls in the reference's order: same generator state,
+    same bands / spans (host logic only - nothing is launched)."""
+    import torch
+    from helpers import pkg
+    uu = pkg("utils.utils")
+    g = load_golden("spec_aug")
+    for name in sorted({k.split("_")[0] for k in g.files}):
+        x = g[name + "_x"]
+        cfg = "-".join(str(int(v)) for v in g[name + "_cfg"])
+        torch.manual_seed(int(g[name + "_seed"][0]))
+        got = uu.spec_aug_draw(x.shape[0], x.shape[2], torch.as_tensor(g[name + "_lens"]), cfg, torch.device("cpu"))
+        for a, b in zip(got, _spec_aug_masks(g, name)):
+            np.testing.assert_array_equal(a.numpy(), b)
+
+
 def test_assigner_tail_matches_reference():
     """attentionAssigner.py:36-40 + cif_model.py:43-48, values and autograd gradients
     produced by the reference's own ops (tests/golden/make_golden.py: make_assigner_tail)."""
