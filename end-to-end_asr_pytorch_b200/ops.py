@@ -170,6 +170,49 @@ def spec_aug_apply(features, lens, f0, fw, t0, tw):
     return features
 
 
+def linear_act(x, weight, bias=None, relu=False):
+    """y = act(x W^T + b) on the tensor cores with the bias / ReLU fused into the epilogue (module.py:50,
+    attention.py:40-45): x [..., K] bf16, weight [N, K] bf16, bias [N] (any float dtype) -> [..., N] bf16.
+    Forward only (evaluation path); N % 128 == 0 and K % 64 == 0."""
+    _require_cuda("x", x, torch.bfloat16)
+    _require_cuda("weight", weight, torch.bfloat16)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != K:
+        raise ValueError("linear_act: weight must be [N, K] with K = x.shape[-1]")
+    x2 = x.detach().reshape(-1, K).contiguous()
+    w = weight.detach().contiguous()
+    b = None if bias is None else bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    y = torch.empty((x2.shape[0], N), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().asr_linear_act_bf16(ptr(x2), ptr(w), ptr(b), x2.shape[0], N, K, 1 if relu else 0, ptr(y), stream_ptr()),
+              "asr_linear_act_bf16")
+    return y.reshape(*x.shape[:-1], N)
+
+
+def linear_residual_layernorm(x, weight, bias, residual, ln_weight, ln_bias, eps=1e-5):
+    """y = LayerNorm(x W^T + b + residual) (module.py:50-52, attention.py:59-60 with dropout off): x [..., K] bf16,
+    weight [512, K] bf16, residual [..., 512] bf16, LayerNorm weight / bias [512] -> [..., 512] bf16.  Forward only."""
+    _require_cuda("x", x, torch.bfloat16)
+    _require_cuda("weight", weight, torch.bfloat16)
+    _require_cuda("residual", residual, torch.bfloat16)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != K or residual.shape[-1] != N or residual.shape[:-1] != x.shape[:-1]:
+        raise ValueError("linear_residual_layernorm: weight [N, K], residual [..., N] with x [..., K]")
+    x2 = x.detach().reshape(-1, K).contiguous()
+    r2 = residual.detach().reshape(-1, N).contiguous()
+    w = weight.detach().contiguous()
+    f32 = lambda t: None if t is None else t.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    b, g, be = f32(bias), f32(ln_weight), f32(ln_bias)
+    y = torch.empty((x2.shape[0], N), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().asr_linear_residual_layernorm_bf16(ptr(x2), ptr(w), ptr(b), ptr(r2), ptr(g), ptr(be), float(eps),
+                                                            x2.shape[0], N, K, ptr(y), stream_ptr()),
+              "asr_linear_residual_layernorm_bf16")
+    return y.reshape(*x.shape[:-1], N)
+
+
 def cif_label_len(alphas):
     """L of cif_model.py:95-96: max_b int(round(sum_t alphas)) - one host sync, like the reference."""
     return int(torch.round(alphas.sum(-1)).int().max().item())

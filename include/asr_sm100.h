@@ -169,6 +169,25 @@ size_t asr_spec_aug_workspace_bytes(int B, int T, int V);
 int asr_spec_aug_f32(float* feats, const int* lens, const int* f0, const int* fw, const int* t0, const int* tw,
                      int R, int B, int T, int V, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- linear layers with fused epilogues ------------------- */
+/*
+ * y = act(x W^T + bias): x [M,K] bf16, W [N,K] bf16 (torch Linear.weight as it is), bias [N]
+ * f32 or NULL, y [M,N] bf16, fp32 accumulation; relu != 0 applies max(.,0).  Replaces
+ * relu(w_1(x)) of PositionwiseFeedForward, /root/reference/src/transformer/module.py:50,
+ * and the w_qs / w_ks / w_vs projections of attention.py:40-45.  N % 128 == 0, K % 64 == 0.
+ */
+int asr_linear_act_bf16(const void* x, const void* w, const float* bias, int M, int N, int K, int relu,
+                        void* y, void* stream);
+/*
+ * y = LayerNorm(x W^T + bias + residual) * gamma + beta over the last dimension, N = 512:
+ * w_2 + residual + layer_norm of module.py:50-52 and fc + residual + layer_norm of
+ * attention.py:59-60 with the dropout between them off (evaluation or p = 0).  residual
+ * [M,512] bf16, gamma / beta [512] f32, eps as nn.LayerNorm (1e-5 by default).  K % 64 == 0.
+ */
+int asr_linear_residual_layernorm_bf16(const void* x, const void* w, const float* bias, const void* residual,
+                                       const float* gamma, const float* beta, float eps, int M, int N, int K,
+                                       void* y, void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at

@@ -1,0 +1,81 @@
+"""tcgen05 linear layers with fused epilogues vs a plain torch fp32 reference of the same op on
+the same bf16-rounded inputs (bf16 output: 2e-2 of the output scale)."""
+import pytest
+import torch
+
+from helpers import pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=2e-2):
+    a, b = a.float(), b.float()
+    scale = b.abs().max().item() + 1e-6
+    err = (a - b).abs().max().item()
+    assert err <= tol * scale, (err, scale)
+
+
+def _rand(shape, gen, std=1.0):
+    return (torch.randn(*shape, generator=gen) * std).cuda().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K,relu,with_bias", [(128, 128, 64, False, True), (256, 512, 512, True, True), (1000, 2048, 512, True, True),
+                                                  (77, 512, 2048, False, False), (10688, 2048, 512, True, True), (1, 128, 128, True, True)])
+def test_linear_act(M, N, K, relu, with_bias):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(M + N + K)
+    x, w = _rand((M, K), gen), _rand((N, K), gen, K ** -0.5)
+    b = torch.randn(N, generator=gen).cuda() if with_bias else None
+    y = ops.linear_act(x, w, b, relu=relu)
+    ref = torch.nn.functional.linear(x.float(), w.float(), b)
+    if relu:
+        ref = torch.relu(ref)
+    assert y.dtype == torch.bfloat16 and y.shape == (M, N)
+    _close(y, ref)
+
+
+def test_linear_act_leading_dims_and_errors():
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(3)
+    x, w = _rand((3, 50, 512), gen), _rand((512, 512), gen, 0.05)
+    y = ops.linear_act(x, w, None)
+    assert y.shape == (3, 50, 512)
+    _close(y, torch.nn.functional.linear(x.float(), w.float()))
+    with pytest.raises(RuntimeError):
+        ops.linear_act(_rand((4, 64), gen), _rand((100, 64), gen))          # N not a multiple of 128
+    with pytest.raises(RuntimeError):
+        ops.linear_act(_rand((4, 80), gen), _rand((128, 80), gen))          # K not a multiple of 64
+    with pytest.raises((RuntimeError, ValueError, TypeError)):
+        ops.linear_act(torch.zeros(4, 64, dtype=torch.bfloat16), w)          # CPU tensor: no fallback
+
+
+@pytest.mark.parametrize("M,K", [(128, 512), (300, 2048), (10688, 2048), (5, 64), (129, 512)])
+def test_linear_residual_layernorm(M, K):
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(M + K)
+    x, w, res = _rand((M, K), gen), _rand((512, K), gen, K ** -0.5), _rand((M, 512), gen)
+    b = torch.randn(512, generator=gen).cuda()
+    g = (1.0 + 0.1 * torch.randn(512, generator=gen)).cuda()
+    be = (0.1 * torch.randn(512, generator=gen)).cuda()
+    y = ops.linear_residual_layernorm(x, w, b, res, g, be, eps=1e-5)
+    ref = torch.nn.functional.layer_norm(torch.nn.functional.linear(x.float(), w.float(), b) + res.float(), (512,), g, be, 1e-5)
+    assert y.dtype == torch.bfloat16 and y.shape == (M, 512)
+    _close(y, ref)
+
+
+def test_feed_forward_block_matches_reference_module_math():
+    """PositionwiseFeedForward.forward (module.py:46-53) with dropout off: w_2(relu(w_1(x))) + residual -> LayerNorm."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(9)
+    B, T, d, di = 4, 167, 512, 2048
+    x = _rand((B, T, d), gen)
+    w1, b1 = _rand((di, d), gen, d ** -0.5), torch.randn(di, generator=gen).cuda() * 0.1
+    w2, b2 = _rand((d, di), gen, di ** -0.5), torch.randn(d, generator=gen).cuda() * 0.1
+    g, be = torch.ones(d).cuda(), torch.zeros(d).cuda()
+    h = ops.linear_act(x, w1, b1, relu=True)
+    y = ops.linear_residual_layernorm(h, w2, b2, x, g, be)
+    hr = torch.relu(torch.nn.functional.linear(x.float(), w1.float(), b1)).to(torch.bfloat16).float()   # the bf16 hand-over
+    ref = torch.nn.functional.layer_norm(torch.nn.functional.linear(hr, w2.float(), b2) + x.float(), (d,), g, be, 1e-5)
+    _close(y, ref)
+    with pytest.raises(RuntimeError):
+        ops.linear_residual_layernorm(h, _rand((256, di), gen), None, _rand((B, T, 256), gen), torch.ones(256).cuda(), torch.zeros(256).cuda())

@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Fused linear layers vs torch (cuBLAS + separate elementwise kernels): python tools/gemm_bench.py"""
+import os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import importlib
+ops = importlib.import_module("end-to-end_asr_pytorch_b200.ops")
+F = torch.nn.functional
+
+
+def timed(fn, n=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+g = torch.Generator(device="cuda").manual_seed(1)
+for M in (10688, 64 * 1600):
+    d, di = 512, 2048
+    x = torch.randn(M, d, device="cuda", generator=g).bfloat16()
+    w1 = (torch.randn(di, d, device="cuda", generator=g) * d ** -0.5).bfloat16(); b1 = torch.randn(di, device="cuda", generator=g)
+    w2 = (torch.randn(d, di, device="cuda", generator=g) * di ** -0.5).bfloat16(); b2 = torch.randn(d, device="cuda", generator=g)
+    gam, bet = torch.ones(d, device="cuda"), torch.zeros(d, device="cuda")
+    h = ops.linear_act(x, w1, b1, relu=True)
+    b1h, b2h = b1.bfloat16(), b2.bfloat16()
+    gamh, beth = gam.bfloat16(), bet.bfloat16()
+    rows = [("w_1 + bias + relu  [M,512]x[2048,512]", lambda: ops.linear_act(x, w1, b1, relu=True), lambda: torch.relu(F.linear(x, w1, b1h)), 2.0 * M * d * di),
+            ("w_2 + bias + residual + LayerNorm [M,2048]x[512,2048]", lambda: ops.linear_residual_layernorm(h, w2, b2, x, gam, bet),
+             lambda: F.layer_norm(F.linear(h, w2, b2h) + x, (d,), gamh, beth), 2.0 * M * d * di),
+            ("fc + bias + residual + LayerNorm [M,512]x[512,512]", lambda: ops.linear_residual_layernorm(x, w2[:, :512].contiguous(), b2, x, gam, bet),
+             lambda: F.layer_norm(F.linear(x, w2[:, :512].contiguous(), b2h) + x, (d,), gamh, beth), 2.0 * M * d * d)]
+    for name, ours, ref, flop in rows:
+        a, b = timed(ours), timed(ref)
+        print("M=%6d %-56s ours %.3f ms %6.0f TFLOP/s | torch %.3f ms %6.0f TFLOP/s" % (M, name, a, flop / a / 1e9, b, flop / b / 1e9), flush=True)
