@@ -362,6 +362,44 @@ def spec_aug_microbench(pkg, device, iters=5):
             "shape": "B=%d T=%d V=%d, %d bands + %d spans per utterance" % (B, T, V, R, R)}
 
 
+def linear_microbench(pkg, device, iters=10):
+    """Fused tcgen05 linear layers on the feed-forward block of the encoder at the bench batch
+    (M = 64 x 1600 frames, d_model 512, d_inner 2048), next to torch's cuBLAS + eager epilogue on the same tensors."""
+    import importlib
+    ops = importlib.import_module("end-to-end_asr_pytorch_b200.ops")
+    F = torch.nn.functional
+    M, d, di = 64 * 1600, 512, 2048
+    g = torch.Generator(device=device).manual_seed(9)
+    x = torch.randn(M, d, device=device, generator=g).bfloat16()
+    w1 = (torch.randn(di, d, device=device, generator=g) * d ** -0.5).bfloat16()
+    w2 = (torch.randn(d, di, device=device, generator=g) * di ** -0.5).bfloat16()
+    b1, b2 = torch.randn(di, device=device, generator=g), torch.randn(d, device=device, generator=g)
+    gam, bet = torch.ones(d, device=device), torch.zeros(d, device=device)
+    h = ops.linear_act(x, w1, b1, relu=True)
+    b1h, b2h, gamh, beth = b1.bfloat16(), b2.bfloat16(), gam.bfloat16(), bet.bfloat16()
+    rows = [("linear_bias_relu", lambda: ops.linear_act(x, w1, b1, relu=True), lambda: torch.relu(F.linear(x, w1, b1h))),
+            ("linear_residual_layernorm", lambda: ops.linear_residual_layernorm(h, w2, b2, x, gam, bet),
+             lambda: F.layer_norm(F.linear(h, w2, b2h) + x, (d,), gamh, beth))]
+    res = {}
+    for name, ours, ref in rows:
+        t = []
+        for fn in (ours, ref):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1) / iters)
+        flop = 2.0 * M * d * di
+        res[name] = {"ms": t[0], "TFLOPs": flop / t[0] / 1e9, "torch_ms": t[1], "torch_TFLOPs": flop / t[1] / 1e9,
+                     "shape": "M=%d K=%d N=%d bf16" % ((M, d, di) if name == "linear_bias_relu" else (M, di, d))}
+    return res
+
+
 def attention_microbench(pkg, device, iters=5):
     """tcgen05 attention core, forward and backward, on the SURVEY 8(d) microbench shape
     (B*heads = 128, L = 2048, d = 64, no mask); CUDA events, inputs >> L2 per call not needed
@@ -701,6 +739,12 @@ def main():
         kernels.append({"kernel": "spec_aug", "bound": "hbm", "ms": sa["ms"], "algorithmic_bytes": sa["algorithmic_bytes"],
                         "GBps": sa["GBps"], "frac_of_hbm_peak": sa["GBps"] / peaks["hbm_gbs"], "shape": sa["shape"],
                         "in_timed_step": False, "note": "SURVEY 8(f4): SpecAugment, three launches incl. the means"})
+        lin = linear_microbench(pkg, device)
+        for n in ("linear_bias_relu", "linear_residual_layernorm"):
+            kernels.append({"kernel": n, "bound": "tensor", "ms": lin[n]["ms"], "TFLOPs": lin[n]["TFLOPs"],
+                            "frac_of_bf16_peak": lin[n]["TFLOPs"] / peaks["bf16_tflops"], "shape": lin[n]["shape"],
+                            "torch_cublas_plus_eager_TFLOPs": lin[n]["torch_TFLOPs"], "in_timed_step": False,
+                            "note": "SURVEY 8(f3): tcgen05 GEMM with the epilogue fused, next-row kernel"})
         att = attention_microbench(pkg, device)
         for n in ("mha_fwd", "mha_bwd"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": att[n]["ms"], "TFLOPs": att[n]["TFLOPs"],

@@ -283,20 +283,30 @@ extern "C" int asr_linear_act_bf16(const void* x, const void* w, const float* bi
     ASR_REQUIRE(N % 128 == 0 && K % kGK == 0, "asr_linear_act_bf16: N=%d must be a multiple of 128 and K=%d of 64", N, K);
     ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "asr_linear_act_bf16: pointers must be 16-byte aligned");
     if (asr_device_ok() != 0) return 3;
-    constexpr int BN = 128, STAGES = 3;
-    constexpr int smem_bytes = STAGES * (kGATile + BN * kGK * 2) + 256;
-    CUtensorMap tx, tw;
-    if (make_rowmajor_bf16_map(&tx, x, M, K, kGM) || make_rowmajor_bf16_map(&tw, w, N, K, BN)) return 4;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid(N / BN, (M + kGM - 1) / kGM);
-    ASR_REQUIRE(grid.y <= 65535, "asr_linear_act_bf16: M=%d exceeds the grid limit", M);
-    if (relu) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_act_kernel<BN, STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        linear_act_kernel<BN, STAGES, true><<<grid, 192, smem_bytes, st>>>(tx, tw, bias, static_cast<__nv_bfloat16*>(y), M, N, K);
+    // "gemm_variant": 0 = auto, 1 = 128 x 128 tiles, 3-deep ring, two CTAs per SM; 2 = 128 x 256 tiles, 2-deep ring,
+    // two CTAs per SM; 3 = 128 x 256 tiles, 4-deep ring, one CTA per SM
+    int variant = get_opt("gemm_variant");
+    if (variant == 0) variant = 2;      // measured on the FFN shape (M = 102400): 611 / 691 / 548 TFLOP/s for 1 / 2 / 3; cuBLAS + eager bias/ReLU: 690
+    if (N % 256 != 0) variant = 1;
+#define ASR_LAUNCH_LINEAR(BN, STAGES, RL)                                                                                      \
+    do {                                                                                                                       \
+        constexpr int smem_bytes = STAGES * (kGATile + BN * kGK * 2) + 256;                                                    \
+        CUtensorMap tx, tw;                                                                                                    \
+        if (make_rowmajor_bf16_map(&tx, x, M, K, kGM) || make_rowmajor_bf16_map(&tw, w, N, K, BN)) return 4;                   \
+        const dim3 grid(N / BN, (M + kGM - 1) / kGM);                                                                          \
+        ASR_REQUIRE(grid.y <= 65535, "asr_linear_act_bf16: M=%d exceeds the grid limit", M);                                  \
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_act_kernel<BN, STAGES, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
+        linear_act_kernel<BN, STAGES, RL><<<grid, 192, smem_bytes, st>>>(tx, tw, bias, static_cast<__nv_bfloat16*>(y), M, N, K); \
+    } while (0)
+    if (variant == 2) {
+        if (relu) ASR_LAUNCH_LINEAR(256, 2, true); else ASR_LAUNCH_LINEAR(256, 2, false);
+    } else if (variant == 3) {
+        if (relu) ASR_LAUNCH_LINEAR(256, 4, true); else ASR_LAUNCH_LINEAR(256, 4, false);
     } else {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_act_kernel<BN, STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-        linear_act_kernel<BN, STAGES, false><<<grid, 192, smem_bytes, st>>>(tx, tw, bias, static_cast<__nv_bfloat16*>(y), M, N, K);
+        if (relu) ASR_LAUNCH_LINEAR(128, 3, true); else ASR_LAUNCH_LINEAR(128, 3, false);
     }
+#undef ASR_LAUNCH_LINEAR
     ASR_LAUNCH_CHECK();
     return 0;
 }

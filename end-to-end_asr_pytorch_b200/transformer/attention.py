@@ -23,7 +23,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ..ops import mha_core, mha_probs
+from ..ops import mha_core, mha_probs, linear_act, linear_residual_layernorm
+from .module import fused_linear_ok
 
 
 class MultiheadAttention(nn.Module):
@@ -63,9 +64,15 @@ class MultiheadAttention(nn.Module):
         len_k = k.size(1)
 
         residual = q
-        qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
-        kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
-        vh = self.w_vs(v).view(sz_b, len_k, n_head, d_v)
+        fused = fused_linear_ok(self, q, self.w_qs, self.w_ks, self.w_vs, self.fc) and k.dtype == q.dtype and v.dtype == q.dtype
+        if fused:      # evaluation in bf16: the projections as tcgen05 GEMMs with the bias in the epilogue
+            qh = linear_act(q, self.w_qs.weight, self.w_qs.bias).view(sz_b, len_q, n_head, d_k)
+            kh = linear_act(k, self.w_ks.weight, self.w_ks.bias).view(sz_b, len_k, n_head, d_k)
+            vh = linear_act(v, self.w_vs.weight, self.w_vs.bias).view(sz_b, len_k, n_head, d_v)
+        else:
+            qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
+            kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
+            vh = self.w_vs(v).view(sz_b, len_k, n_head, d_v)
 
         p_attn = self.attn_dropout_p if self.training else 0.0
         ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature),
@@ -75,6 +82,9 @@ class MultiheadAttention(nn.Module):
             attn = mha_probs(qh, kh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
 
         output = ctx.reshape(sz_b, len_q, n_head * d_v).to(q.dtype)
+        if fused:      # fc + bias + residual + LayerNorm in one kernel (the 512-wide row stays in tensor memory)
+            return linear_residual_layernorm(output, self.fc.weight, self.fc.bias, residual, self.layer_norm.weight,
+                                             self.layer_norm.bias, self.layer_norm.eps), attn
         output = self.dropout(self.fc(output))
         output = self.layer_norm(output + residual)
         return output, attn

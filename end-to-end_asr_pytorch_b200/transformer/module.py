@@ -37,4 +37,23 @@ class PositionwiseFeedForward(nn.Module):
         self.layer_norm = nn.LayerNorm(d_model)
 
     def forward(self, x):
+        if fused_linear_ok(self, x, self.w_1, self.w_2):
+            # evaluation in bf16: two tcgen05 GEMMs, bias + ReLU and bias + residual + LayerNorm in their epilogues
+            from ..ops import linear_act, linear_residual_layernorm
+            h = linear_act(x, self.w_1.weight, self.w_1.bias, relu=True)
+            return linear_residual_layernorm(h, self.w_2.weight, self.w_2.bias, x, self.layer_norm.weight,
+                                             self.layer_norm.bias, self.layer_norm.eps)
         return self.layer_norm(self.dropout(self.w_2(F.relu(self.w_1(x)))) + x)
+
+
+def fused_linear_ok(module, x, *linears):
+    """The fused tcgen05 linear layers are forward-only and bf16: used when no gradient is being recorded, the
+    dropout between the projection and the LayerNorm is off, and every shape fits (N % 128 == 0, K % 64 == 0,
+    LayerNorm width 512)."""
+    if torch.is_grad_enabled() or not x.is_cuda or x.dtype != torch.bfloat16:
+        return False
+    if module.training and getattr(module, "dropout", None) is not None and module.dropout.p > 0:
+        return False
+    if module.layer_norm.normalized_shape != (512,):
+        return False
+    return all(l.weight.dtype == torch.bfloat16 and l.out_features % 128 == 0 and l.in_features % 64 == 0 for l in linears)

@@ -60,7 +60,9 @@ int         asr_device_ok(void);
  * kept in TMEM as the A operand of P V, 8 = two tiles per CTA sharing K/V, one thread
  * per query row, scores read from TMEM once, 10 = 8 with packed f32x2 arithmetic,
  * 21 = 10 with the tiles taking turns on the XU pipe, P in TMEM and one MMA issuer
- * per tile), "mha_bwd_groups" (softmax-backward
+ * per tile), "gemm_variant" (asr_linear_act_bf16 tiles: 0 = auto = 2,
+ * 1 = 128 x 128 with a 3-deep ring, 2 = 128 x 256 with a 2-deep ring, both two CTAs per SM,
+ * 3 = 128 x 256 with a 4-deep ring, one CTA per SM), "mha_bwd_groups" (softmax-backward
  * warps per CTA = 4 * groups; 0 = default (4 groups), 2). */
 int         asr_set_option(const char* key, int value);
 int         asr_get_option(const char* key, int* value);

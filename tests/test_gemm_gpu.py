@@ -79,3 +79,24 @@ def test_feed_forward_block_matches_reference_module_math():
     _close(y, ref)
     with pytest.raises(RuntimeError):
         ops.linear_residual_layernorm(h, _rand((256, di), gen), None, _rand((B, T, 256), gen), torch.ones(256).cuda(), torch.zeros(256).cuda())
+
+
+def test_modules_take_the_fused_path_in_bf16_eval():
+    """PositionwiseFeedForward / MultiheadAttention in eval + no_grad + bf16 run the fused kernels and agree with their
+    own unfused forward (same bf16 parameters, torch ops) to bf16 accuracy."""
+    module = pkg("transformer.module")
+    attention = pkg("transformer.attention")
+    torch.manual_seed(5)
+    ffn = module.PositionwiseFeedForward(512, 2048, dropout=0.1).cuda().bfloat16().eval()
+    mha = attention.MultiheadAttention(512, 8, dropout=0.1).cuda().bfloat16().eval()
+    x = torch.randn(3, 167, 512, device="cuda").bfloat16()
+    lib = pkg("_lib")
+    with torch.no_grad():
+        n0 = lib.launch_count()
+        y_f = ffn(x)
+        assert lib.launch_count() - n0 == 2                     # two kernels for the whole block
+        o_f, _ = mha(x, x, x)
+    y_u = ffn(x)                                                 # grad mode: the torch path
+    o_u, _ = mha(x, x, x)
+    _close(y_f, y_u.detach(), 3e-2)
+    _close(o_f, o_u.detach(), 3e-2)

@@ -33,6 +33,12 @@ for M in (10688, 64 * 1600):
              lambda: F.layer_norm(F.linear(h, w2, b2h) + x, (d,), gamh, beth), 2.0 * M * d * di),
             ("fc + bias + residual + LayerNorm [M,512]x[512,512]", lambda: ops.linear_residual_layernorm(x, w2[:, :512].contiguous(), b2, x, gam, bet),
              lambda: F.layer_norm(F.linear(x, w2[:, :512].contiguous(), b2h) + x, (d,), gamh, beth), 2.0 * M * d * d)]
+    lib = importlib.import_module("end-to-end_asr_pytorch_b200._lib")
+    for var in (1, 2, 3):
+        lib.set_option("gemm_variant", var)
+        a = timed(rows[0][1])
+        print("M=%6d w_1 variant %d: %.3f ms %6.0f TFLOP/s" % (M, var, a, rows[0][3] / a / 1e9), flush=True)
+    lib.set_option("gemm_variant", 0)
     for name, ours, ref, flop in rows:
         a, b = timed(ours), timed(ref)
         print("M=%6d %-56s ours %.3f ms %6.0f TFLOP/s | torch %.3f ms %6.0f TFLOP/s" % (M, name, a, flop / a / 1e9, b, flop / b / 1e9), flush=True)
