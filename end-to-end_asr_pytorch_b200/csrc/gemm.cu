@@ -128,13 +128,16 @@ linear_act_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
                     uint32_t w[4];
+                    float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (bias != nullptr) {      // the same 32 bytes for every lane: two broadcast loads
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i + 4));
+                        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+                        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+                    }
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        float a0 = v[i + 2 * u], a1 = v[i + 2 * u + 1];
-                        if (bias != nullptr) {
-                            a0 += __ldg(bias + n0 + c + i + 2 * u);
-                            a1 += __ldg(bias + n0 + c + i + 2 * u + 1);
-                        }
+                        float a0 = v[i + 2 * u] + bv[2 * u], a1 = v[i + 2 * u + 1] + bv[2 * u + 1];
                         if (RELU) {
                             a0 = fmaxf(a0, 0.0f);
                             a1 = fmaxf(a1, 0.0f);
@@ -157,7 +160,7 @@ linear_act_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 // ---- y = LayerNorm(x W^T + b + residual) * gamma + beta, N = 512: the whole row lives in tensor memory -----
 constexpr int kLnN = 512;
 constexpr int kLnStages = 2;
-constexpr int kLnSmem = kLnStages * (kGATile + kLnN * kGK * 2) + 256;
+constexpr int kLnSmem = kLnStages * (kGATile + kLnN * kGK * 2) + 256 + 3 * kLnN * 4 /*bias, gamma, beta*/;
 
 __global__ void __launch_bounds__(192, 1)
 linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ bias,
@@ -169,6 +172,7 @@ linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     unsigned char* sA = smem;
     unsigned char* sB = sA + kLnStages * kGATile;
     GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sB + kLnStages * kBTile);
+    float* sPar = reinterpret_cast<float*>(sB + kLnStages * kBTile + 256);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * kGM;
     const int nk = K / kGK;
@@ -196,25 +200,50 @@ linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const int row = m0 + warp * 32 + lane;
         const int rowc = min(row, M - 1);
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-        const __nv_bfloat16* res = residual + (size_t)rowc * kLnN;
+        const uint4* res = reinterpret_cast<const uint4*>(residual + (size_t)rowc * kLnN);      // 64 x 16 bytes per row
+        // while the products run: bias / gamma / beta into shared memory (read back as broadcast float4), and the
+        // first residual chunks into registers
+        for (int i = threadIdx.x; i < kLnN; i += 128) {
+            sPar[i] = bias ? __ldg(bias + i) : 0.0f;
+            sPar[kLnN + i] = __ldg(gamma + i);
+            sPar[2 * kLnN + i] = __ldg(beta + i);
+        }
+        bar_sync_named(1, 128);
+        const float4* sBias4 = reinterpret_cast<const float4*>(sPar);
+        const float4* sGamma4 = reinterpret_cast<const float4*>(sPar + kLnN);
+        const float4* sBeta4 = reinterpret_cast<const float4*>(sPar + 2 * kLnN);
+        constexpr int kPre = 2;                        // residual chunks (32 columns = 4 x 16 bytes) in flight
+        uint4 rbuf[kPre][4];
+#pragma unroll
+        for (int pch = 0; pch < kPre; ++pch)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rbuf[pch][q] = __ldg(res + pch * 4 + q);
         mbar_wait(&bars->acc_full, 0);
         tc_fence_after();
         // pass 1: z = acc + bias + residual, written back to tensor memory; row sum
         float sum = 0.0f;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < kLnN; c += 32) {
+            const int slot = (c / 32) % kPre;
+            uint4 rcur[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rcur[q] = rbuf[slot][q];
+            if (c + 32 * kPre < kLnN) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) rbuf[slot][q] = __ldg(res + (c / 32 + kPre) * 4 + q);
+            }
             float v[32];
             tmem_ld32(taddr + c, v);
             uint32_t z[32];
 #pragma unroll
             for (int i = 0; i < 32; i += 8) {
-                const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(res + c + i));
-                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+                const uint32_t rw[4] = {rcur[i >> 3].x, rcur[i >> 3].y, rcur[i >> 3].z, rcur[i >> 3].w};
+                const float4 ba = sBias4[(c + i) >> 2], bb = sBias4[((c + i) >> 2) + 1];
+                const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const float r0 = __uint_as_float(rw[u] << 16), r1 = __uint_as_float(rw[u] & 0xffff0000u);
-                    const float b0 = bias ? __ldg(bias + c + i + 2 * u) : 0.0f, b1 = bias ? __ldg(bias + c + i + 2 * u + 1) : 0.0f;
-                    const float z0 = v[i + 2 * u] + b0 + r0, z1 = v[i + 2 * u + 1] + b1 + r1;
+                    const float z0 = v[i + 2 * u] + bv[2 * u] + r0, z1 = v[i + 2 * u + 1] + bv[2 * u + 1] + r1;
                     sum += z0 + z1;
                     z[i + 2 * u] = __float_as_uint(z0);
                     z[i + 2 * u + 1] = __float_as_uint(z1);
@@ -226,7 +255,7 @@ linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const float mean = sum * (1.0f / kLnN);
         // pass 2: variance around the mean (as torch's LayerNorm: biased, two-pass accuracy)
         float sq = 0.0f;
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < kLnN; c += 32) {
             float v[32];
             tmem_ld32(taddr + c, v);
@@ -239,19 +268,22 @@ linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const float rstd = rsqrtf(sq * (1.0f / kLnN) + eps);
         // pass 3: normalise, scale, shift, store
         __nv_bfloat16* dst = y + (size_t)rowc * kLnN;
-#pragma unroll 1
+#pragma unroll 2
         for (int c = 0; c < kLnN; c += 32) {
             float v[32];
             tmem_ld32(taddr + c, v);
             if (row < M) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
+                    const float4 ga = sGamma4[(c + i) >> 2], gb = sGamma4[((c + i) >> 2) + 1];
+                    const float4 ea = sBeta4[(c + i) >> 2], eb = sBeta4[((c + i) >> 2) + 1];
+                    const float gv[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+                    const float ev[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
                     uint32_t w[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int n = c + i + 2 * u;
-                        const float a0 = (v[i + 2 * u] - mean) * rstd * __ldg(gamma + n) + __ldg(beta + n);
-                        const float a1 = (v[i + 2 * u + 1] - mean) * rstd * __ldg(gamma + n + 1) + __ldg(beta + n + 1);
+                        const float a0 = fmaf((v[i + 2 * u] - mean) * rstd, gv[2 * u], ev[2 * u]);
+                        const float a1 = fmaf((v[i + 2 * u + 1] - mean) * rstd, gv[2 * u + 1], ev[2 * u + 1]);
                         w[u] = pack_bf16x2(a0, a1);
                     }
                     *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -281,7 +313,7 @@ extern "C" int asr_linear_act_bf16(const void* x, const void* w, const float* bi
     ASR_REQUIRE(x && w && y, "asr_linear_act_bf16: null pointer");
     ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_linear_act_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     ASR_REQUIRE(N % 128 == 0 && K % kGK == 0, "asr_linear_act_bf16: N=%d must be a multiple of 128 and K=%d of 64", N, K);
-    ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "asr_linear_act_bf16: pointers must be 16-byte aligned");
+    ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias), "asr_linear_act_bf16: pointers must be 16-byte aligned");
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // "gemm_variant": 0 = auto, 1 = 128 x 128 tiles, 3-deep ring, two CTAs per SM; 2 = 128 x 256 tiles, 2-deep ring,
