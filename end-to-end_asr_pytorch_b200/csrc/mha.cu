@@ -1826,6 +1826,31 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
                     rnd[1] = philox16(((uint32_t)(key0 + cc) >> 4) + 1, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
                 }
+                if constexpr (!DROP) {
+                    // packed f32x2 arithmetic: P = 2^(S c - lse), dS = P (dP scale - delta scale)
+                    const uint64_t c2 = pack_f32x2(c, c), nl2 = pack_f32x2(-lse2, -lse2);
+                    const uint64_t sc2 = pack_f32x2(a.scale, a.scale), nd2 = pack_f32x2(-dlt * a.scale, -dlt * a.scale);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        float x0, x1;
+                        unpack_f32x2(fma_f32x2(pack_f32x2(sv[i], sv[i + 1]), c2, nl2), x0, x1);
+                        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                        if (need_mask) {
+                            const int key = key0 + cc + i;
+                            bool d0 = key >= lim, d1 = key + 1 >= lim;
+                            if (mrow != nullptr) {
+                                if (key < a.Lk) d0 = d0 || (mrow[key] != 0);
+                                if (key + 1 < a.Lk) d1 = d1 || (mrow[key + 1] != 0);
+                            }
+                            if (d0) p0 = 0.0f;
+                            if (d1) p1 = 0.0f;
+                        }
+                        float s0, s1;
+                        unpack_f32x2(mul_f32x2(pack_f32x2(p0, p1), fma_f32x2(pack_f32x2(dp[i], dp[i + 1]), sc2, nd2)), s0, s1);
+                        pk[(c0 + i) >> 1] = cvt_bf16x2(p0, p1);
+                        dk[(c0 + i) >> 1] = cvt_bf16x2(s0, s1);
+                    }
+                } else {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float p0 = ex2_approx(fmaf(sv[i], c, -lse2));
@@ -1856,6 +1881,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     const __nv_bfloat162 sb = __floats2bfloat162_rn(s0, s1);
                     pk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
                     dk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
+                }
                 }
             }
             float dq[kColsD];
