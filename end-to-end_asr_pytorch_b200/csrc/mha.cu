@@ -1826,8 +1826,9 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
                     rnd[1] = philox16(((uint32_t)(key0 + cc) >> 4) + 1, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
                 }
-                if constexpr (!DROP) {
-                    // packed f32x2 arithmetic: P = 2^(S c - lse), dS = P (dP scale - delta scale)
+                {
+                    // packed f32x2 arithmetic: P = 2^(S c - lse), dS = P (dP' scale - delta scale); with dropout
+                    // (mask M, keep probability k) dP' = dP o M / k and the P that dV sees is P o M / k
                     const uint64_t c2 = pack_f32x2(c, c), nl2 = pack_f32x2(-lse2, -lse2);
                     const uint64_t sc2 = pack_f32x2(a.scale, a.scale), nd2 = pack_f32x2(-dlt * a.scale, -dlt * a.scale);
 #pragma unroll
@@ -1845,43 +1846,22 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             if (d0) p0 = 0.0f;
                             if (d1) p1 = 0.0f;
                         }
-                        float s0, s1;
-                        unpack_f32x2(mul_f32x2(pack_f32x2(p0, p1), fma_f32x2(pack_f32x2(dp[i], dp[i + 1]), sc2, nd2)), s0, s1);
-                        pk[(c0 + i) >> 1] = cvt_bf16x2(p0, p1);
+                        const uint64_t p2 = pack_f32x2(p0, p1);
+                        uint64_t g2 = pack_f32x2(dp[i], dp[i + 1]);      // d(loss)/d(dropped, rescaled probability)
+                        uint64_t pd2 = p2;                               // the probabilities P V was computed with
+                        if (DROP) {
+                            const float k0 = philox_byte(rnd[i >> 4], i & 15) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const float k1 = philox_byte(rnd[i >> 4], (i + 1) & 15) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const uint64_t kf2 = pack_f32x2(k0, k1);
+                            g2 = mul_f32x2(g2, kf2);
+                            pd2 = mul_f32x2(p2, kf2);
+                        }
+                        float s0, s1, q0, q1;
+                        unpack_f32x2(mul_f32x2(p2, fma_f32x2(g2, sc2, nd2)), s0, s1);
+                        unpack_f32x2(pd2, q0, q1);
+                        pk[(c0 + i) >> 1] = cvt_bf16x2(q0, q1);
                         dk[(c0 + i) >> 1] = cvt_bf16x2(s0, s1);
                     }
-                } else {
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float p0 = ex2_approx(fmaf(sv[i], c, -lse2));
-                    float p1 = ex2_approx(fmaf(sv[i + 1], c, -lse2));
-                    if (need_mask) {
-                        const int key = key0 + cc + i;
-                        bool d0 = key >= lim, d1 = key + 1 >= lim;
-                        if (mrow != nullptr) {
-                            if (key < a.Lk) d0 = d0 || (mrow[key] != 0);
-                            if (key + 1 < a.Lk) d1 = d1 || (mrow[key + 1] != 0);
-                        }
-                        if (d0) p0 = 0.0f;
-                        if (d1) p1 = 0.0f;
-                    }
-                    float g0 = dp[i], g1 = dp[i + 1];      // d(loss)/d(dropped, rescaled probability)
-                    float pd0 = p0, pd1 = p1;              // the probabilities P V was computed with
-                    if (DROP) {
-                        const bool k0 = philox_byte(rnd[i >> 4], i & 15) >= a.drop_thresh;
-                        const bool k1 = philox_byte(rnd[i >> 4], (i + 1) & 15) >= a.drop_thresh;
-                        g0 = k0 ? g0 * a.inv_keep : 0.0f;
-                        g1 = k1 ? g1 * a.inv_keep : 0.0f;
-                        pd0 = k0 ? p0 * a.inv_keep : 0.0f;
-                        pd1 = k1 ? p1 * a.inv_keep : 0.0f;
-                    }
-                    const float s0 = p0 * (g0 - dlt) * a.scale;
-                    const float s1 = p1 * (g1 - dlt) * a.scale;
-                    const __nv_bfloat162 pb = __floats2bfloat162_rn(pd0, pd1);
-                    const __nv_bfloat162 sb = __floats2bfloat162_rn(s0, s1);
-                    pk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                    dk[(c0 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&sb);
-                }
                 }
             }
             float dq[kColsD];
