@@ -460,10 +460,15 @@ def _train_inputs(w, device, seed):
     return feats, lens, targets
 
 
-def run_train(args, w, rank, world, device, steps=None, emit=True):
+def run_train(args, w, rank, world, device, steps=None, emit=True, tf32=False):
+    """tf32=True lets torch run the model shell's fp32 Linear / Conv GEMMs on the tensor cores (TF32 inputs, fp32
+    accumulate) instead of cuBLAS's SIMT sgemm - reported next to the reference-faithful fp32 step, never instead."""
     import importlib
     import torch.distributed as dist
     import asr_b200 as pkg
+    tf32_before = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    if tf32:      # the plain run keeps torch's defaults (fp32 matmul; cuDNN may use TF32 for the convolutions, as in the reference's own torch)
+        torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
     cm = importlib.import_module("end-to-end_asr_pytorch_b200.transformer.cif_model")
     lossm = importlib.import_module("end-to-end_asr_pytorch_b200.transformer.loss")
     dp = importlib.import_module("end-to-end_asr_pytorch_b200.dp")
@@ -542,6 +547,7 @@ def run_train(args, w, rank, world, device, steps=None, emit=True):
         if emit:
             print(json.dumps(line), flush=True)
     del model, opt, sync
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_before
     torch.cuda.empty_cache()
     return line
 
@@ -780,7 +786,13 @@ def main():
             train_step = {k: tl[k] for k in ("value", "unit", "ms_per_step", "e2e", "gpu_launches")}
             train_step.update(workload="train", per_gpu=tl["config"]["per_gpu"], params=tl["config"]["params"],
                               grad_allreduce_bytes=tl["config"]["grad_allreduce_bytes"],
-                              parallelism=tl["config"]["parallelism"])
+                              parallelism=tl["config"]["parallelism"],
+                              dtype="f32 model shell as the reference (cuBLAS SIMT sgemm: ~45 % of the step), bf16 attention core")
+        t2 = run_train(args, dict(WORKLOADS["train"]), rank, world, device, steps=5, emit=False, tf32=True)
+        if t2 is not None and train_step is not None:
+            train_step["with_tf32_matmul"] = {"value": t2["value"], "unit": t2["unit"], "ms_per_step": t2["ms_per_step"],
+                                              "note": "same step with torch.backends.*.allow_tf32 = True for the model shell's "
+                                                      "Linear / Conv GEMMs (reduced precision: informational, not the reported value)"}
 
     if rank == 0:
         cpu_baseline = None
