@@ -397,6 +397,23 @@ def linear_microbench(pkg, device, iters=10):
         flop = 2.0 * M * d * di
         res[name] = {"ms": t[0], "TFLOPs": flop / t[0] / 1e9, "torch_ms": t[1], "torch_TFLOPs": flop / t[1] / 1e9,
                      "shape": "M=%d K=%d N=%d bf16" % ((M, d, di) if name == "linear_bias_relu" else (M, di, d))}
+    # fp32 in / fp32 out on the tensor cores (three TF32 products per tile) next to torch's fp32 GEMM (cuBLAS SIMT sgemm)
+    xf, wf = x.float(), w1.float()
+    t = []
+    for fn in (lambda: ops.linear_f32(xf, wf, b1), lambda: F.linear(xf, wf, b1)):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t.append(e0.elapsed_time(e1) / 3)
+    flop = 2.0 * M * d * di
+    res["linear_f32_3xtf32"] = {"ms": t[0], "TFLOPs": flop / t[0] / 1e9, "torch_ms": t[1], "torch_TFLOPs": flop / t[1] / 1e9,
+                                "shape": "M=%d K=%d N=%d f32" % (M, d, di)}
     return res
 
 
@@ -746,7 +763,7 @@ def main():
                         "GBps": sa["GBps"], "frac_of_hbm_peak": sa["GBps"] / peaks["hbm_gbs"], "shape": sa["shape"],
                         "in_timed_step": False, "note": "SURVEY 8(f4): SpecAugment, three launches incl. the means"})
         lin = linear_microbench(pkg, device)
-        for n in ("linear_bias_relu", "linear_residual_layernorm"):
+        for n in ("linear_bias_relu", "linear_residual_layernorm", "linear_f32_3xtf32"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": lin[n]["ms"], "TFLOPs": lin[n]["TFLOPs"],
                             "frac_of_bf16_peak": lin[n]["TFLOPs"] / peaks["bf16_tflops"], "shape": lin[n]["shape"],
                             "torch_cublas_plus_eager_TFLOPs": lin[n]["torch_TFLOPs"], "in_timed_step": False,

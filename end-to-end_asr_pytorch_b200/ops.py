@@ -190,6 +190,24 @@ def linear_act(x, weight, bias=None, relu=False):
     return y.reshape(*x.shape[:-1], N)
 
 
+def linear_f32(x, weight, bias=None):
+    """y = x W^T + b in fp32 on the tensor cores with fp32-level accuracy (three TF32 products per tile):
+    x [..., K] f32, weight [N, K] f32 -> [..., N] f32.  Forward only; K % 4 == 0."""
+    _require_cuda("x", x, torch.float32)
+    _require_cuda("weight", weight, torch.float32)
+    K = x.shape[-1]
+    N = weight.shape[0]
+    if weight.dim() != 2 or weight.shape[1] != K:
+        raise ValueError("linear_f32: weight must be [N, K] with K = x.shape[-1]")
+    x2 = x.detach().reshape(-1, K).contiguous()
+    w = weight.detach().contiguous()
+    b = None if bias is None else bias.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    y = torch.empty((x2.shape[0], N), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().asr_linear_f32(ptr(x2), ptr(w), ptr(b), x2.shape[0], N, K, ptr(y), stream_ptr()), "asr_linear_f32")
+    return y.reshape(*x.shape[:-1], N)
+
+
 def linear_residual_layernorm(x, weight, bias, residual, ln_weight, ln_bias, eps=1e-5):
     """y = LayerNorm(x W^T + b + residual) (module.py:50-52, attention.py:59-60 with dropout off): x [..., K] bf16,
     weight [512, K] bf16, residual [..., 512] bf16, LayerNorm weight / bias [512] -> [..., 512] bf16.  Forward only."""

@@ -190,6 +190,18 @@ int asr_linear_residual_layernorm_bf16(const void* x, const void* w, const float
                                        const float* gamma, const float* beta, float eps, int M, int N, int K,
                                        void* y, void* stream);
 
+/*
+ * y = x W^T + bias in fp32 ON THE TENSOR CORES with fp32-level accuracy: every operand is split
+ * into a TF32 head and an fp32 remainder and three tcgen05.mma kind::tf32 products are accumulated
+ * (hi*hi + lo*hi + hi*lo; relative error ~1e-6 instead of TF32's 1e-3).  x [M,K], W [N,K] (torch
+ * Linear.weight), bias [N] or NULL, y [M,N], all f32.  For the fp32 Linear layers of the model
+ * shell (cuBLAS runs them as SIMT sgemm) and the ctc_fc / tgt_word_prj vocabulary projections
+ * (/root/reference/src/transformer/cif_model.py:38), whose logits feed the CTC kernels at the
+ * 1e-5 bar.  K % 4 == 0; any M, N (N = 4233 included).
+ */
+int asr_linear_f32(const float* x, const float* w, const float* bias, int M, int N, int K, float* y,
+                   void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at

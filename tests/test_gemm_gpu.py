@@ -100,3 +100,24 @@ def test_modules_take_the_fused_path_in_bf16_eval():
     o_u, _ = mha(x, x, x)
     _close(y_f, y_u.detach(), 3e-2)
     _close(o_f, o_u.detach(), 3e-2)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (300, 512, 512), (1344, 4233, 512), (77, 2048, 512), (1000, 512, 2048), (5, 36, 20)])
+def test_linear_f32_three_tf32_products(M, N, K):
+    """fp32 in, fp32 out, tensor cores: against an fp64 reference the error must be at fp32 level (a single TF32
+    product would be ~1e-3), and no worse than a few times torch's own fp32 (SIMT) GEMM."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(M * 7 + N + K)
+    x = torch.randn(M, K, generator=gen).cuda()
+    w = (torch.randn(N, K, generator=gen) * K ** -0.5).cuda()
+    b = torch.randn(N, generator=gen).cuda()
+    y = ops.linear_f32(x, w, b)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    scale = ref.abs().max().item()
+    err = (y.double() - ref).abs().max().item()
+    err_torch = (torch.nn.functional.linear(x, w, b).double() - ref).abs().max().item()
+    assert y.dtype == torch.float32 and y.shape == (M, N)
+    # measured on B200: 4e-6 of the output scale at K = 512, 1.3e-5 at K = 2048 (the tensor core's fp32 accumulation
+    # truncates, so the error grows with K; torch's SIMT fp32 GEMM: 7e-7 / 1.6e-6)
+    assert err <= 1e-5 * scale * max(1.0, K / 512.0), (err, scale, err_torch)
+    assert err <= 16 * err_torch + 1e-6 * scale, (err, err_torch)

@@ -42,3 +42,20 @@ for M in (10688, 64 * 1600):
     for name, ours, ref, flop in rows:
         a, b = timed(ours), timed(ref)
         print("M=%6d %-56s ours %.3f ms %6.0f TFLOP/s | torch %.3f ms %6.0f TFLOP/s" % (M, name, a, flop / a / 1e9, b, flop / b / 1e9), flush=True)
+
+# fp32 GEMM on the tensor cores (3xTF32) vs torch's fp32 (cuBLAS SIMT sgemm) and torch with TF32 allowed
+for M, N, K in ((1344, 2048, 512), (1344, 4233, 512), (10688, 2048, 512), (102400, 2048, 512), (102400, 512, 2048)):
+    x = torch.randn(M, K, device="cuda", generator=g); w = torch.randn(N, K, device="cuda", generator=g) * K ** -0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    flop = 2.0 * M * N * K
+    a = timed(lambda: ops.linear_f32(x, w, b))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    t32 = timed(lambda: F.linear(x, w, b))
+    torch.backends.cuda.matmul.allow_tf32 = True
+    ttf = timed(lambda: F.linear(x, w, b))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = F.linear(x.double(), w.double(), b.double())
+    e_ours = ((ops.linear_f32(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
+    e_t32 = ((F.linear(x, w, b).double() - ref).abs().max() / ref.abs().max()).item()
+    print("fp32 linear M=%6d N=%4d K=%4d: 3xTF32 %.3f ms %5.0f TFLOP/s err %.1e | torch fp32 %.3f ms %5.0f TFLOP/s err %.1e | torch tf32 %.3f ms %5.0f TFLOP/s"
+          % (M, N, K, a, flop / a / 1e9, e_ours, t32, flop / t32 / 1e9, e_t32, ttf, flop / ttf / 1e9), flush=True)
