@@ -16,7 +16,7 @@ static std::mutex g_opt_mu;
 static std::map<std::string, int>& opts() {
     static std::map<std::string, int> m = {
         {"cif_fwd_variant", 0}, {"cif_fwd_width", 0}, {"cif_fwd_stages", 0}, {"cif_fwd_rows", 0},
-        {"mha_variant", 0}, {"ctc_fuse_apply", 0}, {"ctc_lattice_variant", 0}, {"ctc_chunks", 0}, {"ctc_finish_per_slice", 0}, {"mha_bwd_groups", 0}, {"gemm_variant", 0},
+        {"mha_variant", 0}, {"ctc_fuse_apply", 0}, {"ctc_lattice_variant", 0}, {"ctc_chunks", 0}, {"ctc_finish_per_slice", 0}, {"mha_bwd_groups", 0}, {"gemm_variant", 0}, {"gemm_f32_bn", 0},
     };
     return m;
 }
