@@ -475,7 +475,11 @@ extern "C" int asr_linear_f32(const float* x, const float* w, const float* bias,
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // "gemm_f32_bn": 0 = auto (256-wide tiles when N >= 256), 128, 256
     int bn = get_opt("gemm_f32_bn");
-    if (bn != 128 && bn != 256) bn = N >= 256 ? 256 : 128;
+    if (bn != 128 && bn != 256) {
+        // 256-wide tiles halve the operand traffic per flop, but small problems need the CTAs: one wave first
+        const long long ctas256 = (long long)((N + 255) / 256) * ((M + kGM - 1) / kGM);
+        bn = (N >= 256 && ctas256 >= num_sms()) ? 256 : 128;
+    }
     CUtensorMap tx, tw;
     if (make_tmap_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, (uint64_t)M, (uint64_t)K, (uint64_t)K * 4, 128, kF3K, CU_TENSOR_MAP_SWIZZLE_128B) ||
         make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 4, (uint32_t)bn, kF3K, CU_TENSOR_MAP_SWIZZLE_128B))

@@ -208,6 +208,41 @@ def linear_f32(x, weight, bias=None):
     return y.reshape(*x.shape[:-1], N)
 
 
+class _LinearF32Function(torch.autograd.Function):
+    """y = x W^T + b with all three GEMMs (y, dx = gy W, dW = gy^T x) on the fp32 tensor-core kernel; the
+    transposed operands are materialised with one copy each (small next to the products)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K).contiguous()
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape = x.shape
+        ctx.has_bias = bias is not None
+        return linear_f32(x2, weight, bias).reshape(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight = ctx.saved_tensors
+        N, K = weight.shape
+        M = x2.shape[0]
+        gy2 = gy.reshape(-1, N).contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            # contraction over N: the kernel wants 16-byte rows (N % 4 == 0); the 4233-wide vocabulary projection falls back
+            gx = (linear_f32(gy2, weight.t().contiguous()) if N % 4 == 0 else gy2 @ weight).reshape(ctx.x_shape)
+        if ctx.needs_input_grad[1]:
+            gw = linear_f32(gy2.t().contiguous(), x2.t().contiguous()) if M % 4 == 0 else gy2.t() @ x2
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy2.sum(0)
+        return gx, gw, gb
+
+
+def linear_f32_autograd(x, weight, bias=None):
+    """Differentiable fp32 linear layer on the tensor cores (three TF32 products per tile, see linear_f32)."""
+    return _LinearF32Function.apply(x, weight, bias)
+
+
 def linear_residual_layernorm(x, weight, bias, residual, ln_weight, ln_bias, eps=1e-5):
     """y = LayerNorm(x W^T + b + residual) (module.py:50-52, attention.py:59-60 with dropout off): x [..., K] bf16,
     weight [512, K] bf16, residual [..., 512] bf16, LayerNorm weight / bias [512] -> [..., 512] bf16.  Forward only."""

@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from ..ops import mha_core, mha_probs, linear_act, linear_residual_layernorm
-from .module import fused_linear_ok
+from .module import fused_linear_ok, Linear
 
 
 class MultiheadAttention(nn.Module):
@@ -39,9 +39,9 @@ class MultiheadAttention(nn.Module):
         self.d_v = d_v
         self.return_attn = return_attn
 
-        self.w_qs = nn.Linear(d_model, n_head * d_k)
-        self.w_ks = nn.Linear(d_model, n_head * d_k)
-        self.w_vs = nn.Linear(d_model, n_head * d_v)
+        self.w_qs = Linear(d_model, n_head * d_k)
+        self.w_ks = Linear(d_model, n_head * d_k)
+        self.w_vs = Linear(d_model, n_head * d_v)
         nn.init.normal_(self.w_qs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
         nn.init.normal_(self.w_ks.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_k)))
         nn.init.normal_(self.w_vs.weight, mean=0, std=np.sqrt(2.0 / (d_model + d_v)))
@@ -50,7 +50,7 @@ class MultiheadAttention(nn.Module):
         self.temperature = np.power(d_k, 0.5)
         self.layer_norm = nn.LayerNorm(d_model)
 
-        self.fc = nn.Linear(n_head * d_v, d_model)
+        self.fc = Linear(n_head * d_v, d_model)
         nn.init.xavier_normal_(self.fc.weight)
 
         self.dropout = nn.Dropout(dropout)

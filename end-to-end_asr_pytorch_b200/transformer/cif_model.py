@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 
 from ..ops import cif as _cif_op
+from .module import Linear
 
 
 def _sibling(name):
@@ -47,7 +48,7 @@ class CIF_Model(nn.Module):
         self.fused_alpha = fused_alpha
         self.decoder = decoder
         self.spec_aug_cfg = spec_aug_cfg
-        self.ctc_fc = nn.Linear(encoder.d_output, decoder.d_output, bias=False)
+        self.ctc_fc = Linear(encoder.d_output, decoder.d_output, bias=False)
 
         for p in self.parameters():
             if p.dim() > 1:

@@ -7,6 +7,8 @@ from collections import OrderedDict
 
 import torch
 import torch.nn as nn
+
+from .module import Linear
 import torch.nn.functional as F
 
 
@@ -44,7 +46,7 @@ class Conv2dSubsample(nn.Module):
             stack["subsample/relu{}".format(i)] = nn.ReLU()
         self.conv = nn.Sequential(stack)
         self.d_conv_out = int(math.ceil(d_input / 2))
-        self.affine = nn.Linear(32 * self.d_conv_out, d_model)
+        self.affine = Linear(32 * self.d_conv_out, d_model)
 
     def forward(self, feats, feat_lengths):
         n_frames = feats.size(1)

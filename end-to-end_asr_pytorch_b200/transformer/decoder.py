@@ -5,6 +5,8 @@ scope).  Names follow Decoder_CIF in
 import torch
 import torch.nn as nn
 
+from .module import Linear
+
 from .encoder import EncoderLayer
 from .module import PositionalEncoding
 
@@ -21,8 +23,8 @@ class Decoder_CIF(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layer_stack = nn.ModuleList([EncoderLayer(d_model, d_inner, n_head, dropout=dropout)
                                           for _ in range(n_layers)])
-        self.input_affine = nn.Linear(2 * d_model, d_model, bias=False)
-        self.tgt_word_prj = nn.Linear(2 * d_model, n_tgt_vocab, bias=False)
+        self.input_affine = Linear(2 * d_model, d_model, bias=False)
+        self.tgt_word_prj = Linear(2 * d_model, n_tgt_vocab, bias=False)
         nn.init.xavier_normal_(self.tgt_word_prj.weight)
 
     def preprocess(self, target):

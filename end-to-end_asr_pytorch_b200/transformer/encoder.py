@@ -3,6 +3,8 @@ tcgen05 attention core).  Names follow /root/reference/src/transformer/encoder.p
 (`linear_in`, `layer_norm_in`, `layer_stack.N.{slf_attn,pos_ffn}`)."""
 import torch.nn as nn
 
+from .module import Linear
+
 from .attention import MultiheadAttention
 from .module import PositionalEncoding, PositionwiseFeedForward
 from ..utils.utils import sequence_mask
@@ -29,7 +31,7 @@ class Encoder(nn.Module):
         self.d_input, self.n_layers, self.n_head = d_input, n_layers, n_head
         self.d_model = self.d_output = d_model
         self.d_inner, self.dropout_rate = d_inner, dropout
-        self.linear_in = nn.Linear(d_input, d_model)
+        self.linear_in = Linear(d_input, d_model)
         self.layer_norm_in = nn.LayerNorm(d_model)
         self.positional_encoding = PositionalEncoding(d_model)
         self.dropout = nn.Dropout(dropout)

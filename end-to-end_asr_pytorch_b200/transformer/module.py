@@ -10,6 +10,26 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# fp32 Linear layers of the model shell on the tensor cores (ops.linear_f32: three TF32 products per tile, ~5e-6
+# relative error; torch's own fp32 path is cuBLAS's SIMT sgemm, ~45 % of the GPU time of the training step on B200).
+# Opt-in: at the reference recipe's per-step shapes (64 utterances x 21 frames = 1344 rows) the kernels take 6.2 ms
+# instead of cuBLAS's 9.3 ms per step, but the step is host-bound there and the Python autograd wrapper (three calls
+# and three transposes per layer) costs more than that: 24.7 vs 22.3 ms per step, measured.  From ~10 k rows on the
+# kernel is 3-4x cuBLAS's sgemm and the wrapper is noise.
+USE_TENSOR_CORE_FP32 = False
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters, same state_dict keys) whose fp32 CUDA forward and backward run on ops.linear_f32."""
+
+    def forward(self, x):
+        if (USE_TENSOR_CORE_FP32 and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
+                and self.in_features % 4 == 0 and x.numel() > 0):
+            from ..ops import linear_f32_autograd
+            return linear_f32_autograd(x, self.weight, self.bias)
+        return F.linear(x, self.weight, self.bias)
+
+
 class PositionalEncoding(nn.Module):
     """Sinusoidal table, returned for the first T positions of the input."""
 
@@ -31,8 +51,8 @@ class PositionwiseFeedForward(nn.Module):
 
     def __init__(self, d_model, d_ff, dropout=0.1):
         super().__init__()
-        self.w_1 = nn.Linear(d_model, d_ff)
-        self.w_2 = nn.Linear(d_ff, d_model)
+        self.w_1 = Linear(d_model, d_ff)
+        self.w_2 = Linear(d_ff, d_model)
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(d_model)
 

@@ -121,3 +121,44 @@ def test_linear_f32_three_tf32_products(M, N, K):
     # truncates, so the error grows with K; torch's SIMT fp32 GEMM: 7e-7 / 1.6e-6)
     assert err <= 1e-5 * scale * max(1.0, K / 512.0), (err, scale, err_torch)
     assert err <= 16 * err_torch + 1e-6 * scale, (err, err_torch)
+
+
+@pytest.mark.parametrize("shape,N,K,bias", [((4, 21, 512), 2048, 512, True), ((1344, 512), 4233, 512, False), ((3, 7, 320), 512, 320, True),
+                                            ((5, 5, 64), 36, 64, True)])
+def test_linear_f32_autograd(shape, N, K, bias):
+    """Forward, dx, dW, db of the differentiable fp32 tensor-core linear layer against torch in fp64."""
+    ops = pkg("ops")
+    gen = torch.Generator().manual_seed(N + K)
+    x = torch.randn(*shape, generator=gen).cuda().requires_grad_(True)
+    w = (torch.randn(N, K, generator=gen) * K ** -0.5).cuda().requires_grad_(True)
+    b = torch.randn(N, generator=gen).cuda().requires_grad_(True) if bias else None
+    gy = torch.randn(*shape[:-1], N, generator=gen).cuda()
+    y = ops.linear_f32_autograd(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = torch.nn.functional.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    for got, ref in ((y, yd), (x.grad, xd.grad), (w.grad, wd.grad)) + (((b.grad, bd.grad),) if bias else ()):
+        scale = ref.abs().max().item()
+        assert (got.double() - ref.detach()).abs().max().item() <= 2e-5 * scale, (got.shape,)
+
+
+def test_shell_linear_can_run_on_the_tensor_core_kernel():
+    module = pkg("transformer.module")
+    lib = pkg("_lib")
+    torch.manual_seed(2)
+    lin = module.Linear(512, 2048).cuda()
+    x = torch.randn(6, 21, 512, device="cuda")
+    n0 = lib.launch_count()
+    y_ref = lin(x)                                   # default: torch's F.linear
+    assert lib.launch_count() == n0
+    module.USE_TENSOR_CORE_FP32 = True
+    try:
+        n0 = lib.launch_count()
+        y = lin(x)
+        assert lib.launch_count() - n0 == 1
+    finally:
+        module.USE_TENSOR_CORE_FP32 = False
+    assert (y - y_ref).abs().max().item() <= 2e-5 * y_ref.abs().max().item()
+    assert sorted(lin.state_dict().keys()) == ["bias", "weight"]
