@@ -1815,24 +1815,23 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             uint32_t pk[kColsS / 2], dk[kColsS / 2];
             mbar_wait(&bars->sdp_full, it & 1);
             tc_fence_after();
+            // 16 columns at a time: S and dP of a 32-column pass would hold 64 registers next to pk / dk / dq, and
+            // the 16-warp instance (96 registers per thread) spilled
 #pragma unroll
-            for (int c0 = 0; c0 < kColsS; c0 += 32) {
+            for (int c0 = 0; c0 < kColsS; c0 += 16) {
                 const int cc = cg * kColsS + c0;
-                float sv[32], dp[32];
-                tmem_ld32(tm_s + lane_base + cc, sv);
-                tmem_ld32(tm_dp + lane_base + cc, dp);
-                uint4 rnd[2];
-                if (DROP) {
-                    rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
-                    rnd[1] = philox16(((uint32_t)(key0 + cc) >> 4) + 1, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
-                }
+                float sv[16], dp[16];
+                tmem_ld16(tm_s + lane_base + cc, sv);
+                tmem_ld16(tm_dp + lane_base + cc, dp);
+                uint4 rnd[1];
+                if (DROP) rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
                 {
                     // packed f32x2 arithmetic: P = 2^(S c - lse), dS = P (dP' scale - delta scale); with dropout
                     // (mask M, keep probability k) dP' = dP o M / k and the P that dV sees is P o M / k
                     const uint64_t c2 = pack_f32x2(c, c), nl2 = pack_f32x2(-lse2, -lse2);
                     const uint64_t sc2 = pack_f32x2(a.scale, a.scale), nd2 = pack_f32x2(-dlt * a.scale, -dlt * a.scale);
 #pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
+                    for (int i = 0; i < 16; i += 2) {
                         float x0, x1;
                         unpack_f32x2(fma_f32x2(pack_f32x2(sv[i], sv[i + 1]), c2, nl2), x0, x1);
                         float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
@@ -1850,8 +1849,8 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         uint64_t g2 = pack_f32x2(dp[i], dp[i + 1]);      // d(loss)/d(dropped, rescaled probability)
                         uint64_t pd2 = p2;                               // the probabilities P V was computed with
                         if (DROP) {
-                            const float k0 = philox_byte(rnd[i >> 4], i & 15) >= a.drop_thresh ? a.inv_keep : 0.0f;
-                            const float k1 = philox_byte(rnd[i >> 4], (i + 1) & 15) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const float k0 = philox_byte(rnd[0], i) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const float k1 = philox_byte(rnd[0], i + 1) >= a.drop_thresh ? a.inv_keep : 0.0f;
                             const uint64_t kf2 = pack_f32x2(k0, k1);
                             g2 = mul_f32x2(g2, kf2);
                             pd2 = mul_f32x2(p2, kf2);
