@@ -77,7 +77,7 @@ def test_core_key_padding_lengths(B, L, H):
     _close(ops.mha_core(q, k, v, mask=mask), ref)                   # dense form of the same mask
 
 
-@pytest.mark.parametrize("B,L,H", [(2, 151, 8), (1, 400, 2)])
+@pytest.mark.parametrize("B,L,H", [(2, 151, 8), (1, 400, 2), (2, 1100, 2)])
 def test_core_causal(B, L, H):
     ops = pkg("ops")
     q, k, v = _rand_qkv(B, L, L, H, seed=L + 7)
