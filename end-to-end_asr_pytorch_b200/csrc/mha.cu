@@ -562,22 +562,29 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (need_mask) apply_mask(r, part * 32);
                 uint32_t pk[16];
                 if (DROP) {
-                    // fp32 exponentials: their sum is the softmax normaliser, the dropped and rescaled copy goes to the P tile
+                    // fp32 exponentials (packed f32x2 arithmetic around them): their sum is the softmax normaliser, the
+                    // dropped and rescaled copy goes to the P tile
+                    const uint64_t c2 = pack_f32x2(c, c), mc2 = pack_f32x2(-mc, -mc);
+                    uint64_t l2 = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
                                                    a.seed_lo, a.seed_hi);
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            float p0 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i]), c, -mc));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i + 1]), c, -mc));
-                            l_part += p0 + p1;
-                            p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
-                            p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
-                            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                            pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                            float x0, x1, q0, q1;
+                            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[g * 16 + i]), __uint_as_float(r[g * 16 + i + 1])), c2, mc2), x0, x1);
+                            const uint64_t p2 = pack_f32x2(ex2_approx(x0), ex2_approx(x1));
+                            l2 = add_f32x2(l2, p2);
+                            const float k0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : a.inv_keep;
+                            const float k1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : a.inv_keep;
+                            unpack_f32x2(mul_f32x2(p2, pack_f32x2(k0, k1)), q0, q1);
+                            pk[(g * 16 + i) >> 1] = cvt_bf16x2(q0, q1);
                         }
                     }
+                    float la, lb;
+                    unpack_f32x2(l2, la, lb);
+                    l_part += la + lb;
                 } else {
                     float ls = 0.0f;
 #pragma unroll
