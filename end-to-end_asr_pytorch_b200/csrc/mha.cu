@@ -1946,11 +1946,14 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 }
 
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per row of 64)
+// (also clears the row's 64 floats of the dQ accumulator [B,Lq,Hh,64], which has the same row order: one launch
+// instead of a memset + this kernel)
 __global__ void __launch_bounds__(256) mha_delta_kernel(const __nv_bfloat16* o, const __nv_bfloat16* d_o, float* delta,
-                                                        int B, int Hh, int Lq) {
+                                                        float* dq_acc, int B, int Hh, int Lq) {
     const int lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // (b, q, h)
     if (row >= (long long)B * Lq * Hh) return;
+    reinterpret_cast<float2*>(dq_acc + row * kD)[lane] = make_float2(0.0f, 0.0f);
     const __nv_bfloat162 ov = reinterpret_cast<const __nv_bfloat162*>(o + row * kD)[lane];
     const __nv_bfloat162 gv = reinterpret_cast<const __nv_bfloat162*>(d_o + row * kD)[lane];
     float s = __low2float(ov) * __low2float(gv) + __high2float(ov) * __high2float(gv);
@@ -2161,10 +2164,9 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
     float* dq_acc = reinterpret_cast<float*>(w);
     const size_t nq_elems = (size_t)B * Lq * Hh * kD;
     float* delta = dq_acc + nq_elems;
-    ASR_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, nq_elems * sizeof(float), st));
     const long long rows = (long long)B * Lq * Hh;
     mha_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
-                                                                 static_cast<const __nv_bfloat16*>(g_out), delta, B, Hh, Lq);
+                                                                 static_cast<const __nv_bfloat16*>(g_out), delta, dq_acc, B, Hh, Lq);
     ASR_LAUNCH_CHECK();
     CUtensorMap tq, tk, tv, tdo, tdq;
     if (make_qkv_map(&tq, q, B, Lq, Hh) || make_qkv_map(&tk, k, B, Lk, Hh) || make_qkv_map(&tv, v, B, Lk, Hh) ||
