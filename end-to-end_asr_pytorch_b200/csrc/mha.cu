@@ -977,8 +977,9 @@ struct __align__(8) MhaBarriers8 {
     uint32_t pad;
 };
 constexpr int kFwd8Threads = 384;   // 8 softmax warps + one utility warpgroup (TMA, MMA, two idle warps)
-constexpr int kFwd8Smem = (2 + 2 * kFwd6Stages + 4) * kTileBytes /*Q x2 + K ring + V ring + P x2*/ + 256 /*barriers*/;
-static_assert(kFwd8Smem <= 232448, "shared memory of the forward kernel");
+// Q x2 + K ring + V ring (+ P x2 unless P lives in tensor memory, MODE bit 4) + barriers
+constexpr int fwd8_smem(int mode) { return (2 + 2 * kFwd6Stages + ((mode & 16) ? 0 : 4)) * kTileBytes + 256; }
+static_assert(fwd8_smem(0) <= 232448, "shared memory of the forward kernel");
 
 // MODE bit 0: the two tiles take turns on the XU pipe (named-barrier token), which keeps them in
 // opposite phases: one loads its scores and finds the row maxima while the other runs its exponentials.  MODE bit 1: fp32
@@ -994,7 +995,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     unsigned char* sK = sQ + 2 * kTileBytes;               // kFwd6Stages tiles
     unsigned char* sV = sK + kFwd6Stages * kTileBytes;     // kFwd6Stages tiles
     unsigned char* sP = sV + kFwd6Stages * kTileBytes;     // [2 tiles][2 key halves][128 rows][128 B]
-    MhaBarriers8* bars = reinterpret_cast<MhaBarriers8*>(sP + 4 * kTileBytes);
+    MhaBarriers8* bars = reinterpret_cast<MhaBarriers8*>(sP + ((MODE & 16) ? 0 : 4) * kTileBytes);
     static_assert(sizeof(MhaBarriers8) <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5;
@@ -2081,8 +2082,8 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
 #define ASR_LAUNCH_FWD8(DR, MODE)                                                                                             \
     do {                                                                                                                      \
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<DR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); \
-        mha_fwd8_kernel<DR, MODE><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);                                      \
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<DR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(MODE))); \
+        mha_fwd8_kernel<DR, MODE><<<grid, kFwd8Threads, fwd8_smem(MODE), st>>>(tq, tk, tv, a);                                \
     } while (0)
         if (a.drop_thresh > 0) ASR_LAUNCH_FWD8(true, 51);
         else if (variant == 8) ASR_LAUNCH_FWD8(false, 0);
