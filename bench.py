@@ -401,16 +401,16 @@ def linear_microbench(pkg, device, iters=10):
     xf, wf = x.float(), w1.float()
     t = []
     for fn in (lambda: ops.linear_f32(xf, wf, b1), lambda: F.linear(xf, wf, b1)):
-        for _ in range(2):
+        for _ in range(3):
             fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(3):
+        for _ in range(iters):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        t.append(e0.elapsed_time(e1) / 3)
+        t.append(e0.elapsed_time(e1) / iters)
     flop = 2.0 * M * d * di
     res["linear_f32_3xtf32"] = {"ms": t[0], "TFLOPs": flop / t[0] / 1e9, "torch_ms": t[1], "torch_TFLOPs": flop / t[1] / 1e9,
                                 "shape": "M=%d K=%d N=%d f32" % (M, d, di)}
