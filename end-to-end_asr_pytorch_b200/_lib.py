@@ -26,6 +26,8 @@ SIGNATURES = {
     "asr_launch_count": (ctypes.c_uint64, []),
     "asr_cif_fwd_f32": (_c_int, [_vp, _vp, _c_float, _c_int, _c_int, _c_int, _c_int,
                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "asr_cif_fwd_hint_f32": (_c_int, [_vp, _vp, _c_float, _c_int, _c_int, _c_int, _c_int,
+                                      _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _vp]),
     "asr_cif_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
     "asr_cif_bwd_f32": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int,
                                  _vp, _vp, _vp, _c_size_t, _vp]),

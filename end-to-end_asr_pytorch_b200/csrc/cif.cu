@@ -750,6 +750,13 @@ using namespace asr;
 extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float threshold, int B, int T, int H, int L,
                                float* out, int* fire_t, int* n_fired, float* cur, float* rem, int* sched,
                                float* alpha_sum, const float* target_num, float* qua_term, void* stream) {
+    return asr_cif_fwd_hint_f32(hidden, alphas, threshold, B, T, H, L, out, fire_t, n_fired, cur, rem, sched, alpha_sum,
+                                target_num, qua_term, 0, stream);
+}
+
+extern "C" int asr_cif_fwd_hint_f32(const float* hidden, const float* alphas, float threshold, int B, int T, int H, int L,
+                                    float* out, int* fire_t, int* n_fired, float* cur, float* rem, int* sched,
+                                    float* alpha_sum, const float* target_num, float* qua_term, int kernel_hint, void* stream) {
     ASR_REQUIRE(B > 0 && T > 0 && H > 0 && L >= 0, "asr_cif_fwd_f32: bad shape B=%d T=%d H=%d L=%d", B, T, H, L);
     ASR_REQUIRE(hidden && alphas && n_fired && cur && rem && sched && alpha_sum, "asr_cif_fwd_f32: null pointer");
     ASR_REQUIRE(L == 0 || (out && fire_t), "asr_cif_fwd_f32: null output with L=%d", L);
@@ -759,7 +766,7 @@ extern "C" int asr_cif_fwd_f32(const float* hidden, const float* alphas, float t
     CifFwdArgs a{hidden, alphas, threshold, B, T, H, L, out, fire_t, n_fired, cur, rem, sched, alpha_sum, target_num, qua_term};
 
     const bool vec4_ok = (H % 4 == 0) && aligned16(hidden) && (L == 0 || aligned16(out));
-    int variant = get_opt("cif_fwd_variant");
+    int variant = kernel_hint > 0 ? kernel_hint : get_opt("cif_fwd_variant");      // per-call hint first, then the process-wide option
     bool auto_v2 = false;
     if (variant == 0) {
         // measured on B200 (tools/gpu_probe.py cif): with enough (utterance, 128-column) slices to keep

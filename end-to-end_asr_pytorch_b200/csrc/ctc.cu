@@ -292,7 +292,15 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
     float* occ = reinterpret_cast<float*>(dupn + 32 * NH);   // [32*NH] per-frame label occupancies (repeat merging)
 
     // ---- per-lane lattice description ------------------------------------------
-    for (int j = lane; j < 32 * NH; j += 32) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
+    // A label outside [0,V) or equal to the blank has no lattice of its own (its gradient entry would collide
+    // with the blank's in K3): the utterance is reported as NaN loss / NaN gradient instead of a silently wrong one.
+    int bad_label = 0;
+    for (int j = lane; j < 32 * NH; j += 32) {
+        const long long c = (j < Sb) ? (long long)__ldg(a.targets + (size_t)b * a.S + j) : -1;
+        if (j < Sb && (c < 0 || c >= a.V || c == a.blank)) bad_label = 1;
+        tgt[j] = (int)c;
+    }
+    bad_label = __any_sync(0xffffffffu, bad_label);
     __syncwarp();
     Lattice<NS> lat;
     bool vl[NH], vb[NH], leader[NH];
@@ -383,10 +391,10 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
         const float a_end = fin[2 * Sb];
         const float a_lab = (Sb > 0) ? fin[2 * Sb - 1] : kNeg;
         const float ll2 = lse2(a_end, a_lab);       // of the rows relative to their blanks
-        feasible = ll2 > -1.0e29f;
+        feasible = ll2 > -1.0e29f && !bad_label;
         nll2 = -ll2;
         const float off = warp_sum(off_acc);
-        if (lane == 0) a.nll[b] = feasible ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
+        if (lane == 0) a.nll[b] = bad_label ? __int_as_float(0x7fc00000) : feasible ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
     }
     if (a.g == nullptr) return;
 
@@ -595,8 +603,13 @@ __global__ void __launch_bounds__(128) ctc_lattice_mitm_kernel(const CtcArgs a, 
     auto bar_full = [&](int c) { return 1 + 4 * half + (c & 1); };
     auto bar_free = [&](int c) { return 3 + 4 * half + (c & 1); };
 
-    for (int j = threadIdx.x; j < 32 * NH; j += 128) tgt[j] = (j < Sb) ? (int)__ldg(a.targets + (size_t)b * a.S + j) : -1;
-    __syncthreads();
+    int bad_label = 0;      // see ctc_lattice_kernel
+    for (int j = threadIdx.x; j < 32 * NH; j += 128) {
+        const long long c = (j < Sb) ? (long long)__ldg(a.targets + (size_t)b * a.S + j) : -1;
+        if (j < Sb && (c < 0 || c >= a.V || c == a.blank)) bad_label = 1;
+        tgt[j] = (int)c;
+    }
+    bad_label = __syncthreads_or(bad_label);
     Lattice<NS> lat;
     bool vl[NH], vb[NH];
 #pragma unroll
@@ -737,10 +750,10 @@ __global__ void __launch_bounds__(128) ctc_lattice_mitm_kernel(const CtcArgs a, 
         const float ll2 = m + lg2f(sum);            // of the rows relative to their blanks
         const float off = warp_sum(off_acc) + mid->off_b;
         if (lane == 0) {
-            const bool ok = ll2 > -1.0e29f;
+            const bool ok = ll2 > -1.0e29f && !bad_label;
             mid->feasible = ok;
             mid->nll2 = -ll2;
-            a.nll[b] = ok ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
+            a.nll[b] = bad_label ? __int_as_float(0x7fc00000) : ok ? -(ll2 + off) * 0.6931471805599453f : -neg_inf();
         }
     }
     __syncthreads();
@@ -1048,7 +1061,7 @@ constexpr int kLatStreams = 8;
 struct CtcPipe {
     cudaStream_t lat[kLatStreams] = {};
     cudaEvent_t k1[kTickets][kMaxChunks] = {}, done[kTickets][kMaxChunks] = {};
-    std::atomic<int> next_ticket{0};
+    std::atomic<int> busy[kTickets] = {};      // 1 between a begin and its finish
 };
 static CtcPipe* ctc_pipe() {
     static std::mutex mu;
@@ -1164,7 +1177,17 @@ extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, co
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CtcPipe* p = ctc_pipe();
     if (p == nullptr) return 3;
-    const int tk = p->next_ticket.fetch_add(1) % kTickets;
+    int tk = -1;
+    for (int t = 0; t < kTickets && tk < 0; ++t) {
+        int expected = 0;
+        if (p->busy[t].compare_exchange_strong(expected, 1)) tk = t;
+    }
+    ASR_REQUIRE(tk >= 0, "asr_ctc_begin_f32: %d calls are already between begin and finish on this device (finish one first)", kTickets);
+    struct Guard {      // a begin that fails half way gives its ticket back
+        std::atomic<int>& f;
+        bool keep = false;
+        ~Guard() { if (!keep) f.store(0); }
+    } guard{p->busy[tk]};
     const int nchunk = ctc_slices(B, T);
     for (int c = 0; c < nchunk; ++c) {
         int b0, n;
@@ -1180,6 +1203,7 @@ extern "C" int asr_ctc_begin_f32(const float* logits, const int64_t* targets, co
         if (rc != 0) return rc;
         ASR_CHECK_CUDA(cudaEventRecord(p->done[tk][c], ls));
     }
+    guard.keep = true;
     *ticket = tk;
     return 0;
 }
@@ -1199,6 +1223,11 @@ static int ctc_finish_impl(const float* logits, const int64_t* targets, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CtcPipe* p = ctc_pipe();
     if (p == nullptr) return 3;
+    ASR_REQUIRE(p->busy[ticket].load() == 1, "asr_ctc_finish_f32: ticket %d is not open (finish called twice, or without begin)", ticket);
+    struct Release {      // the ticket is free again once the waits below are queued (stream order protects the events)
+        std::atomic<int>& f;
+        ~Release() { f.store(0); }
+    } release{p->busy[ticket]};
     const int nchunk = ctc_slices(B, T);
     for (int c = 0; c < nchunk; ++c) {
         int b0, n;

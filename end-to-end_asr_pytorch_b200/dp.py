@@ -31,6 +31,9 @@ class GradAllReduce:
         sync = GradAllReduce(model, bucket_mb=25)
         loss.backward()        # buckets are all-reduced as they fill
         sync.finish()          # wait + average; then optimizer.step()
+
+    One backward pass per reset()/finish() pair (a second one raises: it would add local gradients to sums that
+    are already reduced).  Collectives are issued in a fixed bucket order on every rank.
     """
 
     def __init__(self, module, bucket_mb=25.0, process_group=None):
@@ -54,6 +57,7 @@ class GradAllReduce:
             self._seal(cur)
         self._pending = [0] * len(self.buckets)
         self._handles = []
+        self._next = 0             # buckets are all-reduced strictly in index order on every rank
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
         self.reset()
 
@@ -72,26 +76,38 @@ class GradAllReduce:
             flat.zero_()
             self._pending[i] = len(plist)
         self._handles = []
+        self._next = 0
+
+    def _launch_ready(self, force=False):
+        """All-reduce buckets in index order: bucket i goes out once it is complete AND every bucket before it has gone
+        out, so all ranks issue the same sequence of collectives even when their gradients become ready in a
+        different order (or some never do: `force` sends those from finish())."""
+        while self._next < len(self.buckets) and (force or self._pending[self._next] == 0):
+            flat = self.buckets[self._next][0]
+            if self.world > 1:
+                self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+            self._next += 1
 
     def _on_grad(self, p):
         i = self._owner[p]
         self._pending[i] -= 1
-        if self._pending[i] == 0 and self.world > 1:
-            flat = self.buckets[i][0]
-            self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+        if self._pending[i] < 0 or i < self._next:
+            # a second backward() into a bucket that may already have been summed over ranks would be reduced twice
+            raise RuntimeError("GradAllReduce: a parameter received a second gradient before finish(); one backward pass "
+                               "per reset()/finish() (accumulate micro-batches into the loss, or call finish() in between)")
+        if self._pending[i] == 0:
+            self._launch_ready()
 
     def finish(self):
         """Wait for the outstanding all-reduces and turn the sums into means."""
-        if self.world > 1:
-            for i, (flat, _) in enumerate(self.buckets):
-                if self._pending[i] != 0:      # some parameter of this bucket got no gradient this step
-                    self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
-            for h, flat in self._handles:
-                h.wait()
-                flat.div_(self.world)
+        self._launch_ready(force=True)      # buckets with a parameter that got no gradient this step go out here
+        for h, flat in self._handles:
+            h.wait()
+            flat.div_(self.world)
         for i, (_, plist) in enumerate(self.buckets):
             self._pending[i] = len(plist)
         self._handles = []
+        self._next = 0
 
     def grad_bytes(self):
         return sum(flat.numel() * flat.element_size() for flat, _ in self.buckets)

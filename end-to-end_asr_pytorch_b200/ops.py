@@ -405,6 +405,31 @@ class _MhaCoreFunction(torch.autograd.Function):
         return g_q, g_k, g_v, None, None, None, None, None, None
 
 
+def _check_mha_args(what, q, k, v, kv_len, mask):
+    """Shapes the kernels take as raw pointers: k / v [B,Lk,Hh,D] matching q [B,Lq,Hh,D] with D = 64, kv_len [B],
+    mask broadcastable to [B,Lq,Lk] (expanded here - the reference's masked_fill accepts such masks too)."""
+    B, Lq, Hh, D = q.shape
+    if D != 64:
+        raise ValueError("%s: head dimension %d, the sm_100a attention kernels are built for 64" % (what, D))
+    for name, t in (("k", k), ("v", v)):
+        if t is not None and (t.shape[0] != B or t.shape[2] != Hh or t.shape[3] != D or t.shape[1] != k.shape[1]):
+            raise ValueError("%s: %s %s does not match q %s" % (what, name, tuple(t.shape), tuple(q.shape)))
+    Lk = k.shape[1]
+    if kv_len is not None:
+        if kv_len.numel() != B:
+            raise ValueError("%s: kv_len must have one entry per batch row (%d), got %s" % (what, B, tuple(kv_len.shape)))
+        kv_len = kv_len.reshape(B).to(device=q.device, dtype=torch.int32).contiguous()
+    if mask is not None:
+        if mask.dim() != 3:
+            raise ValueError("%s: mask must be [B, Lq, Lk] (or broadcastable to it), got %s" % (what, tuple(mask.shape)))
+        try:
+            mask = mask.to(device=q.device).expand(B, Lq, Lk)
+        except RuntimeError:
+            raise ValueError("%s: mask %s is not broadcastable to [%d, %d, %d]" % (what, tuple(mask.shape), B, Lq, Lk)) from None
+        mask = mask.ne(0).to(torch.uint8).contiguous()
+    return kv_len, mask
+
+
 def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_p=0.0, seed=None):
     """softmax(mask(q k^T * scale)) v on the tensor cores.
 
@@ -422,10 +447,7 @@ def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_
     if scale is None:
         scale = 1.0 / (q.shape[-1] ** 0.5)
     qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
-    if kv_len is not None:
-        kv_len = kv_len.to(device=q.device, dtype=torch.int32).contiguous()
-    if mask is not None:
-        mask = mask.to(device=q.device).ne(0).to(torch.uint8).contiguous()
+    kv_len, mask = _check_mha_args("mha_core", q, k, v, kv_len, mask)
     if dropout_p > 0.0 and seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     return _MhaCoreFunction.apply(qb, kb, vb, kv_len, mask, bool(causal), float(scale), float(dropout_p),
@@ -450,10 +472,7 @@ def mha_probs(q, k, kv_len=None, mask=None, causal=False, scale=None):
     if scale is None:
         scale = 1.0 / (D ** 0.5)
     qb, kb = q.detach().to(torch.bfloat16).contiguous(), k.detach().to(torch.bfloat16).contiguous()
-    if kv_len is not None:
-        kv_len = kv_len.to(device=q.device, dtype=torch.int32).contiguous()
-    if mask is not None:
-        mask = mask.to(device=q.device).ne(0).to(torch.uint8).contiguous()
+    kv_len, mask = _check_mha_args("mha_probs", q, k, None, kv_len, mask)
     attn = torch.empty((Hh * B, Lq, Lk), dtype=torch.float32, device=q.device)
     with torch.cuda.device(q.device):
         check(_lib.lib().asr_mha_probs_f32(ptr(qb), ptr(kb), ptr(kv_len), ptr(mask), int(causal), B, Hh, Lq, Lk, D,

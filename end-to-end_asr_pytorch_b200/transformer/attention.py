@@ -7,11 +7,15 @@ layer_norm`), and `forward(q, k, v, mask=None) -> (output, attn)`.
 What changes: the scaled-dot-product core (bmm / scale / masked_fill / softmax / bmm
 and the three head-major permute copies, reference :47-57 and :74-86) is one
 tcgen05 kernel working in bf16 with fp32 accumulation directly on the
-[B, L, heads, 64] projection outputs.  The attention-probability matrix is never
-materialised on the training path; `attn` is returned as None unless the module is
-built with `return_attn=True` (every training caller of the reference discards it,
-encoder.py:72, decoder.py:628-633), in which case it is computed by a separate
-kernel in the reference's head-major row order.
+[B, L, heads, 64] projection outputs.  The core never materialises the attention
+probabilities; the second return value `attn` ([(heads*B), Lq, Lk] fp32, head-major
+rows like attention.py:47,62) comes from a separate kernel.  It is returned by default,
+like the reference.  Every training caller discards it (encoder.py:72,
+decoder.py:628-633), so the shells of this package build their layers with
+`return_attn=False` (attn = None, no second kernel) and `patch.install()` turns the
+class default off the same way.  In evaluation mode `attn` equals the reference's; in
+training mode the reference returns the probabilities AFTER dropout (attention.py:83-86)
+while this kernel returns them before dropout.
 
 Dropout on the probabilities (reference :83) happens inside the kernel in training
 mode: a counter-based generator keyed by a per-call seed (drawn from torch's CPU
@@ -30,7 +34,9 @@ from .module import fused_linear_ok, Linear
 class MultiheadAttention(nn.Module):
     ''' Multi-Head Attention module (same parameters as the reference) '''
 
-    def __init__(self, d_model, n_head, d_k=64, d_v=64, dropout=0.1, return_attn=False):
+    RETURN_ATTN_DEFAULT = True      # class-wide default of `return_attn` (patch.install() turns it off)
+
+    def __init__(self, d_model, n_head, d_k=64, d_v=64, dropout=0.1, return_attn=None):
         super().__init__()
         if d_k != 64 or d_v != 64:
             raise ValueError("the sm_100a attention core is built for d_k = d_v = 64 (every reference recipe)")
@@ -78,7 +84,7 @@ class MultiheadAttention(nn.Module):
         ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature),
                        dropout_p=p_attn)
         attn = None
-        if self.return_attn:
+        if self.RETURN_ATTN_DEFAULT if self.return_attn is None else self.return_attn:
             attn = mha_probs(qh, kh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
 
         output = ctx.reshape(sz_b, len_q, n_head * d_v).to(q.dtype)

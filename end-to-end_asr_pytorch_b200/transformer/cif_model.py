@@ -71,7 +71,7 @@ class CIF_Model(nn.Module):
         num = (targets > 0).float().sum(-1)
         noise = torch.rand(targets.size(0)).to(num.device)
         num_noise = num + noise - 0.5
-        if self.fused_alpha and hasattr(self.assigner, "forward_scaled"):
+        if getattr(self, "fused_alpha", False) and hasattr(self.assigner, "forward_scaled"):
             alpha, _num = self.assigner.forward_scaled(encoder_outputs, len_sequence, num_noise)
         else:
             alpha = self.assigner(encoder_outputs, len_sequence)
@@ -86,7 +86,11 @@ class CIF_Model(nn.Module):
 
     def cif(self, hidden, alphas, threshold, log=False):
         """Integrate-and-fire (reference :57-106): [B,T,H], [B,T] -> [B,L,H] with
-        L = max_b round(sum_t alphas).  `log` is accepted for signature parity."""
+        L = max_b round(sum_t alphas).  `log` is accepted for signature parity.
+        The kernels work in fp32 like the reference; a reduced-precision model (bf16 evaluation) is
+        cast at this boundary and the fired frames go back to the activations' dtype."""
+        if hidden.dtype != torch.float32 or alphas.dtype != torch.float32:
+            return _cif_op(hidden.float(), alphas.float(), threshold).to(hidden.dtype)
         return _cif_op(hidden, alphas, threshold)
 
     def recognize(self, input, input_length, char_list, args, threshold=0.95, target_num=None):

@@ -15,7 +15,7 @@ class EncoderLayer(nn.Module):
 
     def __init__(self, d_model, d_inner, n_head, dropout=0.1):
         super().__init__()
-        self.slf_attn = MultiheadAttention(d_model, n_head, dropout=dropout)
+        self.slf_attn = MultiheadAttention(d_model, n_head, dropout=dropout, return_attn=False)      # every caller here discards attn
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
 
     def forward(self, enc_input, non_pad_mask=None, slf_attn_mask=None, kv_len=None, causal=False):
@@ -42,8 +42,9 @@ class Encoder(nn.Module):
         """N x T x D, N -> N x T x d_model.  The key-padding mask of the reference
         (get_attn_pad_mask, utils.py:157-165) is handed to the attention kernel in its
         structured form, as per-utterance key lengths."""
-        non_pad_mask = sequence_mask(input_lengths, padded_input.size(1)).unsqueeze(-1)
         x = self.dropout(self.layer_norm_in(self.linear_in(padded_input)) + self.positional_encoding(padded_input))
+        # in the activations' dtype: a float32 mask would promote bf16 activations (and break the fused bf16 layers)
+        non_pad_mask = sequence_mask(input_lengths, padded_input.size(1), dtype=x.dtype).unsqueeze(-1)
         for layer in self.layer_stack:
             x = layer(x, non_pad_mask=non_pad_mask, kv_len=input_lengths)
         return x

@@ -98,6 +98,19 @@ int asr_cif_fwd_f32(const float* hidden, const float* alphas, float threshold,
                     float* cur, float* rem, int* sched,
                     float* alpha_sum, const float* target_num, float* qua_term,
                     void* stream);
+/*
+ * Same call with a per-call kernel choice: kernel_hint = 0 lets the library choose (like asr_cif_fwd_f32), 1 = plain
+ * one-warp kernel, 2 = one-warp TMA pipeline, 3 = warp-specialised TMA kernel (the one that disturbs co-running
+ * latency-bound kernels least), 4 = schedule + segment-parallel rows.  Every choice produces identical bits; the hint is
+ * tuning state that belongs to the call site (e.g. "queued between asr_ctc_begin_f32 and asr_ctc_finish_f32"), not to
+ * the process-wide option table.
+ */
+int asr_cif_fwd_hint_f32(const float* hidden, const float* alphas, float threshold,
+                         int B, int T, int H, int L,
+                         float* out, int* fire_t, int* n_fired,
+                         float* cur, float* rem, int* sched,
+                         float* alpha_sum, const float* target_num, float* qua_term,
+                         int kernel_hint, void* stream);
 
 /*
  * Analytic backward of the above (SURVEY.md 8a row a2').
@@ -237,9 +250,12 @@ int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
  * almost idle - bench.py puts the CIF forward/backward pair there.  finish then
  * applies the whole batch in one launch (option "ctc_finish_per_slice" = 1: slice
  * by slice as each lattice completes, which is what asr_ctc_fwd_bwd_f32 does).  nll and
- * g_logits are complete (in stream order) after finish.  At most 4 begins may be
- * outstanding per device.  asr_ctc_fwd_bwd_f32 == begin immediately followed by
- * finish. */
+ * g_logits are complete (in stream order) after finish.  The library owns the
+ * lattice streams and 4 ticket slots per device: a 5th begin before any finish
+ * returns an error (it does not alias an open ticket), and finish on a ticket that
+ * is not open returns an error.  asr_ctc_fwd_bwd_f32 == begin immediately followed
+ * by finish.  A target label outside [0,V) or equal to `blank` makes that
+ * utterance's nll and gradient rows NaN (all CTC entry points). */
 int asr_ctc_begin_f32(const float* logits, const int64_t* targets,
                       const int* in_len, const int* tgt_len,
                       int B, int T, int V, int S, int blank,

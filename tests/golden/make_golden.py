@@ -30,6 +30,8 @@ Every array is produced by reference code:
                nll from F.ctc_loss(reduction='none') on the same log-probs.
   * MHA      : transformer.attention.MultiheadAttention (attention.py:6-86),
                eval mode (dropout off), with the masks from utils/utils.py.
+  * Transformer / Conv_CTC_Transformer (transformer.py): small models of BASELINE
+               configs 3 and 2 through forward, cal_ce_loss / cal_ctc_ce_loss and autograd.
 Outputs are small .npz files committed next to this script.
 """
 import os
@@ -429,7 +431,83 @@ def make_cif_model(cif_model, tloss):
           "losses", float(qua), float(ctc), float(ce), "params", sum(p.numel() for p in model.parameters()))
 
 
+def make_transformer_models(tloss):
+    """The encoder-decoder shells of BASELINE configs 2 and 3 built from the reference's own classes and run
+    through their forward, the solver's loss call and autograd (transformer.py:21-35,135-153; solver.py:23-32,83-88).
+    Needs two of the documented shims: `decoder.pad_list` -> the padded tensor (decoder.py:54-56 takes the
+    tuple utils.pad_list returns), and plain `Transformer` is built as Transformer(encoder, decoder) because
+    `create_model` recurses (transformer.py:72)."""
+    import transformer.decoder as rdec
+    import transformer.transformer as rtr
+    import utils.utils as uu
+    from transformer.conv_encoder import Conv2dSubsample
+    from transformer.encoder import Encoder
+    rdec.pad_list = lambda xs, pad_value, max_len=None: uu.pad_list(xs, pad_value, max_len)[0]      # shim 2
+    d_model, vocab = 64, 100
+    out = {}
+
+    def pack(prefix, model, named_grads):
+        for k, v in model.state_dict().items():
+            if not k.endswith(".pe"):
+                out[prefix + "sd:" + k] = v.numpy()
+        for k, p_ in model.named_parameters():
+            if k in named_grads:
+                out[prefix + "grad:" + k] = p_.grad.numpy()
+
+    # ---- config 3: Transformer(Encoder(320, ...), Decoder(...)), CE loss --------------------------------------
+    torch.manual_seed(2027)
+    enc = Encoder(d_input=320, n_layers=2, n_head=2, d_model=d_model, d_inner=128, dropout=0.1)
+    dec = rdec.Decoder(sos_id=2, eos_id=3, n_tgt_vocab=vocab, n_layers=2, n_head=2, d_model=d_model, d_inner=128, dropout=0.1)
+    model = rtr.Transformer(enc, dec).eval()                       # shim 4
+    g = torch.Generator().manual_seed(1237)
+    B, T, S = 5, 50, 9
+    feats = torch.randn(B, T, 320, generator=g)
+    lens = torch.tensor([50, 50, 44, 37, 29])
+    targets = torch.randint(4, vocab - 1, (B, S), generator=g)
+    tl = torch.tensor([9, 7, 8, 5, 3])
+    targets = targets * (torch.arange(S)[None, :] < tl[:, None]).long()
+    logits, targets_eos = model(feats, lens, targets)
+    ce = tloss.cal_ce_loss(logits, targets_eos, smoothing=0.1)
+    ce.backward()
+    out.update({"t:feats": feats.numpy(), "t:lens": lens.numpy(), "t:targets": targets.numpy(), "t:logits": logits.detach().numpy(),
+                "t:targets_eos": targets_eos.numpy(), "t:ce": ce.detach().numpy()})
+    pack("t:", model, ("encoder.linear_in.weight", "decoder.tgt_word_prj.weight", "decoder.tgt_word_emb.weight",
+                       "decoder.layer_stack.0.enc_attn.w_ks.weight", "decoder.layer_stack.1.slf_attn.fc.weight",
+                       "encoder.layer_stack.0.pos_ffn.w_1.bias"))
+    print("transformer: logits", tuple(logits.shape), "ce", float(ce))
+
+    # ---- config 2's model: Conv_CTC_Transformer, CTC (targets + <eos>) + CE -----------------------------------
+    torch.manual_seed(2028)
+    conv = Conv2dSubsample(d_input=320, d_model=d_model, n_layers=3)
+    enc = Encoder(d_input=d_model, n_layers=1, n_head=2, d_model=d_model, d_inner=128, dropout=0.1)
+    dec = rdec.Decoder(sos_id=2, eos_id=3, n_tgt_vocab=vocab, n_layers=1, n_head=2, d_model=d_model, d_inner=128, dropout=0.1)
+    model = rtr.Conv_CTC_Transformer(conv, enc, dec).eval()
+    g = torch.Generator().manual_seed(1238)
+    B, T, S = 6, 167, 12
+    feats = torch.randn(B, T, 320, generator=g)
+    lens = torch.tensor([167, 167, 158, 149, 131, 120])
+    feats = feats * (torch.arange(T)[None, :, None] < lens[:, None, None]).float()
+    targets = torch.randint(4, vocab - 1, (B, S), generator=g)
+    tl = torch.tensor([12, 11, 12, 9, 8, 6])
+    targets = targets * (torch.arange(S)[None, :] < tl[:, None]).long()
+    ctc_logits, len_ctc, logits, targets_eos = model(feats, lens, targets)
+    ctc, ce = tloss.cal_ctc_ce_loss(ctc_logits, len_ctc, logits, targets_eos, smoothing=0.1)
+    (ctc + ce).backward()
+    out.update({"c:feats": feats.numpy(), "c:lens": lens.numpy(), "c:targets": targets.numpy(),
+                "c:ctc_logits": ctc_logits.detach().numpy(), "c:len_ctc": len_ctc.numpy(), "c:logits": logits.detach().numpy(),
+                "c:targets_eos": targets_eos.numpy(), "c:ctc": ctc.detach().numpy(), "c:ce": ce.detach().numpy()})
+    pack("c:", model, ("ctc_fc.weight", "conv_encoder.affine.weight", "decoder.tgt_word_prj.weight",
+                       "decoder.layer_stack.0.enc_attn.w_qs.weight", "encoder.layer_stack.0.slf_attn.w_vs.bias"))
+    np.savez_compressed(os.path.join(HERE, "transformer_models.npz"), **out)
+    print("conv_ctc_transformer: logits", tuple(logits.shape), "ctc_logits", tuple(ctc_logits.shape), "losses", float(ctc), float(ce))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "transformer_models":      # only the round-2 addition
+        cif_model, tloss, closs, attention, uutils = _import_reference()
+        torch.set_num_threads(1)
+        make_transformer_models(tloss)
+        return
     cif_model, tloss, closs, attention, uutils = _import_reference()
     torch.set_num_threads(1)
     make_cif(cif_model)
@@ -442,6 +520,7 @@ def main():
     make_mha(attention, uutils)
     make_masks(uutils)
     make_cif_model(cif_model, tloss)
+    make_transformer_models(tloss)
 
 
 if __name__ == "__main__":
