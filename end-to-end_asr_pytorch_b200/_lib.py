@@ -62,6 +62,11 @@ SIGNATURES = {
     "asr_mha_bwd_dropout_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
                                           _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, ctypes.c_uint64,
                                           _vp, _vp, _vp, _vp, _c_size_t, _vp]),
+    "asr_mha_fwd_dropout_dev_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                              _c_float, _c_float, _vp, ctypes.c_uint64, _vp, _vp, _vp]),
+    "asr_mha_bwd_dropout_dev_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int,
+                                              _c_int, _c_int, _c_int, _c_int, _c_int, _c_float, _c_float, _vp, ctypes.c_uint64,
+                                              _vp, _vp, _vp, _vp, _c_size_t, _vp]),
     "asr_mha_dropout_keep_prob": (_c_float, [_c_float]),
     "asr_mha_dropout_keep_u8": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_float, ctypes.c_uint64, _vp, _vp]),
     "asr_mha_probs_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -4,21 +4,27 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <map>
-#include <mutex>
-#include <string>
 
 namespace asr {
 
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
-static std::mutex g_opt_mu;
-static std::map<std::string, int>& opts() {
-    static std::map<std::string, int> m = {
-        {"cif_fwd_variant", 0}, {"cif_fwd_width", 0}, {"cif_fwd_stages", 0}, {"cif_fwd_rows", 0},
-        {"mha_variant", 0}, {"ctc_fuse_apply", 0}, {"ctc_lattice_variant", 0}, {"ctc_chunks", 0}, {"ctc_finish_per_slice", 0}, {"mha_bwd_groups", 0}, {"gemm_variant", 0}, {"gemm_f32_bn", 0},
-    };
-    return m;
+// Tuning options: a fixed table of atomics, read on every call without a lock (the names are compile-time constants
+// of the callers, a dozen strcmp's are cheaper than a mutex'd std::map<std::string> lookup).
+struct Opt {
+    const char* name;
+    std::atomic<int> value;
+};
+static Opt g_opts[] = {
+    {"cif_fwd_variant", {0}}, {"cif_fwd_width", {0}}, {"cif_fwd_stages", {0}}, {"cif_fwd_rows", {0}},
+    {"mha_variant", {0}}, {"ctc_fuse_apply", {0}}, {"ctc_lattice_variant", {0}}, {"ctc_chunks", {0}},
+    {"ctc_finish_per_slice", {0}}, {"mha_bwd_groups", {0}}, {"gemm_variant", {0}}, {"gemm_f32_bn", {0}},
+    {"gemm_split_k", {0}}, {"ctc_lattice_split", {0}},
+};
+static Opt* find_opt(const char* key) {
+    for (Opt& o : g_opts)
+        if (strcmp(o.name, key) == 0) return &o;
+    return nullptr;
 }
 
 void set_error(const char* fmt, ...) {
@@ -29,9 +35,8 @@ void set_error(const char* fmt, ...) {
 }
 
 int get_opt(const char* key) {
-    std::lock_guard<std::mutex> lk(g_opt_mu);
-    auto it = opts().find(key);
-    return it == opts().end() ? 0 : it->second;
+    const Opt* o = find_opt(key);
+    return o ? o->value.load(std::memory_order_relaxed) : 0;
 }
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
@@ -116,6 +121,8 @@ int asr_device_ok(void) {
         asr::set_error("cudaGetDevice: %s", cudaGetErrorString(e));
         return 1;
     }
+    static std::atomic<uint64_t> ok_mask{0};      // devices already checked (this runs on every compute call)
+    if (dev < 64 && (ok_mask.load(std::memory_order_relaxed) >> dev) & 1) return 0;
     int major = 0;
     e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
     if (e != cudaSuccess) {
@@ -126,28 +133,27 @@ int asr_device_ok(void) {
         asr::set_error("device %d has compute capability %d.x; libasr_sm100 is sm_100a only", dev, major);
         return 2;
     }
+    if (dev < 64) ok_mask.fetch_or(1ull << dev, std::memory_order_relaxed);
     return 0;
 }
 
 int asr_set_option(const char* key, int value) {
-    std::lock_guard<std::mutex> lk(asr::g_opt_mu);
-    auto it = asr::opts().find(key);
-    if (it == asr::opts().end()) {
-        asr::set_error("unknown option '%s'", key);
+    asr::Opt* o = key ? asr::find_opt(key) : nullptr;
+    if (o == nullptr) {
+        asr::set_error("unknown option '%s'", key ? key : "(null)");
         return 2;
     }
-    it->second = value;
+    o->value.store(value, std::memory_order_relaxed);
     return 0;
 }
 
 int asr_get_option(const char* key, int* value) {
-    std::lock_guard<std::mutex> lk(asr::g_opt_mu);
-    auto it = asr::opts().find(key);
-    if (it == asr::opts().end()) {
-        asr::set_error("unknown option '%s'", key);
+    const asr::Opt* o = key ? asr::find_opt(key) : nullptr;
+    if (o == nullptr || value == nullptr) {
+        asr::set_error("unknown option '%s'", key ? key : "(null)");
         return 2;
     }
-    *value = it->second;
+    *value = o->value.load(std::memory_order_relaxed);
     return 0;
 }
 

@@ -45,7 +45,17 @@ struct MhaFwdArgs {
     uint32_t drop_thresh;       // 0 = no dropout
     float inv_keep;
     uint32_t seed_lo, seed_hi;
+    const uint64_t* seed_dev;   // not null: the seed is *seed_dev + (seed_hi:seed_lo), read on the device (a step captured in
+                                // a CUDA graph gets fresh masks on every replay by bumping one device word)
 };
+
+__device__ __forceinline__ void effective_seed(const uint64_t* seed_dev, uint32_t& lo, uint32_t& hi) {
+    if (seed_dev != nullptr) {
+        const uint64_t s = __ldg(reinterpret_cast<const unsigned long long*>(seed_dev)) + (((uint64_t)hi << 32) | lo);
+        lo = (uint32_t)s;
+        hi = (uint32_t)(s >> 32);
+    }
+}
 
 // Philox4x32-7 (counter-based: forward and backward regenerate the same bits from the element's
 // coordinates).  One call yields the 16 random bytes of keys [k16*16, k16*16+16) of row q of head bh.
@@ -83,271 +93,8 @@ struct __align__(8) MhaBarriers {
     uint32_t pad;
 };
 
-// Per-tile resources of the softmax warps (one 128-query tile).
-struct FwdTile {
-    uint64_t* s_full;
-    uint64_t* s_free;
-    uint64_t* p_full;
-    uint64_t* pv_full;
-    uint32_t tmem_s, tmem_pv, tmem_l;
-    unsigned char* sP;
-};
-
-// Online softmax + epilogue of one 128-query tile: thread `row` owns query row q0 + row (= TMEM lane row).
-__device__ __forceinline__ void fwd_softmax_tile(const MhaFwdArgs& a, const FwdTile& t, int row, int q0, int b, int h,
-                                                 int kvlen, int nblk) {
-        const int qi = q0 + row;
-        const uint32_t lane_base = (uint32_t)((row >> 5) * 32) << 16;
-        float o[kD];
-#pragma unroll
-        for (int i = 0; i < kD; ++i) o[i] = 0.0f;
-        float m_run = -INFINITY;   // running max of the raw scores
-        float l_run = 0.0f;
-        const float c = a.scale_log2;
-        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
-
-        for (int j = 0; j < nblk; ++j) {
-            const int key0 = j * kBN;
-            // mask limit for this row: keys >= lim are masked
-            int lim = kvlen;
-            if (a.causal) lim = min(lim, qi + 1);
-            const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
-
-            mbar_wait(t.s_full, j & 1);
-            tc_fence_after();
-            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + cc + i;
-                    bool dead = key >= lim;
-                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                    if (dead) r[i] = 0xff800000u;   // -inf
-                }
-            };
-            // pass 1: row max.  TMEM loads are double-buffered: chunk c+1 is in flight while chunk c is reduced.
-            float m_blk = -INFINITY;
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t.tmem_s + lane_base, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int cc = 0; cc < kBN; cc += 64) {
-                    tmem_ld32_issue(t.tmem_s + lane_base + cc + 32, rb);
-                    if (need_mask) apply_mask(ra, cc);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(ra[i]));
-                    tmem_ld_wait();
-                    if (cc + 64 < kBN) tmem_ld32_issue(t.tmem_s + lane_base + cc + 64, ra);
-                    if (need_mask) apply_mask(rb, cc + 32);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(rb[i]));
-                    if (cc + 64 < kBN) tmem_ld_wait();
-                }
-            }
-            const float m_new = fmaxf(m_run, m_blk);
-            const float m_use = (m_new == -INFINITY) ? 0.0f : m_new;   // fully masked so far: keep exp2 finite
-            const float alpha = ex2_approx((m_run - m_use) * c);       // m_run = -inf -> 0
-            const float mc = m_use * c;
-            // pass 2: probabilities -> bf16 -> shared memory (K-major, 128B swizzle), row sum
-            auto emit = [&](uint32_t (&r)[32], int cc) {
-                if (need_mask) apply_mask(r, cc);
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
-                // 32 keys = 64 bytes = four 16-byte chunks of this row's 128-byte line in key half (cc / 64)
-                unsigned char* prow = t.sP + (cc >> 6) * kTileBytes + row * 128;
-                const int chunk0 = (cc & 63) >> 3;
-#pragma unroll
-                for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = (chunk0 + q4) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(prow + chunk * 16) = make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-                }
-            };
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t.tmem_s + lane_base, ra);
-                tmem_ld_wait();
-#pragma unroll
-                for (int cc = 0; cc < kBN; cc += 64) {
-                    tmem_ld32_issue(t.tmem_s + lane_base + cc + 32, rb);
-                    emit(ra, cc);
-                    tmem_ld_wait();
-                    if (cc + 64 < kBN) tmem_ld32_issue(t.tmem_s + lane_base + cc + 64, ra);
-                    emit(rb, cc + 32);
-                    if (cc + 64 < kBN) tmem_ld_wait();
-                }
-            }
-            tc_fence_before();
-            mbar_arrive_warp(t.s_free);       // S may be overwritten by the next Q K^T
-            fence_proxy_async();              // P (generic proxy) -> visible to the tensor core (async proxy)
-            mbar_arrive_warp(t.p_full);
-
-            m_run = m_new;
-
-            mbar_wait(t.pv_full, j & 1);
-            tc_fence_after();
-            l_run = fmaf(l_run, alpha, tmem_ld1(t.tmem_l + lane_base));   // row sum of the bf16 P, from the tensor core
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(t.tmem_pv + lane_base, ra);
-                tmem_ld32_issue(t.tmem_pv + lane_base + 32, rb);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[i] = fmaf(o[i], alpha, __uint_as_float(ra[i]));
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[32 + i] = fmaf(o[32 + i], alpha, __uint_as_float(rb[i]));
-            }
-            tc_fence_before();
-        }
-        // epilogue: O / l -> bf16 -> out[b, qi, h, :]; a fully masked row is 0/0 = NaN like the reference
-        if (qi < a.Lq) {
-            const float inv = 1.0f / l_run;
-            __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD;
-#pragma unroll
-            for (int i = 0; i < kD; i += 8) {
-                uint32_t w[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const __nv_bfloat162 v2 = __floats2bfloat162_rn(o[i + 2 * u] * inv, o[i + 2 * u + 1] * inv);
-                    w[u] = *reinterpret_cast<const uint32_t*>(&v2);
-                }
-                *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-            if (a.lse != nullptr)
-                a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_run * c + log2f(l_run)) * 0.6931471805599453f;
-        }
-}
-
-constexpr int kFwdThreads = 192;
 // Q + 2x(K,V) + P + barriers = 112.1 KB, so that two CTAs (and their 2 x 256 TMEM columns) share one SM
 constexpr int kFwdSmem = kTileBytes /*Q*/ + 4 * kTileBytes /*K,V x2*/ + 2 * kTileBytes /*P*/ + 128 /*barriers*/ + 128 /*ones*/;
-
-__global__ void __launch_bounds__(kFwdThreads, 2)
-mha_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-               const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];   // 128B-swizzled tiles need 1024-byte alignment
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    unsigned char* sQ = smem;
-    unsigned char* sK = sQ + kTileBytes;          // 2 stages
-    unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
-    unsigned char* sP = sV + 2 * kTileBytes;      // [2 key halves][128 rows][128 B]
-    MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sP + 2 * kTileBytes);
-    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sP + 2 * kTileBytes + 128);   // 128 bytes of bf16 1.0
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
-    fence_proxy_async();   // generic-proxy write -> visible to the tensor core after the block barrier below
-    const int q0 = blockIdx.x * kBM;
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
-    // keys that can matter for this tile: up to kvlen, and up to the last query row when causal
-    int k_end = a.causal ? min(kvlen, q0 + kBM) : kvlen;
-    if (a.dense_mask) k_end = a.Lk;
-    const int nblk = max(1, (k_end + kBN - 1) / kBN);
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bars->q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->kv_full[s], 1);
-            mbar_init(&bars->kv_empty[s], 1);
-        }
-        mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->s_free, 4);      // one arrival per softmax warp
-        mbar_init(&bars->p_full, 4);
-        mbar_init(&bars->pv_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 5) {
-        tmem_alloc(&bars->tmem_base, 256);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    const uint32_t tmem_s = tmem;          // 128 columns: S
-    const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
-    const uint32_t tmem_l = tmem + 192;    // 16 columns: P x ones (row sums)
-
-    if (warp == 4) {
-        // ===== TMA producer =====
-        if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_q);
-            tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_v);
-            mbar_arrive_expect_tx(&bars->q_full, kTileBytes);
-            tma_load_4d(sQ, &tm_q, 0, h, q0, b, &bars->q_full);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
-                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
-                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
-                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
-            }
-        }
-    } else if (warp == 5) {
-        // ===== MMA issuer (one thread) =====
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
-            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
-            const uint32_t q_addr = smem_u32(sQ);
-            const uint32_t p_addr = smem_u32(sP);
-            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
-            fence_proxy_async();   // the ones tile was written through the generic proxy
-            mbar_wait(&bars->q_full, 0);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
-                if (j > 0) mbar_wait(&bars->s_free, (j - 1) & 1);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sK + s * kTileBytes);
-                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
-#pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk) {
-                    const uint64_t ad = smem_desc_sw128(q_addr + kk * 32, 16, 1024);
-                    const uint64_t bd = smem_desc_sw128(k_addr + kk * 32, 16, 1024);
-                    umma_bf16(tmem_s, ad, bd, idesc_s, kk > 0 ? 1u : 0u);
-                }
-                tc_commit(&bars->s_full);
-                // P V once the softmax warps have published P
-                mbar_wait(&bars->p_full, j & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < kBN / 16; ++kk) {
-                    const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
-                    umma_bf16(tmem_pv, ad, bd, idesc_pv, kk > 0 ? 1u : 0u);
-                    umma_bf16(tmem_l, ad, ones_desc, idesc_l, kk > 0 ? 1u : 0u);
-                }
-                tc_commit(&bars->pv_full);
-                tc_commit(&bars->kv_empty[s]);
-            }
-        }
-    } else {
-        // ===== softmax + epilogue: thread = query row =====
-        FwdTile t;
-        t.s_full = &bars->s_full;
-        t.s_free = &bars->s_free;
-        t.p_full = &bars->p_full;
-        t.pv_full = &bars->pv_full;
-        t.tmem_s = tmem_s;
-        t.tmem_pv = tmem_pv;
-        t.tmem_l = tmem_l;
-        t.sP = sP;
-        fwd_softmax_tile(a, t, threadIdx.x, q0, b, h, kvlen, nblk);
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 256);
-    }
-}
 
 // ---- forward, eight softmax warps per tile --------------------------------------------------
 // 10 warps: softmax warps 0-7 (warp w: TMEM lane quarter w % 4 = query rows, key half w / 4 of
@@ -369,6 +116,8 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint32_t seed_lo = a.seed_lo, seed_hi = a.seed_hi;
+    if (DROP) effective_seed(a.seed_dev, seed_lo, seed_hi);
     unsigned char* sQ = smem;
     unsigned char* sK = sQ + kTileBytes;          // 2 stages
     unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
@@ -569,7 +318,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                     for (int g = 0; g < 2; ++g) {
                         const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
-                                                   a.seed_lo, a.seed_hi);
+                                                   seed_lo, seed_hi);
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
                             float x0, x1, q0, q1;
@@ -623,280 +372,6 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
             float l_run = tmem_ld1(tmem_l + lane_base);
             if (!kUseOnes) l_run += tmem_ld1(tmem_l + lane_base + 1);
-            tc_fence_before();
-            if (qi < a.Lq) {
-                const float inv = 1.0f / l_run;
-                __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + half * 32;
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(r[i + 2 * u]) * inv, __uint_as_float(r[i + 2 * u + 1]) * inv);
-                        w[u] = *reinterpret_cast<const uint32_t*>(&v2);
-                    }
-                    *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-                if (a.lse != nullptr && half == 0)
-                    a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_used * c + log2f(l_run)) * 0.6931471805599453f;
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 256);
-    }
-}
-
-// ---- forward, eight softmax warps per tile, P in tensor memory -----------------------------------
-// Same thread layout as mha_fwd3_kernel, but the probabilities never touch shared memory: each
-// thread writes its packed bf16 P over the S columns it has just read (tcgen05.st) and the
-// P V / P x ones products take their A operand from TMEM.  Per 128-key block that removes the
-// 32 KB P store and two 32 KB P reads from the shared-memory pipe, which was the bound
-// (176 KB per block at 128 B/clk ~ 1400 cycles against ~800 cycles of tensor work).  S and P
-// share columns, so Q K^T of block j+1 runs after P V of block j (tensor-pipe issue order); the
-// second CTA on the SM fills the gap.
-// TMEM: S/P 0-127 (P of keys [64h+32p, +32) packed in columns 64h+32p .. +15) | O 128-191 | L 192-207.
-// 10 warps: softmax warps 0-7 (warp w: TMEM lane quarter w % 4 = query rows, key half w / 4 of
-// every 128-key block), TMA producer (warp 8), MMA issuer (warp 9); two CTAs per SM.
-// A query row is shared by two threads: each takes the maximum over its 64 scores, the two
-// halves meet through shared memory and a 256-thread named barrier, each exponentiates its
-// half and owns 32 of the 64 output columns.  Four softmax warps per SM sub-partition (two
-// CTAs) hide the dependent-instruction latency that one warp per sub-partition leaves exposed.
-// The tensor pipe is fed out of order with respect to the tiles: S of block j+1 is issued as
-// soon as S of block j has been read (before P V of block j), and O is updated with P V of
-// block j-1 while block j is in flight, so neither product is waited for right after its issue.
-constexpr int kFwd4Threads = 320;
-constexpr int kFwd4Smem = 5 * kTileBytes /*Q + K,V x2*/ + 128 /*barriers*/ + 128 /*ones*/ + 2 * 128 * 2 /*row maxima*/;
-
-template <bool DROP>
-__global__ void __launch_bounds__(kFwd4Threads, 2)
-mha_fwd4_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    unsigned char* sQ = smem;
-    unsigned char* sK = sQ + kTileBytes;          // 2 stages
-    unsigned char* sV = sK + 2 * kTileBytes;      // 2 stages
-    MhaBarriers* bars = reinterpret_cast<MhaBarriers*>(sV + 2 * kTileBytes);
-    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sV + 2 * kTileBytes + 128);   // 128 bytes of bf16 1.0
-    __nv_bfloat16* sMax = reinterpret_cast<__nv_bfloat16*>(sV + 2 * kTileBytes + 256);   // [2 halves][128 rows]
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
-    fence_proxy_async();
-    const int q0 = blockIdx.x * kBM;
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
-    int k_end = a.causal ? min(kvlen, q0 + kBM) : kvlen;
-    if (a.dense_mask) k_end = a.Lk;
-    const int nblk = max(1, (k_end + kBN - 1) / kBN);
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bars->q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->kv_full[s], 1);
-            mbar_init(&bars->kv_empty[s], 1);
-        }
-        mbar_init(&bars->s_full, 1);
-        mbar_init(&bars->p_full, 8);      // one arrival per softmax warp
-        mbar_init(&bars->pv_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 9) {
-        tmem_alloc(&bars->tmem_base, 256);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    const uint32_t tmem_s = tmem;          // 128 columns: S
-    const uint32_t tmem_pv = tmem + 128;   // 64 columns: P V
-    const uint32_t tmem_l = tmem + 192;    // 16 columns: P x ones (row sums)
-
-    if (warp == 8) {
-        // ===== TMA producer =====
-        if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_q);
-            tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_v);
-            mbar_arrive_expect_tx(&bars->q_full, kTileBytes);
-            tma_load_4d(sQ, &tm_q, 0, h, q0, b, &bars->q_full);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
-                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
-                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
-                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
-            }
-        }
-    } else if (warp == 9) {
-        // ===== MMA issuer (one thread) =====
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
-            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);     // row sums = P x ones
-            const uint32_t q_addr = smem_u32(sQ);
-            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
-            fence_proxy_async();
-            mbar_wait(&bars->q_full, 0);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                mbar_wait(&bars->kv_full[s], (j >> 1) & 1);
-                tc_fence_after();
-                const uint32_t k_addr = smem_u32(sK + s * kTileBytes);
-                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
-                // S overwrites the P of the previous block: ordered behind its P V by the pipe's issue order
-#pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_bf16(tmem_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
-                              idesc_s, kk > 0 ? 1u : 0u);
-                tc_commit(&bars->s_full);             // also: every earlier product (P V of block j-1) is complete
-                mbar_wait(&bars->p_full, j & 1);      // P of block j is in TMEM
-                tc_fence_after();
-#pragma unroll
-                for (int kk = 0; kk < kBN / 16; ++kk) {
-                    // keys [16 kk, 16 kk + 16): half kk >> 2, 32-key part (kk >> 1) & 1, 8 packed columns
-                    const uint32_t a_tmem = tmem_s + 64 * (kk >> 2) + 32 * ((kk >> 1) & 1) + 8 * (kk & 1);
-                    const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
-                    umma_bf16_ts(tmem_pv, a_tmem, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
-                    if (!DROP) umma_bf16_ts(tmem_l, a_tmem, ones_desc, idesc_l, (j > 0 || kk > 0) ? 1u : 0u);
-                }
-                tc_commit(&bars->pv_full);
-                tc_commit(&bars->kv_empty[s]);
-            }
-        }
-    } else {
-        // ===== softmax + epilogue: thread = (query row, key half) =====
-        // O and the row sums accumulate in TMEM across the key blocks (P V and P x ones issued with
-        // accumulate).  They are scaled with m_used, the row maximum at the last rescale; a new
-        // maximum only forces a rescale (TMEM load, multiply, TMEM store) when it exceeds m_used by
-        // more than 8 in the exponent - otherwise the probabilities simply run up to 2^8, which
-        // bf16 P and the fp32 accumulators hold without loss.
-        const int row = (warp & 3) * 32 + lane;
-        const int half = warp >> 2;
-        const int qi = q0 + row;
-        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-        float m_used = -INFINITY;
-        float l_part = 0.0f;         // DROP: sum of this thread's (undropped) probabilities, scaled like O
-        const float c = a.scale_log2;
-        const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
-        for (int j = 0; j < nblk; ++j) {
-            const int key0 = j * kBN + half * 64;
-            int lim = kvlen;
-            if (a.causal) lim = min(lim, qi + 1);
-            const bool need_mask = (j * kBN + kBN > lim) || (mrow != nullptr);
-            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + cc + i;
-                    bool dead = key >= lim;
-                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                    if (dead) r[i] = 0xff800000u;   // -inf
-                }
-            };
-            mbar_wait(&bars->s_full, j & 1);
-            tc_fence_after();
-            // pass 1: maximum over this thread's 64 scores, then over both halves of the row
-            float m_half = -INFINITY;
-            {
-                uint32_t ra[32], rb[32];
-                tmem_ld32_issue(tmem_s + lane_base + half * 64, ra);
-                tmem_ld32_issue(tmem_s + lane_base + half * 64 + 32, rb);
-                tmem_ld_wait();
-                if (need_mask) {
-                    apply_mask(ra, 0);
-                    apply_mask(rb, 32);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) m_half = fmaxf(m_half, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
-            }
-            // (any common reference works for the exponent, so the halves trade bf16-rounded maxima:
-            // 512 bytes instead of 1 KB keeps two CTAs on one SM; the next write is ordered behind
-            // this read by the s_free -> s_full chain)
-            const __nv_bfloat16 m_half_r = __float2bfloat16_rn(m_half);
-            sMax[half * 128 + row] = m_half_r;
-            bar_sync_named(1, 256);
-            const float m_new = fmaxf(m_used, fmaxf(__bfloat162float(m_half_r), __bfloat162float(sMax[(half ^ 1) * 128 + row])));
-            // (s_full of this block was committed after P V of the previous one: O is stable here)
-            const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);   // same answer in both threads of the row
-            if (j == 0) {
-                m_used = m_new;
-            } else if (__any_sync(0xffffffffu, grow)) {          // TMEM accesses are warp-collective: all lanes go
-                const float f = grow ? ex2_approx((m_used - m_new) * c) : 1.0f;   // m_used = -inf -> 0
-                uint32_t r[32];
-                tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * f);
-                tmem_st32(tmem_pv + lane_base + half * 32, r);
-                if (DROP) {
-                    l_part *= f;
-                } else if (half == 0) {
-                    tmem_st1(tmem_l + lane_base, tmem_ld1(tmem_l + lane_base) * f);
-                }
-                tmem_st_wait();
-                if (grow) m_used = m_new;
-            }
-            const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
-            // pass 2: probabilities -> packed bf16 -> over the S columns just read (A operand of P V)
-#pragma unroll
-            for (int part = 0; part < 2; ++part) {
-                uint32_t r[32];
-                tmem_ld32_issue(tmem_s + lane_base + half * 64 + part * 32, r);
-                tmem_ld_wait();
-                if (need_mask) apply_mask(r, part * 32);
-                uint32_t pk[16];
-                if (DROP) {
-                    // fp32 exponentials: their sum is the softmax normaliser, the dropped and rescaled copy goes to the P tile
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
-                                                   a.seed_lo, a.seed_hi);
-#pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            float p0 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i]), c, -mc));
-                            float p1 = ex2_approx(fmaf(__uint_as_float(r[g * 16 + i + 1]), c, -mc));
-                            l_part += p0 + p1;
-                            p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
-                            p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
-                            const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                            pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2)
-                        pk[i >> 1] = ex2_bf16x2(fmaf(__uint_as_float(r[i]), c, -mc), fmaf(__uint_as_float(r[i + 1]), c, -mc));
-                }
-                tmem_st16(tmem_s + lane_base + half * 64 + part * 32, pk);
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive_warp(&bars->p_full);
-        }
-        mbar_wait(&bars->pv_full, (nblk - 1) & 1);
-        tc_fence_after();
-        // epilogue: O / l -> bf16 -> out[b, qi, h, half*32 ..]; a fully masked row is 0/0 = NaN like the reference
-        if (DROP) {
-            // the two halves of a row add their normaliser parts through two spare accumulator columns
-            tmem_st1(tmem_l + lane_base + half, l_part);
-            tmem_st_wait();
-            tc_fence_before();
-            bar_sync_named(1, 256);
-            tc_fence_after();
-        }
-        {
-            uint32_t r[32];
-            tmem_ld32_issue(tmem_pv + lane_base + half * 32, r);
-            float l_run = tmem_ld1(tmem_l + lane_base);
-            if (DROP) l_run += tmem_ld1(tmem_l + lane_base + 1);
             tc_fence_before();
             if (qi < a.Lq) {
                 const float inv = 1.0f / l_run;
@@ -991,6 +466,8 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint32_t seed_lo = a.seed_lo, seed_hi = a.seed_hi;
+    if (DROP) effective_seed(a.seed_dev, seed_lo, seed_hi);
     unsigned char* sQ = smem;                              // 2 tiles
     unsigned char* sK = sQ + 2 * kTileBytes;               // kFwd6Stages tiles
     unsigned char* sV = sK + kFwd6Stages * kTileBytes;     // kFwd6Stages tiles
@@ -1351,7 +828,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                             for (int g = 0; g < 2; ++g) {
                                 const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
-                                                           a.seed_lo, a.seed_hi);
+                                                           seed_lo, seed_hi);
 #pragma unroll
                                 for (int i = 0; i < 16; i += 2) {
                                     float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
@@ -1426,158 +903,6 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
 }
 
-// ---- forward, two query tiles per CTA in ping-pong -------------------------------------------
-// 10 warps: softmax warpgroup 0 (warps 0-3, tile 0), softmax warpgroup 1 (warps 4-7, tile 1), TMA
-// producer (warp 8), MMA issuer (warp 9).  Both tiles share the K/V stages; while one warpgroup
-// runs its softmax the tensor core works for the other (S, PV and row-sum MMAs), so the serial
-// MMA -> softmax -> MMA chain of a single tile no longer leaves the tensor pipe idle.
-// TMEM: S0 0-127 | S1 128-255 | PV0 256-319 | PV1 320-383 | L0 384-399 | L1 400-415 (512 allocated).
-struct __align__(8) MhaBarriers2 {
-    uint64_t q_full;
-    uint64_t kv_full[2];
-    uint64_t kv_empty[2];
-    uint64_t s_full[2];
-    uint64_t s_free[2];
-    uint64_t p_full[2];
-    uint64_t pv_full[2];
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-constexpr int kFwd2Threads = 320;
-constexpr int kFwd2Smem = 2 * kTileBytes /*Q x2*/ + 4 * kTileBytes /*K,V x2*/ + 4 * kTileBytes /*P x2*/ + 128 + 128;
-
-__global__ void __launch_bounds__(kFwd2Threads, 1)
-mha_fwd2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    unsigned char* sQ = smem;                       // 2 tiles
-    unsigned char* sK = sQ + 2 * kTileBytes;        // 2 stages
-    unsigned char* sV = sK + 2 * kTileBytes;        // 2 stages
-    unsigned char* sP = sV + 2 * kTileBytes;        // 2 tiles x [2 key halves][128][128B]
-    MhaBarriers2* bars = reinterpret_cast<MhaBarriers2*>(sP + 4 * kTileBytes);
-    uint32_t* sOnes = reinterpret_cast<uint32_t*>(sP + 4 * kTileBytes + 128);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) sOnes[threadIdx.x] = 0x3F803F80u;
-    fence_proxy_async();
-    const int q0 = blockIdx.x * (2 * kBM);
-    const int h = blockIdx.y;
-    const int b = blockIdx.z;
-    const int ntile = (q0 + kBM < a.Lq) ? 2 : 1;
-    const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
-    int k_end = a.causal ? min(kvlen, q0 + kBM * ntile) : kvlen;
-    if (a.dense_mask) k_end = a.Lk;
-    const int nblk = max(1, (k_end + kBN - 1) / kBN);
-
-    if (threadIdx.x == 0) {
-        mbar_init(&bars->q_full, 1);
-        for (int s = 0; s < 2; ++s) {
-            mbar_init(&bars->kv_full[s], 1);
-            mbar_init(&bars->kv_empty[s], 1);
-            mbar_init(&bars->s_full[s], 1);
-            mbar_init(&bars->s_free[s], 4);   // one arrival per softmax warp
-            mbar_init(&bars->p_full[s], 4);
-            mbar_init(&bars->pv_full[s], 1);
-        }
-        fence_mbar_init();
-    }
-    if (warp == 9) {
-        tmem_alloc(&bars->tmem_base, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-
-    if (warp == 8) {
-        // ===== TMA producer =====
-        if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_q);
-            tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_v);
-            mbar_arrive_expect_tx(&bars->q_full, ntile * kTileBytes);
-            for (int t = 0; t < ntile; ++t) tma_load_4d(sQ + t * kTileBytes, &tm_q, 0, h, q0 + t * kBM, b, &bars->q_full);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                if (j >= 2) mbar_wait(&bars->kv_empty[s], ((j >> 1) - 1) & 1);
-                mbar_arrive_expect_tx(&bars->kv_full[s], 2 * kTileBytes);
-                tma_load_4d(sK + s * kTileBytes, &tm_k, 0, h, j * kBN, b, &bars->kv_full[s]);
-                tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->kv_full[s]);
-            }
-        }
-    } else if (warp == 9) {
-        // ===== MMA issuer (one thread) =====
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);
-            constexpr uint32_t idesc_l = make_idesc(kBM, 16, 0, 0);
-            const uint64_t ones_desc = smem_desc_ones(smem_u32(sOnes));
-            auto issue_s = [&](int t, int stage) {
-                const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
-                const uint32_t k_addr = smem_u32(sK + stage * kTileBytes);
-#pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_bf16(tmem + t * 128, smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                              smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_s, kk > 0 ? 1u : 0u);
-                tc_commit(&bars->s_full[t]);
-            };
-            mbar_wait(&bars->q_full, 0);
-            mbar_wait(&bars->kv_full[0], 0);
-            tc_fence_after();
-            for (int t = 0; t < ntile; ++t) issue_s(t, 0);
-            for (int j = 0; j < nblk; ++j) {
-                const int s = j & 1;
-                const uint32_t v_addr = smem_u32(sV + s * kTileBytes);
-                for (int t = 0; t < ntile; ++t) {
-                    const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
-                    mbar_wait(&bars->p_full[t], j & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int kk = 0; kk < kBN / 16; ++kk) {
-                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-                        umma_bf16(tmem + 256 + t * 64, ad, smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024), idesc_pv,
-                                  kk > 0 ? 1u : 0u);
-                        umma_bf16(tmem + 384 + t * 16, ad, ones_desc, idesc_l, kk > 0 ? 1u : 0u);
-                    }
-                    tc_commit(&bars->pv_full[t]);
-                    if (t == ntile - 1) tc_commit(&bars->kv_empty[s]);
-                    if (j + 1 < nblk) {
-                        if (t == 0) mbar_wait(&bars->kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                        mbar_wait(&bars->s_free[t], j & 1);   // this tile's S buffer has been consumed
-                        tc_fence_after();
-                        issue_s(t, (j + 1) & 1);
-                    }
-                }
-            }
-        }
-    } else {
-        // ===== softmax warpgroups =====
-        const int t = warp >> 2;
-        if (t < ntile) {
-            FwdTile ft;
-            ft.s_full = &bars->s_full[t];
-            ft.s_free = &bars->s_free[t];
-            ft.p_full = &bars->p_full[t];
-            ft.pv_full = &bars->pv_full[t];
-            ft.tmem_s = tmem + t * 128;
-            ft.tmem_pv = tmem + 256 + t * 64;
-            ft.tmem_l = tmem + 384 + t * 16;
-            ft.sP = sP + t * 2 * kTileBytes;
-            fwd_softmax_tile(a, ft, threadIdx.x & 127, q0 + t * kBM, b, h, kvlen, nblk);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 9) {
-        tc_fence_after();
-        tmem_dealloc(tmem, 512);
-    }
-}
-
 // =====================================================================================
 // Backward.  One CTA per (b, head, 128-key tile j); loop over the 128-query tiles i.
 //   S  = Q_i K_j^T            dP = dO_i V_j^T                (both into TMEM)
@@ -1605,6 +930,7 @@ struct MhaBwdArgs {
     uint32_t drop_thresh; // dropout on the probabilities, same meaning as in MhaFwdArgs
     float inv_keep;
     uint32_t seed_lo, seed_hi;
+    const uint64_t* seed_dev;
 };
 
 struct __align__(8) MhaBwdBarriers {
@@ -1616,7 +942,9 @@ struct __align__(8) MhaBwdBarriers {
     uint64_t dq_full;
     uint32_t tmem_base;
     uint32_t pad;
+    uint32_t seed[2];      // effective dropout seed (kept in shared memory: the 16-warp instance has no register to spare)
 };
+static_assert(sizeof(MhaBwdBarriers) <= 128, "barrier block of the backward kernel");
 
 constexpr int kBwdSmem = 2 * kTileBytes /*K,V*/ + 4 * kTileBytes /*Q,dO x2*/ + 2 * kTileBytes /*P*/ + 2 * kTileBytes /*dS*/ +
                          2 * kTileBytes /*dQ staging: two [128 x 32] fp32 boxes*/ + 128;
@@ -1678,6 +1006,12 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_init(&bars->pds_full, 4 * CG);   // one arrival per softmax warp
         mbar_init(&bars->dq_full, 1);
         fence_mbar_init();
+        if (DROP) {
+            uint32_t lo = a.seed_lo, hi = a.seed_hi;
+            effective_seed(a.seed_dev, lo, hi);
+            bars->seed[0] = lo;
+            bars->seed[1] = hi;
+        }
     }
     constexpr int kTmaWarp = 4 * CG, kMmaWarp = 4 * CG + 1;
     if (warp == kMmaWarp) {
@@ -1832,7 +1166,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tmem_ld16(tm_s + lane_base + cc, sv);
                 tmem_ld16(tm_dp + lane_base + cc, dp);
                 uint4 rnd[1];
-                if (DROP) rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), a.seed_lo, a.seed_hi);
+                if (DROP) rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), bars->seed[0], bars->seed[1]);
                 {
                     // packed f32x2 arithmetic: P = 2^(S c - lse), dS = P (dP' scale - delta scale); with dropout
                     // (mask M, keep probability k) dP' = dP o M / k and the P that dV sees is P o M / k
@@ -2045,7 +1379,7 @@ using namespace asr;
 
 static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
                         int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
-                        float p_drop, uint64_t seed, void* stream) {
+                        float p_drop, uint64_t seed, const uint64_t* seed_dev, void* stream) {
     ASR_REQUIRE(q && k && v && out, "asr_mha_fwd_bf16: null pointer");
     ASR_REQUIRE(D == kD, "asr_mha_fwd_bf16: head dim %d not supported (64 only)", D);
     ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_fwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
@@ -2068,44 +1402,37 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);
     a.seed_lo = (uint32_t)seed;
     a.seed_hi = (uint32_t)(seed >> 32);
-    // "mha_variant": 0 = auto (21), 1 = one tile per CTA with four softmax warps, 2 = two tiles per CTA
-    // in ping-pong, 3 = one tile per CTA with eight softmax warps and O accumulated in TMEM, 4 = 3 with P in
-    // tensor memory, 8 = two tiles per CTA, one thread per row, scores read once, 10 = 8 with packed f32x2
-    // arithmetic, 21 = 10 with the XU token, P in tensor memory and one MMA issuer per tile (measured at
-    // L = 2048: 550 / 550 / 603 / 687 TFLOP/s for 3 / 8 / 10 / 21).  Dropout exists in variants 3 and 21.
+    a.seed_dev = seed_dev;
+    // Two kernels (the four earlier generations are gone, DESIGN.md 4 keeps their numbers):
+    //   mha_fwd8_kernel<DROP, 51>  CTA = two 128-query tiles sharing every K/V tile, one thread per query row, P in
+    //                              tensor memory: the long-sequence kernel (L = 2048: 687 TFLOP/s)
+    //   mha_fwd3_kernel<DROP>      CTA = one 128-query tile, two threads per row, two CTAs per SM: with dropout (the
+    //                              Philox work per element favours two threads per row: 418 vs 312 TFLOP/s) and for short
+    //                              query sequences (Lq <= 128: the second tile of a 256-query CTA would be empty; model
+    //                              shapes are L = 21 .. 167, U <= 15)
+    // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel.
     const int variant = get_opt("mha_variant");
-    if (a.drop_thresh > 0 && variant != 21) {   // with dropout the two-threads-per-row kernel wins (397 vs 312 TFLOP/s: Philox per element)
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
+    const bool drop = a.drop_thresh > 0;
+    const bool one_tile = variant == 3 || (variant != 21 && (drop || Lq <= kBM));
+    static bool attr_done[4] = {false, false, false, false};      // cudaFuncSetAttribute once per kernel, not per call
+    if (one_tile) {
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-        mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
-    } else if (variant == 0 || variant == 8 || variant == 10 || variant == 21) {
-        dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
-#define ASR_LAUNCH_FWD8(DR, MODE)                                                                                             \
-    do {                                                                                                                      \
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<DR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(MODE))); \
-        mha_fwd8_kernel<DR, MODE><<<grid, kFwd8Threads, fwd8_smem(MODE), st>>>(tq, tk, tv, a);                                \
-    } while (0)
-        if (a.drop_thresh > 0) ASR_LAUNCH_FWD8(true, 51);
-        else if (variant == 8) ASR_LAUNCH_FWD8(false, 0);
-        else if (variant == 10) ASR_LAUNCH_FWD8(false, 2);
-        else ASR_LAUNCH_FWD8(false, 51);
-#undef ASR_LAUNCH_FWD8
-    } else if (variant == 4) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd4Smem));
-        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-        mha_fwd4_kernel<false><<<grid, kFwd4Threads, kFwd4Smem, st>>>(tq, tk, tv, a);
-    } else if (variant == 3) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem));
-        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-        mha_fwd3_kernel<false><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
-    } else if (variant == 2) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd2Smem));
-        dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
-        mha_fwd2_kernel<<<grid, kFwd2Threads, kFwd2Smem, st>>>(tq, tk, tv, a);
+        if (drop) {
+            if (!attr_done[0]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem)); attr_done[0] = true; }
+            mha_fwd3_kernel<true><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+        } else {
+            if (!attr_done[1]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd3Smem)); attr_done[1] = true; }
+            mha_fwd3_kernel<false><<<grid, kFwd3Threads, kFwd3Smem, st>>>(tq, tk, tv, a);
+        }
     } else {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
-        dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
-        mha_fwd_kernel<<<grid, kFwdThreads, kFwdSmem, st>>>(tq, tk, tv, a);
+        dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
+        if (drop) {
+            if (!attr_done[2]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<true, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(51))); attr_done[2] = true; }
+            mha_fwd8_kernel<true, 51><<<grid, kFwd8Threads, fwd8_smem(51), st>>>(tq, tk, tv, a);
+        } else {
+            if (!attr_done[3]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(51))); attr_done[3] = true; }
+            mha_fwd8_kernel<false, 51><<<grid, kFwd8Threads, fwd8_smem(51), st>>>(tq, tk, tv, a);
+        }
     }
     ASR_LAUNCH_CHECK();
     return 0;
@@ -2114,13 +1441,21 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
 extern "C" int asr_mha_fwd_bf16(const void* q, const void* k, const void* v, const int* kv_len, const uint8_t* dense_mask,
                                 int causal, int B, int Hh, int Lq, int Lk, int D, float scale, void* out, float* lse,
                                 void* stream) {
-    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, 0.0f, 0, stream);
+    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, 0.0f, 0, nullptr, stream);
 }
 
 extern "C" int asr_mha_fwd_dropout_bf16(const void* q, const void* k, const void* v, const int* kv_len,
                                         const uint8_t* dense_mask, int causal, int B, int Hh, int Lq, int Lk, int D,
                                         float scale, float p_drop, uint64_t seed, void* out, float* lse, void* stream) {
-    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, p_drop, seed, stream);
+    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, p_drop, seed, nullptr, stream);
+}
+
+extern "C" int asr_mha_fwd_dropout_dev_bf16(const void* q, const void* k, const void* v, const int* kv_len,
+                                            const uint8_t* dense_mask, int causal, int B, int Hh, int Lq, int Lk, int D,
+                                            float scale, float p_drop, const uint64_t* seed_dev, uint64_t seed_add, void* out,
+                                            float* lse, void* stream) {
+    ASR_REQUIRE(seed_dev != nullptr, "asr_mha_fwd_dropout_dev_bf16: seed_dev is null");
+    return mha_fwd_impl(q, k, v, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, out, lse, p_drop, seed_add, seed_dev, stream);
 }
 
 #ifdef ASR_MHA_TRACE
@@ -2150,8 +1485,8 @@ extern "C" size_t asr_mha_bwd_workspace_bytes(int B, int Hh, int Lq, int Lk, int
 
 static int mha_bwd_impl(const void* q, const void* k, const void* v, const void* out, const void* g_out,
                         const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
-                        int Lq, int Lk, int D, float scale, float p_drop, uint64_t seed, void* g_q, void* g_k, void* g_v,
-                        void* ws, size_t ws_bytes, void* stream) {
+                        int Lq, int Lk, int D, float scale, float p_drop, uint64_t seed, const uint64_t* seed_dev, void* g_q,
+                        void* g_k, void* g_v, void* ws, size_t ws_bytes, void* stream) {
     ASR_REQUIRE(q && k && v && out && g_out && lse && g_q && g_k && g_v && ws, "asr_mha_bwd_bf16: null pointer");
     ASR_REQUIRE(D == kD, "asr_mha_bwd_bf16: head dim %d not supported (64 only)", D);
     ASR_REQUIRE(B > 0 && Hh > 0 && Lq > 0 && Lk > 0, "asr_mha_bwd_bf16: bad shape B=%d Hh=%d Lq=%d Lk=%d", B, Hh, Lq, Lk);
@@ -2197,12 +1532,17 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
     a.inv_keep = 256.0f / (256.0f - (float)a.drop_thresh);
     a.seed_lo = (uint32_t)seed;
     a.seed_hi = (uint32_t)(seed >> 32);
+    a.seed_dev = seed_dev;
     const bool drop = a.drop_thresh > 0;
     dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
     const int cgo = get_opt("mha_bwd_groups");   // softmax-backward warps = 4 * groups; 0 = default (4)
 #define ASR_LAUNCH_BWD(CGV, DR)                                                                                              \
     do {                                                                                                                   \
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<CGV, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); \
+        static bool attr_done = false;                                                                                     \
+        if (!attr_done) {                                                                                                  \
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<CGV, DR>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); \
+            attr_done = true;                                                                                              \
+        }                                                                                                                  \
         mha_bwd_kernel<CGV, DR><<<grid, 128 * CGV + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);                          \
     } while (0)
     if (cgo == 2) {
@@ -2223,16 +1563,26 @@ extern "C" int asr_mha_bwd_bf16(const void* q, const void* k, const void* v, con
                                 const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B, int Hh,
                                 int Lq, int Lk, int D, float scale, void* g_q, void* g_k, void* g_v, void* ws,
                                 size_t ws_bytes, void* stream) {
-    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, 0.0f, 0, g_q, g_k, g_v,
-                        ws, ws_bytes, stream);
+    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, 0.0f, 0, nullptr, g_q, g_k,
+                        g_v, ws, ws_bytes, stream);
 }
 
 extern "C" int asr_mha_bwd_dropout_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
                                         const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B,
                                         int Hh, int Lq, int Lk, int D, float scale, float p_drop, uint64_t seed, void* g_q,
                                         void* g_k, void* g_v, void* ws, size_t ws_bytes, void* stream) {
-    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, p_drop, seed, g_q, g_k,
-                        g_v, ws, ws_bytes, stream);
+    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, p_drop, seed, nullptr, g_q,
+                        g_k, g_v, ws, ws_bytes, stream);
+}
+
+extern "C" int asr_mha_bwd_dropout_dev_bf16(const void* q, const void* k, const void* v, const void* out, const void* g_out,
+                                            const float* lse, const int* kv_len, const uint8_t* dense_mask, int causal, int B,
+                                            int Hh, int Lq, int Lk, int D, float scale, float p_drop, const uint64_t* seed_dev,
+                                            uint64_t seed_add, void* g_q, void* g_k, void* g_v, void* ws, size_t ws_bytes,
+                                            void* stream) {
+    ASR_REQUIRE(seed_dev != nullptr, "asr_mha_bwd_dropout_dev_bf16: seed_dev is null");
+    return mha_bwd_impl(q, k, v, out, g_out, lse, kv_len, dense_mask, causal, B, Hh, Lq, Lk, D, scale, p_drop, seed_add, seed_dev,
+                        g_q, g_k, g_v, ws, ws_bytes, stream);
 }
 
 extern "C" int asr_mha_probs_f32(const void* q, const void* k, const int* kv_len, const uint8_t* dense_mask, int causal,

@@ -36,7 +36,9 @@ class GradAllReduce:
     are already reduced).  Collectives are issued in a fixed bucket order on every rank.
     """
 
-    def __init__(self, module, bucket_mb=25.0, process_group=None):
+    def __init__(self, module, bucket_mb=25.0, process_group=None, overlap=True):
+        """overlap=False registers no hooks: every bucket is all-reduced from finish().  That is the mode for a backward
+        pass replayed from a CUDA graph (hooks only run while the graph is being captured, not when it is replayed)."""
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -58,7 +60,7 @@ class GradAllReduce:
         self._pending = [0] * len(self.buckets)
         self._handles = []
         self._next = 0             # buckets are all-reduced strictly in index order on every rank
-        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params] if overlap else []
         self.reset()
 
     def _seal(self, plist):

@@ -368,25 +368,81 @@ def ctc_loss(logits, len_logits, targets, blank=None, return_nll=False):
 # ---------------------------------------------------------------------------------
 # Multi-head attention core  (reference: src/transformer/attention.py:74-86)
 # ---------------------------------------------------------------------------------
+class DropoutSeed:
+    """A dropout seed that lives on the device, for training steps captured in a CUDA graph.
+
+    Host-side arguments are frozen when a graph is captured, so a seed drawn on the host would replay the same
+    dropout masks for ever.  With an active DropoutSeed every attention call of the step uses the mask of
+    `*seed_dev + seed_add`: `seed_add` is a per-call constant handed out by `take()` while the step is traced,
+    and `advance()` - a device-side add, captured with the rest of the step - moves `*seed_dev` on for the next replay.
+
+        ds = ops.DropoutSeed(device)
+        with ops.device_dropout_seed(ds):
+            with torch.cuda.graph(g):
+                loss = step(); loss.backward(); ds.advance()
+    """
+    _STRIDE = 0x9E3779B97F4A7C15        # odd: distinct calls never meet for any realistic number of steps
+
+    def __init__(self, device, seed=None):
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.tensor = torch.tensor([seed], dtype=torch.int64, device=device)
+        self.calls = 0
+
+    def take(self):
+        self.calls += 1
+        return self.tensor, (self.calls * self._STRIDE) & 0xFFFFFFFFFFFFFFFF
+
+    def advance(self):
+        self.tensor.add_(1)
+        self.calls = 0
+
+
+_active_seed = None
+
+
+class device_dropout_seed:
+    """Context manager: attention dropout inside draws its seeds from `ds` (see DropoutSeed)."""
+
+    def __init__(self, ds):
+        self.ds = ds
+
+    def __enter__(self):
+        global _active_seed
+        self.prev, _active_seed = _active_seed, self.ds
+        return self.ds
+
+    def __exit__(self, *exc):
+        global _active_seed
+        _active_seed = self.prev
+        return False
+
+
 class _MhaCoreFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, kv_len, dense_mask, causal, scale, p_drop, seed):
+    def forward(ctx, q, k, v, kv_len, dense_mask, causal, scale, p_drop, seed, seed_dev):
         B, Lq, Hh, D = q.shape
         Lk = k.shape[1]
         out = torch.empty((B, Lq, Hh, D), dtype=torch.bfloat16, device=q.device)
         lse = torch.empty((B, Hh, Lq), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            check(_lib.lib().asr_mha_fwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
-                                                      B, Hh, Lq, Lk, D, ctypes.c_float(scale), ctypes.c_float(p_drop),
-                                                      ctypes.c_uint64(seed), ptr(out), ptr(lse), stream_ptr()),
-                  "asr_mha_fwd_dropout_bf16")
-        ctx.save_for_backward(q, k, v, out, lse, kv_len, dense_mask)
+            if seed_dev is None:
+                check(_lib.lib().asr_mha_fwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
+                                                          B, Hh, Lq, Lk, D, ctypes.c_float(scale), ctypes.c_float(p_drop),
+                                                          ctypes.c_uint64(seed), ptr(out), ptr(lse), stream_ptr()),
+                      "asr_mha_fwd_dropout_bf16")
+            else:
+                check(_lib.lib().asr_mha_fwd_dropout_dev_bf16(ptr(q), ptr(k), ptr(v), ptr(kv_len), ptr(dense_mask), int(causal),
+                                                              B, Hh, Lq, Lk, D, ctypes.c_float(scale), ctypes.c_float(p_drop),
+                                                              ptr(seed_dev), ctypes.c_uint64(seed), ptr(out), ptr(lse),
+                                                              stream_ptr()), "asr_mha_fwd_dropout_dev_bf16")
+        ctx.save_for_backward(q, k, v, out, lse, kv_len, dense_mask, seed_dev)
         ctx.meta = (causal, scale, p_drop, seed)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        q, k, v, out, lse, kv_len, dense_mask = ctx.saved_tensors
+        q, k, v, out, lse, kv_len, dense_mask, seed_dev = ctx.saved_tensors
         causal, scale, p_drop, seed = ctx.meta
         B, Lq, Hh, D = q.shape
         Lk = k.shape[1]
@@ -397,12 +453,19 @@ class _MhaCoreFunction(torch.autograd.Function):
         ws_bytes = _lib.lib().asr_mha_bwd_workspace_bytes(B, Hh, Lq, Lk, D)
         ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=q.device)
         with torch.cuda.device(q.device):
-            check(_lib.lib().asr_mha_bwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
-                                                      ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D, ctypes.c_float(scale),
-                                                      ctypes.c_float(p_drop), ctypes.c_uint64(seed),
-                                                      ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws), ws_bytes, stream_ptr()),
-                  "asr_mha_bwd_dropout_bf16")
-        return g_q, g_k, g_v, None, None, None, None, None, None
+            if seed_dev is None:
+                check(_lib.lib().asr_mha_bwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
+                                                          ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D, ctypes.c_float(scale),
+                                                          ctypes.c_float(p_drop), ctypes.c_uint64(seed),
+                                                          ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws), ws_bytes, stream_ptr()),
+                      "asr_mha_bwd_dropout_bf16")
+            else:
+                check(_lib.lib().asr_mha_bwd_dropout_dev_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(g_out), ptr(lse), ptr(kv_len),
+                                                              ptr(dense_mask), int(causal), B, Hh, Lq, Lk, D,
+                                                              ctypes.c_float(scale), ctypes.c_float(p_drop), ptr(seed_dev),
+                                                              ctypes.c_uint64(seed), ptr(g_q), ptr(g_k), ptr(g_v), ptr(ws),
+                                                              ws_bytes, stream_ptr()), "asr_mha_bwd_dropout_dev_bf16")
+        return g_q, g_k, g_v, None, None, None, None, None, None, None
 
 
 def _check_mha_args(what, q, k, v, kv_len, mask):
@@ -438,7 +501,8 @@ def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_
     dense mask [B,Lq,Lk] (True / non-zero = masked), combined with OR.
     dropout_p > 0 applies the reference's dropout to the probabilities (attention.py:83) inside
     the kernel; `seed` (default: drawn from torch's CPU generator, so torch.manual_seed makes it
-    reproducible) selects the mask, which backward regenerates."""
+    reproducible; inside `device_dropout_seed(...)`: read from the device, see DropoutSeed) selects the
+    mask, which backward regenerates."""
     _require_cuda("q", q)
     if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
         raise ValueError("mha_core: q, k, v must be [B, L, heads, 64]")
@@ -448,10 +512,14 @@ def mha_core(q, k, v, kv_len=None, mask=None, causal=False, scale=None, dropout_
         scale = 1.0 / (q.shape[-1] ** 0.5)
     qb, kb, vb = (t.to(torch.bfloat16).contiguous() for t in (q, k, v))
     kv_len, mask = _check_mha_args("mha_core", q, k, v, kv_len, mask)
+    seed_dev = None
     if dropout_p > 0.0 and seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        if _active_seed is not None:
+            seed_dev, seed = _active_seed.take()
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
     return _MhaCoreFunction.apply(qb, kb, vb, kv_len, mask, bool(causal), float(scale), float(dropout_p),
-                                  int(seed or 0))
+                                  int(seed or 0), seed_dev)
 
 
 def mha_dropout_keep(B, Hh, Lq, Lk, dropout_p, seed, device="cuda"):

@@ -46,6 +46,12 @@ class CIF_Model(nn.Module):
         # math, different fp32 summation order than torch's Linear/sum, so a weight that lands within
         # one ulp of the threshold may fire a frame earlier or later than in the reference.
         self.fused_alpha = fused_alpha
+        # True: no host synchronisation inside forward, so a whole training step can be captured in a CUDA graph:
+        # the noise of :47 is drawn by the device generator (the reference draws it on the host and copies it), the
+        # fired tensor is sized L = targets.size(1) instead of reading max_b round(sum alphas) back (equal whenever
+        # one utterance of the batch has no padding - alphas are scaled to sum to #labels +- 0.5), and the
+        # more-fires-than-rows check (which the reference dies on, :100) is skipped.
+        self.static_shapes = False
         self.decoder = decoder
         self.spec_aug_cfg = spec_aug_cfg
         self.ctc_fc = Linear(encoder.d_output, decoder.d_output, bias=False)
@@ -69,7 +75,8 @@ class CIF_Model(nn.Module):
 
         # quantity (before scaling) and target-length scaling, reference :43-48
         num = (targets > 0).float().sum(-1)
-        noise = torch.rand(targets.size(0)).to(num.device)
+        static = getattr(self, "static_shapes", False)
+        noise = torch.rand(targets.size(0), device=num.device) if static else torch.rand(targets.size(0)).to(num.device)
         num_noise = num + noise - 0.5
         if getattr(self, "fused_alpha", False) and hasattr(self.assigner, "forward_scaled"):
             alpha, _num = self.assigner.forward_scaled(encoder_outputs, len_sequence, num_noise)
@@ -78,7 +85,11 @@ class CIF_Model(nn.Module):
             _num = alpha.sum(-1)
             alpha = alpha * (num_noise / _num)[:, None]
 
-        fired = self.cif(encoder_outputs, alpha, threshold=threshold)
+        if static:
+            fired = _cif_op(encoder_outputs.float(), alpha.float(), threshold, L=targets.size(1),
+                            check_overflow=False).to(encoder_outputs.dtype)
+        else:
+            fired = self.cif(encoder_outputs, alpha, threshold=threshold)
 
         logits = self.decoder(fired, targets)
 

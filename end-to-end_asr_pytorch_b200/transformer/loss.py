@@ -22,7 +22,9 @@ def cal_ce_loss(logits, targets, smoothing=0.0):
         true_dist.scatter_(1, flat_targets.long().unsqueeze(1), 1.0 - smoothing)
         keep = flat_targets.ne(0)
         per_token = -(true_dist * log_prb).sum(dim=1)
-        return per_token.masked_select(keep).sum() / keep.long().sum()
+        # the reference's masked_select(keep).sum() without its dynamic-size result (a host sync): same addends, zeros
+        # in place of the dropped ones
+        return (per_token * keep.to(per_token.dtype)).sum() / keep.long().sum()
     return F.cross_entropy(flat_logits, flat_targets, ignore_index=0, reduction='mean')
 
 

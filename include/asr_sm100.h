@@ -327,6 +327,22 @@ int asr_mha_bwd_dropout_bf16(const void* q, const void* k, const void* v, const 
                              float p_drop, uint64_t seed,
                              void* g_q, void* g_k, void* g_v,
                              void* ws, size_t ws_bytes, void* stream);
+/* The same pair with the seed read ON THE DEVICE: the mask is that of seed = *seed_dev + seed_add.  For training
+ * steps captured in a CUDA graph: the host-side arguments are frozen at capture time, so every attention call of the
+ * step gets its own constant `seed_add` and the step bumps the one device word `*seed_dev` (a captured device-side
+ * add) to draw fresh masks on every replay.  Forward and backward of one call must use the same pair. */
+int asr_mha_fwd_dropout_dev_bf16(const void* q, const void* k, const void* v,
+                                 const int* kv_len, const uint8_t* dense_mask, int causal,
+                                 int B, int Hh, int Lq, int Lk, int D, float scale,
+                                 float p_drop, const uint64_t* seed_dev, uint64_t seed_add,
+                                 void* out, float* lse, void* stream);
+int asr_mha_bwd_dropout_dev_bf16(const void* q, const void* k, const void* v, const void* out,
+                                 const void* g_out, const float* lse,
+                                 const int* kv_len, const uint8_t* dense_mask, int causal,
+                                 int B, int Hh, int Lq, int Lk, int D, float scale,
+                                 float p_drop, const uint64_t* seed_dev, uint64_t seed_add,
+                                 void* g_q, void* g_k, void* g_v,
+                                 void* ws, size_t ws_bytes, void* stream);
 float asr_mha_dropout_keep_prob(float p_drop);
 int asr_mha_dropout_keep_u8(int B, int Hh, int Lq, int Lk, float p_drop, uint64_t seed,
                             uint8_t* keep, void* stream);

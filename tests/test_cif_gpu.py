@@ -177,3 +177,31 @@ def test_alpha_sum_and_quantity_term():
     ref = to_np(alphas).astype(np.float64).sum(-1)
     np.testing.assert_allclose(to_np(aux["alpha_sum"]), ref, rtol=1e-5)
     np.testing.assert_allclose(to_np(aux["qua_term"]), (ref - to_np(num)) ** 2, rtol=1e-4, atol=1e-6)
+
+
+def test_per_call_kernel_hint_matches_the_option_and_is_bit_identical():
+    """asr_cif_fwd_hint_f32: the kernel choice as a per-call argument (bench.py queues the warp-specialised kernel between
+    the CTC phases) instead of the process-wide option table; every choice produces the same bits."""
+    lib = pkg("_lib")
+    L_ = lib.lib()
+    hidden, alphas = make_cif_inputs(6, 300, 256, 20, seed=11)
+    B, T, H = hidden.shape
+    Lout = 22
+    ref = None
+    for hint in (0, 1, 2, 3, 4):
+        out = torch.empty(B, Lout, H, device="cuda")
+        fire_t = torch.empty(B, Lout, dtype=torch.int32, device="cuda")
+        n_fired = torch.empty(B, dtype=torch.int32, device="cuda")
+        cur, rem = torch.empty(B, T, device="cuda"), torch.empty(B, T, device="cuda")
+        sched = torch.empty(B, T, dtype=torch.int32, device="cuda")
+        asum = torch.empty(B, device="cuda")
+        lib.check(L_.asr_cif_fwd_hint_f32(lib.ptr(hidden), lib.ptr(alphas), 0.95, B, T, H, Lout, lib.ptr(out), lib.ptr(fire_t),
+                                          lib.ptr(n_fired), lib.ptr(cur), lib.ptr(rem), lib.ptr(sched), lib.ptr(asum), None, None,
+                                          hint, lib.stream_ptr()), "asr_cif_fwd_hint_f32")
+        got = (out, fire_t, n_fired, cur, rem, sched)
+        if ref is None:
+            ref = got
+        else:
+            for a, b in zip(ref, got):
+                assert torch.equal(a, b), hint
+    assert lib.get_option("cif_fwd_variant") == 0            # the hint did not touch the process-wide option

@@ -298,3 +298,59 @@ def test_extreme_shapes_vs_torch_on_device(B, T, V, S):
         assert ge_ours <= max(1e-5, 3 * ge_ref), (ge_ours, ge_ref)
     for b in range(B):
         assert not to_np(grad)[b, int(in_len[b]):].any()
+
+
+def test_bad_labels_give_nan_not_a_silently_wrong_gradient():
+    """A label equal to the blank or outside [0, V) has no lattice state of its own (its gradient entry would collide
+    with the blank's): the utterance reports NaN loss and NaN gradient rows, the other utterances are untouched."""
+    ops = pkg("ops")
+    B, T, V, S = 4, 40, 50, 6
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=17, full_len=True)
+    good = logits.clone().requires_grad_(True)
+    loss_g, nll_g = ops.ctc_loss(good, in_len, targets, return_nll=True)
+    loss_g.backward()
+    for bad_value in (V - 1, V + 3):
+        t2 = targets.clone()
+        t2[1, 2] = bad_value
+        x = logits.clone().requires_grad_(True)
+        loss, nll = ops.ctc_loss(x, in_len, t2, return_nll=True)
+        loss.backward()
+        assert torch.isnan(nll[1]) and torch.isnan(loss)
+        assert torch.isnan(x.grad[1, : int(in_len[1])]).all()
+        keep = [0, 2, 3]
+        assert torch.equal(nll[keep], nll_g[keep]) and torch.equal(x.grad[keep], good.grad[keep])
+
+
+def test_ticket_ring_fails_loudly():
+    """At most 4 begins may be open per device: the 5th returns an error instead of aliasing an open ticket's events, and
+    finish on a ticket that is not open is refused."""
+    import ctypes
+    lib = pkg("_lib")
+    L = lib.lib()
+    B, T, V, S = 3, 20, 30, 4
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=18)
+    tgt_len = targets.ne(0).sum(1).to(torch.int32)
+    nll, g = torch.empty(B, device="cuda"), torch.empty_like(logits)
+    wsb = L.asr_ctc_workspace_bytes(B, T, V, S)
+    wss = [torch.empty(wsb // 4 + 1, device="cuda") for _ in range(5)]
+    args = lambda ws: (lib.ptr(logits), lib.ptr(targets), lib.ptr(in_len), lib.ptr(tgt_len), B, T, V, S, V - 1, lib.ptr(nll),  # noqa: E731
+                       lib.ptr(g), lib.ptr(ws), wsb, lib.stream_ptr())
+    tickets = []
+    try:
+        for i in range(4):
+            tk = ctypes.c_int(-1)
+            assert L.asr_ctc_begin_f32(*args(wss[i]), ctypes.byref(tk)) == 0
+            tickets.append(tk.value)
+        assert sorted(tickets) == [0, 1, 2, 3]
+        tk = ctypes.c_int(-1)
+        assert L.asr_ctc_begin_f32(*args(wss[4]), ctypes.byref(tk)) != 0
+        assert "between begin and finish" in lib.last_error()
+    finally:
+        for i, t in enumerate(tickets):
+            assert L.asr_ctc_finish_f32(*args(wss[i]), t) == 0
+    assert L.asr_ctc_finish_f32(*args(wss[0]), tickets[0]) != 0 and "not open" in lib.last_error()
+    torch.cuda.synchronize()
+    tk = ctypes.c_int(-1)                        # and the ring is usable again
+    assert L.asr_ctc_begin_f32(*args(wss[0]), ctypes.byref(tk)) == 0
+    assert L.asr_ctc_finish_f32(*args(wss[0]), tk.value) == 0
+    torch.cuda.synchronize()
