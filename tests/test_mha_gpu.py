@@ -49,7 +49,7 @@ def _rand_qkv(B, Lq, Lk, H, seed, std=1.0):
     return q, k, v
 
 
-def _close(a, b, tol=2e-2):
+def _close(a, b, tol=2e-2, elementwise=True):
     """bf16 bar of north_star: rtol 2e-2.  Two readings, both asserted: the worst element against the output scale, and
     every element against its own magnitude with an absolute floor of one bf16 ulp of the scale (elements that cancel to
     ~0 cannot be held to a relative bound)."""
@@ -57,7 +57,8 @@ def _close(a, b, tol=2e-2):
     scale = b.abs().max().item() + 1e-6
     err = (a - b).abs()
     assert err.max().item() <= tol * scale, (err.max().item(), scale)
-    assert (err <= tol * b.abs() + 2.0 ** -7 * scale).all(), ((err - tol * b.abs()).max().item(), scale)
+    if elementwise:
+        assert (err <= tol * b.abs() + 2.0 ** -7 * scale).all(), ((err - tol * b.abs()).max().item(), scale)
 
 
 @pytest.mark.parametrize("B,Lq,Lk,H", [(2, 128, 128, 2), (1, 21, 21, 8), (3, 167, 167, 8), (2, 16, 300, 4),
@@ -277,7 +278,7 @@ def test_dropout_zero_is_the_plain_kernel_and_expectation_is_unbiased():
     for s in range(n):
         acc += ops.mha_core(q, k, v, dropout_p=0.25, seed=1000 + s).float()
     # mean over 64 masks approaches the undropped output: error ~ sqrt(p/(1-p)/n) of a row's spread
-    _close(acc / n, plain, 0.25)
+    _close(acc / n, plain, 0.25, elementwise=False)      # a statistical bound on a mean over random masks
 
 
 def test_module_applies_attention_dropout_only_in_training():
