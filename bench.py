@@ -374,12 +374,19 @@ def self_check(hp):
 class E2EPipe:
     """Public-API step with host inputs.  Every step's inputs come from pinned host memory: the copies of step k+1 run on a
     copy stream while step k computes (two device buffer sets), the way a training input pipeline prefetches; the losses are
-    read back (device -> host, synchronising) every step."""
-    KEYS = ("logits", "hidden", "alphas", "targets", "in_len", "noise")
+    read back (device -> host, synchronising) every step.
+    fused=True (default): the step starts where the reference's does, from the encoder outputs [B,T,H] - the vocabulary
+    projection `ctc_fc` (cif_model.py:38; its weight is a resident parameter) runs fused with the CTC loss
+    (ops.ctc_fc_loss), so the [B,T,V] logits never cross PCIe (0.84 GB per step instead of 7.8 GB) and the
+    step also produces d loss / d ctc_fc.weight.  fused=False: round 1's leg, the logits themselves come from the host."""
 
-    def __init__(self, w, inp, g_out):
+    def __init__(self, w, inp, g_out, fused=True):
         self.ops = pkg("ops")
-        self.w, self.g_out = w, g_out
+        self.w, self.g_out, self.fused = w, g_out, fused
+        self.KEYS = ("hidden", "alphas", "targets", "in_len", "noise") + (() if fused else ("logits",))
+        if fused:
+            g = torch.Generator(device=inp["hidden"].device).manual_seed(77)
+            self.weight = (torch.randn(w["V"], w["H"], device=inp["hidden"].device, generator=g) * w["H"] ** -0.5).requires_grad_(True)
         self.host = {k: inp[k].cpu().pin_memory() for k in self.KEYS}
         self.bufs = [{k: torch.empty_like(inp[k]) for k in self.KEYS} for _ in range(2)]
         self.h2d_bytes = sum(v.numel() * v.element_size() for v in self.host.values())
@@ -407,21 +414,27 @@ class E2EPipe:
         self.prefetch(slot ^ 1)                                   # next step's inputs, under this step's kernels
         torch.cuda.current_stream().wait_event(self.ready[slot])
         buf = self.bufs[slot]
-        logits = buf["logits"].requires_grad_(True)
-        hidden = buf["hidden"].requires_grad_(True)
-        alphas_raw = buf["alphas"].requires_grad_(True)
+        grads = ("hidden", "alphas") + (() if self.fused else ("logits",))
+        for k in grads:
+            buf[k].requires_grad_(True)
+        hidden, alphas_raw = buf["hidden"], buf["alphas"]
         _num, num, alphas = scale_alphas(alphas_raw, buf["targets"], buf["noise"])
         fired = self.ops.cif(hidden, alphas, 0.95)
         qua = torch.pow(_num - num, 2).mean()
-        ctc = self.ops.ctc_loss(logits, buf["in_len"], buf["targets"])
+        if self.fused:
+            ctc = self.ops.ctc_fc_loss(hidden, self.weight, buf["in_len"], buf["targets"])
+        else:
+            ctc = self.ops.ctc_loss(buf["logits"], buf["in_len"], buf["targets"])
         total = ctc + 0.001 * qua + (fired * self.g_out[:, :fired.size(1)]).sum()
         total.backward()
         losses = torch.stack([ctc.detach(), qua.detach()])
         self.free[slot].record()
         losses = losses.cpu()                                     # D2H, synchronises
-        for k in ("logits", "hidden", "alphas"):
+        for k in grads:
             buf[k].grad = None
             buf[k].requires_grad_(False)
+        if self.fused:
+            self.weight.grad = None
         self.k += 1
         return losses
 
@@ -462,6 +475,42 @@ def assigner_microbench(w, inp, device, iters=5):
                              ("cif_alpha_bwd", bwd, 4 * valid * D + 4 * B * T * D + 16 * B * T)):
         ms = cuda_time(fn, iters)
         res[name] = {"ms": ms, "algorithmic_bytes": nbytes, "GBps": nbytes / (ms * 1e-3) / 1e9}
+    return res
+
+
+def ctc_fc_microbench(w, inp, device, peaks, iters=3):
+    """the vocabulary projection fused with the CTC loss on the bench batch - encoder outputs [B,T,H] ->
+    loss, d hidden, d weight, the logits never leaving the call - and its three fp32 tensor-core GEMMs on their own."""
+    ops = pkg("ops")
+    B, T, V, H = w["B"], w["T"], w["V"], w["H"]
+    g = torch.Generator(device=device).manual_seed(78)
+    weight = (torch.randn(V, H, device=device, generator=g) * H ** -0.5).requires_grad_(True)
+    hidden = inp["hidden"].detach().clone().requires_grad_(True)
+
+    def whole():
+        loss = ops.ctc_fc_loss(hidden, weight, inp["in_len"], inp["targets"])
+        loss.backward()
+        hidden.grad = weight.grad = None
+    ms = cuda_time(whole, iters, warm=1)
+    M = B * T
+    flop = 2.0 * M * V * H
+    res = {"ctc_fc_loss": {"ms": ms, "utts_per_s": B / ms * 1e3, "TFLOPs": 3 * flop / ms / 1e9,
+                           "note": "whole call: projection GEMM + CTC (in place on the padded logits) + d hidden and d weight GEMMs; "
+                                   "fp32 in / out, three TF32 products per K step"}}
+    h2 = hidden.detach().reshape(M, H)
+    buf = torch.empty(M, (V + 3) // 4 * 4, device=device)
+    wd = weight.detach()
+    for name, fn in (("gemm_f32_fwd (h W^T)", lambda: ops.gemm_f32(h2, wd, out=buf, split_k=False)),
+                     ("gemm_f32_dx (g W, W MN-major)", lambda: ops.gemm_f32(buf[:, :V], wd, b_mn_major=True, split_k=False)),
+                     ("gemm_f32_dw (g^T h, both MN-major, split-K)", lambda: ops.gemm_f32(buf[:, :V], h2, a_mn_major=True, b_mn_major=True))):
+        t = cuda_time(fn, iters, warm=1)
+        res[name] = {"ms": t, "TFLOPs": flop / t / 1e9}
+    del buf
+    # torch's own path for the same three products (cuBLAS SIMT sgemm in fp32)
+    lg = torch.empty(M, V, device=device)
+    t = cuda_time(lambda: torch.mm(h2, wd.t(), out=lg), 2, warm=1)
+    res["torch_fp32_fwd (cuBLAS)"] = {"ms": t, "TFLOPs": flop / t / 1e9}
+    del lg
     return res
 
 
@@ -964,9 +1013,25 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": world * w["B"] * Ke / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": pipe.h2d_bytes,
                "d2h_bytes_per_step": int(losses.numel() * losses.element_size()), "steps": Ke,
-               "api": "ops.cif + ops.ctc_loss + autograd.backward; pinned-host inputs copied every step on a copy stream "
-                      "(step k+1's copies run under step k's kernels), losses read back every step"}
+               "api": "ops.cif + ops.ctc_fc_loss (ctc_fc projection fused with the CTC loss: the step starts from the encoder "
+                      "outputs, like the reference's) + autograd.backward; pinned-host inputs copied every step on a copy "
+                      "stream (step k+1's copies run under step k's kernels), losses read back every step",
+               "last_losses": [float(x) for x in losses]}
         del pipe
+        # round 1's leg for comparison: the [B,T,V] logits themselves shipped from the host every step (PCIe-bound)
+        if rank == 0 and not args.no_extras:
+            pipe = E2EPipe(w, inp, hp.g_out, fused=False)
+            pipe.start()
+            pipe.step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                pipe.step()
+            torch.cuda.synchronize()
+            e2e["logits_from_host"] = {"value": w["B"] * 3 / (time.perf_counter() - t0), "unit": UNIT,
+                                       "h2d_bytes_per_step": pipe.h2d_bytes, "n_gpus": 1,
+                                       "note": "rank 0 only: ops.ctc_loss on logits copied from the host (round-1 leg)"}
+            del pipe
 
     # ---- roofline of the dominant kernel, rank 0 --------------------------------------
     peaks, peak_src = load_peaks()
@@ -989,6 +1054,10 @@ def main():
             kernels.append({"kernel": n, "bound": "hbm", "ms": asg[n]["ms"], "algorithmic_bytes": asg[n]["algorithmic_bytes"],
                             "GBps": asg[n]["GBps"], "frac_of_hbm_peak": asg[n]["GBps"] / peaks["hbm_gbs"],
                             "in_timed_step": False, "note": "SURVEY 8(f2): assigner tail + alpha scaling, next-row kernel"})
+        fc = ctc_fc_microbench(w, inp, device, peaks)
+        for n, v in fc.items():
+            kernels.append(dict(kernel=n, bound="tensor (tf32 x3, shared-memory bandwidth)", in_timed_step=False,
+                                shape="M=%d (B x T) K=%d N=%d f32" % (w["B"] * w["T"], w["H"], w["V"]), **v))
     traffic = load_traffic()
     dom = kernels[0]
     live_gbps = bm["ctc_rows"] / (rows_live_ms * 1e-3) / 1e9

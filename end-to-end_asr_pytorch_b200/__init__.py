@@ -18,6 +18,6 @@ Python identifier; import it with importlib.import_module(
 repository root.
 """
 from . import _lib  # noqa: F401
-from .ops import cif, cif_label_len, ctc_loss  # noqa: F401
+from .ops import cif, cif_label_len, ctc_loss, ctc_fc_loss  # noqa: F401
 
-__all__ = ["cif", "cif_label_len", "ctc_loss"]
+__all__ = ["cif", "cif_label_len", "ctc_loss", "ctc_fc_loss"]

@@ -41,7 +41,14 @@ SIGNATURES = {
     "asr_linear_act_bf16": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_linear_residual_layernorm_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_float, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_linear_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "asr_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
+    "asr_gemm_f32": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
+                              _vp, _c_size_t, _vp]),
+    "asr_gemm_bf16": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int,
+                               _c_int, _vp, _c_size_t, _vp]),
     "asr_ctc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),
+    "asr_ctc_fwd_bwd_ld_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int, _c_int,
+                                        _vp, _vp, _vp, _c_size_t, _vp]),
     "asr_ctc_fwd_bwd_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,
                                      _vp, _vp, _vp, _c_size_t, _vp]),
     "asr_ctc_begin_f32": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _c_int,

@@ -48,6 +48,7 @@ struct CtcArgs {
     const int* in_len;
     const int* tgt_len;
     int B, T, V, S, blank, SP;
+    int ld;       // row stride of logits / g in floats (>= V)
     int Bn;       // batch size the mean loss is normalised by (>= B when this launch covers a slice of the batch)
     float* nll;
     float* g;     // may be null
@@ -95,8 +96,8 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
     const int t = (int)(row - (long long)b * a.T);
     const int Tb = min(max(__ldg(a.in_len + b), 0), a.T);
     const int V = a.V;
-    const float* x = a.logits + (size_t)row * V;
-    float* g = GRAD ? a.g + (size_t)row * V : nullptr;
+    const float* x = a.logits + (size_t)row * a.ld;
+    float* g = GRAD ? a.g + (size_t)row * a.ld : nullptr;
 
     // 16-byte alignment peel (rows are only 4-byte aligned when V is odd)
     int lead = (int)((4u - ((reinterpret_cast<uintptr_t>(x) >> 2) & 3u)) & 3u);
@@ -401,10 +402,10 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
     if (!feasible) {
         // infeasible alignment (or NaN input): the reference's gradient is NaN on every
         // valid frame row (log_softmax backward spreads the NaN), zero_infinity=False
-        float* g_b = a.g + (size_t)b * T * a.V;
+        float* g_b = a.g + (size_t)b * T * a.ld;
         const float qnan = __int_as_float(0x7fc00000);
-        const size_t n = (size_t)Tb * a.V;
-        for (size_t i = lane; i < n; i += 32) g_b[i] = qnan;
+        for (int t = 0; t < Tb; ++t)
+            for (int i = lane; i < a.V; i += 32) g_b[(size_t)t * a.ld + i] = qnan;
         for (size_t i = lane; i < (size_t)Tb * SP; i += 32) glp_b[i] = 0.0f;   // nothing for K3 to apply
         return;
     }
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
             // class and frame (repeats merged by their first occurrence -> one addend per address,
             // deterministic); occupancies below 1e-12 cannot change the fp32 gradient and are skipped
             const float scale = 1.0f / ((float)a.Bn * (float)max(Sb, 1));
-            float* g_b = a.g + (size_t)b * T * a.V;
+            float* g_b = a.g + (size_t)b * T * a.ld;
             if (!any_dup) {
 #pragma unroll 4
                 for (int i = 0; i < n; ++i) {
@@ -472,7 +473,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
                     const float* ab = blk + (size_t)i * NSL + lane * NS;
                     const float lpb = row[0];
                     float bsum = 0.0f;
-                    float* grow = g_b + (size_t)(t0 + i) * a.V;
+                    float* grow = g_b + (size_t)(t0 + i) * a.ld;
 #pragma unroll
                     for (int q = 0; q < NH; ++q) {
                         bsum += vb[q] ? ex2f((ab[2 * q] - lpb) + nll2) : 0.0f;
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
                     }
                     blpart[i * 33 + lane] = bsum;
                     __syncwarp();
-                    float* grow = g_b + (size_t)(t0 + i) * a.V;
+                    float* grow = g_b + (size_t)(t0 + i) * a.ld;
 #pragma unroll
                     for (int q = 0; q < NH; ++q) {
                         if (leader[q]) {
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(32) ctc_lattice_kernel(const CtcArgs a, int K)
                 float sacc = 0.0f;
 #pragma unroll 8
                 for (int l = 0; l < 32; ++l) sacc += blpart[i * 33 + l];
-                if (!(sacc < 1.0e-12f)) atomicAdd(g_b + (size_t)(t0 + i) * a.V + a.blank, -sacc * scale);
+                if (!(sacc < 1.0e-12f)) atomicAdd(g_b + (size_t)(t0 + i) * a.ld + a.blank, -sacc * scale);
             }
             __syncwarp();
         } else {
@@ -760,10 +761,10 @@ __global__ void __launch_bounds__(128) ctc_lattice_mitm_kernel(const CtcArgs a, 
     if (a.g == nullptr) return;
     const float nll2 = mid->nll2;
     if (!mid->feasible) {
-        float* g_b = a.g + (size_t)b * T * a.V;
+        float* g_b = a.g + (size_t)b * T * a.ld;
         const float qnan = __int_as_float(0x7fc00000);
-        const size_t n = (size_t)Tb * a.V;
-        for (size_t i = threadIdx.x; i < n; i += 128) g_b[i] = qnan;
+        for (int t = 0; t < Tb; ++t)
+            for (int i = threadIdx.x; i < a.V; i += 128) g_b[(size_t)t * a.ld + i] = qnan;
         for (size_t i = threadIdx.x; i < (size_t)Tb * SP; i += 128) glp_b[i] = 0.0f;
         return;
     }
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(256) ctc_apply_kernel(const CtcArgs a) {
     const float scale = 1.0f / ((float)a.Bn * (float)max(Sb, 1));
     const float* orow = a.glp + (size_t)row * a.SP;
     const int* dl = a.dlink + (size_t)b * a.S;
-    float* grow = a.g + (size_t)row * a.V;
+    float* grow = a.g + (size_t)row * a.ld;
     for (int j = lane; j <= Sb; j += 32) {
         float v = orow[j];
         int c = a.blank;
@@ -1088,7 +1089,10 @@ static CtcPipe* ctc_pipe() {
 }
 
 static int ctc_make_args(CtcArgs& a, const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
-                         int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws, size_t ws_bytes) {
+                         int B, int T, int V, int S, int blank, float* nll, float* g_logits, void* ws, size_t ws_bytes, int ld = 0) {
+    if (ld == 0) ld = V;
+    ASR_REQUIRE(ld >= V, "asr_ctc: row stride %d smaller than V=%d", ld, V);
+    ASR_REQUIRE((long long)B * T * (long long)ld < (1ll << 40), "asr_ctc: tensor too large");
     ASR_REQUIRE(B > 0 && T > 0 && V > 1 && S >= 0, "asr_ctc: bad shape B=%d T=%d V=%d S=%d", B, T, V, S);
     ASR_REQUIRE(logits && in_len && tgt_len && nll && ws && (S == 0 || targets), "asr_ctc: null pointer");
     ASR_REQUIRE(blank >= 0 && blank < V, "asr_ctc: blank %d out of range", blank);
@@ -1103,6 +1107,7 @@ static int ctc_make_args(CtcArgs& a, const float* logits, const int64_t* targets
     a.in_len = in_len;
     a.tgt_len = tgt_len;
     a.B = B; a.T = T; a.V = V; a.S = S; a.blank = blank;
+    a.ld = ld;
     a.Bn = B;
     a.SP = table_stride(S);
     a.nll = nll;
@@ -1120,12 +1125,12 @@ static int ctc_make_args(CtcArgs& a, const float* logits, const int64_t* targets
 static CtcArgs ctc_slice(const CtcArgs& a, int b0, int n) {
     CtcArgs ac = a;
     ac.B = n;
-    ac.logits = a.logits + (size_t)b0 * a.T * a.V;
+    ac.logits = a.logits + (size_t)b0 * a.T * a.ld;
     ac.targets = a.targets ? a.targets + (size_t)b0 * a.S : nullptr;
     ac.in_len = a.in_len + b0;
     ac.tgt_len = a.tgt_len + b0;
     ac.nll = a.nll + b0;
-    ac.g = a.g ? a.g + (size_t)b0 * a.T * a.V : nullptr;
+    ac.g = a.g ? a.g + (size_t)b0 * a.T * a.ld : nullptr;
     ac.glp = a.glp + (size_t)b0 * a.T * a.SP;
     ac.dlink = a.dlink + (size_t)b0 * a.S;
     ac.ckpt = a.ckpt + (size_t)b0 * a.ckpt_stride;
@@ -1267,6 +1272,53 @@ extern "C" int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets, 
     int rc = asr_ctc_begin_f32(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, &ticket);
     if (rc != 0) return rc;
     return ctc_finish_impl(logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, stream, ticket, true);
+}
+
+extern "C" int asr_ctc_fwd_bwd_ld_f32(const float* logits, const int64_t* targets, const int* in_len, const int* tgt_len,
+                                      int B, int T, int V, int ld, int S, int blank, float* nll, float* g_logits, void* ws,
+                                      size_t ws_bytes, void* stream) {
+    CtcArgs a;
+    int rc = ctc_make_args(a, logits, targets, in_len, tgt_len, B, T, V, S, blank, nll, g_logits, ws, ws_bytes, ld);
+    if (rc != 0) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int nchunk = ctc_slices(B, T);
+    if (nchunk <= 1) return ctc_run(a, 7, st);
+    // same sliced schedule as asr_ctc_fwd_bwd_f32: rows on the caller's stream, lattices on the library's streams
+    CtcPipe* p = ctc_pipe();
+    if (p == nullptr) return 3;
+    int tk = -1;
+    for (int t = 0; t < kTickets && tk < 0; ++t) {
+        int expected = 0;
+        if (p->busy[t].compare_exchange_strong(expected, 1)) tk = t;
+    }
+    ASR_REQUIRE(tk >= 0, "asr_ctc_fwd_bwd_ld_f32: %d calls are already between begin and finish on this device", kTickets);
+    struct Release {
+        std::atomic<int>& f;
+        ~Release() { f.store(0); }
+    } release{p->busy[tk]};
+    for (int c = 0; c < nchunk; ++c) {
+        int b0, n;
+        ctc_slice_bounds(B, nchunk, c, b0, n);
+        if (n <= 0) continue;
+        const CtcArgs ac = ctc_slice(a, b0, n);
+        rc = ctc_run(ac, 1, st);
+        if (rc != 0) return rc;
+        cudaStream_t ls = p->lat[(tk * kMaxChunks + c) % kLatStreams];
+        ASR_CHECK_CUDA(cudaEventRecord(p->k1[tk][c], st));
+        ASR_CHECK_CUDA(cudaStreamWaitEvent(ls, p->k1[tk][c], 0));
+        rc = ctc_run(ac, 2, ls);
+        if (rc != 0) return rc;
+        ASR_CHECK_CUDA(cudaEventRecord(p->done[tk][c], ls));
+    }
+    for (int c = 0; c < nchunk; ++c) {
+        int b0, n;
+        ctc_slice_bounds(B, nchunk, c, b0, n);
+        if (n <= 0) continue;
+        ASR_CHECK_CUDA(cudaStreamWaitEvent(st, p->done[tk][c], 0));
+        rc = ctc_run(ctc_slice(a, b0, n), 4, st);
+        if (rc != 0) return rc;
+    }
+    return 0;
 }
 
 extern "C" int asr_scale_inplace_f32(float* g, size_t n, const float* scale_dev, void* stream) {

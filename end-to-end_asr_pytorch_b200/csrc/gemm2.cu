@@ -1,0 +1,566 @@
+// gemm2.cu - general tcgen05 GEMMs for the TRAINING half of the linear layers and for the vocabulary
+// projection fused with the CTC loss (8(f1)): C[M,N] = A * B with either operand stored K-major or MN-major, so the
+// three products of a Linear layer y = x W^T run on the tensors as torch stores them - no transposed copies:
+//
+//     forward   y  = x  W^T     A = x  [M,K] K-major          B = W  [N,K]  K-major
+//     dX        gx = gy W       A = gy [M,N] K-major          B = W  [N,K]  MN-major  (contraction over N)
+//     dW        gW = gy^T x     A = gy [M,N] MN-major         B = x  [M,K]  MN-major  (contraction over the rows M)
+//
+// (/root/reference/src/transformer/module.py:46-53, attention.py:40-45,59-60, cif_model.py:38 and what autograd makes of them.)
+//
+// Two element types:
+//   fp32 "3xTF32"  x = hi + lo (hi = the top 19 bits, what the tensor core reads of an fp32 word; lo = x - hi, exact in
+//                  fp32), A B ~= lo_a hi_b + hi_a lo_b + hi_a hi_b as three kind::tf32 MMAs per K step into one fp32
+//                  accumulator: fp32-level accuracy (~5e-6 relative at K = 512) on the tensor pipe.  The lo tiles are
+//                  produced in shared memory by the four epilogue warps - an elementwise pass, so it is layout-agnostic.
+//   bf16           one kind::f16 MMA per K step, fp32 accumulation, bf16 or fp32 output.
+//
+// Tiles: CTA = 128 x BN output tile (BN = 128 or 256), K step = 128 bytes (32 fp32 / 64 bf16).  A K-major tile is one TMA
+// box [rows x 128 bytes]; an MN-major tile is a row of boxes [K step rows x 128 bytes], one per 128-byte chunk of the
+// M / N extent - exactly the canonical 128-byte-swizzled MN-major layout of the tcgen05 shared-memory descriptor
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = one box, SBO = 1024 bytes.  Out-of-range rows / columns are
+// zero-filled by TMA, so odd sizes (the 4233-wide vocabulary) need no padding copies, only 16-byte-aligned row strides.
+// Split-K over gridDim.z (dW of a small layer has few output tiles and a long contraction): partial tiles go to a
+// workspace and a second kernel adds them in a fixed order (deterministic, no atomics).
+#include "common.cuh"
+#include "tcgen05.cuh"
+
+#include <cuda_bf16.h>
+
+#include <algorithm>
+
+namespace asr {
+
+constexpr int kG2M = 128;          // rows of C per CTA
+constexpr int kG2RowBytes = 128;   // bytes of one shared-memory row = one swizzle span
+
+struct __align__(8) Gemm2Barriers {
+    uint64_t full[4];
+    uint64_t split[4];
+    uint64_t empty[4];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// One operand tile: ROWS = extent along M (A) or N (B), ELEM = bytes per element.
+template <bool MN, int ROWS, int ELEM>
+struct G2Tile {
+    static constexpr int kChunk = kG2RowBytes / ELEM;       // elements per 128-byte row: 32 fp32 / 64 bf16
+    static constexpr int kBK = kChunk;                        // K elements per stage
+    static constexpr int kBytes = ROWS * kG2RowBytes;
+    static constexpr int kBoxBytes = kBK * kG2RowBytes;       // MN-major: one box = kBK k-rows x 128 bytes
+    static constexpr int kUmmaK = 32 / ELEM;                  // K of one MMA: 8 (tf32) / 16 (bf16)
+    // mn0 = first row (A) / column (B) of the tile in the M / N extent, kc = first K element of the stage
+    __device__ static __forceinline__ void load(unsigned char* tile, const CUtensorMap* map, int kc, int mn0, uint64_t* bar) {
+        if (!MN) {
+#pragma unroll
+            for (int part = 0; part < (ROWS + 255) / 256; ++part)      // a TMA box has at most 256 rows
+                tma_load_2d(tile + part * 256 * kG2RowBytes, map, kc, mn0 + part * 256, bar);
+        } else {
+#pragma unroll
+            for (int c = 0; c < ROWS / kChunk; ++c) tma_load_2d(tile + c * kBoxBytes, map, mn0 + c * kChunk, kc, bar);
+        }
+    }
+    __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int kk) {
+        return MN ? smem_desc_sw128(tile_addr + kk * kUmmaK * kG2RowBytes, kBoxBytes, 1024)
+                  : smem_desc_sw128(tile_addr + kk * 32, 16, 1024);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32, three TF32 products per K step
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct G2F32Cfg {
+    static constexpr int kStages = BN == 256 ? 2 : 3;
+    static constexpr int kATile = kG2M * kG2RowBytes;            // 16 KB
+    static constexpr int kBTile = BN * kG2RowBytes;
+    static constexpr int kStage = 2 * kATile + 2 * kBTile;       // [A | A lo | B | B lo]
+    static constexpr int kSmem = kStages * kStage + 256;
+};
+
+__device__ __forceinline__ void split_lo_tile(const unsigned char* hi_tile, unsigned char* lo_tile, int bytes, int tid128) {
+    const uint4* hi = reinterpret_cast<const uint4*>(hi_tile);
+    float4* lo = reinterpret_cast<float4*>(lo_tile);
+    for (int idx = tid128; idx < bytes / 16; idx += 128) {
+        const uint4 v = hi[idx];
+        lo[idx] = make_float4(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u), __uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u),
+                              __uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u), __uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
+    }
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1)
+gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ bias,
+                  float* __restrict__ c, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    using Cfg = G2F32Cfg<BN>;
+    using TA = G2Tile<A_MN, kG2M, 4>;
+    using TB = G2Tile<B_MN, BN, 4>;
+    constexpr int kStages = Cfg::kStages;
+    Gemm2Barriers* bars = reinterpret_cast<Gemm2Barriers*>(smem + kStages * Cfg::kStage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kG2M;
+    const int nk_total = (K + TA::kBK - 1) / TA::kBK;          // a K tail is zero-filled by TMA
+    const int k_first = blockIdx.z * stages_per_split;
+    const int nk = max(0, min(stages_per_split, nk_total - k_first));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->split[s], 4);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&bars->tmem_base, BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (warp == 4) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_a);
+            tma_prefetch_desc(&tm_b);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % kStages;
+                if (k >= kStages) mbar_wait(&bars->empty[s], ((k / kStages) - 1) & 1);
+                unsigned char* st = smem + s * Cfg::kStage;
+                mbar_arrive_expect_tx(&bars->full[s], Cfg::kATile + Cfg::kBTile);
+                const int kc = (k_first + k) * TA::kBK;
+                TA::load(st, &tm_a, kc, m0, &bars->full[s]);
+                TB::load(st + 2 * Cfg::kATile, &tm_b, kc, n0, &bars->full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc_tf32(kG2M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % kStages;
+                mbar_wait(&bars->split[s], (k / kStages) & 1);
+                tc_fence_after();
+                const uint32_t base = smem_u32(smem + s * Cfg::kStage);
+                const uint32_t a_hi = base, a_lo = base + Cfg::kATile, b_hi = base + 2 * Cfg::kATile, b_lo = b_hi + Cfg::kBTile;
+#pragma unroll
+                for (int kk = 0; kk < TA::kBK / TA::kUmmaK; ++kk) {
+                    umma_tf32(tmem, TA::desc(a_lo, kk), TB::desc(b_hi, kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                    umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_lo, kk), idesc, 1u);
+                    umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_hi, kk), idesc, 1u);
+                }
+                tc_commit(&bars->empty[s]);
+            }
+            tc_commit(&bars->acc_full);
+        }
+    } else {
+        // splitter: lo = x - (x with the 13 low mantissa bits cleared); the raw tile serves as the TF32 head
+        for (int k = 0; k < nk; ++k) {
+            const int s = k % kStages;
+            mbar_wait(&bars->full[s], (k / kStages) & 1);
+            unsigned char* st = smem + s * Cfg::kStage;
+            split_lo_tile(st, st + Cfg::kATile, Cfg::kATile, threadIdx.x);
+            split_lo_tile(st + 2 * Cfg::kATile, st + 2 * Cfg::kATile + Cfg::kBTile, Cfg::kBTile, threadIdx.x);
+            fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's operand fetch
+            mbar_arrive_warp(&bars->split[s]);
+        }
+        // epilogue: thread = row of the tile (TMEM lane), 32 columns at a time
+        const int row = m0 + warp * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        float* dst = c + (size_t)blockIdx.z * split_stride + (size_t)min(row, M - 1) * ldc + n0;
+        const bool add_bias = bias != nullptr && gridDim.z == 1;
+        // float4 stores when rows are 16-byte aligned; a float4 that starts inside N may run into the row's padding
+        // (ldc >= N rounded up to 4), where the accumulator holds exact zeros (TMA zero fill)
+        const bool vec = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15u) == 0;
+        const int n_store = vec ? min(ldc, (N + 3) & ~3) : N;
+        if (nk > 0) {
+            mbar_wait(&bars->acc_full, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+            if (n0 + cc >= n_store) break;
+            float v[32];
+            if (nk > 0) {
+                tmem_ld32(tmem + lane_base + cc, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (row < M) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int n = n0 + cc + i;
+                    if (vec) {
+                        if (n < n_store) {
+                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            if (add_bias) {
+                                o.x += (n < N) ? __ldg(bias + n) : 0.0f;
+                                o.y += (n + 1 < N) ? __ldg(bias + n + 1) : 0.0f;
+                                o.z += (n + 2 < N) ? __ldg(bias + n + 2) : 0.0f;
+                                o.w += (n + 3 < N) ? __ldg(bias + n + 3) : 0.0f;
+                            }
+                            *reinterpret_cast<float4*>(dst + cc + i) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (n + u < N) dst[cc + i + u] = v[i + u] + (add_bias ? __ldg(bias + n + u) : 0.0f);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, BN);
+    }
+}
+
+// out[i] = sum_z part[z][i] (+ bias[i % N] on the valid columns): fixed order, deterministic
+__global__ void __launch_bounds__(256) splitk_reduce_f32_kernel(const float* __restrict__ part, int splits, size_t split_stride, int M,
+                                                               int N, int ldp, const float* __restrict__ bias, float* __restrict__ out,
+                                                               int ldc) {
+    const size_t total = (size_t)M * N;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int r = (int)(i / N), n = (int)(i - (size_t)r * N);
+        float acc = bias != nullptr ? __ldg(bias + n) : 0.0f;
+        for (int z = 0; z < splits; ++z) acc += part[(size_t)z * split_stride + (size_t)r * ldp + n];
+        out[(size_t)r * ldc + n] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// bf16
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct G2B16Cfg {
+    static constexpr int kStages = BN == 256 ? 2 : 3;
+    static constexpr int kATile = kG2M * kG2RowBytes;
+    static constexpr int kBTile = BN * kG2RowBytes;
+    static constexpr int kStage = kATile + kBTile;
+    static constexpr int kSmem = kStages * kStage + 256;
+};
+
+// EPI bit 0: ReLU; OUT_F32: fp32 output (weight gradients for fp32 master weights, split-K partials) instead of bf16
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool RELU>
+__global__ void __launch_bounds__(192, 2)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ bias,
+                 void* __restrict__ c_, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    using Cfg = G2B16Cfg<BN>;
+    using TA = G2Tile<A_MN, kG2M, 2>;
+    using TB = G2Tile<B_MN, BN, 2>;
+    constexpr int kStages = Cfg::kStages;
+    Gemm2Barriers* bars = reinterpret_cast<Gemm2Barriers*>(smem + kStages * Cfg::kStage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kG2M;
+    const int nk_total = (K + TA::kBK - 1) / TA::kBK;
+    const int k_first = blockIdx.z * stages_per_split;
+    const int nk = max(0, min(stages_per_split, nk_total - k_first));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        mbar_init(&bars->acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&bars->tmem_base, BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (warp == 4) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_a);
+            tma_prefetch_desc(&tm_b);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % kStages;
+                if (k >= kStages) mbar_wait(&bars->empty[s], ((k / kStages) - 1) & 1);
+                unsigned char* st = smem + s * Cfg::kStage;
+                mbar_arrive_expect_tx(&bars->full[s], Cfg::kATile + Cfg::kBTile);
+                const int kc = (k_first + k) * TA::kBK;
+                TA::load(st, &tm_a, kc, m0, &bars->full[s]);
+                TB::load(st + Cfg::kATile, &tm_b, kc, n0, &bars->full[s]);
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc(kG2M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            for (int k = 0; k < nk; ++k) {
+                const int s = k % kStages;
+                mbar_wait(&bars->full[s], (k / kStages) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * Cfg::kStage);
+                const uint32_t b_addr = a_addr + Cfg::kATile;
+#pragma unroll
+                for (int kk = 0; kk < TA::kBK / TA::kUmmaK; ++kk)
+                    umma_bf16(tmem, TA::desc(a_addr, kk), TB::desc(b_addr, kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                tc_commit(&bars->empty[s]);
+            }
+            tc_commit(&bars->acc_full);
+        }
+    } else {
+        const int row = m0 + warp * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        const bool add_bias = bias != nullptr && gridDim.z == 1;
+        if (nk > 0) {
+            mbar_wait(&bars->acc_full, 0);
+            tc_fence_after();
+        }
+        const size_t row_off = (size_t)blockIdx.z * split_stride + (size_t)min(row, M - 1) * ldc + n0;
+        float* dst_f = static_cast<float*>(c_) + row_off;
+        __nv_bfloat16* dst_h = static_cast<__nv_bfloat16*>(c_) + row_off;
+        constexpr int kVecElems = OUT_F32 ? 4 : 8;                       // elements per 16-byte store
+        const bool vec = (ldc % kVecElems) == 0 && (reinterpret_cast<uintptr_t>(c_) & 15u) == 0;
+        const int n_store = vec ? min(ldc, (N + kVecElems - 1) / kVecElems * kVecElems) : N;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+            if (n0 + cc >= n_store) break;
+            float v[32];
+            if (nk > 0) {
+                tmem_ld32(tmem + lane_base + cc, v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            }
+            if (row < M) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = n0 + cc + i;
+                    float x = v[i] + ((add_bias && n < N) ? __ldg(bias + n) : 0.0f);
+                    if (RELU) x = fmaxf(x, 0.0f);
+                    v[i] = x;
+                }
+#pragma unroll
+                for (int i = 0; i < 32; i += kVecElems) {
+                    const int n = n0 + cc + i;
+                    if (vec) {
+                        if (n < n_store) {
+                            if (OUT_F32) {
+                                *reinterpret_cast<float4*>(dst_f + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                            } else {
+                                *reinterpret_cast<uint4*>(dst_h + cc + i) =
+                                    make_uint4(cvt_bf16x2(v[i], v[i + 1]), cvt_bf16x2(v[i + 2], v[i + 3]),
+                                               cvt_bf16x2(v[i + 4], v[i + 5]), cvt_bf16x2(v[i + 6], v[i + 7]));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kVecElems; ++u) {
+                            if (n + u < N) {
+                                if (OUT_F32) dst_f[cc + i + u] = v[i + u];
+                                else dst_h[cc + i + u] = __float2bfloat16_rn(v[i + u]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, BN);
+    }
+}
+
+// partial fp32 tiles -> bf16 or fp32 output (+ bias, ReLU)
+__global__ void __launch_bounds__(256) splitk_reduce_out_kernel(const float* __restrict__ part, int splits, size_t split_stride, int M,
+                                                               int N, int ldp, const float* __restrict__ bias, int relu, void* out_,
+                                                               int ldc, int out_f32) {
+    const size_t total = (size_t)M * N;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int r = (int)(i / N), n = (int)(i - (size_t)r * N);
+        float acc = bias != nullptr ? __ldg(bias + n) : 0.0f;
+        for (int z = 0; z < splits; ++z) acc += part[(size_t)z * split_stride + (size_t)r * ldp + n];
+        if (relu) acc = fmaxf(acc, 0.0f);
+        if (out_f32) static_cast<float*>(out_)[(size_t)r * ldc + n] = acc;
+        else static_cast<__nv_bfloat16*>(out_)[(size_t)r * ldc + n] = __float2bfloat16_rn(acc);
+    }
+}
+
+}  // namespace asr
+
+using namespace asr;
+
+// ---- host side --------------------------------------------------------------------------------------------
+namespace {
+
+struct Plan {
+    int bn, splits, stages_per_split, nk_total;
+    dim3 grid;
+};
+
+// Tile width and split-K: one wave first.  256-wide tiles halve the operand traffic per flop but need the CTAs; a long
+// contraction with few output tiles (dW of a 512 x 512 layer) is cut along K until the SMs are covered.
+Plan make_plan(int M, int N, int K, int bk, int force_bn, int force_splits, bool allow_split) {
+    Plan p;
+    const long long mt = (M + kG2M - 1) / kG2M;
+    const long long ctas256 = mt * ((N + 255) / 256);
+    p.bn = (N >= 256 && ctas256 >= num_sms()) ? 256 : 128;
+    if (force_bn == 128 || force_bn == 256) p.bn = force_bn;
+    const long long ctas = mt * ((N + p.bn - 1) / p.bn);
+    p.nk_total = (K + bk - 1) / bk;
+    int splits = 1;
+    if (allow_split && ctas < num_sms()) {
+        splits = (int)std::min<long long>(8, (num_sms() + ctas - 1) / ctas);
+        while (splits > 1 && p.nk_total / splits < 8) --splits;      // every split keeps at least 8 K steps
+    }
+    if (force_splits > 0) splits = std::max(1, std::min(force_splits, p.nk_total));
+    if (!allow_split) splits = 1;
+    p.stages_per_split = (p.nk_total + splits - 1) / splits;
+    p.splits = (p.nk_total + p.stages_per_split - 1) / p.stages_per_split;
+    p.grid = dim3((unsigned)((N + p.bn - 1) / p.bn), (unsigned)mt, (unsigned)p.splits);
+    return p;
+}
+
+// tensor map of one operand: K-major = [mn rows x k cols] (box ROWS x chunk), MN-major = [k rows x mn cols] (box chunk-k x chunk)
+int make_operand_map(CUtensorMap* map, CUtensorMapDataType dt, int elem, const void* base, bool mn_major, int mn, int k, int ld,
+                     int tile_rows) {
+    const int chunk = kG2RowBytes / elem;
+    if (!mn_major)
+        return make_tmap_2d(map, dt, elem, base, (uint64_t)mn, (uint64_t)k, (uint64_t)ld * elem, (uint32_t)std::min(tile_rows, 256),
+                            (uint32_t)chunk, CU_TENSOR_MAP_SWIZZLE_128B);
+    return make_tmap_2d(map, dt, elem, base, (uint64_t)k, (uint64_t)mn, (uint64_t)ld * elem, (uint32_t)chunk, (uint32_t)chunk,
+                        CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+template <typename KernelT>
+int set_smem_once(KernelT kernel, int bytes, bool& done) {
+    if (!done) {
+        ASR_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        done = true;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" size_t asr_gemm_workspace_bytes(int M, int N, int K) {
+    (void)K;
+    if (M <= 0 || N <= 0) return 0;
+    return (size_t)8 * M * N * sizeof(float) + 256;      // up to 8 split-K partial tiles
+}
+
+extern "C" int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb, const float* bias,
+                            int M, int N, int K, float* c, int ldc, void* ws, size_t ws_bytes, void* stream) {
+    ASR_REQUIRE(a && b && c, "asr_gemm_f32: null pointer");
+    ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_gemm_f32: bad shape M=%d N=%d K=%d", M, N, K);
+    ASR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "asr_gemm_f32: operand row strides (%d, %d) must be multiples of 4 floats (16-byte rows for TMA)", lda, ldb);
+    ASR_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldc >= N, "asr_gemm_f32: row stride smaller than the row");
+    ASR_REQUIRE(aligned16(a) && aligned16(b), "asr_gemm_f32: operands must be 16-byte aligned");
+    ASR_REQUIRE((long long)(M + kG2M - 1) / kG2M <= 65535, "asr_gemm_f32: M=%d exceeds the grid limit", M);
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool can_split = ws != nullptr && ws_bytes >= asr_gemm_workspace_bytes(M, N, K);
+    const Plan p = make_plan(M, N, K, 32, get_opt("gemm_f32_bn"), get_opt("gemm_split_k"), can_split);
+    CUtensorMap ta, tb;
+    if (make_operand_map(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, a_mn_major != 0, M, K, lda, kG2M) ||
+        make_operand_map(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b, b_mn_major != 0, N, K, ldb, p.bn))
+        return 4;
+    float* part = nullptr;
+    if (p.splits > 1) part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* dst = p.splits > 1 ? part : c;
+    const int ldd = p.splits > 1 ? N : ldc;
+    const size_t split_stride = (size_t)M * N;
+#define ASR_G2F(BNV, AM, BM)                                                                                        \
+    do {                                                                                                            \
+        static bool done = false;                                                                                   \
+        if (set_smem_once(gemm_f32x3_kernel<BNV, AM, BM>, G2F32Cfg<BNV>::kSmem, done)) return 1;                     \
+        gemm_f32x3_kernel<BNV, AM, BM><<<p.grid, 192, G2F32Cfg<BNV>::kSmem, st>>>(ta, tb, bias, dst, M, N, K, ldd,    \
+                                                                                 p.stages_per_split, split_stride); \
+    } while (0)
+    const int sel = (p.bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
+    switch (sel) {
+        case 0: ASR_G2F(128, false, false); break;
+        case 1: ASR_G2F(128, false, true); break;
+        case 2: ASR_G2F(128, true, false); break;
+        case 3: ASR_G2F(128, true, true); break;
+        case 4: ASR_G2F(256, false, false); break;
+        case 5: ASR_G2F(256, false, true); break;
+        case 6: ASR_G2F(256, true, false); break;
+        default: ASR_G2F(256, true, true); break;
+    }
+#undef ASR_G2F
+    ASR_LAUNCH_CHECK();
+    if (p.splits > 1) {
+        const size_t total = (size_t)M * N;
+        const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
+        splitk_reduce_f32_kernel<<<blocks, 256, 0, st>>>(part, p.splits, split_stride, M, N, N, bias, c, ldc);
+        ASR_LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void* b, int b_mn_major, int ldb, const float* bias,
+                             int relu, int M, int N, int K, void* c, int ldc, int out_f32, void* ws, size_t ws_bytes, void* stream) {
+    ASR_REQUIRE(a && b && c, "asr_gemm_bf16: null pointer");
+    ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_gemm_bf16: bad shape M=%d N=%d K=%d", M, N, K);
+    ASR_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "asr_gemm_bf16: operand row strides (%d, %d) must be multiples of 8 elements (16-byte rows for TMA)", lda, ldb);
+    ASR_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldc >= N, "asr_gemm_bf16: row stride smaller than the row");
+    ASR_REQUIRE(aligned16(a) && aligned16(b), "asr_gemm_bf16: operands must be 16-byte aligned");
+    ASR_REQUIRE((long long)(M + kG2M - 1) / kG2M <= 65535, "asr_gemm_bf16: M=%d exceeds the grid limit", M);
+    ASR_REQUIRE(!(relu && out_f32), "asr_gemm_bf16: ReLU is fused for bf16 outputs only");
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool can_split = ws != nullptr && ws_bytes >= asr_gemm_workspace_bytes(M, N, K);
+    const Plan p = make_plan(M, N, K, 64, get_opt("gemm_variant") == 1 ? 128 : 0, get_opt("gemm_split_k"), can_split);
+    CUtensorMap ta, tb;
+    if (make_operand_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, a_mn_major != 0, M, K, lda, kG2M) ||
+        make_operand_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, b_mn_major != 0, N, K, ldb, p.bn))
+        return 4;
+    const bool split = p.splits > 1;
+    float* part = split ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255) : nullptr;
+    void* dst = split ? static_cast<void*>(part) : c;
+    const int ldd = split ? N : ldc;
+    const size_t split_stride = (size_t)M * N;
+    const bool f32 = split || out_f32 != 0;
+    const bool rl = relu != 0 && !split;
+#define ASR_G2H(BNV, AM, BM, F32, RL)                                                                                     \
+    do {                                                                                                                  \
+        static bool done = false;                                                                                         \
+        if (set_smem_once(gemm_bf16_kernel<BNV, AM, BM, F32, RL>, G2B16Cfg<BNV>::kSmem, done)) return 1;                    \
+        gemm_bf16_kernel<BNV, AM, BM, F32, RL><<<p.grid, 192, G2B16Cfg<BNV>::kSmem, st>>>(ta, tb, bias, dst, M, N, K, ldd,   \
+                                                                                        p.stages_per_split, split_stride); \
+    } while (0)
+#define ASR_G2H_LAYOUT(BNV, F32, RL)                                    \
+    do {                                                                \
+        if (!a_mn_major && !b_mn_major) ASR_G2H(BNV, false, false, F32, RL); \
+        else if (!a_mn_major) ASR_G2H(BNV, false, true, F32, RL);        \
+        else if (!b_mn_major) ASR_G2H(BNV, true, false, F32, RL);        \
+        else ASR_G2H(BNV, true, true, F32, RL);                          \
+    } while (0)
+    if (p.bn == 256) {
+        if (f32) ASR_G2H_LAYOUT(256, true, false);
+        else if (rl) ASR_G2H_LAYOUT(256, false, true);
+        else ASR_G2H_LAYOUT(256, false, false);
+    } else {
+        if (f32) ASR_G2H_LAYOUT(128, true, false);
+        else if (rl) ASR_G2H_LAYOUT(128, false, true);
+        else ASR_G2H_LAYOUT(128, false, false);
+    }
+#undef ASR_G2H_LAYOUT
+#undef ASR_G2H
+    ASR_LAUNCH_CHECK();
+    if (split) {
+        const size_t total = (size_t)M * N;
+        const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
+        splitk_reduce_out_kernel<<<blocks, 256, 0, st>>>(part, p.splits, split_stride, M, N, N, bias, relu, c, ldc, out_f32);
+        ASR_LAUNCH_CHECK();
+    }
+    return 0;
+}

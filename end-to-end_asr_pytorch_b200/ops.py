@@ -208,39 +208,157 @@ def linear_f32(x, weight, bias=None):
     return y.reshape(*x.shape[:-1], N)
 
 
+def _gemm_ws(M, N, K, device):
+    nbytes = _lib.lib().asr_gemm_workspace_bytes(M, N, K)
+    return torch.empty((nbytes // 4 + 1,), dtype=torch.float32, device=device), nbytes
+
+
+def gemm_f32(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None, n_valid=None, split_k=True):
+    """C = A B (+ bias) in fp32 on the tensor cores at fp32-level accuracy (three TF32 products per K step), operands as stored:
+    a: [M,K] (a_mn_major False) or [K,M] (True); b: [N,K] (False) or [K,N] (True); 2-D, last dim contiguous, row strides
+    multiples of 4.  `out` may be a [M, ld >= N] buffer (its first N columns are written, plus zeros up to the next
+    multiple of 4).  The building block of the linear layers' backward products and of ops.ctc_fc_loss."""
+    _require_cuda("a", a, torch.float32)
+    _require_cuda("b", b, torch.float32)
+    if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("gemm_f32: 2-D operands with a contiguous last dimension expected")
+    M, K = (a.shape[1], a.shape[0]) if a_mn_major else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else (b.shape[0], b.shape[1])
+    if n_valid is not None:
+        if b_mn_major:
+            N = n_valid
+        else:
+            raise ValueError("gemm_f32: n_valid applies to an MN-major b")
+    if K != Kb:
+        raise ValueError("gemm_f32: contraction lengths differ (%d vs %d)" % (K, Kb))
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    elif out.dim() != 2 or out.shape[0] != M or out.shape[1] < N or out.stride(1) != 1:
+        raise ValueError("gemm_f32: out must be [M, >= N] with a contiguous last dimension")
+    ws, wsb = _gemm_ws(M, N, K, a.device) if split_k else (None, 0)
+    if bias is not None:
+        bias = bias.detach().to(device=a.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(a.device):
+        check(_lib.lib().asr_gemm_f32(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0), ptr(bias),
+                                      M, N, K, ptr(out), out.stride(0), ptr(ws), wsb, stream_ptr()), "asr_gemm_f32")
+    return out
+
+
+def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, bias=None, relu=False, out_dtype=torch.bfloat16, split_k=True):
+    """C = A B (+ bias, ReLU) with bf16 operands and fp32 accumulation on the tensor cores; same operand conventions as
+    gemm_f32 (row strides multiples of 8).  out_dtype bf16 or fp32 (weight gradients for fp32 master weights)."""
+    _require_cuda("a", a, torch.bfloat16)
+    _require_cuda("b", b, torch.bfloat16)
+    if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+        raise ValueError("gemm_bf16: 2-D operands with a contiguous last dimension expected")
+    M, K = (a.shape[1], a.shape[0]) if a_mn_major else (a.shape[0], a.shape[1])
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn_major else (b.shape[0], b.shape[1])
+    if K != Kb:
+        raise ValueError("gemm_bf16: contraction lengths differ (%d vs %d)" % (K, Kb))
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    ws, wsb = _gemm_ws(M, N, K, a.device) if split_k else (None, 0)
+    if bias is not None:
+        bias = bias.detach().to(device=a.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(a.device):
+        check(_lib.lib().asr_gemm_bf16(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0), ptr(bias),
+                                       int(relu), M, N, K, ptr(out), out.stride(0), int(out_dtype == torch.float32), ptr(ws), wsb,
+                                       stream_ptr()), "asr_gemm_bf16")
+    return out
+
+
 class _LinearF32Function(torch.autograd.Function):
-    """y = x W^T + b with all three GEMMs (y, dx = gy W, dW = gy^T x) on the fp32 tensor-core kernel; the
-    transposed operands are materialised with one copy each (small next to the products)."""
+    """y = x W^T + b with all three products (y, dx = gy W, dW = gy^T x) on the fp32 tensor-core GEMM, every operand read
+    as torch stores it (K-major or MN-major descriptors): no transposed copies.  Reference: what autograd does for an
+    nn.Linear of the model shell (module.py:46-53, attention.py:40-45,59-60) - there as cuBLAS SIMT sgemm."""
 
     @staticmethod
     def forward(ctx, x, weight, bias):
         K = x.shape[-1]
-        x2 = x.reshape(-1, K).contiguous()
-        ctx.save_for_backward(x2, weight)
+        x2 = x.reshape(-1, K)
+        if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        ctx.save_for_backward(x2, w)
         ctx.x_shape = x.shape
         ctx.has_bias = bias is not None
-        return linear_f32(x2, weight, bias).reshape(*x.shape[:-1], weight.shape[0])
+        return gemm_f32(x2, w, bias=bias, split_k=False).reshape(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, gy):
-        x2, weight = ctx.saved_tensors
-        N, K = weight.shape
-        M = x2.shape[0]
-        gy2 = gy.reshape(-1, N).contiguous()
+        x2, w = ctx.saved_tensors
+        N, K = w.shape
+        gy2 = gy.reshape(-1, N)
+        if gy2.stride(1) != 1 or gy2.stride(0) % 4 != 0 or gy2.data_ptr() % 16 != 0:
+            gy2 = gy2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            # contraction over N: the kernel wants 16-byte rows (N % 4 == 0); the 4233-wide vocabulary projection falls back
-            gx = (linear_f32(gy2, weight.t().contiguous()) if N % 4 == 0 else gy2 @ weight).reshape(ctx.x_shape)
+            gx = gemm_f32(gy2, w, b_mn_major=True, split_k=False).reshape(ctx.x_shape)      # contraction over N
         if ctx.needs_input_grad[1]:
-            gw = linear_f32(gy2.t().contiguous(), x2.t().contiguous()) if M % 4 == 0 else gy2.t() @ x2
+            gw = gemm_f32(gy2, x2, a_mn_major=True, b_mn_major=True)                         # contraction over the rows
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = gy2.sum(0)
         return gx, gw, gb
 
 
+def linear_f32_ok(x, weight):
+    """Shapes the fp32 tensor-core linear layer takes: 16-byte rows for every operand of its three products."""
+    return weight.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and x.numel() > 0
+
+
 def linear_f32_autograd(x, weight, bias=None):
-    """Differentiable fp32 linear layer on the tensor cores (three TF32 products per tile, see linear_f32)."""
+    """Differentiable fp32 linear layer on the tensor cores (three TF32 products per tile, see gemm_f32)."""
     return _LinearF32Function.apply(x, weight, bias)
+
+
+class _LinearBf16Function(torch.autograd.Function):
+    """bf16 linear layer for mixed-precision training (fp32 master weights, bf16 activations): y = act(x W^T + b) with the
+    bias / ReLU in the GEMM epilogue; backward dx = (gy o relu') W in bf16 and dW = gy^T x accumulated and written in fp32
+    (the master weights' dtype), both on operands as stored.  The ReLU mask comes from the saved output (y > 0)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        K = x.shape[-1]
+        x2 = x.reshape(-1, K)
+        if x2.dtype != torch.bfloat16:
+            x2 = x2.to(torch.bfloat16)
+        if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        w16 = weight.detach().to(torch.bfloat16).contiguous()
+        y = gemm_bf16(x2, w16, bias=bias, relu=relu, split_k=False)
+        ctx.save_for_backward(x2, w16, y if relu else None)
+        ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
+        ctx.has_bias, ctx.relu = bias is not None, relu
+        ctx.w_dtype = weight.dtype
+        return y.reshape(*x.shape[:-1], w16.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, w16, y = ctx.saved_tensors
+        N, K = w16.shape
+        gy2 = gy.reshape(-1, N)
+        if gy2.dtype != torch.bfloat16:
+            gy2 = gy2.to(torch.bfloat16)
+        if ctx.relu:
+            gy2 = gy2 * (y > 0).to(gy2.dtype)
+        if gy2.stride(1) != 1 or gy2.stride(0) % 8 != 0 or gy2.data_ptr() % 16 != 0:
+            gy2 = gy2.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = gemm_bf16(gy2, w16, b_mn_major=True, split_k=False).reshape(ctx.x_shape).to(ctx.x_dtype)
+        if ctx.needs_input_grad[1]:
+            gw = gemm_bf16(gy2, x2, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32).to(ctx.w_dtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = gy2.float().sum(0)
+        return gx, gw, gb, None
+
+
+def linear_bf16_ok(x, weight):
+    return weight.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.numel() > 0
+
+
+def linear_bf16_autograd(x, weight, bias=None, relu=False):
+    """Differentiable bf16 linear layer (+ fused bias / ReLU) on the tensor cores, fp32 weight gradients."""
+    return _LinearBf16Function.apply(x, weight, bias, bool(relu))
 
 
 def linear_residual_layernorm(x, weight, bias, residual, ln_weight, ln_bias, eps=1e-5):
@@ -363,6 +481,103 @@ def ctc_loss(logits, len_logits, targets, blank=None, return_nll=False):
     if return_nll:
         return loss, nll
     return loss
+
+
+# ---------------------------------------------------------------------------------
+# Vocabulary projection fused with the CTC loss  (reference: ctc_fc at src/transformer/cif_model.py:38,
+# transformer.py:148, ctcModel/decoder.py:32-36 followed by the loss call of loss.py:39-43)
+# ---------------------------------------------------------------------------------
+class _CtcFcLossFunction(torch.autograd.Function):
+    """loss = ctc(h W^T): the [B,T,V] logits live only inside this call, in rows padded to a multiple of 4 floats.
+    One fp32 tensor-core GEMM writes them, the CTC kernels replace them IN PLACE by d loss / d logits (every row is
+    read once and written once), and two more GEMMs read that gradient as stored - K-major for d h = g W, MN-major
+    for d W = g^T h - so no [B,T,V] tensor is ever copied, transposed or kept for backward."""
+
+    @staticmethod
+    def forward(ctx, hidden, weight, targets, in_len, tgt_len, blank):
+        B, T, K = hidden.shape
+        V = weight.shape[0]
+        dev = hidden.device
+        ld = (V + 3) // 4 * 4
+        h2 = hidden.reshape(B * T, K)
+        if not h2.is_contiguous():
+            h2 = h2.contiguous()
+        w = weight if weight.is_contiguous() else weight.contiguous()
+        buf = torch.empty((B * T, ld), dtype=torch.float32, device=dev)
+        gemm_f32(h2, w, out=buf, split_k=False)                                   # logits, columns [0, V)
+        need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        nll = torch.empty((B,), dtype=torch.float32, device=dev)
+        S = targets.shape[1]
+        ws_bytes = _lib.lib().asr_ctc_workspace_bytes(B, T, V, S)
+        ws = torch.empty((ws_bytes // 4 + 1,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_ctc_fwd_bwd_ld_f32(ptr(buf), ptr(targets) if S > 0 else None, ptr(in_len), ptr(tgt_len),
+                                                    B, T, V, ld, S, int(blank), ptr(nll), ptr(buf) if need_grad else None,
+                                                    ptr(ws), ws_bytes, stream_ptr()), "asr_ctc_fwd_bwd_ld_f32")
+        loss = (nll / tgt_len.clamp(min=1).to(nll.dtype)).mean()
+        gh = gw = None
+        if need_grad:
+            g = buf[:, :V]                                                        # [B*T, V], row stride ld
+            if ctx.needs_input_grad[0]:
+                gh = gemm_f32(g, w, b_mn_major=True, split_k=False).reshape(B, T, K)
+            if ctx.needs_input_grad[1]:
+                gw = gemm_f32(g, h2, a_mn_major=True, b_mn_major=True)
+        ctx.grads = (gh, gw)
+        ctx.mark_non_differentiable(nll)
+        return loss, nll
+
+    @staticmethod
+    def backward(ctx, g_loss, g_nll_unused):
+        gh, gw = ctx.grads
+        ctx.grads = (None, None)
+        ref = gh if gh is not None else gw
+        if ref is None:
+            return None, None, None, None, None, None
+        scale = g_loss.reshape(1).to(dtype=torch.float32, device=ref.device).contiguous()
+        with torch.cuda.device(ref.device):
+            for t in (gh, gw):
+                if t is not None:      # scales in place on the device only when the incoming gradient is not exactly 1
+                    check(_lib.lib().asr_scale_inplace_f32(ptr(t), t.numel(), ptr(scale), stream_ptr()), "asr_scale_inplace_f32")
+        return gh, gw, None, None, None, None
+
+
+def ctc_fc_loss(hidden, weight, len_logits, targets, blank=None, return_nll=False):
+    """Mean CTC loss of the projected logits hidden [B,T,K] x weight [V,K]^T (no bias, like ctc_fc) without materialising
+    them for the caller: see _CtcFcLossFunction.  Same conventions as ctc_loss (targets [B,S] 0-padded int64, blank = V-1)."""
+    _require_cuda("hidden", hidden, torch.float32)
+    _require_cuda("weight", weight, torch.float32)
+    if hidden.dim() != 3 or weight.dim() != 2 or weight.shape[1] != hidden.shape[2]:
+        raise ValueError("ctc_fc_loss: hidden [B,T,K] and weight [V,K] expected")
+    if hidden.shape[2] % 4 != 0:
+        raise ValueError("ctc_fc_loss: K must be a multiple of 4")
+    V = weight.shape[0]
+    if blank is None:
+        blank = V - 1
+    targets_c = targets.to(device=hidden.device, dtype=torch.int64).contiguous()
+    tgt_len = targets_c.ne(0).sum(1).to(torch.int32)
+    in_len = len_logits.to(device=hidden.device, dtype=torch.int32).contiguous()
+    loss, nll = _CtcFcLossFunction.apply(hidden, weight, targets_c, in_len, tgt_len, blank)
+    return (loss, nll) if return_nll else loss
+
+
+class ProjectedLogits:
+    """Stand-in for the `ctc_logits` tensor a model returns when the projection is fused with the loss: it carries the
+    projection's input and weight to `cal_ctc_ce_loss` / `cal_ctc_qua_ce_loss` / `cal_loss`, which call ctc_fc_loss.
+    `materialize()` gives the actual [B,T,V] tensor to any other consumer."""
+
+    def __init__(self, hidden, weight):
+        self.hidden, self.weight = hidden, weight
+
+    def size(self, dim=None):
+        shape = tuple(self.hidden.shape[:-1]) + (self.weight.shape[0],)
+        return shape if dim is None else shape[dim]
+
+    @property
+    def shape(self):
+        return self.size()
+
+    def materialize(self):
+        return torch.nn.functional.linear(self.hidden, self.weight)
 
 
 # ---------------------------------------------------------------------------------

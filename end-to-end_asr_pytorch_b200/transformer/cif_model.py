@@ -17,7 +17,7 @@ import importlib
 import torch
 import torch.nn as nn
 
-from ..ops import cif as _cif_op
+from ..ops import cif as _cif_op, ProjectedLogits
 from .module import Linear
 
 
@@ -52,6 +52,11 @@ class CIF_Model(nn.Module):
         # one utterance of the batch has no padding - alphas are scaled to sum to #labels +- 0.5), and the
         # more-fires-than-rows check (which the reference dies on, :100) is skipped.
         self.static_shapes = False
+        # True (training mode only): forward returns an ops.ProjectedLogits in place of `ctc_logits`, and the loss
+        # functions of this package run the ctc_fc projection fused with the CTC loss: the
+        # [B,T,V] logits are produced, turned into their gradient in place and consumed by the backward GEMMs inside
+        # one call, instead of living in HBM from forward to backward.
+        self.fused_ctc_fc = False
         self.decoder = decoder
         self.spec_aug_cfg = spec_aug_cfg
         self.ctc_fc = Linear(encoder.d_output, decoder.d_output, bias=False)
@@ -70,7 +75,11 @@ class CIF_Model(nn.Module):
         conv_outputs, len_sequence = self.conv_encoder(features, len_features)
         encoder_outputs = self.encoder(conv_outputs, len_sequence)
 
-        ctc_logits = self.ctc_fc(encoder_outputs)
+        if (getattr(self, "fused_ctc_fc", False) and self.training and encoder_outputs.is_cuda
+                and encoder_outputs.dtype == torch.float32 and not torch.is_autocast_enabled("cuda")):
+            ctc_logits = ProjectedLogits(encoder_outputs, self.ctc_fc.weight)
+        else:
+            ctc_logits = self.ctc_fc(encoder_outputs)
         len_ctc_logits = len_sequence
 
         # quantity (before scaling) and target-length scaling, reference :43-48

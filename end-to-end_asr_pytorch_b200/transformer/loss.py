@@ -8,7 +8,7 @@ stays plain PyTorch, restated here so the module is self-contained.
 import torch
 import torch.nn.functional as F
 
-from ..ops import ctc_loss as _ctc_loss
+from ..ops import ctc_loss as _ctc_loss, ctc_fc_loss as _ctc_fc_loss, ProjectedLogits
 
 
 def cal_ce_loss(logits, targets, smoothing=0.0):
@@ -31,7 +31,10 @@ def cal_ce_loss(logits, targets, smoothing=0.0):
 def cal_ctc_ce_loss(logits_ctc, len_logits_ctc, logits_ce, targets, smoothing=0.0):
     """(ctc_loss, ce_loss) - reference loss.py:34-48.  blank = V-1, target
     lengths = number of non-zero labels, reduction 'mean', zero_infinity off."""
-    ctc = _ctc_loss(logits_ctc, len_logits_ctc, targets, blank=logits_ctc.size(-1) - 1)
+    if isinstance(logits_ctc, ProjectedLogits):      # projection fused with the loss (SURVEY.md 8(f1)): the logits never reach HBM twice
+        ctc = _ctc_fc_loss(logits_ctc.hidden, logits_ctc.weight, len_logits_ctc, targets, blank=logits_ctc.size(-1) - 1)
+    else:
+        ctc = _ctc_loss(logits_ctc, len_logits_ctc, targets, blank=logits_ctc.size(-1) - 1)
     ce = cal_ce_loss(logits_ce, targets, smoothing)
     return ctc, ce
 

@@ -10,24 +10,32 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-# fp32 Linear layers of the model shell on the tensor cores (ops.linear_f32: three TF32 products per tile, ~5e-6
-# relative error; torch's own fp32 path is cuBLAS's SIMT sgemm, ~45 % of the GPU time of the training step on B200).
-# Opt-in: at the reference recipe's per-step shapes (64 utterances x 21 frames = 1344 rows) the kernels take 6.2 ms
-# instead of cuBLAS's 9.3 ms per step, but the step is host-bound there and the Python autograd wrapper (three calls
-# and three transposes per layer) costs more than that: 24.7 vs 22.3 ms per step, measured.  From ~10 k rows on the
-# kernel is 3-4x cuBLAS's sgemm and the wrapper is noise.
-USE_TENSOR_CORE_FP32 = False
+# Linear layers of the model shell on this package's tensor-core GEMMs (csrc/gemm2.cu), forward AND backward, operands as
+# torch stores them (no transposed copies):
+#   fp32 (the reference's precision): three TF32 products per K step, ~5e-6 relative error; torch's own fp32 path is
+#        cuBLAS's SIMT sgemm, ~45 % of the GPU time of the training step on B200.
+#   bf16 under torch.autocast(bf16) (BASELINE config 3): bias / ReLU in the epilogue, fp32 weight gradients.
+# Both switches can be turned off to fall back to torch's F.linear (cuBLAS), e.g. for A/B measurements.
+USE_TENSOR_CORE_FP32 = True
+USE_TENSOR_CORE_BF16 = True
 
 
 class Linear(nn.Linear):
-    """nn.Linear (same parameters, same state_dict keys) whose fp32 CUDA forward and backward run on ops.linear_f32."""
+    """nn.Linear (same parameters, same state_dict keys) whose CUDA forward and backward run on the GEMMs of this package.
+    `relu=True` fuses max(., 0) (feed-forward block, module.py:50)."""
 
-    def forward(self, x):
-        if (USE_TENSOR_CORE_FP32 and x.is_cuda and x.dtype == torch.float32 and self.weight.dtype == torch.float32
-                and self.in_features % 4 == 0 and x.numel() > 0):
-            from ..ops import linear_f32_autograd
-            return linear_f32_autograd(x, self.weight, self.bias)
-        return F.linear(x, self.weight, self.bias)
+    def forward(self, x, relu=False):
+        if x.is_cuda and x.numel() > 0 and self.weight.dtype == torch.float32:
+            from .. import ops
+            if torch.is_autocast_enabled("cuda"):
+                if (USE_TENSOR_CORE_BF16 and torch.get_autocast_dtype("cuda") == torch.bfloat16
+                        and ops.linear_bf16_ok(x, self.weight)):
+                    return ops.linear_bf16_autograd(x, self.weight, self.bias, relu=relu)
+            elif USE_TENSOR_CORE_FP32 and x.dtype == torch.float32 and ops.linear_f32_ok(x, self.weight):
+                y = ops.linear_f32_autograd(x, self.weight, self.bias)
+                return F.relu(y) if relu else y
+        y = F.linear(x, self.weight, self.bias)
+        return F.relu(y) if relu else y
 
 
 class PositionalEncoding(nn.Module):
@@ -63,7 +71,7 @@ class PositionwiseFeedForward(nn.Module):
             h = linear_act(x, self.w_1.weight, self.w_1.bias, relu=True)
             return linear_residual_layernorm(h, self.w_2.weight, self.w_2.bias, x, self.layer_norm.weight,
                                              self.layer_norm.bias, self.layer_norm.eps)
-        return self.layer_norm(self.dropout(self.w_2(F.relu(self.w_1(x)))) + x)
+        return self.layer_norm(self.dropout(self.w_2(self.w_1(x, relu=True))) + x)
 
 
 def fused_linear_ok(module, x, *linears):

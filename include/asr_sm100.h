@@ -215,6 +215,32 @@ int asr_linear_residual_layernorm_bf16(const void* x, const void* w, const float
 int asr_linear_f32(const float* x, const float* w, const float* bias, int M, int N, int K, float* y,
                    void* stream);
 
+/*
+ * General GEMMs for the TRAINING half of the linear layers and for the vocabulary projection
+ * fused with the CTC loss (8(f1)):  C[M,N] = A B (+ bias[N]),  either operand K-major or MN-major, so that all
+ * three products of y = x W^T run on the tensors as torch stores them, without transposed copies
+ * (what autograd computes for /root/reference/src/transformer/module.py:46-53, attention.py:40-45,59-60,
+ * cif_model.py:38):
+ *     forward  y  = x  W^T :  A = x  (a_mn_major 0, [M,K], lda)   B = W  (b_mn_major 0, [N,K], ldb)
+ *     dX       gx = gy W   :  A = gy (a_mn_major 0, [M,N])        B = W  (b_mn_major 1: stored [K_contract = N, N_out = K])
+ *     dW       gW = gy^T x :  A = gy (a_mn_major 1: stored [K_contract = rows, M_out = N])   B = x (b_mn_major 1)
+ * a_mn_major = 0: a is [M,K] with row stride lda;  1: a is [K,M] with row stride lda (same for b with N).
+ * Row strides in elements, multiples of 16 bytes; sizes themselves are free (TMA zero-fills the edges, e.g. the
+ * 4233-wide vocabulary inside rows padded to 4240).  c [M,N] with row stride ldc.
+ * asr_gemm_f32 : fp32 in / out on the tensor cores at fp32-level accuracy (three TF32 products per K step).
+ * asr_gemm_bf16: bf16 operands, fp32 accumulation, bf16 output (out_f32 = 0; relu = 1 fuses max(.,0)) or fp32 output
+ *                (out_f32 = 1: weight gradients for fp32 master weights).
+ * ws / ws_bytes: optional workspace of asr_gemm_workspace_bytes(M, N, K) bytes; with it, products with few output
+ * tiles and a long contraction (dW) are split along K and reduced in a fixed order (deterministic).
+ */
+size_t asr_gemm_workspace_bytes(int M, int N, int K);
+int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
+                 const float* bias, int M, int N, int K, float* c, int ldc,
+                 void* ws, size_t ws_bytes, void* stream);
+int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void* b, int b_mn_major, int ldb,
+                  const float* bias, int relu, int M, int N, int K, void* c, int ldc, int out_f32,
+                  void* ws, size_t ws_bytes, void* stream);
+
 /* ---- CTC loss (fused log-softmax, alpha-beta, gradient) ------------------ */
 /*
  * Replaces log_softmax + torch.nn.functional.ctc_loss as called at
@@ -242,6 +268,15 @@ int asr_ctc_fwd_bwd_f32(const float* logits, const int64_t* targets,
                         int B, int T, int V, int S, int blank,
                         float* nll, float* g_logits,
                         void* ws, size_t ws_bytes, void* stream);
+/* The same call on logits / gradient rows with a row stride ld >= V (in floats; ld % 4 == 0 gives 16-byte-aligned
+ * rows).  g_logits may alias logits: every row is read completely before its gradient is written, so the gradient
+ * can replace the logits in place - the form the fused vocabulary projection uses (asr_gemm_f32 writes the logits
+ * into rows padded to a multiple of 4, the CTC kernels turn them into the gradient, two more GEMMs consume it). */
+int asr_ctc_fwd_bwd_ld_f32(const float* logits, const int64_t* targets,
+                           const int* in_len, const int* tgt_len,
+                           int B, int T, int V, int ld, int S, int blank,
+                           float* nll, float* g_logits,
+                           void* ws, size_t ws_bytes, void* stream);
 /* The same call in two phases.  begin queues the row kernels on `stream` and the
  * lattices on library-owned streams and returns a ticket; finish (same arguments,
  * same stream, the ticket) waits for the lattices and applies the sparse gradient

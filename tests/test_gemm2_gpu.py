@@ -1,0 +1,222 @@
+"""The general tcgen05 GEMMs (csrc/gemm2.cu: K-major / MN-major operands, fp32 "3xTF32" and bf16, split-K), the
+training-mode linear layers built on them (forward, dX and dW of module.py:46-53 /
+attention.py:40-45,59-60 without transposed copies) and the vocabulary projection fused with the CTC loss (8(f1):
+cif_model.py:38 + loss.py:39-43) - against torch in fp64 / fp32 on the same device."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import pkg, make_ctc_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).cuda().to(dtype)
+
+
+def _operands(M, N, K, a_mn, b_mn, seed, dtype=torch.float32):
+    a = _rand((K, M) if a_mn else (M, K), seed, dtype=dtype)
+    b = _rand((K, N) if b_mn else (N, K), seed + 1, dtype=dtype)
+    A = (a.t() if a_mn else a).double()
+    B = (b if b_mn else b.t()).double()
+    return a, b, A @ B
+
+
+LAYOUTS = [(False, False), (False, True), (True, False), (True, True)]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (1344, 512, 512), (300, 2048, 512), (257, 132, 100), (1344, 512, 2048), (64, 4236, 512)])
+def test_gemm_f32_layouts_match_fp64(M, N, K, a_mn, b_mn):
+    """fp32-level accuracy (three TF32 products): 2e-5 of the result scale at K <= 2048; cuBLAS-with-TF32 would be 1e-3."""
+    ops = pkg("ops")
+    if (a_mn and M % 4) or (b_mn and N % 4) or (not (a_mn and b_mn) and K % 4):
+        pytest.skip("row stride not a multiple of 16 bytes for this layout")
+    a, b, ref = _operands(M, N, K, a_mn, b_mn, seed=M + N + K)
+    for split in (False, True):
+        got = ops.gemm_f32(a, b, a_mn_major=a_mn, b_mn_major=b_mn, split_k=split)
+        err = (got.double() - ref).abs().max().item() / ref.abs().max().item()
+        assert err <= 2e-5, (err, split)
+
+
+def test_gemm_f32_forced_split_k_and_bias_and_padded_output():
+    ops, lib = pkg("ops"), pkg("_lib")
+    M, N, K = 200, 4233, 512          # the vocabulary projection: odd N inside rows padded to a multiple of 4
+    a, b, ref = _operands(M, N, K, False, False, seed=3)
+    bias = _rand((N,), 9)
+    out = torch.full((M, 4236), float("nan"), device="cuda")
+    ops.gemm_f32(a, b, bias=bias, out=out, split_k=False)
+    ref_b = ref + bias.double()
+    assert (out[:, :N].double() - ref_b).abs().max().item() <= 2e-5 * ref_b.abs().max().item()
+    assert torch.isfinite(out[:, N:]).all()              # zeros (+ nothing) in the padding, never NaN garbage
+    try:
+        lib.set_option("gemm_split_k", 4)
+        got = ops.gemm_f32(a, b, bias=bias)
+    finally:
+        lib.set_option("gemm_split_k", 0)
+    assert (got.double() - ref_b).abs().max().item() <= 2e-5 * ref_b.abs().max().item()
+    # long contraction, few output tiles: dW = g^T h with the gradient rows padded (a strided view), split along K
+    rows, V, H = 5000, 4233, 512
+    g = torch.zeros(rows, 4236, device="cuda")
+    g[:, :V] = _rand((rows, V), 4, 1e-3)
+    h = _rand((rows, H), 5)
+    got = ops.gemm_f32(g[:, :V], h, a_mn_major=True, b_mn_major=True)
+    ref = g[:, :V].double().t() @ h.double()
+    assert got.shape == (V, H)
+    assert (got.double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+    got = ops.gemm_f32(g[:, :V], _rand((V, H), 6), b_mn_major=True, split_k=False)      # d h = g W, K = 4233 with a zero-filled tail
+    assert got.shape == (rows, H)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (1350, 512, 512), (15030, 2048, 512), (264, 136, 200), (512, 512, 15030)])
+def test_gemm_bf16_layouts(M, N, K, a_mn, b_mn):
+    ops = pkg("ops")
+    if (a_mn and M % 8) or (b_mn and N % 8) or (not (a_mn and b_mn) and K % 8):
+        pytest.skip("row stride not a multiple of 16 bytes for this layout")
+    a, b, ref = _operands(M, N, K, a_mn, b_mn, seed=M + N + K, dtype=torch.bfloat16)
+    scale = ref.abs().max().item()
+    got = ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32)
+    assert (got.double() - ref).abs().max().item() <= 5e-4 * scale      # exact bf16 products, fp32 accumulation (K up to 15030)
+    bias = _rand((N,), 7)
+    got16 = ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, bias=bias, relu=True)
+    ref16 = torch.relu(ref + bias.double())
+    assert got16.dtype == torch.bfloat16
+    assert (got16.double() - ref16).abs().max().item() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("rows,K,N,bias", [(1344, 512, 2048, True), (1344, 2048, 512, True), (896, 1024, 512, False), (300, 512, 4, True)])
+def test_linear_f32_autograd_matches_torch(rows, K, N, bias):
+    ops = pkg("ops")
+    x = _rand((4, rows // 4, K), 1).requires_grad_(True)
+    w = _rand((N, K), 2, K ** -0.5).requires_grad_(True)
+    b = _rand((N,), 3).requires_grad_(True) if bias else None
+    gy = _rand((4, rows // 4, N), 4)
+    y = ops.linear_f32_autograd(x, w, b)
+    y.backward(gy)
+    xd, wd = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    bd = b.detach().double().requires_grad_(True) if bias else None
+    yd = F.linear(xd, wd, bd)
+    yd.backward(gy.double())
+    rel = lambda got, want: (got.double() - want).abs().max().item() / want.abs().max().item()  # noqa: E731
+    assert rel(y, yd) <= 2e-5 and rel(x.grad, xd.grad) <= 2e-5 and rel(w.grad, wd.grad) <= 2e-5
+    if bias:
+        assert rel(b.grad, bd.grad) <= 1e-5
+
+
+def test_model_linear_layers_train_through_the_repo_gemms(monkeypatch):
+    """PositionwiseFeedForward and the attention projections in training mode: forward and all parameter gradients
+    through csrc/gemm2.cu (fp32, and bf16 under autocast) against torch's own F.linear path (the switches off)."""
+    mod = pkg("transformer.module")
+    lib = pkg("_lib")
+    torch.manual_seed(0)
+    ffn = mod.PositionwiseFeedForward(512, 2048, dropout=0.0).cuda().train()
+    x = _rand((8, 168, 512), 5)
+    gy = _rand((8, 168, 512), 6)
+
+    def run(autocast):
+        ffn.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            y = ffn(xi)
+        y.float().backward(gy)
+        return y.float().detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in ffn.named_parameters()}
+    for autocast, tol in ((False, 3e-5), (True, 3e-2)):
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", False)
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", False)
+        n0 = lib.launch_count()
+        ref = run(autocast)
+        assert lib.launch_count() == n0                       # torch only
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", True)
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", True)
+        n0 = lib.launch_count()
+        got = run(autocast)
+        assert lib.launch_count() - n0 >= 6                   # 2 layers x (forward, dX, dW)
+        rel = lambda a, b: (a.double() - b.double()).abs().max().item() / (b.double().abs().max().item() + 1e-12)  # noqa: E731
+        assert rel(got[0], ref[0]) <= tol and rel(got[1], ref[1]) <= tol
+        for k in ref[2]:
+            assert got[2][k].dtype == torch.float32
+            assert rel(got[2][k], ref[2][k]) <= tol, (k, autocast)
+
+
+def test_ctc_strided_rows_in_place_is_bit_identical():
+    """asr_ctc_fwd_bwd_ld_f32 on rows padded to a multiple of 4 floats, gradient written over the logits, against the
+    contiguous out-of-place call."""
+    lib, ops = pkg("_lib"), pkg("ops")
+    L = lib.lib()
+    B, T, V, S = 5, 60, 4233, 7
+    logits, targets, in_len = make_ctc_inputs(B, T, V, S, seed=23)
+    x = logits.clone().requires_grad_(True)
+    loss, nll_ref = ops.ctc_loss(x, in_len, targets, return_nll=True)
+    loss.backward()
+    ld = 4236
+    buf = torch.full((B * T, ld), 7.0, device="cuda")
+    buf[:, :V] = logits.reshape(B * T, V)
+    tgt_len = targets.ne(0).sum(1).to(torch.int32)
+    nll = torch.empty(B, device="cuda")
+    wsb = L.asr_ctc_workspace_bytes(B, T, V, S)
+    ws = torch.empty(wsb // 4 + 1, device="cuda")
+    lib.check(L.asr_ctc_fwd_bwd_ld_f32(lib.ptr(buf), lib.ptr(targets), lib.ptr(in_len), lib.ptr(tgt_len), B, T, V, ld, S, V - 1,
+                                       lib.ptr(nll), lib.ptr(buf), lib.ptr(ws), wsb, lib.stream_ptr()), "ld")
+    assert torch.equal(nll, nll_ref)
+    assert torch.equal(buf[:, :V].reshape(B, T, V), x.grad)
+    assert (buf[:, V:] == 7.0).all()                          # the padding columns are never touched
+
+
+@pytest.mark.parametrize("B,T,S,V,K", [(4, 50, 6, 300, 64), (6, 167, 14, 4233, 512), (32, 200, 10, 4233, 512)])
+def test_ctc_fc_loss_matches_projection_plus_ctc(B, T, S, V, K):
+    """8(f1): loss, d hidden and d weight of ctc(h W^T) against F.linear + F.log_softmax + F.ctc_loss in fp64 on the device,
+    and against torch's own fp32 path (the bar: 1e-5 of the scale, or twice torch-fp32's own error)."""
+    ops = pkg("ops")
+    _, targets, in_len = make_ctc_inputs(B, T, V, S, seed=31)
+    h = _rand((B, T, K), 1)
+    w = _rand((V, K), 2, K ** -0.5)
+    tgt_len = targets.ne(0).sum(1)
+
+    def torch_path(dtype):
+        hh, ww = h.detach().to(dtype).requires_grad_(True), w.detach().to(dtype).requires_grad_(True)
+        lp = F.log_softmax(F.linear(hh, ww), dim=-1).transpose(0, 1)
+        loss = F.ctc_loss(lp, targets, in_len.long(), tgt_len, blank=V - 1)
+        loss.backward()
+        return loss.detach(), hh.grad, ww.grad
+    l64, gh64, gw64 = torch_path(torch.float64)
+    l32, gh32, gw32 = torch_path(torch.float32)
+    hh, ww = h.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    loss, nll = ops.ctc_fc_loss(hh, ww, in_len, targets, return_nll=True)
+    (2.0 * loss).backward()                                   # incoming gradient scale is applied on the device
+    rel = lambda a, b: (a.double() - b).abs().max().item() / b.abs().max().item()  # noqa: E731
+    assert abs(float(loss) - float(l64)) <= max(1e-5, 2 * abs(float(l32) - float(l64)) / abs(float(l64))) * abs(float(l64))
+    assert rel(hh.grad / 2, gh64) <= max(2e-5, 2 * rel(gh32, gh64)), (rel(hh.grad / 2, gh64), rel(gh32, gh64))
+    assert rel(ww.grad / 2, gw64) <= max(2e-5, 2 * rel(gw32, gw64)), (rel(ww.grad / 2, gw64), rel(gw32, gw64))
+    # and the un-fused route of this package (projection by torch, ops.ctc_loss) agrees on the loss
+    plain = ops.ctc_loss(F.linear(h, w), in_len, targets)
+    assert abs(float(plain) - float(loss)) <= 2e-5 * abs(float(plain))
+
+
+def test_cif_model_with_fused_ctc_fc_matches_the_plain_route():
+    from test_model_shell import _build, _golden_state, G
+    tl = pkg("transformer.loss")
+    res = []
+    for fused in (False, True):
+        model = _build()
+        model.load_state_dict(_golden_state(), strict=False)
+        model = model.cuda().train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+            if hasattr(m, "attn_dropout_p"):
+                m.attn_dropout_p = 0.0
+        model.fused_ctc_fc = fused
+        feats, lens, targets = (torch.as_tensor(G[k]).cuda() for k in ("feats", "lens", "targets"))
+        torch.manual_seed(int(G["rand_seed"]))
+        out = model(feats, lens, targets)
+        assert isinstance(out[0], pkg("ops").ProjectedLogits) == fused
+        qua, ctc, ce = tl.cal_ctc_qua_ce_loss(out[0], out[1], out[2], out[3], out[4], targets, smoothing=0.1)
+        (0.001 * qua + ctc + ce).backward()
+        res.append((float(ctc), model.ctc_fc.weight.grad.clone(), model.encoder.linear_in.weight.grad.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 2e-5 * abs(res[0][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
