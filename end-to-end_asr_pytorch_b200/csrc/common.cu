@@ -77,6 +77,15 @@ int make_tmap_nd(CUtensorMap* map, CUtensorMapDataType dtype, size_t elem_bytes,
                  CUtensorMapSwizzle swizzle) {
     EncodeTiledFn fn = encode_fn();
     ASR_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs a context current on the calling thread.  A thread that has only
+    // ever selected a device (torch's autograd worker threads do cudaSetDevice and nothing else before calling into this
+    // library) may not have the primary context bound yet -> CUDA_ERROR_INVALID_CONTEXT (201).  One runtime call per
+    // thread binds it.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t gdim[5];
     cuuint64_t gstr[4];
     cuuint32_t bx[5];

@@ -168,6 +168,9 @@ __global__ void __launch_bounds__(NT) ctc_rows_kernel(const CtcArgs a) {
     }
 
     if (GRAD) {
+        // gradient written over the logits (asr_ctc_fwd_bwd_ld_f32 with g == logits): the gather above reads scattered
+        // elements of the row, which another thread of the CTA must not have overwritten yet
+        if (a.g == a.logits) __syncthreads();
         const float coef = 1.0f / (Ssum * (float)a.Bn * (float)max(Sb, 1));
         float4* gv = reinterpret_cast<float4*>(g + lead);
 #pragma unroll

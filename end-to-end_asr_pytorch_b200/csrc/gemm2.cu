@@ -18,7 +18,9 @@
 // Tiles: CTA = 128 x BN output tile (BN = 128 or 256), K step = 128 bytes (32 fp32 / 64 bf16).  A K-major tile is one TMA
 // box [rows x 128 bytes]; an MN-major tile is a row of boxes [K step rows x 128 bytes], one per 128-byte chunk of the
 // M / N extent - exactly the canonical 128-byte-swizzled MN-major layout of the tcgen05 shared-memory descriptor
-// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = one box, SBO = 1024 bytes.  Out-of-range rows / columns are
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units: LBO = one box, SBO = 1024 bytes (bf16); MN-major tf32 operands exist only
+// in the 32-byte-atom flavour of that swizzle (TMA SWIZZLE_128B_ATOM_32B, descriptor layout 1, 4-row K groups, SBO = 512),
+// which is what the fp32 kernel uses for them.  Out-of-range rows / columns are
 // zero-filled by TMA, so odd sizes (the 4233-wide vocabulary) need no padding copies, only 16-byte-aligned row strides.
 // Split-K over gridDim.z (dW of a small layer has few output tiles and a long contraction): partial tiles go to a
 // workspace and a second kernel adds them in a fixed order (deterministic, no atomics).
@@ -63,8 +65,11 @@ struct G2Tile {
         }
     }
     __device__ static __forceinline__ uint64_t desc(uint32_t tile_addr, int kk) {
-        return MN ? smem_desc_sw128(tile_addr + kk * kUmmaK * kG2RowBytes, kBoxBytes, 1024)
-                  : smem_desc_sw128(tile_addr + kk * 32, 16, 1024);
+        if (!MN) return smem_desc_sw128(tile_addr + kk * 32, 16, 1024);
+        // MN-major: 16-bit operands use the plain 128-byte swizzle (atoms of 8 K rows, SBO = 1024); 32-bit (tf32) operands
+        // must use the 32-byte-atom flavour (atoms of 4 K rows, SBO = 512) - the tile was loaded with the matching TMA swizzle
+        if (ELEM == 4) return smem_desc_sw128_base32(tile_addr + kk * kUmmaK * kG2RowBytes, kBoxBytes, 512);
+        return smem_desc_sw128(tile_addr + kk * kUmmaK * kG2RowBytes, kBoxBytes, 1024);
     }
 };
 
@@ -115,8 +120,11 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         mbar_init(&bars->acc_full, 1);
         fence_mbar_init();
     }
+    // Two accumulators [128 x BN]: the head products hi_a hi_b go to the first, the two correction products to the second.
+    // The tensor core's fp32 accumulation loses up to an ulp OF THE ACCUMULATOR per addition; kept apart, the main sum
+    // takes one addition per K step instead of three and the corrections (2^-11 of the magnitude) round among themselves.
     if (warp == 5) {
-        tmem_alloc(&bars->tmem_base, BN);
+        tmem_alloc(&bars->tmem_base, 2 * BN);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -148,9 +156,10 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 const uint32_t a_hi = base, a_lo = base + Cfg::kATile, b_hi = base + 2 * Cfg::kATile, b_lo = b_hi + Cfg::kBTile;
 #pragma unroll
                 for (int kk = 0; kk < TA::kBK / TA::kUmmaK; ++kk) {
-                    umma_tf32(tmem, TA::desc(a_lo, kk), TB::desc(b_hi, kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
-                    umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_lo, kk), idesc, 1u);
-                    umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_hi, kk), idesc, 1u);
+                    const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                    umma_tf32(tmem + BN, TA::desc(a_lo, kk), TB::desc(b_hi, kk), idesc, acc);
+                    umma_tf32(tmem + BN, TA::desc(a_hi, kk), TB::desc(b_lo, kk), idesc, 1u);
+                    umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_hi, kk), idesc, acc);
                 }
                 tc_commit(&bars->empty[s]);
             }
@@ -185,7 +194,11 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             if (n0 + cc >= n_store) break;
             float v[32];
             if (nk > 0) {
+                float corr[32];
                 tmem_ld32(tmem + lane_base + cc, v);
+                tmem_ld32(tmem + BN + lane_base + cc, corr);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += corr[i];
             } else {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
@@ -218,7 +231,7 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem, BN);
+        tmem_dealloc(tmem, 2 * BN);
     }
 }
 
@@ -436,7 +449,7 @@ int make_operand_map(CUtensorMap* map, CUtensorMapDataType dt, int elem, const v
         return make_tmap_2d(map, dt, elem, base, (uint64_t)mn, (uint64_t)k, (uint64_t)ld * elem, (uint32_t)std::min(tile_rows, 256),
                             (uint32_t)chunk, CU_TENSOR_MAP_SWIZZLE_128B);
     return make_tmap_2d(map, dt, elem, base, (uint64_t)k, (uint64_t)mn, (uint64_t)ld * elem, (uint32_t)chunk, (uint32_t)chunk,
-                        CU_TENSOR_MAP_SWIZZLE_128B);
+                        elem == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 template <typename KernelT>

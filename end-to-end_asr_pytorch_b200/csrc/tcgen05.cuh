@@ -194,6 +194,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t
     d |= (uint64_t)2 << 61;
     return d;
 }
+// The same descriptor with LayoutType 1 = SWIZZLE_128B_BASE32B (32-byte chunks swizzled within a 128-byte span, Swizzle<2,5,2>;
+// TMA: CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  It is the ONLY shared-memory layout the tensor core accepts for MN-major
+// 32-bit (tf32) operands: atoms of 128 bytes along M/N x 4 rows along K, SBO = distance between 4-row groups.
+__device__ __forceinline__ uint64_t smem_desc_sw128_base32(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)1 << 61;
+    return d;
+}
 // All-ones B operand: no swizzle, zero leading / stride offsets, so every 8x16-byte core matrix of the
 // [N x K] operand aliases the same 128 bytes of bf16 1.0.  P x ones gives the row sums of the bf16
 // probabilities exactly as the tensor core sees them (fp32 accumulate) without any CUDA-core adds.

@@ -288,7 +288,11 @@ class _LinearF32Function(torch.autograd.Function):
         x2, w = ctx.saved_tensors
         N, K = w.shape
         gy2 = gy.reshape(-1, N)
-        if gy2.stride(1) != 1 or gy2.stride(0) % 4 != 0 or gy2.data_ptr() % 16 != 0:
+        if N % 4 != 0:      # odd widths (a 4233-class vocabulary): rows padded to 16 bytes, the operand is the [:, :N] view
+            buf = gy2.new_empty((gy2.shape[0], (N + 3) // 4 * 4))
+            buf[:, :N] = gy2
+            gy2 = buf[:, :N]
+        elif gy2.stride(1) != 1 or gy2.stride(0) % 4 != 0 or gy2.data_ptr() % 16 != 0:
             gy2 = gy2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
@@ -301,7 +305,8 @@ class _LinearF32Function(torch.autograd.Function):
 
 
 def linear_f32_ok(x, weight):
-    """Shapes the fp32 tensor-core linear layer takes: 16-byte rows for every operand of its three products."""
+    """Shapes the fp32 tensor-core linear layer takes without a padding copy: 16-byte rows for every operand of its
+    three products (linear_f32_autograd itself also accepts an odd output width and pads the incoming gradient)."""
     return weight.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and x.numel() > 0
 
 

@@ -108,8 +108,10 @@ def test_linear_f32_autograd_matches_torch(rows, K, N, bias):
 
 
 def test_model_linear_layers_train_through_the_repo_gemms(monkeypatch):
-    """PositionwiseFeedForward and the attention projections in training mode: forward and all parameter gradients
-    through csrc/gemm2.cu (fp32, and bf16 under autocast) against torch's own F.linear path (the switches off)."""
+    """PositionwiseFeedForward in training mode: forward and all parameter gradients through csrc/gemm2.cu - fp32, and bf16
+    under autocast - against torch's own F.linear path (the switches off).  The bf16 route is held to the error torch's
+    own bf16 route makes against the fp32 result: two bf16 implementations differ wherever a pre-activation rounds to
+    the other side of zero (the ReLU mask of that element flips), so they are compared with the truth, not each other."""
     mod = pkg("transformer.module")
     lib = pkg("_lib")
     torch.manual_seed(0)
@@ -117,34 +119,37 @@ def test_model_linear_layers_train_through_the_repo_gemms(monkeypatch):
     x = _rand((8, 168, 512), 5)
     gy = _rand((8, 168, 512), 6)
 
-    def run(autocast):
+    def run(autocast, ours):
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", ours)
+        monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", ours)
         ffn.zero_grad()
         xi = x.clone().requires_grad_(True)
+        n0 = lib.launch_count()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             y = ffn(xi)
         y.float().backward(gy)
-        return y.float().detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in ffn.named_parameters()}
-    for autocast, tol in ((False, 3e-5), (True, 3e-2)):
-        monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", False)
-        monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", False)
-        n0 = lib.launch_count()
-        ref = run(autocast)
-        assert lib.launch_count() == n0                       # torch only
-        monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", True)
-        monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", True)
-        n0 = lib.launch_count()
-        got = run(autocast)
-        assert lib.launch_count() - n0 >= 6                   # 2 layers x (forward, dX, dW)
-        rel = lambda a, b: (a.double() - b.double()).abs().max().item() / (b.double().abs().max().item() + 1e-12)  # noqa: E731
-        assert rel(got[0], ref[0]) <= tol and rel(got[1], ref[1]) <= tol
-        for k in ref[2]:
-            assert got[2][k].dtype == torch.float32
-            assert rel(got[2][k], ref[2][k]) <= tol, (k, autocast)
+        used = lib.launch_count() - n0
+        assert (used >= 6) if ours else (used == 0)           # 2 layers x (forward, dX, dW) - or torch only
+        out = {"y": y.float().detach(), "x.grad": xi.grad.clone()}
+        out.update({k: p.grad.clone() for k, p in ffn.named_parameters()})
+        assert all(v.dtype == torch.float32 for v in out.values())
+        return out
+    rel = lambda a, b: (a.double() - b.double()).abs().max().item() / (b.double().abs().max().item() + 1e-12)  # noqa: E731
+    truth = run(False, False)                                  # torch fp32 (cuBLAS sgemm)
+    ours32 = run(False, True)
+    for k in truth:
+        assert rel(ours32[k], truth[k]) <= 3e-5, (k, rel(ours32[k], truth[k]))
+    torch16, ours16 = run(True, False), run(True, True)
+    for k in truth:
+        e_ours, e_torch = rel(ours16[k], truth[k]), rel(torch16[k], truth[k])
+        assert e_ours <= max(2e-2, 1.5 * e_torch), (k, e_ours, e_torch)
 
 
-def test_ctc_strided_rows_in_place_is_bit_identical():
+def test_ctc_strided_rows_in_place_matches_the_contiguous_call():
     """asr_ctc_fwd_bwd_ld_f32 on rows padded to a multiple of 4 floats, gradient written over the logits, against the
-    contiguous out-of-place call."""
+    contiguous out-of-place call.  Not bit-identical by construction: with V odd the contiguous rows start at four
+    different 16-byte phases, so the element-to-thread assignment of the row sums differs from the aligned padded rows
+    (last-bit differences of the log-sum-exp)."""
     lib, ops = pkg("_lib"), pkg("ops")
     L = lib.lib()
     B, T, V, S = 5, 60, 4233, 7
@@ -161,9 +166,18 @@ def test_ctc_strided_rows_in_place_is_bit_identical():
     ws = torch.empty(wsb // 4 + 1, device="cuda")
     lib.check(L.asr_ctc_fwd_bwd_ld_f32(lib.ptr(buf), lib.ptr(targets), lib.ptr(in_len), lib.ptr(tgt_len), B, T, V, ld, S, V - 1,
                                        lib.ptr(nll), lib.ptr(buf), lib.ptr(ws), wsb, lib.stream_ptr()), "ld")
-    assert torch.equal(nll, nll_ref)
-    assert torch.equal(buf[:, :V].reshape(B, T, V), x.grad)
+    torch.testing.assert_close(nll, nll_ref, rtol=2e-6, atol=0)
+    got = buf[:, :V].reshape(B, T, V)
+    assert (got - x.grad).abs().max().item() <= 2e-6 * x.grad.abs().max().item()
     assert (buf[:, V:] == 7.0).all()                          # the padding columns are never touched
+    # and the aligned layout out of place (separate gradient buffer) is bit-identical to the in-place run
+    buf2 = torch.full((B * T, ld), 7.0, device="cuda")
+    buf2[:, :V] = logits.reshape(B * T, V)
+    g2 = torch.zeros(B * T, ld, device="cuda")
+    nll2 = torch.empty(B, device="cuda")
+    lib.check(L.asr_ctc_fwd_bwd_ld_f32(lib.ptr(buf2), lib.ptr(targets), lib.ptr(in_len), lib.ptr(tgt_len), B, T, V, ld, S, V - 1,
+                                       lib.ptr(nll2), lib.ptr(g2), lib.ptr(ws), wsb, lib.stream_ptr()), "ld")
+    assert torch.equal(nll2, nll) and torch.equal(g2[:, :V], buf[:, :V])
 
 
 @pytest.mark.parametrize("B,T,S,V,K", [(4, 50, 6, 300, 64), (6, 167, 14, 4233, 512), (32, 200, 10, 4233, 512)])

@@ -144,21 +144,19 @@ def test_linear_f32_autograd(shape, N, K, bias):
         assert (got.double() - ref.detach()).abs().max().item() <= 2e-5 * scale, (got.shape,)
 
 
-def test_shell_linear_can_run_on_the_tensor_core_kernel():
+def test_shell_linear_runs_on_the_tensor_core_kernel_and_can_be_switched_off(monkeypatch):
     module = pkg("transformer.module")
     lib = pkg("_lib")
     torch.manual_seed(2)
     lin = module.Linear(512, 2048).cuda()
     x = torch.randn(6, 21, 512, device="cuda")
+    monkeypatch.setattr(module, "USE_TENSOR_CORE_FP32", False)
     n0 = lib.launch_count()
-    y_ref = lin(x)                                   # default: torch's F.linear
+    y_ref = lin(x)                                   # torch's F.linear (cuBLAS SIMT sgemm)
     assert lib.launch_count() == n0
-    module.USE_TENSOR_CORE_FP32 = True
-    try:
-        n0 = lib.launch_count()
-        y = lin(x)
-        assert lib.launch_count() - n0 == 1
-    finally:
-        module.USE_TENSOR_CORE_FP32 = False
+    monkeypatch.setattr(module, "USE_TENSOR_CORE_FP32", True)
+    n0 = lib.launch_count()
+    y = lin(x)                                       # the default: csrc/gemm2.cu
+    assert lib.launch_count() - n0 == 1
     assert (y - y_ref).abs().max().item() <= 2e-5 * y_ref.abs().max().item()
     assert sorted(lin.state_dict().keys()) == ["bias", "weight"]

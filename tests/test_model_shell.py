@@ -80,12 +80,16 @@ def _run(model):
 
 
 @pytest.mark.gpu
-def test_full_forward_backward_matches_reference_with_fp32_attention(monkeypatch):
+@pytest.mark.parametrize("tc_fp32", [False, True], ids=["torch_sgemm", "tensor_core_3xtf32"])
+def test_full_forward_backward_matches_reference_with_fp32_attention(monkeypatch, tc_fp32):
     att = pkg("transformer.attention")
     monkeypatch.setattr(att, "mha_core", _torch_fp32_core)
     # the caller-side convolutions / GEMMs must run in true fp32 for a 1e-3 comparison (cuDNN uses TF32 by default)
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    # the shell's Linear layers: torch's SIMT sgemm (7e-7 per product) or this package's 3xTF32 tensor-core GEMMs (~3e-6);
+    # the network amplifies either (softmax / LayerNorm backward are differences of near-equal numbers)
+    monkeypatch.setattr(pkg("transformer.module"), "USE_TENSOR_CORE_FP32", tc_fp32)
     model = _build()
     model.load_state_dict(_golden_state(), strict=False)
     model = model.cuda().eval()
@@ -103,7 +107,7 @@ def test_full_forward_backward_matches_reference_with_fp32_attention(monkeypatch
     for k in [k for k in G.files if k.startswith("grad:")]:
         ref = G[k]
         got = to_np(params[k[5:]].grad)
-        assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, k
+        assert np.abs(got - ref).max() <= (6e-3 if tc_fp32 else 2e-3) * np.abs(ref).max() + 1e-7, k
 
 
 @pytest.mark.gpu

@@ -107,10 +107,14 @@ def _check_grads(model, prefix, tol):
 
 
 @pytest.mark.gpu
-def test_transformer_matches_reference_with_fp32_attention(monkeypatch):
+@pytest.mark.parametrize("tc_fp32", [False, True], ids=["torch_sgemm", "tensor_core_3xtf32"])
+def test_transformer_matches_reference_with_fp32_attention(monkeypatch, tc_fp32):
     monkeypatch.setattr(pkg("transformer.attention"), "mha_core", _torch_fp32_core)
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    # the shell's Linear layers: torch's SIMT sgemm (7e-7 per product) or this package's 3xTF32 tensor-core GEMMs (~3e-6);
+    # the network amplifies either (softmax / LayerNorm backward are differences of near-equal numbers)
+    monkeypatch.setattr(pkg("transformer.module"), "USE_TENSOR_CORE_FP32", tc_fp32)
     model = _build_transformer()
     model.load_state_dict(_state("t:"), strict=False)
     model = model.cuda().eval()
@@ -118,14 +122,18 @@ def test_transformer_matches_reference_with_fp32_attention(monkeypatch):
     np.testing.assert_array_equal(to_np(targets_eos), G["t:targets_eos"])
     np.testing.assert_allclose(to_np(logits), G["t:logits"], rtol=1e-3, atol=5e-4)
     np.testing.assert_allclose(float(ce), G["t:ce"], rtol=1e-4)
-    _check_grads(model, "t:", 2e-3)
+    _check_grads(model, "t:", 6e-3 if tc_fp32 else 2e-3)
 
 
 @pytest.mark.gpu
-def test_conv_ctc_transformer_matches_reference_with_fp32_attention(monkeypatch):
+@pytest.mark.parametrize("tc_fp32", [False, True], ids=["torch_sgemm", "tensor_core_3xtf32"])
+def test_conv_ctc_transformer_matches_reference_with_fp32_attention(monkeypatch, tc_fp32):
     monkeypatch.setattr(pkg("transformer.attention"), "mha_core", _torch_fp32_core)
     monkeypatch.setattr(torch.backends.cudnn, "allow_tf32", False)
     monkeypatch.setattr(torch.backends.cuda.matmul, "allow_tf32", False)
+    # the shell's Linear layers: torch's SIMT sgemm (7e-7 per product) or this package's 3xTF32 tensor-core GEMMs (~3e-6);
+    # the network amplifies either (softmax / LayerNorm backward are differences of near-equal numbers)
+    monkeypatch.setattr(pkg("transformer.module"), "USE_TENSOR_CORE_FP32", tc_fp32)
     model = _build_conv_ctc()
     model.load_state_dict(_state("c:"), strict=False)
     model = model.cuda().eval()
@@ -136,7 +144,7 @@ def test_conv_ctc_transformer_matches_reference_with_fp32_attention(monkeypatch)
     np.testing.assert_allclose(to_np(logits), G["c:logits"], rtol=1e-3, atol=5e-4)
     np.testing.assert_allclose(float(ctc), G["c:ctc"], rtol=1e-4)      # the fused sm_100a CTC with <eos>-extended targets
     np.testing.assert_allclose(float(ce), G["c:ce"], rtol=1e-4)
-    _check_grads(model, "c:", 2e-3)
+    _check_grads(model, "c:", 6e-3 if tc_fp32 else 2e-3)
 
 
 @pytest.mark.gpu
