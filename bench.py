@@ -13,7 +13,8 @@ data-parallel gradient exchange of that training step:
     CIF forward on the encoder frames [B,T,H] + quantity term  (a1-a3)
     CIF backward                                               (a2')
     NCCL all-reduce (mean) of the model's fp32 gradient buckets: the 52.3 M parameters of the reference recipe's
-    CIF_Model = 209 MB in 25 MB buckets, launched where the backward half of the step begins and waited for at its end
+    CIF_Model = 209 MB in 25 MB buckets, launched behind the CTC row pass (from where gradients exist) and waited for
+    at the end of the step
 
 Shape = the largest one of BASELINE config 2 (CTC sweep: B=256, T=1600, S=80, V=4233) with the CIF layer of config 4
 run on the same batch (H=512).  Every rank processes its own batch (data parallel by utterance, weak scaling).
@@ -287,8 +288,9 @@ class HotPath:
     def step_overlapped(self, ev=None):
         """One hot-path pass the way the library is meant to be driven: one stream, the CTC call in its two phases with
         the CIF forward/backward pair queued in between, where it runs next to the last slice's latency-bound lattice.
-        The gradient all-reduce of the training step (N > 1) goes out where the backward half begins (after the CIF
-        forward) and is waited for at the end of the step.
+        The gradient all-reduce of the training step (N > 1) goes out behind the CTC row pass - the point of the step
+        from which gradients exist (the row pass writes the dense part of d loss / d logits) - runs on NCCL's stream next
+        to the lattices, the CIF pair and the apply pass, and is waited for at the end of the step.
         ev = (before, after): CUDA events around the row kernels (all slices; they are the only work begin puts on this
         stream), i.e. the dominant kernel timed inside the timed region."""
         args = self._ctc_args() + (self.lib.stream_ptr(),)
@@ -298,9 +300,9 @@ class HotPath:
         self.lib.check(self.L.asr_ctc_begin_f32(*args, ctypes.byref(ticket)), "asr_ctc_begin_f32")
         if ev is not None:
             ev[1].record()
-        self.cif_fwd(self.cif_hint_overlapped)
         if self.buckets is not None:
-            self.buckets.launch()
+            self.buckets.launch()      # behind the row pass on this stream: the dense CTC gradient exists from here on
+        self.cif_fwd(self.cif_hint_overlapped)
         self.cif_bwd()
         self.lib.check(self.L.asr_ctc_finish_f32(*args, ticket.value), "asr_ctc_finish_f32")
         if self.buckets is not None:
@@ -680,6 +682,7 @@ def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=Fals
     reference-faithful fp32 step, never instead."""
     import torch.distributed as dist
     w = dict(WORKLOADS[wname])
+    torch.backends.cudnn.benchmark = True      # the conv front end is cuDNN's (out of scope): let it pick its fastest algorithms
     tf32_before = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
     if tf32:      # the plain run keeps torch's defaults (fp32 matmul; cuDNN may use TF32 for the convolutions, as in the reference's own torch)
         torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
@@ -692,6 +695,7 @@ def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=Fals
     else:
         model = pkg("transformer.cif_model").CIF_Model.create_model(_model_args(w)).to(device).train()
         model.static_shapes = graph
+        model.fused_ctc_fc = True          # ctc_fc projection fused with the CTC loss
     dp.broadcast_parameters(model, 0)
     sync = dp.GradAllReduce(model, bucket_mb=25, overlap=not graph)
     opt = torch.optim.Adam(model.parameters(), lr=2e-4, betas=(0.9, 0.98), eps=1e-9, fused=True)
@@ -1146,7 +1150,7 @@ def main():
             "config": dict(workload=args.workload, **w, L=L_out, valid_frames=valid_frames,
                            grad_allreduce_bytes_per_step=(buckets.bytes if buckets is not None else 0),
                            grad_allreduce=("NCCL all-reduce (mean) of %d fp32 gradient buckets = the %d parameters of the recipe's "
-                                           "CIF_Model, launched after the CIF forward, waited for at the end of every timed step"
+                                           "CIF_Model, launched behind the CTC row pass, waited for at the end of every timed step"
                                            % (len(buckets.flat), n_params)) if buckets is not None else
                                           "none at N = 1 (one rank: nothing to exchange)",
                            parallelism="dp%d by utterance; gradients only over NCCL" % world,

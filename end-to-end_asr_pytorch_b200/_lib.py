@@ -9,7 +9,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libasr_sm100.so")
+# ASR_SM100_LIB: an alternative build of the same library (e.g. the -DASR_MHA_TRACE instrumented one of tools/mha_trace.py)
+LIB_PATH = os.environ.get("ASR_SM100_LIB") or os.path.join(_HERE, "csrc", "libasr_sm100.so")
 
 _c_int = ctypes.c_int
 _c_float = ctypes.c_float
@@ -41,6 +42,7 @@ SIGNATURES = {
     "asr_linear_act_bf16": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_linear_residual_layernorm_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_float, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_linear_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
+    "asr_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "asr_gemm_f32": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
                               _vp, _c_size_t, _vp]),

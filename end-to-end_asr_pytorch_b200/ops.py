@@ -266,6 +266,19 @@ def gemm_bf16(a, b, a_mn_major=False, b_mn_major=False, bias=None, relu=False, o
     return out
 
 
+def colsum(x):
+    """Column sums of a 2-D fp32 / bf16 matrix (last dim contiguous) in fp32 - the bias gradient of a linear layer - in one
+    pass with a fixed summation order (deterministic)."""
+    _require_cuda("x", x)
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("colsum: 2-D fp32 / bf16 matrix with a contiguous last dimension expected")
+    M, N = x.shape
+    out = torch.empty((N,), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(_lib.lib().asr_colsum(ptr(x), int(x.dtype == torch.bfloat16), M, N, x.stride(0), ptr(out), stream_ptr()), "asr_colsum")
+    return out
+
+
 class _LinearF32Function(torch.autograd.Function):
     """y = x W^T + b with all three products (y, dx = gy W, dW = gy^T x) on the fp32 tensor-core GEMM, every operand read
     as torch stores it (K-major or MN-major descriptors): no transposed copies.  Reference: what autograd does for an
@@ -281,7 +294,7 @@ class _LinearF32Function(torch.autograd.Function):
         ctx.save_for_backward(x2, w)
         ctx.x_shape = x.shape
         ctx.has_bias = bias is not None
-        return gemm_f32(x2, w, bias=bias, split_k=False).reshape(*x.shape[:-1], w.shape[0])
+        return gemm_f32(x2, w, bias=bias).reshape(*x.shape[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, gy):
@@ -296,18 +309,20 @@ class _LinearF32Function(torch.autograd.Function):
             gy2 = gy2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_f32(gy2, w, b_mn_major=True, split_k=False).reshape(ctx.x_shape)      # contraction over N
+            gx = gemm_f32(gy2, w, b_mn_major=True).reshape(ctx.x_shape)      # contraction over N
         if ctx.needs_input_grad[1]:
             gw = gemm_f32(gy2, x2, a_mn_major=True, b_mn_major=True)                         # contraction over the rows
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.sum(0)
+            gb = colsum(gy2)
         return gx, gw, gb
 
 
 def linear_f32_ok(x, weight):
-    """Shapes the fp32 tensor-core linear layer takes without a padding copy: 16-byte rows for every operand of its
-    three products (linear_f32_autograd itself also accepts an odd output width and pads the incoming gradient)."""
-    return weight.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0 and x.numel() > 0
+    """Shapes the fp32 tensor-core linear layer takes: 16-byte rows for every operand of its three products; an odd
+    output width (the 4233-wide vocabulary projections) costs one padding copy of the incoming gradient, which is
+    worth it from ~64 columns on (the assigner's 1-wide head stays with torch)."""
+    N, K = weight.shape
+    return K % 4 == 0 and (N % 4 == 0 or N >= 64) and x.numel() > 0
 
 
 def linear_f32_autograd(x, weight, bias=None):
@@ -329,7 +344,7 @@ class _LinearBf16Function(torch.autograd.Function):
         if x2.stride(1) != 1 or x2.stride(0) % 8 != 0 or x2.data_ptr() % 16 != 0:
             x2 = x2.contiguous()
         w16 = weight.detach().to(torch.bfloat16).contiguous()
-        y = gemm_bf16(x2, w16, bias=bias, relu=relu, split_k=False)
+        y = gemm_bf16(x2, w16, bias=bias, relu=relu)
         ctx.save_for_backward(x2, w16, y if relu else None)
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.has_bias, ctx.relu = bias is not None, relu
@@ -349,11 +364,11 @@ class _LinearBf16Function(torch.autograd.Function):
             gy2 = gy2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
-            gx = gemm_bf16(gy2, w16, b_mn_major=True, split_k=False).reshape(ctx.x_shape).to(ctx.x_dtype)
+            gx = gemm_bf16(gy2, w16, b_mn_major=True).reshape(ctx.x_shape).to(ctx.x_dtype)
         if ctx.needs_input_grad[1]:
             gw = gemm_bf16(gy2, x2, a_mn_major=True, b_mn_major=True, out_dtype=torch.float32).to(ctx.w_dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = gy2.float().sum(0)
+            gb = colsum(gy2)
         return gx, gw, gb, None
 
 

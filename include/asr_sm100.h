@@ -234,6 +234,9 @@ int asr_linear_f32(const float* x, const float* w, const float* bias, int M, int
  * tiles and a long contraction (dW) are split along K and reduced in a fixed order (deterministic).
  */
 size_t asr_gemm_workspace_bytes(int M, int N, int K);
+/* out[n] = sum_m x[m, n] in fp32 (x fp32 or bf16 [M,N], row stride ld elements): the bias gradient of a linear layer
+ * (the column sums of gy), one pass, fixed order (deterministic). */
+int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, float* out, void* stream);
 int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
                  const float* bias, int M, int N, int K, float* c, int ldc,
                  void* ws, size_t ws_bytes, void* stream);

@@ -234,3 +234,16 @@ def test_cif_model_with_fused_ctc_fc_matches_the_plain_route():
     assert abs(res[0][0] - res[1][0]) <= 2e-5 * abs(res[0][0])
     for a, b in zip(res[0][1:], res[1][1:]):
         assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,dtype", [(1344, 512, torch.float32), (15030, 2048, torch.bfloat16), (7, 4233, torch.float32), (300, 33, torch.bfloat16)])
+def test_colsum_is_the_bias_gradient(M, N, dtype):
+    ops = pkg("ops")
+    x = _rand((M, N), M + N, dtype=dtype)
+    got = ops.colsum(x)
+    ref = x.double().sum(0)
+    assert got.dtype == torch.float32
+    assert (got.double() - ref).abs().max().item() <= 2e-6 * x.double().abs().sum(0).max().item()
+    assert torch.equal(got, ops.colsum(x))                      # fixed summation order
+    view = _rand((M, N + 8), 3, dtype=dtype)[:, :N]            # strided rows
+    assert (ops.colsum(view).double() - view.double().sum(0)).abs().max().item() <= 2e-6 * view.double().abs().sum(0).max().item()

@@ -1,40 +1,24 @@
 #!/usr/bin/env python3
-"""Attention core timing: python tools/mha_bench.py [B L H]  (forward variants and backward warp-group counts)"""
+"""Attention core forward / backward: TFLOP/s per kernel variant on the microbench shapes + max error vs an fp32 reference.
+    python tools/mha_bench.py [variant ...]      (mha_variant values; default 21 22)"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import asr_b200
-lib = asr_b200._lib; L = lib.lib(); ptr, sp, check = lib.ptr, lib.stream_ptr, lib.check
-shapes = [(16, 2048, 8), (16, 512, 8), (4, 4096, 8)] if len(sys.argv) < 4 else [tuple(int(x) for x in sys.argv[1:4])]
-for B, Ls, H in shapes:
-    g = torch.Generator(device="cuda").manual_seed(5)
+import bench
+lib = bench.pkg("_lib"); L = lib.lib(); p, sp = lib.ptr, lib.stream_ptr
+variants = [int(x) for x in sys.argv[1:]] or [21, 22]
+g = torch.Generator(device="cuda").manual_seed(5)
+for (B, Ls, H) in ((16, 2048, 8), (8, 4096, 8), (64, 512, 8)):
     q, k, v, do = (torch.randn(B, Ls, H, 64, device="cuda", generator=g).to(torch.bfloat16) for _ in range(4))
     out = torch.empty_like(q); lse = torch.empty(B, H, Ls, device="cuda")
-    gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
-    wsb = L.asr_mha_bwd_workspace_bytes(B, H, Ls, Ls, 64); ws = torch.empty(wsb // 4 + 1, device="cuda")
-    def fwd(): check(L.asr_mha_fwd_bf16(ptr(q), ptr(k), ptr(v), None, None, 0, B, H, Ls, Ls, 64, 0.125, ptr(out), ptr(lse), sp()), "fwd")
-    def bwd(): check(L.asr_mha_bwd_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(do), ptr(lse), None, None, 0, B, H, Ls, Ls, 64, 0.125, ptr(gq), ptr(gk), ptr(gv), ptr(ws), wsb, sp()), "bwd")
-    def timed(fn, n=10):
-        for _ in range(3): fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n): fn()
-        e1.record(); torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
-    flop = 4.0 * B * H * Ls * Ls * 64
-    for var in (3, 4, 8, 10, 21):
+    qs, ks, vs = (t[:1].float().permute(0, 2, 1, 3) for t in (q, k, v))
+    ref = torch.softmax(qs @ ks.transpose(-1, -2) * 0.125, -1) @ vs
+    ref = ref.permute(0, 2, 1, 3)
+    for var in variants:
         lib.set_option("mha_variant", var)
-        ms = timed(fwd)
-        print("B=%d L=%d H=%d fwd variant %d: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, var, ms, flop / ms / 1e9), flush=True)
+        fwd = lambda: lib.check(L.asr_mha_fwd_bf16(p(q), p(k), p(v), None, None, 0, B, H, Ls, Ls, 64, 0.125, p(out), p(lse), sp()), "fwd")
+        ms = min(bench.cuda_time(fwd, 10, warm=3) for _ in range(3))
+        err = (out[:1].float() - ref).abs().max().item() / ref.abs().max().item()
+        print("B=%d L=%d variant %d: fwd %.4f ms  %.1f TFLOP/s  max err %.2e of scale" % (B, Ls, var, ms, 4.0 * B * H * Ls * Ls * 64 / ms / 1e9, err), flush=True)
     lib.set_option("mha_variant", 0)
-    for grp in (2, 4):
-        lib.set_option("mha_bwd_groups", grp)
-        ms = timed(bwd)
-        print("B=%d L=%d H=%d bwd %2d softmax warps: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, 4 * grp, ms, 2.5 * flop / ms / 1e9), flush=True)
-    lib.set_option("mha_bwd_groups", 0)
-    def fwd_d(): check(L.asr_mha_fwd_dropout_bf16(ptr(q), ptr(k), ptr(v), None, None, 0, B, H, Ls, Ls, 64, 0.125, 0.1, 77, ptr(out), ptr(lse), sp()), "fwd")
-    def bwd_d(): check(L.asr_mha_bwd_dropout_bf16(ptr(q), ptr(k), ptr(v), ptr(out), ptr(do), ptr(lse), None, None, 0, B, H, Ls, Ls, 64, 0.125, 0.1, 77, ptr(gq), ptr(gk), ptr(gv), ptr(ws), wsb, sp()), "bwd")
-    ms = timed(fwd_d); print("B=%d L=%d H=%d fwd with dropout 0.1: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, ms, flop / ms / 1e9), flush=True)
-    ms = timed(bwd_d); print("B=%d L=%d H=%d bwd with dropout 0.1: %.3f ms  %.0f TFLOP/s" % (B, Ls, H, ms, 2.5 * flop / ms / 1e9), flush=True)
