@@ -406,30 +406,32 @@ __global__ void __launch_bounds__(256) splitk_reduce_out_kernel(const float* __r
     }
 }
 
-// Column sums (bias gradients): CTA = 32 columns x all rows; 8 row groups of 32 lanes read 128 contiguous bytes per row
-// (64 for bf16), then the 8 partial sums of a column are added in a fixed order.
+// Column sums (bias gradients): CTA = 32 columns x all rows; 32 row groups of 32 lanes (1024 threads) read 128 contiguous
+// bytes per row (64 for bf16), eight rows in flight per thread, then the 32 partial sums of a column are added in a fixed
+// order (deterministic).
 template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
-    __shared__ float part[8][33];
+__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
+    __shared__ float part[32][33];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
     const int n = blockIdx.x * 32 + lane;
     float acc = 0.0f;
     if (n < N) {
         const T* col = x + n;
         int m = grp;
-        for (; m + 24 < M; m += 32) {       // four rows in flight per thread
-            const float a0 = (float)col[(size_t)m * ld], a1 = (float)col[(size_t)(m + 8) * ld];
-            const float a2 = (float)col[(size_t)(m + 16) * ld], a3 = (float)col[(size_t)(m + 24) * ld];
-            acc += (a0 + a1) + (a2 + a3);
+        for (; m + 7 * 32 < M; m += 8 * 32) {
+            float a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = (float)col[(size_t)(m + 32 * u) * ld];
+            acc += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         }
-        for (; m < M; m += 8) acc += (float)col[(size_t)m * ld];
+        for (; m < M; m += 32) acc += (float)col[(size_t)m * ld];
     }
     part[grp][lane] = acc;
     __syncthreads();
     if (grp == 0 && n < N) {
         float s = 0.0f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) s += part[g][lane];
+        for (int g = 0; g < 32; ++g) s += part[g][lane];
         out[n] = s;
     }
 }
@@ -444,9 +446,9 @@ extern "C" int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, floa
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const unsigned blocks = (unsigned)((N + 31) / 32);
     if (is_bf16)
-        colsum_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), M, N, ld, out);
+        colsum_kernel<__nv_bfloat16><<<blocks, 1024, 0, st>>>(static_cast<const __nv_bfloat16*>(x), M, N, ld, out);
     else
-        colsum_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float*>(x), M, N, ld, out);
+        colsum_kernel<float><<<blocks, 1024, 0, st>>>(static_cast<const float*>(x), M, N, ld, out);
     ASR_LAUNCH_CHECK();
     return 0;
 }

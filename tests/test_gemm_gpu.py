@@ -157,6 +157,6 @@ def test_shell_linear_runs_on_the_tensor_core_kernel_and_can_be_switched_off(mon
     monkeypatch.setattr(module, "USE_TENSOR_CORE_FP32", True)
     n0 = lib.launch_count()
     y = lin(x)                                       # the default: csrc/gemm2.cu
-    assert lib.launch_count() - n0 == 1
+    assert 1 <= lib.launch_count() - n0 <= 2          # the GEMM (+ its split-K reduction)
     assert (y - y_ref).abs().max().item() <= 2e-5 * y_ref.abs().max().item()
     assert sorted(lin.state_dict().keys()) == ["bias", "weight"]
