@@ -46,6 +46,8 @@ SIGNATURES = {
     "asr_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "asr_gemm_f32": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
                               _vp, _c_size_t, _vp]),
+    "asr_gemm_f32_ragged": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
+                                     _vp, _c_int, _c_int, _vp, _c_size_t, _vp]),
     "asr_gemm_bf16": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _c_int,
                                _c_int, _vp, _c_size_t, _vp]),
     "asr_ctc_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int, _c_int]),

@@ -98,7 +98,8 @@ __device__ __forceinline__ void split_lo_tile(const unsigned char* hi_tile, unsi
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ bias,
-                  float* __restrict__ c, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride) {
+                  float* __restrict__ c, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride,
+                  const int* __restrict__ row_len, int group_rows, int dead_mode) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     using Cfg = G2F32Cfg<BN>;
@@ -110,7 +111,26 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kG2M;
     const int nk_total = (K + TA::kBK - 1) / TA::kBK;          // a K tail is zero-filled by TMA
     const int k_first = blockIdx.z * stages_per_split;
-    const int nk = max(0, min(stages_per_split, nk_total - k_first));
+    int nk = max(0, min(stages_per_split, nk_total - k_first));
+    // Ragged rows (padded utterances): the "row" dimension - M when A is K-major, the contraction when A is MN-major - is
+    // made of groups of `group_rows` rows of which only the first row_len[g] are valid; the others are known to be zero
+    // (gradient rows of padded frames) or never read (their logits).  A row tile / K step that lies entirely in padding
+    // is skipped: dead_mode 1 = A K-major, dead tiles are not written at all; 2 = A K-major, dead tiles are written as
+    // zeros; 3 = contraction over the rows, dead K steps contribute nothing.
+    auto rows_dead = [&](int r0, int n) {       // rows [r0, r0 + n) all padding?
+        const int g0 = r0 / group_rows, g1 = (r0 + n - 1) / group_rows;
+        for (int g = g0; g <= g1; ++g) {
+            const int lo = max(r0, g * group_rows) - g * group_rows;      // first row of the range inside group g
+            if (lo < __ldg(row_len + g)) return false;
+        }
+        return true;
+    };
+    if (row_len != nullptr && (dead_mode == 1 || dead_mode == 2) && rows_dead(m0, min(kG2M, M - m0))) {
+        if (dead_mode == 1) return;      // uniform for the CTA, before any barrier / allocation
+        nk = 0;
+    }
+    const bool skip_k = row_len != nullptr && dead_mode == 3;
+    auto stage_dead = [&](int k) { return skip_k && rows_dead((k_first + k) * TA::kBK, min(TA::kBK, K - (k_first + k) * TA::kBK)); };
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars->full[s], 1);
@@ -135,47 +155,57 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         if (elect_one_sync()) {
             tma_prefetch_desc(&tm_a);
             tma_prefetch_desc(&tm_b);
+            int it = 0;                                  // live stages only: every role counts them the same way
             for (int k = 0; k < nk; ++k) {
-                const int s = k % kStages;
-                if (k >= kStages) mbar_wait(&bars->empty[s], ((k / kStages) - 1) & 1);
+                if (stage_dead(k)) continue;
+                const int s = it % kStages;
+                if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
                 unsigned char* st = smem + s * Cfg::kStage;
                 mbar_arrive_expect_tx(&bars->full[s], Cfg::kATile + Cfg::kBTile);
                 const int kc = (k_first + k) * TA::kBK;
                 TA::load(st, &tm_a, kc, m0, &bars->full[s]);
                 TB::load(st + 2 * Cfg::kATile, &tm_b, kc, n0, &bars->full[s]);
+                ++it;
             }
         }
     } else if (warp == 5) {
         if (elect_one_sync()) {
             constexpr uint32_t idesc = make_idesc_tf32(kG2M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int it = 0;
             for (int k = 0; k < nk; ++k) {
-                const int s = k % kStages;
-                mbar_wait(&bars->split[s], (k / kStages) & 1);
+                if (stage_dead(k)) continue;
+                const int s = it % kStages;
+                mbar_wait(&bars->split[s], (it / kStages) & 1);
                 tc_fence_after();
                 const uint32_t base = smem_u32(smem + s * Cfg::kStage);
                 const uint32_t a_hi = base, a_lo = base + Cfg::kATile, b_hi = base + 2 * Cfg::kATile, b_lo = b_hi + Cfg::kBTile;
 #pragma unroll
                 for (int kk = 0; kk < TA::kBK / TA::kUmmaK; ++kk) {
-                    const uint32_t acc = (k > 0 || kk > 0) ? 1u : 0u;
+                    const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
                     umma_tf32(tmem + BN, TA::desc(a_lo, kk), TB::desc(b_hi, kk), idesc, acc);
                     umma_tf32(tmem + BN, TA::desc(a_hi, kk), TB::desc(b_lo, kk), idesc, 1u);
                     umma_tf32(tmem, TA::desc(a_hi, kk), TB::desc(b_hi, kk), idesc, acc);
                 }
                 tc_commit(&bars->empty[s]);
+                ++it;
             }
-            tc_commit(&bars->acc_full);
+            if (it > 0) tc_commit(&bars->acc_full);
         }
     } else {
         // splitter: lo = x - (x with the 13 low mantissa bits cleared); the raw tile serves as the TF32 head
+        int live = 0;
         for (int k = 0; k < nk; ++k) {
-            const int s = k % kStages;
-            mbar_wait(&bars->full[s], (k / kStages) & 1);
+            if (stage_dead(k)) continue;
+            const int s = live % kStages;
+            mbar_wait(&bars->full[s], (live / kStages) & 1);
             unsigned char* st = smem + s * Cfg::kStage;
             split_lo_tile(st, st + Cfg::kATile, Cfg::kATile, threadIdx.x);
             split_lo_tile(st + 2 * Cfg::kATile, st + 2 * Cfg::kATile + Cfg::kBTile, Cfg::kBTile, threadIdx.x);
             fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's operand fetch
             mbar_arrive_warp(&bars->split[s]);
+            ++live;
         }
+        nk = live;                        // the epilogue below: zeros when no stage was live
         // epilogue: thread = row of the tile (TMEM lane), 32 columns at a time
         const int row = m0 + warp * 32 + lane;
         const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
@@ -514,7 +544,20 @@ extern "C" size_t asr_gemm_workspace_bytes(int M, int N, int K) {
 
 extern "C" int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb, const float* bias,
                             int M, int N, int K, float* c, int ldc, void* ws, size_t ws_bytes, void* stream) {
+    return asr_gemm_f32_ragged(a, a_mn_major, lda, b, b_mn_major, ldb, bias, M, N, K, c, ldc, nullptr, 0, 0, ws, ws_bytes, stream);
+}
+
+extern "C" int asr_gemm_f32_ragged(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
+                                   const float* bias, int M, int N, int K, float* c, int ldc, const int* row_len, int group_rows,
+                                   int skip_dead_output, void* ws, size_t ws_bytes, void* stream) {
     ASR_REQUIRE(a && b && c, "asr_gemm_f32: null pointer");
+    int dead_mode = 0;
+    if (row_len != nullptr) {
+        ASR_REQUIRE(group_rows > 0, "asr_gemm_f32_ragged: group_rows must be positive");
+        ASR_REQUIRE(!a_mn_major || b_mn_major, "asr_gemm_f32_ragged: with the rows as the contraction, both operands must be MN-major");
+        ASR_REQUIRE((a_mn_major ? K : M) % group_rows == 0, "asr_gemm_f32_ragged: the row count must be a multiple of group_rows");
+        dead_mode = a_mn_major ? 3 : (skip_dead_output ? 1 : 2);
+    }
     ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_gemm_f32: bad shape M=%d N=%d K=%d", M, N, K);
     ASR_REQUIRE(lda % 4 == 0 && ldb % 4 == 0, "asr_gemm_f32: operand row strides (%d, %d) must be multiples of 4 floats (16-byte rows for TMA)", lda, ldb);
     ASR_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldc >= N, "asr_gemm_f32: row stride smaller than the row");
@@ -538,7 +581,8 @@ extern "C" int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float
         static bool done = false;                                                                                   \
         if (set_smem_once(gemm_f32x3_kernel<BNV, AM, BM>, G2F32Cfg<BNV>::kSmem, done)) return 1;                     \
         gemm_f32x3_kernel<BNV, AM, BM><<<p.grid, 192, G2F32Cfg<BNV>::kSmem, st>>>(ta, tb, bias, dst, M, N, K, ldd,    \
-                                                                                 p.stages_per_split, split_stride); \
+                                                                                 p.stages_per_split, split_stride, \
+                                                                                 row_len, group_rows, dead_mode);  \
     } while (0)
     const int sel = (p.bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
     switch (sel) {

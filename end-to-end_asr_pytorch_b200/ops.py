@@ -213,11 +213,14 @@ def _gemm_ws(M, N, K, device):
     return torch.empty((nbytes // 4 + 1,), dtype=torch.float32, device=device), nbytes
 
 
-def gemm_f32(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None, n_valid=None, split_k=True):
+def gemm_f32(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None, n_valid=None, split_k=True, row_len=None,
+             group_rows=0, skip_dead_output=False):
     """C = A B (+ bias) in fp32 on the tensor cores at fp32-level accuracy (three TF32 products per K step), operands as stored:
     a: [M,K] (a_mn_major False) or [K,M] (True); b: [N,K] (False) or [K,N] (True); 2-D, last dim contiguous, row strides
     multiples of 4.  `out` may be a [M, ld >= N] buffer (its first N columns are written, plus zeros up to the next
-    multiple of 4).  The building block of the linear layers' backward products and of ops.ctc_fc_loss."""
+    multiple of 4).  The building block of the linear layers' backward products and of ops.ctc_fc_loss.
+    row_len [groups] i32 + group_rows: ragged rows (padded utterances of `group_rows` frames each, row_len[g] valid) -
+    tiles / K steps that lie entirely in padding are skipped, see asr_gemm_f32_ragged."""
     _require_cuda("a", a, torch.float32)
     _require_cuda("b", b, torch.float32)
     if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
@@ -239,8 +242,9 @@ def gemm_f32(a, b, a_mn_major=False, b_mn_major=False, bias=None, out=None, n_va
     if bias is not None:
         bias = bias.detach().to(device=a.device, dtype=torch.float32).contiguous()
     with torch.cuda.device(a.device):
-        check(_lib.lib().asr_gemm_f32(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0), ptr(bias),
-                                      M, N, K, ptr(out), out.stride(0), ptr(ws), wsb, stream_ptr()), "asr_gemm_f32")
+        check(_lib.lib().asr_gemm_f32_ragged(ptr(a), int(a_mn_major), a.stride(0), ptr(b), int(b_mn_major), b.stride(0), ptr(bias),
+                                             M, N, K, ptr(out), out.stride(0), ptr(row_len), int(group_rows),
+                                             int(skip_dead_output), ptr(ws), wsb, stream_ptr()), "asr_gemm_f32")
     return out
 
 
@@ -524,7 +528,10 @@ class _CtcFcLossFunction(torch.autograd.Function):
             h2 = h2.contiguous()
         w = weight if weight.is_contiguous() else weight.contiguous()
         buf = torch.empty((B * T, ld), dtype=torch.float32, device=dev)
-        gemm_f32(h2, w, out=buf, split_k=False)                                   # logits, columns [0, V)
+        # frames beyond an utterance's length: their logits are never read and their gradient rows are exactly zero, so all
+        # three products skip the row tiles / K steps that lie entirely in the padding
+        rag = dict(row_len=in_len, group_rows=T)
+        gemm_f32(h2, w, out=buf, split_k=False, skip_dead_output=True, **rag)     # logits, columns [0, V)
         need_grad = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         nll = torch.empty((B,), dtype=torch.float32, device=dev)
         S = targets.shape[1]
@@ -539,9 +546,9 @@ class _CtcFcLossFunction(torch.autograd.Function):
         if need_grad:
             g = buf[:, :V]                                                        # [B*T, V], row stride ld
             if ctx.needs_input_grad[0]:
-                gh = gemm_f32(g, w, b_mn_major=True, split_k=False).reshape(B, T, K)
+                gh = gemm_f32(g, w, b_mn_major=True, split_k=False, **rag).reshape(B, T, K)
             if ctx.needs_input_grad[1]:
-                gw = gemm_f32(g, h2, a_mn_major=True, b_mn_major=True)
+                gw = gemm_f32(g, h2, a_mn_major=True, b_mn_major=True, **rag)
         ctx.grads = (gh, gw)
         ctx.mark_non_differentiable(nll)
         return loss, nll

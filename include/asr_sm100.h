@@ -240,6 +240,15 @@ int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, float* out, voi
 int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
                  const float* bias, int M, int N, int K, float* c, int ldc,
                  void* ws, size_t ws_bytes, void* stream);
+/* asr_gemm_f32 on RAGGED rows (a padded batch of utterances): the row dimension - M when a is K-major, the contraction
+ * when a is MN-major (then b must be MN-major too) - consists of groups of `group_rows` rows of which only the first
+ * row_len[g] are valid; rows beyond are known to be zero (gradient rows of padded frames) or never read (their logits).
+ * Row tiles / K steps that lie entirely in padding are skipped: for a K-major a, dead output tiles are left unwritten
+ * (skip_dead_output = 1) or written as zeros (0).  Results on the valid rows are identical to asr_gemm_f32. */
+int asr_gemm_f32_ragged(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
+                        const float* bias, int M, int N, int K, float* c, int ldc,
+                        const int* row_len, int group_rows, int skip_dead_output,
+                        void* ws, size_t ws_bytes, void* stream);
 int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void* b, int b_mn_major, int ldb,
                   const float* bias, int relu, int M, int N, int K, void* c, int ldc, int out_f32,
                   void* ws, size_t ws_bytes, void* stream);

@@ -247,3 +247,29 @@ def test_colsum_is_the_bias_gradient(M, N, dtype):
     assert torch.equal(got, ops.colsum(x))                      # fixed summation order
     view = _rand((M, N + 8), 3, dtype=dtype)[:, :N]            # strided rows
     assert (ops.colsum(view).double() - view.double().sum(0)).abs().max().item() <= 2e-6 * view.double().abs().sum(0).max().item()
+
+
+def test_gemm_f32_ragged_rows_skip_padding_without_changing_valid_results():
+    """asr_gemm_f32_ragged: row tiles / K steps that lie entirely in the padding of an utterance are skipped; valid rows
+    are bit-identical to the plain call, dead output tiles are zeros (or left alone), dead K steps contribute nothing."""
+    ops = pkg("ops")
+    B, T, K, N = 6, 200, 64, 300                     # T not a multiple of the 128-row tiles / 32-row K steps: tiles straddle utterances
+    lens = torch.tensor([200, 37, 0, 129, 64, 1], dtype=torch.int32, device="cuda")
+    valid = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).reshape(-1)
+    x = _rand((B * T, K), 1)
+    w = _rand((N, K), 2)
+    full = ops.gemm_f32(x, w, split_k=False)
+    out = torch.full((B * T, N), 5.0, device="cuda")
+    ops.gemm_f32(x, w, out=out, split_k=False, row_len=lens, group_rows=T, skip_dead_output=True)
+    assert torch.equal(out[valid], full[valid])
+    assert (out[400:512] == 5.0).all()               # the row tile [384, 512) lies entirely in padding: never written
+    z = ops.gemm_f32(x, w, split_k=False, row_len=lens, group_rows=T)
+    assert torch.equal(z[valid], full[valid]) and (z[400:512] == 0).all()
+    # contraction over the rows: zero the padded rows (what the CTC row pass guarantees), then skipping changes nothing
+    g = _rand((B * T, N), 3) * valid[:, None]
+    h = _rand((B * T, K), 4)
+    ref = ops.gemm_f32(g, h, a_mn_major=True, b_mn_major=True, split_k=False)
+    for split in (False, True):
+        got = ops.gemm_f32(g, h, a_mn_major=True, b_mn_major=True, split_k=split, row_len=lens, group_rows=T)
+        assert (got - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    assert torch.equal(ops.gemm_f32(g, h, a_mn_major=True, b_mn_major=True, split_k=False, row_len=lens, group_rows=T), ref)
