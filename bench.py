@@ -85,6 +85,9 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the microbenches, the sweep and the full-model steps")
     ap.add_argument("--no-graph", action="store_true", help="full-model steps: eager launches instead of a CUDA graph")
     ap.add_argument("--no-allreduce", action="store_true", help="hot-path step without the gradient all-reduce (N > 1)")
+    ap.add_argument("--allreduce-at", default="rows", choices=["rows", "start", "end"],
+                    help="where the hot-path step launches its gradient all-reduce: behind the CTC row pass (default), at the "
+                         "start of the step, or after the last kernel (no overlap) - for measuring the overlap")
     return ap.parse_args()
 
 
@@ -231,8 +234,9 @@ class GradBuckets:
 class HotPath:
     """Preallocated buffers + direct C-ABI calls (what the autograd wrappers do, minus the allocator)."""
 
-    def __init__(self, w, inp, buckets=None):
+    def __init__(self, w, inp, buckets=None, allreduce_at="rows"):
         self.w, self.inp = w, inp
+        self.allreduce_at = allreduce_at
         self.lib = pkg("_lib")
         self.L = self.lib.lib()
         self.buckets = buckets
@@ -295,17 +299,21 @@ class HotPath:
         stream), i.e. the dominant kernel timed inside the timed region."""
         args = self._ctc_args() + (self.lib.stream_ptr(),)
         ticket = ctypes.c_int(0)
+        if self.buckets is not None and self.allreduce_at == "start":
+            self.buckets.launch()
         if ev is not None:
             ev[0].record()
         self.lib.check(self.L.asr_ctc_begin_f32(*args, ctypes.byref(ticket)), "asr_ctc_begin_f32")
         if ev is not None:
             ev[1].record()
-        if self.buckets is not None:
+        if self.buckets is not None and self.allreduce_at == "rows":
             self.buckets.launch()      # behind the row pass on this stream: the dense CTC gradient exists from here on
         self.cif_fwd(self.cif_hint_overlapped)
         self.cif_bwd()
         self.lib.check(self.L.asr_ctc_finish_f32(*args, ticket.value), "asr_ctc_finish_f32")
         if self.buckets is not None:
+            if self.allreduce_at == "end":
+                self.buckets.launch()
             self.buckets.wait()
 
     def step(self, ev=None):
@@ -671,7 +679,7 @@ def _train_inputs(w, device, seed):
     return feats, lens, targets
 
 
-def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=False, graph=True):
+def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=False, graph=True, torch_linear=False):
     """One optimiser step of a whole model per "step": forward, the reference's losses, backward, gradient all-reduce
     (NCCL, mean over ranks), Adam.  wname = "train" / "train_long": CIF_Model (config 5) with the fp32 shell of the
     reference; "transformer_bf16": Transformer (config 3) under bf16 autocast.
@@ -687,6 +695,10 @@ def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=Fals
     if tf32:      # the plain run keeps torch's defaults (fp32 matmul; cuDNN may use TF32 for the convolutions, as in the reference's own torch)
         torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
     lossm, dp, ops, lib = pkg("transformer.loss"), pkg("dp"), pkg("ops"), pkg("_lib")
+    module = pkg("transformer.module")
+    switches_before = (module.USE_TENSOR_CORE_FP32, module.USE_TENSOR_CORE_BF16)
+    if torch_linear:      # A/B: the shell's Linear layers on torch's F.linear (cuBLAS) instead of this package's GEMMs
+        module.USE_TENSOR_CORE_FP32 = module.USE_TENSOR_CORE_BF16 = False
     bf16 = wname == "transformer_bf16"
     torch.manual_seed(1234)
     if bf16:
@@ -817,6 +829,7 @@ def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=Fals
         if emit:
             print(json.dumps(line), flush=True)
     del model, opt, sync
+    module.USE_TENSOR_CORE_FP32, module.USE_TENSOR_CORE_BF16 = switches_before
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32_before
     torch.cuda.empty_cache()
     return line
@@ -949,7 +962,7 @@ def main():
     inp = make_inputs(w, device, 1236 + rank)
     n_params = cif_model_param_count(w)
     buckets = GradBuckets(n_params, device, world) if (world > 1 and not args.no_allreduce) else None
-    hp = HotPath(w, inp, buckets)
+    hp = HotPath(w, inp, buckets, args.allreduce_at)
     K, W = args.steps, max(args.warmup, 3)
 
     def barrier():
@@ -1128,8 +1141,16 @@ def main():
                                               "note": "same step with torch.backends.*.allow_tf32 = True for the model shell's "
                                                       "Linear / Conv GEMMs (reduced precision: informational, not the reported value)"}
         tt = run_train(args, "transformer_bf16", rank, world, device, steps=10, emit=False, graph=not args.no_graph)
+        tc = run_train(args, "transformer_bf16", rank, world, device, steps=10, emit=False, graph=not args.no_graph, torch_linear=True)
+        tf = run_train(args, "train", rank, world, device, steps=10, emit=False, graph=not args.no_graph, torch_linear=True)
         if tt is not None:
             transformer_step = brief(tt, per_gpu=dict(WORKLOADS["transformer_bf16"]))
+            transformer_step["with_torch_linear"] = {"value": tc["value"], "ms_per_step": tc["ms_per_step"],
+                                                     "note": "same step with the shell's Linear layers on torch's F.linear (cuBLAS bf16) "
+                                                             "instead of csrc/gemm2.cu"}
+            train_step["with_torch_linear"] = {"value": tf["value"], "ms_per_step": tf["ms_per_step"],
+                                               "note": "same step with the shell's Linear layers on torch's F.linear (cuBLAS SIMT sgemm) "
+                                                       "instead of csrc/gemm2.cu"}
 
     if rank == 0:
         cpu_baseline = None
