@@ -10,7 +10,7 @@ Layout
   ctcModel/        (attention.py, loss.py, cif_model.py)
   utils/utils.py   attention-mask builders (reference: src/utils/utils.py:125-165)
   patch.py         installs the drop-ins into an imported reference tree
-  dp.py            data-parallel gradient all-reduce (one process per GPU, NCCL)
+  dp.py            data-parallel gradient all-reduce (one process per GPU; csrc/allreduce.cu over NVLink peer memory, or NCCL)
 
 The directory name is the one the build contract asks for and is not a valid
 Python identifier; import it with importlib.import_module(

@@ -43,6 +43,8 @@ SIGNATURES = {
     "asr_linear_residual_layernorm_bf16": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_float, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_linear_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
+    "asr_allreduce_signal_bytes": (_c_size_t, [_c_int, _c_int]),
+    "asr_allreduce_mean_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_size_t, _c_size_t, _c_int, _vp]),
     "asr_gemm_workspace_bytes": (_c_size_t, [_c_int, _c_int, _c_int]),
     "asr_gemm_f32": (_c_int, [_vp, _c_int, _c_int, _vp, _c_int, _c_int, _vp, _c_int, _c_int, _c_int, _vp, _c_int,
                               _vp, _c_size_t, _vp]),

@@ -24,6 +24,8 @@
 
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 namespace asr {
 
 
@@ -403,6 +405,21 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #ifdef ASR_MHA_TRACE
 // clock64 stamps of CTA (0,0,0): [tile][block < 16][point < 20], read back with asr_debug_mha_trace (tools/mha_trace.py)
 __device__ long long g_mha_trace[2 * 16 * 20];
+// per-CTA timeline of mha_fwd8_kernel (tools/mha_cta_timeline.py): [linear CTA id < 2048][sm id, entry, softmax role start,
+// last block done, exit]
+__device__ long long g_mha_cta[2048 * 5];
+__device__ __forceinline__ void mha_cta_stamp(int slot) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (cta < 2048) {
+        if (slot == 1) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_mha_cta[cta * 5] = smid;
+        }
+        g_mha_cta[cta * 5 + slot] = clock64();
+    }
+}
+#define MHA_CTA_STAMP(slot) do { if (threadIdx.x == 0) mha_cta_stamp(slot); } while (0)
 #define MHA_TRACE(t, j, k)                                                                    \
     do {                                                                                      \
         if (lane == 0 && (warp & 3) == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) \
@@ -418,6 +435,7 @@ __device__ long long g_mha_trace[2 * 16 * 20];
         if ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && (j) < 16) g_mha_trace[((t) * 16 + (j)) * 20 + (k)] = clock64(); \
     } while (0)
 #else
+#define MHA_CTA_STAMP(slot) do { } while (0)
 #define MHA_TRACE(t, j, k) do { } while (0)
 #define MHA_TRACE_MMA(t, j, k) do { } while (0)
 #define MHA_TRACE_WARP(t, j, k) do { } while (0)
@@ -465,6 +483,7 @@ __global__ void __launch_bounds__(kFwd8Threads, 1)
 mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
     extern __shared__ __align__(1024) unsigned char smem[];
+    MHA_CTA_STAMP(1);
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint32_t seed_lo = a.seed_lo, seed_hi = a.seed_hi;
     if (DROP) effective_seed(a.seed_dev, seed_lo, seed_hi);
@@ -699,6 +718,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             // key blocks just passes the token on); tile 1 grants the first turn.
             const bool pp = (MODE & 1) && ntile == 2;
             const int nturn = pp ? nblk : nbt;
+            MHA_CTA_STAMP(2);
             if (pp && t == 1) bar_arrive_named(1, 256);
             for (int j = 0; j < nturn; ++j) {
                 if (j >= nbt) {
@@ -866,6 +886,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 MHA_TRACE_WARP(t, j, 12);
             }
             // epilogue
+            MHA_CTA_STAMP(3);
             mbar_wait(&bars->pv_full[t], (nbt - 1) & 1);
             tc_fence_after();
             const float inv = 1.0f / l_run;
@@ -893,6 +914,483 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (qi < a.Lq && a.lse != nullptr)
                 a.lse[((size_t)b * a.Hh + h) * a.Lq + qi] = (m_used * c + log2f(l_run)) * 0.6931471805599453f;
         }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+    MHA_CTA_STAMP(4);
+}
+
+// ---- forward, persistent: the default two-tile kernel with the work items looped inside the CTA --------------
+// Per-CTA timeline of mha_fwd8_kernel (tools/mha_cta_timeline.py, L = 2048): 51 100 cycles per work item on an SM, of
+// which 41 900 are the key-block loop; the rest is per-CTA cost - 910 cycles of barrier / tensor-memory set-up, ~3400
+// until the first S is ready (tensor-map fetch, Q and K loads, the first product), ~3350 from the last block to the
+// exit (last P V, normalise, store, dealloc) and ~1540 in which the SM waits for its next CTA: 18 % of the time at
+// L = 2048, 10 % at L = 4096.  Here one CTA per SM walks the (batch, head, 256-query) items i = blockIdx.x, + gridDim.x,
+// ...; the roles keep running across items:
+//   * the K / V rings and every per-block barrier continue with CTA-wide block counters (stage = block % 4);
+//   * Q is double-buffered: the producer fetches the next item's Q (and its first K / V blocks) while the current
+//     item is still in its key-block loop (q_free: both issuers have finished the item's last Q K^T);
+//   * an issuer starts the next item's S = Q K^T as soon as the last scores of the current item are in registers, i.e.
+//     under the last block's exponentials and the epilogue; the first P V of an item overwrites O, so it waits for o_free
+//     (the epilogue has read the accumulator);
+//   * tensor memory is allocated once.
+// Inner structure, TMEM layout and numerics are those of mha_fwd8_kernel<DROP, 51> (outputs are bit-identical).
+struct __align__(8) MhaBarriersP {
+    uint64_t q_full[2];     // per Q buffer (items alternate)
+    uint64_t q_free[2];
+    uint64_t k_full[kFwd6Stages];
+    uint64_t k_empty[kFwd6Stages];
+    uint64_t v_full[kFwd6Stages];
+    uint64_t v_empty[kFwd6Stages];
+    uint64_t s_full[2];     // per tile
+    uint64_t s_free[2];
+    uint64_t p_full[2];
+    uint64_t pv_full[2];
+    uint64_t o_free[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+static_assert(sizeof(MhaBarriersP) <= 256, "barrier block");
+constexpr int kFwdPSmem = (4 + 2 * kFwd6Stages) * kTileBytes + 256;     // Q x2 x2 + K ring + V ring + barriers
+static_assert(kFwdPSmem <= 232448, "shared memory of the persistent forward kernel");
+
+struct MhaItem {
+    int b, h, q0, ntile, nb0, nb1, nblk;      // (no array: a runtime tile index would push the struct into local memory)
+    __device__ __forceinline__ int nb(int t) const { return t == 0 ? nb0 : nb1; }
+};
+// The items of a CTA: item = blockIdx.x, + gridDim.x, ...; item -> (batch, head, 256-query tile), tiles fastest.  The walk
+// keeps (batch * heads + head, tile) and advances them by additions (three divisions once per thread instead of per item).
+struct MhaItemWalk {
+    int bh, qt, dbh, dqt, nq2, left;
+    __device__ __forceinline__ MhaItemWalk(int n_items, int nq2_) : nq2(nq2_) {
+        const int first = blockIdx.x, step = gridDim.x;
+        bh = first / nq2;
+        qt = first - bh * nq2;
+        dbh = step / nq2;
+        dqt = step - dbh * nq2;
+        left = first < n_items ? (n_items - 1 - first) / step + 1 : 0;
+    }
+    __device__ __forceinline__ bool valid() const { return left > 0; }
+    __device__ __forceinline__ void next() {
+        --left;
+        bh += dbh;
+        qt += dqt;
+        if (qt >= nq2) {
+            qt -= nq2;
+            ++bh;
+        }
+    }
+    __device__ __forceinline__ MhaItem get(const MhaFwdArgs& a) const {
+        MhaItem it;
+        // causal items get lighter towards the first queries: rotate the tile order per (batch, head), so that the items
+        // of one CTA do not all fall on the same query tile
+        int q = qt;
+        if (a.causal) {
+            q = qt + bh % nq2;
+            if (q >= nq2) q -= nq2;
+        }
+        it.b = bh / a.Hh;
+        it.h = bh - it.b * a.Hh;
+        it.q0 = q * 2 * kBM;
+        const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + it.b), 0), a.Lk) : a.Lk;
+        it.ntile = (it.q0 + kBM < a.Lq) ? 2 : 1;
+        int k_end0 = a.causal ? min(kvlen, it.q0 + kBM) : kvlen;
+        int k_end1 = a.causal ? min(kvlen, it.q0 + 2 * kBM) : kvlen;
+        if (a.dense_mask) k_end0 = k_end1 = a.Lk;
+        it.nb0 = max(1, (k_end0 + kBN - 1) / kBN);
+        it.nb1 = (it.ntile == 2) ? max(1, (k_end1 + kBN - 1) / kBN) : 0;
+        it.nblk = max(it.nb0, it.nb1);
+        return it;
+    }
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(kFwd8Threads, 1)
+mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a, const int n_items, const int nq2) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint32_t seed_lo = a.seed_lo, seed_hi = a.seed_hi;
+    if (DROP) effective_seed(a.seed_dev, seed_lo, seed_hi);
+    unsigned char* sQ = smem;                              // [2 buffers][2 tiles]
+    unsigned char* sK = sQ + 4 * kTileBytes;               // kFwd6Stages tiles
+    unsigned char* sV = sK + kFwd6Stages * kTileBytes;     // kFwd6Stages tiles
+    MhaBarriersP* bars = reinterpret_cast<MhaBarriersP*>(sV + kFwd6Stages * kTileBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars->q_full[i], 1);
+            mbar_init(&bars->q_free[i], 2);               // one arrival per tile issuer
+        }
+        for (int s = 0; s < kFwd6Stages; ++s) {
+            mbar_init(&bars->k_full[s], 1);
+            mbar_init(&bars->k_empty[s], 2);              // both issuers release every stage (a tile that does not need
+            mbar_init(&bars->v_full[s], 1);               // the block arrives without a product)
+            mbar_init(&bars->v_empty[s], 2);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(&bars->s_full[t], 1);
+            mbar_init(&bars->s_free[t], 4);               // one arrival per softmax warp of the tile
+            mbar_init(&bars->p_full[t], 4);
+            mbar_init(&bars->pv_full[t], 1);
+            mbar_init(&bars->o_free[t], 4);
+        }
+        fence_mbar_init();
+    }
+    constexpr int kTmaWarp = 8, kMmaWarp = 9;
+    if (warp == kMmaWarp) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+
+    if (warp == kTmaWarp) {
+        // ===== TMA producer =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            int g = 0;                                    // blocks loaded by this CTA so far
+            int k = 0;                                    // items
+            for (MhaItemWalk walk(n_items, nq2); walk.valid(); walk.next(), ++k) {
+                const MhaItem it = walk.get(a);
+                const int qb = k & 1;
+                if (k >= 2) mbar_wait(&bars->q_free[qb], ((k >> 1) - 1) & 1);     // the item two back is done with this Q buffer
+                mbar_arrive_expect_tx(&bars->q_full[qb], it.ntile * kTileBytes);
+                for (int t = 0; t < it.ntile; ++t)
+                    tma_load_4d(sQ + (qb * 2 + t) * kTileBytes, &tm_q, 0, it.h, it.q0 + t * kBM, it.b, &bars->q_full[qb]);
+                for (int j = 0; j < it.nblk; ++j, ++g) {
+                    const int s = g % kFwd6Stages;
+                    const int use = g / kFwd6Stages;
+                    if (use > 0) mbar_wait(&bars->k_empty[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&bars->k_full[s], kTileBytes);
+                    tma_load_4d(sK + s * kTileBytes, &tm_k, 0, it.h, j * kBN, it.b, &bars->k_full[s]);
+                    if (use > 0) mbar_wait(&bars->v_empty[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&bars->v_full[s], kTileBytes);
+                    tma_load_4d(sV + s * kTileBytes, &tm_v, 0, it.h, j * kBN, it.b, &bars->v_full[s]);
+                }
+            }
+        }
+    } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+        // ===== MMA issuers, one elected thread per tile =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+        const int t = warp - kMmaWarp;
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
+            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A from tensor memory, B MN-major
+            const uint32_t tmem_s = tmem + 128 * t;
+            const uint32_t tmem_o = tmem + 256 + 64 * t;
+            const uint32_t tmem_p = tmem + 384 + 64 * t;
+            int g = 0;        // K / V blocks seen by this CTA before the current item
+            int n = 0;        // blocks this tile has issued before the current item (phases of s_*, p_*, pv_*)
+            int act = 0;      // items in which this tile was active (phase of o_free)
+            int k = 0;
+            // S of block j of item `it` (its first block is the CTA's block g0 and this tile's block n0; Q buffer k0 & 1), or
+            // just the release of the K stage when this tile does not need the block
+            auto issue_s = [&](const MhaItem& it, int g0, int n0, int k0, int j) {
+                const int nbt = it.nb(t);
+                const int qb = k0 & 1;
+                const int ks = (g0 + j) % kFwd6Stages;
+                if (j == 0) mbar_wait(&bars->q_full[qb], (k0 >> 1) & 1);
+                mbar_wait(&bars->k_full[ks], ((g0 + j) / kFwd6Stages) & 1);
+                if (j >= nbt) {
+                    mbar_arrive(&bars->k_empty[ks]);
+                    if (nbt == 0 && j == 0) mbar_arrive(&bars->q_free[qb]);
+                    return;
+                }
+                if (n0 + j > 0) mbar_wait(&bars->s_free[t], (n0 + j - 1) & 1);      // the previous scores are in registers
+                tc_fence_after();
+                const uint32_t q_addr = smem_u32(sQ + (qb * 2 + t) * kTileBytes);
+                const uint32_t k_addr = smem_u32(sK + ks * kTileBytes);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tmem_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              idesc_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->s_full[t]);
+                tc_commit(&bars->k_empty[ks]);
+                if (j + 1 == nbt) tc_commit(&bars->q_free[qb]);     // this tile's last Q K^T of the item: Q is free behind it
+            };
+            MhaItemWalk walk(n_items, nq2);
+            MhaItem it = walk.get(a);
+            if (walk.valid()) issue_s(it, 0, 0, 0, 0);
+            while (walk.valid()) {
+                walk.next();
+                const bool has_next = walk.valid();
+                MhaItem nx = it;
+                if (has_next) nx = walk.get(a);
+                const int nbt = it.nb(t);
+                for (int j = 0; j < it.nblk; ++j) {
+                    const int vs = (g + j) % kFwd6Stages;
+                    // the next block's scores first: they only need s_free, which arrives long before p_full.  Behind an
+                    // item's last block that is the FIRST block of the next item: its product runs under this item's last
+                    // exponentials and epilogue.
+                    if (j + 1 < it.nblk) issue_s(it, g, n, k, j + 1);
+                    else if (has_next) {
+                        MHA_TRACE_MMA(t, k + 1, 10);
+                        issue_s(nx, g + it.nblk, n + nbt, k + 1, 0);
+                        MHA_TRACE_MMA(t, k + 1, 11);
+                    }
+                    mbar_wait(&bars->v_full[vs], ((g + j) / kFwd6Stages) & 1);
+                    if (j >= nbt) {
+                        mbar_arrive(&bars->v_empty[vs]);
+                        continue;
+                    }
+                    mbar_wait(&bars->p_full[t], (n + j) & 1);
+                    if (j == 0 && act > 0) mbar_wait(&bars->o_free[t], (act - 1) & 1);   // the last epilogue has read O
+                    tc_fence_after();
+                    const uint32_t v_addr = smem_u32(sV + vs * kTileBytes);
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk)
+                        umma_bf16_ts(tmem_o, tmem_p + 8 * kk, smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024), idesc_pv,
+                                     (j > 0 || kk > 0) ? 1u : 0u);
+                    tc_commit(&bars->pv_full[t]);
+                    tc_commit(&bars->v_empty[vs]);
+                    if (j == 0) MHA_TRACE_MMA(t, k, 12);
+                    if (j + 1 == it.nblk) MHA_TRACE_MMA(t, k, 13);
+                }
+                g += it.nblk;
+                n += nbt;
+                if (nbt > 0) ++act;
+                ++k;
+                it = nx;
+            }
+        }
+    } else if (warp >= 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");   // the idle warp of the utility warpgroup
+    } else {
+        // ===== softmax + epilogue: warps 0-3 own tile 0, warps 4-7 tile 1; thread = query row =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");    // 8 x 32 x 216 + 4 x 32 x 72 = 384 x 168, the CTA's pool
+        const int t = warp >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const uint32_t tmem_s = tmem + 128 * t + lane_base;
+        const uint32_t tmem_o = tmem + 256 + 64 * t + lane_base;
+        const uint32_t tmem_p = tmem + 384 + 64 * t + lane_base;
+        const float c = a.scale_log2;
+        int n = 0;            // blocks this tile has processed before the current item
+        // The epilogue of an item is DEFERRED behind the first key block of the tile's next item: the wait for the item's
+        // last P V (~850 cycles from the hand-over to the visible barrier) then costs nothing, and the normalise / store
+        // runs while the other tile holds the XU pipe.  `ep_*` is the finished item's state.
+        bool ep_pending = false;
+        float ep_m = 0.0f, ep_l = 0.0f;
+        int ep_qi = 0, ep_b = 0, ep_h = 0;
+        auto epilogue = [&]() {
+            // (its last P V completed long ago when this runs deferred: the next item's first block has waited for it
+            // before storing its probabilities)
+            mbar_wait(&bars->pv_full[t], (n - 1) & 1);
+            tc_fence_after();
+            uint32_t o32[2][32];
+            tmem_ld32_issue(tmem_o, o32[0]);
+            tmem_ld32_issue(tmem_o + 32, o32[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive_warp(&bars->o_free[t]);        // the next item's first P V may overwrite O
+            const float inv = 1.0f / ep_l;
+            if (ep_qi < a.Lq) {
+                __nv_bfloat16* dst = a.out + (((size_t)ep_b * a.Lq + ep_qi) * a.Hh + ep_h) * kD;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const __nv_bfloat162 v2 = __floats2bfloat162_rn(__uint_as_float(o32[hh][i + 2 * u]) * inv,
+                                                                             __uint_as_float(o32[hh][i + 2 * u + 1]) * inv);
+                            w[u] = *reinterpret_cast<const uint32_t*>(&v2);
+                        }
+                        *reinterpret_cast<uint4*>(dst + 32 * hh + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                if (a.lse != nullptr)
+                    a.lse[((size_t)ep_b * a.Hh + ep_h) * a.Lq + ep_qi] = (ep_m * c + log2f(ep_l)) * 0.6931471805599453f;
+            }
+            ep_pending = false;
+        };
+        // Token ring of the two tiles: tile 0 waits on named barrier 1, tile 1 on barrier 2; a tile holds the token while it
+        // runs its exponentials and then hands it to the other tile, which keeps the tiles in opposite phases.  The ring runs
+        // on across the items (tile 1 hands the token back after its last block too, so tile 0 can start the next item's
+        // exponentials at once); tile 1 grants the very first turn.  Items with one tile do not touch it.
+        bool ring_started = false;
+        int kk_item = -1;
+        for (MhaItemWalk walk(n_items, nq2); walk.valid(); walk.next()) {
+            const MhaItem it = walk.get(a);
+            ++kk_item;
+            if (t >= it.ntile) continue;
+            const int b = it.b, h = it.h;
+            const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+            const int qi = it.q0 + t * kBM + row;
+            const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+            float m_used = -INFINITY;
+            float l_run = 0.0f;          // sum of the row's (undropped) probabilities, scaled like O
+            const int nbt = it.nb(t);
+            const bool pp = it.ntile == 2;
+            const int nturn = pp ? it.nblk : nbt;
+            MHA_TRACE(t, kk_item, 0);
+            if (pp && t == 1 && !ring_started) bar_arrive_named(1, 256);
+            if (pp) ring_started = true;
+            for (int j = 0; j < nturn; ++j) {
+                if (j >= nbt) {
+                    bar_sync_named(1 + t, 256);
+                    bar_arrive_named(2 - t, 256);
+                    continue;
+                }
+                const int key0 = j * kBN;
+                int lim = kvlen;
+                if (a.causal) lim = min(lim, qi + 1);
+                const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+                if (j == 0) MHA_TRACE(t, kk_item, 8);
+                mbar_wait(&bars->s_full[t], (n + j) & 1);
+                tc_fence_after();
+                if (j == 0) MHA_TRACE(t, kk_item, 9);
+                uint32_t r[4][32];           // the row's 128 scores: read from TMEM exactly once
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tmem_ld32_issue(tmem_s + 32 * q, r[q]);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive_warp(&bars->s_free[t]);      // the scores are in registers: S may be overwritten
+                if (j == 0) MHA_TRACE(t, kk_item, 1);
+                if (j == 1) MHA_TRACE(t, kk_item, 6);
+                if (j == 2) MHA_TRACE(t, kk_item, 7);
+                float m_q[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (need_mask) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int key = key0 + 32 * q + i;
+                            bool dead = key >= lim;
+                            if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
+                            if (dead) r[q][i] = 0xff800000u;   // -inf
+                        }
+                    }
+                    m_q[q] = -INFINITY;          // four independent chains
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) m_q[q] = fmaxf(m_q[q], __uint_as_float(r[q][i]));
+                }
+                const float m_blk = fmaxf(fmaxf(m_q[0], m_q[1]), fmaxf(m_q[2], m_q[3]));
+                const float m_new = fmaxf(m_used, m_blk);
+                const bool grow = (j > 0) && ((m_new - m_used) * c > 8.0f);
+                bool pv_waited = false;
+                if (j == 0) {
+                    m_used = m_new;
+                } else if (__any_sync(0xffffffffu, grow)) {      // TMEM accesses are warp-collective: all lanes go
+                    // O is being accumulated by P V of this tile's previous block: wait for it before touching O
+                    mbar_wait(&bars->pv_full[t], (n + j - 1) & 1);
+                    tc_fence_after();
+                    pv_waited = true;
+                    const float f = grow ? ex2_approx((m_used - m_new) * c) : 1.0f;   // m_used = -inf -> 0
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        uint32_t o32[32];
+                        tmem_ld32_issue(tmem_o + 32 * hh, o32);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o32[i] = __float_as_uint(__uint_as_float(o32[i]) * f);
+                        tmem_st32(tmem_o + 32 * hh, o32);
+                    }
+                    l_run *= f;
+                    tmem_st_wait();
+                    if (grow) m_used = m_new;
+                }
+                const float mc = ((m_used == -INFINITY) ? 0.0f : m_used) * c;   // fully masked so far: keep exp2 finite
+                // The P columns are free once P V of the previous block - of the previous ITEM at an item's first block - has
+                // read them.
+                if (n + j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (n + j - 1) & 1);
+                float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                uint32_t pk_all[4][16];
+                if (!DROP) {
+                    // x = s * scale - max in place, packed; no XU work yet
+                    const uint64_t c2 = pack_f32x2(c, c);
+                    const uint64_t mc2 = pack_f32x2(-mc, -mc);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float x0, x1;
+                            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1])), c2, mc2), x0, x1);
+                            r[q][i] = __float_as_uint(x0);
+                            r[q][i + 1] = __float_as_uint(x1);
+                        }
+                    }
+                    if (pp) {
+                        bar_sync_named(1 + t, 256);          // this tile's turn on the XU pipe
+                        if (j == 0) MHA_TRACE(t, kk_item, 2);
+                        // the exponentials stay behind the barrier (they are pure: ptxas would hoist most of them above it, into
+                        // the other tile's turn - two warps of a sub-partition feeding the XU pipe at once are slower than one
+                        // after the other: 2980 vs 2630 cycles per key block)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) reg_tie32(r[q]);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint64_t ls2 = pack_f32x2(0.0f, 0.0f);
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            const float p0 = ex2_approx(__uint_as_float(r[q][i]));
+                            const float p1 = ex2_approx(__uint_as_float(r[q][i + 1]));
+                            ls2 = add_f32x2(ls2, pack_f32x2(p0, p1));
+                            pk_all[q][i >> 1] = cvt_bf16x2(p0, p1);
+                        }
+                        float l0, l1;
+                        unpack_f32x2(ls2, l0, l1);
+                        lsum[q] = l0 + l1;
+                        tmem_st16(tmem_p + 16 * q, pk_all[q]);
+                    }
+                } else {
+                    if (pp) bar_sync_named(1 + t, 256);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t (&pk)[16] = pk_all[q];
+#pragma unroll
+                        for (int g2 = 0; g2 < 2; ++g2) {
+                            const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g2 * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                       seed_lo, seed_hi);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) {
+                                float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g2 * 16 + i]), c, -mc));
+                                float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g2 * 16 + i + 1]), c, -mc));
+                                lsum[q] += p0 + p1;
+                                p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                                p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                                const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                                pk[(g2 * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                            }
+                        }
+                        tmem_st16(tmem_p + 16 * q, pk);
+                    }
+                }
+                if (pp) bar_arrive_named(2 - t, 256);
+                l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive_warp(&bars->p_full[t]);
+                if (j == 0) MHA_TRACE(t, kk_item, 3);
+                if (j == 0 && ep_pending) epilogue();        // of the previous item (n still counts its blocks only)
+                if (j == 0) MHA_TRACE(t, kk_item, 4);
+                if (j + 1 == nturn) MHA_TRACE(t, kk_item, 5);
+            }
+            n += nbt;
+            ep_pending = true;
+            ep_m = m_used;
+            ep_l = l_run;
+            ep_qi = qi;
+            ep_b = b;
+            ep_h = h;
+        }
+        if (ep_pending) epilogue();
     }
 
     tc_fence_before();
@@ -1410,10 +1908,16 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     //                              Philox work per element favours two threads per row: 418 vs 312 TFLOP/s) and for short
     //                              query sequences (Lq <= 128: the second tile of a 256-query CTA would be empty; model
     //                              shapes are L = 21 .. 167, U <= 15)
-    // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel.
+    //   mha_fwdp_kernel<DROP>      the two-tile kernel with the work items looped inside one CTA per SM (set-up, first loads,
+    //                              epilogue and CTA turnaround overlap the neighbouring items): without dropout, when an item has
+    //                              few key blocks - measured against mha_fwd8_kernel on B200 (tools/mha_persistent_sweep.py):
+    //                              L = 167 -11 %, 256 -19 %, 512 -12 %, 1024 -6 %, 1536 -3 % of the time, L = 2048 equal, 4096 +3 %;
+    //                              causal: -14 % at L = 256, -6 % at 1024, +5 % at 2048 (its static item order balances worse)
+    // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel, 40 = always mha_fwdp_kernel.
     const int variant = get_opt("mha_variant");
     const bool drop = a.drop_thresh > 0;
-    const bool one_tile = variant == 3 || (variant != 21 && (drop || Lq <= kBM));
+    const bool one_tile = variant == 3 || (variant != 21 && variant != 40 && (drop || Lq <= kBM));
+    const bool persistent = !drop && !one_tile && (variant == 40 || (variant == 0 && Lk <= (causal ? 1024 : 1536)));
     static bool attr_done[4] = {false, false, false, false};      // cudaFuncSetAttribute once per kernel, not per call
     if (one_tile) {
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
@@ -1426,6 +1930,13 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         }
     } else {
         dim3 grid((Lq + 2 * kBM - 1) / (2 * kBM), Hh, B);
+        if (persistent) {
+            const int nq2 = (Lq + 2 * kBM - 1) / (2 * kBM);
+            const int n_items = B * Hh * nq2;
+            static bool done = false;
+            if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPSmem)); done = true; }
+            mha_fwdp_kernel<false><<<dim3(std::min(n_items, num_sms())), kFwd8Threads, kFwdPSmem, st>>>(tq, tk, tv, a, n_items, nq2);
+        } else
         if (drop) {
             if (!attr_done[2]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<true, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(51))); attr_done[2] = true; }
             mha_fwd8_kernel<true, 51><<<grid, kFwd8Threads, fwd8_smem(51), st>>>(tq, tk, tv, a);
@@ -1461,6 +1972,9 @@ extern "C" int asr_mha_fwd_dropout_dev_bf16(const void* q, const void* k, const 
 #ifdef ASR_MHA_TRACE
 extern "C" int asr_debug_mha_trace(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, asr::g_mha_trace, sizeof(long long) * 2 * 16 * 20);
+}
+extern "C" int asr_debug_mha_cta(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, asr::g_mha_cta, sizeof(long long) * 2048 * 5);
 }
 #endif
 

@@ -1,4 +1,6 @@
-"""Data-parallel training plumbing: one process per GPU, gradients only over NCCL.
+"""Data-parallel training plumbing: one process per GPU, gradients only - over NVLink / NVSwitch peer memory with this
+package's own all-reduce kernel (`PeerAllReduce`, csrc/allreduce.cu) where the box offers symmetric memory, over NCCL
+otherwise.
 
 The hot-path kernels have no cross-utterance coupling: every rank runs
 them on its own utterances and the only exchange per step is the parameter-gradient
@@ -12,6 +14,8 @@ Loss normalisation note: `ctc_loss`, the quantity loss and the CE are local-batc
 means; averaging gradients over ranks equals the global-batch gradient when every
 rank holds the same number of utterances / tokens (true for the synthetic configs).
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -117,6 +121,79 @@ class GradAllReduce:
     def remove(self):
         for h in self._hooks:
             h.remove()
+
+
+class PeerAllReduce:
+    """One flat fp32 gradient buffer in SYMMETRIC memory, averaged over the ranks by this package's kernel
+    (`asr_allreduce_mean_f32`: NVSwitch multicast load-reduce + broadcast store, or plain peer loads / stores when the box
+    has no multicast objects).  torch.distributed._symmetric_memory is used for what it is: the allocator and the exchange
+    of the peer / multicast handles; no collective of torch or NCCL runs on the data.
+
+        ar = PeerAllReduce(n_floats, device)          # collective: every rank of the group calls it
+        ar.flat[...]                                  # the bucket (gradients accumulate here)
+        ar.launch()                                   # on a side stream behind the current one; returns at once
+        ar.wait()                                     # the current stream waits for the reduced values
+
+    `available()` tells whether this process group / device can do it; GradAllReduce falls back to NCCL otherwise.
+    """
+
+    CTAS = 32
+
+    @staticmethod
+    def available(device=None):
+        if not (dist.is_available() and dist.is_initialized() and torch.cuda.is_available()):
+            return False
+        if dist.get_backend() != "nccl":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem  # noqa: F401
+        except Exception:
+            return False
+        return True
+
+    def __init__(self, numel, device, process_group=None, ctas=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.group = process_group if process_group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.ctas = int(ctas or self.CTAS)
+        self.numel = int(numel)
+        padded = (self.numel + 3) // 4 * 4
+        flag_words = _lib.lib().asr_allreduce_signal_bytes(self.world, self.ctas) // 4
+        with torch.cuda.device(device):
+            self._buf = symm_mem.empty(padded, dtype=torch.float32, device=device)
+            self._flags = symm_mem.empty(max(flag_words, 4), dtype=torch.int32, device=device)
+            self._buf.zero_()
+            self._flags.zero_()
+            torch.cuda.synchronize()
+            self._h = symm_mem.rendezvous(self._buf, self.group)
+            self._hf = symm_mem.rendezvous(self._flags, self.group)
+            self.stream = torch.cuda.Stream(device=device)
+        self.flat = self._buf[:self.numel]
+        self.multicast = int(self._h.multicast_ptr or 0)
+        dist.barrier(self.group)            # every rank's flags are zero before anybody's first launch raises one
+        self._done = torch.cuda.Event()
+
+    def launch(self, offset=0, numel=None):
+        """Average elements [offset, offset + numel) (multiples of 4) over the ranks, on the side stream, behind everything the
+        current stream has queued so far."""
+        n = (self.numel + 3) // 4 * 4 - offset if numel is None else int(numel)
+        cur = torch.cuda.current_stream(self._buf.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.device(self._buf.device):
+            self._lib.check(self._lib.lib().asr_allreduce_mean_f32(
+                ctypes.c_void_p(int(self._h.buffer_ptrs_dev)), ctypes.c_void_p(self.multicast or None),
+                ctypes.c_void_p(int(self._hf.buffer_ptrs_dev)), self.rank, self.world, int(offset), n, self.ctas,
+                ctypes.c_void_p(self.stream.cuda_stream)), "asr_allreduce_mean_f32")
+        self._done.record(self.stream)
+
+    def wait(self):
+        torch.cuda.current_stream(self._buf.device).wait_event(self._done)
+
+    def flavour(self):
+        return "nvswitch multicast (multimem.ld_reduce / multimem.st)" if self.multicast else "peer loads / stores"
 
 
 def shard_utterances(n_utts, rank=None, world=None):

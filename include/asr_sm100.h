@@ -400,6 +400,22 @@ int asr_mha_probs_f32(const void* q, const void* k,
                       int B, int Hh, int Lq, int Lk, int D, float scale,
                       float* attn, void* stream);
 
+/* ---- gradient all-reduce over NVLink / NVSwitch peer memory ----------------------------------------
+ * The data-parallel wrapper of the training loop (/root/reference/src/transformer/solver.py:141-161 is the single-GPU loop
+ * it wraps) averages the fp32 gradient buckets over the ranks.  Every rank calls this on its own stream with the same
+ * (offset, n, ctas); the bucket lives in symmetric memory:
+ *   peer_ptrs_dev    device array [world] of the bucket's base address in every rank, as mapped in THIS process
+ *   multicast_ptr    the bucket's multicast address (NVSwitch multicast object), or NULL: without it the kernel reads
+ *                    and writes the peer mappings directly
+ *   signal_ptrs_dev  device array [world] of every rank's flag area (uint32, zero-initialised,
+ *                    asr_allreduce_signal_bytes(world, ctas) bytes), as mapped in this process
+ * In place: on return (stream order) elements [offset, offset + n) of EVERY rank's bucket hold the mean over the ranks.
+ * offset and n in floats, multiples of 4.  ctas: thread blocks (1..128) - the kernel is bound by the links, a few dozen
+ * suffice and leave the SMs to the kernels it overlaps with. */
+size_t asr_allreduce_signal_bytes(int world, int ctas);
+int asr_allreduce_mean_f32(const void* peer_ptrs_dev, void* multicast_ptr, const void* signal_ptrs_dev,
+                           int rank, int world, size_t offset, size_t n, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,8 +15,8 @@ MHA = load_golden("mha")
 CASES = ["self_pad", "self_causal", "cross", "nomask"]
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (3, 2), (21, 0)],
-                ids=["auto", "one_tile_kernel_bwd8w", "two_tile_kernel"])
+@pytest.fixture(autouse=True, params=[(0, 0), (3, 2), (21, 0), (40, 0)],
+                ids=["auto", "one_tile_kernel_bwd8w", "two_tile_kernel", "persistent_two_tile_kernel"])
 def fwd_variant(request):
     """The two forward kernels (auto picks by shape / dropout; 3 = always one 128-query tile per CTA, two threads per
     row; 21 = always two tiles per CTA, one thread per row) and the softmax-backward warp groups (16 warps by default,
@@ -324,6 +324,32 @@ def test_long_sequence_microbench_shape(causal):
     ref.backward(g)
     for got, want in zip((qr, kr, vr), ref_in):
         _close(got.grad, want.grad, tol=3e-2)
+
+
+@pytest.mark.parametrize("B,L,H,causal", [(16, 700, 8, False), (5, 1200, 8, True), (40, 300, 4, False), (3, 2048, 8, True)])
+def test_persistent_kernel_is_bitwise_the_two_tile_kernel(B, L, H, causal):
+    """The persistent forward kernel walks several (batch, head, 256-query) items per CTA - Q double-buffered, the next
+    item's first product issued under the current item's last block, the epilogue deferred behind the next item's first
+    block.  Same arithmetic in the same order as the one-item-per-CTA kernel: outputs and log-sum-exps must be
+    bit-identical, on shapes with more items than SMs (2.6, 1.4, 2.2 items per CTA), ragged key lengths, a query tile
+    that is half empty (L % 256 <= 128: items with ONE tile) and the causal mask (tiles of one item with different
+    numbers of key blocks)."""
+    lib = pkg("_lib")
+    q, k, v = _rand_qkv(B, L, L, H, seed=91, std=0.7)
+    g = torch.Generator().manual_seed(92)
+    kv_len = torch.randint(L // 3, L + 1, (B,), generator=g).to(torch.int32).cuda()
+    outs = []
+    for variant in (21, 40):
+        lib.set_option("mha_variant", variant)
+        out = torch.full_like(q, float("nan"))
+        lse = torch.full((B, H, L), float("nan"), device="cuda")
+        lib.check(lib.lib().asr_mha_fwd_bf16(lib.ptr(q), lib.ptr(k), lib.ptr(v), lib.ptr(kv_len), None, int(causal), B, H, L, L, 64,
+                                             0.125, lib.ptr(out), lib.ptr(lse), lib.stream_ptr()), "asr_mha_fwd_bf16")
+        outs.append((out, lse))
+    torch.cuda.synchronize()
+    assert torch.isfinite(outs[1][0].float()).all() and torch.isfinite(outs[1][1]).all()
+    assert torch.equal(outs[0][0].view(torch.int16), outs[1][0].view(torch.int16))
+    assert torch.equal(outs[0][1], outs[1][1])
 
 
 def test_broadcastable_masks_are_expanded_and_bad_shapes_rejected():

@@ -23,7 +23,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t addr) {
     return d;
 }
 constexpr int NP = 16;
-__global__ void probe(float* out, long long* cyc, int iw, int g, int groups, int iters, float cc, float mm) {
+__global__ void probe(float* out, long long* cyc, int iw, int g, int groups, int iters, float cc, float mm, int wait_mode) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base;
@@ -53,8 +53,14 @@ __global__ void probe(float* out, long long* cyc, int iw, int g, int groups, int
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
                 uint32_t ok = 0;
-                while (!ok)
-                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(it & 1), "r"(200000u) : "memory");
+                while (!ok) {
+                    if (wait_mode == 0)
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(it & 1), "r"(200000u) : "memory");
+                    else if (wait_mode == 1)
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(it & 1) : "memory");
+                    else
+                        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&bar)), "r"(it & 1) : "memory");
+                }
             }
             issued_cyc = clock64() - t0;
             cyc[1] = issued_cyc;
@@ -95,17 +101,20 @@ int main() {
     cudaMalloc(&out, 1 << 20); cudaMalloc(&cyc, 64);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     const int iters = 1024;   // worker: 1024 * 16 pairs * ~21 cycles = 344 k cycles
-    struct { int iw, g, groups; const char* name; } cases[] = {
-        {0, 0, 0, "no issuer"},
-        {4, 4, 1500, "issuer on the worker's sub-partition, groups of 4"},
-        {5, 4, 1500, "issuer on another sub-partition, groups of 4"},
-        {4, 12, 500, "same sub-partition, groups of 12"},
-        {5, 12, 500, "other sub-partition, groups of 12"},
-        {4, 1, 4000, "same sub-partition, groups of 1"},
+    struct { int iw, g, groups; const char* name; int wm; } cases[] = {
+        {0, 0, 0, "no issuer", 0},
+        {4, 4, 1500, "issuer on the worker's sub-partition, groups of 4", 0},
+        {5, 4, 1500, "issuer on another sub-partition, groups of 4", 0},
+        {4, 12, 500, "same sub-partition, groups of 12", 0},
+        {5, 12, 500, "other sub-partition, groups of 12", 0},
+        {4, 1, 4000, "same sub-partition, groups of 1", 0},
+        {4, 1, 4000, "groups of 1, plain try_wait", 1},
+        {4, 1, 4000, "groups of 1, test_wait spin", 2},
+        {5, 1, 4000, "groups of 1, test_wait spin, other sub-partition", 2},
     };
     for (auto& c : cases) {
         long long h[2] = {0, 0};
-        for (int rep = 0; rep < 2; ++rep) { cudaMemset(cyc, 0, 64); probe<<<1, 256, 65536>>>(out, cyc, c.iw, c.g, c.groups, iters, 0.18f, -0.5f); cudaDeviceSynchronize(); }
+        for (int rep = 0; rep < 2; ++rep) { cudaMemset(cyc, 0, 64); probe<<<1, 256, 65536>>>(out, cyc, c.iw, c.g, c.groups, iters, 0.18f, -0.5f, c.wm); cudaDeviceSynchronize(); }
         cudaMemcpy(h, cyc, 16, cudaMemcpyDeviceToHost);
         printf("%-52s worker cycles per pair = %.2f   issuer: %lld cycles for %d MMAs (%.1f per MMA)\n", c.name, (double)h[0] / (iters * (double)NP), h[1], c.g * c.groups, c.g ? (double)h[1] / (c.g * c.groups) : 0.0);
     }
