@@ -85,6 +85,8 @@ def parse_args():
     ap.add_argument("--no-extras", action="store_true", help="skip the microbenches, the sweep and the full-model steps")
     ap.add_argument("--no-graph", action="store_true", help="full-model steps: eager launches instead of a CUDA graph")
     ap.add_argument("--no-allreduce", action="store_true", help="hot-path step without the gradient all-reduce (N > 1)")
+    ap.add_argument("--allreduce", default="auto", choices=["auto", "peer", "nccl"],
+                    help="gradient all-reduce of the hot-path step at N > 1: this package's peer-memory kernel or NCCL buckets")
     ap.add_argument("--allreduce-at", default="rows", choices=["rows", "start", "end"],
                     help="where the hot-path step launches its gradient all-reduce: behind the CTC row pass (default), at the "
                          "start of the step, or after the last kernel (no overlap) - for measuring the overlap")
@@ -204,25 +206,52 @@ def cif_model_param_count(w):
 
 
 class GradBuckets:
-    """fp32 gradient buckets of the reference recipe's CIF_Model (25 MB each, like dp.GradAllReduce) and their NCCL
-    all-reduce.  The hot-path step stands for the model's backward pass here, so the buckets hold synthetic gradients;
-    their size, count and the collective are those of the real training step (bench.py --workload train runs it)."""
+    """The fp32 gradients of the reference recipe's CIF_Model and their all-reduce (mean).  The hot-path step stands for
+    the model's backward pass here, so the buffer holds synthetic gradients; its size and the collective are those of the
+    real training step (bench.py --workload train runs it).
+    backend "peer": one symmetric-memory buffer, averaged by this package's kernel over NVLink peer memory
+    (dp.PeerAllReduce -> asr_allreduce_mean_f32); "nccl": 25 MB buckets, one NCCL all-reduce each (round 2's first
+    version, and the fallback when symmetric memory is not available)."""
 
-    def __init__(self, n_params, device, world, bucket_mb=25.0):
+    def __init__(self, n_params, device, world, backend="auto", bucket_mb=25.0):
         self.world = world
-        per = int(bucket_mb * 1024 * 1024) // 4
-        sizes = [per] * (n_params // per) + ([n_params % per] if n_params % per else [])
-        g = torch.Generator(device=device).manual_seed(99)
-        self.flat = [torch.randn(n, device=device, generator=g) * 1e-3 for n in sizes]
         self.bytes = 4 * n_params
+        self.n_params = n_params
+        dp = pkg("dp")
+        if backend == "auto":
+            backend = "peer" if (world > 1 and dp.PeerAllReduce.available(device)) else "nccl"
+        self.backend = backend
+        g = torch.Generator(device=device).manual_seed(99)
         self.handles = []
+        if backend == "peer":
+            self.peer = dp.PeerAllReduce(n_params, device)
+            self.peer.flat.copy_(torch.randn(n_params, device=device, generator=g) * 1e-3)
+            self.flat = [self.peer.flat]
+            self.how = ("this package's all-reduce kernel over NVLink peer memory (asr_allreduce_mean_f32, %s, %d CTAs; "
+                        "torch symmetric memory only allocates and exchanges the handles), one launch over the %d fp32 "
+                        "gradients of the recipe's CIF_Model" % (self.peer.flavour(), self.peer.ctas, n_params))
+        else:
+            self.peer = None
+            per = int(bucket_mb * 1024 * 1024) // 4
+            sizes = [per] * (n_params // per) + ([n_params % per] if n_params % per else [])
+            self.flat = [torch.randn(n, device=device, generator=g) * 1e-3 for n in sizes]
+            self.how = ("NCCL all-reduce (mean) of %d fp32 gradient buckets = the %d parameters of the recipe's CIF_Model"
+                        % (len(self.flat), n_params))
 
     def launch(self):
         import torch.distributed as dist
-        if self.world > 1:
+        if self.world <= 1:
+            return
+        if self.peer is not None:
+            self.peer.launch()
+        else:
             self.handles = [dist.all_reduce(f, op=dist.ReduceOp.AVG, async_op=True) for f in self.flat]
 
     def wait(self):
+        if self.peer is not None:
+            if self.world > 1:
+                self.peer.wait()  # stream-level: the compute stream waits for the side stream, the host does not
+            return
         for h in self.handles:
             h.wait()          # stream-level: the compute stream waits for NCCL, the host does not
         self.handles = []
@@ -961,7 +990,7 @@ def main():
         lib.set_option(key, int(val))
     inp = make_inputs(w, device, 1236 + rank)
     n_params = cif_model_param_count(w)
-    buckets = GradBuckets(n_params, device, world) if (world > 1 and not args.no_allreduce) else None
+    buckets = GradBuckets(n_params, device, world, args.allreduce) if (world > 1 and not args.no_allreduce) else None
     hp = HotPath(w, inp, buckets, args.allreduce_at)
     K, W = args.steps, max(args.warmup, 3)
 
@@ -1170,11 +1199,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload=args.workload, **w, L=L_out, valid_frames=valid_frames,
                            grad_allreduce_bytes_per_step=(buckets.bytes if buckets is not None else 0),
-                           grad_allreduce=("NCCL all-reduce (mean) of %d fp32 gradient buckets = the %d parameters of the recipe's "
-                                           "CIF_Model, launched behind the CTC row pass, waited for at the end of every timed step"
-                                           % (len(buckets.flat), n_params)) if buckets is not None else
-                                          "none at N = 1 (one rank: nothing to exchange)",
-                           parallelism="dp%d by utterance; gradients only over NCCL" % world,
+                           grad_allreduce=(buckets.how + ", launched behind the CTC row pass, waited for at the end of every timed step")
+                                          if buckets is not None else "none at N = 1 (one rank: nothing to exchange)",
+                           parallelism="dp%d by utterance; gradients only over NVLink" % world,
                            schedule="serial, one stream" if args.serial else
                            "one stream; CTC begin (rows + lattices on library streams) / CIF pair (forward: kernel hint 3) / CTC finish (apply)",
                            l2="inputs (%.1f GB logits + %.1f GB hidden per GPU) exceed the 126 MB L2; no flush needed" % (

@@ -20,13 +20,12 @@
 // final: they were written by earlier kernels of each rank's stream) and once after the last store (nobody leaves - and
 // lets its stream overwrite the bucket - before every rank has written its slice everywhere).
 // Few CTAs on purpose: the kernel runs next to HBM-bound kernels of the training step and is bound by the links, not by
-// the SMs; `ctas` x 512 threads x 4 x 16 bytes are in flight.
+// the SMs; `ctas` x 512 threads x 8 (multicast) or 16 (peer flavour) x 16 bytes are in flight.
 #include "common.cuh"
 
 namespace asr {
 
 constexpr int kArThreads = 512;
-constexpr int kArUnroll = 4;
 
 __device__ __forceinline__ void flag_raise(uint32_t* addr) {
     // 0 -> 1, waiting for the previous round's flag to be consumed; release: this rank's earlier writes are visible first
@@ -79,48 +78,69 @@ struct AllReduceArgs {
     float scale;                // 1 / world
 };
 
-template <bool kMulticast>
+// kUnroll 16-byte elements per thread and pass; the peer flavour reads each of them from kWorld buffers (kWorld = 0: any
+// number of ranks, one element per pass), so kUnroll * kWorld loads are in flight per thread - the links want megabytes in
+// flight (measured on two B200s, 209 MB: 16 CTAs x 512 threads x 8 loads 2.4 ms, 128 CTAs 0.40 ms).
+template <bool kMulticast, int kWorld, int kUnroll>
 __global__ void __launch_bounds__(kArThreads) allreduce_mean_kernel(const AllReduceArgs a) {
     ranks_barrier(a.pads, a.rank, a.world, 0);
+    const int world = kWorld > 0 ? kWorld : a.world;
     // this rank's slice, in float4 units
-    const size_t per = (a.n4 + a.world - 1) / a.world;
+    const size_t per = (a.n4 + world - 1) / world;
     const size_t lo = a.off4 + min(a.n4, per * (size_t)a.rank);
     const size_t hi = a.off4 + min(a.n4, per * (size_t)a.rank + per);
     const size_t stride = (size_t)gridDim.x * kArThreads;
-    for (size_t i0 = lo + (size_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += stride * kArUnroll) {
-        float4 v[kArUnroll];
+    for (size_t i0 = lo + (size_t)blockIdx.x * kArThreads + threadIdx.x; i0 < hi; i0 += stride * kUnroll) {
+        float4 v[kUnroll];
         if (kMulticast) {
 #pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const size_t i = i0 + u * stride;
                 if (i < hi) v[u] = multimem_ld_reduce_add(a.mc + 4 * i);
             }
 #pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const size_t i = i0 + u * stride;
                 if (i < hi) {
                     v[u].x *= a.scale; v[u].y *= a.scale; v[u].z *= a.scale; v[u].w *= a.scale;
                     multimem_st(a.mc + 4 * i, v[u]);
                 }
             }
-        } else {
+        } else if (kWorld > 0) {
+            float4 w[kUnroll][kWorld > 0 ? kWorld : 1];
 #pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const size_t i = i0 + u * stride;
-                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < hi) {
-                    for (int p = 0; p < a.world; ++p) {       // rank order: the same sum on every run
-                        const float4 w = __ldcg(reinterpret_cast<const float4*>(a.peers[p]) + i);
-                        v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
-                    }
-                }
+#pragma unroll
+                for (int p = 0; p < kWorld; ++p)
+                    if (i < hi) w[u][p] = __ldcg(reinterpret_cast<const float4*>(a.peers[p]) + i);
             }
 #pragma unroll
-            for (int u = 0; u < kArUnroll; ++u) {
+            for (int u = 0; u < kUnroll; ++u) {
                 const size_t i = i0 + u * stride;
                 if (i < hi) {
-                    v[u].x *= a.scale; v[u].y *= a.scale; v[u].z *= a.scale; v[u].w *= a.scale;
-                    for (int p = 0; p < a.world; ++p) __stcg(reinterpret_cast<float4*>(a.peers[p]) + i, v[u]);
+                    float4 t = w[u][0];
+#pragma unroll
+                    for (int p = 1; p < kWorld; ++p) {         // rank order: the same sum on every rank and run
+                        t.x += w[u][p].x; t.y += w[u][p].y; t.z += w[u][p].z; t.w += w[u][p].w;
+                    }
+                    t.x *= a.scale; t.y *= a.scale; t.z *= a.scale; t.w *= a.scale;
+#pragma unroll
+                    for (int p = 0; p < kWorld; ++p) __stcg(reinterpret_cast<float4*>(a.peers[p]) + i, t);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const size_t i = i0 + u * stride;
+                if (i < hi) {
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int p = 0; p < world; ++p) {
+                        const float4 w = __ldcg(reinterpret_cast<const float4*>(a.peers[p]) + i);
+                        t.x += w.x; t.y += w.y; t.z += w.z; t.w += w.w;
+                    }
+                    t.x *= a.scale; t.y *= a.scale; t.z *= a.scale; t.w *= a.scale;
+                    for (int p = 0; p < world; ++p) __stcg(reinterpret_cast<float4*>(a.peers[p]) + i, t);
                 }
             }
         }
@@ -156,8 +176,11 @@ extern "C" int asr_allreduce_mean_f32(const void* peer_ptrs_dev, void* multicast
     a.n4 = n / 4;
     a.scale = 1.0f / (float)world;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (multicast_ptr != nullptr) allreduce_mean_kernel<true><<<ctas, kArThreads, 0, st>>>(a);
-    else allreduce_mean_kernel<false><<<ctas, kArThreads, 0, st>>>(a);
+    if (multicast_ptr != nullptr) allreduce_mean_kernel<true, 0, 8><<<ctas, kArThreads, 0, st>>>(a);
+    else if (world == 2) allreduce_mean_kernel<false, 2, 8><<<ctas, kArThreads, 0, st>>>(a);
+    else if (world == 4) allreduce_mean_kernel<false, 4, 4><<<ctas, kArThreads, 0, st>>>(a);
+    else if (world == 8) allreduce_mean_kernel<false, 8, 2><<<ctas, kArThreads, 0, st>>>(a);
+    else allreduce_mean_kernel<false, 0, 2><<<ctas, kArThreads, 0, st>>>(a);
     ASR_LAUNCH_CHECK();
     return 0;
 }

@@ -15,6 +15,7 @@ means; averaging gradients over ranks equals the global-batch gradient when ever
 rank holds the same number of utterances / tokens (true for the synthetic configs).
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -40,9 +41,12 @@ class GradAllReduce:
     are already reduced).  Collectives are issued in a fixed bucket order on every rank.
     """
 
-    def __init__(self, module, bucket_mb=25.0, process_group=None, overlap=True):
+    def __init__(self, module, bucket_mb=25.0, process_group=None, overlap=True, backend="auto"):
         """overlap=False registers no hooks: every bucket is all-reduced from finish().  That is the mode for a backward
-        pass replayed from a CUDA graph (hooks only run while the graph is being captured, not when it is replayed)."""
+        pass replayed from a CUDA graph (hooks only run while the graph is being captured, not when it is replayed).
+        backend: "peer" = the buckets are ranges of ONE symmetric-memory buffer, averaged by this package's kernel over
+        NVLink peer memory (PeerAllReduce; fp32 parameters on one device); "nccl" = one NCCL all-reduce per bucket;
+        "auto" = peer when the process group, the device and the parameters allow it."""
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
         params = [p for p in module.parameters() if p.requires_grad]
@@ -50,25 +54,48 @@ class GradAllReduce:
         self.buckets = []          # (flat buffer, [params])
         self._owner = {}
         cap = int(bucket_mb * 1024 * 1024)
+        uniform = bool(params) and all(p.dtype == torch.float32 and p.device == params[0].device and p.is_cuda for p in params)
+        if backend == "auto":
+            backend = "peer" if (self.world > 1 and uniform and PeerAllReduce.available(params[0].device)) else "nccl"
+        if backend == "peer" and not uniform:
+            raise ValueError("GradAllReduce(backend='peer') needs fp32 parameters on one CUDA device")
+        self.backend = backend
+        groups = []
         cur, cur_bytes = [], 0
         # reverse order: the last layers' gradients are ready first
         for p in reversed(params):
             nbytes = p.numel() * p.element_size()
             if cur and (cur_bytes + nbytes > cap or p.dtype != cur[0].dtype or p.device != cur[0].device):
-                self._seal(cur)
+                groups.append(cur)
                 cur, cur_bytes = [], 0
             cur.append(p)
             cur_bytes += nbytes
         if cur:
-            self._seal(cur)
+            groups.append(cur)
+        self.peer = None
+        self._ranges = []          # peer backend: (offset, padded length) of every bucket inside the symmetric buffer
+        if backend == "peer":
+            pad4 = lambda n: (n + 3) // 4 * 4
+            total = sum(pad4(sum(p.numel() for p in g)) for g in groups)
+            self.peer = PeerAllReduce(total, params[0].device, process_group)
+            off = 0
+            for g in groups:
+                n = sum(p.numel() for p in g)
+                self._ranges.append((off, pad4(n)))
+                self._seal(g, self.peer.flat[off:off + n])
+                off += pad4(n)
+        else:
+            for g in groups:
+                self._seal(g)
         self._pending = [0] * len(self.buckets)
         self._handles = []
         self._next = 0             # buckets are all-reduced strictly in index order on every rank
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params] if overlap else []
         self.reset()
 
-    def _seal(self, plist):
-        flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
+    def _seal(self, plist, flat=None):
+        if flat is None:
+            flat = torch.zeros(sum(p.numel() for p in plist), dtype=plist[0].dtype, device=plist[0].device)
         off = 0
         for p in plist:
             p.grad = flat[off:off + p.numel()].view_as(p)      # gradient lives inside the bucket
@@ -91,7 +118,17 @@ class GradAllReduce:
         while self._next < len(self.buckets) and (force or self._pending[self._next] == 0):
             flat = self.buckets[self._next][0]
             if self.world > 1:
-                self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
+                if self.peer is not None:
+                    if force and self._next == 0:
+                        # nothing has gone out yet (graph replay, or finish() right after backward): one launch for all
+                        self.peer.launch()
+                        self._next = len(self.buckets)
+                        self._handles.append((None, None))
+                        return
+                    self.peer.launch(*self._ranges[self._next])
+                    self._handles.append((None, None))
+                else:
+                    self._handles.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat))
             self._next += 1
 
     def _on_grad(self, p):
@@ -107,9 +144,13 @@ class GradAllReduce:
     def finish(self):
         """Wait for the outstanding all-reduces and turn the sums into means."""
         self._launch_ready(force=True)      # buckets with a parameter that got no gradient this step go out here
-        for h, flat in self._handles:
-            h.wait()
-            flat.div_(self.world)
+        if self.peer is not None:
+            if self._handles:
+                self.peer.wait()           # the kernel writes means: nothing to divide
+        else:
+            for h, flat in self._handles:
+                h.wait()
+                flat.div_(self.world)
         for i, (_, plist) in enumerate(self.buckets):
             self._pending[i] = len(plist)
         self._handles = []
@@ -151,7 +192,9 @@ class PeerAllReduce:
             return False
         return True
 
-    def __init__(self, numel, device, process_group=None, ctas=None):
+    def __init__(self, numel, device, process_group=None, ctas=None, multicast=None):
+        """multicast: None = by world size (bytes per link and direction for n gradient bytes: multicast n (1 + 1/W), peer
+        loads / stores 2 n (W - 1) / W - the switch wins from four ranks on), True / False to force a flavour."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
@@ -173,6 +216,12 @@ class PeerAllReduce:
             self.stream = torch.cuda.Stream(device=device)
         self.flat = self._buf[:self.numel]
         self.multicast = int(self._h.multicast_ptr or 0)
+        if multicast is None and os.environ.get("ASR_ALLREDUCE_MULTICAST") in ("0", "1"):     # measurement override
+            multicast = os.environ["ASR_ALLREDUCE_MULTICAST"] == "1"
+        if multicast is False or (multicast is None and self.world < 4):
+            self.multicast = 0
+        if multicast is True and not self.multicast:
+            raise RuntimeError("PeerAllReduce: this box offers no multicast address for symmetric memory")
         dist.barrier(self.group)            # every rank's flags are zero before anybody's first launch raises one
         self._done = torch.cuda.Event()
 
