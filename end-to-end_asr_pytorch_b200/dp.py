@@ -193,8 +193,11 @@ class PeerAllReduce:
         return True
 
     def __init__(self, numel, device, process_group=None, ctas=None, multicast=None):
-        """multicast: None = by world size (bytes per link and direction for n gradient bytes: multicast n (1 + 1/W), peer
-        loads / stores 2 n (W - 1) / W - the switch wins from four ranks on), True / False to force a flavour."""
+        """multicast: False / None = peer loads and stores, True = the NVSwitch multicast flavour.  Bytes per link and
+        direction for n gradient bytes: multicast n (1 + 1/W), peer 2 n (W - 1) / W.  Measured on B200 (209 MB): at two
+        ranks the peer flavour wins outright (0.39 vs 0.60 ms); at eight the multicast flavour is faster alone (0.52 vs
+        0.65 ms; NCCL 0.60) but disturbs the HBM-bound kernels it overlaps with more (hot-path step 3.23 vs 3.10 ms), so the
+        peer flavour is the default.  ASR_ALLREDUCE_MULTICAST=0/1 overrides None."""
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self._lib = _lib
@@ -218,7 +221,7 @@ class PeerAllReduce:
         self.multicast = int(self._h.multicast_ptr or 0)
         if multicast is None and os.environ.get("ASR_ALLREDUCE_MULTICAST") in ("0", "1"):     # measurement override
             multicast = os.environ["ASR_ALLREDUCE_MULTICAST"] == "1"
-        if multicast is False or (multicast is None and self.world < 4):
+        if not multicast:
             self.multicast = 0
         if multicast is True and not self.multicast:
             raise RuntimeError("PeerAllReduce: this box offers no multicast address for symmetric memory")
