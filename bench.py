@@ -12,9 +12,9 @@ data-parallel gradient exchange of that training step:
     CTC loss + gradient on the logits [B,T,V]                  (a4: K1 row pass, K2 lattice, K3 sparse update)
     CIF forward on the encoder frames [B,T,H] + quantity term  (a1-a3)
     CIF backward                                               (a2')
-    NCCL all-reduce (mean) of the model's fp32 gradient buckets: the 52.3 M parameters of the reference recipe's
-    CIF_Model = 209 MB in 25 MB buckets, launched behind the CTC row pass (from where gradients exist) and waited for
-    at the end of the step
+    all-reduce (mean) of the model's fp32 gradients - the 52.3 M parameters of the reference recipe's CIF_Model = 209 MB -
+    by this package's kernel over NVLink peer memory (csrc/allreduce.cu; NCCL in 25 MB buckets is the fallback and
+    `--allreduce nccl`), launched behind the CTC row pass (from where gradients exist), waited for at the end of the step
 
 Shape = the largest one of BASELINE config 2 (CTC sweep: B=256, T=1600, S=80, V=4233) with the CIF layer of config 4
 run on the same batch (H=512).  Every rank processes its own batch (data parallel by utterance, weak scaling).
@@ -29,7 +29,7 @@ The JSON line carries:
   cpu_baseline   the reference's own CPU path on a bounded sample of the same workload, on this box's host cores
   self_check     outputs of the timed (overlapped) schedule compared bit for bit with the serial schedule after the loop
   ctc_sweep      BASELINE config 2: whole-call CTC GB/s at the sweep shapes
-  train_step     BASELINE config 5: the whole CIF_Model trained data parallel (CUDA-graph step, NCCL all-reduce)
+  train_step     BASELINE config 5: the whole CIF_Model trained data parallel (CUDA-graph step, gradient all-reduce)
   transformer_step  BASELINE config 3: SpeechTransformer 6+6 bf16 training step
 `--impl reference` times the reference's CPU path (rank 0), `--impl reference-gpu` the reference's eager-GPU path
 (its Python CIF loop, ATen ctc_loss) on cuda:0, both in the same JSON shape.  The reference modules are the unmodified
@@ -218,25 +218,32 @@ class GradBuckets:
         self.bytes = 4 * n_params
         self.n_params = n_params
         dp = pkg("dp")
+        self.peer, fallback = None, ""
         if backend == "auto":
             backend = "peer" if (world > 1 and dp.PeerAllReduce.available(device)) else "nccl"
+            if backend == "peer":
+                # a box without peer access / symmetric memory: every rank fails alike and takes NCCL
+                try:
+                    self.peer = dp.PeerAllReduce(n_params, device)
+                except Exception as e:      # noqa: BLE001
+                    backend, fallback = "nccl", " (symmetric memory unavailable: %s)" % str(e)[:80]
         self.backend = backend
         g = torch.Generator(device=device).manual_seed(99)
         self.handles = []
         if backend == "peer":
-            self.peer = dp.PeerAllReduce(n_params, device)
+            if self.peer is None:
+                self.peer = dp.PeerAllReduce(n_params, device)
             self.peer.flat.copy_(torch.randn(n_params, device=device, generator=g) * 1e-3)
             self.flat = [self.peer.flat]
             self.how = ("this package's all-reduce kernel over NVLink peer memory (asr_allreduce_mean_f32, %s, %d CTAs; "
                         "torch symmetric memory only allocates and exchanges the handles), one launch over the %d fp32 "
                         "gradients of the recipe's CIF_Model" % (self.peer.flavour(), self.peer.ctas, n_params))
         else:
-            self.peer = None
             per = int(bucket_mb * 1024 * 1024) // 4
             sizes = [per] * (n_params // per) + ([n_params % per] if n_params % per else [])
             self.flat = [torch.randn(n, device=device, generator=g) * 1e-3 for n in sizes]
-            self.how = ("NCCL all-reduce (mean) of %d fp32 gradient buckets = the %d parameters of the recipe's CIF_Model"
-                        % (len(self.flat), n_params))
+            self.how = ("NCCL all-reduce (mean) of %d fp32 gradient buckets = the %d parameters of the recipe's CIF_Model%s"
+                        % (len(self.flat), n_params, fallback))
 
     def launch(self):
         import torch.distributed as dist
@@ -322,7 +329,7 @@ class HotPath:
         """One hot-path pass the way the library is meant to be driven: one stream, the CTC call in its two phases with
         the CIF forward/backward pair queued in between, where it runs next to the last slice's latency-bound lattice.
         The gradient all-reduce of the training step (N > 1) goes out behind the CTC row pass - the point of the step
-        from which gradients exist (the row pass writes the dense part of d loss / d logits) - runs on NCCL's stream next
+        from which gradients exist (the row pass writes the dense part of d loss / d logits) - runs on a side stream next
         to the lattices, the CIF pair and the apply pass, and is waited for at the end of the step.
         ev = (before, after): CUDA events around the row kernels (all slices; they are the only work begin puts on this
         stream), i.e. the dominant kernel timed inside the timed region."""
@@ -848,7 +855,8 @@ def run_train(args, wname, rank, world, device, steps=None, emit=True, tf32=Fals
                 "config": dict(workload=wname, model=model_name, params=n_params, grad_allreduce_bytes=sync.grad_bytes(), **w,
                                launch="CUDA graph of forward + backward, then bucket all-reduce + fused Adam" if graph else
                                "eager launches, all-reduce overlapped from gradient hooks",
-                               parallelism="dp%d by utterance, NCCL gradient all-reduce inside every timed step" % world,
+                               parallelism="dp%d by utterance, gradient all-reduce (%s) inside every timed step" % (
+                                   world, "this package's peer-memory kernel" if getattr(sync, "peer", None) is not None else "NCCL"),
                                note="training mode: attention-probability dropout 0.1 applied inside the tcgen05 kernels"),
                 "clocks": clocks,
                 "e2e": {"value": world * w["B"] * Ke / float(dt.item()), "unit": UNIT,

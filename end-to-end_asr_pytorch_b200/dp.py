@@ -55,7 +55,8 @@ class GradAllReduce:
         self._owner = {}
         cap = int(bucket_mb * 1024 * 1024)
         uniform = bool(params) and all(p.dtype == torch.float32 and p.device == params[0].device and p.is_cuda for p in params)
-        if backend == "auto":
+        auto = backend == "auto"
+        if auto:
             backend = "peer" if (self.world > 1 and uniform and PeerAllReduce.available(params[0].device)) else "nccl"
         if backend == "peer" and not uniform:
             raise ValueError("GradAllReduce(backend='peer') needs fp32 parameters on one CUDA device")
@@ -77,7 +78,14 @@ class GradAllReduce:
         if backend == "peer":
             pad4 = lambda n: (n + 3) // 4 * 4
             total = sum(pad4(sum(p.numel() for p in g)) for g in groups)
-            self.peer = PeerAllReduce(total, params[0].device, process_group)
+            try:
+                self.peer = PeerAllReduce(total, params[0].device, process_group)
+            except Exception:           # noqa: BLE001  (no peer access on this box: every rank fails alike)
+                if auto:
+                    backend = self.backend = "nccl"
+                else:
+                    raise
+        if backend == "peer":
             off = 0
             for g in groups:
                 n = sum(p.numel() for p in g)
