@@ -649,7 +649,8 @@ def attention_microbench(device, peaks, iters=5):
         return t_f, t_b, 4.0 * H * 64 * pairs, 10.0 * H * 64 * pairs
 
     for name, kw in (("L=2048", {}), ("L=2048 dropout 0.1", dict(drop=0.1)), ("L=2048 causal + key padding", dict(causal=1, ragged=True)),
-                     ("L=4096", dict(Lq=4096, B=8))):
+                     ("L=4096", dict(Lq=4096, B=8)), ("L=512 (persistent forward kernel)", dict(Lq=512, B=64)),
+                     ("L=1024 (persistent forward kernel)", dict(Lq=1024, B=32))):
         B, Lq = kw.pop("B", 16), kw.pop("Lq", 2048)
         t_f, t_b, ff, fb = run(B, Lq, Lq, 8, **kw)
         out["shapes"].append({"shape": "B=%d heads=8 %s d=64 bf16" % (B, name), "fwd_ms": t_f, "bwd_ms": t_b,

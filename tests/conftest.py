@@ -13,6 +13,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_sanitize: runs a slice of the GPU suite under compute-sanitizer (slow; -m gpu_sanitize)")
 
 
 def load_golden(name):

@@ -1,0 +1,60 @@
+"""compute-sanitizer over one small call of every kernel family (memcheck: out-of-bounds / misaligned accesses;
+racecheck on the shared-memory pipelines of the CTC lattice).  Slow (the tool serialises and instruments every launch), so it
+has its own marker:  python -m pytest tests -m gpu_sanitize"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu_sanitize
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SANITIZER = shutil.which("compute-sanitizer") or "/usr/local/cuda/bin/compute-sanitizer"
+
+# the smoke entry point (CIF forward / backward, CTC through the reference's entry point, attention forward) plus the
+# kernels it does not reach: attention backward, the persistent forward kernel, the fp32 GEMMs, the one-rank all-reduce
+SCRIPT = r"""
+import importlib, sys, tempfile
+sys.path.insert(0, %r)
+import torch
+import __graft_entry__ as ge
+ge.smoke()
+pkg = importlib.import_module(ge.PKG)
+ops, lib = importlib.import_module(ge.PKG + ".ops"), importlib.import_module(ge.PKG + "._lib")
+g = torch.Generator().manual_seed(3)
+for variant in (21, 40):
+    lib.set_option("mha_variant", variant)
+    q, k, v = (torch.randn(3, 300, 2, 64, generator=g).cuda().to(torch.bfloat16).requires_grad_(True) for _ in range(3))
+    out = ops.mha_core(q, k, v, kv_len=torch.tensor([300, 211, 129], dtype=torch.int32).cuda(), causal=(variant == 40))
+    out.float().square().sum().backward()
+lib.set_option("mha_variant", 0)
+x = torch.randn(200, 96, device="cuda", requires_grad=True)
+w = torch.randn(77, 96, device="cuda", requires_grad=True)
+ops.linear_f32_autograd(x, w, None).square().sum().backward()
+import torch.distributed as dist
+dp = importlib.import_module(ge.PKG + ".dp")
+dist.init_process_group("nccl", store=dist.FileStore(tempfile.mktemp(prefix="asr_san_"), 1), rank=0, world_size=1,
+                        device_id=torch.device("cuda", 0))
+if dp.PeerAllReduce.available(torch.device("cuda", 0)):
+    ar = dp.PeerAllReduce(40004, torch.device("cuda", 0), ctas=4)
+    ar.flat.normal_()
+    ar.launch(); ar.wait()
+torch.cuda.synchronize()
+dist.destroy_process_group()
+print("sanitized run complete")
+""" % ROOT
+
+
+@pytest.mark.parametrize("tool", ["memcheck"])
+def test_kernels_are_clean_under_compute_sanitizer(tool):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    if not os.path.exists(SANITIZER):
+        pytest.skip("compute-sanitizer not installed")
+    out = subprocess.run([SANITIZER, "--tool", tool, "--error-exitcode", "7", sys.executable, "-c", SCRIPT],
+                         capture_output=True, text=True, timeout=1800, cwd=ROOT)
+    tail = (out.stdout + out.stderr)[-4000:]
+    assert "sanitized run complete" in out.stdout, tail
+    assert out.returncode == 0 and "ERROR SUMMARY: 0 errors" in (out.stdout + out.stderr), tail

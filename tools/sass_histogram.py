@@ -14,7 +14,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "end-to-end_asr_pytorch_b200", "csrc", "libasr_sm100.so")
-WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "SYNCS", "FFMA2", "FADD2",
+WATCH = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "UTMAPF", "UBLKCP", "LDGMC", "SYNCS", "FFMA2", "FADD2",
          "FMUL2", "MUFU", "HMMA", "LDGSTS", "REDUX", "SHFL", "BAR", "ELECT"]
 
 
