@@ -1150,7 +1150,7 @@ def main():
     if mha is not None:
         top = mha["shapes"][0]
         mha_roofline = {
-            "fwd": {"bound": "tensor", "kernel": "asr::mha_fwd8_kernel<false, 51>", "achieved": top["fwd_TFLOPs"],
+            "fwd": {"bound": "tensor", "kernel": "asr::mha_fwdp_kernel<false> (persistent two-tile forward)", "achieved": top["fwd_TFLOPs"],
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": top["fwd_frac_of_bf16_peak"],
                     "avg_launch_ms": top["fwd_ms"], "shape": top["shape"], "flops": "4 B h Lq Lk d"},
             "bwd": {"bound": "tensor", "kernel": "asr::mha_bwd_kernel<4, false> (+ delta and dQ-convert kernels)",

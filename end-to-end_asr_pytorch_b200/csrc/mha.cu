@@ -23,6 +23,7 @@
 #include "tcgen05.cuh"
 
 #include <cuda_bf16.h>
+#include <type_traits>
 
 #include <algorithm>
 
@@ -745,17 +746,36 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_fence_before();
                 mbar_arrive_warp(&bars->s_free[t]);      // the scores are in registers: S may be overwritten
                 float m_q[4];
+                if (__builtin_expect(need_mask, 0)) {
+                    // dead keys of this row as four 32-bit masks: the length / causal limit by arithmetic, a dense mask by a
+                    // ROLLED byte loop (unrolled it is 128 x (address, LDG.U8, compare, select): a quarter of the kernel's code)
+                    uint32_t dead[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (need_mask) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int key = key0 + 32 * q + i;
-                            bool dead = key >= lim;
-                            if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                            if (dead) r[q][i] = 0xff800000u;   // -inf
+                    for (int q = 0; q < 4; ++q) {
+                        const int live = lim - (key0 + 32 * q);                 // keys [0, live) of this chunk are inside the limit
+                        dead[q] = live >= 32 ? 0u : live <= 0 ? 0xffffffffu : (0xffffffffu << live);
+                    }
+                    if (mrow != nullptr) {
+                        const int kmax = min(kBN, a.Lk - key0);
+#pragma unroll 1
+                        for (int kk = 0; kk < kmax; ++kk) {
+                            const uint32_t bit = (mrow[key0 + kk] != 0) ? (1u << (kk & 31)) : 0u;
+                            const int q = kk >> 5;
+                            dead[0] |= (q == 0) ? bit : 0u;
+                            dead[1] |= (q == 1) ? bit : 0u;
+                            dead[2] |= (q == 2) ? bit : 0u;
+                            dead[3] |= (q == 3) ? bit : 0u;
                         }
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if ((dead[q] >> i) & 1u) r[q][i] = 0xff800000u;   // -inf
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                     m_q[q] = -INFINITY;          // four independent chains
 #pragma unroll
                     for (int i = 0; i < 32; ++i) m_q[q] = fmaxf(m_q[q], __uint_as_float(r[q][i]));
@@ -767,7 +787,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 MHA_TRACE(t, j, 3);
                 if (j == 0) {
                     m_used = m_new;
-                } else if (__any_sync(0xffffffffu, grow)) {      // TMEM accesses are warp-collective: all lanes go
+                } else if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {      // TMEM accesses are warp-collective: all lanes go
                     // O is being accumulated by P V of this tile's previous block: wait for it before touching O
                     mbar_wait(&bars->pv_full[t], (j - 1) & 1);
                     tc_fence_after();
@@ -967,17 +987,23 @@ struct MhaItem {
 // keeps (batch * heads + head, tile) and advances them by additions (three divisions once per thread instead of per item).
 struct MhaItemWalk {
     int bh, qt, dbh, dqt, nq2, left;
-    __device__ __forceinline__ MhaItemWalk(int n_items, int nq2_) : nq2(nq2_) {
+    int k, n_bh;        // causal walk: visit number, batch * heads
+    bool causal;
+    __device__ __forceinline__ MhaItemWalk(const MhaFwdArgs& a, int n_items, int nq2_) : nq2(nq2_) {
         const int first = blockIdx.x, step = gridDim.x;
         bh = first / nq2;
         qt = first - bh * nq2;
         dbh = step / nq2;
         dqt = step - dbh * nq2;
         left = first < n_items ? (n_items - 1 - first) / step + 1 : 0;
+        k = 0;
+        n_bh = a.B * a.Hh;
+        causal = a.causal != 0 && a.dense_mask == nullptr;
     }
     __device__ __forceinline__ bool valid() const { return left > 0; }
     __device__ __forceinline__ void next() {
         --left;
+        ++k;
         bh += dbh;
         qt += dqt;
         if (qt >= nq2) {
@@ -987,16 +1013,24 @@ struct MhaItemWalk {
     }
     __device__ __forceinline__ MhaItem get(const MhaFwdArgs& a) const {
         MhaItem it;
-        // causal items get lighter towards the first queries: rotate the tile order per (batch, head), so that the items
-        // of one CTA do not all fall on the same query tile
-        int q = qt;
-        if (a.causal) {
-            q = qt + bh % nq2;
-            if (q >= nq2) q -= nq2;
+        int ibh = bh, iq = qt;
+        if (causal) {
+            // Causal items cost 2 (qt + 1) key blocks: they are dealt longest first and in snake order (visit k: position
+            // k G + c on even visits, k G + G - 1 - c on odd ones, in the list sorted by falling cost), which evens out the
+            // CTAs' totals without a work counter.  The price is one division per item and K / V tiles that are shared by
+            // CTAs of different visits instead of neighbours.
+            const int G = gridDim.x, c = blockIdx.x;
+            const int p = k * G + ((k & 1) ? G - 1 - c : c);
+            const int total = n_bh * nq2;
+            // the last visit is ragged: positions beyond the list belong to nobody; the plain walk counted `left` for
+            // position k G + c, so map the tail straight
+            const int pp = p < total ? p : k * G + c;
+            iq = nq2 - 1 - pp / n_bh;
+            ibh = pp - (pp / n_bh) * n_bh;
         }
-        it.b = bh / a.Hh;
-        it.h = bh - it.b * a.Hh;
-        it.q0 = q * 2 * kBM;
+        it.b = ibh / a.Hh;
+        it.h = ibh - it.b * a.Hh;
+        it.q0 = iq * 2 * kBM;
         const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + it.b), 0), a.Lk) : a.Lk;
         it.ntile = (it.q0 + kBM < a.Lq) ? 2 : 1;
         int k_end0 = a.causal ? min(kvlen, it.q0 + kBM) : kvlen;
@@ -1064,7 +1098,7 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tma_prefetch_desc(&tm_v);
             int g = 0;                                    // blocks loaded by this CTA so far
             int k = 0;                                    // items
-            for (MhaItemWalk walk(n_items, nq2); walk.valid(); walk.next(), ++k) {
+            for (MhaItemWalk walk(a, n_items, nq2); walk.valid(); walk.next(), ++k) {
                 const MhaItem it = walk.get(a);
                 const int qb = k & 1;
                 if (k >= 2) mbar_wait(&bars->q_free[qb], ((k >> 1) - 1) & 1);     // the item two back is done with this Q buffer
@@ -1122,7 +1156,7 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tc_commit(&bars->k_empty[ks]);
                 if (j + 1 == nbt) tc_commit(&bars->q_free[qb]);     // this tile's last Q K^T of the item: Q is free behind it
             };
-            MhaItemWalk walk(n_items, nq2);
+            MhaItemWalk walk(a, n_items, nq2);
             MhaItem it = walk.get(a);
             if (walk.valid()) issue_s(it, 0, 0, 0, 0);
             while (walk.valid()) {
@@ -1225,7 +1259,7 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         // exponentials at once); tile 1 grants the very first turn.  Items with one tile do not touch it.
         bool ring_started = false;
         int kk_item = -1;
-        for (MhaItemWalk walk(n_items, nq2); walk.valid(); walk.next()) {
+        for (MhaItemWalk walk(a, n_items, nq2); walk.valid(); walk.next()) {
             const MhaItem it = walk.get(a);
             ++kk_item;
             if (t >= it.ntile) continue;
@@ -1265,17 +1299,37 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (j == 1) MHA_TRACE(t, kk_item, 6);
                 if (j == 2) MHA_TRACE(t, kk_item, 7);
                 float m_q[4];
+                if (__builtin_expect(need_mask, 0)) {
+                    // dead keys of this row as four 32-bit masks: the length / causal limit by arithmetic, a dense mask by a
+                    // ROLLED byte loop (unrolled it is 128 x (address, LDG.U8, compare, select): a quarter of the kernel's
+                    // code, which the persistent loop pays for in instruction-cache misses)
+                    uint32_t dead[4];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (need_mask) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            const int key = key0 + 32 * q + i;
-                            bool dead = key >= lim;
-                            if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                            if (dead) r[q][i] = 0xff800000u;   // -inf
+                    for (int q = 0; q < 4; ++q) {
+                        const int live = lim - (key0 + 32 * q);                 // keys [0, live) of this chunk are inside the limit
+                        dead[q] = live >= 32 ? 0u : live <= 0 ? 0xffffffffu : (0xffffffffu << live);
+                    }
+                    if (mrow != nullptr) {
+                        const int kmax = min(kBN, a.Lk - key0);
+#pragma unroll 1
+                        for (int kk = 0; kk < kmax; ++kk) {
+                            const uint32_t bit = (mrow[key0 + kk] != 0) ? (1u << (kk & 31)) : 0u;
+                            const int q = kk >> 5;
+                            dead[0] |= (q == 0) ? bit : 0u;
+                            dead[1] |= (q == 1) ? bit : 0u;
+                            dead[2] |= (q == 2) ? bit : 0u;
+                            dead[3] |= (q == 3) ? bit : 0u;
                         }
                     }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if ((dead[q] >> i) & 1u) r[q][i] = 0xff800000u;   // -inf
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                     m_q[q] = -INFINITY;          // four independent chains
 #pragma unroll
                     for (int i = 0; i < 32; ++i) m_q[q] = fmaxf(m_q[q], __uint_as_float(r[q][i]));
@@ -1286,7 +1340,7 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 bool pv_waited = false;
                 if (j == 0) {
                     m_used = m_new;
-                } else if (__any_sync(0xffffffffu, grow)) {      // TMEM accesses are warp-collective: all lanes go
+                } else if (__builtin_expect(__any_sync(0xffffffffu, grow), 0)) {      // TMEM accesses are warp-collective: all lanes go
                     // O is being accumulated by P V of this tile's previous block: wait for it before touching O
                     mbar_wait(&bars->pv_full[t], (n + j - 1) & 1);
                     tc_fence_after();
@@ -1649,6 +1703,20 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             if (a.causal) lim = min(lim, qi + 1);
             const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
             const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+            // dead keys among this thread's kColsS columns as a bit mask: the length / causal limit by arithmetic, a dense
+            // mask by a rolled byte loop (unrolled into the packed loop below it was two guarded byte loads per pair)
+            using dead_t = typename std::conditional<(kColsS <= 32), uint32_t, uint64_t>::type;
+            dead_t dead = 0;
+            if (__builtin_expect(need_mask, 0)) {
+                const int first = key0 + cg * kColsS;
+                const int live = lim - first;                     // columns [0, live) are inside the limit
+                dead = live >= kColsS ? (dead_t)0 : live <= 0 ? (dead_t)~(dead_t)0 : (dead_t)((dead_t)~(dead_t)0 << live);
+                if (mrow != nullptr) {
+                    const int kmax = min(kColsS, a.Lk - first);
+#pragma unroll 1
+                    for (int kk = 0; kk < kmax; ++kk) dead |= (dead_t)(mrow[first + kk] != 0) << kk;
+                }
+            }
 
             // P and dS of this thread's columns, packed bf16, kept in registers until the products of
             // the previous tile have released the shared-memory tiles
@@ -1675,16 +1743,8 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         float x0, x1;
                         unpack_f32x2(fma_f32x2(pack_f32x2(sv[i], sv[i + 1]), c2, nl2), x0, x1);
                         float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
-                        if (need_mask) {
-                            const int key = key0 + cc + i;
-                            bool d0 = key >= lim, d1 = key + 1 >= lim;
-                            if (mrow != nullptr) {
-                                if (key < a.Lk) d0 = d0 || (mrow[key] != 0);
-                                if (key + 1 < a.Lk) d1 = d1 || (mrow[key + 1] != 0);
-                            }
-                            if (d0) p0 = 0.0f;
-                            if (d1) p1 = 0.0f;
-                        }
+                        if ((dead >> (c0 + i)) & 1u) p0 = 0.0f;
+                        if ((dead >> (c0 + i + 1)) & 1u) p1 = 0.0f;
                         const uint64_t p2 = pack_f32x2(p0, p1);
                         uint64_t g2 = pack_f32x2(dp[i], dp[i + 1]);      // d(loss)/d(dropped, rescaled probability)
                         uint64_t pd2 = p2;                               // the probabilities P V was computed with
@@ -1909,15 +1969,16 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     //                              query sequences (Lq <= 128: the second tile of a 256-query CTA would be empty; model
     //                              shapes are L = 21 .. 167, U <= 15)
     //   mha_fwdp_kernel<DROP>      the two-tile kernel with the work items looped inside one CTA per SM (set-up, first loads,
-    //                              epilogue and CTA turnaround overlap the neighbouring items): without dropout, when an item has
-    //                              few key blocks - measured against mha_fwd8_kernel on B200 (tools/mha_persistent_sweep.py):
-    //                              L = 167 -11 %, 256 -19 %, 512 -12 %, 1024 -6 %, 1536 -3 % of the time, L = 2048 equal, 4096 +3 %;
-    //                              causal: -14 % at L = 256, -6 % at 1024, +5 % at 2048 (its static item order balances worse)
+    //                              epilogue and CTA turnaround overlap the neighbouring items; causal items dealt longest
+    //                              first in snake order): every two-tile call without dropout.  Measured against
+    //                              mha_fwd8_kernel on B200 (tools/mha_persistent_sweep.py), time: L = 167 -11 %, 256 -17 %,
+    //                              512 -13 %, 1024 -6 %, 2048 -3 %, 4096 equal; causal: -19 % at 256, -14 % at 512,
+    //                              -8 % at 1024, -11 % at 2048 and 4096
     // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel, 40 = always mha_fwdp_kernel.
     const int variant = get_opt("mha_variant");
     const bool drop = a.drop_thresh > 0;
     const bool one_tile = variant == 3 || (variant != 21 && variant != 40 && (drop || Lq <= kBM));
-    const bool persistent = !drop && !one_tile && (variant == 40 || (variant == 0 && Lk <= (causal ? 1024 : 1536)));
+    const bool persistent = !drop && !one_tile && (variant == 40 || variant == 0);
     static bool attr_done[4] = {false, false, false, false};      // cudaFuncSetAttribute once per kernel, not per call
     if (one_tile) {
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);

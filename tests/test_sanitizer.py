@@ -53,7 +53,9 @@ def test_kernels_are_clean_under_compute_sanitizer(tool):
         pytest.skip("needs a CUDA device")
     if not os.path.exists(SANITIZER):
         pytest.skip("compute-sanitizer not installed")
-    out = subprocess.run([SANITIZER, "--tool", tool, "--error-exitcode", "7", sys.executable, "-c", SCRIPT],
+    # (--report-api-errors no: under the tool torch's symmetric-memory set-up probes the multicast driver calls, gets
+    # CUDA_ERROR_INVALID_VALUE and carries on without multicast - a host API return code, not a kernel fault)
+    out = subprocess.run([SANITIZER, "--tool", tool, "--report-api-errors", "no", "--error-exitcode", "7", sys.executable, "-c", SCRIPT],
                          capture_output=True, text=True, timeout=1800, cwd=ROOT)
     tail = (out.stdout + out.stderr)[-4000:]
     assert "sanitized run complete" in out.stdout, tail
