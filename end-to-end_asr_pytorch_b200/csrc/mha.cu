@@ -247,14 +247,28 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             int lim = kvlen;
             if (a.causal) lim = min(lim, qi + 1);
             const bool need_mask = (j * kBN + kBN > lim) || (mrow != nullptr);
-            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int key = key0 + cc + i;
-                    bool dead = key >= lim;
-                    if (mrow != nullptr && key < a.Lk) dead = dead || (mrow[key] != 0);
-                    if (dead) r[i] = 0xff800000u;   // -inf
+            // dead keys among this thread's 64 as two 32-bit masks (length / causal limit by arithmetic, a dense mask by a
+            // rolled byte loop: unrolled per key it was most of the kernel's code)
+            uint32_t dead_lo = 0, dead_hi = 0;
+            if (__builtin_expect(need_mask, 0)) {
+                const int live = lim - key0;
+                dead_lo = live >= 32 ? 0u : live <= 0 ? 0xffffffffu : (0xffffffffu << live);
+                dead_hi = live >= 64 ? 0u : live <= 32 ? 0xffffffffu : (0xffffffffu << (live - 32));
+                if (mrow != nullptr) {
+                    const int kmax = min(64, a.Lk - key0);
+#pragma unroll 1
+                    for (int kk = 0; kk < kmax; ++kk) {
+                        const uint32_t bit = (mrow[key0 + kk] != 0) ? (1u << (kk & 31)) : 0u;
+                        dead_lo |= (kk < 32) ? bit : 0u;
+                        dead_hi |= (kk < 32) ? 0u : bit;
+                    }
                 }
+            }
+            auto apply_mask = [&](uint32_t (&r)[32], int cc) {
+                const uint32_t dead = cc ? dead_hi : dead_lo;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if ((dead >> i) & 1u) r[i] = 0xff800000u;   // -inf
             };
             mbar_wait(&bars->s_full, j & 1);
             tc_fence_after();
