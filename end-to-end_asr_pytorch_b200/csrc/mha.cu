@@ -470,7 +470,7 @@ constexpr int kFwd6Stages = 4;   // K and V rings: a TMA load takes longer than 
 // the current block's exponentials.  Two tiles per CTA (warps 0-3 and 4-7) share every K/V tile (4-deep TMA
 // rings for K and for V: a load takes longer than a block of work) and run in opposite phases.  O
 // accumulates in TMEM with the lazy rescale of mha_fwd3_kernel.
-// TMEM (512 columns): S_A 0-127 | S_B 128-255 | O_A 256-319 | O_B 320-383 | P_A 384-447 | P_B 448-511 (MODE bit 4).
+// TMEM (512 columns): S_A 0-127 | S_B 128-255 | O_A 256-319 | O_B 320-383 | P_A 384-447 | P_B 448-511.
 struct __align__(8) MhaBarriers8 {
     uint64_t q_full;
     uint64_t k_full[kFwd6Stages];
@@ -485,15 +485,16 @@ struct __align__(8) MhaBarriers8 {
     uint32_t pad;
 };
 constexpr int kFwd8Threads = 384;   // 8 softmax warps + one utility warpgroup (TMA, MMA, two idle warps)
-// Q x2 + K ring + V ring (+ P x2 unless P lives in tensor memory, MODE bit 4) + barriers
-constexpr int fwd8_smem(int mode) { return (2 + 2 * kFwd6Stages + ((mode & 16) ? 0 : 4)) * kTileBytes + 256; }
-static_assert(fwd8_smem(0) <= 232448, "shared memory of the forward kernel");
+// Q x2 + K ring + V ring + barriers (P lives in tensor memory)
+constexpr int kFwd8Smem = (2 + 2 * kFwd6Stages) * kTileBytes + 256;
+static_assert(kFwd8Smem <= 232448, "shared memory of the forward kernel");
 
-// MODE bit 0: the two tiles take turns on the XU pipe (named-barrier token), which keeps them in
-// opposite phases: one loads its scores and finds the row maxima while the other runs its exponentials.  MODE bit 1: fp32
-// exponentials with packed f32x2 arithmetic (FFMA2 / FADD2), row sums from the unrounded fp32 values.  MODE bit 4:
-// P stays in tensor memory (own columns) as the A operand of P V.  MODE bit 5: one MMA issuer per tile.
-template <bool DROP, int MODE>
+// The two tiles take turns on the XU pipe (named-barrier token), which keeps them in opposite phases: one loads its scores
+// and finds the row maxima while the other runs its exponentials.  Exponentials in fp32 with packed f32x2 arithmetic
+// (FFMA2 / FADD2), row sums from the unrounded fp32 values; P stays in tensor memory (own columns) as the A operand of
+// P V; one MMA issuer per tile.  (Round 2 measured the alternatives - P through shared memory, one issuer for both tiles,
+// bf16x2 exponentials, no token: DESIGN.md 4 keeps the numbers - and removed them.)
+template <bool DROP>
 __global__ void __launch_bounds__(kFwd8Threads, 1)
 mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const MhaFwdArgs a) {
@@ -505,8 +506,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     unsigned char* sQ = smem;                              // 2 tiles
     unsigned char* sK = sQ + 2 * kTileBytes;               // kFwd6Stages tiles
     unsigned char* sV = sK + kFwd6Stages * kTileBytes;     // kFwd6Stages tiles
-    unsigned char* sP = sV + kFwd6Stages * kTileBytes;     // [2 tiles][2 key halves][128 rows][128 B]
-    MhaBarriers8* bars = reinterpret_cast<MhaBarriers8*>(sP + ((MODE & 16) ? 0 : 4) * kTileBytes);
+    MhaBarriers8* bars = reinterpret_cast<MhaBarriers8*>(sV + kFwd6Stages * kTileBytes);
     static_assert(sizeof(MhaBarriers8) <= 256, "barrier block");
 
     const int warp = threadIdx.x >> 5;
@@ -530,10 +530,10 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_init(&bars->q_full, 1);
         for (int s = 0; s < kFwd6Stages; ++s) {
             mbar_init(&bars->k_full[s], 1);
-            // MODE bit 5: one MMA issuer per tile, each of them releases every stage once
-            mbar_init(&bars->k_empty[s], (MODE & 32) ? ntile : 1);
+            // one MMA issuer per tile, each of them releases every stage once
+            mbar_init(&bars->k_empty[s], ntile);
             mbar_init(&bars->v_full[s], 1);
-            mbar_init(&bars->v_empty[s], (MODE & 32) ? ntile : 1);
+            mbar_init(&bars->v_empty[s], ntile);
         }
         for (int t = 0; t < 2; ++t) {
             mbar_init(&bars->s_full[t], 1);
@@ -575,8 +575,8 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 tma_load_4d(sV + s * kTileBytes, &tm_v, 0, h, j * kBN, b, &bars->v_full[s]);
             }
         }
-    } else if ((MODE & 32) && (warp == kMmaWarp || warp == kMmaWarp + 1)) {
-        // ===== MMA issuers, one elected thread per tile (MODE bit 5) =====
+    } else if (warp == kMmaWarp || warp == kMmaWarp + 1) {
+        // ===== MMA issuers, one elected thread per tile =====
         // A single issuer walking S(0) S(1) PV(0) PV(1) in order spends ~100 cycles per Q K^T MMA, ~70 per P V
         // MMA and 100-200 per (already complete) mbarrier wait - its sub-partition is shared with two busy
         // softmax warps - which adds up to the whole period of a key block.  Two issuers on two sub-partitions
@@ -590,7 +590,6 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const uint32_t tmem_s = tmem + 128 * t;
             const uint32_t tmem_o = tmem + 256 + 64 * t;
             const uint32_t tmem_p = tmem + 384 + 64 * t;
-            const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
             const int nbt = nb[t];
             // S of block j, or just the release of its K stage when this tile does not need the block
             auto issue_s = [&](int j) {
@@ -631,82 +630,11 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                 for (int kk = 0; kk < kBN / 16; ++kk) {
                     const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
-                    if (MODE & 16) {
-                        umma_bf16_ts(tmem_o, tmem_p + 8 * kk, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                    } else {
-                        const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-                        umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                    }
+                    umma_bf16_ts(tmem_o, tmem_p + 8 * kk, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
                 }
                 tc_commit(&bars->pv_full[t]);
                 tc_commit(&bars->v_empty[vs]);
                 MHA_TRACE_MMA(t, j, 9);
-            }
-        }
-    } else if (warp == kMmaWarp) {
-        // ===== MMA issuer (one thread) =====
-        // S of a tile's next block is issued as soon as its scores have been read (s_free), P V when P is there.
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc_s = make_idesc(kBM, kBN, 0, 0);    // S = Q K^T : A, B K-major
-            constexpr uint32_t idesc_pv = make_idesc(kBM, kD, 0, 1);    // PV = P V  : A K-major, B MN-major
-            // S of (tile t, block j); `last` releases the K stage (no later product reads it)
-            auto issue_s = [&](int t, int j, bool last) {
-                const int ks = j % kFwd6Stages;
-                mbar_wait(&bars->k_full[ks], (j / kFwd6Stages) & 1);
-                if (j > 0) mbar_wait(&bars->s_free[t], (j - 1) & 1);      // scores of block j-1 are in registers
-                tc_fence_after();
-                MHA_TRACE_MMA(t, j, 10);
-                const uint32_t q_addr = smem_u32(sQ + t * kTileBytes);
-                const uint32_t k_addr = smem_u32(sK + ks * kTileBytes);
-#pragma unroll
-                for (int kk = 0; kk < kD / 16; ++kk)
-                    umma_bf16(tmem + 128 * t, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
-                              idesc_s, kk > 0 ? 1u : 0u);
-                tc_commit(&bars->s_full[t]);
-                if (last) tc_commit(&bars->k_empty[ks]);
-                MHA_TRACE_MMA(t, j, 11);
-            };
-            mbar_wait(&bars->q_full, 0);
-            for (int t = 0; t < ntile; ++t) issue_s(t, 0, t == ntile - 1);
-            for (int j = 0; j < nblk; ++j) {
-                const int vs = j % kFwd6Stages;
-                const uint32_t v_addr = smem_u32(sV + vs * kTileBytes);
-                // next block's scores first: they only need s_free, which arrives long before p_full
-                for (int t = 0; t < ntile; ++t) {
-                    if (j + 1 < nb[t]) {
-                        bool last_k = true;
-                        for (int t2 = t + 1; t2 < ntile; ++t2) last_k = last_k && (j + 1 >= nb[t2]);
-                        issue_s(t, j + 1, last_k);
-                    }
-                }
-                for (int t = 0; t < ntile; ++t) {
-                    if (j >= nb[t]) continue;                 // causal: the first tile needs fewer key blocks
-                    MHA_TRACE_MMA(t, j, 16);
-                    mbar_wait(&bars->v_full[vs], (j / kFwd6Stages) & 1);
-                    MHA_TRACE_MMA(t, j, 17);
-                    mbar_wait(&bars->p_full[t], j & 1);       // P of (t, j) is in shared memory / tensor memory
-                    tc_fence_after();
-                    MHA_TRACE_MMA(t, j, 8);
-                    const uint32_t p_addr = smem_u32(sP + t * 2 * kTileBytes);
-                    const uint32_t tmem_o = tmem + 256 + 64 * t;
-#pragma unroll
-                    for (int kk = 0; kk < kBN / 16; ++kk) {
-                        const uint64_t bd = smem_desc_sw128(v_addr + kk * 2048, kTileBytes, 1024);
-                        if (MODE & 16) {
-                            // A operand = the row's packed bf16 probabilities in tensor memory: 16 keys = 8 columns
-                            umma_bf16_ts(tmem_o, tmem + 384 + 64 * t + 8 * kk, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                        } else {
-                            const uint64_t ad = smem_desc_sw128(p_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024);
-                            umma_bf16(tmem_o, ad, bd, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);   // O accumulates over the blocks
-                        }
-                    }
-                    tc_commit(&bars->pv_full[t]);
-                    MHA_TRACE_MMA(t, j, 9);
-                    bool last_v = true;
-                    for (int t2 = t + 1; t2 < ntile; ++t2) last_v = last_v && (j >= nb[t2]);
-                    if (last_v) tc_commit(&bars->v_empty[vs]);
-                }
             }
         }
     } else if (warp >= 8) {
@@ -722,16 +650,15 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
             const uint32_t tmem_s = tmem + 128 * t + lane_base;
             const uint32_t tmem_o = tmem + 256 + 64 * t + lane_base;
-            unsigned char* prow = sP + t * 2 * kTileBytes + row * 128;
             float m_used = -INFINITY;
             float l_run = 0.0f;          // sum of the row's (undropped) probabilities, scaled like O
             const float c = a.scale_log2;
             const int nbt = nb[t];
-            // token ring of the two tiles (MODE bit 0): tile 0 waits on barrier 1, tile 1 on barrier 2; a tile holds
+            // token ring of the two tiles: tile 0 waits on barrier 1, tile 1 on barrier 2; a tile holds
             // the token while it runs its exponentials and then hands it to the other tile, so the two tiles
             // cannot fall into lockstep on the XU pipe.  Both tiles walk nblk turns (a tile that has run out of
             // key blocks just passes the token on); tile 1 grants the first turn.
-            const bool pp = (MODE & 1) && ntile == 2;
+            const bool pp = ntile == 2;
             const int nturn = pp ? nblk : nbt;
             MHA_CTA_STAMP(2);
             if (pp && t == 1) bar_arrive_named(1, 256);
@@ -826,22 +753,9 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (j > 0 && !pv_waited) mbar_wait(&bars->pv_full[t], (j - 1) & 1);
                 float lsum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
                 uint32_t pk_all[4][16];
-                // 32 keys = 16 packed columns of the row's TMEM lane (MODE bit 4), or 64 bytes = four 16-byte chunks of
-                // the row's 128-byte line in key half q / 2 of the shared P tile
-                auto store_chunk = [&](int q) {
-                    if (MODE & 16) {
-                        tmem_st16(tmem + 384 + 64 * t + lane_base + 16 * q, pk_all[q]);
-                        return;
-                    }
-                    unsigned char* pr = prow + (q >> 1) * kTileBytes;
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        const int chunk = ((q & 1) * 4 + q4) ^ (row & 7);
-                        *reinterpret_cast<uint4*>(pr + chunk * 16) =
-                            make_uint4(pk_all[q][4 * q4], pk_all[q][4 * q4 + 1], pk_all[q][4 * q4 + 2], pk_all[q][4 * q4 + 3]);
-                    }
-                };
-                if (!DROP && (MODE & 2)) {
+                // 32 keys = 16 packed columns of the row's TMEM lane
+                auto store_chunk = [&](int q) { tmem_st16(tmem + 384 + 64 * t + lane_base + 16 * q, pk_all[q]); };
+                if (!DROP) {
                     // x = s * scale - max in place, packed; no XU work yet
                     const uint64_t c2 = pack_f32x2(c, c);
                     const uint64_t mc2 = pack_f32x2(-mc, -mc);
@@ -878,29 +792,19 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t (&pk)[16] = pk_all[q];
-                        if (DROP) {
 #pragma unroll
-                            for (int g = 0; g < 2; ++g) {
-                                const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
-                                                           seed_lo, seed_hi);
+                        for (int g = 0; g < 2; ++g) {
+                            const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
+                                                       seed_lo, seed_hi);
 #pragma unroll
-                                for (int i = 0; i < 16; i += 2) {
-                                    float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
-                                    float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i + 1]), c, -mc));
-                                    lsum[q] += p0 + p1;
-                                    p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
-                                    p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
-                                    const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                                    pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
-                                }
-                            }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                const uint32_t w = ex2_bf16x2(fmaf(__uint_as_float(r[q][i]), c, -mc), fmaf(__uint_as_float(r[q][i + 1]), c, -mc));
-                                pk[i >> 1] = w;
-                                // the normaliser is the sum of the probabilities P V really uses: the bf16 values
-                                lsum[q] += __uint_as_float(w << 16) + __uint_as_float(w & 0xffff0000u);
+                            for (int i = 0; i < 16; i += 2) {
+                                float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i]), c, -mc));
+                                float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g * 16 + i + 1]), c, -mc));
+                                lsum[q] += p0 + p1;
+                                p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
+                                p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
+                                const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
+                                pk[(g * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
                             }
                         }
                         store_chunk(q);
@@ -909,12 +813,8 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                 if (pp && (t == 0 || j + 1 < nturn)) bar_arrive_named(2 - t, 256);
                 l_run += (lsum[0] + lsum[1]) + (lsum[2] + lsum[3]);
                 MHA_TRACE(t, j, 6);
-                if (MODE & 16) {
-                    tmem_st_wait();
-                    tc_fence_before();
-                } else {
-                    fence_proxy_async();          // P (generic proxy) -> visible to the tensor core (async proxy)
-                }
+                tmem_st_wait();
+                tc_fence_before();
                 mbar_arrive_warp(&bars->p_full[t]);
                 MHA_TRACE(t, j, 7);
                 MHA_TRACE_WARP(t, j, 12);
@@ -973,7 +873,7 @@ mha_fwd8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 //     under the last block's exponentials and the epilogue; the first P V of an item overwrites O, so it waits for o_free
 //     (the epilogue has read the accumulator);
 //   * tensor memory is allocated once.
-// Inner structure, TMEM layout and numerics are those of mha_fwd8_kernel<DROP, 51> (outputs are bit-identical).
+// Inner structure, TMEM layout and numerics are those of mha_fwd8_kernel<DROP> (outputs are bit-identical).
 struct __align__(8) MhaBarriersP {
     uint64_t q_full[2];     // per Q buffer (items alternate)
     uint64_t q_free[2];
@@ -1975,9 +1875,10 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     a.seed_lo = (uint32_t)seed;
     a.seed_hi = (uint32_t)(seed >> 32);
     a.seed_dev = seed_dev;
-    // Two kernels (the four earlier generations are gone, DESIGN.md 4 keeps their numbers):
-    //   mha_fwd8_kernel<DROP, 51>  CTA = two 128-query tiles sharing every K/V tile, one thread per query row, P in
-    //                              tensor memory: the long-sequence kernel (L = 2048: 687 TFLOP/s)
+    // Three kernels (the earlier generations are gone, DESIGN.md 4 keeps their numbers):
+    //   mha_fwd8_kernel<DROP>      CTA = two 128-query tiles sharing every K/V tile, one thread per query row, P in
+    //                              tensor memory, one CTA per (batch, head, 256 queries): L = 2048 707 TFLOP/s; kept as the
+    //                              reference point of the persistent kernel (mha_variant = 21)
     //   mha_fwd3_kernel<DROP>      CTA = one 128-query tile, two threads per row, two CTAs per SM: with dropout (the
     //                              Philox work per element favours two threads per row: 418 vs 312 TFLOP/s) and for short
     //                              query sequences (Lq <= 128: the second tile of a 256-query CTA would be empty; model
@@ -2013,11 +1914,11 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
             mha_fwdp_kernel<false><<<dim3(std::min(n_items, num_sms())), kFwd8Threads, kFwdPSmem, st>>>(tq, tk, tv, a, n_items, nq2);
         } else
         if (drop) {
-            if (!attr_done[2]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<true, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(51))); attr_done[2] = true; }
-            mha_fwd8_kernel<true, 51><<<grid, kFwd8Threads, fwd8_smem(51), st>>>(tq, tk, tv, a);
+            if (!attr_done[2]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); attr_done[2] = true; }
+            mha_fwd8_kernel<true><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);
         } else {
-            if (!attr_done[3]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false, 51>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd8_smem(51))); attr_done[3] = true; }
-            mha_fwd8_kernel<false, 51><<<grid, kFwd8Threads, fwd8_smem(51), st>>>(tq, tk, tv, a);
+            if (!attr_done[3]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); attr_done[3] = true; }
+            mha_fwd8_kernel<false><<<grid, kFwd8Threads, kFwd8Smem, st>>>(tq, tk, tv, a);
         }
     }
     ASR_LAUNCH_CHECK();
