@@ -333,19 +333,23 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint64_t c2 = pack_f32x2(c, c), mc2 = pack_f32x2(-mc, -mc);
                     uint64_t l2 = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
+                    const uint32_t thr4 = a.drop_thresh * 0x01010101u;
                     for (int g = 0; g < 2; ++g) {
                         const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
                                                    seed_lo, seed_hi);
+                        // keep masks of four keys at a time: bytes of 0xff where the random byte is >= the threshold (six
+                        // integer instructions per word), widened to the two bf16 lanes of a packed pair by a byte permute
+                        // and ANDed into the packed probabilities.  The 1 / keep scale is applied once, in the epilogue.
+                        const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
-                            float x0, x1, q0, q1;
+                            float x0, x1;
                             unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[g * 16 + i]), __uint_as_float(r[g * 16 + i + 1])), c2, mc2), x0, x1);
-                            const uint64_t p2 = pack_f32x2(ex2_approx(x0), ex2_approx(x1));
-                            l2 = add_f32x2(l2, p2);
-                            const float k0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : a.inv_keep;
-                            const float k1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : a.inv_keep;
-                            unpack_f32x2(mul_f32x2(p2, pack_f32x2(k0, k1)), q0, q1);
-                            pk[(g * 16 + i) >> 1] = cvt_bf16x2(q0, q1);
+                            const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                            l2 = add_f32x2(l2, pack_f32x2(p0, p1));
+                            const uint32_t keep4 = __vcmpgeu4(rw[i >> 2], thr4);
+                            const uint32_t keep2 = __byte_perm(keep4, 0, (i & 2) ? 0x3322 : 0x1100);
+                            pk[(g * 16 + i) >> 1] = cvt_bf16x2(p0, p1) & keep2;
                         }
                     }
                     float la, lb;
@@ -391,7 +395,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             if (!kUseOnes) l_run += tmem_ld1(tmem_l + lane_base + 1);
             tc_fence_before();
             if (qi < a.Lq) {
-                const float inv = 1.0f / l_run;
+                const float inv = (DROP ? a.inv_keep : 1.0f) / l_run;      // kept probabilities went into P V unscaled
                 __nv_bfloat16* dst = a.out + (((size_t)b * a.Lq + qi) * a.Hh + h) * kD + half * 32;
 #pragma unroll
                 for (int i = 0; i < 32; i += 8) {
