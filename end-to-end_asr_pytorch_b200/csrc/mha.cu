@@ -84,6 +84,17 @@ __device__ __forceinline__ uint32_t philox_byte(const uint4& r, int k) {
     return (w >> ((k & 3) * 8)) & 0xffu;
 }
 
+// Keep masks of a packed bf16 pair (0xffff per kept lane) from two random bytes of `word` (bytes 2p, 2p + 1): a byte permute
+// turns each byte into the fp16 number 1 + byte / 1024 (0x3c00 | byte), and ONE packed fp16 compare against 1 + thresh / 1024
+// (`thr_h2` = 0x3c00 | thresh in both halves) yields the mask - two instructions per pair where extract / compare / select
+// per key were six.
+__device__ __forceinline__ uint32_t keep_mask2(uint32_t word, int p, uint32_t thr_h2) {
+    const uint32_t x = __byte_perm(word, 0x3c3c3c3cu, p ? 0x4342 : 0x4140);
+    uint32_t m;
+    asm("set.ge.u32.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x), "r"(thr_h2));
+    return m;
+}
+
 struct __align__(8) MhaBarriers {
     uint64_t q_full;
     uint64_t kv_full[2];
@@ -333,13 +344,12 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     const uint64_t c2 = pack_f32x2(c, c), mc2 = pack_f32x2(-mc, -mc);
                     uint64_t l2 = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
-                    const uint32_t thr4 = a.drop_thresh * 0x01010101u;
+                    const uint32_t thr_h2 = (0x3c00u | a.drop_thresh) * 0x00010001u;
                     for (int g = 0; g < 2; ++g) {
                         const uint4 rnd = philox16((uint32_t)(key0 + part * 32 + g * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
                                                    seed_lo, seed_hi);
-                        // keep masks of four keys at a time: bytes of 0xff where the random byte is >= the threshold (six
-                        // integer instructions per word), widened to the two bf16 lanes of a packed pair by a byte permute
-                        // and ANDed into the packed probabilities.  The 1 / keep scale is applied once, in the epilogue.
+                        // the keep mask of a packed pair (keep_mask2) is ANDed into the packed probabilities; the 1 / keep scale
+                        // is applied once, in the epilogue
                         const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                         for (int i = 0; i < 16; i += 2) {
@@ -347,9 +357,7 @@ mha_fwd3_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                             unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[g * 16 + i]), __uint_as_float(r[g * 16 + i + 1])), c2, mc2), x0, x1);
                             const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
                             l2 = add_f32x2(l2, pack_f32x2(p0, p1));
-                            const uint32_t keep4 = __vcmpgeu4(rw[i >> 2], thr4);
-                            const uint32_t keep2 = __byte_perm(keep4, 0, (i & 2) ? 0x3322 : 0x1100);
-                            pk[(g * 16 + i) >> 1] = cvt_bf16x2(p0, p1) & keep2;
+                            pk[(g * 16 + i) >> 1] = cvt_bf16x2(p0, p1) & keep_mask2(rw[i >> 2], (i >> 1) & 1, thr_h2);
                         }
                     }
                     float la, lb;
@@ -1149,7 +1157,7 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive_warp(&bars->o_free[t]);        // the next item's first P V may overwrite O
-            const float inv = 1.0f / ep_l;
+            const float inv = (DROP ? a.inv_keep : 1.0f) / ep_l;      // with dropout the kept probabilities went into P V unscaled
             if (ep_qi < a.Lq) {
                 __nv_bfloat16* dst = a.out + (((size_t)ep_b * a.Lq + ep_qi) * a.Hh + ep_h) * kD;
 #pragma unroll
@@ -1322,25 +1330,43 @@ mha_fwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                         tmem_st16(tmem_p + 16 * q, pk_all[q]);
                     }
                 } else {
+                    // with dropout: the same packed pre-scaling pass, then exponentials, the row sum of the UNDROPPED
+                    // probabilities and the keep masks (keep_mask2: one byte permute + one packed fp16 compare per pair, ANDed
+                    // into the packed probabilities; the 1 / keep scale is applied in the epilogue)
+                    const uint64_t c2 = pack_f32x2(c, c);
+                    const uint64_t mc2 = pack_f32x2(-mc, -mc);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float x0, x1;
+                            unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(r[q][i]), __uint_as_float(r[q][i + 1])), c2, mc2), x0, x1);
+                            r[q][i] = __float_as_uint(x0);
+                            r[q][i + 1] = __float_as_uint(x1);
+                        }
+                    }
+                    const uint32_t thr_h2 = (0x3c00u | a.drop_thresh) * 0x00010001u;
                     if (pp) bar_sync_named(1 + t, 256);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         uint32_t (&pk)[16] = pk_all[q];
+                        uint64_t ls2 = pack_f32x2(0.0f, 0.0f);
 #pragma unroll
                         for (int g2 = 0; g2 < 2; ++g2) {
                             const uint4 rnd = philox16((uint32_t)(key0 + 32 * q + g2 * 16) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h),
                                                        seed_lo, seed_hi);
+                            const uint32_t rw[4] = {rnd.x, rnd.y, rnd.z, rnd.w};
 #pragma unroll
                             for (int i = 0; i < 16; i += 2) {
-                                float p0 = ex2_approx(fmaf(__uint_as_float(r[q][g2 * 16 + i]), c, -mc));
-                                float p1 = ex2_approx(fmaf(__uint_as_float(r[q][g2 * 16 + i + 1]), c, -mc));
-                                lsum[q] += p0 + p1;
-                                p0 = (philox_byte(rnd, i) < a.drop_thresh) ? 0.0f : p0 * a.inv_keep;
-                                p1 = (philox_byte(rnd, i + 1) < a.drop_thresh) ? 0.0f : p1 * a.inv_keep;
-                                const __nv_bfloat162 pb = __floats2bfloat162_rn(p0, p1);
-                                pk[(g2 * 16 + i) >> 1] = *reinterpret_cast<const uint32_t*>(&pb);
+                                const float p0 = ex2_approx(__uint_as_float(r[q][g2 * 16 + i]));
+                                const float p1 = ex2_approx(__uint_as_float(r[q][g2 * 16 + i + 1]));
+                                ls2 = add_f32x2(ls2, pack_f32x2(p0, p1));
+                                pk[(g2 * 16 + i) >> 1] = cvt_bf16x2(p0, p1) & keep_mask2(rw[i >> 2], (i >> 1) & 1, thr_h2);
                             }
                         }
+                        float l0, l1;
+                        unpack_f32x2(ls2, l0, l1);
+                        lsum[q] = l0 + l1;
                         tmem_st16(tmem_p + 16 * q, pk);
                     }
                 }
@@ -1896,8 +1922,8 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel, 40 = always mha_fwdp_kernel.
     const int variant = get_opt("mha_variant");
     const bool drop = a.drop_thresh > 0;
-    const bool one_tile = variant == 3 || (variant != 21 && variant != 40 && (drop || Lq <= kBM));
-    const bool persistent = !drop && !one_tile && (variant == 40 || variant == 0);
+    const bool one_tile = variant == 3 || (variant != 21 && variant != 40 && Lq <= kBM);
+    const bool persistent = !one_tile && (variant == 40 || variant == 0);
     static bool attr_done[4] = {false, false, false, false};      // cudaFuncSetAttribute once per kernel, not per call
     if (one_tile) {
         dim3 grid((Lq + kBM - 1) / kBM, Hh, B);
@@ -1913,9 +1939,16 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
         if (persistent) {
             const int nq2 = (Lq + 2 * kBM - 1) / (2 * kBM);
             const int n_items = B * Hh * nq2;
-            static bool done = false;
-            if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPSmem)); done = true; }
-            mha_fwdp_kernel<false><<<dim3(std::min(n_items, num_sms())), kFwd8Threads, kFwdPSmem, st>>>(tq, tk, tv, a, n_items, nq2);
+            const dim3 pgrid(std::min(n_items, num_sms()));
+            if (drop) {
+                static bool done = false;
+                if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPSmem)); done = true; }
+                mha_fwdp_kernel<true><<<pgrid, kFwd8Threads, kFwdPSmem, st>>>(tq, tk, tv, a, n_items, nq2);
+            } else {
+                static bool done = false;
+                if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPSmem)); done = true; }
+                mha_fwdp_kernel<false><<<pgrid, kFwd8Threads, kFwdPSmem, st>>>(tq, tk, tv, a, n_items, nq2);
+            }
         } else
         if (drop) {
             if (!attr_done[2]) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_fwd8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd8Smem)); attr_done[2] = true; }
