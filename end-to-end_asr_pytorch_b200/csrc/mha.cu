@@ -1906,19 +1906,14 @@ static int mha_fwd_impl(const void* q, const void* k, const void* v, const int* 
     a.seed_hi = (uint32_t)(seed >> 32);
     a.seed_dev = seed_dev;
     // Three kernels (the earlier generations are gone, DESIGN.md 4 keeps their numbers):
-    //   mha_fwd8_kernel<DROP>      CTA = two 128-query tiles sharing every K/V tile, one thread per query row, P in
-    //                              tensor memory, one CTA per (batch, head, 256 queries): L = 2048 707 TFLOP/s; kept as the
-    //                              reference point of the persistent kernel (mha_variant = 21)
-    //   mha_fwd3_kernel<DROP>      CTA = one 128-query tile, two threads per row, two CTAs per SM: with dropout (the
-    //                              Philox work per element favours two threads per row: 418 vs 312 TFLOP/s) and for short
-    //                              query sequences (Lq <= 128: the second tile of a 256-query CTA would be empty; model
-    //                              shapes are L = 21 .. 167, U <= 15)
-    //   mha_fwdp_kernel<DROP>      the two-tile kernel with the work items looped inside one CTA per SM (set-up, first loads,
-    //                              epilogue and CTA turnaround overlap the neighbouring items; causal items dealt longest
-    //                              first in snake order): every two-tile call without dropout.  Measured against
-    //                              mha_fwd8_kernel on B200 (tools/mha_persistent_sweep.py), time: L = 167 -11 %, 256 -17 %,
-    //                              512 -13 %, 1024 -6 %, 2048 -3 %, 4096 equal; causal: -19 % at 256, -14 % at 512,
-    //                              -8 % at 1024, -11 % at 2048 and 4096
+    //   mha_fwdp_kernel<DROP>      PERSISTENT: one CTA per SM walks the (batch, head, 256-query) items; per item two 128-query
+    //                              tiles share every K/V tile, one thread per query row, P in tensor memory.  Every call with
+    //                              more than 128 queries, with and without dropout (L = 2048: 722 TFLOP/s, 537 with dropout)
+    //   mha_fwd8_kernel<DROP>      the same inner structure with one CTA per item (L = 2048: 707 TFLOP/s): the reference point
+    //                              of the persistent kernel (mha_variant = 21; outputs bit-identical without dropout)
+    //   mha_fwd3_kernel<DROP>      CTA = one 128-query tile, two threads per row, two CTAs per SM: short query sequences
+    //                              (Lq <= 128: the second tile of a 256-query item would be empty; model shapes are
+    //                              L = 21 .. 167, U <= 15); with dropout at L = 2048: 481 TFLOP/s
     // "mha_variant": 0 = that rule, 3 = always mha_fwd3_kernel, 21 = always mha_fwd8_kernel, 40 = always mha_fwdp_kernel.
     const int variant = get_opt("mha_variant");
     const bool drop = a.drop_thresh > 0;
