@@ -1436,6 +1436,7 @@ struct __align__(8) MhaBwdBarriers {
     uint64_t sdp_full;
     uint64_t pds_full;
     uint64_t dq_full;
+    uint64_t dq_free;      // DQW: the dQ warps have read the dQ accumulator of a tile
     uint32_t tmem_base;
     uint32_t pad;
     uint32_t seed[2];      // effective dropout seed (kept in shared memory: the 16-warp instance has no register to spare)
@@ -1463,8 +1464,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // (warp w: TMEM lane quarter w % 4 = query rows, column group w / 4).  One warp per SM
 // sub-partition (CG = 1) leaves every dependent instruction's latency exposed; 4 per
 // sub-partition hide it.
-template <int CG, bool DROP>
-__global__ void __launch_bounds__(128 * CG + 64, 1)
+// DQW: four more warps (one per TMEM lane quarter) take dQ out of the CTA: they wait for a tile's dQ = dS K, read it from
+// tensor memory, stage it in shared memory and issue the bulk reduce-add, while the softmax-backward warps are already on the
+// next tile.  On those warps' own timeline (clock64: ~4900 cycles per 128 x 128 tile = softmax 1600-2000 + P / dS store +
+// hand-over ~700 + dQ load and flush 900-1500 + loop top ~800) the flush was a quarter; the tensor pipe needs 1280 cycles
+// per tile.  24 warps (16 softmax, TMA, MMA, two idle, four dQ) at 80 registers, reallocated with setmaxnreg to 96 / 40 / 56.
+template <int CG, bool DROP, bool DQW = false>
+__global__ void __launch_bounds__(DQW ? 768 : 128 * CG + 64, 1)
 mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
                const __grid_constant__ CUtensorMap tm_dqacc, const MhaBwdArgs a) {
@@ -1501,6 +1507,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         mbar_init(&bars->sdp_full, 1);
         mbar_init(&bars->pds_full, 4 * CG);   // one arrival per softmax warp
         mbar_init(&bars->dq_full, 1);
+        mbar_init(&bars->dq_free, 4);
         fence_mbar_init();
         if (DROP) {
             uint32_t lo = a.seed_lo, hi = a.seed_hi;
@@ -1520,6 +1527,43 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const uint32_t tmem = bars->tmem_base;
     const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
 
+    static_assert(!DQW || CG == 4, "the dQ warps come with the 16-warp instance");
+    if (DQW && warp >= 4 * CG && warp < 4 * CG + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // TMA, MMA, two idle warps
+    if (DQW && warp >= 4 * CG + 4) {
+        // ===== dQ warps: thread = query row of the tile =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        const bool lead = (warp == 4 * CG + 4) && lane == 0;
+        for (int it = 0; it < nsteps; ++it) {
+            mbar_wait(&bars->dq_full, it & 1);
+            tc_fence_after();
+            if (lead) bulk_wait_read0();                      // the previous tile's reduce has read the staging
+            bar_sync_named(1, 128);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {                  // columns 0-31 | 32-63: one [128 x 32] fp32 box each
+                float dq[32];
+                tmem_ld32(tm_dq + lane_base + 32 * hf, dq);
+                unsigned char* dst = sDQ + hf * kTileBytes + row * 128;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const int chunk = (i >> 2) ^ (row & 7);
+                    *reinterpret_cast<float4*>(dst + chunk * 16) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_warp(&bars->dq_free);                 // the accumulator may take the next tile's dS K
+            fence_proxy_async();
+            bar_sync_named(2, 128);
+            if (lead) {
+                tma_reduce_add_4d(&tm_dqacc, sDQ, 0, h, (i_start + it) * kBM, b);
+                tma_reduce_add_4d(&tm_dqacc, sDQ + kTileBytes, 32, h, (i_start + it) * kBM, b);
+                bulk_commit();
+            }
+        }
+        if (lead && nsteps > 0) bulk_wait0();                 // the reduces must have landed before the kernel ends
+    } else
     if (warp == kTmaWarp) {
         // ===== TMA producer =====
         if (nsteps > 0 && elect_one_sync()) {
@@ -1584,6 +1628,10 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                               smem_desc_sw128(q_addr + kk * 2048, kTileBytes, 1024), id_t, (it > 0 || kk > 0) ? 1u : 0u);
                 }
                 // contraction over the 128 keys: dS K-major (two 64-key halves), K tile MN-major
+                if (DQW && it > 0) {
+                    mbar_wait(&bars->dq_free, (it - 1) & 1);      // the dQ warps have read the previous tile's dQ
+                    tc_fence_after();
+                }
 #pragma unroll
                 for (int kk = 0; kk < kBN / 16; ++kk) {
                     umma_bf16(tm_dq, smem_desc_sw128(ds_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024),
@@ -1593,8 +1641,11 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 tc_commit(&bars->qdo_empty[s]);
             }
         }
+    } else if (warp >= 4 * CG) {
+        // (DQW: the two idle warps of the utility warpgroup)
     } else {
         // ===== softmax-backward warps: thread = (query row of the tile, column group); key row in the epilogue =====
+        if (DQW) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
         const int row = (warp & 3) * 32 + lane;
         const int cg = warp >> 2;
         constexpr int kColsS = kBN / CG;    // S / dP columns of this thread
@@ -1712,7 +1763,7 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 // dV/dK/dQ of the previous tile are done: its P/dS tiles are free and its dQ is in TMEM
                 mbar_wait(&bars->dq_full, (it - 1) & 1);
                 tc_fence_after();
-                load_dq(dq);
+                if (!DQW) load_dq(dq);
             }
 #pragma unroll
             for (int c0 = 0; c0 < kColsS; c0 += 32) {
@@ -1730,15 +1781,17 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive_warp(&bars->pds_full);
-            if (it > 0) flush_dq(dq, i_start + it - 1);
+            if (!DQW && it > 0) flush_dq(dq, i_start + it - 1);
         }
         if (nsteps > 0) {
-            float dq[kColsD];
-            mbar_wait(&bars->dq_full, (nsteps - 1) & 1);
+            mbar_wait(&bars->dq_full, (nsteps - 1) & 1);      // every product of the key tile is done: dK, dV are final
             tc_fence_after();
-            load_dq(dq);
-            flush_dq(dq, i_start + nsteps - 1);
-            if (dq_issuer) bulk_wait0();    // the reduce must have landed before the kernel ends
+            if (!DQW) {
+                float dq[kColsD];
+                load_dq(dq);
+                flush_dq(dq, i_start + nsteps - 1);
+                if (dq_issuer) bulk_wait0();    // the reduce must have landed before the kernel ends
+            }
         }
         // epilogue: dK_j, dV_j (thread = key row, kColsD columns).  The TMEM loads are warp-collective,
         // so every thread issues them; only rows inside the sequence store.
@@ -2057,7 +2110,17 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
     a.seed_dev = seed_dev;
     const bool drop = a.drop_thresh > 0;
     dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
-    const int cgo = get_opt("mha_bwd_groups");   // softmax-backward warps = 4 * groups; 0 = default (4)
+    const int cgo = get_opt("mha_bwd_groups");   // 0 / 5 = 16 softmax-backward warps + 4 dQ warps (default), 4 = 16 warps that
+                                                 // also flush dQ, 2 = 8 warps
+#define ASR_LAUNCH_BWD_DQW(DR)                                                                                              \
+    do {                                                                                                                   \
+        static bool attr_done = false;                                                                                     \
+        if (!attr_done) {                                                                                                  \
+            ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwd_kernel<4, DR, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); \
+            attr_done = true;                                                                                              \
+        }                                                                                                                  \
+        mha_bwd_kernel<4, DR, true><<<grid, 768, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);                                  \
+    } while (0)
 #define ASR_LAUNCH_BWD(CGV, DR)                                                                                              \
     do {                                                                                                                   \
         static bool attr_done = false;                                                                                     \
@@ -2067,12 +2130,15 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
         }                                                                                                                  \
         mha_bwd_kernel<CGV, DR><<<grid, 128 * CGV + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);                          \
     } while (0)
-    if (cgo == 2) {
+    if (cgo == 0 || cgo == 5) {          // default: the 16-warp instance with dedicated dQ warps
+        if (drop) ASR_LAUNCH_BWD_DQW(true); else ASR_LAUNCH_BWD_DQW(false);
+    } else if (cgo == 2) {
         if (drop) ASR_LAUNCH_BWD(2, true); else ASR_LAUNCH_BWD(2, false);
     } else {
         if (drop) ASR_LAUNCH_BWD(4, true); else ASR_LAUNCH_BWD(4, false);
     }
 #undef ASR_LAUNCH_BWD
+#undef ASR_LAUNCH_BWD_DQW
     ASR_LAUNCH_CHECK();
     size_t blocks = (nq_elems / 4 + 255) / 256;
     if (blocks > (size_t)num_sms() * 16) blocks = (size_t)num_sms() * 16;
