@@ -1835,6 +1835,407 @@ mha_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
+// ---- backward, persistent: the 16 + 4-warp kernel above with the (batch, head, key tile) items looped inside one CTA per SM
+// Per CTA the one-item kernel pays ~9000 cycles around its query-tile loop (barrier / tensor-memory set-up, the first K, V, Q,
+// dO loads and products, the dK / dV epilogue, the SM's turnaround to the next CTA): 11 % at L = 2048, most of the call at the
+// model's shapes (two query tiles per key tile).  Here the roles keep running across items: the Q / dO ring and the per-tile
+// barriers continue on CTA-wide tile counters; K / V of the next item are fetched as soon as the last products of the current
+// item have read them (kv_free), i.e. under the epilogue; the next item's first S / dP products go out as soon as K / V have
+// landed, and its first dV / dK products - which overwrite the accumulators - wait for acc_free (the epilogue has read dK, dV).
+// Causal items cost (number of query tiles - key tile index) tiles: they are dealt longest first in snake order.
+struct __align__(8) MhaBwdBarriersP {
+    uint64_t kv_full, kv_free;
+    uint64_t qdo_full[2];
+    uint64_t qdo_empty[2];
+    uint64_t sdp_full;
+    uint64_t pds_full;
+    uint64_t dq_full;
+    uint64_t dq_free;
+    uint64_t acc_free;
+    uint32_t tmem_base;
+    uint32_t pad;
+    uint32_t seed[2];
+};
+static_assert(sizeof(MhaBwdBarriersP) <= 128, "barrier block of the persistent backward kernel");
+
+struct MhaBwdItem {
+    int b, h, key0, i_start, nsteps;
+};
+struct MhaBwdWalk {
+    int k, left, n_bh, nkt;
+    bool causal;
+    __device__ __forceinline__ MhaBwdWalk(const MhaBwdArgs& a, int n_items, int nkt_) : nkt(nkt_) {
+        const int first = blockIdx.x, step = gridDim.x;
+        left = first < n_items ? (n_items - 1 - first) / step + 1 : 0;
+        k = 0;
+        n_bh = a.B * a.Hh;
+        causal = a.causal != 0 && a.dense_mask == nullptr;
+    }
+    __device__ __forceinline__ bool valid() const { return left > 0; }
+    __device__ __forceinline__ void next() { --left; ++k; }
+    __device__ __forceinline__ MhaBwdItem get(const MhaBwdArgs& a) const {
+        const int G = gridDim.x, c = blockIdx.x;
+        int jt, bh;
+        if (causal) {
+            // longest first (key tile 0 sees every query tile), snake order over the CTAs; a ragged last visit maps straight
+            const int total = n_bh * nkt;
+            const int p = k * G + ((k & 1) ? G - 1 - c : c);
+            const int pp = p < total ? p : k * G + c;
+            jt = pp / n_bh;
+            bh = pp - jt * n_bh;
+        } else {
+            const int item = k * G + c;            // key tiles of one (batch, head) next to each other: Q / dO stay in L2
+            bh = item / nkt;
+            jt = item - bh * nkt;
+        }
+        MhaBwdItem it;
+        it.b = bh / a.Hh;
+        it.h = bh - it.b * a.Hh;
+        it.key0 = jt * kBN;
+        const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + it.b), 0), a.Lk) : a.Lk;
+        const int nq = (a.Lq + kBM - 1) / kBM;
+        it.i_start = a.causal ? (it.key0 / kBM) : 0;
+        if (a.dense_mask == nullptr && it.key0 >= kvlen) it.i_start = nq;      // a key tile that is entirely padding
+        it.nsteps = max(0, nq - it.i_start);
+        return it;
+    }
+};
+
+template <bool DROP>
+__global__ void __launch_bounds__(768, 1)
+mha_bwdp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_dqacc, const MhaBwdArgs a, const int n_items, const int nkt) {
+    constexpr int CG = 4;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    unsigned char* sK = smem;
+    unsigned char* sV = sK + kTileBytes;
+    unsigned char* sQ = sV + kTileBytes;            // 2 stages
+    unsigned char* sDO = sQ + 2 * kTileBytes;       // 2 stages
+    unsigned char* sP = sDO + 2 * kTileBytes;       // [2][128][128B]
+    unsigned char* sDS = sP + 2 * kTileBytes;       // [2][128][128B]
+    unsigned char* sDQ = sDS + 2 * kTileBytes;      // [2][128][128B] fp32 staging of one dQ tile (columns 0-31 | 32-63)
+    MhaBwdBarriersP* bars = reinterpret_cast<MhaBwdBarriersP*>(sDQ + 2 * kTileBytes);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->kv_full, 1);
+        mbar_init(&bars->kv_free, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&bars->qdo_full[s], 1);
+            mbar_init(&bars->qdo_empty[s], 1);
+        }
+        mbar_init(&bars->sdp_full, 1);
+        mbar_init(&bars->pds_full, 4 * CG);   // one arrival per softmax warp
+        mbar_init(&bars->dq_full, 1);
+        mbar_init(&bars->dq_free, 4);
+        mbar_init(&bars->acc_free, 4 * CG);
+        fence_mbar_init();
+        if (DROP) {
+            uint32_t lo = a.seed_lo, hi = a.seed_hi;
+            effective_seed(a.seed_dev, lo, hi);
+            bars->seed[0] = lo;
+            bars->seed[1] = hi;
+        }
+    }
+    constexpr int kTmaWarp = 4 * CG, kMmaWarp = 4 * CG + 1;
+    if (warp == kMmaWarp) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+
+    // CTA-wide counters, kept alike by every role: g = query tiles processed before the current item, m = items with at
+    // least one tile before the current one (phases of kv_full / kv_free / acc_free)
+    if (warp >= 4 * CG && warp < 4 * CG + 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // TMA, MMA, two idle warps
+    if (warp >= 4 * CG + 4) {
+        // ===== dQ warps: thread = query row of the tile =====
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        const bool lead = (warp == 4 * CG + 4) && lane == 0;
+        int g = 0;
+        for (MhaBwdWalk walk(a, n_items, nkt); walk.valid(); walk.next()) {
+            const MhaBwdItem item = walk.get(a);
+            for (int it = 0; it < item.nsteps; ++it, ++g) {
+                mbar_wait(&bars->dq_full, g & 1);
+                tc_fence_after();
+                if (lead) bulk_wait_read0();                      // the previous tile's reduce has read the staging
+                bar_sync_named(1, 128);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {                  // columns 0-31 | 32-63: one [128 x 32] fp32 box each
+                    float dq[32];
+                    tmem_ld32(tm_dq + lane_base + 32 * hf, dq);
+                    unsigned char* dst = sDQ + hf * kTileBytes + row * 128;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const int chunk = (i >> 2) ^ (row & 7);
+                        *reinterpret_cast<float4*>(dst + chunk * 16) = make_float4(dq[i], dq[i + 1], dq[i + 2], dq[i + 3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_warp(&bars->dq_free);                 // the accumulator may take the next tile's dS K
+                fence_proxy_async();
+                bar_sync_named(2, 128);
+                if (lead) {
+                    tma_reduce_add_4d(&tm_dqacc, sDQ, 0, item.h, (item.i_start + it) * kBM, item.b);
+                    tma_reduce_add_4d(&tm_dqacc, sDQ + kTileBytes, 32, item.h, (item.i_start + it) * kBM, item.b);
+                    bulk_commit();
+                }
+            }
+        }
+        if (lead) bulk_wait0();                                   // the reduces must have landed before the kernel ends
+    } else if (warp == kTmaWarp) {
+        // ===== TMA producer =====
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_q);
+            tma_prefetch_desc(&tm_do);
+            tma_prefetch_desc(&tm_k);
+            tma_prefetch_desc(&tm_v);
+            int g = 0, m = 0;
+            for (MhaBwdWalk walk(a, n_items, nkt); walk.valid(); walk.next()) {
+                const MhaBwdItem item = walk.get(a);
+                if (item.nsteps == 0) continue;
+                if (m > 0) mbar_wait(&bars->kv_free, (m - 1) & 1);     // the previous item's last products have read K, V
+                mbar_arrive_expect_tx(&bars->kv_full, 2 * kTileBytes);
+                tma_load_4d(sK, &tm_k, 0, item.h, item.key0, item.b, &bars->kv_full);
+                tma_load_4d(sV, &tm_v, 0, item.h, item.key0, item.b, &bars->kv_full);
+                for (int it = 0; it < item.nsteps; ++it, ++g) {
+                    const int s = g & 1;
+                    if (g >= 2) mbar_wait(&bars->qdo_empty[s], ((g >> 1) - 1) & 1);
+                    mbar_arrive_expect_tx(&bars->qdo_full[s], 2 * kTileBytes);
+                    tma_load_4d(sQ + s * kTileBytes, &tm_q, 0, item.h, (item.i_start + it) * kBM, item.b, &bars->qdo_full[s]);
+                    tma_load_4d(sDO + s * kTileBytes, &tm_do, 0, item.h, (item.i_start + it) * kBM, item.b, &bars->qdo_full[s]);
+                }
+                ++m;
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ===== MMA issuer =====
+        // Order on the tensor pipe: S/dP of tile t+1 go BEFORE dV/dK/dQ of tile t, so the softmax warps can start on tile
+        // t+1 while the three accumulating products of tile t run.  Across an item boundary "tile t+1" is the first tile of
+        // the next item, whose S / dP need the next item's K, V: they follow the current item's last dV / dK / dQ instead.
+        if (elect_one_sync()) {
+            constexpr uint32_t id_s = make_idesc(kBM, kBN, 0, 0);     // S  = Q K^T   / dP = dO V^T
+            constexpr uint32_t id_t = make_idesc(kBN, kD, 1, 1);      // dV = P^T dO  / dK = dS^T Q  (A and B MN-major)
+            constexpr uint32_t id_q = make_idesc(kBM, kD, 0, 1);      // dQ = dS K    (A K-major, B MN-major)
+            const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+            const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sDS);
+            auto issue_sdp = [&](int gt) {
+                const int s = gt & 1;
+                const uint32_t q_addr = smem_u32(sQ + s * kTileBytes);
+                const uint32_t do_addr = smem_u32(sDO + s * kTileBytes);
+                mbar_wait(&bars->qdo_full[s], (gt >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tm_s, smem_desc_sw128(q_addr + kk * 32, 16, 1024), smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                              id_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+                for (int kk = 0; kk < kD / 16; ++kk)
+                    umma_bf16(tm_dp, smem_desc_sw128(do_addr + kk * 32, 16, 1024), smem_desc_sw128(v_addr + kk * 32, 16, 1024),
+                              id_s, kk > 0 ? 1u : 0u);
+                tc_commit(&bars->sdp_full);
+            };
+            int g = 0, m = 0;
+            for (MhaBwdWalk walk(a, n_items, nkt); walk.valid(); walk.next()) {
+                const MhaBwdItem item = walk.get(a);
+                if (item.nsteps == 0) continue;
+                mbar_wait(&bars->kv_full, m & 1);
+                // S / dP of the item's first tile: the S / dP columns are free (the softmax warps arrived on pds_full of the
+                // previous tile after reading them; that barrier was waited for before the previous tile's products)
+                issue_sdp(g);
+                for (int it = 0; it < item.nsteps; ++it, ++g) {
+                    const int s = g & 1;
+                    const uint32_t q_addr = smem_u32(sQ + s * kTileBytes);
+                    const uint32_t do_addr = smem_u32(sDO + s * kTileBytes);
+                    // P/dS of this tile are in shared memory; S/dP (TMEM) have been read
+                    mbar_wait(&bars->pds_full, g & 1);
+                    tc_fence_after();
+                    if (it + 1 < item.nsteps) issue_sdp(g + 1);
+                    if (it == 0 && m > 0) {
+                        mbar_wait(&bars->acc_free, (m - 1) & 1);      // the previous item's epilogue has read dK, dV
+                        tc_fence_after();
+                    }
+                    // contraction over the 128 queries of the tile: 8 steps of 16 rows (2048 bytes)
+#pragma unroll
+                    for (int kk = 0; kk < kBM / 16; ++kk) {
+                        umma_bf16(tm_dv, smem_desc_sw128(p_addr + kk * 2048, kTileBytes, 1024),
+                                  smem_desc_sw128(do_addr + kk * 2048, kTileBytes, 1024), id_t, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < kBM / 16; ++kk) {
+                        umma_bf16(tm_dk, smem_desc_sw128(ds_addr + kk * 2048, kTileBytes, 1024),
+                                  smem_desc_sw128(q_addr + kk * 2048, kTileBytes, 1024), id_t, (it > 0 || kk > 0) ? 1u : 0u);
+                    }
+                    // contraction over the 128 keys: dS K-major (two 64-key halves), K tile MN-major
+                    if (g > 0) {
+                        mbar_wait(&bars->dq_free, (g - 1) & 1);       // the dQ warps have read the previous tile's dQ
+                        tc_fence_after();
+                    }
+#pragma unroll
+                    for (int kk = 0; kk < kBN / 16; ++kk) {
+                        umma_bf16(tm_dq, smem_desc_sw128(ds_addr + (kk >> 2) * kTileBytes + (kk & 3) * 32, 16, 1024),
+                                  smem_desc_sw128(k_addr + kk * 2048, kTileBytes, 1024), id_q, kk > 0 ? 1u : 0u);
+                    }
+                    tc_commit(&bars->dq_full);
+                    tc_commit(&bars->qdo_empty[s]);
+                    if (it + 1 == item.nsteps) tc_commit(&bars->kv_free);     // K, V may be overwritten behind these products
+                }
+                ++m;
+            }
+        }
+    } else if (warp >= 4 * CG) {
+        // (the two idle warps of the utility warpgroup)
+    } else {
+        // ===== softmax-backward warps: thread = (query row of the tile, column group); key row in the epilogue =====
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        const int row = (warp & 3) * 32 + lane;
+        const int cg = warp >> 2;
+        constexpr int kColsS = kBN / CG;    // S / dP columns of this thread
+        constexpr int kColsD = kD / CG;     // dK / dV columns of this thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        const float c = a.scale_log2;
+        int g = 0;
+        for (MhaBwdWalk walk(a, n_items, nkt); walk.valid(); walk.next()) {
+            const MhaBwdItem item = walk.get(a);
+            const int b = item.b, h = item.h, key0 = item.key0, i_start = item.i_start, nsteps = item.nsteps;
+            const int kvlen = a.kv_len ? min(max(__ldg(a.kv_len + b), 0), a.Lk) : a.Lk;
+            // row statistics of the next tile are fetched one tile ahead
+            auto load_stats = [&](int it, float& lse2_o, float& dlt_o) {
+                const int qi = (i_start + it) * kBM + row;
+                const bool ok = it < nsteps && qi < a.Lq;
+                const size_t stat = ((size_t)b * a.Hh + h) * a.Lq + (ok ? qi : 0);
+                lse2_o = ok ? __ldg(a.lse + stat) * 1.4426950408889634f : INFINITY;
+                dlt_o = ok ? __ldg(a.delta + stat) : 0.0f;
+            };
+            float lse2_n, dlt_n;
+            load_stats(0, lse2_n, dlt_n);
+            for (int it = 0; it < nsteps; ++it, ++g) {
+                const int qi = (i_start + it) * kBM + row;
+                const float lse2 = lse2_n, dlt = dlt_n;
+                load_stats(it + 1, lse2_n, dlt_n);
+                int lim = kvlen;
+                if (a.causal) lim = min(lim, qi + 1);
+                const uint8_t* mrow = a.dense_mask ? a.dense_mask + ((size_t)b * a.Lq + min(qi, a.Lq - 1)) * a.Lk : nullptr;
+                const bool need_mask = (key0 + kBN > lim) || (mrow != nullptr);
+                uint32_t dead = 0;               // dead keys among this thread's 32 columns
+                if (__builtin_expect(need_mask, 0)) {
+                    const int first = key0 + cg * kColsS;
+                    const int live = lim - first;
+                    dead = live >= kColsS ? 0u : live <= 0 ? 0xffffffffu : (0xffffffffu << live);
+                    if (mrow != nullptr) {
+                        const int kmax = min(kColsS, a.Lk - first);
+#pragma unroll 1
+                        for (int kk = 0; kk < kmax; ++kk) dead |= (uint32_t)(mrow[first + kk] != 0) << kk;
+                    }
+                }
+                uint32_t pk[kColsS / 2], dk[kColsS / 2];
+                mbar_wait(&bars->sdp_full, g & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c0 = 0; c0 < kColsS; c0 += 16) {
+                    const int cc = cg * kColsS + c0;
+                    float sv[16], dp[16];
+                    tmem_ld16(tm_s + lane_base + cc, sv);
+                    tmem_ld16(tm_dp + lane_base + cc, dp);
+                    uint4 rnd[1];
+                    if (DROP) rnd[0] = philox16((uint32_t)(key0 + cc) >> 4, (uint32_t)qi, (uint32_t)(b * a.Hh + h), bars->seed[0], bars->seed[1]);
+                    const uint64_t c2 = pack_f32x2(c, c), nl2 = pack_f32x2(-lse2, -lse2);
+                    const uint64_t sc2 = pack_f32x2(a.scale, a.scale), nd2 = pack_f32x2(-dlt * a.scale, -dlt * a.scale);
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float x0, x1;
+                        unpack_f32x2(fma_f32x2(pack_f32x2(sv[i], sv[i + 1]), c2, nl2), x0, x1);
+                        float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
+                        if ((dead >> (c0 + i)) & 1u) p0 = 0.0f;
+                        if ((dead >> (c0 + i + 1)) & 1u) p1 = 0.0f;
+                        const uint64_t p2 = pack_f32x2(p0, p1);
+                        uint64_t g2 = pack_f32x2(dp[i], dp[i + 1]);      // d(loss)/d(dropped, rescaled probability)
+                        uint64_t pd2 = p2;                               // the probabilities P V was computed with
+                        if (DROP) {
+                            const float k0 = philox_byte(rnd[0], i) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const float k1 = philox_byte(rnd[0], i + 1) >= a.drop_thresh ? a.inv_keep : 0.0f;
+                            const uint64_t kf2 = pack_f32x2(k0, k1);
+                            g2 = mul_f32x2(g2, kf2);
+                            pd2 = mul_f32x2(p2, kf2);
+                        }
+                        float s0, s1, q0, q1;
+                        unpack_f32x2(mul_f32x2(p2, fma_f32x2(g2, sc2, nd2)), s0, s1);
+                        unpack_f32x2(pd2, q0, q1);
+                        pk[(c0 + i) >> 1] = cvt_bf16x2(q0, q1);
+                        dk[(c0 + i) >> 1] = cvt_bf16x2(s0, s1);
+                    }
+                }
+                if (g > 0) {
+                    // dV/dK/dQ of the previous tile (of this item or the one before) are done: the P / dS tiles are free
+                    mbar_wait(&bars->dq_full, (g - 1) & 1);
+                    tc_fence_after();
+                }
+#pragma unroll
+                for (int c0 = 0; c0 < kColsS; c0 += 32) {
+                    const int cc = cg * kColsS + c0;
+                    const int off = (cc >> 6) * kTileBytes + row * 128;
+                    const int chunk0 = (cc & 63) >> 3;
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int chunk = (chunk0 + q4) ^ (row & 7);
+                        const int w0 = (c0 >> 1) + 4 * q4;
+                        *reinterpret_cast<uint4*>(sP + off + chunk * 16) = make_uint4(pk[w0], pk[w0 + 1], pk[w0 + 2], pk[w0 + 3]);
+                        *reinterpret_cast<uint4*>(sDS + off + chunk * 16) = make_uint4(dk[w0], dk[w0 + 1], dk[w0 + 2], dk[w0 + 3]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive_warp(&bars->pds_full);
+            }
+            // epilogue: dK_j, dV_j (thread = key row, kColsD columns)
+            float acc[2][kColsD];
+            if (nsteps > 0) {
+                mbar_wait(&bars->dq_full, (g - 1) & 1);      // every product of the key tile is done: dK, dV are final
+                tc_fence_after();
+                tmem_ld16(tm_dk + lane_base + cg * kColsD, acc[0]);
+                tmem_ld16(tm_dv + lane_base + cg * kColsD, acc[1]);
+                tc_fence_before();
+                mbar_arrive_warp(&bars->acc_free);           // the next item's first dV / dK products may overwrite them
+            } else {
+#pragma unroll
+                for (int i = 0; i < kColsD; ++i) acc[0][i] = acc[1][i] = 0.0f;
+            }
+            const int key = key0 + row;
+            if (key < a.Lk) {
+                const size_t kv_off = (((size_t)b * a.Lk + key) * a.Hh + h) * kD + cg * kColsD;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {
+                    __nv_bfloat16* dst = (part == 0 ? a.g_k : a.g_v) + kv_off;
+#pragma unroll
+                    for (int i = 0; i < kColsD; i += 8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) w[u] = cvt_bf16x2(acc[part][i + 2 * u], acc[part][i + 2 * u + 1]);
+                        *reinterpret_cast<uint4*>(dst + i) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // delta[b,h,q] = sum_d dO[b,q,h,d] * O[b,q,h,d]   (one warp per row of 64)
 // (also clears the row's 64 floats of the dQ accumulator [B,Lq,Hh,64], which has the same row order: one launch
 // instead of a memset + this kernel)
@@ -2110,8 +2511,8 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
     a.seed_dev = seed_dev;
     const bool drop = a.drop_thresh > 0;
     dim3 grid((Lk + kBN - 1) / kBN, Hh, B);
-    const int cgo = get_opt("mha_bwd_groups");   // 0 / 5 = 16 softmax-backward warps + 4 dQ warps (default), 4 = 16 warps that
-                                                 // also flush dQ, 2 = 8 warps
+    const int cgo = get_opt("mha_bwd_groups");   // 0 / 7 = persistent kernel (16 softmax-backward warps + 4 dQ warps; default),
+                                                 // 5 = the same with one CTA per item, 4 = 16 warps that also flush dQ, 2 = 8 warps
 #define ASR_LAUNCH_BWD_DQW(DR)                                                                                              \
     do {                                                                                                                   \
         static bool attr_done = false;                                                                                     \
@@ -2130,7 +2531,20 @@ static int mha_bwd_impl(const void* q, const void* k, const void* v, const void*
         }                                                                                                                  \
         mha_bwd_kernel<CGV, DR><<<grid, 128 * CGV + 64, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a);                          \
     } while (0)
-    if (cgo == 0 || cgo == 5) {          // default: the 16-warp instance with dedicated dQ warps
+    if (cgo == 0 || cgo == 7) {          // default, persistent: one CTA per SM walks the (batch, head, key tile) items
+        const int nkt = (Lk + kBN - 1) / kBN;
+        const int n_items = B * Hh * nkt;
+        const dim3 pgrid(std::min(n_items, num_sms()));
+        if (drop) {
+            static bool done = false;
+            if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwdp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); done = true; }
+            mha_bwdp_kernel<true><<<pgrid, 768, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a, n_items, nkt);
+        } else {
+            static bool done = false;
+            if (!done) { ASR_CHECK_CUDA(cudaFuncSetAttribute(mha_bwdp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem)); done = true; }
+            mha_bwdp_kernel<false><<<pgrid, 768, kBwdSmem, st>>>(tq, tk, tv, tdo, tdq, a, n_items, nkt);
+        }
+    } else if (cgo == 5) {               // one CTA per item: the 16-warp instance with dedicated dQ warps
         if (drop) ASR_LAUNCH_BWD_DQW(true); else ASR_LAUNCH_BWD_DQW(false);
     } else if (cgo == 2) {
         if (drop) ASR_LAUNCH_BWD(2, true); else ASR_LAUNCH_BWD(2, false);

@@ -15,12 +15,13 @@ MHA = load_golden("mha")
 CASES = ["self_pad", "self_causal", "cross", "nomask"]
 
 
-@pytest.fixture(autouse=True, params=[(0, 0), (3, 2), (21, 0), (40, 0), (0, 4)],
-                ids=["auto", "one_tile_kernel_bwd8w", "two_tile_kernel", "persistent_two_tile_kernel", "bwd_16_warps_flush_dq"])
+@pytest.fixture(autouse=True, params=[(0, 0), (3, 2), (21, 0), (40, 0), (0, 4), (0, 5)],
+                ids=["auto", "one_tile_kernel_bwd8w", "two_tile_kernel", "persistent_two_tile_kernel", "bwd_16_warps_flush_dq", "bwd_one_cta_per_item"])
 def fwd_variant(request):
     """The two forward kernels (auto picks by shape / dropout; 3 = always one 128-query tile per CTA, two threads per
     row; 21 = always two tiles per CTA, one thread per row; 40 = always the persistent kernel) and the softmax-backward
-    layouts (default: 16 warps + 4 dQ warps; 4 = 16 warps that flush dQ themselves; 2 = 8 warps)."""
+    layouts (default: persistent kernel, 16 warps + 4 dQ warps; 5 = the same with one CTA per key tile; 4 = 16 warps that
+    flush dQ themselves; 2 = 8 warps)."""
     lib = pkg("_lib")
     lib.set_option("mha_variant", request.param[0])
     lib.set_option("mha_bwd_groups", request.param[1])
