@@ -986,6 +986,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
+    for kv in args.opt:
+        key, val = kv.split("=")
+        pkg("_lib").set_option(key, int(val))
     if "D" in w:      # full-model workloads
         run_train(args, args.workload, rank, world, device, graph=not args.no_graph)
         if world > 1:
@@ -996,9 +999,6 @@ def main():
     lib = pkg("_lib")
     if args.ctc_chunks:
         lib.set_option("ctc_chunks", args.ctc_chunks)
-    for kv in args.opt:
-        key, val = kv.split("=")
-        lib.set_option(key, int(val))
     inp = make_inputs(w, device, 1236 + rank)
     n_params = cif_model_param_count(w)
     buckets = GradBuckets(n_params, device, world, args.allreduce) if (world > 1 and not args.no_allreduce) else None

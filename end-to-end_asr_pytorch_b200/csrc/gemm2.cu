@@ -22,8 +22,13 @@
 // in the 32-byte-atom flavour of that swizzle (TMA SWIZZLE_128B_ATOM_32B, descriptor layout 1, 4-row K groups, SBO = 512),
 // which is what the fp32 kernel uses for them.  Out-of-range rows / columns are
 // zero-filled by TMA, so odd sizes (the 4233-wide vocabulary) need no padding copies, only 16-byte-aligned row strides.
-// Split-K over gridDim.z (dW of a small layer has few output tiles and a long contraction): partial tiles go to a
-// workspace and a second kernel adds them in a fixed order (deterministic, no atomics).
+// Split-K over gridDim.z (dW of a small layer has few output tiles and a long contraction; at the model's shapes nearly
+// every product has fewer tiles than the GPU has SMs).  The CTAs of one output tile form a thread-block CLUSTER along z:
+// each leaves its partial tile in its own shared memory (the operand ring is free by then), and after a cluster barrier
+// CTA z adds rows [z * 128 / S, ...) of all S partial tiles through distributed shared memory in a fixed order (bias
+// first, then split 0, 1, ...: deterministic, no atomics) and stores them with row-contiguous 16-byte stores - no
+// workspace, no second launch.  The older flavour (partial tiles to a workspace + a reduce kernel) remains for 256-wide
+// tiles, whose partial tile does not fit next to nothing else in shared memory, and behind option gemm_split_mode = 1.
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -44,6 +49,78 @@ struct __align__(8) Gemm2Barriers {
     uint32_t tmem_base;
     uint32_t pad;
 };
+
+// ---- split-K inside a cluster -----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all(bool alone) {      // alone: a cluster of one CTA (or no cluster at all)
+    if (alone) __syncthreads();
+    else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta) {
+    uint32_t remote;
+    float4 v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta));
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+constexpr int kG2MaxSplits = 8;                               // = the portable cluster size
+template <int BN>
+struct G2Part {                                               // one CTA's partial tile in its shared memory
+    static constexpr int kLd = BN + 4;                        // row stride in floats: a warp's 32 row-strided float4 stores hit 8 distinct bank groups per phase
+    static constexpr int kBytes = kG2M * kLd * 4;
+};
+// thread `row` of the tile leaves 32 accumulator columns in the partial tile
+template <int BN>
+__device__ __forceinline__ void part_store32(unsigned char* smem, int row, int cc, const float (&v)[32]) {
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(smem) + (size_t)row * G2Part<BN>::kLd + cc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+// After the cluster barrier: this CTA's share of the tile's rows, 128 threads, one float4 (4 columns of one row) per
+// thread and pass, two passes in flight.  init(r, c) -> the float4 the sum starts from (bias), emit(r, c, sum).
+template <int BN, typename Init, typename Emit>
+__device__ __forceinline__ void cluster_splitk_reduce(unsigned char* smem, int tid128, int n_cols, Init init, Emit emit) {
+    constexpr int kF4 = BN / 4;
+    const int S = (int)cluster_nctarank(), z = (int)cluster_ctarank();
+    const int rows_per = (kG2M + S - 1) / S;
+    const int r_lo = z * rows_per, r_hi = min(kG2M, r_lo + rows_per);
+    const int total = max(0, r_hi - r_lo) * kF4;
+    const uint32_t base = smem_u32(smem);
+    for (int idx0 = tid128; idx0 < total; idx0 += 256) {
+        float4 part[2][kG2MaxSplits];
+        int r[2], c[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int idx = idx0 + 128 * u;
+            r[u] = r_lo + idx / kF4;
+            c[u] = (idx % kF4) * 4;
+            live[u] = idx < total && c[u] < n_cols;
+            const uint32_t off = base + (uint32_t)(r[u] * G2Part<BN>::kLd + c[u]) * 4u;
+#pragma unroll
+            for (int s = 0; s < kG2MaxSplits; ++s)
+                if (live[u] && s < S) part[u][s] = ld_dsmem_f4(off, (uint32_t)s);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;
+            float4 acc = init(r[u], c[u]);
+#pragma unroll
+            for (int s = 0; s < kG2MaxSplits; ++s)
+                if (s < S) { acc.x += part[u][s].x; acc.y += part[u][s].y; acc.z += part[u][s].z; acc.w += part[u][s].w; }
+            emit(r[u], c[u], acc);
+        }
+    }
+}
 
 // One operand tile: ROWS = extent along M (A) or N (B), ELEM = bytes per element.
 template <bool MN, int ROWS, int ELEM>
@@ -99,7 +176,7 @@ template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1)
 gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ bias,
                   float* __restrict__ c, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride,
-                  const int* __restrict__ row_len, int group_rows, int dead_mode) {
+                  const int* __restrict__ row_len, int group_rows, int dead_mode, int stage_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     using Cfg = G2F32Cfg<BN>;
@@ -112,6 +189,10 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     const int nk_total = (K + TA::kBK - 1) / TA::kBK;          // a K tail is zero-filled by TMA
     const int k_first = blockIdx.z * stages_per_split;
     int nk = max(0, min(stages_per_split, nk_total - k_first));
+    // split-K inside a cluster: partial tiles meet in shared memory.  stage_out: an unsplit tile takes the same way out
+    // (accumulator -> shared memory -> row-contiguous stores) instead of one strided 16-byte store per thread and row
+    const bool alone = cluster_nctarank() == 1;
+    const bool clustered = !alone || (stage_out != 0 && gridDim.z == 1);
     // Ragged rows (padded utterances): the "row" dimension - M when A is K-major, the contraction when A is MN-major - is
     // made of groups of `group_rows` rows of which only the first row_len[g] are valid; the others are known to be zero
     // (gradient rows of padded frames) or never read (their logits).  A row tile / K step that lies entirely in padding
@@ -233,6 +314,10 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
+            if (clustered) {          // the operand ring is free: every MMA that read it has completed (acc_full)
+                part_store32<BN>(smem, warp * 32 + lane, cc, v);
+                continue;
+            }
             if (row < M) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
@@ -257,6 +342,39 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             }
         }
         tc_fence_before();
+    }
+    if (clustered) {
+        cluster_sync_all(alone);
+        if (warp < 4) {
+            const bool vec = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c) & 15u) == 0;
+            const int n_store = vec ? min(ldc, (N + 3) & ~3) : N;
+            auto bias4 = [&](int, int col) {
+                const int n = n0 + col;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) {
+                    o.x = (n < N) ? __ldg(bias + n) : 0.0f;
+                    o.y = (n + 1 < N) ? __ldg(bias + n + 1) : 0.0f;
+                    o.z = (n + 2 < N) ? __ldg(bias + n + 2) : 0.0f;
+                    o.w = (n + 3 < N) ? __ldg(bias + n + 3) : 0.0f;
+                }
+                return o;
+            };
+            auto emit = [&](int r, int col, const float4& o) {
+                const int gr = m0 + r, n = n0 + col;
+                if (gr >= M) return;
+                float* out = c + (size_t)gr * ldc + n;
+                if (vec) {
+                    *reinterpret_cast<float4*>(out) = o;
+                } else {
+                    if (n < N) out[0] = o.x;
+                    if (n + 1 < N) out[1] = o.y;
+                    if (n + 2 < N) out[2] = o.z;
+                    if (n + 3 < N) out[3] = o.w;
+                }
+            };
+            cluster_splitk_reduce<BN>(smem, threadIdx.x, min(BN, n_store - n0), bias4, emit);
+        }
+        cluster_sync_all(alone);        // nobody leaves while a peer still reads its partial tile
     }
     __syncthreads();
     if (warp == 5) {
@@ -295,7 +413,7 @@ struct G2B16Cfg {
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool RELU>
 __global__ void __launch_bounds__(192, 2)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const float* __restrict__ bias,
-                 void* __restrict__ c_, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride) {
+                 void* __restrict__ c_, int M, int N, int K, int ldc, int stages_per_split, size_t split_stride, int stage_out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     using Cfg = G2B16Cfg<BN>;
@@ -308,6 +426,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int nk_total = (K + TA::kBK - 1) / TA::kBK;
     const int k_first = blockIdx.z * stages_per_split;
     const int nk = max(0, min(stages_per_split, nk_total - k_first));
+    constexpr bool kCanCluster = G2Part<BN>::kBytes <= kStages * Cfg::kStage;      // the partial tile must fit in the operand ring
+    const bool alone = cluster_nctarank() == 1;
+    const bool clustered = kCanCluster && (!alone || (stage_out != 0 && gridDim.z == 1));
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars->full[s], 1);
@@ -378,6 +499,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = 0.0f;
             }
+            if (kCanCluster && clustered) {
+                part_store32<BN>(smem, warp * 32 + lane, cc, v);
+                continue;
+            }
             if (row < M) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -412,6 +537,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
         tc_fence_before();
+    }
+    if (kCanCluster && clustered) {
+        cluster_sync_all(alone);
+        if (warp < 4) {
+            constexpr int kAlign = OUT_F32 ? 16 : 8;             // four outputs per store
+            const bool vec = (ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(c_) & (kAlign - 1)) == 0;
+            const int n_store = vec ? min(ldc, (N + 3) & ~3) : N;
+            auto bias4 = [&](int, int col) {
+                const int n = n0 + col;
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias != nullptr) {
+                    o.x = (n < N) ? __ldg(bias + n) : 0.0f;
+                    o.y = (n + 1 < N) ? __ldg(bias + n + 1) : 0.0f;
+                    o.z = (n + 2 < N) ? __ldg(bias + n + 2) : 0.0f;
+                    o.w = (n + 3 < N) ? __ldg(bias + n + 3) : 0.0f;
+                }
+                return o;
+            };
+            auto emit = [&](int r, int col, float4 o) {
+                const int gr = m0 + r, n = n0 + col;
+                if (gr >= M) return;
+                if (RELU) { o.x = fmaxf(o.x, 0.0f); o.y = fmaxf(o.y, 0.0f); o.z = fmaxf(o.z, 0.0f); o.w = fmaxf(o.w, 0.0f); }
+                const size_t at = (size_t)gr * ldc + n;
+                if (OUT_F32) {
+                    float* out = static_cast<float*>(c_) + at;
+                    if (vec) {
+                        *reinterpret_cast<float4*>(out) = o;
+                    } else {
+                        if (n < N) out[0] = o.x;
+                        if (n + 1 < N) out[1] = o.y;
+                        if (n + 2 < N) out[2] = o.z;
+                        if (n + 3 < N) out[3] = o.w;
+                    }
+                } else {
+                    __nv_bfloat16* out = static_cast<__nv_bfloat16*>(c_) + at;
+                    if (vec) {
+                        *reinterpret_cast<uint2*>(out) = make_uint2(cvt_bf16x2(o.x, o.y), cvt_bf16x2(o.z, o.w));
+                    } else {
+                        if (n < N) out[0] = __float2bfloat16_rn(o.x);
+                        if (n + 1 < N) out[1] = __float2bfloat16_rn(o.y);
+                        if (n + 2 < N) out[2] = __float2bfloat16_rn(o.z);
+                        if (n + 3 < N) out[3] = __float2bfloat16_rn(o.w);
+                    }
+                }
+            };
+            cluster_splitk_reduce<BN>(smem, threadIdx.x, min(BN, n_store - n0), bias4, emit);
+        }
+        cluster_sync_all(alone);
     }
     __syncthreads();
     if (warp == 5) {
@@ -491,27 +664,94 @@ struct Plan {
     dim3 grid;
 };
 
-// Tile width and split-K: one wave first.  256-wide tiles halve the operand traffic per flop but need the CTAs; a long
-// contraction with few output tiles (dW of a 512 x 512 layer) is cut along K until the SMs are covered.
-Plan make_plan(int M, int N, int K, int bk, int force_bn, int force_splits, bool allow_split) {
-    Plan p;
-    const long long mt = (M + kG2M - 1) / kG2M;
-    const long long ctas256 = mt * ((N + 255) / 256);
-    p.bn = (N >= 256 && ctas256 >= num_sms()) ? 256 : 128;
-    if (force_bn == 128 || force_bn == 256) p.bn = force_bn;
-    const long long ctas = mt * ((N + p.bn - 1) / p.bn);
-    p.nk_total = (K + bk - 1) / bk;
-    int splits = 1;
-    if (allow_split && ctas < num_sms()) {
-        splits = (int)std::min<long long>(8, (num_sms() + ctas - 1) / ctas);
-        while (splits > 1 && p.nk_total / splits < 8) --splits;      // every split keeps at least 8 K steps
+// Tile width and split-K are chosen by a small cost model, fitted to CUDA-graph replays of the model's shapes on a B200
+// (tools/gemm_split_bench.py --sweep; microseconds): a CTA costs  steps x t_step(BN) + t_tile(BN)  (+ the cluster
+// reduction when it shares its tile), and the launch takes as many such rounds as the tiles need at the number of
+// CTAs - or whole clusters - the GPU holds at once.  That last number is NOT num_sms / splits: a cluster lives inside
+// one GPC, so e.g. clusters of 5 one-CTA-per-SM kernels leave SMs of every GPC idle (28 tiles x 5 took two rounds);
+// cudaOccupancyMaxActiveClusters knows, and is asked once per (kernel, BN, cluster size).
+struct G2Cost {
+    float t_step[2];          // one K step (128 bytes of K) of a 128 x BN tile, BN = 128 / 256
+    float t_tile[2];          // accumulator -> global memory, barriers, TMEM allocation
+    float t_cluster;          // a tile shared by a cluster: two cluster barriers + the reduction, less what the row-contiguous stores save
+    int ctas_per_sm;
+    bool cluster_256;         // may a 256-wide tile be split inside a cluster (its partial tile must fit in the operand ring)
+};
+constexpr G2Cost kCostF32 = {{0.87f, 1.28f}, {2.4f, 5.0f}, 0.3f, 1, true};
+constexpr G2Cost kCostB16 = {{0.225f, 0.43f}, {2.0f, 4.5f}, 2.3f, 2, false};
+
+template <typename KernelT>
+int query_max_clusters(KernelT kernel, int smem, int cluster_z) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1, 1, (unsigned)cluster_z);
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)cluster_z;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return 0;
     }
-    if (force_splits > 0) splits = std::max(1, std::min(force_splits, p.nk_total));
-    if (!allow_split) splits = 1;
-    p.stages_per_split = (p.nk_total + splits - 1) / splits;
-    p.splits = (p.nk_total + p.stages_per_split - 1) / p.stages_per_split;
-    p.grid = dim3((unsigned)((N + p.bn - 1) / p.bn), (unsigned)mt, (unsigned)p.splits);
-    return p;
+    return n;
+}
+
+// clusters of `splits` CTAs (one per output tile) the GPU holds at once; 0 = such a cluster cannot be launched
+int max_clusters(bool f32, int bn, int splits);      // defined below the kernels' launchers (needs their instances)
+
+Plan make_plan(bool f32, int M, int N, int K, int bk, int force_bn, int force_splits, bool allow_split, bool in_cluster) {
+    const G2Cost& cm = f32 ? kCostF32 : kCostB16;
+    const long long mt = (M + kG2M - 1) / kG2M;
+    const int nk_total = (K + bk - 1) / bk;
+    Plan best = {};
+    float best_cost = -1.0f;
+    for (int bi = 0; bi < 2; ++bi) {
+        const int bn = bi ? 256 : 128;
+        if ((force_bn == 128 || force_bn == 256) && bn != force_bn) continue;
+        if (bn == 256 && N <= 128 && force_bn != 256) continue;
+        const long long tiles = mt * ((N + bn - 1) / bn);
+        for (int want = 1; want <= kG2MaxSplits; ++want) {
+            if (force_splits > 0 && want != std::max(1, std::min(force_splits, std::min(nk_total, kG2MaxSplits)))) continue;
+            if (want > 1 && !allow_split) break;
+            const int steps = (nk_total + want - 1) / want;
+            const int splits = (nk_total + steps - 1) / steps;
+            if (splits != want && force_splits <= 0) continue;            // the same plan as a smaller `want`
+            if (splits > 1 && steps < 4 && force_splits <= 0) continue;   // too little work per CTA to pay for the hand-over
+            const bool clustered = splits > 1 && in_cluster && (bn == 128 || cm.cluster_256);
+            long long room;                                               // tiles in flight
+            if (clustered) {
+                room = max_clusters(f32, bn, splits);
+                if (room <= 0) continue;
+            } else {
+                room = std::max<long long>(1, (long long)num_sms() * cm.ctas_per_sm / splits);
+            }
+            const long long rounds = (tiles + room - 1) / room;
+            float cost = (float)rounds * ((float)steps * cm.t_step[bi] + cm.t_tile[bi] + (splits > 1 ? cm.t_cluster + 0.1f * splits : 0.0f));
+            if (splits > 1 && !clustered) cost += 4.5f;                   // partial tiles through the workspace + the reduce kernel
+            if (best_cost < 0.0f || cost < best_cost) {
+                best_cost = cost;
+                best.bn = bn;
+                best.splits = splits;
+                best.stages_per_split = steps;
+                best.nk_total = nk_total;
+                best.grid = dim3((unsigned)((N + bn - 1) / bn), (unsigned)mt, (unsigned)splits);
+            }
+        }
+    }
+    if (best_cost < 0.0f) {      // nothing admissible (cannot happen with splits = 1 allowed): one CTA per 128 x 128 tile
+        best.bn = 128;
+        best.splits = 1;
+        best.stages_per_split = nk_total;
+        best.nk_total = nk_total;
+        best.grid = dim3((unsigned)((N + 127) / 128), (unsigned)mt, 1u);
+    }
+    return best;
 }
 
 // tensor map of one operand: K-major = [mn rows x k cols] (box ROWS x chunk), MN-major = [k rows x mn cols] (box chunk-k x chunk)
@@ -532,6 +772,43 @@ int set_smem_once(KernelT kernel, int bytes, bool& done) {
         done = true;
     }
     return 0;
+}
+
+
+// <<<grid, 192, smem, st>>> with the gridDim.z CTAs of an output tile as one cluster when cluster_z > 1
+template <typename KernelT, typename... Args>
+cudaError_t launch_g2(KernelT kernel, dim3 grid, int smem, cudaStream_t st, int cluster_z, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)cluster_z;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster_z > 1 ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+
+int max_clusters(bool f32, int bn, int splits) {
+    static int cache[2][2][kG2MaxSplits + 1];      // 0 = not asked yet, -1 = cannot be launched
+    if (splits < 2 || splits > kG2MaxSplits) return 0;
+    int& slot = cache[f32 ? 1 : 0][bn == 256 ? 1 : 0][splits];
+    if (slot == 0) {
+        int n;
+        if (f32)
+            n = bn == 256 ? query_max_clusters(gemm_f32x3_kernel<256, false, false>, G2F32Cfg<256>::kSmem, splits)
+                          : query_max_clusters(gemm_f32x3_kernel<128, false, false>, G2F32Cfg<128>::kSmem, splits);
+        else
+            n = bn == 256 ? query_max_clusters(gemm_bf16_kernel<256, false, false, true, false>, G2B16Cfg<256>::kSmem, splits)
+                          : query_max_clusters(gemm_bf16_kernel<128, false, false, true, false>, G2B16Cfg<128>::kSmem, splits);
+        slot = n > 0 ? n : -1;
+    }
+    return slot > 0 ? slot : 0;
 }
 
 }  // namespace
@@ -566,23 +843,32 @@ extern "C" int asr_gemm_f32_ragged(const float* a, int a_mn_major, int lda, cons
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool can_split = ws != nullptr && ws_bytes >= asr_gemm_workspace_bytes(M, N, K);
-    const Plan p = make_plan(M, N, K, 32, get_opt("gemm_f32_bn"), get_opt("gemm_split_k"), can_split);
+    const bool cluster_mode = get_opt("gemm_split_mode") != 1;
+    const Plan p = make_plan(true, M, N, K, 32, get_opt("gemm_f32_bn"), get_opt("gemm_split_k"), can_split, cluster_mode);
     CUtensorMap ta, tb;
     if (make_operand_map(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a, a_mn_major != 0, M, K, lda, kG2M) ||
         make_operand_map(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, b, b_mn_major != 0, N, K, ldb, p.bn))
         return 4;
+    // split-K: inside a cluster (default), or through the workspace + a reduce kernel (option gemm_split_mode = 1)
+    const bool in_cluster = p.splits > 1 && cluster_mode;
+    const bool via_ws = p.splits > 1 && !in_cluster;
+    // rows the epilogue cannot store 16 bytes at a time (an odd row stride: the 4233-wide vocabulary) leave through shared
+    // memory, where a warp writes one contiguous row segment instead of 32 strided scalars (measured: 51 -> 39 us at
+    // M = 896, N = 4233); option gemm_stage_out: 1 = never, 2 = always
+    const bool direct_vec = (ldc & 3) == 0 && aligned16(c);
+    const int stage_out = get_opt("gemm_stage_out") == 2 || (get_opt("gemm_stage_out") == 0 && !direct_vec) ? 1 : 0;
     float* part = nullptr;
-    if (p.splits > 1) part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-    float* dst = p.splits > 1 ? part : c;
-    const int ldd = p.splits > 1 ? N : ldc;
-    const size_t split_stride = (size_t)M * N;
+    if (via_ws) part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    float* dst = via_ws ? part : c;
+    const int ldd = via_ws ? N : ldc;
+    const size_t split_stride = via_ws ? (size_t)M * N : 0;
 #define ASR_G2F(BNV, AM, BM)                                                                                        \
     do {                                                                                                            \
         static bool done = false;                                                                                   \
         if (set_smem_once(gemm_f32x3_kernel<BNV, AM, BM>, G2F32Cfg<BNV>::kSmem, done)) return 1;                     \
-        gemm_f32x3_kernel<BNV, AM, BM><<<p.grid, 192, G2F32Cfg<BNV>::kSmem, st>>>(ta, tb, bias, dst, M, N, K, ldd,    \
-                                                                                 p.stages_per_split, split_stride, \
-                                                                                 row_len, group_rows, dead_mode);  \
+        ASR_CHECK_CUDA(launch_g2(gemm_f32x3_kernel<BNV, AM, BM>, p.grid, G2F32Cfg<BNV>::kSmem, st,                   \
+                                 in_cluster ? p.splits : 1, ta, tb, bias, dst, M, N, K, ldd, p.stages_per_split,    \
+                                 split_stride, row_len, group_rows, dead_mode, stage_out));                        \
     } while (0)
     const int sel = (p.bn == 256 ? 4 : 0) | (a_mn_major ? 2 : 0) | (b_mn_major ? 1 : 0);
     switch (sel) {
@@ -597,7 +883,7 @@ extern "C" int asr_gemm_f32_ragged(const float* a, int a_mn_major, int lda, cons
     }
 #undef ASR_G2F
     ASR_LAUNCH_CHECK();
-    if (p.splits > 1) {
+    if (via_ws) {
         const size_t total = (size_t)M * N;
         const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)num_sms() * 8);
         splitk_reduce_f32_kernel<<<blocks, 256, 0, st>>>(part, p.splits, split_stride, M, N, N, bias, c, ldc);
@@ -618,12 +904,20 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool can_split = ws != nullptr && ws_bytes >= asr_gemm_workspace_bytes(M, N, K);
-    const Plan p = make_plan(M, N, K, 64, get_opt("gemm_variant") == 1 ? 128 : 0, get_opt("gemm_split_k"), can_split);
+    const bool cluster_mode = get_opt("gemm_split_mode") != 1;
+    const Plan p = make_plan(false, M, N, K, 64, get_opt("gemm_variant") == 1 ? 128 : (get_opt("gemm_variant") == 2 ? 256 : 0),
+                             get_opt("gemm_split_k"), can_split, cluster_mode);
     CUtensorMap ta, tb;
     if (make_operand_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, a_mn_major != 0, M, K, lda, kG2M) ||
         make_operand_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, b_mn_major != 0, N, K, ldb, p.bn))
         return 4;
-    const bool split = p.splits > 1;
+    // 256-wide tiles: the partial tile does not fit in the bf16 kernel's operand ring - those go through the workspace
+    const bool in_cluster = p.splits > 1 && p.bn == 128 && cluster_mode;
+    // as in asr_gemm_f32: outputs whose rows cannot take 16-byte stores go out through shared memory (bf16, M = 896,
+    // N = 4233: 50 -> 16 us)
+    const bool direct_vec = (ldc % (out_f32 ? 4 : 8)) == 0 && aligned16(c);
+    const int stage_out = get_opt("gemm_stage_out") == 2 || (get_opt("gemm_stage_out") == 0 && !direct_vec) ? 1 : 0;
+    const bool split = p.splits > 1 && !in_cluster;
     float* part = split ? reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255) : nullptr;
     void* dst = split ? static_cast<void*>(part) : c;
     const int ldd = split ? N : ldc;
@@ -634,8 +928,9 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     do {                                                                                                                  \
         static bool done = false;                                                                                         \
         if (set_smem_once(gemm_bf16_kernel<BNV, AM, BM, F32, RL>, G2B16Cfg<BNV>::kSmem, done)) return 1;                    \
-        gemm_bf16_kernel<BNV, AM, BM, F32, RL><<<p.grid, 192, G2B16Cfg<BNV>::kSmem, st>>>(ta, tb, bias, dst, M, N, K, ldd,   \
-                                                                                        p.stages_per_split, split_stride); \
+        ASR_CHECK_CUDA(launch_g2(gemm_bf16_kernel<BNV, AM, BM, F32, RL>, p.grid, G2B16Cfg<BNV>::kSmem, st,                 \
+                                 in_cluster ? p.splits : 1, ta, tb, bias, dst, M, N, K, ldd, p.stages_per_split,          \
+                                 split_stride, stage_out));                                                              \
     } while (0)
 #define ASR_G2H_LAYOUT(BNV, F32, RL)                                    \
     do {                                                                \
