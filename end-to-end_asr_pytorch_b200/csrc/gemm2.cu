@@ -609,34 +609,74 @@ __global__ void __launch_bounds__(256) splitk_reduce_out_kernel(const float* __r
     }
 }
 
-// Column sums (bias gradients): CTA = 32 columns x all rows; 32 row groups of 32 lanes (1024 threads) read 128 contiguous
-// bytes per row (64 for bf16), eight rows in flight per thread, then the 32 partial sums of a column are added in a fixed
-// order (deterministic).
-template <typename T>
-__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, int M, int N, int ld, float* __restrict__ out) {
-    __shared__ float part[32][33];
+// Column sums (bias gradients).  CTA = kCols columns x one chunk of the rows: 32 row groups of 32 lanes (1024 threads)
+// read 128 contiguous bytes per row - 32 fp32 columns, or 64 bf16 columns as pairs when the rows are 4-byte aligned -
+// eight rows in flight per thread; the 32 partial sums of a column are added in a fixed order.  The row chunks of one
+// column block are a thread-block cluster along y (up to 8 CTAs: a [15030 x 512] gradient has only 16 column blocks,
+// which left 130 SMs idle): each leaves its column sums in shared memory and CTA 0 of the cluster adds them in chunk
+// order through distributed shared memory - one launch, no scratch buffer, deterministic.
+template <typename T, int V>      // V = columns per lane: 1, or 2 (bf16 pairs)
+__global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, int M, int N, int ld, int rows_per_cta, float* __restrict__ out) {
+    constexpr int kCols = 32 * V;
+    __shared__ float part[32][kCols + 1];
+    __shared__ __align__(16) float csum[kCols];
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const int n = blockIdx.x * 32 + lane;
-    float acc = 0.0f;
-    if (n < N) {
-        const T* col = x + n;
-        int m = grp;
-        for (; m + 7 * 32 < M; m += 8 * 32) {
-            float a[8];
+    const int n = blockIdx.x * kCols + V * lane;
+    const int m_lo = blockIdx.y * rows_per_cta, m_hi = min(M, m_lo + rows_per_cta);
+    float acc[V];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = (float)col[(size_t)(m + 32 * u) * ld];
-            acc += ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    for (int v = 0; v < V; ++v) acc[v] = 0.0f;
+    auto load = [&](int m, float (&dst)[V]) {
+        if (V == 2) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + (size_t)m * ld + n));
+            dst[0] = f.x;
+            dst[V - 1] = f.y;
+        } else {
+            dst[0] = (float)x[(size_t)m * ld + n];
         }
-        for (; m < M; m += 32) acc += (float)col[(size_t)m * ld];
-    }
-    part[grp][lane] = acc;
-    __syncthreads();
-    if (grp == 0 && n < N) {
-        float s = 0.0f;
+    };
+    if (n < N) {         // V == 2: N is even, so a pair is inside or outside as a whole
+        int m = m_lo + grp;
+        for (; m + 7 * 32 < m_hi; m += 8 * 32) {
+            float a[8][V];
 #pragma unroll
-        for (int g = 0; g < 32; ++g) s += part[g][lane];
-        out[n] = s;
+            for (int u = 0; u < 8; ++u) load(m + 32 * u, a[u]);
+#pragma unroll
+            for (int v = 0; v < V; ++v)
+                acc[v] += ((a[0][v] + a[1][v]) + (a[2][v] + a[3][v])) + ((a[4][v] + a[5][v]) + (a[6][v] + a[7][v]));
+        }
+        for (; m < m_hi; m += 32) {
+            float a[V];
+            load(m, a);
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[v] += a[v];
+        }
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) part[grp][V * lane + v] = acc[v];
+    __syncthreads();
+    if (threadIdx.x < kCols) {
+        float t = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 32; ++g) t += part[g][threadIdx.x];
+        csum[threadIdx.x] = t;
+    }
+    const bool alone = cluster_nctarank() == 1;
+    cluster_sync_all(alone);
+    if (cluster_ctarank() == 0 && threadIdx.x < kCols && blockIdx.x * kCols + threadIdx.x < N) {
+        const uint32_t addr = smem_u32(&csum[threadIdx.x]);
+        const int chunks = (int)cluster_nctarank();
+        float t = 0.0f;
+        for (int r = 0; r < chunks; ++r) {
+            uint32_t remote;
+            float v;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(r));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+            t += v;
+        }
+        out[blockIdx.x * kCols + threadIdx.x] = t;
+    }
+    cluster_sync_all(alone);          // the chunks' shared memory stays until CTA 0 has read it
 }
 
 }  // namespace asr
@@ -647,11 +687,32 @@ extern "C" int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, floa
     ASR_REQUIRE(x && out && M > 0 && N > 0 && ld >= N, "asr_colsum: bad arguments");
     if (asr_device_ok() != 0) return 3;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned blocks = (unsigned)((N + 31) / 32);
-    if (is_bf16)
-        colsum_kernel<__nv_bfloat16><<<blocks, 1024, 0, st>>>(static_cast<const __nv_bfloat16*>(x), M, N, ld, out);
+    const bool pairs = is_bf16 && (N % 2) == 0 && (ld % 2) == 0 && (reinterpret_cast<uintptr_t>(x) & 3u) == 0;
+    const int cols = pairs ? 64 : 32;
+    const int col_blocks = (N + cols - 1) / cols;
+    // row chunks: enough CTAs for two per SM's worth of loads in flight, at least 1024 rows each (below that the cluster
+    // launch costs more than the idle SMs: 3.4 -> 4.4 us at M = 1344), at most one cluster (8)
+    int chunks = std::min(kG2MaxSplits, std::max(1, (2 * num_sms() + col_blocks - 1) / col_blocks));
+    chunks = std::max(1, std::min(chunks, M / 1024));
+    const int rows_per_cta = (M + chunks - 1) / chunks;
+    chunks = (M + rows_per_cta - 1) / rows_per_cta;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)col_blocks, (unsigned)chunks, 1);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = (unsigned)chunks;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = chunks > 1 ? 1 : 0;
+    if (pairs)
+        ASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, colsum_kernel<__nv_bfloat16, 2>, static_cast<const __nv_bfloat16*>(x), M, N, ld, rows_per_cta, out));
+    else if (is_bf16)
+        ASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, colsum_kernel<__nv_bfloat16, 1>, static_cast<const __nv_bfloat16*>(x), M, N, ld, rows_per_cta, out));
     else
-        colsum_kernel<float><<<blocks, 1024, 0, st>>>(static_cast<const float*>(x), M, N, ld, out);
+        ASR_CHECK_CUDA(cudaLaunchKernelEx(&cfg, colsum_kernel<float, 1>, static_cast<const float*>(x), M, N, ld, rows_per_cta, out));
     ASR_LAUNCH_CHECK();
     return 0;
 }

@@ -51,7 +51,23 @@ class Conv2dSubsample(nn.Module):
     def forward(self, feats, feat_lengths):
         n_frames = feats.size(1)
         x = F.pad(feats, (0, 10, 0, 20)).unsqueeze(1)                  # [B, 1, T+20, D+10]
-        x = self.conv(x)[:, :, :, :self.d_conv_out]
+        if x.is_cuda:
+            # NHWC activations on the GPU: cuDNN's tensor-core convolutions are NHWC kernels, and with NCHW tensors every
+            # call is wrapped in layout-conversion kernels (measured in the config-5 training step: 1.2 ms of nchwToNhwc /
+            # nhwcToNchw per step around 1.3 ms of convolutions).  The parameters keep torch's default layout (so do their
+            # gradients, which the flat all-reduce buckets and the fused optimizer rely on); the 9 K-element NHWC copy of
+            # a weight is made per call.  With one input channel NCHW and NHWC are the same bytes, but torch reads the
+            # layout off the strides and a size-1 dimension is ambiguous: spell the NHWC strides out.
+            _, _, hh, ww = x.shape
+            x = x.as_strided(x.shape, (hh * ww, 1, ww, 1))
+            for layer in self.conv:
+                if isinstance(layer, nn.Conv2d):
+                    x = F.conv2d(x, layer.weight.contiguous(memory_format=torch.channels_last), layer.bias, layer.stride)
+                else:
+                    x = layer(x)
+        else:
+            x = self.conv(x)
+        x = x[:, :, :, :self.d_conv_out]
         B, C, T, D = x.size()
         x = x.permute(0, 2, 1, 3).contiguous().view(B, T, C * D)
         out_len = feat_lengths

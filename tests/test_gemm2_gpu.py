@@ -297,7 +297,9 @@ def test_cif_model_with_fused_ctc_fc_matches_the_plain_route():
         assert (a - b).abs().max().item() <= 1e-4 * a.abs().max().item()
 
 
-@pytest.mark.parametrize("M,N,dtype", [(1344, 512, torch.float32), (15030, 2048, torch.bfloat16), (7, 4233, torch.float32), (300, 33, torch.bfloat16)])
+@pytest.mark.parametrize("M,N,dtype", [(1344, 512, torch.float32), (15030, 2048, torch.bfloat16), (7, 4233, torch.float32), (300, 33, torch.bfloat16),
+                                       (15030, 512, torch.bfloat16), (15030, 512, torch.float32), (2049, 70, torch.bfloat16), (513, 4236, torch.bfloat16),
+                                       (100000, 64, torch.float32)])
 def test_colsum_is_the_bias_gradient(M, N, dtype):
     ops = pkg("ops")
     x = _rand((M, N), M + N, dtype=dtype)

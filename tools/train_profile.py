@@ -15,6 +15,7 @@ lossm = bench.pkg("transformer.loss")
 w = dict(bench.WORKLOADS[wname])
 bf16 = wname == "transformer_bf16"
 dev = torch.device("cuda")
+torch.backends.cudnn.benchmark = True          # as bench.py runs the step
 torch.manual_seed(1234)
 if bf16:
     model = bench.pkg("transformer.transformer").Transformer.create_model(bench._model_args(w)).to(dev).train()
@@ -44,6 +45,13 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as p:
     for _ in range(3): step()
     torch.cuda.synchronize()
 ka = p.key_averages()
-cuda_total = sum(e.self_device_time_total for e in ka) / 3e3
-print("GPU busy per step %.2f ms" % cuda_total)
-print(ka.table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=90))
+# kernels only (device_type CUDA events), per step
+from torch.autograd import DeviceType
+rows = [(e.key, e.self_device_time_total / 3e3, e.count / 3) for e in ka if e.device_type == DeviceType.CUDA]
+rows.sort(key=lambda r: -r[1])
+total = sum(r[1] for r in rows)
+print("GPU busy per step %.2f ms in %.0f launches" % (total, sum(r[2] for r in rows)))
+ours = sum(r[1] for r in rows if "asr::" in r[0])
+print("this package's kernels: %.2f ms (%.0f %%)" % (ours, 100 * ours / total))
+for name, ms, n in rows[:45]:
+    print("%8.3f ms %5.1f %% %6.1f x %7.1f us  %s" % (ms, 100 * ms / total, n, ms / n * 1e3, name[:110]))
