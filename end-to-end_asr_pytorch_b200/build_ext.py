@@ -15,8 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libasr_sm100.so")
 STAMP = os.path.join(CSRC, ".build_stamp")
-SOURCES = ["common.cu", "cif.cu", "assigner.cu", "specaug.cu", "ctc.cu", "mha.cu", "gemm.cu", "gemm2.cu", "allreduce.cu"]
-HEADERS = ["common.cuh", "tcgen05.cuh", os.path.join("..", "..", "include", "asr_sm100.h")]
+SOURCES = ["common.cu", "cif.cu", "assigner.cu", "specaug.cu", "ctc.cu", "mha.cu", "gemm.cu", "gemm2.cu", "allreduce.cu", "ln.cu"]
+HEADERS = ["common.cuh", "tcgen05.cuh", "philox.cuh", os.path.join("..", "..", "include", "asr_sm100.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

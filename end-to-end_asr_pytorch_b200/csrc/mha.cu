@@ -21,6 +21,7 @@
 //                     softmax warps read PV from TMEM and fold it into the fp32 O registers.
 #include "common.cuh"
 #include "tcgen05.cuh"
+#include "philox.cuh"
 
 #include <cuda_bf16.h>
 #include <type_traits>
@@ -51,38 +52,6 @@ struct MhaFwdArgs {
     const uint64_t* seed_dev;   // not null: the seed is *seed_dev + (seed_hi:seed_lo), read on the device (a step captured in
                                 // a CUDA graph gets fresh masks on every replay by bumping one device word)
 };
-
-__device__ __forceinline__ void effective_seed(const uint64_t* seed_dev, uint32_t& lo, uint32_t& hi) {
-    if (seed_dev != nullptr) {
-        const uint64_t s = __ldg(reinterpret_cast<const unsigned long long*>(seed_dev)) + (((uint64_t)hi << 32) | lo);
-        lo = (uint32_t)s;
-        hi = (uint32_t)(s >> 32);
-    }
-}
-
-// Philox4x32-7 (counter-based: forward and backward regenerate the same bits from the element's
-// coordinates).  One call yields the 16 random bytes of keys [k16*16, k16*16+16) of row q of head bh.
-__device__ __forceinline__ uint4 philox16(uint32_t k16, uint32_t q, uint32_t bh, uint32_t seed_lo, uint32_t seed_hi) {
-    uint32_t c0 = k16, c1 = q, c2 = bh, c3 = 0x2545F491u;
-    uint32_t k0 = seed_lo, k1 = seed_hi;
-#pragma unroll
-    for (int r = 0; r < 7; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
-        c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
-        c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-}
-// random byte of key (k & 15) out of a philox16 result
-__device__ __forceinline__ uint32_t philox_byte(const uint4& r, int k) {
-    const uint32_t w = (k & 8) ? ((k & 4) ? r.w : r.z) : ((k & 4) ? r.y : r.x);
-    return (w >> ((k & 3) * 8)) & 0xffu;
-}
 
 // Keep masks of a packed bf16 pair (0xffff per kept lane) from two random bytes of `word` (bytes 2p, 2p + 1): a byte permute
 // turns each byte into the fp16 number 1 + byte / 1024 (0x3c00 | byte), and ONE packed fp16 compare against 1 + thresh / 1024
@@ -2314,12 +2283,6 @@ __global__ void __launch_bounds__(256) mha_dropout_keep_kernel(uint8_t* keep, in
     const uint4 rnd = philox16((uint32_t)k16, (uint32_t)q, (uint32_t)bh, seed_lo, seed_hi);
     uint8_t* dst = keep + ((size_t)bh * Lq + q) * Lk + (size_t)k16 * 16;
     for (int i = 0; i < 16 && k16 * 16 + i < Lk; ++i) dst[i] = philox_byte(rnd, i) >= thresh ? 1 : 0;
-}
-
-static inline uint32_t drop_threshold(float p_drop) {
-    if (!(p_drop > 0.0f)) return 0;
-    int t = (int)(p_drop * 256.0f + 0.5f);
-    return (uint32_t)(t < 0 ? 0 : (t > 255 ? 255 : t));
 }
 
 static int make_qkv_map(CUtensorMap* map, const void* base, int B, int L, int Hh) {

@@ -788,3 +788,96 @@ def mha_probs(q, k, kv_len=None, mask=None, causal=False, scale=None):
         check(_lib.lib().asr_mha_probs_f32(ptr(qb), ptr(kb), ptr(kv_len), ptr(mask), int(causal), B, Hh, Lq, Lk, D,
                                            ctypes.c_float(scale), ptr(attn), stream_ptr()), "asr_mha_probs_f32")
     return attn
+
+
+# ---------------------------------------------------------------------------------------
+# dropout + residual + LayerNorm of the training step (csrc/ln.cu)
+# ---------------------------------------------------------------------------------------
+LN_WIDTHS = (256, 512, 1024)
+
+
+class _ResidualLayerNormFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, residual, weight, bias, eps, p_drop, seed, seed_dev):
+        D = y.shape[-1]
+        y2 = y.reshape(-1, D)
+        r2 = residual.reshape(-1, D) if residual is not None else None
+        M = y2.shape[0]
+        dev = y.device
+        out = torch.empty((M, D), dtype=torch.float32, device=dev)
+        mean = torch.empty((M,), dtype=torch.float32, device=dev)
+        rstd = torch.empty((M,), dtype=torch.float32, device=dev)
+        z_is_y = r2 is None and p_drop == 0.0 and y2.dtype == torch.float32
+        z = None if z_is_y else torch.empty((M, D), dtype=torch.float32, device=dev)
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_ln_fwd(ptr(y2), int(y2.dtype == torch.bfloat16), ptr(r2), ptr(w32), ptr(b32), M, D,
+                                        ctypes.c_float(eps), ctypes.c_float(p_drop), ctypes.c_uint64(seed), ptr(seed_dev),
+                                        ptr(z), ptr(out), ptr(mean), ptr(rstd), stream_ptr()), "asr_ln_fwd")
+        ctx.save_for_backward(y2 if z_is_y else z, mean, rstd, w32, seed_dev)
+        ctx.meta = (y.shape, y.dtype, residual is not None, p_drop, seed)
+        return out.reshape(y.shape)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        z, mean, rstd, w32, seed_dev = ctx.saved_tensors
+        shape, y_dtype, has_res, p_drop, seed = ctx.meta
+        M, D = z.shape
+        dev = z.device
+        g2 = g_out.reshape(M, D)
+        if g2.dtype != torch.float32 or not g2.is_contiguous():
+            g2 = g2.float().contiguous()
+        need_y, need_r = ctx.needs_input_grad[0], has_res and ctx.needs_input_grad[1]
+        same = p_drop == 0.0 and y_dtype == torch.float32          # dy is dz: one tensor serves both
+        g_z = torch.empty((M, D), dtype=torch.float32, device=dev) if (need_r or (need_y and same)) else None
+        g_y = torch.empty((M, D), dtype=y_dtype, device=dev) if (need_y and not same) else None
+        if g_z is None and g_y is None:
+            g_z = torch.empty((M, D), dtype=torch.float32, device=dev)
+        g_wb = torch.empty((2, D), dtype=torch.float32, device=dev)
+        ws_bytes = _lib.lib().asr_ln_bwd_workspace_bytes(M, D)
+        ws = torch.empty((ws_bytes // 4 + 4,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(_lib.lib().asr_ln_bwd(ptr(g2), ptr(z), ptr(mean), ptr(rstd), ptr(w32), M, D, ctypes.c_float(p_drop),
+                                        ctypes.c_uint64(seed), ptr(seed_dev), ptr(g_z), ptr(g_y), int(y_dtype == torch.bfloat16),
+                                        ptr(g_wb), ptr(ws), ws_bytes, stream_ptr()), "asr_ln_bwd")
+        gy = (g_z if same else g_y).reshape(shape) if need_y else None
+        gr = g_z.reshape(shape) if need_r else None
+        return gy, gr, g_wb[0], g_wb[1], None, None, None, None
+
+
+def residual_layer_norm_available(y, residual, weight):
+    """True when residual_layer_norm takes these operands (CUDA, width 256 / 512 / 1024, y fp32 / bf16, residual fp32)."""
+    return (y.is_cuda and y.shape[-1] in LN_WIDTHS and y.dtype in (torch.float32, torch.bfloat16) and y.is_contiguous()
+            and weight.shape == (y.shape[-1],)
+            and (residual is None or (residual.dtype == torch.float32 and residual.shape == y.shape and residual.is_contiguous())))
+
+
+def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, training=True, seed=None):
+    """LayerNorm(dropout(y) + residual) -> fp32, with autograd (module.py:50-52, attention.py:59-60, encoder.py:49 of the
+    reference): one kernel forward, one (+ a column sum of per-CTA partials) backward.  y [..., D] fp32 or bf16, residual
+    [..., D] fp32 or None, weight / bias [D] (gamma / beta).  The dropout mask comes from the library's Philox stream
+    (`seed`: default drawn from torch's CPU generator; inside `device_dropout_seed(...)` read from the device) and is
+    regenerated in the backward - see ln_dropout_keep."""
+    _require_cuda("y", y)
+    if not residual_layer_norm_available(y, residual, weight):
+        raise ValueError("residual_layer_norm: unsupported operands (width %d, dtypes %s / %s)" % (
+            y.shape[-1], y.dtype, None if residual is None else residual.dtype))
+    p = float(dropout_p) if training else 0.0
+    if not 0.0 <= p < 1.0:
+        raise ValueError("residual_layer_norm: dropout_p must be in [0, 1)")
+    seed_dev = None
+    if p > 0.0 and seed is None:
+        if _active_seed is not None:
+            seed_dev, seed = _active_seed.take()
+        else:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    return _ResidualLayerNormFunction.apply(y, residual, weight, bias, float(eps), p, int(seed or 0), seed_dev)
+
+
+def ln_dropout_keep(M, D, dropout_p, seed, device="cuda"):
+    """(keep mask [M, D] bool, keep probability) of residual_layer_norm's dropout for (dropout_p, seed)."""
+    keep = torch.empty((M, D), dtype=torch.uint8, device=device)
+    with torch.cuda.device(keep.device):
+        check(_lib.lib().asr_ln_dropout_keep(ptr(keep), M, D, ctypes.c_float(dropout_p), ctypes.c_uint64(seed), stream_ptr()),
+              "asr_ln_dropout_keep")
+    return keep.bool(), float(_lib.lib().asr_ln_dropout_keep_prob(ctypes.c_float(dropout_p)))

@@ -28,7 +28,7 @@ import torch
 import torch.nn as nn
 
 from ..ops import mha_core, mha_probs, linear_act, linear_residual_layernorm
-from .module import fused_linear_ok, Linear
+from .module import fused_linear_ok, Linear, dropout_residual_layer_norm
 
 
 class MultiheadAttention(nn.Module):
@@ -91,6 +91,4 @@ class MultiheadAttention(nn.Module):
         if fused:      # fc + bias + residual + LayerNorm in one kernel (the 512-wide row stays in tensor memory)
             return linear_residual_layernorm(output, self.fc.weight, self.fc.bias, residual, self.layer_norm.weight,
                                              self.layer_norm.bias, self.layer_norm.eps), attn
-        output = self.dropout(self.fc(output))
-        output = self.layer_norm(output + residual)
-        return output, attn
+        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.fc(output), residual), attn

@@ -3,7 +3,7 @@ tcgen05 attention core).  Names follow /root/reference/src/transformer/encoder.p
 (`linear_in`, `layer_norm_in`, `layer_stack.N.{slf_attn,pos_ffn}`)."""
 import torch.nn as nn
 
-from .module import Linear
+from .module import Linear, dropout_residual_layer_norm
 
 from .attention import MultiheadAttention
 from .module import PositionalEncoding, PositionwiseFeedForward
@@ -42,7 +42,7 @@ class Encoder(nn.Module):
         """N x T x D, N -> N x T x d_model.  The key-padding mask of the reference
         (get_attn_pad_mask, utils.py:157-165) is handed to the attention kernel in its
         structured form, as per-utterance key lengths."""
-        x = self.dropout(self.layer_norm_in(self.linear_in(padded_input)) + self.positional_encoding(padded_input))
+        x = self.dropout(dropout_residual_layer_norm(self.layer_norm_in, None, self.linear_in(padded_input)) + self.positional_encoding(padded_input))
         # in the activations' dtype: a float32 mask would promote bf16 activations (and break the fused bf16 layers)
         non_pad_mask = sequence_mask(input_lengths, padded_input.size(1), dtype=x.dtype).unsqueeze(-1)
         for layer in self.layer_stack:

@@ -18,6 +18,24 @@ import torch.nn.functional as F
 # Both switches can be turned off to fall back to torch's F.linear (cuBLAS), e.g. for A/B measurements.
 USE_TENSOR_CORE_FP32 = True
 USE_TENSOR_CORE_BF16 = True
+# LayerNorm(dropout(y) + residual) at the end of every sub-layer as ONE kernel each way (csrc/ln.cu) while gradients are
+# recorded on CUDA; off: nn.Dropout, +, nn.LayerNorm as the reference runs them.
+USE_FUSED_LAYER_NORM = True
+
+
+def dropout_residual_layer_norm(layer_norm, dropout, y, residual=None):
+    """layer_norm(dropout(y) + residual) - module.py:50-52 / attention.py:59-60 / encoder.py:49 of the reference - with the
+    parameters of the given nn.LayerNorm / nn.Dropout (dropout may be None)."""
+    if USE_FUSED_LAYER_NORM and y.is_cuda and torch.is_grad_enabled() and layer_norm.elementwise_affine:
+        from .. import ops
+        yc = y.contiguous()
+        rc = residual.contiguous() if residual is not None else None
+        if len(layer_norm.normalized_shape) == 1 and ops.residual_layer_norm_available(yc, rc, layer_norm.weight):
+            p = dropout.p if (dropout is not None and dropout.training) else 0.0
+            return ops.residual_layer_norm(yc, rc, layer_norm.weight, layer_norm.bias, layer_norm.eps, p, True)
+    if dropout is not None:
+        y = dropout(y)
+    return layer_norm(y + residual if residual is not None else y)
 
 
 class Linear(nn.Linear):
@@ -71,7 +89,7 @@ class PositionwiseFeedForward(nn.Module):
             h = linear_act(x, self.w_1.weight, self.w_1.bias, relu=True)
             return linear_residual_layernorm(h, self.w_2.weight, self.w_2.bias, x, self.layer_norm.weight,
                                              self.layer_norm.bias, self.layer_norm.eps)
-        return self.layer_norm(self.dropout(self.w_2(self.w_1(x, relu=True))) + x)
+        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.w_2(self.w_1(x, relu=True)), x)
 
 
 def fused_linear_ok(module, x, *linears):

@@ -230,13 +230,35 @@ int asr_linear_f32(const float* x, const float* w, const float* bias, int M, int
  * asr_gemm_f32 : fp32 in / out on the tensor cores at fp32-level accuracy (three TF32 products per K step).
  * asr_gemm_bf16: bf16 operands, fp32 accumulation, bf16 output (out_f32 = 0; relu = 1 fuses max(.,0)) or fp32 output
  *                (out_f32 = 1: weight gradients for fp32 master weights).
- * ws / ws_bytes: optional workspace of asr_gemm_workspace_bytes(M, N, K) bytes; with it, products with few output
- * tiles and a long contraction (dW) are split along K and reduced in a fixed order (deterministic).
+ * ws / ws_bytes: optional workspace of asr_gemm_workspace_bytes(M, N, K) bytes; passing it allows products with few
+ * output tiles (dW of a small layer; at the model's shapes nearly every product) to be split along K.  The CTAs of one
+ * output tile are a thread-block cluster and add their partial tiles through distributed shared memory in a fixed order
+ * (deterministic; the workspace itself is only used for 256-wide bf16 tiles and with option gemm_split_mode = 1).
  */
 size_t asr_gemm_workspace_bytes(int M, int N, int K);
 /* out[n] = sum_m x[m, n] in fp32 (x fp32 or bf16 [M,N], row stride ld elements): the bias gradient of a linear layer
  * (the column sums of gy), one pass, fixed order (deterministic). */
 int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, float* out, void* stream);
+/* LayerNorm(dropout(y) + residual) of a training step, and its backward - replaces what torch runs for
+ * /root/reference/src/transformer/module.py:50-52, attention.py:59-60 and encoder.py:49 (nn.Dropout, +, nn.LayerNorm and
+ * their autograd nodes).  y [M, D] fp32 or bf16 (y_bf16), residual [M, D] fp32 or NULL, gamma / beta [D], D = 256 / 512 /
+ * 1024; z [M, D] = dropout(y) + residual is written for the backward (NULL: not written - only when it would equal y);
+ * out [M, D], mean / rstd [M] fp32.  Dropout keeps an element when its Philox byte >= round(256 p_drop), scaled by
+ * 1 / asr_ln_dropout_keep_prob(p_drop); the mask is regenerated in the backward from the same seed (seed_dev != NULL: the
+ * seed is *seed_dev + seed, read on the device - CUDA-graph replays).
+ * asr_ln_bwd: g_out, z, mean, rstd, gamma as saved -> g_z [M, D] fp32 (the residual's gradient; NULL: not wanted), g_y [M, D]
+ * fp32 / bf16 (= g_z * keep / p_keep; NULL: not wanted), g_gamma_beta [2, D].  ws: asr_ln_bwd_workspace_bytes(M, D) bytes.
+ * Fixed summation orders throughout (deterministic). */
+float asr_ln_dropout_keep_prob(float p_drop);
+int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta, int M, int D,
+               float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
+               float* rstd, void* stream);
+size_t asr_ln_bwd_workspace_bytes(int M, int D);
+int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma, int M, int D,
+               float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
+               float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream);
+/* keep [M, D] u8 = 1 where that dropout keeps the element (tests, inspection) */
+int asr_ln_dropout_keep(uint8_t* keep, int M, int D, float p_drop, uint64_t seed, void* stream);
 int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,
                  const float* bias, int M, int N, int K, float* c, int ldc,
                  void* ws, size_t ws_bytes, void* stream);

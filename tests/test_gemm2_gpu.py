@@ -183,6 +183,7 @@ def test_model_linear_layers_train_through_the_repo_gemms(monkeypatch):
     def run(autocast, ours):
         monkeypatch.setattr(mod, "USE_TENSOR_CORE_FP32", ours)
         monkeypatch.setattr(mod, "USE_TENSOR_CORE_BF16", ours)
+        monkeypatch.setattr(mod, "USE_FUSED_LAYER_NORM", ours)
         ffn.zero_grad()
         xi = x.clone().requires_grad_(True)
         n0 = lib.launch_count()
