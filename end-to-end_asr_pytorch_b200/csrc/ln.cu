@@ -8,7 +8,8 @@
 // at a fifth of the memory bandwidth), and the dropout backward (read dz and the mask; write dy): 13 passes over a
 // [rows x d_model] tensor.  Here:
 //
-//   forward   read y, residual;  write z = dropout(y) + residual (saved for backward) and out;  mean / rstd per row
+//   forward   read y, residual;  write z = dropout(y) + residual (saved for backward) and out;  mean / rstd per row;
+//             out may be scaled per row (the non-pad mask every layer multiplies its sub-layers' outputs with)
 //   backward  read g_out, z;     write dz (= the residual's gradient) and dy = dz * keep / p_keep;  gamma / beta gradients
 //             accumulated in registers over the rows a warp walks, added across the CTA's warps in a fixed order, one
 //             partial row per CTA, and a column sum over the partial rows (gemm2.cu's asr_colsum): deterministic
@@ -36,6 +37,7 @@ struct LnArgs {
     const float* residual;    // [M, D] or null
     const float* gamma;
     const float* beta;
+    const float* row_scale;   // [M] or null: out = LayerNorm(...) * row_scale[row] (the layers' non-pad mask)
     float* z;                 // forward: out (nullable);  backward: in
     float* out;               // forward: LayerNorm output;  backward: g_out (in)
     float* mean;              // [M]
@@ -143,13 +145,14 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const LnArgs a) {
             a.mean[row] = mean;
             a.rstd[row] = rstd;
         }
+        const float rs = a.row_scale != nullptr ? __ldg(a.row_scale + row) : 1.0f;
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             float4 o;
-            o.x = (v[j][0] - mean) * rstd * gam[j][0] + bet[j][0];
-            o.y = (v[j][1] - mean) * rstd * gam[j][1] + bet[j][1];
-            o.z = (v[j][2] - mean) * rstd * gam[j][2] + bet[j][2];
-            o.w = (v[j][3] - mean) * rstd * gam[j][3] + bet[j][3];
+            o.x = ((v[j][0] - mean) * rstd * gam[j][0] + bet[j][0]) * rs;
+            o.y = ((v[j][1] - mean) * rstd * gam[j][1] + bet[j][1]) * rs;
+            o.z = ((v[j][2] - mean) * rstd * gam[j][2] + bet[j][2]) * rs;
+            o.w = ((v[j][3] - mean) * rstd * gam[j][3] + bet[j][3]) * rs;
             store4(a.out + base + 4 * (lane + 32 * j), o);
         }
     }
@@ -174,12 +177,13 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const LnArgs a) {
     for (int row = blockIdx.x * kLnWarps + warp; row < a.M; row += gridDim.x * kLnWarps) {
         const size_t base = (size_t)row * D;
         const float mean = a.mean[row], rstd = a.rstd[row];
+        const float rs = a.row_scale != nullptr ? __ldg(a.row_scale + row) : 1.0f;
         float go[NJ][4], xh[NJ][4];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const float4 g = *reinterpret_cast<const float4*>(a.out + base + 4 * (lane + 32 * j));
             const float4 z = *reinterpret_cast<const float4*>(a.z + base + 4 * (lane + 32 * j));
-            go[j][0] = g.x; go[j][1] = g.y; go[j][2] = g.z; go[j][3] = g.w;
+            go[j][0] = g.x * rs; go[j][1] = g.y * rs; go[j][2] = g.z * rs; go[j][3] = g.w * rs;
             xh[j][0] = (z.x - mean) * rstd; xh[j][1] = (z.y - mean) * rstd; xh[j][2] = (z.z - mean) * rstd; xh[j][3] = (z.w - mean) * rstd;
         }
         float s1 = 0.0f, s2 = 0.0f;
@@ -268,8 +272,8 @@ static int ln_check(const char* who, int M, int D, float p_drop) {
 
 extern "C" float asr_ln_dropout_keep_prob(float p_drop) { return (256.0f - (float)drop_threshold(p_drop)) / 256.0f; }
 
-extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta, int M, int D,
-                          float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
+extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta,
+                          const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
                           float* rstd, void* stream) {
     if (ln_check("asr_ln_fwd", M, D, p_drop)) return 2;
     ASR_REQUIRE(y && gamma && beta && out && mean && rstd, "asr_ln_fwd: null pointer");
@@ -277,7 +281,7 @@ extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, cons
                 "asr_ln_fwd: pointers must be 16-byte aligned");
     if (asr_device_ok() != 0) return 3;
     LnArgs a = {};
-    a.y = y; a.residual = residual; a.gamma = gamma; a.beta = beta; a.z = z; a.out = out; a.mean = mean; a.rstd = rstd;
+    a.y = y; a.residual = residual; a.gamma = gamma; a.beta = beta; a.row_scale = row_scale; a.z = z; a.out = out; a.mean = mean; a.rstd = rstd;
     a.seed_dev = seed_dev; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
     a.thresh = drop_threshold(p_drop);
     a.inv_keep = 256.0f / (256.0f - (float)a.thresh);
@@ -294,8 +298,8 @@ extern "C" size_t asr_ln_bwd_workspace_bytes(int M, int D) {
     return (size_t)ln_grid(M) * 2 * (size_t)D * sizeof(float);
 }
 
-extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma, int M, int D,
-                          float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
+extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
+                          const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                           float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream) {
     if (ln_check("asr_ln_bwd", M, D, p_drop)) return 2;
     ASR_REQUIRE(g_out && z && mean && rstd && gamma && g_gamma_beta && ws, "asr_ln_bwd: null pointer");
@@ -305,7 +309,7 @@ extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean,
     ASR_REQUIRE(ws_bytes >= asr_ln_bwd_workspace_bytes(M, D), "asr_ln_bwd: workspace too small");
     if (asr_device_ok() != 0) return 3;
     LnArgs a = {};
-    a.gamma = gamma; a.z = const_cast<float*>(z); a.out = const_cast<float*>(g_out);
+    a.gamma = gamma; a.row_scale = row_scale; a.z = const_cast<float*>(z); a.out = const_cast<float*>(g_out);
     a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd);
     a.g_z = g_z; a.g_y = g_y; a.partial = static_cast<float*>(ws);
     a.seed_dev = seed_dev; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);

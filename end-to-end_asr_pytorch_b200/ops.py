@@ -798,7 +798,7 @@ LN_WIDTHS = (256, 512, 1024)
 
 class _ResidualLayerNormFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, residual, weight, bias, eps, p_drop, seed, seed_dev):
+    def forward(ctx, y, residual, weight, bias, eps, p_drop, seed, seed_dev, row_scale):
         D = y.shape[-1]
         y2 = y.reshape(-1, D)
         r2 = residual.reshape(-1, D) if residual is not None else None
@@ -811,16 +811,16 @@ class _ResidualLayerNormFunction(torch.autograd.Function):
         z = None if z_is_y else torch.empty((M, D), dtype=torch.float32, device=dev)
         w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         with torch.cuda.device(dev):
-            check(_lib.lib().asr_ln_fwd(ptr(y2), int(y2.dtype == torch.bfloat16), ptr(r2), ptr(w32), ptr(b32), M, D,
+            check(_lib.lib().asr_ln_fwd(ptr(y2), int(y2.dtype == torch.bfloat16), ptr(r2), ptr(w32), ptr(b32), ptr(row_scale), M, D,
                                         ctypes.c_float(eps), ctypes.c_float(p_drop), ctypes.c_uint64(seed), ptr(seed_dev),
                                         ptr(z), ptr(out), ptr(mean), ptr(rstd), stream_ptr()), "asr_ln_fwd")
-        ctx.save_for_backward(y2 if z_is_y else z, mean, rstd, w32, seed_dev)
+        ctx.save_for_backward(y2 if z_is_y else z, mean, rstd, w32, seed_dev, row_scale)
         ctx.meta = (y.shape, y.dtype, residual is not None, p_drop, seed)
         return out.reshape(y.shape)
 
     @staticmethod
     def backward(ctx, g_out):
-        z, mean, rstd, w32, seed_dev = ctx.saved_tensors
+        z, mean, rstd, w32, seed_dev, row_scale = ctx.saved_tensors
         shape, y_dtype, has_res, p_drop, seed = ctx.meta
         M, D = z.shape
         dev = z.device
@@ -837,12 +837,12 @@ class _ResidualLayerNormFunction(torch.autograd.Function):
         ws_bytes = _lib.lib().asr_ln_bwd_workspace_bytes(M, D)
         ws = torch.empty((ws_bytes // 4 + 4,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(_lib.lib().asr_ln_bwd(ptr(g2), ptr(z), ptr(mean), ptr(rstd), ptr(w32), M, D, ctypes.c_float(p_drop),
+            check(_lib.lib().asr_ln_bwd(ptr(g2), ptr(z), ptr(mean), ptr(rstd), ptr(w32), ptr(row_scale), M, D, ctypes.c_float(p_drop),
                                         ctypes.c_uint64(seed), ptr(seed_dev), ptr(g_z), ptr(g_y), int(y_dtype == torch.bfloat16),
                                         ptr(g_wb), ptr(ws), ws_bytes, stream_ptr()), "asr_ln_bwd")
         gy = (g_z if same else g_y).reshape(shape) if need_y else None
         gr = g_z.reshape(shape) if need_r else None
-        return gy, gr, g_wb[0], g_wb[1], None, None, None, None
+        return gy, gr, g_wb[0], g_wb[1], None, None, None, None, None
 
 
 def residual_layer_norm_available(y, residual, weight):
@@ -852,12 +852,13 @@ def residual_layer_norm_available(y, residual, weight):
             and (residual is None or (residual.dtype == torch.float32 and residual.shape == y.shape and residual.is_contiguous())))
 
 
-def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, training=True, seed=None):
-    """LayerNorm(dropout(y) + residual) -> fp32, with autograd (module.py:50-52, attention.py:59-60, encoder.py:49 of the
+def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, training=True, seed=None, row_scale=None):
+    """LayerNorm(dropout(y) + residual) [* row_scale] -> fp32, with autograd (module.py:50-52, attention.py:59-60, encoder.py:49 of the
     reference): one kernel forward, one (+ a column sum of per-CTA partials) backward.  y [..., D] fp32 or bf16, residual
     [..., D] fp32 or None, weight / bias [D] (gamma / beta).  The dropout mask comes from the library's Philox stream
     (`seed`: default drawn from torch's CPU generator; inside `device_dropout_seed(...)` read from the device) and is
-    regenerated in the backward - see ln_dropout_keep."""
+    regenerated in the backward - see ln_dropout_keep.  row_scale: one constant factor per row ([...] or [..., 1], e.g. the
+    non-pad mask the layers multiply every sub-layer output with - encoder.py:76-80, decoder.py:628-634)."""
     _require_cuda("y", y)
     if not residual_layer_norm_available(y, residual, weight):
         raise ValueError("residual_layer_norm: unsupported operands (width %d, dtypes %s / %s)" % (
@@ -871,7 +872,11 @@ def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, trai
             seed_dev, seed = _active_seed.take()
         else:
             seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    return _ResidualLayerNormFunction.apply(y, residual, weight, bias, float(eps), p, int(seed or 0), seed_dev)
+    if row_scale is not None:
+        if row_scale.numel() != y.numel() // y.shape[-1]:
+            raise ValueError("residual_layer_norm: row_scale must hold one factor per row")
+        row_scale = row_scale.detach().reshape(-1).to(device=y.device, dtype=torch.float32).contiguous()
+    return _ResidualLayerNormFunction.apply(y, residual, weight, bias, float(eps), p, int(seed or 0), seed_dev, row_scale)
 
 
 def ln_dropout_keep(M, D, dropout_p, seed, device="cuda"):

@@ -61,10 +61,12 @@ class MultiheadAttention(nn.Module):
 
         self.dropout = nn.Dropout(dropout)
 
-    def forward(self, q, k, v, mask=None, kv_len=None, causal=False):
+    def forward(self, q, k, v, mask=None, kv_len=None, causal=False, out_scale=None):
         """q [B,Lq,d_model], k,v [B,Lk,d_model], mask [B,Lq,Lk] (True = masked) or None.
         `kv_len` / `causal` are optional structured forms of the reference's masks
-        (get_attn_pad_mask / get_subsequent_mask); they are OR-ed with `mask`."""
+        (get_attn_pad_mask / get_subsequent_mask); they are OR-ed with `mask`.
+        `out_scale` [B,Lq,1] (optional): the non-pad mask the calling layer multiplies the output with
+        (encoder.py:76, decoder.py:628-632), folded into the LayerNorm kernel on the training path."""
         n_head, d_k, d_v = self.n_head, self.d_k, self.d_v
         sz_b, len_q, _ = q.size()
         len_k = k.size(1)
@@ -76,9 +78,17 @@ class MultiheadAttention(nn.Module):
             kh = linear_act(k, self.w_ks.weight, self.w_ks.bias).view(sz_b, len_k, n_head, d_k)
             vh = linear_act(v, self.w_vs.weight, self.w_vs.bias).view(sz_b, len_k, n_head, d_v)
         else:
-            qh = self.w_qs(q).view(sz_b, len_q, n_head, d_k)
-            kh = self.w_ks(k).view(sz_b, len_k, n_head, d_k)
-            vh = self.w_vs(v).view(sz_b, len_k, n_head, d_v)
+            qi, ki, vi = q, k, v
+            bf16_autocast = (q.is_cuda and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16)
+            if bf16_autocast and q.dtype == torch.float32:
+                # autocast casts every Linear input on its own: a self-attention layer would convert the same activations
+                # three times (and its backward convert three gradients back); once is enough
+                qi = q.to(torch.bfloat16)
+                ki = qi if k is q else k.to(torch.bfloat16)
+                vi = ki if v is k else (qi if v is q else v.to(torch.bfloat16))
+            qh = self.w_qs(qi).view(sz_b, len_q, n_head, d_k)
+            kh = self.w_ks(ki).view(sz_b, len_k, n_head, d_k)
+            vh = self.w_vs(vi).view(sz_b, len_k, n_head, d_v)
 
         p_attn = self.attn_dropout_p if self.training else 0.0
         ctx = mha_core(qh, kh, vh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature),
@@ -87,8 +97,11 @@ class MultiheadAttention(nn.Module):
         if self.RETURN_ATTN_DEFAULT if self.return_attn is None else self.return_attn:
             attn = mha_probs(qh, kh, kv_len=kv_len, mask=mask, causal=causal, scale=1.0 / float(self.temperature))
 
-        output = ctx.reshape(sz_b, len_q, n_head * d_v).to(q.dtype)
+        output = ctx.reshape(sz_b, len_q, n_head * d_v)
         if fused:      # fc + bias + residual + LayerNorm in one kernel (the 512-wide row stays in tensor memory)
-            return linear_residual_layernorm(output, self.fc.weight, self.fc.bias, residual, self.layer_norm.weight,
-                                             self.layer_norm.bias, self.layer_norm.eps), attn
-        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.fc(output), residual), attn
+            out = linear_residual_layernorm(output.to(q.dtype), self.fc.weight, self.fc.bias, residual, self.layer_norm.weight,
+                                            self.layer_norm.bias, self.layer_norm.eps)
+            return (out if out_scale is None else out * out_scale), attn
+        if not (q.is_cuda and torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16):
+            output = output.to(q.dtype)       # under bf16 autocast the projection takes the kernel's bf16 output as it is
+        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.fc(output), residual, out_scale), attn

@@ -28,12 +28,10 @@ class DecoderLayer(nn.Module):
                 slf_kv_len=None, slf_causal=False, enc_kv_len=None):
         """The masks are the reference's dense [B,Lq,Lk] tensors and / or their structured forms
         (`slf_kv_len` + `slf_causal` for decoder.py:74-78, `enc_kv_len` for get_attn_pad_mask)."""
-        out, _ = self.slf_attn(dec_input, dec_input, dec_input, mask=slf_attn_mask, kv_len=slf_kv_len, causal=slf_causal)
-        out = out * non_pad_mask
-        out, _ = self.enc_attn(out, enc_output, enc_output, mask=dec_enc_attn_mask, kv_len=enc_kv_len)
-        out = out * non_pad_mask
-        out = self.pos_ffn(out) * non_pad_mask
-        return out
+        out, _ = self.slf_attn(dec_input, dec_input, dec_input, mask=slf_attn_mask, kv_len=slf_kv_len, causal=slf_causal,
+                               out_scale=non_pad_mask)
+        out, _ = self.enc_attn(out, enc_output, enc_output, mask=dec_enc_attn_mask, kv_len=enc_kv_len, out_scale=non_pad_mask)
+        return self.pos_ffn(out, out_scale=non_pad_mask)
 
 
 class Decoder(nn.Module):

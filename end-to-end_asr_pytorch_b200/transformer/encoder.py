@@ -19,10 +19,9 @@ class EncoderLayer(nn.Module):
         self.pos_ffn = PositionwiseFeedForward(d_model, d_inner, dropout=dropout)
 
     def forward(self, enc_input, non_pad_mask=None, slf_attn_mask=None, kv_len=None, causal=False):
-        out, _ = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask, kv_len=kv_len, causal=causal)
-        out = out * non_pad_mask
-        out = self.pos_ffn(out) * non_pad_mask
-        return out
+        out, _ = self.slf_attn(enc_input, enc_input, enc_input, mask=slf_attn_mask, kv_len=kv_len, causal=causal,
+                               out_scale=non_pad_mask)
+        return self.pos_ffn(out, out_scale=non_pad_mask)
 
 
 class Encoder(nn.Module):

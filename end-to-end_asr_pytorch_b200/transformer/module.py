@@ -23,19 +23,21 @@ USE_TENSOR_CORE_BF16 = True
 USE_FUSED_LAYER_NORM = True
 
 
-def dropout_residual_layer_norm(layer_norm, dropout, y, residual=None):
-    """layer_norm(dropout(y) + residual) - module.py:50-52 / attention.py:59-60 / encoder.py:49 of the reference - with the
-    parameters of the given nn.LayerNorm / nn.Dropout (dropout may be None)."""
+def dropout_residual_layer_norm(layer_norm, dropout, y, residual=None, row_scale=None):
+    """layer_norm(dropout(y) + residual) [* row_scale] - module.py:50-52 / attention.py:59-60 / encoder.py:49 of the reference,
+    and the non-pad mask the layers apply next (encoder.py:76-80) - with the parameters of the given nn.LayerNorm /
+    nn.Dropout (dropout may be None).  row_scale: [..., 1] or None."""
     if USE_FUSED_LAYER_NORM and y.is_cuda and torch.is_grad_enabled() and layer_norm.elementwise_affine:
         from .. import ops
         yc = y.contiguous()
         rc = residual.contiguous() if residual is not None else None
         if len(layer_norm.normalized_shape) == 1 and ops.residual_layer_norm_available(yc, rc, layer_norm.weight):
             p = dropout.p if (dropout is not None and dropout.training) else 0.0
-            return ops.residual_layer_norm(yc, rc, layer_norm.weight, layer_norm.bias, layer_norm.eps, p, True)
+            return ops.residual_layer_norm(yc, rc, layer_norm.weight, layer_norm.bias, layer_norm.eps, p, True, row_scale=row_scale)
     if dropout is not None:
         y = dropout(y)
-    return layer_norm(y + residual if residual is not None else y)
+    out = layer_norm(y + residual if residual is not None else y)
+    return out if row_scale is None else out * row_scale
 
 
 class Linear(nn.Linear):
@@ -82,14 +84,17 @@ class PositionwiseFeedForward(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.layer_norm = nn.LayerNorm(d_model)
 
-    def forward(self, x):
+    def forward(self, x, out_scale=None):
+        """out_scale [..., 1] (optional): the non-pad mask the calling layer multiplies the result with, folded into the
+        LayerNorm kernel on the training path."""
         if fused_linear_ok(self, x, self.w_1, self.w_2):
             # evaluation in bf16: two tcgen05 GEMMs, bias + ReLU and bias + residual + LayerNorm in their epilogues
             from ..ops import linear_act, linear_residual_layernorm
             h = linear_act(x, self.w_1.weight, self.w_1.bias, relu=True)
-            return linear_residual_layernorm(h, self.w_2.weight, self.w_2.bias, x, self.layer_norm.weight,
-                                             self.layer_norm.bias, self.layer_norm.eps)
-        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.w_2(self.w_1(x, relu=True)), x)
+            out = linear_residual_layernorm(h, self.w_2.weight, self.w_2.bias, x, self.layer_norm.weight,
+                                            self.layer_norm.bias, self.layer_norm.eps)
+            return out if out_scale is None else out * out_scale
+        return dropout_residual_layer_norm(self.layer_norm, self.dropout, self.w_2(self.w_1(x, relu=True)), x, out_scale)
 
 
 def fused_linear_ok(module, x, *linears):

@@ -243,19 +243,20 @@ int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, float* out, voi
  * /root/reference/src/transformer/module.py:50-52, attention.py:59-60 and encoder.py:49 (nn.Dropout, +, nn.LayerNorm and
  * their autograd nodes).  y [M, D] fp32 or bf16 (y_bf16), residual [M, D] fp32 or NULL, gamma / beta [D], D = 256 / 512 /
  * 1024; z [M, D] = dropout(y) + residual is written for the backward (NULL: not written - only when it would equal y);
- * out [M, D], mean / rstd [M] fp32.  Dropout keeps an element when its Philox byte >= round(256 p_drop), scaled by
+ * out [M, D], mean / rstd [M] fp32.  row_scale [M] or NULL: out is multiplied by row_scale[row] (the non-pad mask of
+ * encoder.py:76-80 / decoder.py:628-634; constant, no gradient).  Dropout keeps an element when its Philox byte >= round(256 p_drop), scaled by
  * 1 / asr_ln_dropout_keep_prob(p_drop); the mask is regenerated in the backward from the same seed (seed_dev != NULL: the
  * seed is *seed_dev + seed, read on the device - CUDA-graph replays).
  * asr_ln_bwd: g_out, z, mean, rstd, gamma as saved -> g_z [M, D] fp32 (the residual's gradient; NULL: not wanted), g_y [M, D]
  * fp32 / bf16 (= g_z * keep / p_keep; NULL: not wanted), g_gamma_beta [2, D].  ws: asr_ln_bwd_workspace_bytes(M, D) bytes.
  * Fixed summation orders throughout (deterministic). */
 float asr_ln_dropout_keep_prob(float p_drop);
-int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta, int M, int D,
-               float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
+int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta,
+               const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
                float* rstd, void* stream);
 size_t asr_ln_bwd_workspace_bytes(int M, int D);
-int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma, int M, int D,
-               float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
+int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
+               const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream);
 /* keep [M, D] u8 = 1 where that dropout keeps the element (tests, inspection) */
 int asr_ln_dropout_keep(uint8_t* keep, int M, int D, float p_drop, uint64_t seed, void* stream);

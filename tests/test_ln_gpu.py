@@ -86,6 +86,33 @@ def test_dropout_mask_is_regenerated_in_the_backward(M, D, p, dtype):
     assert _rel(ev, _reference(y, res, w, b, 1e-5)[0].detach()) <= 2e-6
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_row_scale_is_the_non_pad_mask_of_the_layers(dtype):
+    """out = LayerNorm(dropout(y) + residual) * mask[row] (encoder.py:76-80, decoder.py:628-634 of the reference): masked rows
+    are exact zeros and pass no gradient - not to y, not to the residual, not to gamma / beta."""
+    ops = pkg("ops")
+    M, D, p, seed = 1350, 512, 0.1, 99
+    keep, keep_prob = ops.ln_dropout_keep(M, D, p, seed)
+    mask = (torch.arange(M, device="cuda") % 15 < 11).reshape(90, 15, 1)
+    y = _rand((90, 15, D), 1, 2.0, dtype).requires_grad_(True)
+    res = _rand((90, 15, D), 2).requires_grad_(True)
+    w = (_rand((D,), 3, 0.2) + 1.0).requires_grad_(True)
+    b = _rand((D,), 4, 0.1).requires_grad_(True)
+    g = _rand((90, 15, D), 5)
+    out = ops.residual_layer_norm(y, res, w, b, 1e-5, dropout_p=p, seed=seed, row_scale=mask)
+    out.backward(g)
+    ref, (yd, rd, wd, bd) = _reference(y.reshape(M, D), res.reshape(M, D), w, b, 1e-5, keep, keep_prob)
+    ref = ref * mask.reshape(M, 1).double()
+    ref.backward(g.reshape(M, D).double())
+    assert (out[~mask.expand_as(out)] == 0).all()
+    assert _rel(out.reshape(M, D), ref.detach()) <= 2e-6
+    assert _rel(y.grad.reshape(M, D), yd.grad) <= (1e-5 if dtype == torch.float32 else 6e-3)
+    assert (res.grad[~mask.expand_as(out)] == 0).all()
+    assert _rel(res.grad.reshape(M, D), rd.grad) <= 1e-5 and _rel(w.grad, wd.grad) <= 1e-5 and _rel(b.grad, bd.grad) <= 1e-5
+    with pytest.raises(ValueError):
+        ops.residual_layer_norm(y, res, w, b, row_scale=mask[:, :3])
+
+
 def test_device_side_seed_matches_the_host_seed_it_stands_for():
     """Inside device_dropout_seed(...) the kernels read *seed_dev + the call's constant (CUDA-graph replays): the same mask
     as passing that sum from the host, and a new one after advance()."""
@@ -133,6 +160,7 @@ def test_sub_layers_train_through_the_fused_layer_norm(monkeypatch, autocast):
     mha.return_attn = False
     x = _rand((8, 168, 512), 5)
     gy = _rand((8, 168, 512), 6)
+    pad = (torch.arange(168, device="cuda")[None, :, None] < torch.tensor([168, 100, 7, 168, 1, 50, 160, 33], device="cuda")[:, None, None]).float()
 
     def run(fused):
         monkeypatch.setattr(mod, "USE_FUSED_LAYER_NORM", fused)
@@ -142,7 +170,7 @@ def test_sub_layers_train_through_the_fused_layer_norm(monkeypatch, autocast):
             xi = x.clone().requires_grad_(True)
             n0 = lib.launch_count()
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
-                y = layer(xi) if name == "ffn" else layer(xi, xi, xi)[0]
+                y = layer(xi, out_scale=pad) if name == "ffn" else layer(xi, xi, xi, out_scale=pad)[0]
             assert y.dtype == torch.float32
             y.backward(gy)
             res[name] = (lib.launch_count() - n0, y.detach(), xi.grad.clone(), {k: p.grad.clone() for k, p in layer.named_parameters()})
