@@ -580,6 +580,36 @@ def spec_aug_microbench(device, iters=5):
             "shape": "B=%d T=%d V=%d, %d bands + %d spans per utterance" % (B, T, V, R, R)}
 
 
+def layer_norm_microbench(device, iters=10):
+    """LayerNorm(dropout(y) + residual) * non-pad mask, forward and backward (csrc/ln.cu) at the bench batch
+    (M = 64 x 1600 frames, d_model 512; y bf16 as under autocast, residual / out fp32, dropout 0.1): HBM-bound, every
+    tensor (105 - 210 MB) larger than L2.  Algorithmic bytes per element: forward 2 (y) + 4 (residual) + 4 (z, saved) +
+    4 (out); backward 4 (g) + 4 (z) + 4 (dz) + 2 (dy); the gamma / beta partial rows and their column sum are noise."""
+    ops = pkg("ops")
+    M, D = 64 * 1600, 512
+    g = torch.Generator(device=device).manual_seed(10)
+    y = torch.randn(M, D, device=device, generator=g).bfloat16().requires_grad_(True)
+    res = torch.randn(M, D, device=device, generator=g).requires_grad_(True)
+    gam = torch.ones(D, device=device, requires_grad=True)
+    bet = torch.zeros(D, device=device, requires_grad=True)
+    mask = (torch.rand(M, device=device, generator=g) < 0.8).float()
+    go = torch.randn(M, D, device=device, generator=g)
+    out = [None]
+
+    def fwd():
+        out[0] = ops.residual_layer_norm(y, res, gam, bet, 1e-5, dropout_p=0.1, seed=11, row_scale=mask)
+
+    def bwd():
+        out[0].backward(go, retain_graph=True)
+        y.grad = res.grad = gam.grad = bet.grad = None
+    f = cuda_time(fwd, iters)
+    b = cuda_time(bwd, iters)
+    nb = 14 * M * D
+    return {"ln_fwd": {"ms": f, "algorithmic_bytes": nb, "GBps": nb / (f * 1e-3) / 1e9},
+            "ln_bwd": {"ms": b, "algorithmic_bytes": nb, "GBps": nb / (b * 1e-3) / 1e9},
+            "shape": "M=%d D=%d, y bf16, residual / out fp32, dropout 0.1, row mask" % (M, D)}
+
+
 def linear_microbench(device, iters=10):
     """Fused tcgen05 linear layers on the feed-forward block of the encoder at the bench batch
     (M = 64 x 1600 frames, d_model 512, d_inner 2048), next to torch's cuBLAS + eager epilogue on the same tensors."""
@@ -1140,6 +1170,13 @@ def main():
         kernels.append({"kernel": "spec_aug", "bound": "hbm", "ms": sa["ms"], "algorithmic_bytes": sa["algorithmic_bytes"],
                         "GBps": sa["GBps"], "frac_of_hbm_peak": sa["GBps"] / peaks["hbm_gbs"], "shape": sa["shape"],
                         "in_timed_step": False, "note": "SURVEY 8(f4): SpecAugment, three launches incl. the means"})
+        lnb = layer_norm_microbench(device)
+        for n in ("ln_fwd", "ln_bwd"):
+            kernels.append({"kernel": n, "bound": "hbm", "ms": lnb[n]["ms"], "algorithmic_bytes": lnb[n]["algorithmic_bytes"],
+                            "GBps": lnb[n]["GBps"], "frac_of_hbm_peak": lnb[n]["GBps"] / peaks["hbm_gbs"], "shape": lnb["shape"],
+                            "in_timed_step": False,
+                            "note": "SURVEY 8(f3): dropout + residual + LayerNorm (+ non-pad mask) in one kernel each way; "
+                                    "the backward figure includes the column sum of the per-CTA gamma / beta partial rows"})
         lin = linear_microbench(device)
         for n in ("linear_bias_relu", "linear_residual_layernorm", "linear_f32_3xtf32"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": lin[n]["ms"], "TFLOPs": lin[n]["TFLOPs"],
@@ -1155,7 +1192,7 @@ def main():
             "fwd": {"bound": "tensor", "kernel": "asr::mha_fwdp_kernel<false> (persistent two-tile forward)", "achieved": top["fwd_TFLOPs"],
                     "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": top["fwd_frac_of_bf16_peak"],
                     "avg_launch_ms": top["fwd_ms"], "shape": top["shape"], "flops": "4 B h Lq Lk d"},
-            "bwd": {"bound": "tensor", "kernel": "asr::mha_bwd_kernel<4, false> (+ delta and dQ-convert kernels)",
+            "bwd": {"bound": "tensor", "kernel": "asr::mha_bwdp_kernel<false> (persistent; + delta and dQ-convert kernels)",
                     "achieved": top["bwd_TFLOPs"], "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": top["bwd_frac_of_bf16_peak"], "avg_launch_ms": top["bwd_ms"], "shape": top["shape"],
                     "flops": "10 B h Lq Lk d"},

@@ -61,8 +61,12 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
     return r;
 }
-__device__ __forceinline__ void cluster_sync_all(bool alone) {      // alone: a cluster of one CTA (or no cluster at all)
+// alone: a cluster of one CTA (or no cluster at all).  exit_only: the barrier only keeps a CTA's shared memory alive until its
+// peers have read it - no data is handed over, so the arrival needs no release (which costs a MEMBAR.ALL.GPU behind the
+// epilogue's global stores) and the wait no acquire (a CCTL.IVALL)
+__device__ __forceinline__ void cluster_sync_all(bool alone, bool exit_only = false) {
     if (alone) __syncthreads();
+    else if (exit_only) asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
     else asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_addr, uint32_t cta) {
@@ -374,7 +378,7 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             };
             cluster_splitk_reduce<BN>(smem, threadIdx.x, min(BN, n_store - n0), bias4, emit);
         }
-        cluster_sync_all(alone);        // nobody leaves while a peer still reads its partial tile
+        cluster_sync_all(alone, true);  // nobody leaves while a peer still reads its partial tile
     }
     __syncthreads();
     if (warp == 5) {
@@ -584,7 +588,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             };
             cluster_splitk_reduce<BN>(smem, threadIdx.x, min(BN, n_store - n0), bias4, emit);
         }
-        cluster_sync_all(alone);
+        cluster_sync_all(alone, true);
     }
     __syncthreads();
     if (warp == 5) {
@@ -676,7 +680,7 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const T* __restrict__ x, i
         }
         out[blockIdx.x * kCols + threadIdx.x] = t;
     }
-    cluster_sync_all(alone);          // the chunks' shared memory stays until CTA 0 has read it
+    cluster_sync_all(alone, true);    // the chunks' shared memory stays until CTA 0 has read it
 }
 
 }  // namespace asr

@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(256) ln_dropout_keep_kernel(uint8_t* keep, int
     for (int e = 0; e < 4; ++e) keep[(size_t)row * D + 4 * grp + e] = philox_byte(rnd, 4 * (j & 3) + e) >= thresh ? 1 : 0;
 }
 
-static int ln_grid(int M) { return std::max(1, std::min((M + kLnWarps - 1) / kLnWarps, 2 * num_sms())); }
+// CTAs per SM: what the registers allow (forward 80 -> 3, backward 128 -> 2); an HBM-bound kernel wants the loads of all of them in flight
+static int ln_grid(int M, int per_sm) { return std::max(1, std::min((M + kLnWarps - 1) / kLnWarps, per_sm * num_sms())); }
 
 }  // namespace asr
 
@@ -287,7 +288,7 @@ extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, cons
     a.inv_keep = 256.0f / (256.0f - (float)a.thresh);
     a.eps = eps; a.M = M;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ln_grid(M);
+    const int grid = ln_grid(M, 3);
     ASR_LN_DISPATCH(ln_fwd_kernel, y_bf16, D, <<<grid, kLnWarps * 32, 0, st>>>(a));
     ASR_LAUNCH_CHECK();
     return 0;
@@ -295,7 +296,7 @@ extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, cons
 
 extern "C" size_t asr_ln_bwd_workspace_bytes(int M, int D) {
     if (M <= 0 || D <= 0) return 0;
-    return (size_t)ln_grid(M) * 2 * (size_t)D * sizeof(float);
+    return (size_t)ln_grid(M, 2) * 2 * (size_t)D * sizeof(float);
 }
 
 extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
@@ -317,7 +318,7 @@ extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean,
     a.inv_keep = 256.0f / (256.0f - (float)a.thresh);
     a.M = M;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int grid = ln_grid(M);
+    const int grid = ln_grid(M, 2);
     ASR_LN_DISPATCH(ln_bwd_kernel, y_bf16, D, <<<grid, kLnWarps * 32, 0, st>>>(a));
     ASR_LAUNCH_CHECK();
     return asr_colsum(ws, 0, grid, 2 * D, 2 * D, g_gamma_beta, stream);
