@@ -928,20 +928,43 @@ __global__ void __launch_bounds__(256) ctc_apply_kernel(const CtcArgs a) {
     if (t >= Tb) return;
     const int Sb = min(max(__ldg(a.tgt_len + b), 0), a.S);
     const float scale = 1.0f / ((float)a.Bn * (float)max(Sb, 1));
-    const float* orow = a.glp + (size_t)row * a.SP;
-    const int* dl = a.dlink + (size_t)b * a.S;
-    float* grow = a.g + (size_t)row * a.ld;
-    for (int j = lane; j <= Sb; j += 32) {
-        float v = orow[j];
-        int c = a.blank;
-        if (j > 0) {
-            const int link = __ldg(dl + j - 1);
-            if (link >> 30) continue;   // a repeat: its first occurrence carries the sum
-            for (int nx = (link & 0x3fffffff) - 1; nx >= 0; nx = (__ldg(dl + nx) & 0x3fffffff) - 1) v += orow[1 + nx];
-            c = (int)__ldg(a.targets + (size_t)b * a.S + (j - 1));
-            c = min(max(c, 0), a.V - 1);
+    const float* __restrict__ orow = a.glp + (size_t)row * a.SP;
+    const int* __restrict__ dl = a.dlink + (size_t)b * a.S;
+    float* __restrict__ grow = a.g + (size_t)row * a.ld;
+    // Up to four entries per lane and pass (S + 1 <= 128 in one pass), in three phases so that a lane's independent
+    // loads are in flight together: occupancies / links / classes, then the gradient words, then the stores.  Every
+    // address of the row is touched by exactly one (lane, entry), so the order of the read-modify-writes is free.
+    constexpr int kE = 4;
+    for (int j0 = 0; j0 <= Sb; j0 += 32 * kE) {
+        float v[kE], g[kE];
+        int c[kE], link[kE];
+        bool ok[kE];
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+            const int j = j0 + lane + 32 * e;
+            ok[e] = j <= Sb;
+            v[e] = ok[e] ? orow[j] : 0.0f;
+            link[e] = (ok[e] && j > 0) ? __ldg(dl + j - 1) : 0;
+            c[e] = (ok[e] && j > 0) ? (int)__ldg(a.targets + (size_t)b * a.S + (j - 1)) : a.blank;
         }
-        if (!(fabsf(v) < 1.0e-12f)) grow[c] -= v * scale;   // NaN goes through
+#pragma unroll
+        for (int e = 0; e < kE; ++e) {
+            const int j = j0 + lane + 32 * e;
+            if (ok[e] && j > 0) {
+                if (link[e] >> 30) {
+                    ok[e] = false;      // a repeat: its first occurrence carries the sum
+                } else {
+                    for (int nx = (link[e] & 0x3fffffff) - 1; nx >= 0; nx = (__ldg(dl + nx) & 0x3fffffff) - 1) v[e] += orow[1 + nx];
+                    c[e] = min(max(c[e], 0), a.V - 1);
+                }
+            }
+            ok[e] = ok[e] && !(fabsf(v[e]) < 1.0e-12f);      // NaN goes through
+        }
+#pragma unroll
+        for (int e = 0; e < kE; ++e) g[e] = ok[e] ? grow[c[e]] : 0.0f;
+#pragma unroll
+        for (int e = 0; e < kE; ++e)
+            if (ok[e]) grow[c[e]] = g[e] - v[e] * scale;
     }
 }
 
