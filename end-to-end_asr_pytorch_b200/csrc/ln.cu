@@ -245,6 +245,28 @@ __global__ void __launch_bounds__(256) ln_dropout_keep_kernel(uint8_t* keep, int
 }
 
 // CTAs per SM: what the registers allow (forward 80 -> 3, backward 128 -> 2); an HBM-bound kernel wants the loads of all of them in flight
+// out = (y > 0) ? gy : 0 on bf16 vectors of 8: the ReLU backward of the feed-forward block's first layer (the mask comes
+// from the saved OUTPUT, module.py:50), one pass instead of torch's compare + cast + multiply
+__global__ void __launch_bounds__(256) relu_bwd_bf16_kernel(const uint4* __restrict__ gy, const uint4* __restrict__ y, uint4* __restrict__ out,
+                                                           size_t n8, const __nv_bfloat16* gy_tail, const __nv_bfloat16* y_tail,
+                                                           __nv_bfloat16* out_tail, int tail) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const uint4 g = gy[i], v = y[i];
+        uint4 o;
+        // y > 0 as torch evaluates it (false for zero, negative and NaN activations)
+        auto pick = [](uint32_t gw, uint32_t yw) {
+            const __nv_bfloat162 yy = *reinterpret_cast<const __nv_bfloat162*>(&yw);
+            const float2 f = __bfloat1622float2(yy);
+            return (f.x > 0.0f ? (gw & 0x0000ffffu) : 0u) | (f.y > 0.0f ? (gw & 0xffff0000u) : 0u);
+        };
+        o.x = pick(g.x, v.x); o.y = pick(g.y, v.y); o.z = pick(g.z, v.z); o.w = pick(g.w, v.w);
+        out[i] = o;
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < tail)
+        out_tail[threadIdx.x] = __bfloat162float(y_tail[threadIdx.x]) > 0.0f ? gy_tail[threadIdx.x] : __float2bfloat16_rn(0.0f);
+}
+
 static int ln_grid(int M, int per_sm) { return std::max(1, std::min((M + kLnWarps - 1) / kLnWarps, per_sm * num_sms())); }
 
 }  // namespace asr
@@ -331,6 +353,22 @@ extern "C" int asr_ln_dropout_keep(uint8_t* keep, int M, int D, float p_drop, ui
     const long long total = (long long)M * (D / 4);
     ln_dropout_keep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         keep, M, D, drop_threshold(p_drop), (uint32_t)seed, (uint32_t)(seed >> 32));
+    ASR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int asr_relu_bwd_bf16(const void* gy, const void* y, void* out, size_t n, void* stream) {
+    ASR_REQUIRE(gy && y && out, "asr_relu_bwd_bf16: null pointer");
+    ASR_REQUIRE(aligned16(gy) && aligned16(y) && aligned16(out), "asr_relu_bwd_bf16: pointers must be 16-byte aligned");
+    if (asr_device_ok() != 0) return 3;
+    if (n == 0) return 0;
+    const size_t n8 = n / 8;
+    const int tail = (int)(n - n8 * 8);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((n8 + 255) / 256, (size_t)num_sms() * 8));
+    const __nv_bfloat16 *g16 = static_cast<const __nv_bfloat16*>(gy), *y16 = static_cast<const __nv_bfloat16*>(y);
+    relu_bwd_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(gy), static_cast<const uint4*>(y), static_cast<uint4*>(out), n8, g16 + n8 * 8, y16 + n8 * 8,
+        static_cast<__nv_bfloat16*>(out) + n8 * 8, tail);
     ASR_LAUNCH_CHECK();
     return 0;
 }

@@ -363,7 +363,13 @@ class _LinearBf16Function(torch.autograd.Function):
         if gy2.dtype != torch.bfloat16:
             gy2 = gy2.to(torch.bfloat16)
         if ctx.relu:
-            gy2 = gy2 * (y > 0).to(gy2.dtype)
+            if gy2.is_contiguous() and y.is_contiguous() and gy2.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
+                masked = torch.empty_like(gy2)
+                with torch.cuda.device(gy2.device):
+                    check(_lib.lib().asr_relu_bwd_bf16(ptr(gy2), ptr(y), ptr(masked), gy2.numel(), stream_ptr()), "asr_relu_bwd_bf16")
+                gy2 = masked
+            else:
+                gy2 = gy2 * (y > 0).to(gy2.dtype)
         if gy2.stride(1) != 1 or gy2.stride(0) % 8 != 0 or gy2.data_ptr() % 16 != 0:
             gy2 = gy2.contiguous()
         gx = gw = gb = None

@@ -258,6 +258,9 @@ size_t asr_ln_bwd_workspace_bytes(int M, int D);
 int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
                const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream);
+/* out[i] = y[i] > 0 ? gy[i] : 0 (bf16, n elements, 16-byte aligned): the ReLU backward of module.py:50 from the saved
+ * output, what torch runs as compare + cast + multiply. */
+int asr_relu_bwd_bf16(const void* gy, const void* y, void* out, size_t n, void* stream);
 /* keep [M, D] u8 = 1 where that dropout keeps the element (tests, inspection) */
 int asr_ln_dropout_keep(uint8_t* keep, int M, int D, float p_drop, uint64_t seed, void* stream);
 int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb,

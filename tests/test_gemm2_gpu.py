@@ -338,3 +338,26 @@ def test_gemm_f32_ragged_rows_skip_padding_without_changing_valid_results():
         # split along K: the same products added in another order (up to eight partial sums), well inside the 2e-5 contract
         assert (got - ref).abs().max().item() <= 4e-6 * ref.abs().max().item()
     assert torch.equal(ops.gemm_f32(g, h, a_mn_major=True, b_mn_major=True, split_k=False, row_len=lens, group_rows=T), ref)
+
+
+@pytest.mark.parametrize("rows,N", [(1344, 2048), (7, 24), (33, 40)])
+def test_relu_backward_of_the_bf16_linear_is_torchs(rows, N):
+    """dX / dW of relu(x W^T + b) under bf16: the gradient is masked by the saved output (y > 0) in one kernel - the same
+    bits as torch's gy * (y > 0), zeros, negatives and NaN activations included."""
+    ops, lib = pkg("ops"), pkg("_lib")
+    y = _rand((rows, N), 1, dtype=torch.bfloat16)
+    y.view(-1)[::7] = 0.0
+    y.view(-1)[3::11] = float("nan")
+    gy = _rand((rows, N), 2, dtype=torch.bfloat16)
+    out = torch.empty_like(gy)
+    lib.check(lib.lib().asr_relu_bwd_bf16(lib.ptr(gy), lib.ptr(y), lib.ptr(out), gy.numel(), lib.stream_ptr()), "relu_bwd")
+    assert torch.equal(out, gy * (y > 0).to(gy.dtype))
+    x = _rand((rows, 64), 3, dtype=torch.bfloat16).requires_grad_(True)
+    w = _rand((N, 64), 4, 0.2).requires_grad_(True)
+    b = _rand((N,), 5).requires_grad_(True)
+    g = _rand((rows, N), 6, dtype=torch.bfloat16)
+    ops.linear_bf16_autograd(x, w, b, relu=True).backward(g)
+    xd, wd, bd = x.detach().double().requires_grad_(True), w.detach().bfloat16().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    F.relu(F.linear(xd, wd, bd)).backward(g.double())
+    rel = lambda got, want: (got.double() - want).abs().max().item() / want.abs().max().item()  # noqa: E731
+    assert rel(x.grad, xd.grad) <= 2e-2 and rel(w.grad, wd.grad) <= 2e-2 and rel(b.grad, bd.grad) <= 2e-2
