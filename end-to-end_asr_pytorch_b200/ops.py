@@ -360,9 +360,9 @@ class _LinearBf16Function(torch.autograd.Function):
         x2, w16, y = ctx.saved_tensors
         N, K = w16.shape
         gy2 = gy.reshape(-1, N)
-        if gy2.dtype != torch.bfloat16:
-            gy2 = gy2.to(torch.bfloat16)
         if ctx.relu:
+            if gy2.dtype != torch.bfloat16:
+                gy2 = gy2.to(torch.bfloat16)
             if gy2.is_contiguous() and y.is_contiguous() and gy2.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
                 masked = torch.empty_like(gy2)
                 with torch.cuda.device(gy2.device):
@@ -370,8 +370,15 @@ class _LinearBf16Function(torch.autograd.Function):
                 gy2 = masked
             else:
                 gy2 = gy2 * (y > 0).to(gy2.dtype)
-        if gy2.stride(1) != 1 or gy2.stride(0) % 8 != 0 or gy2.data_ptr() % 16 != 0:
-            gy2 = gy2.contiguous()
+        if N % 8 != 0:      # odd widths (the 4233-class vocabulary): rows padded to 16 bytes, the operand is the [:, :N] view
+            buf = torch.empty((gy2.shape[0], (N + 7) // 8 * 8), dtype=torch.bfloat16, device=gy2.device)
+            buf[:, :N] = gy2          # converts on the way
+            gy2 = buf[:, :N]
+        else:
+            if gy2.dtype != torch.bfloat16:
+                gy2 = gy2.to(torch.bfloat16)
+            if gy2.stride(1) != 1 or gy2.stride(0) % 8 != 0 or gy2.data_ptr() % 16 != 0:
+                gy2 = gy2.contiguous()
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = gemm_bf16(gy2, w16, b_mn_major=True).reshape(ctx.x_shape).to(ctx.x_dtype)
@@ -383,7 +390,10 @@ class _LinearBf16Function(torch.autograd.Function):
 
 
 def linear_bf16_ok(x, weight):
-    return weight.shape[1] % 8 == 0 and weight.shape[0] % 8 == 0 and x.numel() > 0
+    """Shapes the bf16 tensor-core linear layer takes: 16-byte rows for every operand of its three products; an odd output
+    width (the 4233-wide vocabulary projection) costs one padding copy of the incoming gradient, as in linear_f32_ok."""
+    N, K = weight.shape
+    return K % 8 == 0 and (N % 8 == 0 or N >= 64) and x.numel() > 0
 
 
 def linear_bf16_autograd(x, weight, bias=None, relu=False):

@@ -361,3 +361,28 @@ def test_relu_backward_of_the_bf16_linear_is_torchs(rows, N):
     F.relu(F.linear(xd, wd, bd)).backward(g.double())
     rel = lambda got, want: (got.double() - want).abs().max().item() / want.abs().max().item()  # noqa: E731
     assert rel(x.grad, xd.grad) <= 2e-2 and rel(w.grad, wd.grad) <= 2e-2 and rel(b.grad, bd.grad) <= 2e-2
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_bf16_linear_with_an_odd_output_width(relu):
+    """The 4233-class vocabulary projection under bf16 autocast (decoder.py:58 `tgt_word_prj`): forward through the
+    shared-memory epilogue (rows of 4233 bf16 cannot take 16-byte stores), backward on the gradient padded to 4240 columns."""
+    ops, lib = pkg("ops"), pkg("_lib")
+    rows, K, N = 1350, 512, 4233
+    x = _rand((rows, K), 1, dtype=torch.bfloat16).requires_grad_(True)
+    w = _rand((N, K), 2, K ** -0.5).requires_grad_(True)
+    b = _rand((N,), 3).requires_grad_(True)
+    g = _rand((rows, N), 4)                      # an fp32 gradient, as the loss hands it over
+    assert ops.linear_bf16_ok(x, w)
+    n0 = lib.launch_count()
+    y = ops.linear_bf16_autograd(x, w, b, relu=relu)
+    y.backward(g.to(y.dtype))
+    assert lib.launch_count() - n0 >= 4 and y.shape == (rows, N) and y.dtype == torch.bfloat16
+    xd, wd, bd = x.detach().double().requires_grad_(True), w.detach().bfloat16().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    yd = F.linear(xd, wd, bd)
+    if relu:      # the mask of the bf16 output: a pre-activation within a bf16 ulp of zero may round to the other side
+        yd = yd * (y.detach() > 0).double()
+    yd.backward(g.to(y.dtype).double())
+    rel = lambda got, want: (got.double() - want).abs().max().item() / want.abs().max().item()  # noqa: E731
+    assert rel(y, yd.detach()) <= 1e-2
+    assert rel(x.grad, xd.grad) <= 2e-2 and rel(w.grad, wd.grad) <= 2e-2 and rel(b.grad, bd.grad) <= 2e-2
