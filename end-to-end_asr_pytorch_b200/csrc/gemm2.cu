@@ -597,6 +597,167 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// bf16, persistent: one CTA walks the output tiles  blockIdx.x, + gridDim.x, ...  (n fastest: neighbours share A rows in L2).
+// At the model's shapes a tile is SHORT (K = 512: eight K steps, ~1.8 us of tensor work) and the one-tile kernel spends
+// most of a CTA's life on set-up and tear-down (TMEM allocation, barrier initialisation, the first loads' latency, the
+// epilogue with nothing behind it).  Here the roles keep running across tiles: the TMA ring never drains (the producer
+// is already loading tile i + 1 while tile i's products run), the accumulator is double-buffered in tensor memory
+// (2 x BN columns: the epilogue of tile i reads buffer i & 1 while the products of tile i + 1 fill the other one), and the
+// fixed costs are paid once per CTA.  Two CTAs per SM as before (2 x 256 TMEM columns, 2 x 96 KB).
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(8) Gemm2BarriersP {
+    uint64_t full[4];
+    uint64_t empty[4];
+    uint64_t acc_full[2];
+    uint64_t acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool RELU>
+__global__ void __launch_bounds__(192, 2)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                            const float* __restrict__ bias, void* __restrict__ c_, int M, int N, int K, int ldc, int tiles_n,
+                            int n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    using Cfg = G2B16Cfg<BN>;
+    using TA = G2Tile<A_MN, kG2M, 2>;
+    using TB = G2Tile<B_MN, BN, 2>;
+    constexpr int kStages = Cfg::kStages;
+    Gemm2BarriersP* bars = reinterpret_cast<Gemm2BarriersP*>(smem + kStages * Cfg::kStage);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nk = (K + TA::kBK - 1) / TA::kBK;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&bars->full[s], 1);
+            mbar_init(&bars->empty[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&bars->acc_full[b], 1);
+            mbar_init(&bars->acc_empty[b], 4);        // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(&bars->tmem_base, 2 * BN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = bars->tmem_base;
+    if (warp == 4) {
+        if (elect_one_sync()) {
+            tma_prefetch_desc(&tm_a);
+            tma_prefetch_desc(&tm_b);
+            int it = 0;                                   // K steps since the kernel started: the ring does not care about tiles
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * kG2M, n0 = (tile % tiles_n) * BN;
+                for (int k = 0; k < nk; ++k, ++it) {
+                    const int s = it % kStages;
+                    if (it >= kStages) mbar_wait(&bars->empty[s], ((it / kStages) - 1) & 1);
+                    unsigned char* st = smem + s * Cfg::kStage;
+                    mbar_arrive_expect_tx(&bars->full[s], Cfg::kATile + Cfg::kBTile);
+                    TA::load(st, &tm_a, k * TA::kBK, m0, &bars->full[s]);
+                    TB::load(st + Cfg::kATile, &tm_b, k * TA::kBK, n0, &bars->full[s]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (elect_one_sync()) {
+            constexpr uint32_t idesc = make_idesc(kG2M, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int it = 0, lt = 0;                           // lt: tiles of this CTA so far
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const int buf = lt & 1;
+                if (lt >= 2) {                            // the epilogue must have emptied this buffer (tile lt - 2)
+                    mbar_wait(&bars->acc_empty[buf], ((lt >> 1) - 1) & 1);
+                    tc_fence_after();
+                }
+                const uint32_t acc = tmem + (uint32_t)(buf * BN);
+                for (int k = 0; k < nk; ++k, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&bars->full[s], (it / kStages) & 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * Cfg::kStage);
+                    const uint32_t b_addr = a_addr + Cfg::kATile;
+#pragma unroll
+                    for (int kk = 0; kk < TA::kBK / TA::kUmmaK; ++kk)
+                        umma_bf16(acc, TA::desc(a_addr, kk), TB::desc(b_addr, kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+                    tc_commit(&bars->empty[s]);
+                }
+                tc_commit(&bars->acc_full[buf]);
+            }
+        }
+    } else {
+        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+        constexpr int kVecElems = OUT_F32 ? 4 : 8;                       // elements per 16-byte store
+        const bool vec = (ldc % kVecElems) == 0 && (reinterpret_cast<uintptr_t>(c_) & 15u) == 0;
+        const int n_store = vec ? min(ldc, (N + kVecElems - 1) / kVecElems * kVecElems) : N;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int buf = lt & 1;
+            const int m0 = (tile / tiles_n) * kG2M, n0 = (tile % tiles_n) * BN;
+            const int row = m0 + warp * 32 + lane;
+            mbar_wait(&bars->acc_full[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const size_t row_off = (size_t)min(row, M - 1) * ldc + n0;
+            float* dst_f = static_cast<float*>(c_) + row_off;
+            __nv_bfloat16* dst_h = static_cast<__nv_bfloat16*>(c_) + row_off;
+            const uint32_t acc = tmem + (uint32_t)(buf * BN) + lane_base;
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 32) {
+                if (n0 + cc >= n_store) break;
+                float v[32];
+                tmem_ld32(acc + cc, v);
+                if (cc + 32 >= BN || n0 + cc + 32 >= n_store) {       // last read of this buffer: hand it back before the stores
+                    tc_fence_before();
+                    mbar_arrive_warp(&bars->acc_empty[buf]);
+                }
+                if (row < M) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = n0 + cc + i;
+                        float x = v[i] + ((bias != nullptr && n < N) ? __ldg(bias + n) : 0.0f);
+                        if (RELU) x = fmaxf(x, 0.0f);
+                        v[i] = x;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += kVecElems) {
+                        const int n = n0 + cc + i;
+                        if (vec) {
+                            if (n < n_store) {
+                                if (OUT_F32) {
+                                    *reinterpret_cast<float4*>(dst_f + cc + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                } else {
+                                    *reinterpret_cast<uint4*>(dst_h + cc + i) =
+                                        make_uint4(cvt_bf16x2(v[i], v[i + 1]), cvt_bf16x2(v[i + 2], v[i + 3]),
+                                                   cvt_bf16x2(v[i + 4], v[i + 5]), cvt_bf16x2(v[i + 6], v[i + 7]));
+                                }
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kVecElems; ++u) {
+                                if (n + u < N) {
+                                    if (OUT_F32) dst_f[cc + i + u] = v[i + u];
+                                    else dst_h[cc + i + u] = __float2bfloat16_rn(v[i + u]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 2 * BN);
+    }
+}
+
 // partial fp32 tiles -> bf16 or fp32 output (+ bias, ReLU)
 __global__ void __launch_bounds__(256) splitk_reduce_out_kernel(const float* __restrict__ part, int splits, size_t split_stride, int M,
                                                                int N, int ldp, const float* __restrict__ bias, int relu, void* out_,
@@ -989,6 +1150,34 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     const size_t split_stride = (size_t)M * N;
     const bool f32 = split || out_f32 != 0;
     const bool rl = relu != 0 && !split;
+    // more tiles than the GPU holds CTAs (two per SM): the persistent kernel - option gemm_persistent: 1 = never, 2 = whenever unsplit
+    const long long tiles = (long long)p.grid.x * p.grid.y;
+    const int pers_opt = get_opt("gemm_persistent");
+    if (p.splits == 1 && p.bn == 128 && stage_out == 0 && pers_opt != 1 && (pers_opt == 2 || tiles > 2LL * num_sms()) && tiles < (1LL << 30)) {
+        const int tiles_n = (int)p.grid.x, n_tiles = (int)tiles;
+        const dim3 grid((unsigned)std::min<long long>(tiles, 2LL * num_sms()));
+#define ASR_G2P(AM, BM, F32, RL)                                                                                          \
+    do {                                                                                                                  \
+        static bool done = false;                                                                                         \
+        if (set_smem_once(gemm_bf16_persistent_kernel<128, AM, BM, F32, RL>, G2B16Cfg<128>::kSmem, done)) return 1;         \
+        gemm_bf16_persistent_kernel<128, AM, BM, F32, RL><<<grid, 192, G2B16Cfg<128>::kSmem, st>>>(ta, tb, bias, c, M, N, K, \
+                                                                                                  ldc, tiles_n, n_tiles);  \
+    } while (0)
+#define ASR_G2P_LAYOUT(F32, RL)                                  \
+    do {                                                         \
+        if (!a_mn_major && !b_mn_major) ASR_G2P(false, false, F32, RL); \
+        else if (!a_mn_major) ASR_G2P(false, true, F32, RL);     \
+        else if (!b_mn_major) ASR_G2P(true, false, F32, RL);     \
+        else ASR_G2P(true, true, F32, RL);                       \
+    } while (0)
+        if (out_f32) ASR_G2P_LAYOUT(true, false);
+        else if (relu) ASR_G2P_LAYOUT(false, true);
+        else ASR_G2P_LAYOUT(false, false);
+#undef ASR_G2P_LAYOUT
+#undef ASR_G2P
+        ASR_LAUNCH_CHECK();
+        return 0;
+    }
 #define ASR_G2H(BNV, AM, BM, F32, RL)                                                                                     \
     do {                                                                                                                  \
         static bool done = false;                                                                                         \

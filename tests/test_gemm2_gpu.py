@@ -386,3 +386,31 @@ def test_bf16_linear_with_an_odd_output_width(relu):
     rel = lambda got, want: (got.double() - want).abs().max().item() / want.abs().max().item()  # noqa: E731
     assert rel(y, yd.detach()) <= 1e-2
     assert rel(x.grad, xd.grad) <= 2e-2 and rel(w.grad, wd.grad) <= 2e-2 and rel(b.grad, bd.grad) <= 2e-2
+
+
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("M,N,K", [(15030, 512, 512), (40000, 128, 64), (1350, 2048, 1024), (264, 136, 200), (128, 128, 64)])
+def test_persistent_bf16_gemm_is_bitwise_the_one_tile_kernel(M, N, K, a_mn, b_mn):
+    """gemm_persistent = 2: one CTA walks several output tiles with the accumulator double-buffered in tensor memory - the
+    same products in the same order as one CTA per tile (gemm_persistent = 1)."""
+    ops, lib = pkg("ops"), pkg("_lib")
+    if (a_mn and M % 8) or (b_mn and N % 8) or (not (a_mn and b_mn) and K % 8):
+        pytest.skip("row stride not a multiple of 16 bytes for this layout")
+    a, b, ref = _operands(M, N, K, a_mn, b_mn, seed=M + N + K, dtype=torch.bfloat16)
+    bias = _rand((N,), 7)
+    got = {}
+    try:
+        lib.set_option("gemm_split_k", 1)
+        lib.set_option("gemm_variant", 1)          # 128-wide tiles on both routes
+        for mode in (1, 2):
+            lib.set_option("gemm_persistent", mode)
+            got[mode] = (ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, bias=bias, relu=True),
+                         ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, out_dtype=torch.float32),
+                         ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn))
+    finally:
+        lib.set_option("gemm_split_k", 0)
+        lib.set_option("gemm_variant", 0)
+        lib.set_option("gemm_persistent", 0)
+    for x, y in zip(got[1], got[2]):
+        assert torch.equal(x, y)
+    assert (got[2][1].double() - ref).abs().max().item() <= 5e-4 * ref.abs().max().item()

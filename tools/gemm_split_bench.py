@@ -32,6 +32,8 @@ shapes = [("fwd  x W^T", 1344, 512, 512, False, False), ("fwd  w_1", 1344, 2048,
           ("dX   g W", 1344, 512, 512, False, True), ("dX   w_1", 1344, 512, 2048, False, True), ("dX   w_2", 1344, 2048, 512, False, True),
           ("dW   g^T x", 512, 512, 1344, True, True), ("dW   w_1", 2048, 512, 1344, True, True), ("dW   w_2", 512, 2048, 1344, True, True),
           ("dec  x W^T", 896, 512, 512, False, False), ("dec  w_1", 896, 2048, 512, False, False), ("dec dW", 512, 512, 896, True, True),
+          ("enc  x W^T", 15030, 512, 512, False, False), ("enc  w_1", 15030, 2048, 512, False, False), ("enc  w_2", 15030, 512, 2048, False, False),
+          ("enc  dX", 15030, 512, 512, False, True), ("enc  dW", 512, 512, 15030, True, True), ("enc dW w_1", 2048, 512, 15030, True, True),
           ("fc 4233", 896, 4233, 512, False, False), ("fc dW", 4233, 512, 896, True, True), ("fc dX", 896, 512, 4233, False, True)]
 sweep = "--sweep" in sys.argv
 for dt in (torch.float32, torch.bfloat16):
@@ -69,4 +71,9 @@ for dt in (torch.float32, torch.bfloat16):
                 lib.set_option("gemm_split_mode", mode); lib.set_option("gemm_split_k", force); lib.set_option("gemm_stage_out", stage)
                 res.append("%s %6.2f" % (label, timed_graph(fn)))
             lib.set_option("gemm_split_mode", 0); lib.set_option("gemm_split_k", 0); lib.set_option("gemm_stage_out", 0)
+            if dt == torch.bfloat16:
+                for label, pers, var in (("one tile per CTA bn128", 1, 1), ("persistent bn128", 2, 1), ("one tile bn256", 1, 2), ("auto", 0, 0)):
+                    lib.set_option("gemm_persistent", pers); lib.set_option("gemm_variant", var); lib.set_option("gemm_split_k", 1 if pers else 0)
+                    res.append("%s %6.2f" % (label, timed_graph(fn)))
+                lib.set_option("gemm_persistent", 0); lib.set_option("gemm_variant", 0); lib.set_option("gemm_split_k", 0)
         print("%-8s %-11s M=%5d N=%5d K=%5d  us/call: %s" % (str(dt).split(".")[1], name, M, N, K, " | ".join(res)), flush=True)
