@@ -615,8 +615,15 @@ struct __align__(8) Gemm2BarriersP {
     uint32_t pad;
 };
 
+template <int BN>
+struct G2B16PCfg {      // 128-wide tiles: two CTAs per SM (2 x 256 TMEM columns, 2 x 96 KB); 256-wide: one CTA owns the SM (512 columns, 4 stages)
+    static constexpr int kStages = BN == 256 ? 4 : 3;
+    static constexpr int kCtasPerSm = BN == 256 ? 1 : 2;
+    static constexpr int kSmem = kStages * G2B16Cfg<BN>::kStage + 256;
+};
+
 template <int BN, bool A_MN, bool B_MN, bool OUT_F32, bool RELU>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(192, G2B16PCfg<BN>::kCtasPerSm)
 gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                             const float* __restrict__ bias, void* __restrict__ c_, int M, int N, int K, int ldc, int tiles_n,
                             int n_tiles) {
@@ -625,7 +632,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tm_a, const __gr
     using Cfg = G2B16Cfg<BN>;
     using TA = G2Tile<A_MN, kG2M, 2>;
     using TB = G2Tile<B_MN, BN, 2>;
-    constexpr int kStages = Cfg::kStages;
+    constexpr int kStages = G2B16PCfg<BN>::kStages;
     Gemm2BarriersP* bars = reinterpret_cast<Gemm2BarriersP*>(smem + kStages * Cfg::kStage);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nk = (K + TA::kBK - 1) / TA::kBK;
@@ -1150,29 +1157,38 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     const size_t split_stride = (size_t)M * N;
     const bool f32 = split || out_f32 != 0;
     const bool rl = relu != 0 && !split;
-    // more tiles than the GPU holds CTAs (two per SM): the persistent kernel - option gemm_persistent: 1 = never, 2 = whenever unsplit
+    // more tiles than the GPU holds CTAs: the persistent kernel - option gemm_persistent: 1 = never, 2 = whenever unsplit
     const long long tiles = (long long)p.grid.x * p.grid.y;
     const int pers_opt = get_opt("gemm_persistent");
-    if (p.splits == 1 && p.bn == 128 && stage_out == 0 && pers_opt != 1 && (pers_opt == 2 || tiles > 2LL * num_sms()) && tiles < (1LL << 30)) {
+    const int resident = (p.bn == 256 ? 1 : 2) * num_sms();
+    // (256-wide tiles, one CTA per SM: measured no better than one CTA per tile at two per SM - 18.4 vs 15.7 us at M = 15030,
+    // N = K = 512 - so only on request)
+    if (p.splits == 1 && stage_out == 0 && pers_opt != 1 && (pers_opt == 2 || (p.bn == 128 && tiles > resident)) && tiles < (1LL << 30)) {
         const int tiles_n = (int)p.grid.x, n_tiles = (int)tiles;
-        const dim3 grid((unsigned)std::min<long long>(tiles, 2LL * num_sms()));
-#define ASR_G2P(AM, BM, F32, RL)                                                                                          \
-    do {                                                                                                                  \
-        static bool done = false;                                                                                         \
-        if (set_smem_once(gemm_bf16_persistent_kernel<128, AM, BM, F32, RL>, G2B16Cfg<128>::kSmem, done)) return 1;         \
-        gemm_bf16_persistent_kernel<128, AM, BM, F32, RL><<<grid, 192, G2B16Cfg<128>::kSmem, st>>>(ta, tb, bias, c, M, N, K, \
-                                                                                                  ldc, tiles_n, n_tiles);  \
+        const dim3 grid((unsigned)std::min<long long>(tiles, resident));
+#define ASR_G2P(BNV, AM, BM, F32, RL)                                                                                       \
+    do {                                                                                                                    \
+        static bool done = false;                                                                                           \
+        if (set_smem_once(gemm_bf16_persistent_kernel<BNV, AM, BM, F32, RL>, G2B16PCfg<BNV>::kSmem, done)) return 1;          \
+        gemm_bf16_persistent_kernel<BNV, AM, BM, F32, RL><<<grid, 192, G2B16PCfg<BNV>::kSmem, st>>>(ta, tb, bias, c, M, N, K, \
+                                                                                                   ldc, tiles_n, n_tiles);  \
     } while (0)
-#define ASR_G2P_LAYOUT(F32, RL)                                  \
-    do {                                                         \
-        if (!a_mn_major && !b_mn_major) ASR_G2P(false, false, F32, RL); \
-        else if (!a_mn_major) ASR_G2P(false, true, F32, RL);     \
-        else if (!b_mn_major) ASR_G2P(true, false, F32, RL);     \
-        else ASR_G2P(true, true, F32, RL);                       \
+#define ASR_G2P_LAYOUT(BNV, F32, RL)                                  \
+    do {                                                              \
+        if (!a_mn_major && !b_mn_major) ASR_G2P(BNV, false, false, F32, RL); \
+        else if (!a_mn_major) ASR_G2P(BNV, false, true, F32, RL);     \
+        else if (!b_mn_major) ASR_G2P(BNV, true, false, F32, RL);     \
+        else ASR_G2P(BNV, true, true, F32, RL);                       \
     } while (0)
-        if (out_f32) ASR_G2P_LAYOUT(true, false);
-        else if (relu) ASR_G2P_LAYOUT(false, true);
-        else ASR_G2P_LAYOUT(false, false);
+        if (p.bn == 256) {
+            if (out_f32) ASR_G2P_LAYOUT(256, true, false);
+            else if (relu) ASR_G2P_LAYOUT(256, false, true);
+            else ASR_G2P_LAYOUT(256, false, false);
+        } else {
+            if (out_f32) ASR_G2P_LAYOUT(128, true, false);
+            else if (relu) ASR_G2P_LAYOUT(128, false, true);
+            else ASR_G2P_LAYOUT(128, false, false);
+        }
 #undef ASR_G2P_LAYOUT
 #undef ASR_G2P
         ASR_LAUNCH_CHECK();

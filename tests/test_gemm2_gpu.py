@@ -388,9 +388,10 @@ def test_bf16_linear_with_an_odd_output_width(relu):
     assert rel(x.grad, xd.grad) <= 2e-2 and rel(w.grad, wd.grad) <= 2e-2 and rel(b.grad, bd.grad) <= 2e-2
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
 @pytest.mark.parametrize("M,N,K", [(15030, 512, 512), (40000, 128, 64), (1350, 2048, 1024), (264, 136, 200), (128, 128, 64)])
-def test_persistent_bf16_gemm_is_bitwise_the_one_tile_kernel(M, N, K, a_mn, b_mn):
+def test_persistent_bf16_gemm_is_bitwise_the_one_tile_kernel(M, N, K, a_mn, b_mn, variant):
     """gemm_persistent = 2: one CTA walks several output tiles with the accumulator double-buffered in tensor memory - the
     same products in the same order as one CTA per tile (gemm_persistent = 1)."""
     ops, lib = pkg("ops"), pkg("_lib")
@@ -401,7 +402,7 @@ def test_persistent_bf16_gemm_is_bitwise_the_one_tile_kernel(M, N, K, a_mn, b_mn
     got = {}
     try:
         lib.set_option("gemm_split_k", 1)
-        lib.set_option("gemm_variant", 1)          # 128-wide tiles on both routes
+        lib.set_option("gemm_variant", variant)    # 128- or 256-wide tiles, the same on both routes
         for mode in (1, 2):
             lib.set_option("gemm_persistent", mode)
             got[mode] = (ops.gemm_bf16(a, b, a_mn_major=a_mn, b_mn_major=b_mn, bias=bias, relu=True),

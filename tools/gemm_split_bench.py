@@ -72,7 +72,7 @@ for dt in (torch.float32, torch.bfloat16):
                 res.append("%s %6.2f" % (label, timed_graph(fn)))
             lib.set_option("gemm_split_mode", 0); lib.set_option("gemm_split_k", 0); lib.set_option("gemm_stage_out", 0)
             if dt == torch.bfloat16:
-                for label, pers, var in (("one tile per CTA bn128", 1, 1), ("persistent bn128", 2, 1), ("one tile bn256", 1, 2), ("auto", 0, 0)):
+                for label, pers, var in (("one tile per CTA bn128", 1, 1), ("persistent bn128", 2, 1), ("one tile bn256", 1, 2), ("persistent bn256", 2, 2), ("auto", 0, 0)):
                     lib.set_option("gemm_persistent", pers); lib.set_option("gemm_variant", var); lib.set_option("gemm_split_k", 1 if pers else 0)
                     res.append("%s %6.2f" % (label, timed_graph(fn)))
                 lib.set_option("gemm_persistent", 0); lib.set_option("gemm_variant", 0); lib.set_option("gemm_split_k", 0)
