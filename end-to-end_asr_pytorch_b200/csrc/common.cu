@@ -19,7 +19,7 @@ static Opt g_opts[] = {
     {"cif_fwd_variant", {0}}, {"cif_fwd_width", {0}}, {"cif_fwd_stages", {0}}, {"cif_fwd_rows", {0}},
     {"mha_variant", {0}}, {"ctc_fuse_apply", {0}}, {"ctc_lattice_variant", {0}}, {"ctc_chunks", {0}},
     {"ctc_finish_per_slice", {0}}, {"mha_bwd_groups", {0}}, {"gemm_variant", {0}}, {"gemm_f32_bn", {0}},
-    {"gemm_split_k", {0}}, {"gemm_split_mode", {0}}, {"gemm_stage_out", {0}}, {"gemm_persistent", {0}}, {"ctc_lattice_split", {0}},
+    {"gemm_split_k", {0}}, {"gemm_split_mode", {0}}, {"gemm_stage_out", {0}}, {"gemm_persistent", {0}}, {"gemm_debug", {0}}, {"ctc_lattice_split", {0}},
 };
 static Opt* find_opt(const char* key) {
     for (Opt& o : g_opts)
