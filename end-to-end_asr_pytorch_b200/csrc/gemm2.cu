@@ -1176,8 +1176,27 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool can_split = ws != nullptr && ws_bytes >= asr_gemm_workspace_bytes(M, N, K);
     const bool cluster_mode = get_opt("gemm_split_mode") != 1;
-    const Plan p = make_plan(false, M, N, K, 64, get_opt("gemm_variant") == 1 ? 128 : (get_opt("gemm_variant") == 2 ? 256 : 0),
-                             get_opt("gemm_split_k"), can_split, cluster_mode);
+    const int force_bn = get_opt("gemm_variant") == 1 ? 128 : (get_opt("gemm_variant") == 2 ? 256 : 0);
+    Plan p = make_plan(false, M, N, K, 64, force_bn, get_opt("gemm_split_k"), can_split, cluster_mode);
+    // Unsplit products with more 128-wide tiles than two CTAs per SM hold (the encoder's M = 15030 rows) take the persistent
+    // kernel; its tile width by measurement (CUDA-graph replays, us, 128 / 256 wide): N = K = 512: 12.2 / 12.4, N = 2048:
+    // 35.9 / 33.7, K = 2048: 30.3 / 27.6 - 256 wide (one CTA per SM, four stages) once N or K reaches 1024 and there is a tile
+    // for every SM.
+    bool persistent = false;
+    {
+        const int pers_opt = get_opt("gemm_persistent");
+        const long long mt = (M + kG2M - 1) / kG2M;
+        const long long tiles128 = mt * ((N + 127) / 128), tiles256 = mt * ((N + 255) / 256);
+        if (p.splits == 1 && pers_opt != 1) {
+            if (pers_opt == 2) {
+                persistent = true;
+            } else if (tiles128 > 2LL * num_sms()) {
+                persistent = true;
+                if (force_bn == 0) p.bn = ((N >= 1024 || K >= 1024) && tiles256 >= num_sms()) ? 256 : 128;
+            }
+            if (persistent) p.grid = dim3((unsigned)((N + p.bn - 1) / p.bn), (unsigned)mt, 1u);
+        }
+    }
     CUtensorMap ta, tb;
     if (make_operand_map(&ta, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a, a_mn_major != 0, M, K, lda, kG2M) ||
         make_operand_map(&tb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, b, b_mn_major != 0, N, K, ldb, p.bn))
@@ -1195,13 +1214,10 @@ extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void*
     const size_t split_stride = (size_t)M * N;
     const bool f32 = split || out_f32 != 0;
     const bool rl = relu != 0 && !split;
-    // more tiles than the GPU holds CTAs: the persistent kernel - option gemm_persistent: 1 = never, 2 = whenever unsplit
+    // the persistent kernel (decided above; option gemm_persistent: 1 = never, 2 = whenever unsplit)
     const long long tiles = (long long)p.grid.x * p.grid.y;
-    const int pers_opt = get_opt("gemm_persistent");
     const int resident = (p.bn == 256 ? 1 : 2) * num_sms();
-    // (256-wide tiles, one CTA per SM: measured no better than one CTA per tile at two per SM - 18.4 vs 15.7 us at M = 15030,
-    // N = K = 512 - so only on request)
-    if (p.splits == 1 && stage_out == 0 && pers_opt != 1 && (pers_opt == 2 || (p.bn == 128 && tiles > resident)) && tiles < (1LL << 30)) {
+    if (persistent && stage_out == 0 && tiles < (1LL << 30)) {
         const int tiles_n = (int)p.grid.x, n_tiles = (int)tiles;
         const dim3 grid((unsigned)std::min<long long>(tiles, resident));
 #define ASR_G2P(BNV, AM, BM, F32, RL)                                                                                       \
