@@ -322,26 +322,44 @@ gemm_f32x3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 part_store32<BN>(smem, warp * 32 + lane, cc, v);
                 continue;
             }
-            if (row < M) {
+            if (vec) {
+                // A thread owns a ROW of the tile: stored directly, each of its 16-byte pieces lands in another 128-byte line
+                // (32 lines per instruction; at the 4233-wide projection the epilogue was ~30 % of a tile's time).  The warp
+                // parks its 32 x 32 chunk in the operand ring (free: every MMA has completed) and writes it back four full
+                // 128-byte rows per instruction.
+                if (add_bias) {
+                    if (n0 + cc + 32 <= N && (reinterpret_cast<uintptr_t>(bias) & 15u) == 0) {
 #pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const int n = n0 + cc + i;
-                    if (vec) {
-                        if (n < n_store) {
-                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            if (add_bias) {
-                                o.x += (n < N) ? __ldg(bias + n) : 0.0f;
-                                o.y += (n + 1 < N) ? __ldg(bias + n + 1) : 0.0f;
-                                o.z += (n + 2 < N) ? __ldg(bias + n + 2) : 0.0f;
-                                o.w += (n + 3 < N) ? __ldg(bias + n + 3) : 0.0f;
-                            }
-                            *reinterpret_cast<float4*>(dst + cc + i) = o;
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + cc + i));
+                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                         }
                     } else {
 #pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (n + u < N) dst[cc + i + u] = v[i + u] + (add_bias ? __ldg(bias + n + u) : 0.0f);
+                        for (int i = 0; i < 32; ++i) v[i] += (n0 + cc + i < N) ? __ldg(bias + n0 + cc + i) : 0.0f;
                     }
+                }
+                constexpr int kParkRow = 36;                       // floats per parked row: 32 + 4 of padding (conflict-free)
+                float* park = reinterpret_cast<float*>(smem) + warp * 32 * kParkRow;
+                float4* mine = reinterpret_cast<float4*>(park + lane * kParkRow);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mine[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                __syncwarp();
+                const int piece = lane & 7;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int r = (lane >> 3) + 4 * j;
+                    const int grow = m0 + warp * 32 + r, n = n0 + cc + piece * 4;
+                    if (grow < M && n < n_store)
+                        *reinterpret_cast<float4*>(c + (size_t)blockIdx.z * split_stride + (size_t)grow * ldc + n) =
+                            *reinterpret_cast<const float4*>(park + r * kParkRow + piece * 4);
+                }
+                __syncwarp();
+            } else if (row < M) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int n = n0 + cc + i;
+                    if (n < N) dst[cc + i] = v[i] + (add_bias ? __ldg(bias + n) : 0.0f);
                 }
             }
         }
