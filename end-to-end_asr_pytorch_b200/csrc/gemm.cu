@@ -299,202 +299,22 @@ linear_res_ln_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     }
 }
 
-// ---- y = x W^T + b in fp32 on the tensor cores: three TF32 products per tile ("3xTF32") ---------------------
-// x = hi + lo with hi = x with its 13 low mantissa bits cleared (exactly a TF32 number) and lo = x - hi (exact in
-// fp32); x W^T ~= hi_x hi_w + lo_x hi_w + hi_x lo_w, the dropped lo_x lo_w term is below 2^-22 of the product.
-// fp32 tiles [rows x 32] arrive by TMA (128-byte rows, 128-byte swizzle); the four epilogue warps split them in
-// place (hi) and into a twin buffer (lo) - an elementwise pass, so the swizzle does not matter - and hand the
-// stage to the MMA thread, which issues 12 tcgen05.mma kind::tf32 (M128 N128 K8) per 32-wide K step.
-constexpr int kF3K = 32;                         // fp32 K per stage (128-byte rows)
-constexpr int kF3ATile = 128 * kF3K * 4;         // 16 KB
-
-template <int BN>
-struct F3Cfg {
-    static constexpr int kStages = BN == 256 ? 2 : 3;
-    static constexpr int kBTile = BN * kF3K * 4;
-    static constexpr int kStage = 2 * kF3ATile + 2 * kBTile;      // [A | A lo | B | B lo]
-    static constexpr int kSmem = kStages * kStage + 256;
-};
-
-struct __align__(8) F3Barriers {
-    uint64_t full[3];
-    uint64_t split[3];
-    uint64_t empty[3];
-    uint64_t acc_full;
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
-linear_f32x3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ bias,
-                    float* __restrict__ y, int M, int N, int K) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    using Cfg = F3Cfg<BN>;
-    constexpr int kStages = Cfg::kStages;
-    F3Barriers* bars = reinterpret_cast<F3Barriers*>(smem + kStages * Cfg::kStage);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kGM;
-    const int nk = (K + kF3K - 1) / kF3K;        // a K tail is zero-filled by TMA
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->split[s], 4);
-            mbar_init(&bars->empty[s], 1);
-        }
-        mbar_init(&bars->acc_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 5) {
-        tmem_alloc(&bars->tmem_base, BN);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    if (warp == 4) {
-        if (elect_one_sync()) {
-            tma_prefetch_desc(&tm_x);
-            tma_prefetch_desc(&tm_w);
-            for (int k = 0; k < nk; ++k) {
-                const int s = k % kStages;
-                if (k >= kStages) mbar_wait(&bars->empty[s], ((k / kStages) - 1) & 1);
-                unsigned char* st = smem + s * Cfg::kStage;
-                mbar_arrive_expect_tx(&bars->full[s], kF3ATile + Cfg::kBTile);
-                tma_load_2d(st, &tm_x, k * kF3K, m0, &bars->full[s]);
-                tma_load_2d(st + 2 * kF3ATile, &tm_w, k * kF3K, n0, &bars->full[s]);
-            }
-        }
-    } else if (warp == 5) {
-        if (elect_one_sync()) {
-            constexpr uint32_t idesc = make_idesc_tf32(kGM, BN, 0, 0);
-            for (int k = 0; k < nk; ++k) {
-                const int s = k % kStages;
-                mbar_wait(&bars->split[s], (k / kStages) & 1);
-                tc_fence_after();
-                const uint32_t base = smem_u32(smem + s * Cfg::kStage);
-                const uint32_t a_hi = base, a_lo = base + kF3ATile, b_hi = base + 2 * kF3ATile, b_lo = b_hi + Cfg::kBTile;
-#pragma unroll
-                for (int kk = 0; kk < kF3K / 8; ++kk) {
-                    const uint32_t o = kk * 32;      // 8 fp32 = 32 bytes along K
-                    umma_tf32(tmem, smem_desc_sw128(a_lo + o, 16, 1024), smem_desc_sw128(b_hi + o, 16, 1024), idesc, (k > 0 || kk > 0) ? 1u : 0u);
-                    umma_tf32(tmem, smem_desc_sw128(a_hi + o, 16, 1024), smem_desc_sw128(b_lo + o, 16, 1024), idesc, 1u);
-                    umma_tf32(tmem, smem_desc_sw128(a_hi + o, 16, 1024), smem_desc_sw128(b_hi + o, 16, 1024), idesc, 1u);
-                }
-                tc_commit(&bars->empty[s]);
-            }
-            tc_commit(&bars->acc_full);
-        }
-    } else {
-        // splitter: lo = x - (x with the 13 low mantissa bits cleared).  The "hi" operand is the RAW fp32 tile: the
-        // tensor core reads the top 19 bits of each word (measured: clearing the low bits explicitly changes nothing
-        // in the result), so only the lo tiles are written
-        for (int k = 0; k < nk; ++k) {
-            const int s = k % kStages;
-            mbar_wait(&bars->full[s], (k / kStages) & 1);
-            unsigned char* st = smem + s * Cfg::kStage;
-            {
-                const uint4* hi = reinterpret_cast<const uint4*>(st);
-                float4* lo = reinterpret_cast<float4*>(st + kF3ATile);
-#pragma unroll
-                for (int j = 0; j < kF3ATile / 16 / 128; ++j) {
-                    const int idx = j * 128 + threadIdx.x;
-                    const uint4 v = hi[idx];
-                    lo[idx] = make_float4(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u), __uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u),
-                                          __uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u), __uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
-                }
-            }
-            {
-                const uint4* hi = reinterpret_cast<const uint4*>(st + 2 * kF3ATile);
-                float4* lo = reinterpret_cast<float4*>(st + 2 * kF3ATile + Cfg::kBTile);
-#pragma unroll
-                for (int j = 0; j < Cfg::kBTile / 16 / 128; ++j) {
-                    const int idx = j * 128 + threadIdx.x;
-                    const uint4 v = hi[idx];
-                    lo[idx] = make_float4(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u), __uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u),
-                                          __uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u), __uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
-                }
-            }
-            fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's operand fetch
-            mbar_arrive_warp(&bars->split[s]);
-        }
-        // epilogue: thread = row, fp32 out, 128 contiguous bytes per thread and chunk
-        const int row = m0 + warp * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        mbar_wait(&bars->acc_full, 0);
-        tc_fence_after();
-        float* dst = y + (size_t)min(row, M - 1) * N + n0;
-        const bool vec = (N & 3) == 0;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tmem_ld32(tmem + lane_base + c, v);
-            if (row < M) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (vec) {
-                        if (n0 + c + i < N) {      // N % 4 == 0: a float4 lies wholly inside or outside
-                            float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                            if (bias != nullptr) {
-                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i));
-                                o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-                            }
-                            *reinterpret_cast<float4*>(dst + c + i) = o;
-                        }
-                    } else {                       // odd widths (the 4233-class vocabulary projection): scalar stores
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int n = n0 + c + i + u;
-                            if (n < N) dst[c + i + u] = v[i + u] + (bias != nullptr ? __ldg(bias + n) : 0.0f);
-                        }
-                    }
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        tmem_dealloc(tmem, BN);
-    }
-}
 
 }  // namespace asr
 
 using namespace asr;
 
+extern "C" int asr_gemm_f32(const float* a, int a_mn_major, int lda, const float* b, int b_mn_major, int ldb, const float* bias, int M,
+                            int N, int K, float* c, int ldc, void* ws, size_t ws_bytes, void* stream);
+
+// y = x W^T + b in fp32 (three TF32 products per K step): the general GEMM of gemm2.cu with both operands K-major.  (Round 1
+// had its own kernel for this entry point; it lacked the row-contiguous epilogue and the split-K plan and is gone.)
 extern "C" int asr_linear_f32(const float* x, const float* w, const float* bias, int M, int N, int K, float* y, void* stream) {
     ASR_REQUIRE(x && w && y, "asr_linear_f32: null pointer");
     ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_linear_f32: bad shape M=%d N=%d K=%d", M, N, K);
     ASR_REQUIRE(K % 4 == 0, "asr_linear_f32: K=%d must be a multiple of 4 (16-byte rows for TMA)", K);
-    ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && (N % 4 != 0 || aligned16(bias)), "asr_linear_f32: pointers must be 16-byte aligned");
-    if (asr_device_ok() != 0) return 3;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // "gemm_f32_bn": 0 = auto (256-wide tiles when N >= 256), 128, 256
-    int bn = get_opt("gemm_f32_bn");
-    if (bn != 128 && bn != 256) {
-        // 256-wide tiles halve the operand traffic per flop, but small problems need the CTAs: one wave first
-        const long long ctas256 = (long long)((N + 255) / 256) * ((M + kGM - 1) / kGM);
-        bn = (N >= 256 && ctas256 >= num_sms()) ? 256 : 128;
-    }
-    CUtensorMap tx, tw;
-    if (make_tmap_2d(&tx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, (uint64_t)M, (uint64_t)K, (uint64_t)K * 4, 128, kF3K, CU_TENSOR_MAP_SWIZZLE_128B) ||
-        make_tmap_2d(&tw, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w, (uint64_t)N, (uint64_t)K, (uint64_t)K * 4, (uint32_t)bn, kF3K, CU_TENSOR_MAP_SWIZZLE_128B))
-        return 4;
-    const dim3 grid((N + bn - 1) / bn, (M + kGM - 1) / kGM);
-    ASR_REQUIRE(grid.y <= 65535, "asr_linear_f32: M=%d exceeds the grid limit", M);
-    if (bn == 256) {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_f32x3_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<256>::kSmem));
-        linear_f32x3_kernel<256><<<grid, 192, F3Cfg<256>::kSmem, st>>>(tx, tw, bias, y, M, N, K);
-    } else {
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_f32x3_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, F3Cfg<128>::kSmem));
-        linear_f32x3_kernel<128><<<grid, 192, F3Cfg<128>::kSmem, st>>>(tx, tw, bias, y, M, N, K);
-    }
-    ASR_LAUNCH_CHECK();
-    return 0;
+    ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y), "asr_linear_f32: pointers must be 16-byte aligned");
+    return asr_gemm_f32(x, 0, K, w, 0, K, bias, M, N, K, y, N, nullptr, 0, stream);
 }
 
 static int make_rowmajor_bf16_map(CUtensorMap* map, const void* base, int rows, int cols, int box_rows) {
