@@ -2,7 +2,8 @@
 //
 //   asr_linear_act_bf16                : y = act(x W^T + b)                       act = identity | ReLU
 //       w_1 of PositionwiseFeedForward (/root/reference/src/transformer/module.py:35-53: relu(w_1(x))) and the
-//       q / k / v projections of MultiheadAttention (attention.py:40-45).
+//       q / k / v projections of MultiheadAttention (attention.py:40-45).  Since round 2 this entry point (and
+//       asr_linear_f32) runs the general GEMMs of gemm2.cu; only the LayerNorm kernel lives here.
 //   asr_linear_residual_layernorm_bf16 : y = LayerNorm(x W^T + b + residual) * gamma + beta,  N = d_model = 512
 //       w_2 + residual + layer_norm of the feed-forward block (module.py:50-52) and fc + residual + layer_norm of
 //       the attention block (attention.py:59-60), dropout off (evaluation, or p = 0).
@@ -77,84 +78,6 @@ __device__ __forceinline__ void gemm_issue(uint32_t tmem, unsigned char* sA, uns
         tc_commit(&bars->empty[s]);       // the stage is free once these products have read it
     }
     tc_commit(&bars->acc_full);
-}
-
-// ---- y = act(x W^T + b) ------------------------------------------------------------------------------------
-template <int BN, int STAGES, bool RELU>
-__global__ void __launch_bounds__(192, 2)
-linear_act_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const float* __restrict__ bias,
-                  __nv_bfloat16* __restrict__ y, int M, int N, int K) {
-    extern __shared__ __align__(1024) unsigned char smem[];
-    if ((smem_u32(smem) & 1023u) != 0) __trap();
-    constexpr int kBTile = BN * kGK * 2;
-    unsigned char* sA = smem;
-    unsigned char* sB = sA + STAGES * kGATile;
-    GemmBarriers* bars = reinterpret_cast<GemmBarriers*>(sB + STAGES * kBTile);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * kGM;
-    const int nk = K / kGK;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&bars->full[s], 1);
-            mbar_init(&bars->empty[s], 1);
-        }
-        mbar_init(&bars->acc_full, 1);
-        fence_mbar_init();
-    }
-    if (warp == 5) {
-        tmem_alloc(&bars->tmem_base, BN);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = bars->tmem_base;
-    if (warp == 4) {
-        if (elect_one_sync()) gemm_produce<BN, STAGES>(&tm_x, &tm_w, sA, sB, bars, m0, n0, nk);
-    } else if (warp == 5) {
-        if (elect_one_sync()) gemm_issue<BN, STAGES>(tmem, sA, sB, bars, nk);
-    } else {
-        // epilogue: thread = row of the tile (TMEM lane), 32 columns at a time
-        const int row = m0 + warp * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-        mbar_wait(&bars->acc_full, 0);
-        tc_fence_after();
-        __nv_bfloat16* dst = y + (size_t)min(row, M - 1) * N + n0;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-            float v[32];
-            tmem_ld32(tmem + lane_base + c, v);
-            if (row < M) {
-#pragma unroll
-                for (int i = 0; i < 32; i += 8) {
-                    uint32_t w[4];
-                    float bv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (bias != nullptr) {      // the same 32 bytes for every lane: two broadcast loads
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c + i + 4));
-                        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-                        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        float a0 = v[i + 2 * u] + bv[2 * u], a1 = v[i + 2 * u + 1] + bv[2 * u + 1];
-                        if (RELU) {
-                            a0 = fmaxf(a0, 0.0f);
-                            a1 = fmaxf(a1, 0.0f);
-                        }
-                        w[u] = pack_bf16x2(a0, a1);
-                    }
-                    *reinterpret_cast<uint4*>(dst + c + i) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
-        }
-        tc_fence_before();
-    }
-    __syncthreads();
-    if (warp == 5) {
-        tc_fence_after();
-        tmem_dealloc(tmem, BN);
-    }
 }
 
 // ---- y = LayerNorm(x W^T + b + residual) * gamma + beta, N = 512: the whole row lives in tensor memory -----
@@ -322,39 +245,20 @@ static int make_rowmajor_bf16_map(CUtensorMap* map, const void* base, int rows, 
                         (uint32_t)box_rows, (uint32_t)kGK, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
+extern "C" int asr_gemm_bf16(const void* a, int a_mn_major, int lda, const void* b, int b_mn_major, int ldb, const float* bias,
+                             int relu, int M, int N, int K, void* c, int ldc, int out_f32, void* ws, size_t ws_bytes, void* stream);
+
+// y = act(x W^T + b) in bf16: the general GEMM of gemm2.cu with both operands K-major - at the feed-forward shapes its
+// persistent kernel (accumulator double-buffered in tensor memory, rows leaving through shared memory).  Round 1's own
+// kernel for this entry point (one CTA per tile, a thread storing its row 16 bytes at a time) ran at 705 TFLOP/s where the
+// persistent one reaches 1000 (M = 102400, N = 2048, K = 512), with the same output bits; it is gone.
 extern "C" int asr_linear_act_bf16(const void* x, const void* w, const float* bias, int M, int N, int K, int relu, void* y,
                                    void* stream) {
     ASR_REQUIRE(x && w && y, "asr_linear_act_bf16: null pointer");
     ASR_REQUIRE(M > 0 && N > 0 && K > 0, "asr_linear_act_bf16: bad shape M=%d N=%d K=%d", M, N, K);
     ASR_REQUIRE(N % 128 == 0 && K % kGK == 0, "asr_linear_act_bf16: N=%d must be a multiple of 128 and K=%d of 64", N, K);
     ASR_REQUIRE(aligned16(x) && aligned16(w) && aligned16(y) && aligned16(bias), "asr_linear_act_bf16: pointers must be 16-byte aligned");
-    if (asr_device_ok() != 0) return 3;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // "gemm_variant": 0 = auto, 1 = 128 x 128 tiles, 3-deep ring, two CTAs per SM; 2 = 128 x 256 tiles, 2-deep ring,
-    // two CTAs per SM; 3 = 128 x 256 tiles, 4-deep ring, one CTA per SM
-    int variant = get_opt("gemm_variant");
-    if (variant == 0) variant = 2;      // measured on the FFN shape (M = 102400): 611 / 691 / 548 TFLOP/s for 1 / 2 / 3; cuBLAS + eager bias/ReLU: 690
-    if (N % 256 != 0) variant = 1;
-#define ASR_LAUNCH_LINEAR(BN, STAGES, RL)                                                                                      \
-    do {                                                                                                                       \
-        constexpr int smem_bytes = STAGES * (kGATile + BN * kGK * 2) + 256;                                                    \
-        CUtensorMap tx, tw;                                                                                                    \
-        if (make_rowmajor_bf16_map(&tx, x, M, K, kGM) || make_rowmajor_bf16_map(&tw, w, N, K, BN)) return 4;                   \
-        const dim3 grid(N / BN, (M + kGM - 1) / kGM);                                                                          \
-        ASR_REQUIRE(grid.y <= 65535, "asr_linear_act_bf16: M=%d exceeds the grid limit", M);                                  \
-        ASR_CHECK_CUDA(cudaFuncSetAttribute(linear_act_kernel<BN, STAGES, RL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)); \
-        linear_act_kernel<BN, STAGES, RL><<<grid, 192, smem_bytes, st>>>(tx, tw, bias, static_cast<__nv_bfloat16*>(y), M, N, K); \
-    } while (0)
-    if (variant == 2) {
-        if (relu) ASR_LAUNCH_LINEAR(256, 2, true); else ASR_LAUNCH_LINEAR(256, 2, false);
-    } else if (variant == 3) {
-        if (relu) ASR_LAUNCH_LINEAR(256, 4, true); else ASR_LAUNCH_LINEAR(256, 4, false);
-    } else {
-        if (relu) ASR_LAUNCH_LINEAR(128, 3, true); else ASR_LAUNCH_LINEAR(128, 3, false);
-    }
-#undef ASR_LAUNCH_LINEAR
-    ASR_LAUNCH_CHECK();
-    return 0;
+    return asr_gemm_bf16(x, 0, K, w, 0, K, bias, relu, M, N, K, y, N, 0, nullptr, 0, stream);
 }
 
 extern "C" int asr_linear_residual_layernorm_bf16(const void* x, const void* w, const float* bias, const void* residual,
