@@ -625,6 +625,8 @@ def linear_microbench(device, iters=10):
     h = ops.linear_act(x, w1, b1, relu=True)
     b1h, b2h, gamh, beth = b1.bfloat16(), b2.bfloat16(), gam.bfloat16(), bet.bfloat16()
     rows = [("linear_bias_relu", lambda: ops.linear_act(x, w1, b1, relu=True), lambda: torch.relu(F.linear(x, w1, b1h))),
+            ("linear_residual_layernorm_one_kernel", lambda: ops.linear_residual_layernorm(h, w2, b2, x, gam, bet, one_kernel=True),
+             lambda: F.layer_norm(F.linear(h, w2, b2h) + x, (d,), gamh, beth)),
             ("linear_residual_layernorm", lambda: ops.linear_residual_layernorm(h, w2, b2, x, gam, bet),
              lambda: F.layer_norm(F.linear(h, w2, b2h) + x, (d,), gamh, beth))]
     res = {}
@@ -1178,11 +1180,12 @@ def main():
                             "note": "SURVEY 8(f3): dropout + residual + LayerNorm (+ non-pad mask) in one kernel each way; "
                                     "the backward figure includes the column sum of the per-CTA gamma / beta partial rows"})
         lin = linear_microbench(device)
-        for n in ("linear_bias_relu", "linear_residual_layernorm", "linear_f32_3xtf32"):
+        for n in ("linear_bias_relu", "linear_residual_layernorm", "linear_residual_layernorm_one_kernel", "linear_f32_3xtf32"):
             kernels.append({"kernel": n, "bound": "tensor", "ms": lin[n]["ms"], "TFLOPs": lin[n]["TFLOPs"],
                             "frac_of_bf16_peak": lin[n]["TFLOPs"] / peaks["bf16_tflops"], "shape": lin[n]["shape"],
                             "torch_cublas_plus_eager_TFLOPs": lin[n]["torch_TFLOPs"], "in_timed_step": False,
-                            "note": "SURVEY 8(f3): tcgen05 GEMM with the epilogue fused, next-row kernel"})
+                            "note": "SURVEY 8(f3): tcgen05 GEMM with the epilogue fused, next-row kernel (linear_residual_layernorm: persistent GEMM + "
+                                    "bf16 LayerNorm kernel; _one_kernel: the fp32 row normalised inside tensor memory)"})
         mha = attention_microbench(device, peaks)
         sweep = ctc_sweep(device, peaks)
     mha_roofline = None

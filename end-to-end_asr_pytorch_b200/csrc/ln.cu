@@ -233,6 +233,62 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const LnArgs a) {
     for (int i = threadIdx.x; i < 2 * D; i += kLnWarps * 32) dst[i] = (&red[0][0])[i];
 }
 
+// Evaluation flavour: out = LayerNorm(y + residual) * gamma + beta with bf16 y / residual / out (the model in bf16, no
+// gradient): three 2-byte passes over the rows, nothing saved.
+template <int NJ>
+__global__ void __launch_bounds__(kLnWarps * 32) ln_eval_bf16_kernel(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ residual,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    __nv_bfloat16* __restrict__ out, int M, float eps) {
+    constexpr int D = 128 * NJ;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float gam[NJ][4], bet[NJ][4];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+        gam[j][0] = g.x; gam[j][1] = g.y; gam[j][2] = g.z; gam[j][3] = g.w;
+        bet[j][0] = b.x; bet[j][1] = b.y; bet[j][2] = b.z; bet[j][3] = b.w;
+    }
+    for (int row = blockIdx.x * kLnWarps + warp; row < M; row += gridDim.x * kLnWarps) {
+        const size_t base = (size_t)row * D;
+        float v[NJ][4];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const float4 t = load4<__nv_bfloat16>(y + base + 4 * (lane + 32 * j));
+            v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+        }
+        if (residual != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const float4 r = load4<__nv_bfloat16>(residual + base + 4 * (lane + 32 * j));
+                v[j][0] += r.x; v[j][1] += r.y; v[j][2] += r.z; v[j][3] += r.w;
+            }
+        }
+        float s = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s += (v[j][0] + v[j][1]) + (v[j][2] + v[j][3]);
+        const float mean = warp_sum(s) * (1.0f / D);
+        float q = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float d = v[j][e] - mean;
+                q += d * d;
+            }
+        const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            float4 o;
+            o.x = (v[j][0] - mean) * rstd * gam[j][0] + bet[j][0];
+            o.y = (v[j][1] - mean) * rstd * gam[j][1] + bet[j][1];
+            o.z = (v[j][2] - mean) * rstd * gam[j][2] + bet[j][2];
+            o.w = (v[j][3] - mean) * rstd * gam[j][3] + bet[j][3];
+            store4(out + base + 4 * (lane + 32 * j), o);
+        }
+    }
+}
+
 // keep[row, col] = 1 where the dropout keeps the element (the bits the kernels regenerate): for tests
 __global__ void __launch_bounds__(256) ln_dropout_keep_kernel(uint8_t* keep, int M, int D, uint32_t thresh, uint32_t lo, uint32_t hi) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one float4 group each
@@ -369,6 +425,24 @@ extern "C" int asr_relu_bwd_bf16(const void* gy, const void* y, void* out, size_
     relu_bwd_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const uint4*>(gy), static_cast<const uint4*>(y), static_cast<uint4*>(out), n8, g16 + n8 * 8, y16 + n8 * 8,
         static_cast<__nv_bfloat16*>(out) + n8 * 8, tail);
+    ASR_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int asr_ln_eval_bf16(const void* y, const void* residual, const float* gamma, const float* beta, int M, int D, float eps,
+                                void* out, void* stream) {
+    if (ln_check("asr_ln_eval_bf16", M, D, 0.0f)) return 2;
+    ASR_REQUIRE(y && gamma && beta && out, "asr_ln_eval_bf16: null pointer");
+    ASR_REQUIRE(aligned16(y) && aligned16(residual) && aligned16(gamma) && aligned16(beta) && aligned16(out),
+                "asr_ln_eval_bf16: pointers must be 16-byte aligned");
+    if (asr_device_ok() != 0) return 3;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = ln_grid(M, 4);
+    const __nv_bfloat16 *y16 = static_cast<const __nv_bfloat16*>(y), *r16 = static_cast<const __nv_bfloat16*>(residual);
+    __nv_bfloat16* o16 = static_cast<__nv_bfloat16*>(out);
+    if (D == 256) ln_eval_bf16_kernel<2><<<grid, kLnWarps * 32, 0, st>>>(y16, r16, gamma, beta, o16, M, eps);
+    else if (D == 512) ln_eval_bf16_kernel<4><<<grid, kLnWarps * 32, 0, st>>>(y16, r16, gamma, beta, o16, M, eps);
+    else ln_eval_bf16_kernel<8><<<grid, kLnWarps * 32, 0, st>>>(y16, r16, gamma, beta, o16, M, eps);
     ASR_LAUNCH_CHECK();
     return 0;
 }

@@ -258,6 +258,11 @@ size_t asr_ln_bwd_workspace_bytes(int M, int D);
 int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
                const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream);
+/* Evaluation flavour of the above: out = LayerNorm(y + residual) * gamma + beta, y / residual (or NULL) / out bf16 [M, D],
+ * nothing saved.  With asr_gemm_bf16 in front it is the faster route for module.py:50-52 / attention.py:59-60 in evaluation
+ * (0.22 ms against 0.31 ms of the one-kernel asr_linear_residual_layernorm_bf16 at M = 102400, K = 2048). */
+int asr_ln_eval_bf16(const void* y, const void* residual, const float* gamma, const float* beta, int M, int D, float eps,
+                     void* out, void* stream);
 /* out[i] = y[i] > 0 ? gy[i] : 0 (bf16, n elements, 16-byte aligned): the ReLU backward of module.py:50 from the saved
  * output, what torch runs as compare + cast + multiply. */
 int asr_relu_bwd_bf16(const void* gy, const void* y, void* out, size_t n, void* stream);

@@ -49,15 +49,18 @@ def test_linear_act_leading_dims_and_errors():
         ops.linear_act(torch.zeros(4, 64, dtype=torch.bfloat16), w)          # CPU tensor: no fallback
 
 
+@pytest.mark.parametrize("one_kernel", [False, True])
 @pytest.mark.parametrize("M,K", [(128, 512), (300, 2048), (10688, 2048), (5, 64), (129, 512)])
-def test_linear_residual_layernorm(M, K):
+def test_linear_residual_layernorm(M, K, one_kernel):
+    """Both routes: the persistent GEMM + the bf16 LayerNorm kernel (default), and the single kernel that keeps the fp32 row
+    in tensor memory."""
     ops = pkg("ops")
     gen = torch.Generator().manual_seed(M + K)
     x, w, res = _rand((M, K), gen), _rand((512, K), gen, K ** -0.5), _rand((M, 512), gen)
     b = torch.randn(512, generator=gen).cuda()
     g = (1.0 + 0.1 * torch.randn(512, generator=gen)).cuda()
     be = (0.1 * torch.randn(512, generator=gen)).cuda()
-    y = ops.linear_residual_layernorm(x, w, b, res, g, be, eps=1e-5)
+    y = ops.linear_residual_layernorm(x, w, b, res, g, be, eps=1e-5, one_kernel=one_kernel)
     ref = torch.nn.functional.layer_norm(torch.nn.functional.linear(x.float(), w.float(), b) + res.float(), (512,), g, be, 1e-5)
     assert y.dtype == torch.bfloat16 and y.shape == (M, 512)
     _close(y, ref)
@@ -77,8 +80,12 @@ def test_feed_forward_block_matches_reference_module_math():
     hr = torch.relu(torch.nn.functional.linear(x.float(), w1.float(), b1)).to(torch.bfloat16).float()   # the bf16 hand-over
     ref = torch.nn.functional.layer_norm(torch.nn.functional.linear(hr, w2.float(), b2) + x.float(), (d,), g, be, 1e-5)
     _close(y, ref)
-    with pytest.raises(RuntimeError):
-        ops.linear_residual_layernorm(h, _rand((256, di), gen), None, _rand((B, T, 256), gen), torch.ones(256).cuda(), torch.zeros(256).cuda())
+    with pytest.raises(RuntimeError):      # the single kernel is built for d_model = 512
+        ops.linear_residual_layernorm(h, _rand((256, di), gen), None, _rand((B, T, 256), gen), torch.ones(256).cuda(), torch.zeros(256).cuda(),
+                                      one_kernel=True)
+    w3, r3 = _rand((256, di), gen, di ** -0.5), _rand((B, T, 256), gen)
+    y3 = ops.linear_residual_layernorm(h, w3, None, r3, torch.ones(256).cuda(), torch.zeros(256).cuda())      # the two-kernel route: 256 / 512 / 1024
+    _close(y3, torch.nn.functional.layer_norm(torch.nn.functional.linear(h.float(), w3.float()) + r3.float(), (256,), None, None, 1e-5))
 
 
 def test_modules_take_the_fused_path_in_bf16_eval():
@@ -94,7 +101,7 @@ def test_modules_take_the_fused_path_in_bf16_eval():
     with torch.no_grad():
         n0 = lib.launch_count()
         y_f = ffn(x)
-        assert lib.launch_count() - n0 == 2                     # two kernels for the whole block
+        assert lib.launch_count() - n0 == 3                     # relu(w_1 x + b); w_2 h + b; LayerNorm(. + x)
         o_f, _ = mha(x, x, x)
     y_u = ffn(x)                                                 # grad mode: the torch path
     o_u, _ = mha(x, x, x)
