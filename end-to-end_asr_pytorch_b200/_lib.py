@@ -45,9 +45,9 @@ SIGNATURES = {
     "asr_linear_f32": (_c_int, [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_colsum": (_c_int, [_vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp]),
     "asr_ln_dropout_keep_prob": (_c_float, [_c_float]),
-    "asr_ln_fwd": (_c_int, [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_float, _c_float, _c_uint64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "asr_ln_fwd": (_c_int, [_vp, _c_int, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_float, _c_float, _c_uint64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "asr_ln_bwd_workspace_bytes": (_c_size_t, [_c_int, _c_int]),
-    "asr_ln_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_float, _c_uint64, _vp, _vp, _vp, _c_int, _vp, _vp, _c_size_t, _vp]),
+    "asr_ln_bwd": (_c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _c_int, _c_int, _c_float, _c_uint64, _vp, _vp, _vp, _c_int, _vp, _vp, _c_size_t, _vp]),
     "asr_ln_eval_bf16": (_c_int, [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_float, _vp, _vp]),
     "asr_relu_bwd_bf16": (_c_int, [_vp, _vp, _vp, _c_size_t, _vp]),
     "asr_ln_dropout_keep": (_c_int, [_vp, _c_int, _c_int, _c_float, _c_uint64, _vp]),

@@ -42,6 +42,7 @@ struct LnArgs {
     float* out;               // forward: LayerNorm output;  backward: g_out (in)
     float* mean;              // [M]
     float* rstd;              // [M]
+    __nv_bfloat16* out_bf16;  // forward: a bf16 copy of out for the next layer's GEMM (or null);  backward: its gradient (in, or null)
     float* g_z;               // backward: [M, D] or null
     void* g_y;                // backward: [M, D] fp32 / bf16 or null
     float* partial;           // backward: [gridDim.x, 2, D]
@@ -154,6 +155,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const LnArgs a) {
             o.z = ((v[j][2] - mean) * rstd * gam[j][2] + bet[j][2]) * rs;
             o.w = ((v[j][3] - mean) * rstd * gam[j][3] + bet[j][3]) * rs;
             store4(a.out + base + 4 * (lane + 32 * j), o);
+            if (a.out_bf16 != nullptr) store4(a.out_bf16 + base + 4 * (lane + 32 * j), o);
         }
     }
 }
@@ -181,7 +183,12 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const LnArgs a) {
         float go[NJ][4], xh[NJ][4];
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
-            const float4 g = *reinterpret_cast<const float4*>(a.out + base + 4 * (lane + 32 * j));
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.out != nullptr) g = *reinterpret_cast<const float4*>(a.out + base + 4 * (lane + 32 * j));
+            if (a.out_bf16 != nullptr) {         // the gradient that arrived through the bf16 copy
+                const float4 h = load4<__nv_bfloat16>(a.out_bf16 + base + 4 * (lane + 32 * j));
+                g.x += h.x; g.y += h.y; g.z += h.z; g.w += h.w;
+            }
             const float4 z = *reinterpret_cast<const float4*>(a.z + base + 4 * (lane + 32 * j));
             go[j][0] = g.x * rs; go[j][1] = g.y * rs; go[j][2] = g.z * rs; go[j][3] = g.w * rs;
             xh[j][0] = (z.x - mean) * rstd; xh[j][1] = (z.y - mean) * rstd; xh[j][2] = (z.z - mean) * rstd; xh[j][3] = (z.w - mean) * rstd;
@@ -352,15 +359,15 @@ static int ln_check(const char* who, int M, int D, float p_drop) {
 extern "C" float asr_ln_dropout_keep_prob(float p_drop) { return (256.0f - (float)drop_threshold(p_drop)) / 256.0f; }
 
 extern "C" int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta,
-                          const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
-                          float* rstd, void* stream) {
+                          const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z,
+                          float* out, void* out_bf16, float* mean, float* rstd, void* stream) {
     if (ln_check("asr_ln_fwd", M, D, p_drop)) return 2;
     ASR_REQUIRE(y && gamma && beta && out && mean && rstd, "asr_ln_fwd: null pointer");
-    ASR_REQUIRE(aligned16(y) && aligned16(residual) && aligned16(gamma) && aligned16(beta) && aligned16(z) && aligned16(out),
+    ASR_REQUIRE(aligned16(y) && aligned16(residual) && aligned16(gamma) && aligned16(beta) && aligned16(z) && aligned16(out) && aligned16(out_bf16),
                 "asr_ln_fwd: pointers must be 16-byte aligned");
     if (asr_device_ok() != 0) return 3;
     LnArgs a = {};
-    a.y = y; a.residual = residual; a.gamma = gamma; a.beta = beta; a.row_scale = row_scale; a.z = z; a.out = out; a.mean = mean; a.rstd = rstd;
+    a.y = y; a.residual = residual; a.gamma = gamma; a.beta = beta; a.row_scale = row_scale; a.z = z; a.out = out; a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.mean = mean; a.rstd = rstd;
     a.seed_dev = seed_dev; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);
     a.thresh = drop_threshold(p_drop);
     a.inv_keep = 256.0f / (256.0f - (float)a.thresh);
@@ -377,11 +384,12 @@ extern "C" size_t asr_ln_bwd_workspace_bytes(int M, int D) {
     return (size_t)ln_grid(M, 2) * 2 * (size_t)D * sizeof(float);
 }
 
-extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
+extern "C" int asr_ln_bwd(const float* g_out, const void* g_out_bf16, const float* z, const float* mean, const float* rstd, const float* gamma,
                           const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                           float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream) {
     if (ln_check("asr_ln_bwd", M, D, p_drop)) return 2;
-    ASR_REQUIRE(g_out && z && mean && rstd && gamma && g_gamma_beta && ws, "asr_ln_bwd: null pointer");
+    ASR_REQUIRE((g_out || g_out_bf16) && z && mean && rstd && gamma && g_gamma_beta && ws, "asr_ln_bwd: null pointer");
+    ASR_REQUIRE(aligned16(g_out_bf16), "asr_ln_bwd: pointers must be 16-byte aligned");
     ASR_REQUIRE(g_z || g_y, "asr_ln_bwd: neither input gradient requested");
     ASR_REQUIRE(aligned16(g_out) && aligned16(z) && aligned16(gamma) && aligned16(g_z) && aligned16(g_y) && aligned16(ws),
                 "asr_ln_bwd: pointers must be 16-byte aligned");
@@ -389,6 +397,7 @@ extern "C" int asr_ln_bwd(const float* g_out, const float* z, const float* mean,
     if (asr_device_ok() != 0) return 3;
     LnArgs a = {};
     a.gamma = gamma; a.row_scale = row_scale; a.z = const_cast<float*>(z); a.out = const_cast<float*>(g_out);
+    a.out_bf16 = static_cast<__nv_bfloat16*>(const_cast<void*>(g_out_bf16));
     a.mean = const_cast<float*>(mean); a.rstd = const_cast<float*>(rstd);
     a.g_z = g_z; a.g_y = g_y; a.partial = static_cast<float*>(ws);
     a.seed_dev = seed_dev; a.seed_lo = (uint32_t)seed; a.seed_hi = (uint32_t)(seed >> 32);

@@ -823,7 +823,7 @@ LN_WIDTHS = (256, 512, 1024)
 
 class _ResidualLayerNormFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, residual, weight, bias, eps, p_drop, seed, seed_dev, row_scale):
+    def forward(ctx, y, residual, weight, bias, eps, p_drop, seed, seed_dev, row_scale, want_bf16):
         D = y.shape[-1]
         y2 = y.reshape(-1, D)
         r2 = residual.reshape(-1, D) if residual is not None else None
@@ -834,24 +834,35 @@ class _ResidualLayerNormFunction(torch.autograd.Function):
         rstd = torch.empty((M,), dtype=torch.float32, device=dev)
         z_is_y = r2 is None and p_drop == 0.0 and y2.dtype == torch.float32
         z = None if z_is_y else torch.empty((M, D), dtype=torch.float32, device=dev)
+        out16 = torch.empty((M, D), dtype=torch.bfloat16, device=dev) if want_bf16 else None
         w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
         with torch.cuda.device(dev):
             check(_lib.lib().asr_ln_fwd(ptr(y2), int(y2.dtype == torch.bfloat16), ptr(r2), ptr(w32), ptr(b32), ptr(row_scale), M, D,
                                         ctypes.c_float(eps), ctypes.c_float(p_drop), ctypes.c_uint64(seed), ptr(seed_dev),
-                                        ptr(z), ptr(out), ptr(mean), ptr(rstd), stream_ptr()), "asr_ln_fwd")
+                                        ptr(z), ptr(out), ptr(out16), ptr(mean), ptr(rstd), stream_ptr()), "asr_ln_fwd")
         ctx.save_for_backward(y2 if z_is_y else z, mean, rstd, w32, seed_dev, row_scale)
         ctx.meta = (y.shape, y.dtype, residual is not None, p_drop, seed)
-        return out.reshape(y.shape)
+        if want_bf16:
+            return out.reshape(y.shape), out16.reshape(y.shape)
+        return out.reshape(y.shape), None
 
     @staticmethod
-    def backward(ctx, g_out):
+    def backward(ctx, g_out, g_out16):
         z, mean, rstd, w32, seed_dev, row_scale = ctx.saved_tensors
         shape, y_dtype, has_res, p_drop, seed = ctx.meta
         M, D = z.shape
         dev = z.device
-        g2 = g_out.reshape(M, D)
-        if g2.dtype != torch.float32 or not g2.is_contiguous():
-            g2 = g2.float().contiguous()
+        g2 = g16 = None
+        if g_out is not None:
+            g2 = g_out.reshape(M, D)
+            if g2.dtype != torch.float32 or not g2.is_contiguous():
+                g2 = g2.float().contiguous()
+        if g_out16 is not None:          # what came back through the bf16 copy (the next layer's dX): added inside the kernel
+            g16 = g_out16.reshape(M, D)
+            if g16.dtype != torch.bfloat16 or not g16.is_contiguous():
+                g16 = g16.to(torch.bfloat16).contiguous()
+        if g2 is None and g16 is None:
+            g2 = torch.zeros((M, D), dtype=torch.float32, device=dev)
         need_y, need_r = ctx.needs_input_grad[0], has_res and ctx.needs_input_grad[1]
         same = p_drop == 0.0 and y_dtype == torch.float32          # dy is dz: one tensor serves both
         g_z = torch.empty((M, D), dtype=torch.float32, device=dev) if (need_r or (need_y and same)) else None
@@ -862,12 +873,12 @@ class _ResidualLayerNormFunction(torch.autograd.Function):
         ws_bytes = _lib.lib().asr_ln_bwd_workspace_bytes(M, D)
         ws = torch.empty((ws_bytes // 4 + 4,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            check(_lib.lib().asr_ln_bwd(ptr(g2), ptr(z), ptr(mean), ptr(rstd), ptr(w32), ptr(row_scale), M, D, ctypes.c_float(p_drop),
+            check(_lib.lib().asr_ln_bwd(ptr(g2), ptr(g16), ptr(z), ptr(mean), ptr(rstd), ptr(w32), ptr(row_scale), M, D, ctypes.c_float(p_drop),
                                         ctypes.c_uint64(seed), ptr(seed_dev), ptr(g_z), ptr(g_y), int(y_dtype == torch.bfloat16),
                                         ptr(g_wb), ptr(ws), ws_bytes, stream_ptr()), "asr_ln_bwd")
         gy = (g_z if same else g_y).reshape(shape) if need_y else None
         gr = g_z.reshape(shape) if need_r else None
-        return gy, gr, g_wb[0], g_wb[1], None, None, None, None, None
+        return gy, gr, g_wb[0], g_wb[1], None, None, None, None, None, None
 
 
 def residual_layer_norm_available(y, residual, weight):
@@ -877,13 +888,27 @@ def residual_layer_norm_available(y, residual, weight):
             and (residual is None or (residual.dtype == torch.float32 and residual.shape == y.shape and residual.is_contiguous())))
 
 
-def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, training=True, seed=None, row_scale=None):
+BF16_COPY_ATTR = "_asr_bf16"          # a tensor attribute: the bf16 copy residual_layer_norm wrote next to its fp32 output
+
+
+def bf16_copy_of(x):
+    """The bf16 copy that residual_layer_norm(bf16_copy=True) attached to its output (same values, same autograd node), or
+    None.  The bf16 linear layers of the shell take it instead of converting x again."""
+    c = getattr(x, BF16_COPY_ATTR, None)
+    return c if (c is not None and c.shape == x.shape and c.device == x.device) else None
+
+
+def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, training=True, seed=None, row_scale=None,
+                        bf16_copy=False):
     """LayerNorm(dropout(y) + residual) [* row_scale] -> fp32, with autograd (module.py:50-52, attention.py:59-60, encoder.py:49 of the
     reference): one kernel forward, one (+ a column sum of per-CTA partials) backward.  y [..., D] fp32 or bf16, residual
     [..., D] fp32 or None, weight / bias [D] (gamma / beta).  The dropout mask comes from the library's Philox stream
     (`seed`: default drawn from torch's CPU generator; inside `device_dropout_seed(...)` read from the device) and is
     regenerated in the backward - see ln_dropout_keep.  row_scale: one constant factor per row ([...] or [..., 1], e.g. the
-    non-pad mask the layers multiply every sub-layer output with - encoder.py:76-80, decoder.py:628-634)."""
+    non-pad mask the layers multiply every sub-layer output with - encoder.py:76-80, decoder.py:628-634).
+    bf16_copy=True (bf16 autocast): the kernel also writes the output in bf16 and attaches it to the returned fp32 tensor
+    (`bf16_copy_of`): the next bf16 GEMM reads it instead of running a conversion kernel, and the gradient that comes back
+    through it is added to the fp32 one inside the backward kernel."""
     _require_cuda("y", y)
     if not residual_layer_norm_available(y, residual, weight):
         raise ValueError("residual_layer_norm: unsupported operands (width %d, dtypes %s / %s)" % (
@@ -901,7 +926,11 @@ def residual_layer_norm(y, residual, weight, bias, eps=1e-5, dropout_p=0.0, trai
         if row_scale.numel() != y.numel() // y.shape[-1]:
             raise ValueError("residual_layer_norm: row_scale must hold one factor per row")
         row_scale = row_scale.detach().reshape(-1).to(device=y.device, dtype=torch.float32).contiguous()
-    return _ResidualLayerNormFunction.apply(y, residual, weight, bias, float(eps), p, int(seed or 0), seed_dev, row_scale)
+    out, out16 = _ResidualLayerNormFunction.apply(y, residual, weight, bias, float(eps), p, int(seed or 0), seed_dev, row_scale,
+                                                  bool(bf16_copy))
+    if out16 is not None:
+        setattr(out, BF16_COPY_ATTR, out16)
+    return out
 
 
 def ln_dropout_keep(M, D, dropout_p, seed, device="cuda"):

@@ -83,9 +83,11 @@ class MultiheadAttention(nn.Module):
             if bf16_autocast and q.dtype == torch.float32:
                 # autocast casts every Linear input on its own: a self-attention layer would convert the same activations
                 # three times (and its backward convert three gradients back); once is enough
-                qi = q.to(torch.bfloat16)
-                ki = qi if k is q else k.to(torch.bfloat16)
-                vi = ki if v is k else (qi if v is q else v.to(torch.bfloat16))
+                from ..ops import bf16_copy_of
+                cast = lambda t: (lambda c: t.to(torch.bfloat16) if c is None else c)(bf16_copy_of(t))  # noqa: E731
+                qi = cast(q)
+                ki = qi if k is q else cast(k)
+                vi = ki if v is k else (qi if v is q else cast(v))
             qh = self.w_qs(qi).view(sz_b, len_q, n_head, d_k)
             kh = self.w_ks(ki).view(sz_b, len_k, n_head, d_k)
             vh = self.w_vs(vi).view(sz_b, len_k, n_head, d_v)

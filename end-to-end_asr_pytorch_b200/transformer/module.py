@@ -33,7 +33,10 @@ def dropout_residual_layer_norm(layer_norm, dropout, y, residual=None, row_scale
         rc = residual.contiguous() if residual is not None else None
         if len(layer_norm.normalized_shape) == 1 and ops.residual_layer_norm_available(yc, rc, layer_norm.weight):
             p = dropout.p if (dropout is not None and dropout.training) else 0.0
-            return ops.residual_layer_norm(yc, rc, layer_norm.weight, layer_norm.bias, layer_norm.eps, p, True, row_scale=row_scale)
+            # under bf16 autocast the consumer is a bf16 GEMM: let the kernel write the bf16 copy it will read
+            shadow = torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.bfloat16
+            return ops.residual_layer_norm(yc, rc, layer_norm.weight, layer_norm.bias, layer_norm.eps, p, True, row_scale=row_scale,
+                                           bf16_copy=shadow)
     if dropout is not None:
         y = dropout(y)
     out = layer_norm(y + residual if residual is not None else y)
@@ -50,7 +53,8 @@ class Linear(nn.Linear):
             if torch.is_autocast_enabled("cuda"):
                 if (USE_TENSOR_CORE_BF16 and torch.get_autocast_dtype("cuda") == torch.bfloat16
                         and ops.linear_bf16_ok(x, self.weight)):
-                    return ops.linear_bf16_autograd(x, self.weight, self.bias, relu=relu)
+                    xb = ops.bf16_copy_of(x)          # written by the LayerNorm kernel that produced x
+                    return ops.linear_bf16_autograd(x if xb is None else xb, self.weight, self.bias, relu=relu)
             elif USE_TENSOR_CORE_FP32 and x.dtype == torch.float32 and ops.linear_f32_ok(x, self.weight):
                 y = ops.linear_f32_autograd(x, self.weight, self.bias)
                 return F.relu(y) if relu else y

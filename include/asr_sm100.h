@@ -249,13 +249,15 @@ int asr_colsum(const void* x, int is_bf16, int M, int N, int ld, float* out, voi
  * seed is *seed_dev + seed, read on the device - CUDA-graph replays).
  * asr_ln_bwd: g_out, z, mean, rstd, gamma as saved -> g_z [M, D] fp32 (the residual's gradient; NULL: not wanted), g_y [M, D]
  * fp32 / bf16 (= g_z * keep / p_keep; NULL: not wanted), g_gamma_beta [2, D].  ws: asr_ln_bwd_workspace_bytes(M, D) bytes.
+ * out_bf16 (asr_ln_fwd, optional): a bf16 copy of out for the next layer's bf16 GEMM (saves autocast's conversion kernel);
+ * g_out_bf16 (asr_ln_bwd, optional): the gradient that came back through that copy, added to g_out (either may be NULL).
  * Fixed summation orders throughout (deterministic). */
 float asr_ln_dropout_keep_prob(float p_drop);
 int asr_ln_fwd(const void* y, int y_bf16, const float* residual, const float* gamma, const float* beta,
-               const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out, float* mean,
-               float* rstd, void* stream);
+               const float* row_scale, int M, int D, float eps, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* z, float* out,
+               void* out_bf16, float* mean, float* rstd, void* stream);
 size_t asr_ln_bwd_workspace_bytes(int M, int D);
-int asr_ln_bwd(const float* g_out, const float* z, const float* mean, const float* rstd, const float* gamma,
+int asr_ln_bwd(const float* g_out, const void* g_out_bf16, const float* z, const float* mean, const float* rstd, const float* gamma,
                const float* row_scale, int M, int D, float p_drop, uint64_t seed, const uint64_t* seed_dev, float* g_z, void* g_y, int y_bf16,
                float* g_gamma_beta, void* ws, size_t ws_bytes, void* stream);
 /* Evaluation flavour of the above: out = LayerNorm(y + residual) * gamma + beta, y / residual (or NULL) / out bf16 [M, D],

@@ -113,6 +113,34 @@ def test_row_scale_is_the_non_pad_mask_of_the_layers(dtype):
         ops.residual_layer_norm(y, res, w, b, row_scale=mask[:, :3])
 
 
+def test_bf16_copy_and_the_gradient_that_comes_back_through_it():
+    """bf16_copy=True: the kernel also writes its output in bf16 (what the next bf16 GEMM reads instead of a conversion
+    kernel); the gradient arriving through that copy is added to the fp32 one inside the backward kernel."""
+    ops = pkg("ops")
+    M, D = 1350, 512
+    y = _rand((M, D), 1, 2.0, torch.bfloat16).requires_grad_(True)
+    res = _rand((M, D), 2).requires_grad_(True)
+    w = (_rand((D,), 3, 0.2) + 1.0).requires_grad_(True)
+    b = _rand((D,), 4, 0.1).requires_grad_(True)
+    g32, g16 = _rand((M, D), 5), _rand((M, D), 6, dtype=torch.bfloat16)
+    out = ops.residual_layer_norm(y, res, w, b, 1e-5, bf16_copy=True)
+    out16 = ops.bf16_copy_of(out)
+    assert out16 is not None and out16.dtype == torch.bfloat16 and torch.equal(out16, out.detach().bfloat16())
+    assert ops.bf16_copy_of(out * 1.0) is None                     # any op makes a new tensor: no stale copies
+    torch.autograd.backward([out, out16], [g32, g16])
+    ref, (yd, rd, wd, bd) = _reference(y, res, w, b, 1e-5)
+    ref.backward(g32.double() + g16.double())
+    assert _rel(y.grad, yd.grad) <= 6e-3 and _rel(res.grad, rd.grad) <= 1e-5
+    assert _rel(w.grad, wd.grad) <= 1e-5 and _rel(b.grad, bd.grad) <= 1e-5
+    # only the copy is used downstream (a layer whose fp32 output feeds nothing else)
+    y2 = y.detach().clone().requires_grad_(True)
+    out = ops.residual_layer_norm(y2, res.detach(), w.detach(), b.detach(), 1e-5, bf16_copy=True)
+    ops.bf16_copy_of(out).backward(g16)
+    ref, (yd, _, _, _) = _reference(y, res, w, b, 1e-5)
+    ref.backward(g16.double())
+    assert _rel(y2.grad, yd.grad) <= 6e-3
+
+
 def test_device_side_seed_matches_the_host_seed_it_stands_for():
     """Inside device_dropout_seed(...) the kernels read *seed_dev + the call's constant (CUDA-graph replays): the same mask
     as passing that sum from the host, and a new one after advance()."""
