@@ -26,7 +26,10 @@ USE_FUSED_LAYER_NORM = True
 def dropout_residual_layer_norm(layer_norm, dropout, y, residual=None, row_scale=None):
     """layer_norm(dropout(y) + residual) [* row_scale] - module.py:50-52 / attention.py:59-60 / encoder.py:49 of the reference,
     and the non-pad mask the layers apply next (encoder.py:76-80) - with the parameters of the given nn.LayerNorm /
-    nn.Dropout (dropout may be None).  row_scale: [..., 1] or None."""
+    nn.Dropout (dropout may be None).  row_scale: [..., 1] or None.
+    Under bf16 autocast the returned fp32 tensor carries a bf16 copy written by the same kernel (ops.bf16_copy_of), which
+    the shell's Linear / MultiheadAttention read instead of converting it again.  The copy belongs to that tensor OBJECT: any
+    out-of-place op yields a tensor without it; do not modify the returned tensor in place before handing it to a Linear."""
     if USE_FUSED_LAYER_NORM and y.is_cuda and torch.is_grad_enabled() and layer_norm.elementwise_affine:
         from .. import ops
         yc = y.contiguous()
